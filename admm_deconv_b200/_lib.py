@@ -1,0 +1,126 @@
+"""ctypes binding of the C ABI in ``include/admmtv.h`` (libadmmtv.so, built by nvcc for sm_100a).
+
+There is no CPU fallback: if the shared library is missing, ``load()`` raises, and every compute
+entry point of the library itself fails without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadmmtv.so")
+
+ACT = {"identity": 0, "relu": 1, "relu6": 2, "relu1": 3}
+FLAG_NO_CLAMP = 1
+FLAG_NOGRAD_REPEAT = 2
+
+# every symbol include/admmtv.h declares (tests check the .so exports exactly these)
+SYMBOLS = (
+    "admmtv_version",
+    "admmtv_strerror",
+    "admmtv_check",
+    "admmtv_workspace_bytes",
+    "admmtv_forward",
+    "admmtv_backward",
+    "admmtv_forward_host",
+    "admmtv_forward_launches",
+    "admmtv_backward_launches",
+)
+
+
+class Desc(C.Structure):
+    """struct admmtv_desc (include/admmtv.h)."""
+
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("P", C.c_int32), ("B", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32),
+        ("iters", C.c_int32), ("iso", C.c_int32), ("activation", C.c_int32), ("has_bias", C.c_int32),
+        ("device", C.c_int32), ("flags", C.c_int32),
+        ("creg", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
+class AdmmTvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{msg} (code {code})")
+        self.code = code
+
+
+class AdmmTvLib:
+    """Thin typed wrapper; pointers are plain integers (device or host addresses)."""
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise OSError(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback for the ADMM-TV path."
+            )
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        vp, sz = C.c_void_p, C.c_size_t
+        L.admmtv_version.restype = C.c_int
+        L.admmtv_strerror.restype = C.c_char_p
+        L.admmtv_strerror.argtypes = [C.c_int]
+        L.admmtv_check.argtypes = [C.POINTER(Desc)]
+        L.admmtv_workspace_bytes.argtypes = [C.POINTER(Desc), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+        L.admmtv_forward.argtypes = [C.POINTER(Desc)] + [vp] * 9
+        L.admmtv_backward.argtypes = [C.POINTER(Desc)] + [vp] * 14
+        L.admmtv_forward_host.argtypes = [C.POINTER(Desc)] + [vp] * 6
+        L.admmtv_forward_launches.argtypes = [C.POINTER(Desc), C.c_int]
+        L.admmtv_backward_launches.argtypes = [C.POINTER(Desc)]
+        for name in SYMBOLS:
+            getattr(L, name)  # AttributeError if a declared symbol is not exported
+
+    def strerror(self, code: int) -> str:
+        return self.lib.admmtv_strerror(code).decode()
+
+    def _raise(self, code: int):
+        if code != 0:
+            raise AdmmTvError(code, self.strerror(code))
+
+    def version(self) -> int:
+        return self.lib.admmtv_version()
+
+    def check(self, d: Desc) -> int:
+        return self.lib.admmtv_check(C.byref(d))
+
+    def workspace_bytes(self, d: Desc):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._raise(self.lib.admmtv_workspace_bytes(C.byref(d), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def forward(self, d: Desc, y, h, lam, rho, bias, x_out, ws, ckpt, stream=0):
+        self._raise(self.lib.admmtv_forward(C.byref(d), y, h, lam, rho, bias, x_out, ws, ckpt, stream))
+
+    def backward(self, d: Desc, xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar, biasbar, ws, stream=0):
+        self._raise(self.lib.admmtv_backward(C.byref(d), xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar,
+                                             biasbar, ws, stream))
+
+    def forward_host(self, d: Desc, y, h, lam, rho, bias, x_out):
+        self._raise(self.lib.admmtv_forward_host(C.byref(d), y, h, lam, rho, bias, x_out))
+
+    def forward_launches(self, d: Desc, with_ckpt: bool) -> int:
+        return self.lib.admmtv_forward_launches(C.byref(d), int(with_ckpt))
+
+    def backward_launches(self, d: Desc) -> int:
+        return self.lib.admmtv_backward_launches(C.byref(d))
+
+
+_LIB: Optional[AdmmTvLib] = None
+
+
+def load() -> AdmmTvLib:
+    """The product library.  Raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        _LIB = AdmmTvLib(LIB_PATH)
+    return _LIB
+
+
+def make_desc(M, N, P, B, kh, kw, iters, iso=False, activation="identity", has_bias=False, device=0, flags=0,
+              creg=0.0) -> Desc:
+    act = ACT[activation] if isinstance(activation, str) else int(activation)
+    return Desc(M, N, P, B, kh, kw, iters, int(bool(iso)), act, int(bool(has_bias)), device, flags, float(creg), 0)

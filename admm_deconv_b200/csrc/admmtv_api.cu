@@ -1,0 +1,378 @@
+// admmtv_api.cu -- the C ABI of include/admmtv.h: argument checking, workspace carving and the
+// launch sequences.  No torch types, no global mutable state; every table lives in the caller's
+// workspace.  Compiled by nvcc for sm_100a (product) -- see compat.cuh for the test-only
+// emulation build.
+#include "../../include/admmtv.h"
+#include "kernels.cuh"
+
+#include <stdio.h>
+
+namespace admmtv {
+
+static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
+static inline int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+struct Geom {
+  int M, N, P, B, S, Q, LM, LN, K, kh, kw, nh;
+  size_t plane;  // N*M
+  size_t pk;     // Q*N*M  (pair-packed complex elements)
+};
+static Geom geom(const admmtv_desc* d) {
+  Geom g;
+  g.M = d->M; g.N = d->N; g.P = d->P; g.B = d->B;
+  g.S = d->P * d->B;
+  g.Q = (g.S + 1) / 2;
+  g.LM = ilog2(d->M); g.LN = ilog2(d->N);
+  g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
+  g.plane = (size_t)d->N * d->M;
+  g.pk = g.plane * g.Q;
+  return g;
+}
+
+// ---- workspace / checkpoint carving ---------------------------------------------------------
+struct Carver {
+  unsigned char* base;
+  size_t off;
+  explicit Carver(void* p) : base(reinterpret_cast<unsigned char*>(p)), off(0) {}
+  template <class T>
+  T* take(size_t count) {
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align256(count * sizeof(T));
+    return r;
+  }
+};
+
+struct FwdWs {
+  float2 *twM, *twN;
+  double2* T;
+  float* ctab;
+  float2* ktab;
+  float* mask;
+  float2 *bpk, *specA, *specB, *v0, *v1;
+  size_t bytes;
+};
+static FwdWs carve_fwd(const Geom& g, void* ws) {
+  Carver c(ws);
+  FwdWs w;
+  w.twM = c.take<float2>(g.M);
+  w.twN = c.take<float2>(g.N);
+  w.T = c.take<double2>((size_t)g.M * (g.kw > 0 ? g.kw : 1));
+  w.ctab = c.take<float>(g.plane);
+  w.ktab = c.take<float2>(g.plane);
+  w.mask = c.take<float>(g.nh + 2);
+  w.bpk = c.take<float2>(g.pk);
+  w.specA = c.take<float2>(g.pk);
+  w.specB = c.take<float2>(g.pk);
+  w.v0 = c.take<float2>(2 * g.pk);
+  w.v1 = c.take<float2>(2 * g.pk);
+  w.bytes = c.off;
+  return w;
+}
+
+struct Ckpt {
+  float* mask;   // [2 + nh]
+  float2* vck;   // (K-1) slots of [Q][2][N][M]   : v_1 .. v_{K-1}
+  float2* zck;   // K slots of [Q][N][M]          : F r_1 .. F r_K
+  size_t bytes;
+};
+static Ckpt carve_ckpt(const Geom& g, void* p) {
+  Carver c(p);
+  Ckpt k;
+  k.mask = c.take<float>(g.nh + 2);
+  k.vck = c.take<float2>((size_t)(g.K > 1 ? g.K - 1 : 0) * 2 * g.pk);
+  k.zck = c.take<float2>((size_t)g.K * g.pk);
+  k.bytes = c.off;
+  return k;
+}
+
+#include "bwd_ws.inc"
+
+// ---- launch helpers -------------------------------------------------------------------------
+#define ADMMTV_CHECK_LAUNCH()                      \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+#define ADMMTV_SWITCH_LOG2(val, NAME, ...)                                   \
+  switch (val) {                                                             \
+    case 5: { constexpr int NAME = 5; __VA_ARGS__ } break;                   \
+    case 6: { constexpr int NAME = 6; __VA_ARGS__ } break;                   \
+    case 7: { constexpr int NAME = 7; __VA_ARGS__ } break;                   \
+    case 8: { constexpr int NAME = 8; __VA_ARGS__ } break;                   \
+    case 9: { constexpr int NAME = 9; __VA_ARGS__ } break;                   \
+    case 10: { constexpr int NAME = 10; __VA_ARGS__ } break;                 \
+    case 11: { constexpr int NAME = 11; __VA_ARGS__ } break;                 \
+    case 12: { constexpr int NAME = 12; __VA_ARGS__ } break;                 \
+    default: return ADMMTV_ERR_UNSUPPORTED;                                  \
+  }
+
+template <class K, class Args>
+static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, const Args& a) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  ADMMTV_LAUNCH(kern, grid, dim3(nt), smem, st, a);
+  ADMMTV_CHECK_LAUNCH();
+  return 0;
+}
+
+static dim3 dim1_grid(const Geom& g, int CO) { return dim3((unsigned)((g.N + CO - 1) / CO), (unsigned)g.Q); }
+
+static int run_pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {
+  ADMMTV_SWITCH_LOG2(g.LM, LM, {
+    using Cfg = Dim1Cfg<LM>;
+    const dim3 grid = dim1_grid(g, Cfg::CO);
+    if (mode == 0) return launch_k(k_pack_fft1<LM, 0>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    if (mode == 1) return launch_k(k_pack_fft1<LM, 1>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    return launch_k(k_pack_fft1<LM, 2>, grid, Cfg::NT, Cfg::SMEM, st, a);
+  })
+  return 0;
+}
+static int run_dim1_out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st) {
+  ADMMTV_SWITCH_LOG2(g.LM, LM, {
+    using Cfg = Dim1Cfg<LM>;
+    const dim3 grid = dim1_grid(g, Cfg::CO);
+    if (mode == 0) return launch_k(k_dim1_out<LM, 0>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    return launch_k(k_dim1_out<LM, 1>, grid, Cfg::NT, Cfg::SMEM, st, a);
+  })
+  return 0;
+}
+static int run_dim1_fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st) {
+  ADMMTV_SWITCH_LOG2(g.LM, LM, {
+    using Cfg = Dim1Cfg<LM>;
+    const dim3 grid = dim1_grid(g, Cfg::CO);
+    if (has_vprev) return launch_k(k_dim1_fwd<LM, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    return launch_k(k_dim1_fwd<LM, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+  })
+  return 0;
+}
+// variant ids for k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)
+enum Dim2Variant { D2_C = 0, D2_C_SAVE, D2_KCONJ /*conj(K)/MN as stored*/, D2_C_ACCG, D2_FWDONLY, D2_K_ACCP /*K = conj of stored*/ };
+static int run_dim2(const Geom& g, Dim2Variant v, const Dim2Args& a, cudaStream_t st) {
+  ADMMTV_SWITCH_LOG2(g.LN, LN, {
+    using Cfg = Dim2Cfg<LN>;
+    const dim3 grid((unsigned)(g.M / Cfg::TR), (unsigned)g.Q);
+    switch (v) {
+      case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+      case D2_C_SAVE: return launch_k(k_dim2<LN, 0, true, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+      case D2_KCONJ: return launch_k(k_dim2<LN, 1, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+      case D2_C_ACCG: return launch_k(k_dim2<LN, 0, false, 1, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+      case D2_FWDONLY: return launch_k(k_dim2<LN, 0, false, 0, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
+      case D2_K_ACCP: return launch_k(k_dim2<LN, 2, false, 2, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    }
+  })
+  return 0;
+}
+
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Enqueue the setup kernels shared by forward and backward.
+static int run_setup(const Geom& g, const float* h, const float* rho, float2* twM, float2* twN, double2* T,
+                     float* ctab, float2* ktab, float2* sig, cudaStream_t st) {
+  {
+    const int n = g.M > g.N ? g.M : g.N;
+    ADMMTV_LAUNCH(k_setup_twiddles, dim3((n + 255) / 256), dim3(256), 0, st, twM, g.M, twN, g.N);
+    ADMMTV_CHECK_LAUNCH();
+  }
+  if (g.kh > 0) {
+    const int n = g.M * g.kw;
+    ADMMTV_LAUNCH(k_setup_psf_dim1, dim3((n + 127) / 128), dim3(128), 0, st, h, g.kh, g.kw, g.M, T);
+    ADMMTV_CHECK_LAUNCH();
+  }
+  {
+    const size_t n = g.plane;
+    ADMMTV_LAUNCH(k_setup_tables, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, (const double2*)T, g.kh, g.kw, g.M,
+                  g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig);
+    ADMMTV_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace admmtv
+
+using namespace admmtv;
+
+extern "C" {
+
+int admmtv_version(void) { return ADMMTV_VERSION; }
+
+const char* admmtv_strerror(int code) {
+  switch (code) {
+    case ADMMTV_OK: return "ok";
+    case ADMMTV_ERR_NULL: return "admmtv: null pointer argument";
+    case ADMMTV_ERR_SHAPE: return "admmtv: invalid shape (dims must be positive, PSF no larger than the image)";
+    case ADMMTV_ERR_UNSUPPORTED: return "admmtv: unsupported size (M and N must be powers of two in 32..4096)";
+    case ADMMTV_ERR_ITERS: return "admmtv: iters must be >= 1";
+    case ADMMTV_ERR_ENUM: return "admmtv: invalid enum / flag value in descriptor";
+    case ADMMTV_ERR_ALIGN: return "admmtv: workspace and checkpoint must be 256-byte aligned";
+    case ADMMTV_ERR_NO_DEVICE: return "admmtv: CUDA device unavailable (there is no CPU fallback)";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "admmtv: unknown error";
+}
+
+int admmtv_check(const admmtv_desc* d) {
+  if (!d) return ADMMTV_ERR_NULL;
+  if (d->M <= 0 || d->N <= 0 || d->P <= 0 || d->B <= 0) return ADMMTV_ERR_SHAPE;
+  if (d->kh < 0 || d->kw < 0 || ((d->kh == 0) != (d->kw == 0))) return ADMMTV_ERR_SHAPE;
+  if (d->kh > d->M || d->kw > d->N) return ADMMTV_ERR_SHAPE;
+  if ((d->M & (d->M - 1)) || (d->N & (d->N - 1)) || d->M < 32 || d->N < 32 || d->M > 4096 || d->N > 4096)
+    return ADMMTV_ERR_UNSUPPORTED;
+  if (d->iters < 1) return ADMMTV_ERR_ITERS;
+  if (d->iso != 0 && d->iso != 1) return ADMMTV_ERR_ENUM;
+  if (d->activation < 0 || d->activation > 3) return ADMMTV_ERR_ENUM;
+  if (d->has_bias != 0 && d->has_bias != 1) return ADMMTV_ERR_ENUM;
+  if (d->flags & ~(ADMMTV_FLAG_NO_CLAMP | ADMMTV_FLAG_NOGRAD_REPEAT)) return ADMMTV_ERR_ENUM;
+  if (d->reserved != 0) return ADMMTV_ERR_ENUM;
+  if (d->device < 0) return ADMMTV_ERR_ENUM;
+  return ADMMTV_OK;
+}
+
+int admmtv_workspace_bytes(const admmtv_desc* d, size_t* fwd_bytes, size_t* ckpt_bytes, size_t* bwd_bytes) {
+  int rc = admmtv_check(d);
+  if (rc) return rc;
+  const Geom g = geom(d);
+  if (fwd_bytes) *fwd_bytes = carve_fwd(g, nullptr).bytes;
+  if (ckpt_bytes) *ckpt_bytes = carve_ckpt(g, nullptr).bytes;
+  if (bwd_bytes) *bwd_bytes = carve_bwd(g, nullptr).bytes;
+  return ADMMTV_OK;
+}
+
+int admmtv_forward_launches(const admmtv_desc* d, int with_ckpt) {
+  (void)with_ckpt;
+  if (admmtv_check(d)) return 0;
+  int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 3 : 0);
+  n += d->iters + (d->iters - 1) + 1;
+  return n;
+}
+
+int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
+                   float* x_out, void* workspace, void* ckpt, void* stream) {
+  int rc = admmtv_check(d);
+  if (rc) return rc;
+  if (!y || !lambda || !rho || !x_out || !workspace) return ADMMTV_ERR_NULL;
+  if (d->kh > 0 && !h) return ADMMTV_ERR_NULL;
+  if (d->has_bias && !bias) return ADMMTV_ERR_NULL;
+  if (d->iso) return ADMMTV_ERR_UNSUPPORTED;  // TODO(iso)
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ADMMTV_ERR_ALIGN;
+  DeviceGuard guard(d->device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Geom g = geom(d);
+  const FwdWs w = carve_fwd(g, workspace);
+  Ckpt ck;
+  if (ckpt) ck = carve_ckpt(g, ckpt);
+
+  // deconv_admm.jl:216-219 (persisted clamp) + gradient masks for the pullback
+  ADMMTV_LAUNCH(k_clamp_params, dim3(1), dim3(128), 0, st, lambda, rho, h, g.nh, d->creg,
+                (d->flags & ADMMTV_FLAG_NO_CLAMP) ? 0 : 1, ckpt ? ck.mask : w.mask);
+  ADMMTV_CHECK_LAUNCH();
+  if ((rc = run_setup(g, h, rho, w.twM, w.twN, w.T, w.ctab, w.ktab, nullptr, st))) return rc;
+
+  // y -> pair-pack -> dim-1 spectrum (ops.jl:101 + first FFT pass)
+  {
+    PackArgs a{};
+    a.src = y; a.spec = w.specA; a.twM = w.twM; a.N = g.N; a.S = g.S;
+    a.packed_out = g.kh > 0 ? nullptr : w.bpk;  // empty h: b = y (ops.jl:149-151)
+    if ((rc = run_pack_fft1(g, 0, a, st))) return rc;
+  }
+  if (g.kh > 0) {
+    // b = H^T y = F^-1( conj(K) F y )  (ops.jl:163,168; hoisted out of the loop)
+    Dim2Args a{};
+    a.in = w.specA; a.out = w.specB; a.ktab = w.ktab; a.twN = w.twN; a.M = g.M;
+    if ((rc = run_dim2(g, D2_KCONJ, a, st))) return rc;
+    OutArgs o{};
+    o.spec = w.specB; o.packed = w.bpk; o.twM = w.twM; o.N = g.N; o.S = g.S;
+    if ((rc = run_dim1_out(g, 0, o, st))) return rc;
+    PackArgs p{};
+    p.src_packed = w.bpk; p.spec = w.specA; p.twM = w.twM; p.N = g.N; p.S = g.S;
+    if ((rc = run_pack_fft1(g, 2, p, st))) return rc;
+  }
+
+  // the unrolled iterations (ops.jl:166-174)
+  for (int k = 1; k <= g.K; ++k) {
+    Dim2Args a{};
+    a.in = w.specA; a.out = w.specB; a.ctab = w.ctab; a.twN = w.twN; a.M = g.M;
+    if (ckpt) a.zsave = ck.zck + (size_t)(k - 1) * g.pk;
+    if ((rc = run_dim2(g, ckpt ? D2_C_SAVE : D2_C, a, st))) return rc;
+    if (k < g.K) {
+      Dim1FwdArgs f{};
+      f.spec_in = w.specB; f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM;
+      f.lambda = lambda; f.rho = rho; f.N = g.N;
+      if (ckpt) {
+        f.vprev = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
+        f.vnew = ck.vck + (size_t)(k - 1) * 2 * g.pk;
+      } else {
+        f.vprev = (k & 1) ? w.v1 : w.v0;
+        f.vnew = (k & 1) ? w.v0 : w.v1;
+      }
+      if ((rc = run_dim1_fwd(g, k > 1, f, st))) return rc;
+    }
+  }
+  // x_K -> user layout, + bias, activation (ops.jl:175, deconv_admm.jl:222-224)
+  {
+    OutArgs o{};
+    o.spec = w.specB; o.planes = x_out; o.bias = d->has_bias ? bias : nullptr; o.twM = w.twM;
+    o.N = g.N; o.S = g.S; o.act = d->activation;
+    if ((rc = run_dim1_out(g, 1, o, st))) return rc;
+  }
+  return ADMMTV_OK;
+}
+
+#include "bwd_api.inc"
+
+int admmtv_forward_host(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
+                        float* x_out) {
+  int rc = admmtv_check(d);
+  if (rc) return rc;
+  if (!y || !lambda || !rho || !x_out) return ADMMTV_ERR_NULL;
+  DeviceGuard guard(d->device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  const Geom g = geom(d);
+  size_t fwd = 0;
+  admmtv_workspace_bytes(d, &fwd, nullptr, nullptr);
+  const size_t nimg = g.plane * g.S * sizeof(float);
+  unsigned char* dev = nullptr;
+  const size_t o_y = 0, o_x = align256(nimg), o_h = o_x + align256(nimg), o_l = o_h + align256((g.nh + 1) * sizeof(float)),
+               o_r = o_l + 256, o_b = o_r + 256, o_ws = o_b + 256;
+  cudaError_t e = cudaMalloc((void**)&dev, o_ws + fwd);
+  if (e != cudaSuccess) return (int)e;
+  cudaStream_t st = 0;
+  cudaMemcpyAsync(dev + o_y, y, nimg, cudaMemcpyHostToDevice, st);
+  if (g.nh) cudaMemcpyAsync(dev + o_h, h, g.nh * sizeof(float), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dev + o_l, lambda, sizeof(float), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dev + o_r, rho, sizeof(float), cudaMemcpyHostToDevice, st);
+  if (d->has_bias && bias) cudaMemcpyAsync(dev + o_b, bias, sizeof(float), cudaMemcpyHostToDevice, st);
+  rc = admmtv_forward(d, (const float*)(dev + o_y), g.nh ? (float*)(dev + o_h) : nullptr, (float*)(dev + o_l),
+                      (float*)(dev + o_r), d->has_bias ? (const float*)(dev + o_b) : nullptr, (float*)(dev + o_x),
+                      dev + o_ws, nullptr, st);
+  if (rc == 0) {
+    cudaMemcpyAsync(x_out, dev + o_x, nimg, cudaMemcpyDeviceToHost, st);
+    if (g.nh) cudaMemcpyAsync(h, dev + o_h, g.nh * sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(lambda, dev + o_l, sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(rho, dev + o_r, sizeof(float), cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  cudaFree(dev);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// fft_core.cuh -- register-resident radix-{2,4,8,16} butterflies, the per-length stage plans
+// and the digit-reversed position<->frequency maps shared by every kernel of the path.
+//
+// Design (DESIGN.md "FFT"): a length-L complex transform is a sequence of NS in-place passes.
+// The forward transform is decimation-in-frequency (natural order in, digit-reversed order
+// out); the inverse is the exact transpose, decimation-in-time (digit-reversed in, natural
+// out).  Because every spectral operation of the ADMM iteration is a pointwise multiply by a
+// table, the tables are stored in digit-reversed order and no reordering pass ever runs.
+//
+// Replaces: CUFFT.rfft / CUFFT.irfft at /root/reference/src/ops/ops.jl:108,117-118,168 and
+// FFTW rfft/irfft at :26,35-36,86.
+#pragma once
+
+#include "compat.cuh"
+
+namespace admmtv {
+
+// ------------------------------------------------------------------------------------------
+// stage plans (DIF order: stage 0 works on the whole line, the last stage on R-long blocks)
+// ------------------------------------------------------------------------------------------
+ADMMTV_HD constexpr int plan_radix(int L, int s) {
+  switch (L) {
+    case 32:   return s == 0 ? 8 : (s == 1 ? 4 : 1);
+    case 64:   return s < 2 ? 8 : 1;
+    case 128:  return s == 0 ? 16 : (s == 1 ? 8 : 1);
+    case 256:  return s < 2 ? 16 : 1;
+    case 512:  return s < 3 ? 8 : 1;
+    case 1024: return s == 0 ? 16 : (s < 3 ? 8 : 1);
+    case 2048: return s < 2 ? 16 : (s == 2 ? 8 : 1);
+    case 4096: return s < 3 ? 16 : 1;
+    default:   return 1;
+  }
+}
+ADMMTV_HD constexpr int plan_stages(int L) {
+  int n = 0;
+  while (n < 4 && plan_radix(L, n) > 1) ++n;
+  return n;
+}
+// length of the sub-transforms stage s works on: L / prod_{q<s} R_q
+ADMMTV_HD constexpr int plan_sublen(int L, int s) {
+  int len = L;
+  for (int q = 0; q < s; ++q) len /= plan_radix(L, q);
+  return len;
+}
+ADMMTV_HD constexpr bool plan_supported(int L) { return plan_stages(L) >= 2; }
+
+// frequency index held at storage position p after the forward (DIF) passes
+ADMMTV_HD inline int pos_to_freq(int L, int p) {
+  int k = 0, mult = 1, len = L;
+  for (int s = 0; s < 4; ++s) {
+    int R = plan_radix(L, s);
+    if (R <= 1) break;
+    len /= R;
+    int m = p / len;
+    p -= m * len;
+    k += m * mult;
+    mult *= R;
+  }
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------
+// complex helpers (float2 = re, im)
+// ------------------------------------------------------------------------------------------
+ADMMTV_DI float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+ADMMTV_DI float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+ADMMTV_DI float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+ADMMTV_DI float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+ADMMTV_DI float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+
+// multiply by exp(-+ 2*pi*i * E/16)  (forward: minus sign; INV: plus sign), E compile time
+template <int E, bool INV>
+ADMMTV_DI float2 mul_w16(float2 a) {
+  constexpr float C1 = 0.92387953251128674f;  // cos(pi/8)
+  constexpr float S1 = 0.38268343236508977f;  // sin(pi/8)
+  constexpr float H = 0.70710678118654752f;   // sqrt(1/2)
+  constexpr int e = E & 15;
+  if constexpr (e == 0) return a;
+  else if constexpr (e == 4) return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+  else if constexpr (e == 8) return make_float2(-a.x, -a.y);
+  else if constexpr (e == 12) return INV ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+  else if constexpr (e == 2)
+    return INV ? make_float2((a.x - a.y) * H, (a.x + a.y) * H) : make_float2((a.x + a.y) * H, (a.y - a.x) * H);
+  else if constexpr (e == 6)
+    return INV ? make_float2(-(a.x + a.y) * H, (a.x - a.y) * H) : make_float2((a.y - a.x) * H, -(a.x + a.y) * H);
+  else {
+    // general: w = (c, -+s)
+    constexpr float c = (e == 1) ? C1 : (e == 3) ? S1 : (e == 5) ? -S1 : (e == 7) ? -C1 : 0.f;
+    constexpr float s = (e == 1) ? S1 : (e == 3) ? C1 : (e == 5) ? C1 : (e == 7) ? S1 : 0.f;
+    static_assert(e == 1 || e == 3 || e == 5 || e == 7, "mul_w16: unsupported exponent");
+    // forward w = c - i s ; inverse w = c + i s
+    return INV ? make_float2(a.x * c - a.y * s, a.x * s + a.y * c) : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// size-R DFT in registers, natural order in -> natural order out (recursive radix-2 DIF)
+// ------------------------------------------------------------------------------------------
+template <int R, bool INV>
+struct Dft {
+  static ADMMTV_DI void run(float2* a) {
+    float2 s[R / 2], d[R / 2];
+    unroll_half<0>(a, s, d);
+    Dft<R / 2, INV>::run(s);
+    Dft<R / 2, INV>::run(d);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      a[2 * k] = s[k];
+      a[2 * k + 1] = d[k];
+    }
+  }
+  template <int T>
+  static ADMMTV_DI void unroll_half(const float2* a, float2* s, float2* d) {
+    if constexpr (T < R / 2) {
+      s[T] = cadd(a[T], a[T + R / 2]);
+      d[T] = mul_w16<T * (16 / R), INV>(csub(a[T], a[T + R / 2]));
+      unroll_half<T + 1>(a, s, d);
+    }
+  }
+};
+template <bool INV>
+struct Dft<1, INV> {
+  static ADMMTV_DI void run(float2*) {}
+};
+
+// p[m] = w^m, m = 0..R-1, product tree of depth log2(m)
+template <int R>
+ADMMTV_DI void twiddle_powers(float2 w, float2* p) {
+  p[0] = make_float2(1.f, 0.f);
+  p[1] = w;
+#pragma unroll
+  for (int m = 2; m < R; ++m) p[m] = cmul(p[m / 2], p[m - m / 2]);
+}
+
+// One stage's work item: which line elements it touches and its twiddle base.
+//   elements: base + m*stride, m = 0..R-1 ; twiddle W_LS^(t*m) = tw[t*(L/LS)]^m
+template <int L, int S>
+struct Stage {
+  static constexpr int R = plan_radix(L, S);
+  static constexpr int LS = plan_sublen(L, S);
+  static constexpr int STRIDE = LS / R;  // also the number of distinct t
+  static constexpr int ITEMS = L / R;    // work items per line
+  static constexpr bool HAS_TW = STRIDE > 1;
+  static ADMMTV_DI int base(int wi) { return (wi / STRIDE) * LS + (wi % STRIDE); }
+  static ADMMTV_DI int tindex(int wi) { return (wi % STRIDE) * (L / LS); }
+};
+
+// forward pass on registers: a <- twiddle( DFT_R(a) )
+template <int L, int S>
+ADMMTV_DI void stage_fwd(float2* a, const float2* p /*powers, only if HAS_TW*/) {
+  using St = Stage<L, S>;
+  Dft<St::R, false>::run(a);
+  if constexpr (St::HAS_TW) {
+#pragma unroll
+    for (int m = 1; m < St::R; ++m) a[m] = cmul(a[m], p[m]);
+  }
+}
+// inverse pass on registers: a <- IDFT_R( conj-twiddle(a) )   (p holds conj powers)
+template <int L, int S>
+ADMMTV_DI void stage_inv(float2* a, const float2* p) {
+  using St = Stage<L, S>;
+  if constexpr (St::HAS_TW) {
+#pragma unroll
+    for (int m = 1; m < St::R; ++m) a[m] = cmul(a[m], p[m]);
+  }
+  Dft<St::R, true>::run(a);
+}
+
+// twiddle powers for work item wi of stage S (forward sign, or conjugated for the inverse)
+template <int L, int S, bool INV>
+ADMMTV_DI void stage_twiddles(int wi, const float2* __restrict__ tw, float2* p) {
+  using St = Stage<L, S>;
+  if constexpr (St::HAS_TW) {
+    float2 w = tw[St::tindex(wi)];
+    if (INV) w.y = -w.y;
+    twiddle_powers<St::R>(w, p);
+  }
+}
+
+}  // namespace admmtv

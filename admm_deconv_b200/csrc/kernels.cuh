@@ -1,0 +1,760 @@
+// kernels.cuh -- the hand-written sm_100a kernels of the ADMM-TV path.
+//
+// Data layout in HBM (DESIGN.md "Layout"): the S = P*B independent image planes are processed
+// as Q = ceil(S/2) *plane pairs*: planes (2q, 2q+1) are the real and imaginary part of one
+// complex image.  The x-update operator A = F^-1 C F is real, hence C-linear, so one full
+// complex 2-D FFT of the pair transforms both planes at once with no Hermitian bookkeeping.
+// Every internal array is float2 [Q][N][M] (dim 1 = M contiguous):
+//   bpk   = H^T y                               (pair-packed, spatial)
+//   spec* = spectra between the two FFT passes   (rows = dim-1 frequencies, digit-reversed)
+//   v     = D x + u, the ONLY iteration state:   z = shrink(v), u = v - z   [Q][2][N][M]
+//
+// One ADMM iteration (ops.jl:168-173) is two launches:
+//   k_dim2     : dim-2 FFT -> x C (spectral division, ops.jl:168) -> dim-2 IFFT, per 16-row tile
+//   k_dim1_fwd : dim-1 IFFT -> x ; D(x) (ops.jl:169) ; z/u update (ops.jl:171,173) ;
+//                r = H^T y + rho D^T(z-u) (ops.jl:168 of the NEXT iteration) ; dim-1 FFT
+#pragma once
+
+#include "fft_core.cuh"
+
+namespace admmtv {
+
+#ifndef ADMMTV_EMU
+#define ADMMTV_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define ADMMTV_DYN_SMEM(type, name)                              \
+  extern __shared__ __align__(16) unsigned char name##_raw_[];   \
+  type* name = reinterpret_cast<type*>(name##_raw_)
+#endif
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+template <int R>
+struct TwP {
+  float2 p[R];
+};
+
+// Distribute (work item wi of a line, line c) pairs over the block so that a thread keeps the
+// same wi (hence the same twiddles) whenever the block is at least one line wide.
+template <int ITEMS, int NT, class Prep, class Body>
+ADMMTV_DI void for_items(int tid, int nlines, Prep prep, Body body) {
+  if constexpr (NT >= ITEMS) {
+    static_assert(NT % ITEMS == 0, "block must be a multiple of the line's work items");
+    const int wi = tid % ITEMS;
+    const auto ctx = prep(wi);
+    for (int c = tid / ITEMS; c < nlines; c += NT / ITEMS) body(wi, c, ctx);
+  } else {
+    for (int wi = tid; wi < ITEMS; wi += NT) {
+      const auto ctx = prep(wi);
+      for (int c = 0; c < nlines; ++c) body(wi, c, ctx);
+    }
+  }
+}
+
+template <int R>
+ADMMTV_DI void load_contig(const float2* __restrict__ src, float2* a) {
+  static_assert(R % 2 == 0, "even radix");
+#pragma unroll
+  for (int m = 0; m < R / 2; ++m) {
+    const float4 v = *reinterpret_cast<const float4*>(src + 2 * m);
+    a[2 * m] = make_float2(v.x, v.y);
+    a[2 * m + 1] = make_float2(v.z, v.w);
+  }
+}
+template <int R>
+ADMMTV_DI void store_contig(float2* __restrict__ dst, const float2* a) {
+#pragma unroll
+  for (int m = 0; m < R / 2; ++m)
+    *reinterpret_cast<float4*>(dst + 2 * m) = make_float4(a[2 * m].x, a[2 * m].y, a[2 * m + 1].x, a[2 * m + 1].y);
+}
+
+ADMMTV_DI double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the block; result valid in thread 0.  All threads must call.
+ADMMTV_DI double block_sum(double v) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    r = lane < nw ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+ADMMTV_DI float act_apply(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return fminf(fmaxf(v, 0.f), 6.f);
+  if (act == 3) return fminf(fmaxf(v, 0.f), 1.f);
+  return v;
+}
+// derivative of the activation expressed through its OUTPUT (relu family: 1 strictly inside)
+ADMMTV_DI float act_grad_from_out(float o, int act) {
+  if (act == 1) return o > 0.f ? 1.f : 0.f;
+  if (act == 2) return (o > 0.f && o < 6.f) ? 1.f : 0.f;
+  if (act == 3) return (o > 0.f && o < 1.f) ? 1.f : 0.f;
+  return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// setup: twiddles, PSF spectrum, C / K tables (ops.jl:104-119 restated analytically)
+// ------------------------------------------------------------------------------------------
+// tw[n] = exp(-2 pi i n / L)
+static __global__ void k_setup_twiddles(float2* twM, int M, float2* twN, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < M) {
+    double s, c;
+    sincospi(2.0 * n / M, &s, &c);
+    twM[n] = make_float2((float)c, (float)(-s));
+  }
+  if (n < N) {
+    double s, c;
+    sincospi(2.0 * n / N, &s, &c);
+    twN[n] = make_float2((float)c, (float)(-s));
+  }
+}
+
+// clamp of deconv_admm.jl:216-219, in place; masks (1 = gradient passes) into `mask`:
+// mask[0] = lambda, mask[1] = rho, mask[2..2+kh*kw) = h
+static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int nh, float creg, int do_clamp, float* mask) {
+  for (int i = threadIdx.x; i < nh + 2; i += blockDim.x) {
+    float* p = i == 0 ? lambda : (i == 1 ? rho : h + (i - 2));
+    const float v = *p;
+    float m = 1.f;
+    if (do_clamp) {
+      if (i < 2) {
+        m = (v >= creg) ? 1.f : 0.f;
+        *p = fmaxf(v, creg);
+      } else {
+        m = (v >= 0.f && v <= 1.f) ? 1.f : 0.f;
+        *p = fminf(fmaxf(v, 0.f), 1.f);
+      }
+    }
+    if (mask) mask[i] = m;
+  }
+}
+
+// T[k1][b] = sum_a h[a,b] exp(-2 pi i k1 a / M)      (dim-1 DFT of the corner-placed PSF)
+static __global__ void k_setup_psf_dim1(const float* __restrict__ h, int kh, int kw, int M, double2* T) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * kw) return;
+  const int k1 = idx / kw, b = idx % kw;
+  double re = 0.0, im = 0.0;
+  for (int a = 0; a < kh; ++a) {
+    double s, c;
+    sincospi(2.0 * ((long long)k1 * a % M) / M, &s, &c);
+    const double hv = (double)h[a + kh * b];
+    re += hv * c;
+    im -= hv * s;
+  }
+  T[idx] = make_double2(re, im);
+}
+
+// ctab[p2][p1] = C(k1,k2) / (M N),  C = 1 / (|Sigma|^2 + rho (4 sin^2(pi k2/N) + 4 sin^2(pi k1/M)))   ops.jl:119
+// ktab[p2][p1] = conj(K)(k1,k2) / (M N), K = Sigma exp(+2 pi i (k1 pd/M + k2 pr/N))                   SURVEY 8a-6
+// sig [p2][p1] = Sigma (only written when sig != nullptr; the backward needs it)
+// (p1,p2) are storage positions; (k1,k2) = pos_to_freq of them.
+static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int kw, int M, int N,
+                                      const float* __restrict__ rho_p, float* ctab, float2* ktab, float2* sig) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int p1 = idx % M, p2 = idx / M;
+  const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
+  double sr = 1.0, si = 0.0;
+  if (kh > 0) {
+    sr = 0.0;
+    si = 0.0;
+    for (int b = 0; b < kw; ++b) {
+      double s, c;
+      sincospi(2.0 * ((long long)k2 * b % N) / N, &s, &c);
+      const double2 t = T[k1 * kw + b];
+      // t * (c - i s)
+      sr += t.x * c + t.y * s;
+      si += t.y * c - t.x * s;
+    }
+  }
+  const double rho = (double)*rho_p;
+  double s1, c1, s2, c2;
+  sincospi((double)k2 / N, &s2, &c2);
+  sincospi((double)k1 / M, &s1, &c1);
+  const double lap = 4.0 * s2 * s2 + 4.0 * s1 * s1;
+  const double inv_mn = 1.0 / ((double)M * (double)N);
+  const double C = 1.0 / (sr * sr + si * si + rho * lap);
+  ctab[idx] = (float)(C * inv_mn);
+  if (ktab) {
+    const int pd = kh > 0 ? (kh - 1) / 2 : 0, pr = kw > 0 ? (kw - 1) / 2 : 0;
+    double ps, pc;
+    const double ph = 2.0 * ((double)((long long)k1 * pd % M) / M + (double)((long long)k2 * pr % N) / N);
+    sincospi(ph, &ps, &pc);
+    // K = Sigma * (pc + i ps); store conj(K)/(MN)
+    const double kr = sr * pc - si * ps, ki = sr * ps + si * pc;
+    ktab[idx] = make_float2((float)(kr * inv_mn), (float)(-ki * inv_mn));
+  }
+  if (sig) sig[idx] = make_float2((float)sr, (float)si);
+}
+
+// ------------------------------------------------------------------------------------------
+// dim-1 (contiguous) FFT passes over a tile of columns held in shared memory
+// ------------------------------------------------------------------------------------------
+template <int LM>
+struct Dim1Cfg {
+  static constexpr int M = 1 << LM;
+  static constexpr int NT = LM <= 8 ? M : (LM <= 11 ? 256 : 512);
+  static constexpr int RPT = M / NT;                  // rows per thread in the stencil sweep
+  static constexpr int CHUNK = RPT >= 8 ? 1 : 8 / RPT;  // columns between barriers
+  // tile columns including the 2 halo columns
+  static constexpr int TC = LM <= 8 ? 34 : (LM == 9 ? 18 : (LM <= 11 ? 10 : 6));
+  static constexpr int CO = TC - 2;                   // output columns per block
+  static constexpr size_t SMEM = (size_t)TC * M * sizeof(float2);
+};
+
+// shared-memory element index of (column c, row i) -- the single hook for bank swizzling
+template <int LM>
+ADMMTV_DI int sidx(int c, int i) {
+  return c * (1 << LM) + i;
+}
+
+template <int LM, int NT, int S, bool INV>
+ADMMTV_DI void dim1_smem_stage(float2* X, int ncols, const float2* __restrict__ tw, int tid) {
+  constexpr int M = 1 << LM;
+  using St = Stage<M, S>;
+  for_items<St::ITEMS, NT>(
+      tid, ncols,
+      [&](int wi) {
+        TwP<St::R> t;
+        stage_twiddles<M, S, INV>(wi, tw, t.p);
+        return t;
+      },
+      [&](int wi, int c, const TwP<St::R>& t) {
+        float2 a[St::R];
+        const int base = St::base(wi);
+#pragma unroll
+        for (int m = 0; m < St::R; ++m) a[m] = X[sidx<LM>(c, base + m * St::STRIDE)];
+        if (INV) stage_inv<M, S>(a, t.p);
+        else stage_fwd<M, S>(a, t.p);
+#pragma unroll
+        for (int m = 0; m < St::R; ++m) X[sidx<LM>(c, base + m * St::STRIDE)] = a[m];
+      });
+}
+
+template <int LM, int NT, int S>
+ADMMTV_DI void dim1_inv_stages_down(float2* X, int ncols, const float2* __restrict__ tw, int tid) {
+  if constexpr (S >= 0) {
+    dim1_smem_stage<LM, NT, S, true>(X, ncols, tw, tid);
+    __syncthreads();
+    dim1_inv_stages_down<LM, NT, S - 1>(X, ncols, tw, tid);
+  }
+}
+template <int LM, int NT, int S>
+ADMMTV_DI void dim1_fwd_stages_up(float2* X, int ncols, const float2* __restrict__ tw, int tid) {
+  if constexpr (S < plan_stages(1 << LM) - 1) {
+    dim1_smem_stage<LM, NT, S, false>(X, ncols, tw, tid);
+    __syncthreads();
+    dim1_fwd_stages_up<LM, NT, S + 1>(X, ncols, tw, tid);
+  }
+}
+
+// Inverse dim-1 FFT of `ncols` spectrum columns (digit-reversed rows) -> natural-order columns
+// in X.  The first pass reads global memory directly (contiguous R-element runs).  Ends synced.
+template <int LM, int NT, class ColPtr>
+ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const float2* __restrict__ tw, int tid) {
+  constexpr int M = 1 << LM, NS = plan_stages(M);
+  using St = Stage<M, NS - 1>;
+  static_assert(St::STRIDE == 1, "last plan stage must be contiguous");
+  for_items<St::ITEMS, NT>(
+      tid, ncols, [&](int) { return 0; },
+      [&](int wi, int c, int) {
+        float2 a[St::R];
+        load_contig<St::R>(colptr(c) + wi * St::R, a);
+        Dft<St::R, true>::run(a);
+#pragma unroll
+        for (int m = 0; m < St::R; ++m) X[sidx<LM>(c, wi * St::R + m)] = a[m];
+      });
+  __syncthreads();
+  dim1_inv_stages_down<LM, NT, NS - 2>(X, ncols, tw, tid);
+}
+
+// Forward dim-1 FFT of `ncols` natural-order columns in X (must be synced) -> global spectrum
+// columns (digit-reversed rows).  The last pass writes global memory directly.
+template <int LM, int NT, class ColPtr>
+ADMMTV_DI void dim1_fft_from_smem(float2* X, int ncols, ColPtr colptr, const float2* __restrict__ tw, int tid) {
+  constexpr int M = 1 << LM, NS = plan_stages(M);
+  dim1_fwd_stages_up<LM, NT, 0>(X, ncols, tw, tid);
+  using St = Stage<M, NS - 1>;
+  for_items<St::ITEMS, NT>(
+      tid, ncols, [&](int) { return 0; },
+      [&](int wi, int c, int) {
+        float2 a[St::R];
+#pragma unroll
+        for (int m = 0; m < St::R; ++m) a[m] = X[sidx<LM>(c, wi * St::R + m)];
+        Dft<St::R, false>::run(a);
+        store_contig<St::R>(colptr(c) + wi * St::R, a);
+      });
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pack_fft1: user-layout planes -> pair-pack -> dim-1 FFT -> spectrum
+//   MODE 0: src = y                                  (ops.jl:101 permute + first rfft pass)
+//   MODE 1: src = xbar * act'(x_out); accumulates biasbar (deconv_admm.jl:222-224 pullback)
+//   MODE 2: src = already pair-packed spatial data (b = H^T y -> first x-update input)
+// ------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* src;    // MODE 0/1: (M,N,S) planes
+  const float2* src_packed;  // MODE 2: [Q][N][M] pair-packed spatial data
+  float2* packed_out;  // MODE 0: optional pair-packed copy of the input (b = y when h is empty)
+  const float* xout;   // MODE 1
+  float2* spec;        // [Q][N][M]
+  const float2* twM;
+  double* bias_acc;    // MODE 1, may be null
+  int N, S, act;
+};
+
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
+  using Cfg = Dim1Cfg<LM>;
+  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
+  ADMMTV_DYN_SMEM(float2, X);
+  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
+  const int j0 = blockIdx.x * CO;
+  const int nout = min(CO, N - j0);
+  const size_t plane = (size_t)N * M;
+  const bool has_b = 2 * q + 1 < A.S;
+  const float* pa = A.src + (size_t)(2 * q) * plane;
+  const float* pb = A.src + (size_t)(2 * q + 1) * plane;
+  double bsum = 0.0;
+  for (int e = tid; e < nout * M; e += NT) {
+    const int c = e / M, i = e % M;
+    const size_t off = (size_t)(j0 + c) * M + i;
+    if (MODE == 2) {
+      X[sidx<LM>(c, i)] = A.src_packed[(size_t)q * plane + off];
+      continue;
+    }
+    float va = pa[off], vb = has_b ? pb[off] : 0.f;
+    if (MODE == 0 && A.packed_out) A.packed_out[(size_t)q * plane + off] = make_float2(va, vb);
+    if (MODE == 1) {
+      va *= act_grad_from_out(A.xout[(size_t)(2 * q) * plane + off], A.act);
+      if (has_b) vb *= act_grad_from_out(A.xout[(size_t)(2 * q + 1) * plane + off], A.act);
+      bsum += (double)va + (double)vb;
+    }
+    X[sidx<LM>(c, i)] = make_float2(va, vb);
+  }
+  if (MODE == 1 && A.bias_acc) {
+    const double tot = block_sum(bsum);
+    if (tid == 0) atomicAdd(A.bias_acc, tot);
+  }
+  __syncthreads();
+  float2* sq = A.spec + (size_t)q * plane;
+  dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_dim1_out: spectrum -> dim-1 IFFT -> spatial
+//   MODE 0: pair-packed float2 out (b = H^T y)
+//   MODE 1: user-layout planes, + bias, activation           (deconv_admm.jl:222-224, ops.jl:175)
+// ------------------------------------------------------------------------------------------
+struct OutArgs {
+  const float2* spec;  // [Q][N][M]
+  float2* packed;      // MODE 0
+  float* planes;       // MODE 1: (M,N,S)
+  const float* bias;   // MODE 1, may be null
+  const float2* twM;
+  int N, S, act;
+};
+
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
+  using Cfg = Dim1Cfg<LM>;
+  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
+  ADMMTV_DYN_SMEM(float2, X);
+  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
+  const int j0 = blockIdx.x * CO;
+  const int nout = min(CO, N - j0);
+  const size_t plane = (size_t)N * M;
+  const float2* sq = A.spec + (size_t)q * plane;
+  dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
+  if (MODE == 0) {
+    float2* dst = A.packed + (size_t)q * plane;
+    for (int e = tid; e < nout * M; e += NT) {
+      const int c = e / M, i = e % M;
+      dst[(size_t)(j0 + c) * M + i] = X[sidx<LM>(c, i)];
+    }
+  } else {
+    const bool has_b = 2 * q + 1 < A.S;
+    const float bias = A.bias ? *A.bias : 0.f;
+    float* pa = A.planes + (size_t)(2 * q) * plane;
+    float* pb = A.planes + (size_t)(2 * q + 1) * plane;
+    for (int e = tid; e < nout * M; e += NT) {
+      const int c = e / M, i = e % M;
+      const float2 v = X[sidx<LM>(c, i)];
+      const size_t off = (size_t)(j0 + c) * M + i;
+      pa[off] = act_apply(v.x + bias, A.act);
+      if (has_b) pb[off] = act_apply(v.y + bias, A.act);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_dim1_fwd: the fused per-iteration kernel (anisotropic)
+//   dim-1 IFFT -> x_k                                             (ops.jl:168 irfft, last pass)
+//   v_k = D x_k + u_{k-1},  u_{k-1} = v_{k-1} - ST(v_{k-1}, tau)    (ops.jl:169,171)
+//   z_k = ST(v_k, tau) ; u_k = v_k - z_k                           (ops.jl:171,173)
+//   r_{k+1} = H^T y + rho D^T (z_k - u_k)                          (ops.jl:168, next iteration)
+//   dim-1 FFT of r_{k+1}                                           (ops.jl:168 rfft, first pass)
+// The only state written is v_k (z_k, u_k are recomputed from it), which is also the backward
+// checkpoint.
+// ------------------------------------------------------------------------------------------
+struct Dim1FwdArgs {
+  const float2* spec_in;
+  float2* spec_out;
+  const float2* bpk;
+  const float2* vprev;  // [Q][2][N][M]; ignored when !HAS_VPREV (v_0 = 0)
+  float2* vnew;         // [Q][2][N][M]
+  const float2* twM;
+  const float* lambda;
+  const float* rho;
+  int N;
+};
+
+struct Shrunk {
+  float2 u, w;  // u = v - z ; w = z - u
+};
+ADMMTV_DI float st1(float v, float tau) { return v - fminf(fmaxf(v, -tau), tau); }  // ST, ops.jl:9
+ADMMTV_DI Shrunk shrink_aniso(float2 v, float tau) {
+  const float2 z = make_float2(st1(v.x, tau), st1(v.y, tau));
+  Shrunk s;
+  s.u = csub(v, z);
+  s.w = csub(z, s.u);
+  return s;
+}
+
+template <int RPT>
+ADMMTV_DI void load_rows(const float2* __restrict__ p, float2* out) {
+  if constexpr (RPT % 2 == 0) load_contig<RPT>(p, out);
+  else {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) out[r] = p[r];
+  }
+}
+template <int RPT>
+ADMMTV_DI void store_rows(float2* __restrict__ p, const float2* v) {
+  if constexpr (RPT % 2 == 0) store_contig<RPT>(p, v);
+  else {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) p[r] = v[r];
+  }
+}
+
+template <int LM, bool HAS_VPREV>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
+  using Cfg = Dim1Cfg<LM>;
+  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
+  static_assert(CO % CHUNK == 0, "chunking must divide the tile");
+  ADMMTV_DYN_SMEM(float2, X);
+  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
+  const int j0 = blockIdx.x * CO;
+  const int nout = min(CO, N - j0);  // N and CO are powers of two: nout % CHUNK == 0
+  const size_t plane = (size_t)N * M;
+  const float2* sin_q = A.spec_in + (size_t)q * plane;
+  auto jcol = [&](int c) {
+    int j = j0 - 1 + c;
+    if (j < 0) j += N;
+    if (j >= N) j -= N;
+    return j;
+  };
+
+  // 1. x_k for columns j0-1 .. j0+nout (one halo column each side)
+  dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+
+  // 2. stencil sweep: this thread owns rows i0 .. i0+RPT-1 of every column
+  const float rho = *A.rho;
+  const float tau = *A.lambda / rho;  // ops.jl:102
+  const int i0 = tid * RPT;
+  const float2* vp1 = A.vprev + ((size_t)q * 2 + 0) * plane;
+  const float2* vp2 = A.vprev + ((size_t)q * 2 + 1) * plane;
+  float2* vn1 = A.vnew + ((size_t)q * 2 + 0) * plane;
+  float2* vn2 = A.vnew + ((size_t)q * 2 + 1) * plane;
+  const float2* bq = A.bpk + (size_t)q * plane;
+
+  float2 w1c[RPT];
+  {
+    const int j = jcol(1);
+    float2 up[RPT], vst[RPT];
+    if (HAS_VPREV) load_rows<RPT>(vp1 + (size_t)j * M + i0, up);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const float2 xa = X[sidx<LM>(0, i0 + r)], xb = X[sidx<LM>(1, i0 + r)];
+      float2 v = csub(xb, xa);
+      if (HAS_VPREV) v = cadd(v, shrink_aniso(up[r], tau).u);
+      vst[r] = v;
+      w1c[r] = shrink_aniso(v, tau).w;
+    }
+    store_rows<RPT>(vn1 + (size_t)j * M + i0, vst);
+  }
+
+  for (int c = 1; c <= nout; c += CHUNK) {
+    float2 rr[CHUNK][RPT];
+#pragma unroll
+    for (int cc = 0; cc < CHUNK; ++cc) {
+      const int col = c + cc;
+      const int j = jcol(col), jn = jcol(col + 1);
+      float2 xc[RPT + 2];  // rows i0-1 .. i0+RPT of column col
+      xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
+      xc[RPT + 1] = X[sidx<LM>(col, (i0 + RPT) & (M - 1))];
+
+      // channel 1 (dim-2 difference) at column col+1
+      float2 w1n[RPT];
+      {
+        float2 up[RPT], vst[RPT];
+        if (HAS_VPREV) load_rows<RPT>(vp1 + (size_t)jn * M + i0, up);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          float2 v = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
+          if (HAS_VPREV) v = cadd(v, shrink_aniso(up[r], tau).u);
+          vst[r] = v;
+          w1n[r] = shrink_aniso(v, tau).w;
+        }
+        if (col + 1 <= nout) store_rows<RPT>(vn1 + (size_t)jn * M + i0, vst);
+      }
+      // channel 2 (dim-1 difference) at column col, rows i0 .. i0+RPT (the last is the
+      // neighbour's first row, recomputed here instead of exchanged)
+      float2 w2[RPT + 1];
+      {
+        float2 up[RPT + 1], vst[RPT];
+        if (HAS_VPREV) {
+          load_rows<RPT>(vp2 + (size_t)j * M + i0, up);
+          up[RPT] = vp2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        }
+#pragma unroll
+        for (int r = 0; r <= RPT; ++r) {
+          float2 v = csub(xc[r + 1], xc[r]);
+          if (HAS_VPREV) v = cadd(v, shrink_aniso(up[r], tau).u);
+          if (r < RPT) vst[r] = v;
+          w2[r] = shrink_aniso(v, tau).w;
+        }
+        store_rows<RPT>(vn2 + (size_t)j * M + i0, vst);
+      }
+      float2 bb[RPT];
+      load_rows<RPT>(bq + (size_t)j * M + i0, bb);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const float2 dt = cadd(csub(w1c[r], w1n[r]), csub(w2[r], w2[r + 1]));  // D^T(z-u)
+        rr[cc][r] = make_float2(bb[r].x + rho * dt.x, bb[r].y + rho * dt.y);
+        w1c[r] = w1n[r];
+      }
+    }
+    __syncthreads();  // every thread is done reading columns <= c+CHUNK-1 of this chunk
+#pragma unroll
+    for (int cc = 0; cc < CHUNK; ++cc)
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) X[sidx<LM>(c + cc - 1, i0 + r)] = rr[cc][r];  // r column -> slot col-1
+  }
+  __syncthreads();
+
+  // 3. dim-1 FFT of r_{k+1}: slot s holds output column j0+s
+  float2* sout_q = A.spec_out + (size_t)q * plane;
+  dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_dim2: dim-2 (strided) pass over a tile of TR contiguous rows x all N columns
+//   forward FFT along dim 2 -> [save Z] -> [accumulate conj(Z) Z2] -> multiply by table ->
+//   inverse FFT along dim 2                                  (ops.jl:168  C .* rfft(...))
+// ------------------------------------------------------------------------------------------
+struct Dim2Args {
+  const float2* in;    // [Q][N][M]
+  float2* out;         // [Q][N][M]
+  const float* ctab;   // MUL 0: real table [N][M]
+  const float2* ktab;  // MUL 1/2: complex table [N][M] (2 = use its conjugate)
+  float2* zsave;       // SAVE_Z: [Q][N][M] full spectrum before the multiply
+  const float2* z2;    // ACC: second spectrum [Q][N][M]
+  float* gacc;         // ACC 1: float [N][M] += Re(conj(Z) Z2) ; ACC 2: float2 [N][M] += conj(Z) Z2
+  const float2* twN;
+  int M;
+};
+
+template <int LN>
+struct Dim2Cfg {
+  static constexpr int N = 1 << LN;
+  static constexpr int TR = LN <= 9 ? 16 : (LN <= 11 ? 8 : 4);
+  static constexpr int NT = 256;
+  static constexpr size_t SMEM = (size_t)N * TR * sizeof(float2);
+};
+
+template <int LN, int S, bool INV>
+ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int tid) {
+  using Cfg = Dim2Cfg<LN>;
+  constexpr int N = Cfg::N, TR = Cfg::TR, NT = Cfg::NT, RP = TR / 2;
+  using St = Stage<N, S>;
+  for (int item = tid; item < RP * St::ITEMS; item += NT) {
+    const int rp = item % RP, wi = item / RP;
+    float2 p[St::R];
+    stage_twiddles<N, S, INV>(wi, tw, p);
+    float2 a0[St::R], a1[St::R];
+    const int base = St::base(wi);
+#pragma unroll
+    for (int m = 0; m < St::R; ++m) {
+      const float4 v = *reinterpret_cast<const float4*>(tile + (base + m * St::STRIDE) * TR + 2 * rp);
+      a0[m] = make_float2(v.x, v.y);
+      a1[m] = make_float2(v.z, v.w);
+    }
+    if (INV) {
+      stage_inv<N, S>(a0, p);
+      stage_inv<N, S>(a1, p);
+    } else {
+      stage_fwd<N, S>(a0, p);
+      stage_fwd<N, S>(a1, p);
+    }
+#pragma unroll
+    for (int m = 0; m < St::R; ++m)
+      *reinterpret_cast<float4*>(tile + (base + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+  }
+}
+template <int LN, int S>
+ADMMTV_DI void dim2_fwd_mid(float2* tile, const float2* __restrict__ tw, int tid) {
+  if constexpr (S < plan_stages(1 << LN) - 1) {
+    dim2_smem_stage<LN, S, false>(tile, tw, tid);
+    __syncthreads();
+    dim2_fwd_mid<LN, S + 1>(tile, tw, tid);
+  }
+}
+template <int LN, int S>
+ADMMTV_DI void dim2_inv_mid(float2* tile, const float2* __restrict__ tw, int tid) {
+  if constexpr (S >= 1) {
+    dim2_smem_stage<LN, S, true>(tile, tw, tid);
+    __syncthreads();
+    dim2_inv_mid<LN, S - 1>(tile, tw, tid);
+  }
+}
+
+template <int LN, int MUL, bool SAVE_Z, int ACC, bool FWD_ONLY>
+__global__ void __launch_bounds__(Dim2Cfg<LN>::NT) k_dim2(Dim2Args A) {
+  using Cfg = Dim2Cfg<LN>;
+  constexpr int N = Cfg::N, TR = Cfg::TR, NT = Cfg::NT, RP = TR / 2, NS = plan_stages(N);
+  ADMMTV_DYN_SMEM(float2, tile);  // [N][TR]
+  const int tid = threadIdx.x, M = A.M;
+  const int i0 = blockIdx.x * TR;
+  const size_t qoff = (size_t)blockIdx.y * N * M;
+  const float2* src = A.in + qoff + i0;
+
+  // forward stage 0: global -> registers -> shared
+  {
+    using St = Stage<N, 0>;
+    for (int item = tid; item < RP * St::ITEMS; item += NT) {
+      const int rp = item % RP, wi = item / RP;
+      float2 p[St::R];
+      stage_twiddles<N, 0, false>(wi, A.twN, p);
+      float2 a0[St::R], a1[St::R];
+#pragma unroll
+      for (int m = 0; m < St::R; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(wi + m * St::STRIDE) * M + 2 * rp);
+        a0[m] = make_float2(v.x, v.y);
+        a1[m] = make_float2(v.z, v.w);
+      }
+      stage_fwd<N, 0>(a0, p);
+      stage_fwd<N, 0>(a1, p);
+#pragma unroll
+      for (int m = 0; m < St::R; ++m)
+        *reinterpret_cast<float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+    }
+  }
+  __syncthreads();
+  dim2_fwd_mid<LN, 1>(tile, A.twN, tid);
+
+  // last forward stage fused with the spectral multiply and the first inverse stage
+  {
+    using St = Stage<N, NS - 1>;
+    static_assert(St::STRIDE == 1, "last plan stage must be contiguous");
+    for (int item = tid; item < RP * St::ITEMS; item += NT) {
+      const int rp = item % RP, wi = item / RP;
+      float2 a0[St::R], a1[St::R];
+#pragma unroll
+      for (int m = 0; m < St::R; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + (wi * St::R + m) * TR + 2 * rp);
+        a0[m] = make_float2(v.x, v.y);
+        a1[m] = make_float2(v.z, v.w);
+      }
+      Dft<St::R, false>::run(a0);
+      Dft<St::R, false>::run(a1);
+#pragma unroll
+      for (int m = 0; m < St::R; ++m) {
+        const size_t g = (size_t)(wi * St::R + m) * M + i0 + 2 * rp;  // table / spectrum offset
+        if (SAVE_Z || FWD_ONLY) {
+          float2* zs = FWD_ONLY ? A.out : A.zsave;
+          *reinterpret_cast<float4*>(zs + qoff + g) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+        }
+        if (ACC != 0) {
+          const float4 z2 = *reinterpret_cast<const float4*>(A.z2 + qoff + g);
+          // conj(Z) * Z2
+          const float re0 = a0[m].x * z2.x + a0[m].y * z2.y, im0 = a0[m].x * z2.y - a0[m].y * z2.x;
+          const float re1 = a1[m].x * z2.z + a1[m].y * z2.w, im1 = a1[m].x * z2.w - a1[m].y * z2.z;
+          if (ACC == 1) {
+            atomicAdd(A.gacc + g, re0);
+            atomicAdd(A.gacc + g + 1, re1);
+          } else {
+            atomicAdd(A.gacc + 2 * g, re0);
+            atomicAdd(A.gacc + 2 * g + 1, im0);
+            atomicAdd(A.gacc + 2 * g + 2, re1);
+            atomicAdd(A.gacc + 2 * g + 3, im1);
+          }
+        }
+        if (!FWD_ONLY) {
+          if (MUL == 0) {
+            const float2 cc = *reinterpret_cast<const float2*>(A.ctab + g);
+            a0[m] = cscale(a0[m], cc.x);
+            a1[m] = cscale(a1[m], cc.y);
+          } else {
+            const float4 kk = *reinterpret_cast<const float4*>(A.ktab + g);
+            const float sgn = MUL == 2 ? -1.f : 1.f;
+            a0[m] = cmul(a0[m], make_float2(kk.x, sgn * kk.y));
+            a1[m] = cmul(a1[m], make_float2(kk.z, sgn * kk.w));
+          }
+        }
+      }
+      if (!FWD_ONLY) {
+        Dft<St::R, true>::run(a0);
+        Dft<St::R, true>::run(a1);
+#pragma unroll
+        for (int m = 0; m < St::R; ++m)
+          *reinterpret_cast<float4*>(tile + (wi * St::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+      }
+    }
+  }
+  if (FWD_ONLY) return;
+  __syncthreads();
+  dim2_inv_mid<LN, NS - 2>(tile, A.twN, tid);
+
+  // inverse stage 0: shared -> registers -> global
+  {
+    using St = Stage<N, 0>;
+    float2* dst = A.out + qoff + i0;
+    for (int item = tid; item < RP * St::ITEMS; item += NT) {
+      const int rp = item % RP, wi = item / RP;
+      float2 p[St::R];
+      stage_twiddles<N, 0, true>(wi, A.twN, p);
+      float2 a0[St::R], a1[St::R];
+#pragma unroll
+      for (int m = 0; m < St::R; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp);
+        a0[m] = make_float2(v.x, v.y);
+        a1[m] = make_float2(v.z, v.w);
+      }
+      stage_inv<N, 0>(a0, p);
+      stage_inv<N, 0>(a1, p);
+#pragma unroll
+      for (int m = 0; m < St::R; ++m)
+        *reinterpret_cast<float4*>(dst + (size_t)(wi + m * St::STRIDE) * M + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+    }
+  }
+}
+
+}  // namespace admmtv

@@ -1,0 +1,114 @@
+/*
+ * admmtv.h -- C ABI of the B200-native ADMM-TV deconvolution layer.
+ *
+ * This is the drop-in boundary for ONE hot path of georgegrosu1/admm-deconv:
+ *
+ *   reference interface replaced                         entry point here
+ *   ---------------------------------------------------  ---------------------------------
+ *   tvd_fft(y, λ, ρ, h, isotropic, maxit)                admmtv_forward  (activation=identity,
+ *     src/ops/ops.jl:181-188 -> tvd_fft_gpu :99-178        has_bias=0, ADMMTV_FLAG_NO_CLAMP)
+ *   (d::Admm)(x)  clamp -> tvd_fft -> +bias -> σ          admmtv_forward
+ *     src/layers/deconv_admm.jl:215-225
+ *   Zygote pullback of the two above (no reference code;  admmtv_backward
+ *     tape through ops.jl:166-174)
+ *   CUDA.zeros / temporaries of ops.jl:128-141            admmtv_workspace_bytes (caller owns memory)
+ *   tvd_fft on a CPU Array (ops.jl:187 -> tvd_fft_cpu)    admmtv_forward_host  (host buffers, copies inside)
+ *
+ * Conventions
+ *   - Arrays are Julia arrays: (M,N,P,B) column-major, element (i,j,p,b) at i + M*(j + N*(p + P*b)).
+ *     h is (kh,kw) column-major (the (kh,kw,1,1) Flux.convfilter weight).  All fp32.
+ *   - Unless the name ends in _host, every data pointer is a DEVICE pointer on `desc->device`
+ *     (Julia passes CuPtr{Cfloat}); `stream` is a cudaStream_t passed as void*.
+ *   - Calls only enqueue work on `stream` and return; they never synchronise.
+ *   - Return value: 0 ok; <0 invalid argument / unsupported size (nothing was launched);
+ *     >0 a cudaError_t.  admmtv_strerror() explains either.  Nothing throws across the boundary.
+ *   - The library holds no mutable global state; every table lives in the caller's workspace.
+ *   - There is no CPU fallback: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef ADMMTV_H
+#define ADMMTV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMMTV_VERSION 100 /* 0.1.0 */
+
+/* activation enum: the σ of deconv_admm.jl:224 as used by net_build.jl (:8,107-119,155) */
+enum { ADMMTV_ACT_IDENTITY = 0, ADMMTV_ACT_RELU = 1, ADMMTV_ACT_RELU6 = 2, ADMMTV_ACT_RELU1 = 3 };
+
+/* flags */
+enum {
+  ADMMTV_FLAG_NO_CLAMP = 1,      /* skip deconv_admm.jl:216-219 (bare tvd_fft call) */
+  ADMMTV_FLAG_NOGRAD_REPEAT = 2  /* train.jl:10 variant: no ∂weight through the spatial H^T y path */
+};
+
+/* error codes (<0) */
+enum {
+  ADMMTV_OK = 0,
+  ADMMTV_ERR_NULL = -1,
+  ADMMTV_ERR_SHAPE = -2,        /* non-positive dims, kernel larger than image, ... */
+  ADMMTV_ERR_UNSUPPORTED = -3,  /* M or N not a supported FFT length (power of two, 16..4096) */
+  ADMMTV_ERR_ITERS = -4,
+  ADMMTV_ERR_ENUM = -5,
+  ADMMTV_ERR_ALIGN = -6,        /* workspace / checkpoint not 256-byte aligned */
+  ADMMTV_ERR_NO_DEVICE = -7
+};
+
+typedef struct admmtv_desc {
+  int32_t M, N, P, B;      /* size(y)                                   ops.jl:100 */
+  int32_t kh, kw;          /* size(h)[1:2]; 0,0 = empty h (H = identity) ops.jl:104 */
+  int32_t iters;           /* maxit / d.iters                            ops.jl:166 */
+  int32_t iso;             /* isotropic: 0 = ST (ops.jl:9), 1 = BT (ops.jl:10) */
+  int32_t activation;      /* ADMMTV_ACT_*                               deconv_admm.jl:224 */
+  int32_t has_bias;        /* d.bias is a 1-vector (1) or `false` (0)    deconv_admm.jl:222 */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t flags;           /* ADMMTV_FLAG_* */
+  float creg;              /* clamp floor of λ, ρ                        deconv_admm.jl:216-217 */
+  int32_t reserved;        /* must be 0 */
+} admmtv_desc;
+
+int admmtv_version(void);
+const char* admmtv_strerror(int code);
+
+/* Validates the descriptor without touching the GPU. */
+int admmtv_check(const admmtv_desc* desc);
+
+/* Bytes the caller must provide: `fwd_bytes` workspace for admmtv_forward, `ckpt_bytes` for the
+ * per-iteration checkpoint a later admmtv_backward needs (pass ckpt=NULL to forward for
+ * inference), `bwd_bytes` workspace for admmtv_backward.  Any out pointer may be NULL. */
+int admmtv_workspace_bytes(const admmtv_desc* desc, size_t* fwd_bytes, size_t* ckpt_bytes, size_t* bwd_bytes);
+
+/* Forward.  lambda, rho (1 float each) and h (kh*kw floats) are IN/OUT: unless
+ * ADMMTV_FLAG_NO_CLAMP they are clamped in place (λ,ρ to [creg,∞), h to [0,1]) exactly as the
+ * reference persists the clamp into the layer struct (deconv_admm.jl:216-219).
+ * bias: 1 float or NULL.  x_out: (M,N,P,B), fully overwritten.  ckpt: NULL or ckpt_bytes. */
+int admmtv_forward(const admmtv_desc* desc, const float* y, float* h, float* lambda, float* rho,
+                   const float* bias, float* x_out, void* workspace, void* ckpt, void* stream);
+
+/* Backward (pullback).  xbar is the cotangent of the layer output; x_out the forward result
+ * (needed for σ'); ckpt the buffer the forward call filled; y, h, lambda, rho as left by that
+ * forward call (clamped).  Outputs are fully overwritten: ybar (M,N,P,B), hbar (kh*kw, may be NULL
+ * when kh=0), lambdabar, rhobar (1 float each), biasbar (1 float or NULL). */
+int admmtv_backward(const admmtv_desc* desc, const float* xbar, const float* x_out, const float* y,
+                    const float* h, const float* lambda, const float* rho, const void* ckpt,
+                    float* ybar, float* hbar, float* lambdabar, float* rhobar, float* biasbar,
+                    void* workspace, void* stream);
+
+/* Host-buffer convenience (the reference's tvd_fft on a CPU Array): allocates device memory,
+ * copies y/h/λ/ρ/bias in, runs admmtv_forward, copies x_out (and the clamped h/λ/ρ) back,
+ * frees, synchronises.  All pointers are HOST pointers. */
+int admmtv_forward_host(const admmtv_desc* desc, const float* y, float* h, float* lambda, float* rho,
+                        const float* bias, float* x_out);
+
+/* Number of kernel launches one admmtv_forward / admmtv_backward call enqueues (bench bookkeeping). */
+int admmtv_forward_launches(const admmtv_desc* desc, int with_ckpt);
+int admmtv_backward_launches(const admmtv_desc* desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMMTV_H */
