@@ -25,6 +25,7 @@ SYMBOLS = (
     "admmtv_forward",
     "admmtv_backward",
     "admmtv_forward_host",
+    "admmtv_profile_forward",
     "admmtv_forward_launches",
     "admmtv_backward_launches",
 )
@@ -68,6 +69,7 @@ class AdmmTvLib:
         L.admmtv_workspace_bytes.argtypes = [C.POINTER(Desc), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
         L.admmtv_forward.argtypes = [C.POINTER(Desc)] + [vp] * 9
         L.admmtv_backward.argtypes = [C.POINTER(Desc)] + [vp] * 14
+        L.admmtv_profile_forward.argtypes = [C.POINTER(Desc)] + [vp] * 10
         L.admmtv_forward_host.argtypes = [C.POINTER(Desc)] + [vp] * 6
         L.admmtv_forward_launches.argtypes = [C.POINTER(Desc), C.c_int]
         L.admmtv_backward_launches.argtypes = [C.POINTER(Desc)]
@@ -98,6 +100,12 @@ class AdmmTvLib:
     def backward(self, d: Desc, xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar, biasbar, ws, stream=0):
         self._raise(self.lib.admmtv_backward(C.byref(d), xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar,
                                              biasbar, ws, stream))
+
+    def profile_forward(self, d: Desc, y, h, lam, rho, bias, x_out, ws, ckpt, stream=0):
+        """Returns (total_ms, dim2_ms, dim1_ms, other_ms); synchronises."""
+        ms = (C.c_float * 4)()
+        self._raise(self.lib.admmtv_profile_forward(C.byref(d), y, h, lam, rho, bias, x_out, ws, ckpt, stream, ms))
+        return tuple(ms)
 
     def forward_host(self, d: Desc, y, h, lam, rho, bias, x_out):
         self._raise(self.lib.admmtv_forward_host(C.byref(d), y, h, lam, rho, bias, x_out))

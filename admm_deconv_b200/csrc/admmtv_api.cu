@@ -3,7 +3,8 @@
 // workspace.  Compiled by nvcc for sm_100a (product) -- see compat.cuh for the test-only
 // emulation build.
 #include "../../include/admmtv.h"
-#include "kernels.cuh"
+#include "args.cuh"
+#include "setup_kernels.cuh"
 
 #include <stdio.h>
 
@@ -16,11 +17,6 @@ static inline int ilog2(int v) {
   return l;
 }
 
-struct Geom {
-  int M, N, P, B, S, Q, LM, LN, K, kh, kw, nh;
-  size_t plane;  // N*M
-  size_t pk;     // Q*N*M  (pair-packed complex elements)
-};
 static Geom geom(const admmtv_desc* d) {
   Geom g;
   g.M = d->M; g.N = d->N; g.P = d->P; g.B = d->B;
@@ -91,13 +87,7 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
 
 #include "bwd_ws.inc"
 
-// ---- launch helpers -------------------------------------------------------------------------
-#define ADMMTV_CHECK_LAUNCH()                      \
-  do {                                             \
-    cudaError_t e__ = cudaGetLastError();          \
-    if (e__ != cudaSuccess) return (int)e__;       \
-  } while (0)
-
+// ---- per-size dispatch (definitions live in inst_dim1.cu / inst_dim2.cu) ------------------------
 #define ADMMTV_SWITCH_LOG2(val, NAME, ...)                                   \
   switch (val) {                                                             \
     case 5: { constexpr int NAME = 5; __VA_ARGS__ } break;                   \
@@ -108,66 +98,21 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
     case 10: { constexpr int NAME = 10; __VA_ARGS__ } break;                 \
     case 11: { constexpr int NAME = 11; __VA_ARGS__ } break;                 \
     case 12: { constexpr int NAME = 12; __VA_ARGS__ } break;                 \
-    default: return ADMMTV_ERR_UNSUPPORTED;                                  \
-  }
-
-template <class K, class Args>
-static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, const Args& a) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  ADMMTV_LAUNCH(kern, grid, dim3(nt), smem, st, a);
-  ADMMTV_CHECK_LAUNCH();
-  return 0;
-}
-
-static dim3 dim1_grid(const Geom& g, int CO) { return dim3((unsigned)((g.N + CO - 1) / CO), (unsigned)g.Q); }
+    default: break;                                                          \
+  }                                                                          \
+  return ADMMTV_ERR_UNSUPPORTED;
 
 static int run_pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {
-  ADMMTV_SWITCH_LOG2(g.LM, LM, {
-    using Cfg = Dim1Cfg<LM>;
-    const dim3 grid = dim1_grid(g, Cfg::CO);
-    if (mode == 0) return launch_k(k_pack_fft1<LM, 0>, grid, Cfg::NT, Cfg::SMEM, st, a);
-    if (mode == 1) return launch_k(k_pack_fft1<LM, 1>, grid, Cfg::NT, Cfg::SMEM, st, a);
-    return launch_k(k_pack_fft1<LM, 2>, grid, Cfg::NT, Cfg::SMEM, st, a);
-  })
-  return 0;
+  ADMMTV_SWITCH_LOG2(g.LM, LM, { return Dim1Launch<LM>::pack_fft1(g, mode, a, st); })
 }
 static int run_dim1_out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st) {
-  ADMMTV_SWITCH_LOG2(g.LM, LM, {
-    using Cfg = Dim1Cfg<LM>;
-    const dim3 grid = dim1_grid(g, Cfg::CO);
-    if (mode == 0) return launch_k(k_dim1_out<LM, 0>, grid, Cfg::NT, Cfg::SMEM, st, a);
-    return launch_k(k_dim1_out<LM, 1>, grid, Cfg::NT, Cfg::SMEM, st, a);
-  })
-  return 0;
+  ADMMTV_SWITCH_LOG2(g.LM, LM, { return Dim1Launch<LM>::out(g, mode, a, st); })
 }
 static int run_dim1_fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st) {
-  ADMMTV_SWITCH_LOG2(g.LM, LM, {
-    using Cfg = Dim1Cfg<LM>;
-    const dim3 grid = dim1_grid(g, Cfg::CO);
-    if (has_vprev) return launch_k(k_dim1_fwd<LM, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
-    return launch_k(k_dim1_fwd<LM, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
-  })
-  return 0;
+  ADMMTV_SWITCH_LOG2(g.LM, LM, { return Dim1Launch<LM>::fwd(g, has_vprev, a, st); })
 }
-// variant ids for k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)
-enum Dim2Variant { D2_C = 0, D2_C_SAVE, D2_KCONJ /*conj(K)/MN as stored*/, D2_C_ACCG, D2_FWDONLY, D2_K_ACCP /*K = conj of stored*/ };
 static int run_dim2(const Geom& g, Dim2Variant v, const Dim2Args& a, cudaStream_t st) {
-  ADMMTV_SWITCH_LOG2(g.LN, LN, {
-    using Cfg = Dim2Cfg<LN>;
-    const dim3 grid((unsigned)(g.M / Cfg::TR), (unsigned)g.Q);
-    switch (v) {
-      case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
-      case D2_C_SAVE: return launch_k(k_dim2<LN, 0, true, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
-      case D2_KCONJ: return launch_k(k_dim2<LN, 1, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
-      case D2_C_ACCG: return launch_k(k_dim2<LN, 0, false, 1, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
-      case D2_FWDONLY: return launch_k(k_dim2<LN, 0, false, 0, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
-      case D2_K_ACCP: return launch_k(k_dim2<LN, 2, false, 2, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
-    }
-  })
-  return 0;
+  ADMMTV_SWITCH_LOG2(g.LN, LN, { return Dim2Launch<LN>::run(g, (int)v, a, st); })
 }
 
 struct DeviceGuard {
@@ -263,8 +208,23 @@ int admmtv_forward_launches(const admmtv_desc* d, int with_ckpt) {
   return n;
 }
 
-int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
-                   float* x_out, void* workspace, void* ckpt, void* stream) {
+// Optional per-kernel-class CUDA-event timing (admmtv_profile_forward): class 0 = k_dim2 of the
+// iterations, 1 = k_dim1_fwd, 2 = everything else (setup, H^T y, final).
+struct Timing {
+  enum { MAXL = 4096 };
+  cudaEvent_t ev[MAXL + 1];
+  int cls[MAXL];
+  int n;
+};
+static void tm_mark(Timing* tm, cudaStream_t st, int cls_of_next) {
+  if (!tm || tm->n >= Timing::MAXL) return;
+  cudaEventRecord(tm->ev[tm->n], st);
+  tm->cls[tm->n] = cls_of_next;
+  tm->n++;
+}
+
+static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
+                        float* x_out, void* workspace, void* ckpt, void* stream, Timing* tm) {
   int rc = admmtv_check(d);
   if (rc) return rc;
   if (!y || !lambda || !rho || !x_out || !workspace) return ADMMTV_ERR_NULL;
@@ -280,6 +240,7 @@ int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda
   Ckpt ck;
   if (ckpt) ck = carve_ckpt(g, ckpt);
 
+  tm_mark(tm, st, 2);
   // deconv_admm.jl:216-219 (persisted clamp) + gradient masks for the pullback
   ADMMTV_LAUNCH(k_clamp_params, dim3(1), dim3(128), 0, st, lambda, rho, h, g.nh, d->creg,
                 (d->flags & ADMMTV_FLAG_NO_CLAMP) ? 0 : 1, ckpt ? ck.mask : w.mask);
@@ -311,6 +272,7 @@ int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda
     Dim2Args a{};
     a.in = w.specA; a.out = w.specB; a.ctab = w.ctab; a.twN = w.twN; a.M = g.M;
     if (ckpt) a.zsave = ck.zck + (size_t)(k - 1) * g.pk;
+    tm_mark(tm, st, 0);
     if ((rc = run_dim2(g, ckpt ? D2_C_SAVE : D2_C, a, st))) return rc;
     if (k < g.K) {
       Dim1FwdArgs f{};
@@ -323,9 +285,11 @@ int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda
         f.vprev = (k & 1) ? w.v1 : w.v0;
         f.vnew = (k & 1) ? w.v0 : w.v1;
       }
+      tm_mark(tm, st, 1);
       if ((rc = run_dim1_fwd(g, k > 1, f, st))) return rc;
     }
   }
+  tm_mark(tm, st, 2);
   // x_K -> user layout, + bias, activation (ops.jl:175, deconv_admm.jl:222-224)
   {
     OutArgs o{};
@@ -333,7 +297,43 @@ int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda
     o.N = g.N; o.S = g.S; o.act = d->activation;
     if ((rc = run_dim1_out(g, 1, o, st))) return rc;
   }
+  tm_mark(tm, st, -1);
   return ADMMTV_OK;
+}
+
+int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
+                   float* x_out, void* workspace, void* ckpt, void* stream) {
+  return forward_impl(d, y, h, lambda, rho, bias, x_out, workspace, ckpt, stream, nullptr);
+}
+
+int admmtv_profile_forward(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
+                           float* x_out, void* workspace, void* ckpt, void* stream, float* ms_out) {
+  if (!ms_out) return ADMMTV_ERR_NULL;
+  int rc = admmtv_check(d);
+  if (rc) return rc;
+  if (2 * d->iters + 8 > Timing::MAXL) return ADMMTV_ERR_ITERS;
+  DeviceGuard guard(d->device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  Timing* tm = new Timing();
+  tm->n = 0;
+  const int nev = 2 * d->iters + 8;
+  for (int i = 0; i < nev; ++i) cudaEventCreate(&tm->ev[i]);
+  rc = forward_impl(d, y, h, lambda, rho, bias, x_out, workspace, ckpt, stream, tm);
+  cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0 && e != cudaSuccess) rc = (int)e;
+  ms_out[0] = ms_out[1] = ms_out[2] = ms_out[3] = 0.f;
+  if (rc == 0) {
+    for (int i = 0; i + 1 < tm->n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tm->ev[i], tm->ev[i + 1]);
+      const int c = tm->cls[i];
+      if (c >= 0 && c < 3) ms_out[1 + c] += ms;
+      ms_out[0] += ms;
+    }
+  }
+  for (int i = 0; i < nev; ++i) cudaEventDestroy(tm->ev[i]);
+  delete tm;
+  return rc;
 }
 
 #include "bwd_api.inc"

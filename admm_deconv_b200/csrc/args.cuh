@@ -1,0 +1,87 @@
+// args.cuh -- problem geometry, kernel argument blocks and the per-size launcher declarations.
+// Each FFT length is compiled in its own translation unit (inst_dim1.cu / inst_dim2.cu with
+// -DADMMTV_INST=<log2 length>) so the build parallelises; admmtv_api.cu only sees declarations.
+#pragma once
+
+#include "compat.cuh"
+
+namespace admmtv {
+
+struct Geom {
+  int M, N, P, B, S, Q, LM, LN, K, kh, kw, nh;
+  size_t plane;  // N*M
+  size_t pk;     // Q*N*M  (pair-packed complex elements)
+};
+
+struct PackArgs {
+  const float* src;    // MODE 0/1: (M,N,S) planes
+  const float2* src_packed;  // MODE 2: [Q][N][M] pair-packed spatial data
+  float2* packed_out;  // MODE 0: optional pair-packed copy of the input (b = y when h is empty)
+  const float* xout;   // MODE 1
+  float2* spec;        // [Q][N][M]
+  const float2* twM;
+  double* bias_acc;    // MODE 1, may be null
+  int N, S, act;
+};
+
+struct OutArgs {
+  const float2* spec;  // [Q][N][M]
+  float2* packed;      // MODE 0
+  float* planes;       // MODE 1: (M,N,S)
+  const float* bias;   // MODE 1, may be null
+  const float2* twM;
+  int N, S, act;
+};
+
+struct Dim1FwdArgs {
+  const float2* spec_in;
+  float2* spec_out;
+  const float2* bpk;
+  const float2* vprev;  // [Q][2][N][M]; ignored when !HAS_VPREV (v_0 = 0)
+  float2* vnew;         // [Q][2][N][M]
+  const float2* twM;
+  const float* lambda;
+  const float* rho;
+  int N;
+};
+
+struct Dim2Args {
+  const float2* in;    // [Q][N][M]
+  float2* out;         // [Q][N][M]
+  const float* ctab;   // MUL 0: real table [N][M]
+  const float2* ktab;  // MUL 1/2: complex table [N][M] (2 = use its conjugate)
+  float2* zsave;       // SAVE_Z: [Q][N][M] full spectrum before the multiply
+  const float2* z2;    // ACC: second spectrum [Q][N][M]
+  float* gacc;         // ACC 1: float [N][M] += Re(conj(Z) Z2) ; ACC 2: float2 [N][M] += conj(Z) Z2
+  const float2* twN;
+  int M;
+};
+
+// variants of k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)
+enum Dim2Variant {
+  D2_C = 0,      // x C                                   (forward iteration, inference)
+  D2_C_SAVE,     // save F r_k, then x C                  (forward iteration, training)
+  D2_KCONJ,      // x conj(K)/MN                          (b = H^T y)
+  D2_C_ACCG,     // G += Re(conj(Z) Z2), then x C         (backward iteration)
+  D2_FWDONLY,    // write the full 2-D spectrum, stop     (F y for the PSF-gradient correlation)
+  D2_K_ACCP      // P += conj(Z) Z2, then x K/MN          (ybar = H bbar and hbar correlation)
+};
+
+template <int LM>
+struct Dim1Launch {
+  static int pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st);
+  static int out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st);
+  static int fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st);
+};
+template <int LN>
+struct Dim2Launch {
+  static int run(const Geom& g, int variant, const Dim2Args& a, cudaStream_t st);
+};
+
+#define ADMMTV_CHECK_LAUNCH()                      \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+}  // namespace admmtv

@@ -1,0 +1,45 @@
+// inst_dim1.cu -- instantiates every dim-1 kernel for ONE FFT length M = 2^ADMMTV_INST.
+// Compiled once per supported length (see admm_deconv_b200/build.py).
+#include "kernels.cuh"
+#include "kernels_bwd.cuh"
+
+#ifndef ADMMTV_INST
+#error "compile with -DADMMTV_INST=<log2 M>"
+#endif
+
+namespace admmtv {
+
+template <class K, class Args>
+static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, const Args& a) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  ADMMTV_LAUNCH(kern, grid, dim3(nt), smem, st, a);
+  ADMMTV_CHECK_LAUNCH();
+  return 0;
+}
+
+constexpr int LM = ADMMTV_INST;
+using Cfg = Dim1Cfg<LM>;
+static dim3 dim1_grid(const Geom& g) { return dim3((unsigned)((g.N + Cfg::CO - 1) / Cfg::CO), (unsigned)g.Q); }
+
+template <>
+int Dim1Launch<LM>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {
+  if (mode == 0) return launch_k(k_pack_fft1<LM, 0>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+  if (mode == 1) return launch_k(k_pack_fft1<LM, 1>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+  return launch_k(k_pack_fft1<LM, 2>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+}
+template <>
+int Dim1Launch<LM>::out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st) {
+  if (mode == 0) return launch_k(k_dim1_out<LM, 0>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+  return launch_k(k_dim1_out<LM, 1>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+}
+template <>
+int Dim1Launch<LM>::fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st) {
+  if (has_vprev) return launch_k(k_dim1_fwd<LM, true>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+  return launch_k(k_dim1_fwd<LM, false>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+}
+#include "inst_dim1_bwd.inc"
+
+}  // namespace admmtv

@@ -1,0 +1,38 @@
+// inst_dim2.cu -- instantiates every dim-2 kernel variant for ONE FFT length N = 2^ADMMTV_INST.
+#include "kernels.cuh"
+
+#ifndef ADMMTV_INST
+#error "compile with -DADMMTV_INST=<log2 N>"
+#endif
+
+namespace admmtv {
+
+template <class K, class Args>
+static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, const Args& a) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  ADMMTV_LAUNCH(kern, grid, dim3(nt), smem, st, a);
+  ADMMTV_CHECK_LAUNCH();
+  return 0;
+}
+
+constexpr int LN = ADMMTV_INST;
+
+template <>
+int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a, cudaStream_t st) {
+  using Cfg = Dim2Cfg<LN>;
+  const dim3 grid((unsigned)(g.M / Cfg::TR), (unsigned)g.Q);
+  switch (variant) {
+    case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_C_SAVE: return launch_k(k_dim2<LN, 0, true, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_KCONJ: return launch_k(k_dim2<LN, 1, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_C_ACCG: return launch_k(k_dim2<LN, 0, false, 1, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_FWDONLY: return launch_k(k_dim2<LN, 0, false, 0, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_K_ACCP: return launch_k(k_dim2<LN, 2, false, 2, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+  }
+  return -5;
+}
+
+}  // namespace admmtv

@@ -16,15 +16,11 @@
 #pragma once
 
 #include "fft_core.cuh"
+#include "args.cuh"
+#include "launch_macros.cuh"
 
 namespace admmtv {
 
-#ifndef ADMMTV_EMU
-#define ADMMTV_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define ADMMTV_DYN_SMEM(type, name)                              \
-  extern __shared__ __align__(16) unsigned char name##_raw_[];   \
-  type* name = reinterpret_cast<type*>(name##_raw_)
-#endif
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -102,103 +98,6 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
   if (act == 2) return (o > 0.f && o < 6.f) ? 1.f : 0.f;
   if (act == 3) return (o > 0.f && o < 1.f) ? 1.f : 0.f;
   return 1.f;
-}
-
-// ------------------------------------------------------------------------------------------
-// setup: twiddles, PSF spectrum, C / K tables (ops.jl:104-119 restated analytically)
-// ------------------------------------------------------------------------------------------
-// tw[n] = exp(-2 pi i n / L)
-static __global__ void k_setup_twiddles(float2* twM, int M, float2* twN, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < M) {
-    double s, c;
-    sincospi(2.0 * n / M, &s, &c);
-    twM[n] = make_float2((float)c, (float)(-s));
-  }
-  if (n < N) {
-    double s, c;
-    sincospi(2.0 * n / N, &s, &c);
-    twN[n] = make_float2((float)c, (float)(-s));
-  }
-}
-
-// clamp of deconv_admm.jl:216-219, in place; masks (1 = gradient passes) into `mask`:
-// mask[0] = lambda, mask[1] = rho, mask[2..2+kh*kw) = h
-static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int nh, float creg, int do_clamp, float* mask) {
-  for (int i = threadIdx.x; i < nh + 2; i += blockDim.x) {
-    float* p = i == 0 ? lambda : (i == 1 ? rho : h + (i - 2));
-    const float v = *p;
-    float m = 1.f;
-    if (do_clamp) {
-      if (i < 2) {
-        m = (v >= creg) ? 1.f : 0.f;
-        *p = fmaxf(v, creg);
-      } else {
-        m = (v >= 0.f && v <= 1.f) ? 1.f : 0.f;
-        *p = fminf(fmaxf(v, 0.f), 1.f);
-      }
-    }
-    if (mask) mask[i] = m;
-  }
-}
-
-// T[k1][b] = sum_a h[a,b] exp(-2 pi i k1 a / M)      (dim-1 DFT of the corner-placed PSF)
-static __global__ void k_setup_psf_dim1(const float* __restrict__ h, int kh, int kw, int M, double2* T) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * kw) return;
-  const int k1 = idx / kw, b = idx % kw;
-  double re = 0.0, im = 0.0;
-  for (int a = 0; a < kh; ++a) {
-    double s, c;
-    sincospi(2.0 * ((long long)k1 * a % M) / M, &s, &c);
-    const double hv = (double)h[a + kh * b];
-    re += hv * c;
-    im -= hv * s;
-  }
-  T[idx] = make_double2(re, im);
-}
-
-// ctab[p2][p1] = C(k1,k2) / (M N),  C = 1 / (|Sigma|^2 + rho (4 sin^2(pi k2/N) + 4 sin^2(pi k1/M)))   ops.jl:119
-// ktab[p2][p1] = conj(K)(k1,k2) / (M N), K = Sigma exp(+2 pi i (k1 pd/M + k2 pr/N))                   SURVEY 8a-6
-// sig [p2][p1] = Sigma (only written when sig != nullptr; the backward needs it)
-// (p1,p2) are storage positions; (k1,k2) = pos_to_freq of them.
-static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int kw, int M, int N,
-                                      const float* __restrict__ rho_p, float* ctab, float2* ktab, float2* sig) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * N) return;
-  const int p1 = idx % M, p2 = idx / M;
-  const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
-  double sr = 1.0, si = 0.0;
-  if (kh > 0) {
-    sr = 0.0;
-    si = 0.0;
-    for (int b = 0; b < kw; ++b) {
-      double s, c;
-      sincospi(2.0 * ((long long)k2 * b % N) / N, &s, &c);
-      const double2 t = T[k1 * kw + b];
-      // t * (c - i s)
-      sr += t.x * c + t.y * s;
-      si += t.y * c - t.x * s;
-    }
-  }
-  const double rho = (double)*rho_p;
-  double s1, c1, s2, c2;
-  sincospi((double)k2 / N, &s2, &c2);
-  sincospi((double)k1 / M, &s1, &c1);
-  const double lap = 4.0 * s2 * s2 + 4.0 * s1 * s1;
-  const double inv_mn = 1.0 / ((double)M * (double)N);
-  const double C = 1.0 / (sr * sr + si * si + rho * lap);
-  ctab[idx] = (float)(C * inv_mn);
-  if (ktab) {
-    const int pd = kh > 0 ? (kh - 1) / 2 : 0, pr = kw > 0 ? (kw - 1) / 2 : 0;
-    double ps, pc;
-    const double ph = 2.0 * ((double)((long long)k1 * pd % M) / M + (double)((long long)k2 * pr % N) / N);
-    sincospi(ph, &ps, &pc);
-    // K = Sigma * (pc + i ps); store conj(K)/(MN)
-    const double kr = sr * pc - si * ps, ki = sr * ps + si * pc;
-    ktab[idx] = make_float2((float)(kr * inv_mn), (float)(-ki * inv_mn));
-  }
-  if (sig) sig[idx] = make_float2((float)sr, (float)si);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -306,16 +205,6 @@ ADMMTV_DI void dim1_fft_from_smem(float2* X, int ncols, ColPtr colptr, const flo
 //   MODE 1: src = xbar * act'(x_out); accumulates biasbar (deconv_admm.jl:222-224 pullback)
 //   MODE 2: src = already pair-packed spatial data (b = H^T y -> first x-update input)
 // ------------------------------------------------------------------------------------------
-struct PackArgs {
-  const float* src;    // MODE 0/1: (M,N,S) planes
-  const float2* src_packed;  // MODE 2: [Q][N][M] pair-packed spatial data
-  float2* packed_out;  // MODE 0: optional pair-packed copy of the input (b = y when h is empty)
-  const float* xout;   // MODE 1
-  float2* spec;        // [Q][N][M]
-  const float2* twM;
-  double* bias_acc;    // MODE 1, may be null
-  int N, S, act;
-};
 
 template <int LM, int MODE>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
@@ -360,14 +249,6 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
 //   MODE 0: pair-packed float2 out (b = H^T y)
 //   MODE 1: user-layout planes, + bias, activation           (deconv_admm.jl:222-224, ops.jl:175)
 // ------------------------------------------------------------------------------------------
-struct OutArgs {
-  const float2* spec;  // [Q][N][M]
-  float2* packed;      // MODE 0
-  float* planes;       // MODE 1: (M,N,S)
-  const float* bias;   // MODE 1, may be null
-  const float2* twM;
-  int N, S, act;
-};
 
 template <int LM, int MODE>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
@@ -411,17 +292,6 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
 // The only state written is v_k (z_k, u_k are recomputed from it), which is also the backward
 // checkpoint.
 // ------------------------------------------------------------------------------------------
-struct Dim1FwdArgs {
-  const float2* spec_in;
-  float2* spec_out;
-  const float2* bpk;
-  const float2* vprev;  // [Q][2][N][M]; ignored when !HAS_VPREV (v_0 = 0)
-  float2* vnew;         // [Q][2][N][M]
-  const float2* twM;
-  const float* lambda;
-  const float* rho;
-  int N;
-};
 
 struct Shrunk {
   float2 u, w;  // u = v - z ; w = z - u
@@ -570,17 +440,6 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
 //   forward FFT along dim 2 -> [save Z] -> [accumulate conj(Z) Z2] -> multiply by table ->
 //   inverse FFT along dim 2                                  (ops.jl:168  C .* rfft(...))
 // ------------------------------------------------------------------------------------------
-struct Dim2Args {
-  const float2* in;    // [Q][N][M]
-  float2* out;         // [Q][N][M]
-  const float* ctab;   // MUL 0: real table [N][M]
-  const float2* ktab;  // MUL 1/2: complex table [N][M] (2 = use its conjugate)
-  float2* zsave;       // SAVE_Z: [Q][N][M] full spectrum before the multiply
-  const float2* z2;    // ACC: second spectrum [Q][N][M]
-  float* gacc;         // ACC 1: float [N][M] += Re(conj(Z) Z2) ; ACC 2: float2 [N][M] += conj(Z) Z2
-  const float2* twN;
-  int M;
-};
 
 template <int LN>
 struct Dim2Cfg {

@@ -1,0 +1,107 @@
+// setup_kernels.cuh -- once-per-call table construction (included by admmtv_api.cu only).
+#pragma once
+
+#include "fft_core.cuh"
+#include "launch_macros.cuh"
+
+namespace admmtv {
+
+// ------------------------------------------------------------------------------------------
+// setup: twiddles, PSF spectrum, C / K tables (ops.jl:104-119 restated analytically)
+// ------------------------------------------------------------------------------------------
+// tw[n] = exp(-2 pi i n / L)
+static __global__ void k_setup_twiddles(float2* twM, int M, float2* twN, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < M) {
+    double s, c;
+    sincospi(2.0 * n / M, &s, &c);
+    twM[n] = make_float2((float)c, (float)(-s));
+  }
+  if (n < N) {
+    double s, c;
+    sincospi(2.0 * n / N, &s, &c);
+    twN[n] = make_float2((float)c, (float)(-s));
+  }
+}
+
+// clamp of deconv_admm.jl:216-219, in place; masks (1 = gradient passes) into `mask`:
+// mask[0] = lambda, mask[1] = rho, mask[2..2+kh*kw) = h
+static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int nh, float creg, int do_clamp, float* mask) {
+  for (int i = threadIdx.x; i < nh + 2; i += blockDim.x) {
+    float* p = i == 0 ? lambda : (i == 1 ? rho : h + (i - 2));
+    const float v = *p;
+    float m = 1.f;
+    if (do_clamp) {
+      if (i < 2) {
+        m = (v >= creg) ? 1.f : 0.f;
+        *p = fmaxf(v, creg);
+      } else {
+        m = (v >= 0.f && v <= 1.f) ? 1.f : 0.f;
+        *p = fminf(fmaxf(v, 0.f), 1.f);
+      }
+    }
+    if (mask) mask[i] = m;
+  }
+}
+
+// T[k1][b] = sum_a h[a,b] exp(-2 pi i k1 a / M)      (dim-1 DFT of the corner-placed PSF)
+static __global__ void k_setup_psf_dim1(const float* __restrict__ h, int kh, int kw, int M, double2* T) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * kw) return;
+  const int k1 = idx / kw, b = idx % kw;
+  double re = 0.0, im = 0.0;
+  for (int a = 0; a < kh; ++a) {
+    double s, c;
+    sincospi(2.0 * ((long long)k1 * a % M) / M, &s, &c);
+    const double hv = (double)h[a + kh * b];
+    re += hv * c;
+    im -= hv * s;
+  }
+  T[idx] = make_double2(re, im);
+}
+
+// ctab[p2][p1] = C(k1,k2) / (M N),  C = 1 / (|Sigma|^2 + rho (4 sin^2(pi k2/N) + 4 sin^2(pi k1/M)))   ops.jl:119
+// ktab[p2][p1] = conj(K)(k1,k2) / (M N), K = Sigma exp(+2 pi i (k1 pd/M + k2 pr/N))                   SURVEY 8a-6
+// sig [p2][p1] = Sigma (only written when sig != nullptr; the backward needs it)
+// (p1,p2) are storage positions; (k1,k2) = pos_to_freq of them.
+static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int kw, int M, int N,
+                                      const float* __restrict__ rho_p, float* ctab, float2* ktab, float2* sig) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int p1 = idx % M, p2 = idx / M;
+  const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
+  double sr = 1.0, si = 0.0;
+  if (kh > 0) {
+    sr = 0.0;
+    si = 0.0;
+    for (int b = 0; b < kw; ++b) {
+      double s, c;
+      sincospi(2.0 * ((long long)k2 * b % N) / N, &s, &c);
+      const double2 t = T[k1 * kw + b];
+      // t * (c - i s)
+      sr += t.x * c + t.y * s;
+      si += t.y * c - t.x * s;
+    }
+  }
+  const double rho = (double)*rho_p;
+  double s1, c1, s2, c2;
+  sincospi((double)k2 / N, &s2, &c2);
+  sincospi((double)k1 / M, &s1, &c1);
+  const double lap = 4.0 * s2 * s2 + 4.0 * s1 * s1;
+  const double inv_mn = 1.0 / ((double)M * (double)N);
+  const double C = 1.0 / (sr * sr + si * si + rho * lap);
+  ctab[idx] = (float)(C * inv_mn);
+  if (ktab) {
+    const int pd = kh > 0 ? (kh - 1) / 2 : 0, pr = kw > 0 ? (kw - 1) / 2 : 0;
+    double ps, pc;
+    const double ph = 2.0 * ((double)((long long)k1 * pd % M) / M + (double)((long long)k2 * pr % N) / N);
+    sincospi(ph, &ps, &pc);
+    // K = Sigma * (pc + i ps); store conj(K)/(MN)
+    const double kr = sr * pc - si * ps, ki = sr * ps + si * pc;
+    ktab[idx] = make_float2((float)(kr * inv_mn), (float)(-ki * inv_mn));
+  }
+  if (sig) sig[idx] = make_float2((float)sr, (float)si);
+}
+
+
+}  // namespace admmtv

@@ -1,0 +1,150 @@
+"""Host-side mirror of the reference operator ``tvd_fft`` (src/ops/ops.jl:181-188) over the C ABI.
+
+Array convention.  The reference's arrays are Julia ``(M,N,P,B)`` column-major.  A contiguous
+torch tensor of shape ``(B,P,N,M)`` has exactly that memory layout, so that is what this module
+takes and returns ("Julia index order reversed"); the PSF ``h`` (Julia ``(kh,kw,1,1)``) is a
+contiguous ``(kw,kh)`` / ``(1,1,kw,kh)`` tensor.  ``to_julia`` / ``from_julia`` convert to the
+``(M,N,P,B)``-indexed view the oracle uses.
+
+PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic happens in
+libadmmtv.so (hand-written sm_100a kernels).  There is no fallback: a missing library or a CPU
+tensor raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def to_julia(t: torch.Tensor) -> torch.Tensor:
+    """(B,P,N,M) -> (M,N,P,B)-indexed view (no copy)."""
+    return t.permute(*reversed(range(t.dim())))
+
+
+def from_julia(t: torch.Tensor) -> torch.Tensor:
+    """(M,N,P,B)-indexed array -> contiguous (B,P,N,M) tensor."""
+    return t.permute(*reversed(range(t.dim()))).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check_cuda_f32(name: str, t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the ADMM-TV path has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def _kernel_dims(h: Optional[torch.Tensor]):
+    if h is None or h.numel() == 0:
+        return 0, 0
+    if h.dim() == 4:
+        return int(h.shape[3]), int(h.shape[2])
+    if h.dim() == 2:
+        return int(h.shape[1]), int(h.shape[0])
+    raise ValueError("h must be (kw,kh) or (1,1,kw,kh)")
+
+
+def make_desc_for(y: torch.Tensor, h, iters: int, iso: bool, activation="identity", has_bias=False, flags=0,
+                  creg=0.0) -> _lib.Desc:
+    B, P, N, M = y.shape
+    kh, kw = _kernel_dims(h)
+    return _lib.make_desc(M, N, P, B, kh, kw, iters, iso, activation, has_bias, y.device.index or 0, flags, creg)
+
+
+def _alloc(nbytes: int, device) -> torch.Tensor:
+    # torch's caching allocator returns 512-byte aligned blocks
+    return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+
+
+class _AdmmFunction(torch.autograd.Function):
+    """forward = admmtv_forward, backward = admmtv_backward (the hand-written adjoint that replaces
+    Zygote's tape through ops.jl:166-174)."""
+
+    @staticmethod
+    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags):
+        lib = _lib.load()
+        _check_cuda_f32("y", y)
+        for n, t in (("lambda", lam), ("rho", rho)):
+            _check_cuda_f32(n, t)
+        if h is not None and h.numel() > 0:
+            _check_cuda_f32("h", h)
+        else:
+            h = None
+        if bias is not None:
+            _check_cuda_f32("bias", bias)
+        need_grad = any(t is not None and t.requires_grad for t in (y, lam, rho, h, bias))
+        d = make_desc_for(y, h, iters, iso, activation, bias is not None, flags, creg)
+        fwd_b, ck_b, _ = lib.workspace_bytes(d)
+        ws = _alloc(fwd_b, y.device)
+        ck = _alloc(ck_b, y.device) if need_grad else None
+        x = torch.empty_like(y)
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        # lam / rho / h are clamped IN PLACE (deconv_admm.jl:216-219 persists the clamp)
+        lib.forward(d, _ptr(y), _ptr(h), _ptr(lam), _ptr(rho), _ptr(bias), _ptr(x), _ptr(ws), _ptr(ck), stream)
+        ctx.desc = d
+        ctx.ck = ck
+        ctx.has_h = h is not None
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(y, lam, rho, h if h is not None else torch.empty(0, device=y.device), x)
+        ctx.mark_non_differentiable()
+        return x
+
+    @staticmethod
+    def backward(ctx, xbar):
+        lib = _lib.load()
+        y, lam, rho, h, x = ctx.saved_tensors
+        d = ctx.desc
+        xbar = xbar.contiguous()
+        _, _, bwd_b = lib.workspace_bytes(d)
+        ws = _alloc(bwd_b, y.device)
+        ybar = torch.empty_like(y)
+        hbar = torch.empty_like(h) if ctx.has_h else None
+        lbar = torch.empty_like(lam)
+        rbar = torch.empty_like(rho)
+        bbar = torch.empty(1, dtype=torch.float32, device=y.device) if ctx.has_bias else None
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        lib.backward(d, _ptr(xbar), _ptr(x), _ptr(y), _ptr(h) if ctx.has_h else None, _ptr(lam), _ptr(rho), _ptr(ctx.ck),
+                     _ptr(ybar), _ptr(hbar), _ptr(lbar), _ptr(rbar), _ptr(bbar), _ptr(ws), stream)
+        return ybar, lbar, rbar, hbar, bbar, None, None, None, None, None
+
+
+def admm_layer_call(y, lam, rho, h=None, bias=None, iters=100, iso=False, activation="identity", creg=0.0,
+                    nograd_repeat=False, clamp=True):
+    """The full layer call (d::Admm)(x), deconv_admm.jl:215-225, differentiable."""
+    flags = (0 if clamp else _lib.FLAG_NO_CLAMP) | (_lib.FLAG_NOGRAD_REPEAT if nograd_repeat else 0)
+    return _AdmmFunction.apply(y, lam, rho, h, bias, int(iters), bool(iso), activation, float(creg), flags)
+
+
+def tvd_fft(y, lam, rho, h=None, isotropic=False, maxit=100):
+    """tvd_fft(y, λ, ρ, h, isotropic, maxit) -- ops.jl:181: no clamp, no bias, no activation."""
+    return admm_layer_call(y, lam, rho, h, None, maxit, isotropic, "identity", 0.0, False, clamp=False)
+
+
+tvd_fft_gpu = tvd_fft  # ops.jl:99 (tests/admm_deconv_test.jl:76 calls it directly)
+
+
+def tvd_fft_host(y, lam: float, rho: float, h=None, isotropic=False, maxit=100):
+    """Host-buffer call (the reference's tvd_fft on a CPU Array): numpy in, numpy out, the copies
+    happen inside the C ABI (admmtv_forward_host).  Still runs on the GPU -- no CPU arithmetic."""
+    import numpy as np
+
+    lib = _lib.load()
+    y = np.ascontiguousarray(y, dtype=np.float32)  # (B,P,N,M)
+    B, P, N, M = y.shape
+    kh, kw = (0, 0) if h is None else (h.shape[-1], h.shape[-2])
+    d = _lib.make_desc(M, N, P, B, kh, kw, maxit, isotropic, "identity", False, 0, _lib.FLAG_NO_CLAMP, 0.0)
+    hb = None if h is None else np.ascontiguousarray(h, dtype=np.float32)
+    lb = np.array([lam], dtype=np.float32)
+    rb = np.array([rho], dtype=np.float32)
+    x = np.empty_like(y)
+    lib.forward_host(d, y.ctypes.data, None if hb is None else hb.ctypes.data, lb.ctypes.data, rb.ctypes.data, None,
+                     x.ctypes.data)
+    return x

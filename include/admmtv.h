@@ -104,6 +104,14 @@ int admmtv_backward(const admmtv_desc* desc, const float* xbar, const float* x_o
 int admmtv_forward_host(const admmtv_desc* desc, const float* y, float* h, float* lambda, float* rho,
                         const float* bias, float* x_out);
 
+/* Profiling twin of admmtv_forward: same work, but brackets every launch with CUDA events on
+ * `stream`, SYNCHRONISES, and returns milliseconds in ms_out[4] = {total, sum of the iterations'
+ * dim-2 kernels, sum of the iterations' dim-1 kernels, everything else}.  bench.py uses it for
+ * the per-kernel roofline; it is not part of the drop-in surface. */
+int admmtv_profile_forward(const admmtv_desc* desc, const float* y, float* h, float* lambda, float* rho,
+                           const float* bias, float* x_out, void* workspace, void* ckpt, void* stream,
+                           float* ms_out);
+
 /* Number of kernel launches one admmtv_forward / admmtv_backward call enqueues (bench bookkeeping). */
 int admmtv_forward_launches(const admmtv_desc* desc, int with_ckpt);
 int admmtv_backward_launches(const admmtv_desc* desc);

@@ -14,29 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from admm_deconv_b200 import _lib  # noqa: E402
 
-EMU_DIR = os.path.join(ROOT, "tests", "emu")
-EMU_SO = os.path.join(EMU_DIR, "_build", "libadmmtv_emu.so")
-CSRC = os.path.join(ROOT, "admm_deconv_b200", "csrc")
-
-
-def _sources():
-    out = [os.path.join(EMU_DIR, f) for f in ("cuda_emu.h", "cuda_emu.cpp")]
-    out += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".inc", ".h"))]
-    out.append(os.path.join(ROOT, "include", "admmtv.h"))
-    return out
+from admm_deconv_b200 import build as _build  # noqa: E402
 
 
 def build_emu(force: bool = False) -> str:
-    os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
-    if not force and os.path.exists(EMU_SO):
-        t = os.path.getmtime(EMU_SO)
-        if all(os.path.getmtime(s) <= t for s in _sources()):
-            return EMU_SO
-    cus = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
-    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-DADMMTV_EMU", "-I" + EMU_DIR, "-I" + CSRC,
-           "-x", "c++", *cus, os.path.join(EMU_DIR, "cuda_emu.cpp"), "-o", EMU_SO]
-    subprocess.run(cmd, check=True, cwd=ROOT)
-    return EMU_SO
+    return _build.build(emulate=True, force=force)
 
 
 _EMU = None

@@ -1,0 +1,69 @@
+"""CPU tests of the kernel SOURCES through the thread-per-CUDA-thread emulation (tests/emu/):
+same .cu/.cuh files, same C ABI, numpy buffers instead of device memory.  This checks the index
+arithmetic / halo / barrier logic of the kernels where no GPU exists; the parity tests proper are
+the -m gpu tests, which call the nvcc-built library."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import emu_harness as E
+from cases import make_case, rel_l2
+from oracle import admm_tv_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-5   # north_star: relative L2 <= 1e-5 (fp32) on the restored image
+
+
+def _run(emu, y, h, lam, rho, iso, K, **kw):
+    r = E.forward(emu, y.numpy(), lam, rho, None if h is None else h.numpy()[:, :, 0, 0], iso, K, **kw)
+    return torch.from_numpy(np.ascontiguousarray(r["x"])), r
+
+
+@pytest.mark.parametrize(
+    "M,N,P,B,kh,kw,K",
+    [(32, 32, 1, 2, 0, 0, 1), (32, 32, 1, 1, 0, 0, 4), (32, 64, 3, 1, 5, 4, 3), (64, 32, 1, 3, 3, 3, 5), (128, 32, 1, 2, 7, 7, 3)],
+)
+def test_emu_forward_aniso_vs_oracle(emu, M, N, P, B, kh, kw, K):
+    y, h, _ = make_case(M, N, P, B, kh, kw, 100 + M + N + K)
+    y = y.float().double()
+    h = None if h is None else h.float().double()
+    lam, rho = 0.05, 0.3
+    x, _ = _run(emu, y, h, lam, rho, False, K, flags=1)
+    lam_t = torch.tensor([lam], dtype=torch.float32).double()
+    rho_t = torch.tensor([rho], dtype=torch.float32).double()
+    xo = O.tvd_fft_cpu(y, lam_t, rho_t, h, False, K)
+    assert rel_l2(x, xo) < TOL
+
+
+@pytest.mark.parametrize("L", [256, 512, 1024, 2048, 4096])
+def test_emu_every_fft_length_both_dims(emu, L):
+    for (M, N) in ((L, 32), (32, L)):
+        y, h, _ = make_case(M, N, 2, 1, 3, 3, L)
+        y = y.float().double(); h = h.float().double()
+        x, _ = _run(emu, y, h, 0.05, 0.3, False, 2, flags=1)
+        xo = O.tvd_fft_fast(y, torch.tensor([0.05], dtype=torch.float32).double(),
+                            torch.tensor([0.3], dtype=torch.float32).double(), h, False, 2)
+        assert rel_l2(x, xo) < TOL, (M, N)
+
+
+def test_emu_golden_forward(emu):
+    for f in sorted(glob.glob(os.path.join(HERE, "golden", "aniso_*.npz"))):
+        d = np.load(f)
+        if d["y"].shape[0] > 64:
+            continue
+        h = d["h"][:, :, 0, 0] if "h" in d else None
+        r = E.forward(emu, d["y"], float(d["lam"]), float(d["rho"]), h, bool(d["iso"]), int(d["iters"]),
+                      act=str(d["act"]), bias=float(d["bias"]) if "bias" in d else None, creg=float(d["creg"]))
+        assert rel_l2(torch.from_numpy(np.ascontiguousarray(r["x"])), torch.from_numpy(d["x"])) < TOL, f
+
+
+def test_emu_clamp_is_persisted(emu):
+    y, h, _ = make_case(32, 32, 1, 2, 3, 3, 4)
+    hh = h.numpy()[:, :, 0, 0].copy()
+    hh[0, 0] = -0.5; hh[1, 1] = 1.7
+    r = E.forward(emu, y.numpy(), -1.0, 0.01, hh, False, 2, creg=0.05)
+    assert r["lam"][0] == np.float32(0.05) and r["rho"][0] == np.float32(0.05)     # deconv_admm.jl:216-217
+    assert r["h"][0, 0] == 0.0 and r["h"][1, 1] == 1.0                              # :219
