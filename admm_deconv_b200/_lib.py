@@ -26,6 +26,7 @@ SYMBOLS = (
     "admmtv_backward",
     "admmtv_forward_host",
     "admmtv_profile_forward",
+    "admmtv_ckpt_layout",
     "admmtv_forward_launches",
     "admmtv_backward_launches",
 )
@@ -71,6 +72,7 @@ class AdmmTvLib:
         L.admmtv_backward.argtypes = [C.POINTER(Desc)] + [vp] * 14
         L.admmtv_profile_forward.argtypes = [C.POINTER(Desc)] + [vp] * 10
         L.admmtv_forward_host.argtypes = [C.POINTER(Desc)] + [vp] * 6
+        L.admmtv_ckpt_layout.argtypes = [C.POINTER(Desc), C.POINTER(sz)]
         L.admmtv_forward_launches.argtypes = [C.POINTER(Desc), C.c_int]
         L.admmtv_backward_launches.argtypes = [C.POINTER(Desc)]
         for name in SYMBOLS:
@@ -109,6 +111,11 @@ class AdmmTvLib:
 
     def forward_host(self, d: Desc, y, h, lam, rho, bias, x_out):
         self._raise(self.lib.admmtv_forward_host(C.byref(d), y, h, lam, rho, bias, x_out))
+
+    def ckpt_layout(self, d: Desc):
+        out = (C.c_size_t * 4)()
+        self._raise(self.lib.admmtv_ckpt_layout(C.byref(d), out))
+        return tuple(out)
 
     def forward_launches(self, d: Desc, with_ckpt: bool) -> int:
         return self.lib.admmtv_forward_launches(C.byref(d), int(with_ckpt))

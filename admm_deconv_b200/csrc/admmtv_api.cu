@@ -102,6 +102,19 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
   }                                                                          \
   return ADMMTV_ERR_UNSUPPORTED;
 
+#define ADMMTV_SWITCH_LOG2_RC(val, NAME, RC, ...)                            \
+  switch (val) {                                                             \
+    case 5: { constexpr int NAME = 5; __VA_ARGS__ } break;                   \
+    case 6: { constexpr int NAME = 6; __VA_ARGS__ } break;                   \
+    case 7: { constexpr int NAME = 7; __VA_ARGS__ } break;                   \
+    case 8: { constexpr int NAME = 8; __VA_ARGS__ } break;                   \
+    case 9: { constexpr int NAME = 9; __VA_ARGS__ } break;                   \
+    case 10: { constexpr int NAME = 10; __VA_ARGS__ } break;                 \
+    case 11: { constexpr int NAME = 11; __VA_ARGS__ } break;                 \
+    case 12: { constexpr int NAME = 12; __VA_ARGS__ } break;                 \
+    default: RC = ADMMTV_ERR_UNSUPPORTED; break;                             \
+  }
+
 static int run_pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {
   ADMMTV_SWITCH_LOG2(g.LM, LM, { return Dim1Launch<LM>::pack_fft1(g, mode, a, st); })
 }
@@ -197,6 +210,20 @@ int admmtv_workspace_bytes(const admmtv_desc* d, size_t* fwd_bytes, size_t* ckpt
   if (fwd_bytes) *fwd_bytes = carve_fwd(g, nullptr).bytes;
   if (ckpt_bytes) *ckpt_bytes = carve_ckpt(g, nullptr).bytes;
   if (bwd_bytes) *bwd_bytes = carve_bwd(g, nullptr).bytes;
+  return ADMMTV_OK;
+}
+
+int admmtv_ckpt_layout(const admmtv_desc* d, size_t out[4]) {
+  int rc = admmtv_check(d);
+  if (rc) return rc;
+  if (!out) return ADMMTV_ERR_NULL;
+  const Geom g = geom(d);
+  unsigned char* base = reinterpret_cast<unsigned char*>(uintptr_t(256));
+  const Ckpt k = carve_ckpt(g, base);
+  out[0] = (size_t)(reinterpret_cast<unsigned char*>(k.mask) - base);
+  out[1] = (size_t)(reinterpret_cast<unsigned char*>(k.vck) - base);
+  out[2] = (size_t)(reinterpret_cast<unsigned char*>(k.zck) - base);
+  out[3] = k.bytes;
   return ADMMTV_OK;
 }
 

@@ -57,6 +57,22 @@ struct Dim2Args {
   int M;
 };
 
+struct Dim1BwdArgs {
+  const float2* spec_in;   // dim-1 spectrum of rbar_k
+  float2* spec_out;        // dim-1 spectrum of xbar_{k-1} (or of bbar_total for the last step)
+  const float2* vck;       // v_{k-1}        [Q][2][N][M] (checkpoint)
+  const float2* vbar_in;   // vbar_k         [Q][2][N][M] (ignored when !HAS_VBAR)
+  float2* vbar_out;        // vbar_{k-1}
+  float2* bbar;            // [Q][N][M] running sum of rbar_k
+  float* ybar;             // last step, empty PSF: (M,N,S) planes
+  const float2* twM;
+  const float* lambda;
+  const float* rho;
+  double* acc;             // [0] rhobar (direct term), [1] taubar
+  int N, S;
+  int first;               // 1: bbar is written, not accumulated (k = K)
+};
+
 // variants of k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)
 enum Dim2Variant {
   D2_C = 0,      // x C                                   (forward iteration, inference)
@@ -64,7 +80,8 @@ enum Dim2Variant {
   D2_KCONJ,      // x conj(K)/MN                          (b = H^T y)
   D2_C_ACCG,     // G += Re(conj(Z) Z2), then x C         (backward iteration)
   D2_FWDONLY,    // write the full 2-D spectrum, stop     (F y for the PSF-gradient correlation)
-  D2_K_ACCP      // P += conj(Z) Z2, then x K/MN          (ybar = H bbar and hbar correlation)
+  D2_K_ACCP,     // P += conj(Z) Z2, then x K/MN          (ybar = H bbar and hbar correlation)
+  D2_K           // x K/MN                                (ybar = H bbar only)
 };
 
 template <int LM>
@@ -72,6 +89,8 @@ struct Dim1Launch {
   static int pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st);
   static int out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st);
   static int fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st);
+  static int bwd(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
+  static int bwd_last(const Geom& g, int mode, const Dim1BwdArgs& a, cudaStream_t st);
 };
 template <int LN>
 struct Dim2Launch {

@@ -31,6 +31,7 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a, cudaStrea
     case D2_C_ACCG: return launch_k(k_dim2<LN, 0, false, 1, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_FWDONLY: return launch_k(k_dim2<LN, 0, false, 0, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_K_ACCP: return launch_k(k_dim2<LN, 2, false, 2, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_K: return launch_k(k_dim2<LN, 2, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
   }
   return -5;
 }

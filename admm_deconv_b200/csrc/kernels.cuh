@@ -18,6 +18,7 @@
 #include "fft_core.cuh"
 #include "args.cuh"
 #include "launch_macros.cuh"
+#include "reduce.cuh"
 
 namespace admmtv {
 
@@ -62,28 +63,6 @@ ADMMTV_DI void store_contig(float2* __restrict__ dst, const float2* a) {
 #pragma unroll
   for (int m = 0; m < R / 2; ++m)
     *reinterpret_cast<float4*>(dst + 2 * m) = make_float4(a[2 * m].x, a[2 * m].y, a[2 * m + 1].x, a[2 * m + 1].y);
-}
-
-ADMMTV_DI double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// sum over the block; result valid in thread 0.  All threads must call.
-ADMMTV_DI double block_sum(double v) {
-  __shared__ double red[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  double r = 0.0;
-  if (wid == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    r = lane < nw ? red[lane] : 0.0;
-    r = warp_sum(r);
-  }
-  return r;
 }
 
 ADMMTV_DI float act_apply(float v, int act) {

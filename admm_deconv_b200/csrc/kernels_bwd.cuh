@@ -1,0 +1,197 @@
+// kernels_bwd.cuh -- hand-written adjoint of the unrolled iterations (replaces Zygote's tape
+// through /root/reference/src/ops/ops.jl:166-174; recursion of SURVEY.md 8a-10 restated on the
+// single state v_k = D x_k + u_{k-1}).
+//
+// With e(v) = v - ST(v) (= u), g(v) = ST(v) - e(v) (= z - u) the forward recursion is
+//     x_k = A (b + rho D^T g(v_{k-1})),   v_k = D x_k + e(v_{k-1}),   A = F^-1 C F  (self-adjoint)
+// and one backward iteration k = K..2, given vbar_k (cotangent of v_k; vbar_K = 0), is
+//     xbar_k = [k==K] xbar + D^T vbar_k            (produced by the previous launch, in spectrum form)
+//     rbar_k = A xbar_k                            k_dim2 (also G += Re(conj(F xbar_k) F r_k))
+//     bbar  += rbar_k ;  gbar = rho D rbar_k ;  rhobar += <D rbar_k, g(v_{k-1})>
+//     q = 2 gbar - vbar_k ;  m = 1[|v_{k-1}| > tau]
+//     vbar_{k-1} = vbar_k - gbar + m q ;  taubar -= sum sign(v_{k-1}) m q
+//     xbar_{k-1} = D^T vbar_{k-1}  -> dim-1 FFT                                   k_dim1_bwd
+#pragma once
+
+#include "kernels.cuh"
+
+namespace admmtv {
+
+ADMMTV_DI float sgn_mask(float v, float tau) { return v > tau ? 1.f : (v < -tau ? -1.f : 0.f); }  // sign(v) * 1[|v|>tau]
+
+struct BwdPoint {
+  float2 vbar;  // vbar_{k-1}
+};
+// one (pixel, channel) of the adjoint update; d = (D rbar) component, v = v_{k-1}, eb = vbar_k.
+// Accumulates the scalar partial sums when `own`.
+ADMMTV_DI float2 bwd_point(float2 d, float2 v, float2 eb, float rho, float tau, bool own, double& racc, double& tacc) {
+  const float2 sm = make_float2(sgn_mask(v.x, tau), sgn_mask(v.y, tau));
+  const float2 gb = make_float2(rho * d.x, rho * d.y);
+  const float2 q = make_float2(2.f * gb.x - eb.x, 2.f * gb.y - eb.y);
+  const float2 m = make_float2(fabsf(sm.x), fabsf(sm.y));
+  if (own) {
+    const Shrunk s = shrink_aniso(v, tau);  // s.w = g(v)
+    racc += (double)(d.x * s.w.x) + (double)(d.y * s.w.y);
+    tacc -= (double)(sm.x * q.x) + (double)(sm.y * q.y);
+  }
+  return make_float2(eb.x - gb.x + m.x * q.x, eb.y - gb.y + m.y * q.y);
+}
+
+template <int LM, bool HAS_VBAR>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
+  using Cfg = Dim1Cfg<LM>;
+  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
+  ADMMTV_DYN_SMEM(float2, X);
+  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
+  const int j0 = blockIdx.x * CO;
+  const int nout = min(CO, N - j0);
+  const size_t plane = (size_t)N * M;
+  const float2* sin_q = A.spec_in + (size_t)q * plane;
+  auto jcol = [&](int c) {
+    int j = j0 - 1 + c;
+    if (j < 0) j += N;
+    if (j >= N) j -= N;
+    return j;
+  };
+  // 1. rbar_k for columns j0-1 .. j0+nout
+  dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+
+  const float rho = *A.rho;
+  const float tau = *A.lambda / rho;
+  const int i0 = tid * RPT;
+  const float2* v1 = A.vck + ((size_t)q * 2 + 0) * plane;
+  const float2* v2 = A.vck + ((size_t)q * 2 + 1) * plane;
+  const float2* e1 = A.vbar_in + ((size_t)q * 2 + 0) * plane;
+  const float2* e2 = A.vbar_in + ((size_t)q * 2 + 1) * plane;
+  float2* o1 = A.vbar_out + ((size_t)q * 2 + 0) * plane;
+  float2* o2 = A.vbar_out + ((size_t)q * 2 + 1) * plane;
+  float2* bq = A.bbar + (size_t)q * plane;
+  const float2 zero2 = make_float2(0.f, 0.f);
+  double racc = 0.0, tacc = 0.0;
+
+  float2 n1c[RPT];  // vbar_{k-1}, channel 1, current column
+  {
+    const int j = jcol(1);
+    float2 vv[RPT], ee[RPT];
+    load_rows<RPT>(v1 + (size_t)j * M + i0, vv);
+    if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)j * M + i0, ee);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const float2 d = csub(X[sidx<LM>(1, i0 + r)], X[sidx<LM>(0, i0 + r)]);
+      n1c[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, true, racc, tacc);
+    }
+    store_rows<RPT>(o1 + (size_t)j * M + i0, n1c);
+  }
+
+  for (int c = 1; c <= nout; c += CHUNK) {
+    float2 rr[CHUNK][RPT];
+#pragma unroll
+    for (int cc = 0; cc < CHUNK; ++cc) {
+      const int col = c + cc;
+      const int j = jcol(col), jn = jcol(col + 1);
+      float2 xc[RPT + 2];  // rbar rows i0-1 .. i0+RPT of column col
+      xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
+      xc[RPT + 1] = X[sidx<LM>(col, (i0 + RPT) & (M - 1))];
+
+      // bbar += rbar_k
+      {
+        float2 bb[RPT];
+        if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, bb);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) bb[r] = A.first ? xc[r + 1] : cadd(bb[r], xc[r + 1]);
+        store_rows<RPT>(bq + (size_t)j * M + i0, bb);
+      }
+      // channel 1 at column col+1
+      float2 n1n[RPT];
+      {
+        const bool own = col + 1 <= nout;
+        float2 vv[RPT], ee[RPT];
+        load_rows<RPT>(v1 + (size_t)jn * M + i0, vv);
+        if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)jn * M + i0, ee);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          const float2 d = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
+          n1n[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, own, racc, tacc);
+        }
+        if (own) store_rows<RPT>(o1 + (size_t)jn * M + i0, n1n);
+      }
+      // channel 2 at column col, rows i0 .. i0+RPT
+      float2 n2[RPT + 1];
+      {
+        float2 vv[RPT + 1], ee[RPT + 1];
+        load_rows<RPT>(v2 + (size_t)j * M + i0, vv);
+        vv[RPT] = v2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        if (HAS_VBAR) {
+          load_rows<RPT>(e2 + (size_t)j * M + i0, ee);
+          ee[RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        }
+#pragma unroll
+        for (int r = 0; r <= RPT; ++r) {
+          const float2 d = csub(xc[r + 1], xc[r]);
+          n2[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, r < RPT, racc, tacc);
+        }
+        store_rows<RPT>(o2 + (size_t)j * M + i0, n2);
+      }
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        rr[cc][r] = cadd(csub(n1c[r], n1n[r]), csub(n2[r], n2[r + 1]));  // xbar_{k-1} = D^T vbar_{k-1}
+        n1c[r] = n1n[r];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < CHUNK; ++cc)
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) X[sidx<LM>(c + cc - 1, i0 + r)] = rr[cc][r];
+  }
+  __syncthreads();
+
+  float2* sout_q = A.spec_out + (size_t)q * plane;
+  dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+
+  // scalar partial sums -> fp64 accumulators (one atomic pair per block)
+  const double rsum = block_sum(racc);
+  const double tsum = block_sum(tacc);
+  if (tid == 0) {
+    atomicAdd(A.acc + 0, rsum);
+    atomicAdd(A.acc + 1, tsum);
+  }
+}
+
+// Last backward iteration (k = 1): rbar_1 -> bbar_total = bbar + rbar_1, then either its dim-1
+// FFT (MODE 0, feeds ybar = H bbar and the PSF correlation) or, with an empty PSF, ybar = bbar
+// straight to the user layout (MODE 1).
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A) {
+  using Cfg = Dim1Cfg<LM>;
+  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
+  ADMMTV_DYN_SMEM(float2, X);
+  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
+  const int j0 = blockIdx.x * CO;
+  const int nout = min(CO, N - j0);
+  const size_t plane = (size_t)N * M;
+  const float2* sin_q = A.spec_in + (size_t)q * plane;
+  dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sin_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+  const float2* bq = A.bbar + (size_t)q * plane;
+  const bool has_b = 2 * q + 1 < A.S;
+  for (int e = tid; e < nout * M; e += NT) {
+    const int c = e / M, i = e % M;
+    const size_t off = (size_t)(j0 + c) * M + i;
+    float2 v = X[sidx<LM>(c, i)];
+    if (!A.first) v = cadd(v, bq[off]);
+    if (MODE == 0) X[sidx<LM>(c, i)] = v;
+    else {
+      A.ybar[(size_t)(2 * q) * plane + off] = v.x;
+      if (has_b) A.ybar[(size_t)(2 * q + 1) * plane + off] = v.y;
+    }
+  }
+  if (MODE == 0) {
+    __syncthreads();
+    float2* sout_q = A.spec_out + (size_t)q * plane;
+    dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+  }
+}
+
+}  // namespace admmtv

@@ -3,6 +3,7 @@
 
 #include "fft_core.cuh"
 #include "launch_macros.cuh"
+#include "reduce.cuh"
 
 namespace admmtv {
 
@@ -103,5 +104,85 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
   if (sig) sig[idx] = make_float2((float)sr, (float)si);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// parameter gradients from the spectral accumulators ("after the loop")
+//   Cbar = G/(MN) ; Sbar = -Cbar C^2 (cotangent of |Sigma|^2) ; rhobar += sum Sbar (|Lx|^2+|Ly|^2)
+//   hbar[a,b] = Re sum_k W[k] e^{+2 pi i (k1 a/M + k2 b/N)},
+//   W = 2 Sbar Sigma  +  (1/MN) P e^{-2 pi i (k1 pd/M + k2 pr/N)}   (spectral C path + spatial H^T y path)
+// ------------------------------------------------------------------------------------------
+static __global__ void k_grad_tables(const float* __restrict__ gacc, const float2* __restrict__ pacc,
+                                     const float* __restrict__ ctab, const float2* __restrict__ sig, int kh, int kw,
+                                     int M, int N, int use_spatial, double2* Wn, double* acc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // M*N is a multiple of the block size
+  const int p1 = idx % M, p2 = idx / M;
+  const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
+  const double mn = (double)M * (double)N;
+  const double C = (double)ctab[idx] * mn;
+  const double Sbar = -((double)gacc[idx] / mn) * C * C;
+  double s1, c1, s2, c2;
+  sincospi((double)k2 / N, &s2, &c2);
+  sincospi((double)k1 / M, &s1, &c1);
+  const double lap = 4.0 * s2 * s2 + 4.0 * s1 * s1;
+  const double tot = block_sum(Sbar * lap);
+  if (threadIdx.x == 0) atomicAdd(acc + 3, tot);
+  if (kh > 0) {
+    const float2 sg = sig[idx];
+    double wr = 2.0 * Sbar * (double)sg.x, wi = 2.0 * Sbar * (double)sg.y;
+    if (use_spatial) {
+      const int pd = (kh - 1) / 2, pr = (kw - 1) / 2;
+      double ps, pc;
+      sincospi(2.0 * ((double)((long long)k1 * pd % M) / M + (double)((long long)k2 * pr % N) / N), &ps, &pc);
+      const double pr_ = (double)pacc[idx].x / mn, pi_ = (double)pacc[idx].y / mn;
+      // P * (pc - i ps)
+      wr += pr_ * pc + pi_ * ps;
+      wi += pi_ * pc - pr_ * ps;
+    }
+    Wn[(size_t)k2 * M + k1] = make_double2(wr, wi);
+  }
+}
+
+// U[a][k2] = sum_k1 Wn[k2][k1] e^{+2 pi i k1 a / M}
+static __global__ void k_grad_h_dim1(const double2* __restrict__ Wn, int kh, int M, int N, double2* U) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kh * N) return;
+  const int a = idx / N, k2 = idx % N;
+  double re = 0.0, im = 0.0;
+  for (int k1 = 0; k1 < M; ++k1) {
+    double s, c;
+    sincospi(2.0 * ((long long)k1 * a % M) / M, &s, &c);
+    const double2 w = Wn[(size_t)k2 * M + k1];
+    re += w.x * c - w.y * s;
+    im += w.x * s + w.y * c;
+  }
+  U[idx] = make_double2(re, im);
+}
+
+// hbar[a,b] = mask * Re sum_k2 U[a][k2] e^{+2 pi i k2 b / N}; thread 0 also finalises the scalars:
+//   lambar = taubar / rho ; rhobar = direct + spectral - taubar lambda / rho^2   (tau = lambda ./ rho, ops.jl:102)
+// acc: [0] rho direct, [1] taubar, [2] biasbar, [3] rho spectral.  mask: [0] lambda, [1] rho, [2..] h.
+static __global__ void k_grad_finalize(const double2* __restrict__ U, int kh, int kw, int N, const float* __restrict__ mask,
+                                       const double* __restrict__ acc, const float* __restrict__ lambda,
+                                       const float* __restrict__ rho, float* hbar, float* lambar, float* rhobar,
+                                       float* biasbar) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kh * kw && hbar) {
+    const int a = t % kh, b = t / kh;
+    double re = 0.0;
+    for (int k2 = 0; k2 < N; ++k2) {
+      double s, c;
+      sincospi(2.0 * ((long long)k2 * b % N) / N, &s, &c);
+      const double2 u = U[a * N + k2];
+      re += u.x * c - u.y * s;
+    }
+    hbar[t] = (float)(re * (double)mask[2 + t]);
+  }
+  if (t == 0) {
+    const double lam = (double)*lambda, r = (double)*rho, tb = acc[1];
+    *lambar = (float)((double)mask[0] * tb / r);
+    *rhobar = (float)((double)mask[1] * (acc[0] + acc[3] - tb * lam / (r * r)));
+    if (biasbar) *biasbar = (float)acc[2];
+  }
+}
 
 }  // namespace admmtv

@@ -112,6 +112,12 @@ int admmtv_profile_forward(const admmtv_desc* desc, const float* y, float* h, fl
                            const float* bias, float* x_out, void* workspace, void* ckpt, void* stream,
                            float* ms_out);
 
+/* Byte offsets inside the checkpoint buffer (test / inspection use): out[0] = clamp masks
+ * (2 + kh*kw floats), out[1] = v_k slots, k = 1..iters-1, each float2 [Q][2][N][M] (Q = ceil(P*B/2)
+ * plane pairs: .x = plane 2q, .y = plane 2q+1; [2] = dim-2 / dim-1 difference channel),
+ * out[2] = F r_k slots, k = 1..iters, each float2 [Q][N][M], out[3] = isotropic per-pixel norms. */
+int admmtv_ckpt_layout(const admmtv_desc* desc, size_t out[4]);
+
 /* Number of kernel launches one admmtv_forward / admmtv_backward call enqueues (bench bookkeeping). */
 int admmtv_forward_launches(const admmtv_desc* desc, int with_ckpt);
 int admmtv_backward_launches(const admmtv_desc* desc);

@@ -1,0 +1,125 @@
+"""Teacher-forced fp64 backward  --  TEST INFRASTRUCTURE ONLY (see admm_tv_oracle.py header).
+
+End-to-end gradient parity between an fp32 and an fp64 run is limited by a handful of pixels whose
+|v| sits within rounding of the threshold tau and flips the shrinkage mask 1[|v|>tau]
+ -- not by arithmetic.  To test the backward ARITHMETIC at the 1e-5
+level this module evaluates the exact adjoint recursion of SURVEY.md 8a-10 in fp64 while replaying
+the per-iteration states v_k = D x_k + u_{k-1} that the device forward saved (its checkpoint), so
+both sides use identical masks.  The recursion itself is verified against torch.autograd through
+the literal restatement (tests/test_oracle.py::test_teacher_forced_equals_autograd...).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import admm_tv_oracle as O
+
+DT = torch.float64
+
+
+def _full_tables(M, N, h, rho):
+    k1 = torch.arange(M, dtype=DT).reshape(-1, 1)
+    k2 = torch.arange(N, dtype=DT).reshape(1, -1)
+    L = 4 * torch.sin(math.pi * k2 / N) ** 2 + 4 * torch.sin(math.pi * k1 / M) ** 2
+    if h is None or h.numel() == 0:
+        Sig = torch.ones(M, N, dtype=torch.complex128)
+    else:
+        hh = torch.zeros(M, N, dtype=DT)
+        hh[: h.shape[0], : h.shape[1]] = h[:, :, 0, 0]
+        Sig = torch.fft.fftn(hh)
+    C = 1.0 / (Sig.abs() ** 2 + rho * L)
+    return Sig, L, C
+
+
+def forward_states(y, lam, rho, h, iso, K):
+    """fp64 forward in v-state form; returns (x_K, [v_1..v_{K-1}] as (v1, v2) pairs)."""
+    st: list = []
+    x = O.tvd_fft_fast(y, lam, rho, h, iso, K, states=st)
+    return x, [(s[1], s[2]) for s in st[:-1]]
+
+
+def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, torch.Tensor]], nograd_repeat=False):
+    """Exact adjoint given the states v_1..v_{K-1} (each (M,N,P,B) fp64 pair).  Returns
+    dict(x=ybar, lam, rho, weight)."""
+    M, N, P, B = y.shape
+    tau = lam / rho
+    Sig, L, C = _full_tables(M, N, h, rho)
+    C4 = C.reshape(M, N, 1, 1)
+    fft2 = lambda t: torch.fft.fftn(t, dim=(0, 1))
+    ifft2 = lambda T: torch.fft.ifftn(T, dim=(0, 1)).real
+    b = y if h is None or h.numel() == 0 else O.Ht_roll(y, h)
+
+    def shrink(v1, v2):
+        if iso:
+            n = torch.sqrt(torch.sum(v1 * v1 + v2 * v2, dim=(2, 3), keepdim=True))
+            s = torch.where(n > 0, torch.clamp(1 - tau / n, min=0), torch.zeros_like(n))
+            return s * v1, s * v2, n, s
+        return O.ST(v1, tau), O.ST(v2, tau), None, None
+
+    zero = torch.zeros_like(y)
+    vs = [(zero, zero)] + list(v_states)          # vs[k] = v_k, v_0 = 0
+    vb1, vb2 = zero, zero
+    G = torch.zeros(M, N, dtype=DT)
+    bbar = torch.zeros_like(y)
+    rhobar = torch.zeros((), dtype=DT)
+    taubar = torch.zeros((), dtype=DT)
+    for k in range(K, 0, -1):
+        xk = (xbar if k == K else 0) + (O.Dt_roll(vb1, vb2) if k < K else 0)
+        v1, v2 = vs[k - 1]
+        z1, z2, n, s = shrink(v1, v2)
+        g1, g2 = 2 * z1 - v1, 2 * z2 - v2
+        r = b + rho * O.Dt_roll(g1, g2)
+        Zb = fft2(xk)
+        G += (Zb.conj() * fft2(r)).real.sum(dim=(2, 3))
+        rb = ifft2(C4 * Zb)
+        bbar = bbar + rb
+        if k == 1:
+            break
+        d1, d2 = O.D_roll(rb)
+        rhobar = rhobar + (d1 * g1).sum() + (d2 * g2).sum()
+        gb1, gb2 = rho * d1, rho * d2
+        q1, q2 = 2 * gb1 - vb1, 2 * gb2 - vb2
+        if iso:
+            ip = torch.sum(q1 * v1 + q2 * v2, dim=(2, 3), keepdim=True)
+            act = n > tau
+            coef = torch.where(act, tau * ip / n ** 3, torch.zeros_like(n))
+            nv1 = vb1 - gb1 + s * q1 + coef * v1
+            nv2 = vb2 - gb2 + s * q2 + coef * v2
+            taubar = taubar - torch.where(act, ip / n, torch.zeros_like(n)).sum()
+        else:
+            m1 = (v1.abs() > tau).to(DT)
+            m2 = (v2.abs() > tau).to(DT)
+            nv1 = vb1 - gb1 + m1 * q1
+            nv2 = vb2 - gb2 + m2 * q2
+            taubar = taubar - (torch.sign(v1) * m1 * q1).sum() - (torch.sign(v2) * m2 * q2).sum()
+        vb1, vb2 = nv1, nv2
+    Sbar = -(G / (M * N)) * C * C
+    rhobar = rhobar + (Sbar * L).sum()
+    out = {"lam": (taubar / rho).reshape(1), "rho": (rhobar - taubar * lam / rho ** 2).reshape(1)}
+    if h is None or h.numel() == 0:
+        out["x"] = bbar
+        out["weight"] = None
+        return out
+    kh, kw = h.shape[:2]
+    pd, pr = (kh - 1) // 2, (kw - 1) // 2
+    out["x"] = O.H_forward(bbar, h)
+    Fh = torch.fft.ifftn(2 * Sbar * Sig) * (M * N)
+    hb = torch.zeros(kh, kw, dtype=DT)
+    for a in range(kh):
+        for c in range(kw):
+            hb[a, c] = Fh[a, c].real
+            if not nograd_repeat:
+                hb[a, c] += (bbar * torch.roll(y, shifts=(-(a - pd), -(c - pr)), dims=(0, 1))).sum()
+    out["weight"] = hb.reshape(kh, kw, 1, 1)
+    return out
+
+
+def count_mask_flips(v_a, v_b, tau: float) -> int:
+    """How many shrinkage decisions differ between two state lists (aniso)."""
+    n = 0
+    for (a1, a2), (b1, b2) in zip(v_a, v_b):
+        n += int(((a1.abs() > tau) != (b1.abs() > tau)).sum()) + int(((a2.abs() > tau) != (b2.abs() > tau)).sum())
+    return n

@@ -64,3 +64,20 @@ def forward(lib, y, lam, rho, h=None, iso=False, iters=10, act="identity", bias=
     lib.forward(d, ptr(y), None if hbuf is None else ptr(hbuf), ptr(lbuf), ptr(rbuf),
                 None if bbuf is None else ptr(bbuf), ptr(x), ptr(ws), None if ck is None else ptr(ck), None)
     return dict(x=x, lam=lbuf, rho=rbuf, h=hbuf, ckpt=ck, desc=d, y=y, bias=bbuf, bwd_bytes=bwd_b)
+
+
+def backward(lib, fwd, xbar):
+    """Runs admmtv_backward on the buffers a `forward(..., want_ckpt=True)` call returned."""
+    d = fwd["desc"]
+    M, N, P, B = d.M, d.N, d.P, d.B
+    xbar = f32(xbar)
+    ws = aligned_bytes(fwd["bwd_bytes"])
+    ybar = np.zeros((M, N, P, B), dtype=np.float32, order="F")
+    hbar = None if fwd["h"] is None else np.zeros_like(fwd["h"])
+    lbar = np.zeros(1, dtype=np.float32)
+    rbar = np.zeros(1, dtype=np.float32)
+    bbar = None if fwd["bias"] is None else np.zeros(1, dtype=np.float32)
+    lib.backward(d, ptr(xbar), ptr(fwd["x"]), ptr(fwd["y"]), None if fwd["h"] is None else ptr(fwd["h"]), ptr(fwd["lam"]),
+                 ptr(fwd["rho"]), ptr(fwd["ckpt"]), ptr(ybar), None if hbar is None else ptr(hbar), ptr(lbar), ptr(rbar),
+                 None if bbar is None else ptr(bbar), ptr(ws), None)
+    return dict(ybar=ybar, hbar=hbar, lambar=lbar, rhobar=rbar, biasbar=bbar)

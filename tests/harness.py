@@ -1,0 +1,120 @@
+"""TEST INFRASTRUCTURE: one driver for the C ABI with two backends --
+  EmuBackend : the g++ emulation build of the kernel sources, numpy buffers (CPU suite)
+  GpuBackend : the nvcc-built product library, torch CUDA buffers (-m gpu suite)
+Both return numpy arrays in the Julia (M,N,P,B) index order."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from admm_deconv_b200 import _lib
+
+
+def f32(a) -> np.ndarray:
+    return np.asfortranarray(np.asarray(a, dtype=np.float32))
+
+
+class _Buf:
+    """A typed buffer living on the backend's 'device'."""
+
+    def __init__(self, be, arr: np.ndarray):
+        self.be, self.shape, self.dtype = be, arr.shape, arr.dtype
+        flat = np.ascontiguousarray(arr.reshape(-1, order="F"))
+        if be.gpu:
+            self.t = torch.from_numpy(flat.view(np.uint8).copy()).cuda()
+            self.ptr = self.t.data_ptr()
+        else:
+            raw = np.zeros(flat.nbytes + 256, dtype=np.uint8)
+            off = (-raw.ctypes.data) % 256
+            self.t = raw[off:off + flat.nbytes]
+            self.t[:] = flat.view(np.uint8)
+            self.ptr = self.t.ctypes.data
+
+    def get(self) -> np.ndarray:
+        host = self.t.cpu().numpy() if self.be.gpu else self.t
+        return host.view(self.dtype).reshape(self.shape, order="F").copy()
+
+
+class Backend:
+    gpu = False
+
+    def __init__(self, lib):
+        self.lib = lib
+
+    def buf(self, arr):
+        return _Buf(self, np.asarray(arr))
+
+    def zeros(self, shape, dtype=np.float32):
+        return _Buf(self, np.zeros(shape, dtype=dtype))
+
+    def sync(self):
+        if self.gpu:
+            torch.cuda.synchronize()
+
+    def stream(self):
+        return torch.cuda.current_stream().cuda_stream if self.gpu else None
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, y, lam, rho, h=None, iso=False, iters=10, act="identity", bias=None, creg=0.0, flags=0,
+                want_ckpt=False):
+        y = f32(y)
+        M, N, P, B = y.shape
+        kh, kw = (0, 0) if h is None else (h.shape[0], h.shape[1])
+        d = _lib.make_desc(M, N, P, B, kh, kw, iters, iso, act, bias is not None, 0, flags, creg)
+        fwd_b, ck_b, bwd_b = self.lib.workspace_bytes(d)
+        r = dict(desc=d, bwd_bytes=bwd_b)
+        r["y"] = self.buf(y)
+        r["h"] = None if h is None else self.buf(f32(np.asarray(h).reshape(kh, kw)))
+        r["lam"] = self.buf(np.array([lam], dtype=np.float32))
+        r["rho"] = self.buf(np.array([rho], dtype=np.float32))
+        r["bias"] = None if bias is None else self.buf(np.array([bias], dtype=np.float32))
+        r["x"] = self.zeros((M, N, P, B))
+        ws = self.zeros((fwd_b,), np.uint8)
+        r["ckpt"] = self.zeros((ck_b,), np.uint8) if want_ckpt else None
+        p = lambda b: None if b is None else b.ptr
+        self.lib.forward(d, p(r["y"]), p(r["h"]), p(r["lam"]), p(r["rho"]), p(r["bias"]), p(r["x"]), ws.ptr, p(r["ckpt"]),
+                         self.stream())
+        self.sync()
+        return r
+
+    def backward(self, fwd, xbar):
+        d = fwd["desc"]
+        M, N, P, B = d.M, d.N, d.P, d.B
+        xb = self.buf(f32(xbar))
+        ws = self.zeros((fwd["bwd_bytes"],), np.uint8)
+        out = dict(ybar=self.zeros((M, N, P, B)), hbar=None if fwd["h"] is None else self.zeros(fwd["h"].shape),
+                   lambar=self.zeros((1,)), rhobar=self.zeros((1,)), biasbar=None if fwd["bias"] is None else self.zeros((1,)))
+        p = lambda b: None if b is None else b.ptr
+        self.lib.backward(d, xb.ptr, fwd["x"].ptr, fwd["y"].ptr, p(fwd["h"]), fwd["lam"].ptr, fwd["rho"].ptr, fwd["ckpt"].ptr,
+                          out["ybar"].ptr, p(out["hbar"]), out["lambar"].ptr, out["rhobar"].ptr, p(out["biasbar"]), ws.ptr,
+                          self.stream())
+        self.sync()
+        return {k: (None if v is None else v.get()) for k, v in out.items()}
+
+    def ckpt_states(self, fwd):
+        """[(v1_k, v2_k)] for k = 1..K-1 as fp64 torch (M,N,P,B) arrays, read from the checkpoint."""
+        d = fwd["desc"]
+        M, N, P, B, K = d.M, d.N, d.P, d.B, d.iters
+        S = P * B
+        Q = (S + 1) // 2
+        off = self.lib.ckpt_layout(d)
+        raw = fwd["ckpt"].get()
+        n = (K - 1) * Q * 2 * N * M * 2
+        v = raw[off[1]:off[1] + 4 * n].view(np.float32).reshape(K - 1, Q, 2, N, M, 2)
+        states = []
+        for k in range(K - 1):
+            chans = []
+            for ch in range(2):
+                a = v[k, :, ch]                      # (Q, N, M, 2)
+                planes = np.transpose(a, (2, 1, 0, 3)).reshape(M, N, 2 * Q)[:, :, :S]   # plane index = 2q + c
+                chans.append(torch.from_numpy(planes.reshape(M, N, P, B, order="F").astype(np.float64)))
+            states.append((chans[0], chans[1]))
+        return states
+
+
+class EmuBackend(Backend):
+    gpu = False
+
+
+class GpuBackend(Backend):
+    gpu = True

@@ -1,0 +1,84 @@
+"""Shared parity checks (backend-agnostic: see harness.py)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from cases import rel_l2
+from oracle import admm_tv_oracle as O
+from oracle import teacher_forced as TF
+
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).double()
+
+
+def act_grad(out: torch.Tensor, act: str) -> torch.Tensor:
+    if act == "relu":
+        return (out > 0).double()
+    if act == "relu6":
+        return ((out > 0) & (out < 6)).double()
+    if act == "relu1":
+        return ((out > 0) & (out < 1)).double()
+    return torch.ones_like(out)
+
+
+def close(a: float, b: float, rtol: float, floor: float = 1e-3) -> bool:
+    return abs(a - b) <= rtol * max(abs(b), floor)
+
+
+def check_forward(be, y, h, lam, rho, iso, K, tol=1e-5, fast=True, **kw):
+    """Device forward vs the fp64 oracle on fp32-rounded inputs.  Returns the rel-L2 error."""
+    y = y.float().double()
+    h = None if h is None else h.float().double()
+    r = be.forward(y.numpy(), lam, rho, None if h is None else h.numpy()[:, :, 0, 0], iso, K, flags=1, **kw)
+    lt = torch.tensor([lam], dtype=torch.float32).double()
+    rt = torch.tensor([rho], dtype=torch.float32).double()
+    xo = (O.tvd_fft_fast if fast else O.tvd_fft_cpu)(y, lt, rt, h, iso, K)
+    err = rel_l2(T(r["x"].get()), xo)
+    assert err < tol, err
+    return err
+
+
+def check_backward(be, y, h, lam, rho, iso, K, xbar, act="identity", bias=None, creg=0.0, flags=0,
+                   tol=1e-5, tol_scalar=1e-4, tol_e2e=None):
+    """Device forward+backward vs (1) the teacher-forced fp64 adjoint replaying the device's own
+    checkpointed states (arithmetic parity, tol) and optionally (2) end-to-end fp64 autograd (tol_e2e).
+    Returns a dict of the measured errors and the number of threshold-mask flips."""
+    y = y.float().double()
+    h = None if h is None else h.float().double()
+    xbar = xbar.float().double()
+    f = be.forward(y.numpy(), lam, rho, None if h is None else h.numpy()[:, :, 0, 0], iso, K, act=act, bias=bias, creg=creg,
+                   flags=flags, want_ckpt=True)
+    g = be.backward(f, xbar.numpy())
+    # parameters as the device left them (clamped, fp32)
+    lt = T(f["lam"].get()); rt = T(f["rho"].get())
+    hc = None if h is None else T(f["h"].get()).reshape(h.shape)
+    x_dev = T(f["x"].get())
+    states = be.ckpt_states(f)
+    xbar_eff = xbar * act_grad(x_dev, act)
+    tf = TF.backward(xbar_eff, y, lt, rt, hc, iso, K, states, nograd_repeat=bool(flags & 2))
+    res = {}
+    res["ybar"] = rel_l2(T(g["ybar"]), tf["x"])
+    assert res["ybar"] < tol, ("ybar", res["ybar"])
+    if K > 1:
+        res["lam"] = abs(float(g["lambar"][0]) - float(tf["lam"])) / max(abs(float(tf["lam"])), 1e-3)
+        assert res["lam"] < tol_scalar, ("lambar", float(g["lambar"][0]), float(tf["lam"]))
+    res["rho"] = abs(float(g["rhobar"][0]) - float(tf["rho"])) / max(abs(float(tf["rho"])), 1e-3)
+    assert res["rho"] < tol_scalar, ("rhobar", float(g["rhobar"][0]), float(tf["rho"]))
+    if h is not None:
+        # clamp gate (deconv_admm.jl:219): gradient only where 0 <= h <= 1 before the clamp
+        gate = ((h >= 0) & (h <= 1)).double() if not (flags & 1) else torch.ones_like(h)
+        res["hbar"] = rel_l2(T(g["hbar"]).reshape(h.shape), tf["weight"] * gate)
+        assert res["hbar"] < tol, ("hbar", res["hbar"])
+    if bias is not None:
+        assert close(float(g["biasbar"][0]), float(xbar_eff.sum()), 1e-5)
+    # mask flips of the device forward relative to the fp64 forward, and end-to-end agreement
+    _, st64 = TF.forward_states(y, lt, rt, hc, iso, K)
+    if not iso:
+        res["flips"] = TF.count_mask_flips(states, st64, float(lt / rt))
+    if tol_e2e is not None:
+        bt = None if bias is None else torch.tensor([bias], dtype=torch.float32).double()
+        _, go = O.layer_grads(y, xbar, None if h is None else T(f["h"].get()).reshape(h.shape), bt, lt, rt, K, iso, 0.0, act,
+                              nograd_repeat=bool(flags & 2))
+        res["ybar_e2e"] = rel_l2(T(g["ybar"]), go["x"])
+        assert res["ybar_e2e"] < tol_e2e, ("ybar end-to-end", res["ybar_e2e"], res.get("flips"))
+    return res

@@ -1,0 +1,63 @@
+"""CPU tests of the backward kernel sources through the emulation (see test_emu_forward.py).
+Arithmetic parity is checked teacher-forced (the fp64 adjoint replays the checkpointed states of
+the emulated forward); end-to-end agreement with fp64 autograd is checked where no mask flips."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+from cases import make_case, rel_l2
+from parity import T, check_backward
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def be(emu):
+    return harness.EmuBackend(emu)
+
+
+@pytest.mark.parametrize(
+    "M,N,P,B,kh,kw,K,act,bias,flags",
+    [
+        (32, 32, 1, 2, 0, 0, 1, "identity", None, 0),
+        (32, 32, 1, 2, 0, 0, 3, "identity", None, 0),
+        (32, 64, 3, 1, 5, 4, 4, "identity", None, 0),
+        (64, 32, 1, 2, 3, 3, 5, "relu1", 0.02, 0),
+        (32, 32, 2, 1, 3, 3, 3, "relu", None, 2),       # train.jl:10 @nograd repeat variant
+    ],
+)
+def test_emu_backward_aniso(be, M, N, P, B, kh, kw, K, act, bias, flags):
+    y, h, _ = make_case(M, N, P, B, kh, kw, 7 + M + K)
+    xbar = torch.from_numpy(np.random.default_rng(K).standard_normal((M, N, P, B)))
+    check_backward(be, y, h, 0.05, 0.3, False, K, xbar, act, bias, 0.0, flags, tol=1e-5, tol_scalar=1e-4, tol_e2e=1e-3)
+
+
+def test_emu_clamp_masks_gate_gradients(be):
+    """deconv_admm.jl:216-219 under Zygote: clamp passes the gradient only inside the range."""
+    y, h, _ = make_case(32, 32, 1, 2, 3, 3, 4)
+    hh = h.clone()
+    hh[0, 0] = -0.5
+    hh[1, 1] = 1.7
+    xbar = torch.from_numpy(np.random.default_rng(0).standard_normal((32, 32, 1, 2)))
+    f = be.forward(y.numpy(), 0.01, 0.3, hh.numpy()[:, :, 0, 0], False, 3, creg=0.05, want_ckpt=True)   # lambda < creg
+    g = be.backward(f, xbar.numpy())
+    assert f["lam"].get()[0] == np.float32(0.05)
+    assert g["lambar"][0] == 0.0 and g["rhobar"][0] != 0.0
+    assert g["hbar"][0, 0] == 0.0 and g["hbar"][1, 1] == 0.0 and g["hbar"][2, 2] != 0.0
+    check_backward(be, y, hh, 0.2, 0.3, False, 3, xbar, creg=0.05)
+
+
+def test_emu_golden_backward(be):
+    for f in sorted(glob.glob(os.path.join(HERE, "golden", "aniso_*.npz"))):
+        d = np.load(f)
+        if d["y"].shape[0] > 64:
+            continue
+        y = torch.from_numpy(d["y"]).double()
+        h = torch.from_numpy(d["h"]).double() if "h" in d else None
+        r = check_backward(be, y, h, float(d["lam"]), float(d["rho"]), False, int(d["iters"]), torch.from_numpy(d["xbar"]),
+                           str(d["act"]), float(d["bias"]) if "bias" in d else None, float(d["creg"]), tol=1e-5, tol_scalar=1e-4)
+        print(os.path.basename(f), r)

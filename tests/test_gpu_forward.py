@@ -131,9 +131,9 @@ def test_planes_are_independent_and_batch_order_equivariant():
     perm = torch.tensor([3, 0, 4, 1, 2], device=d0)
     shuf = A.tvd_fft(y[perm].contiguous(), lam, rho, h, False, 8)
     # pairing of planes changes (odd S = 15), results must not
-    assert rel_l2(shuf.cpu(), full[perm].cpu()) < 2e-6
+    assert rel_l2(shuf.cpu(), full[perm].cpu()) < 1e-5
     one = A.tvd_fft(y[2:3].contiguous(), lam, rho, h, False, 8)
-    assert rel_l2(one.cpu(), full[2:3].cpu()) < 2e-6
+    assert rel_l2(one.cpu(), full[2:3].cpu()) < 1e-5
 
 
 def test_host_buffer_entry_point():

@@ -131,3 +131,23 @@ def test_golden_vectors_match_oracle():
         bias = _t(float(d["bias"])) if "bias" in d else None
         out, _ = O.admm_layer(y, h, bias, lam, rho, int(d["iters"]), bool(d["iso"]), float(d["creg"]), str(d["act"]))
         assert rel_l2(out, torch.from_numpy(d["x"])) < 1e-12, f
+
+
+@pytest.mark.parametrize("iso", [False, True])
+@pytest.mark.parametrize("kh,kw", [(0, 0), (5, 4)])
+def test_teacher_forced_recursion_equals_autograd(iso, kh, kw):
+    """The hand-derived adjoint (oracle/teacher_forced.py) fed its own fp64 states
+    reproduces torch.autograd through the literal restatement to round-off."""
+    from oracle import teacher_forced as TF
+    y, h, _ = make_case(16, 32, 3, 2, kh, kw, 12)
+    lam, rho = _t(0.03), _t(0.4)
+    xbar = torch.randn(16, 32, 3, 2, dtype=DT)
+    K = 6
+    _, g = O.layer_grads(y, xbar, h, None, lam, rho, K, iso)
+    x, vs = TF.forward_states(y, lam, rho, h, iso, K)
+    t = TF.backward(xbar, y, lam, rho, h, iso, K, vs)
+    assert rel_l2(t["x"], g["x"]) < 1e-12
+    assert abs(float(t["lam"]) - float(g["lam"])) < 1e-9 * max(1, abs(float(g["lam"])))
+    assert abs(float(t["rho"]) - float(g["rho"])) < 1e-9 * max(1, abs(float(g["rho"])))
+    if h is not None:
+        assert rel_l2(t["weight"], g["weight"]) < 1e-12
