@@ -50,8 +50,15 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(emulate: bool = False, force: bool = False, jobs: int | None = None, verbose: bool = False) -> str:
+def build(emulate: bool = False, force: bool = False, jobs: int | None = None, verbose: bool = False,
+          tag: str | None = None, defines: tuple = (), sizes: tuple | None = None) -> str:
+    """tag/defines/sizes: tuning variants (tools/variants.py) -- libadmmtv_<tag>.so built with extra -D flags,
+    optionally only for some FFT lengths (other lengths then return ADMMTV_ERR_UNSUPPORTED at link... they are
+    compiled as stubs by ADMMTV_STUB)."""
     objdir, lib = (EMU_OBJ, EMU_LIB) if emulate else (OBJ, LIB)
+    if tag:
+        objdir = os.path.join(CSRC, "_obj_" + tag)
+        lib = os.path.join(HERE, f"libadmmtv_{tag}.so")
     os.makedirs(objdir, exist_ok=True)
     deps = _deps() + ([os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "cuda_emu.cpp")] if emulate else [])
     jobs = jobs or os.cpu_count() or 4
@@ -68,6 +75,9 @@ def build(emulate: bool = False, force: bool = False, jobs: int | None = None, v
             cmd = ["nvcc", *NVCC_FLAGS, "-I" + CSRC]
         if define is not None:
             cmd.append(f"-DADMMTV_INST={define}")
+            if sizes is not None and define not in sizes:
+                cmd.append("-DADMMTV_STUB")
+        cmd += [f"-D{x}" for x in defines]
         cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[stem] = r.stderr
@@ -94,7 +104,7 @@ def build(emulate: bool = False, force: bool = False, jobs: int | None = None, v
     if verbose:
         for k, v in sorted(logs.items()):
             sys.stderr.write(f"--- {k}\n{v}\n")
-    if not emulate:
+    if not emulate and logs:
         with open(os.path.join(objdir, "ptxas.log"), "w") as f:
             for k, v in sorted(logs.items()):
                 f.write(f"--- {k}\n{v}\n")

@@ -1,5 +1,16 @@
 // inst_dim1.cu -- instantiates every dim-1 kernel for ONE FFT length M = 2^ADMMTV_INST.
 // Compiled once per supported length (see admm_deconv_b200/build.py).
+#ifdef ADMMTV_STUB
+#include "args.cuh"
+namespace admmtv {
+constexpr int LM_ = ADMMTV_INST;
+template <> int Dim1Launch<LM_>::pack_fft1(const Geom&, int, const PackArgs&, cudaStream_t) { return -3; }
+template <> int Dim1Launch<LM_>::out(const Geom&, int, const OutArgs&, cudaStream_t) { return -3; }
+template <> int Dim1Launch<LM_>::fwd(const Geom&, bool, const Dim1FwdArgs&, cudaStream_t) { return -3; }
+template <> int Dim1Launch<LM_>::bwd(const Geom&, bool, const Dim1BwdArgs&, cudaStream_t) { return -3; }
+template <> int Dim1Launch<LM_>::bwd_last(const Geom&, int, const Dim1BwdArgs&, cudaStream_t) { return -3; }
+}
+#else
 #include "kernels.cuh"
 #include "kernels_bwd.cuh"
 
@@ -43,3 +54,4 @@ int Dim1Launch<LM>::fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cud
 #include "inst_dim1_bwd.inc"
 
 }  // namespace admmtv
+#endif  // ADMMTV_STUB

@@ -1,4 +1,10 @@
 // inst_dim2.cu -- instantiates every dim-2 kernel variant for ONE FFT length N = 2^ADMMTV_INST.
+#ifdef ADMMTV_STUB
+#include "args.cuh"
+namespace admmtv {
+template <> int Dim2Launch<ADMMTV_INST>::run(const Geom&, int, const Dim2Args&, cudaStream_t) { return -3; }
+}
+#else
 #include "kernels.cuh"
 
 #ifndef ADMMTV_INST
@@ -37,3 +43,4 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a, cudaStrea
 }
 
 }  // namespace admmtv
+#endif  // ADMMTV_STUB

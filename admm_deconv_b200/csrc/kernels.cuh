@@ -20,8 +20,13 @@
 #include "launch_macros.cuh"
 #include "reduce.cuh"
 
+#ifndef ADMMTV_UNROLL_ITEMS
+#define ADMMTV_UNROLL_ITEMS 1
+#endif
+
 namespace admmtv {
 
+constexpr int kUnrollItems = ADMMTV_UNROLL_ITEMS;
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -39,6 +44,7 @@ ADMMTV_DI void for_items(int tid, int nlines, Prep prep, Body body) {
     static_assert(NT % ITEMS == 0, "block must be a multiple of the line's work items");
     const int wi = tid % ITEMS;
     const auto ctx = prep(wi);
+#pragma unroll(kUnrollItems)
     for (int c = tid / ITEMS; c < nlines; c += NT / ITEMS) body(wi, c, ctx);
   } else {
     for (int wi = tid; wi < ITEMS; wi += NT) {
@@ -82,22 +88,91 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 // ------------------------------------------------------------------------------------------
 // dim-1 (contiguous) FFT passes over a tile of columns held in shared memory
 // ------------------------------------------------------------------------------------------
+#ifndef ADMMTV_TC9
+#define ADMMTV_TC9 10
+#endif
+#ifndef ADMMTV_PREFETCH
+#define ADMMTV_PREFETCH 1
+#endif
+#ifndef ADMMTV_NT9
+#define ADMMTV_NT9 256
+#endif
+#ifndef ADMMTV_MINB9
+#define ADMMTV_MINB9 1
+#endif
+#ifndef ADMMTV_CHUNK9
+#define ADMMTV_CHUNK9 (8 * ADMMTV_NT9 / 512)
+#endif
+#ifndef ADMMTV_TR9
+#define ADMMTV_TR9 16
+#endif
+#ifndef ADMMTV_NT2
+#define ADMMTV_NT2 256
+#endif
+#ifndef ADMMTV_MINB2
+#define ADMMTV_MINB2 1
+#endif
+// Asynchronous bulk prefetch of a contiguous global range into L2 (TMA unit, no registers, no
+// shared memory): issued for the stencil phase's inputs while the FFT passes run.
+ADMMTV_DI void l2_prefetch_bulk(const void* p, unsigned bytes) {
+#if !defined(ADMMTV_EMU) && ADMMTV_PREFETCH
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+  (void)p;
+  (void)bytes;
+#endif
+}
+
 template <int LM>
 struct Dim1Cfg {
   static constexpr int M = 1 << LM;
-  static constexpr int NT = LM <= 8 ? M : (LM <= 11 ? 256 : 512);
+  static constexpr int NT = LM <= 8 ? M : (LM == 9 ? ADMMTV_NT9 : (LM <= 11 ? 256 : 512));
+  static constexpr int MINB = LM == 9 ? ADMMTV_MINB9 : 1;
   static constexpr int RPT = M / NT;                  // rows per thread in the stencil sweep
-  static constexpr int CHUNK = RPT >= 8 ? 1 : 8 / RPT;  // columns between barriers
+  static constexpr int CHUNK = LM == 9 ? ADMMTV_CHUNK9 : (RPT >= 8 ? 1 : 8 / RPT);  // columns between barriers
   // tile columns including the 2 halo columns
-  static constexpr int TC = LM <= 8 ? 34 : (LM == 9 ? 18 : (LM <= 11 ? 10 : 6));
+  static constexpr int TC = LM <= 7 ? 34 : (LM == 8 ? 18 : (LM == 9 ? ADMMTV_TC9 : 6));
   static constexpr int CO = TC - 2;                   // output columns per block
   static constexpr size_t SMEM = (size_t)TC * M * sizeof(float2);
 };
 
-// shared-memory element index of (column c, row i) -- the single hook for bank swizzling
+// Shared-memory placement of (column c, row i): X[c*M + (i ^ swz_row(i) ^ swz_col(c))].
+// The XOR swizzle folds higher index bits into the 4 bits that select the 8-byte bank pair, so
+// that every FFT pass of the plan (strides M/R, M/R^2, ..., 1) is bank-conflict free; the maps
+// below were found by tools/bank_model.py.  swz is GF(2)-linear and only moves bits downwards, so
+// it is a bijection, and for an element base|off with disjoint bit fields the placement splits as
+// place(base) ^ place(off) -- the per-butterfly offsets m*STRIDE fold into compile-time XOR masks.
+#ifndef ADMMTV_SWZ
+#define ADMMTV_SWZ 1
+#endif
+template <int LM>
+ADMMTV_HD constexpr int swz_row(int i) {
+#if ADMMTV_SWZ
+  if (LM == 5) return ((i >> 2) & 15) ^ ((i >> 3) & 15);
+  if (LM == 6 || LM == 7) return (i >> 3) & 15;
+  if (LM == 8) return (i >> 4) & 15;
+  if (LM == 9 || LM == 10) return ((i >> 2) & 15) ^ ((i >> 3) & 15);
+  return ((i >> 4) & 15) ^ ((i >> 5) & 8);
+#else
+  return 0;
+#endif
+}
+template <int LM>
+ADMMTV_HD constexpr int swz_col(int c) {
+#if ADMMTV_SWZ
+  if (LM == 5) return (c << 2) & 15;
+  if (LM == 6 || LM == 7) return (c << 3) & 15;
+#endif
+  return 0;
+}
 template <int LM>
 ADMMTV_DI int sidx(int c, int i) {
-  return c * (1 << LM) + i;
+  return c * (1 << LM) + (i ^ swz_row<LM>(i) ^ swz_col<LM>(c));
+}
+// placement of a compile-time offset whose bits are disjoint from the base it is combined with
+template <int LM>
+ADMMTV_HD constexpr int soff(int off) {
+  return off ^ swz_row<LM>(off);
 }
 
 template <int LM, int NT, int S, bool INV>
@@ -113,13 +188,13 @@ ADMMTV_DI void dim1_smem_stage(float2* X, int ncols, const float2* __restrict__ 
       },
       [&](int wi, int c, const TwP<St::R>& t) {
         float2 a[St::R];
-        const int base = St::base(wi);
+        const int pb = sidx<LM>(c, St::base(wi));
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) a[m] = X[sidx<LM>(c, base + m * St::STRIDE)];
+        for (int m = 0; m < St::R; ++m) a[m] = X[pb ^ soff<LM>(m * St::STRIDE)];
         if (INV) stage_inv<M, S>(a, t.p);
         else stage_fwd<M, S>(a, t.p);
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) X[sidx<LM>(c, base + m * St::STRIDE)] = a[m];
+        for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m * St::STRIDE)] = a[m];
       });
 }
 
@@ -153,8 +228,9 @@ ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const floa
         float2 a[St::R];
         load_contig<St::R>(colptr(c) + wi * St::R, a);
         Dft<St::R, true>::run(a);
+        const int pb = sidx<LM>(c, wi * St::R);
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) X[sidx<LM>(c, wi * St::R + m)] = a[m];
+        for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m)] = a[m];
       });
   __syncthreads();
   dim1_inv_stages_down<LM, NT, NS - 2>(X, ncols, tw, tid);
@@ -171,8 +247,9 @@ ADMMTV_DI void dim1_fft_from_smem(float2* X, int ncols, ColPtr colptr, const flo
       tid, ncols, [&](int) { return 0; },
       [&](int wi, int c, int) {
         float2 a[St::R];
+        const int pb = sidx<LM>(c, wi * St::R);
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) a[m] = X[sidx<LM>(c, wi * St::R + m)];
+        for (int m = 0; m < St::R; ++m) a[m] = X[pb ^ soff<LM>(m)];
         Dft<St::R, false>::run(a);
         store_contig<St::R>(colptr(c) + wi * St::R, a);
       });
@@ -302,7 +379,7 @@ ADMMTV_DI void store_rows(float2* __restrict__ p, const float2* v) {
 }
 
 template <int LM, bool HAS_VPREV>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
   static_assert(CO % CHUNK == 0, "chunking must divide the tile");
@@ -319,6 +396,16 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
     return j;
   };
 
+  // stencil inputs of this tile -> L2 while the IFFT passes run (one bulk prefetch per array)
+  {
+    const unsigned colb = (unsigned)(M * sizeof(float2));
+    if (HAS_VPREV && tid == 0) {
+      l2_prefetch_bulk(A.vprev + ((size_t)q * 2 + 0) * plane + (size_t)j0 * M, (unsigned)nout * colb);
+      l2_prefetch_bulk(A.vprev + ((size_t)q * 2 + 0) * plane + (size_t)jcol(nout + 1) * M, colb);
+    }
+    if (HAS_VPREV && tid == 32 % NT) l2_prefetch_bulk(A.vprev + ((size_t)q * 2 + 1) * plane + (size_t)j0 * M, (unsigned)nout * colb);
+    if (tid == 64 % NT) l2_prefetch_bulk(A.bpk + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
+  }
   // 1. x_k for columns j0-1 .. j0+nout (one halo column each side)
   dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
@@ -349,6 +436,19 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
   }
 
   for (int c = 1; c <= nout; c += CHUNK) {
+    // (a) every global load of the chunk is issued before any of them is consumed
+    float2 g1[CHUNK][RPT], g2[CHUNK][RPT + 1], gb[CHUNK][RPT];
+#pragma unroll
+    for (int cc = 0; cc < CHUNK; ++cc) {
+      const int j = jcol(c + cc), jn = jcol(c + cc + 1);
+      if (HAS_VPREV) {
+        load_rows<RPT>(vp1 + (size_t)jn * M + i0, g1[cc]);
+        load_rows<RPT>(vp2 + (size_t)j * M + i0, g2[cc]);
+        g2[cc][RPT] = vp2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+      }
+      load_rows<RPT>(bq + (size_t)j * M + i0, gb[cc]);
+    }
+    // (b) stencil
     float2 rr[CHUNK][RPT];
 #pragma unroll
     for (int cc = 0; cc < CHUNK; ++cc) {
@@ -363,12 +463,11 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
       // channel 1 (dim-2 difference) at column col+1
       float2 w1n[RPT];
       {
-        float2 up[RPT], vst[RPT];
-        if (HAS_VPREV) load_rows<RPT>(vp1 + (size_t)jn * M + i0, up);
+        float2 vst[RPT];
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
           float2 v = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
-          if (HAS_VPREV) v = cadd(v, shrink_aniso(up[r], tau).u);
+          if (HAS_VPREV) v = cadd(v, shrink_aniso(g1[cc][r], tau).u);
           vst[r] = v;
           w1n[r] = shrink_aniso(v, tau).w;
         }
@@ -378,26 +477,20 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
       // neighbour's first row, recomputed here instead of exchanged)
       float2 w2[RPT + 1];
       {
-        float2 up[RPT + 1], vst[RPT];
-        if (HAS_VPREV) {
-          load_rows<RPT>(vp2 + (size_t)j * M + i0, up);
-          up[RPT] = vp2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
-        }
+        float2 vst[RPT];
 #pragma unroll
         for (int r = 0; r <= RPT; ++r) {
           float2 v = csub(xc[r + 1], xc[r]);
-          if (HAS_VPREV) v = cadd(v, shrink_aniso(up[r], tau).u);
+          if (HAS_VPREV) v = cadd(v, shrink_aniso(g2[cc][r], tau).u);
           if (r < RPT) vst[r] = v;
           w2[r] = shrink_aniso(v, tau).w;
         }
         store_rows<RPT>(vn2 + (size_t)j * M + i0, vst);
       }
-      float2 bb[RPT];
-      load_rows<RPT>(bq + (size_t)j * M + i0, bb);
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
         const float2 dt = cadd(csub(w1c[r], w1n[r]), csub(w2[r], w2[r + 1]));  // D^T(z-u)
-        rr[cc][r] = make_float2(bb[r].x + rho * dt.x, bb[r].y + rho * dt.y);
+        rr[cc][r] = make_float2(gb[cc][r].x + rho * dt.x, gb[cc][r].y + rho * dt.y);
         w1c[r] = w1n[r];
       }
     }
@@ -423,8 +516,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_fwd(Dim1FwdArgs A) {
 template <int LN>
 struct Dim2Cfg {
   static constexpr int N = 1 << LN;
-  static constexpr int TR = LN <= 9 ? 16 : (LN <= 11 ? 8 : 4);
-  static constexpr int NT = 256;
+  static constexpr int TR = LN <= 8 ? 16 : (LN == 9 ? ADMMTV_TR9 : (LN <= 11 ? 8 : 4));
+  static constexpr int NT = LN == 9 ? ADMMTV_NT2 : 256;
+  static constexpr int MINB = LN == 9 ? ADMMTV_MINB2 : 1;
   static constexpr size_t SMEM = (size_t)N * TR * sizeof(float2);
 };
 
@@ -475,7 +569,7 @@ ADMMTV_DI void dim2_inv_mid(float2* tile, const float2* __restrict__ tw, int tid
 }
 
 template <int LN, int MUL, bool SAVE_Z, int ACC, bool FWD_ONLY>
-__global__ void __launch_bounds__(Dim2Cfg<LN>::NT) k_dim2(Dim2Args A) {
+__global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim2Args A) {
   using Cfg = Dim2Cfg<LN>;
   constexpr int N = Cfg::N, TR = Cfg::TR, NT = Cfg::NT, RP = TR / 2, NS = plan_stages(N);
   ADMMTV_DYN_SMEM(float2, tile);  // [N][TR]

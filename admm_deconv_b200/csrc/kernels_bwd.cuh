@@ -53,6 +53,20 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
     if (j >= N) j -= N;
     return j;
   };
+  {
+    const unsigned colb = (unsigned)(M * sizeof(float2));
+    if (tid == 0) {
+      l2_prefetch_bulk(A.vck + ((size_t)q * 2 + 0) * plane + (size_t)j0 * M, (unsigned)nout * colb);
+      l2_prefetch_bulk(A.vck + ((size_t)q * 2 + 0) * plane + (size_t)jcol(nout + 1) * M, colb);
+    }
+    if (tid == 32 % NT) l2_prefetch_bulk(A.vck + ((size_t)q * 2 + 1) * plane + (size_t)j0 * M, (unsigned)nout * colb);
+    if (HAS_VBAR && tid == 64 % NT) {
+      l2_prefetch_bulk(A.vbar_in + ((size_t)q * 2 + 0) * plane + (size_t)j0 * M, (unsigned)nout * colb);
+      l2_prefetch_bulk(A.vbar_in + ((size_t)q * 2 + 0) * plane + (size_t)jcol(nout + 1) * M, colb);
+    }
+    if (HAS_VBAR && tid == 96 % NT) l2_prefetch_bulk(A.vbar_in + ((size_t)q * 2 + 1) * plane + (size_t)j0 * M, (unsigned)nout * colb);
+    if (!A.first && tid == 128 % NT) l2_prefetch_bulk(A.bbar + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
+  }
   // 1. rbar_k for columns j0-1 .. j0+nout
   dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 

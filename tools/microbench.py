@@ -1,0 +1,41 @@
+"""Times one workload's forward (and optionally fwd+bwd) for several library variants.
+    python tools/microbench.py cfg2 20 base swz swz_pf ...        (tags of tools/variants.py; 'main' = libadmmtv.so)"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from admm_deconv_b200 import _lib, ops  # noqa: E402
+
+name, iters = sys.argv[1], int(sys.argv[2])
+tags = sys.argv[3:]
+w = dict(bench.WORKLOADS[name], iters=iters)
+y, h = bench.make_inputs(w, 1001)
+dev = torch.device("cuda:0")
+y = y.to(dev); h = h.to(dev)
+px = y.numel()
+ref = None
+for tag in tags:
+    path = _lib.LIB_PATH if tag == "main" else os.path.join(ROOT, "admm_deconv_b200", f"libadmmtv_{tag}.so")
+    lib = _lib.AdmmTvLib(path)
+    d = ops.make_desc_for(y, h, iters, False, "identity", False, _lib.FLAG_NO_CLAMP, 0.0)
+    fwd_b, ck_b, bwd_b = lib.workspace_bytes(d)
+    ws = torch.empty(fwd_b, dtype=torch.uint8, device=dev)
+    x = torch.empty_like(y)
+    lam = torch.tensor([0.0041], device=dev); rho = torch.tensor([0.021], device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    args = (d, y.data_ptr(), h.data_ptr(), lam.data_ptr(), rho.data_ptr(), None, x.data_ptr(), ws.data_ptr(), None, st)
+    for _ in range(2):
+        lib.profile_forward(*args)
+    res = [lib.profile_forward(*args) for _ in range(3)]
+    tot, t2, t1, oth = [min(r[i] for r in res) for i in range(4)]
+    if ref is None:
+        ref = x.clone()
+    err = float((x - ref).norm() / ref.norm())
+    it = t2 / iters + t1 / max(iters - 1, 1)
+    print(f"{tag:12s} dim2 {t2/iters*1e3:7.1f} us  dim1 {t1/max(iters-1,1)*1e3:7.1f} us  iter {it*1e3:7.1f} us  "
+          f"alg {40*px/it/1e6:7.0f} GB/s ({40*px/it/1e6/6538.6:.3f})  other {oth:.3f} ms  diff_vs_first {err:.1e}", flush=True)
