@@ -49,6 +49,7 @@ struct FwdWs {
   float2* ktab;
   float* mask;
   float2 *bpk, *specA, *specB, *v0, *v1;
+  float *nsq0, *nsq1;  // isotropic: per-pixel |v_k|^2 ring
   size_t bytes;
 };
 static FwdWs carve_fwd(const Geom& g, void* ws) {
@@ -65,6 +66,8 @@ static FwdWs carve_fwd(const Geom& g, void* ws) {
   w.specB = c.take<float2>(g.pk);
   w.v0 = c.take<float2>(2 * g.pk);
   w.v1 = c.take<float2>(2 * g.pk);
+  w.nsq0 = c.take<float>(g.plane);
+  w.nsq1 = c.take<float>(g.plane);
   w.bytes = c.off;
   return w;
 }
@@ -73,6 +76,7 @@ struct Ckpt {
   float* mask;   // [2 + nh]
   float2* vck;   // (K-1) slots of [Q][2][N][M]   : v_1 .. v_{K-1}
   float2* zck;   // K slots of [Q][N][M]          : F r_1 .. F r_K
+  float* nck;    // isotropic: (K-1) slots of [N][M] : per-pixel |v_k|^2
   size_t bytes;
 };
 static Ckpt carve_ckpt(const Geom& g, void* p) {
@@ -81,6 +85,7 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
   k.mask = c.take<float>(g.nh + 2);
   k.vck = c.take<float2>((size_t)(g.K > 1 ? g.K - 1 : 0) * 2 * g.pk);
   k.zck = c.take<float2>((size_t)g.K * g.pk);
+  k.nck = c.take<float>((size_t)(g.K > 1 ? g.K - 1 : 0) * g.plane);
   k.bytes = c.off;
   return k;
 }
@@ -223,7 +228,7 @@ int admmtv_ckpt_layout(const admmtv_desc* d, size_t out[4]) {
   out[0] = (size_t)(reinterpret_cast<unsigned char*>(k.mask) - base);
   out[1] = (size_t)(reinterpret_cast<unsigned char*>(k.vck) - base);
   out[2] = (size_t)(reinterpret_cast<unsigned char*>(k.zck) - base);
-  out[3] = k.bytes;
+  out[3] = (size_t)(reinterpret_cast<unsigned char*>(k.nck) - base);
   return ADMMTV_OK;
 }
 
@@ -231,7 +236,7 @@ int admmtv_forward_launches(const admmtv_desc* d, int with_ckpt) {
   (void)with_ckpt;
   if (admmtv_check(d)) return 0;
   int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 3 : 0);
-  n += d->iters + (d->iters - 1) + 1;
+  n += d->iters + (d->iters - 1) * (d->iso ? 2 : 1) + 1;
   return n;
 }
 
@@ -257,7 +262,6 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   if (!y || !lambda || !rho || !x_out || !workspace) return ADMMTV_ERR_NULL;
   if (d->kh > 0 && !h) return ADMMTV_ERR_NULL;
   if (d->has_bias && !bias) return ADMMTV_ERR_NULL;
-  if (d->iso) return ADMMTV_ERR_UNSUPPORTED;  // TODO(iso)
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ADMMTV_ERR_ALIGN;
   DeviceGuard guard(d->device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
@@ -301,7 +305,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
     if (ckpt) a.zsave = ck.zck + (size_t)(k - 1) * g.pk;
     tm_mark(tm, st, 0);
     if ((rc = run_dim2(g, ckpt ? D2_C_SAVE : D2_C, a, st))) return rc;
-    if (k < g.K) {
+    if (k < g.K && !d->iso) {
       Dim1FwdArgs f{};
       f.spec_in = w.specB; f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM;
       f.lambda = lambda; f.rho = rho; f.N = g.N;
@@ -314,6 +318,33 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       }
       tm_mark(tm, st, 1);
       if ((rc = run_dim1_fwd(g, k > 1, f, st))) return rc;
+    } else if (k < g.K) {
+      // isotropic: v_k and the per-pixel norm first (pass A), then shrink + D^T + FFT (pass B)
+      IsoArgs a2{};
+      a2.spec_in = w.specB; a2.spec_out = w.specA; a2.bpk = w.bpk; a2.twM = w.twM;
+      a2.lambda = lambda; a2.rho = rho; a2.N = g.N; a2.S = g.S;
+      float* nsq_new;
+      if (ckpt) {
+        a2.v_in = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
+        a2.v_out = ck.vck + (size_t)(k - 1) * 2 * g.pk;
+        a2.nsq_in = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane : nullptr;
+        nsq_new = ck.nck + (size_t)(k - 1) * g.plane;
+      } else {
+        a2.v_in = (k & 1) ? w.v1 : w.v0;
+        a2.v_out = (k & 1) ? w.v0 : w.v1;
+        a2.nsq_in = (k & 1) ? w.nsq1 : w.nsq0;
+        nsq_new = (k & 1) ? w.nsq0 : w.nsq1;
+      }
+      a2.nsq_out = nsq_new;
+      cudaError_t e2 = cudaMemsetAsync(nsq_new, 0, g.plane * sizeof(float), st);
+      if (e2 != cudaSuccess) return (int)e2;
+      tm_mark(tm, st, 1);
+      ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::iso(g, 0, k > 1, a2, st); })
+      if (rc) return rc;
+      IsoArgs b2 = a2;
+      b2.v_in = a2.v_out; b2.nsq_in = nsq_new;
+      ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::iso(g, 1, true, b2, st); })
+      if (rc) return rc;
     }
   }
   tm_mark(tm, st, 2);

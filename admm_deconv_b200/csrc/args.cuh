@@ -73,6 +73,26 @@ struct Dim1BwdArgs {
   int first;               // 1: bbar is written, not accumulated (k = K)
 };
 
+// isotropic passes (kernels_iso.cuh); unused members are null
+struct IsoArgs {
+  const float2* spec_in;
+  float2* spec_out;
+  const float2* bpk;
+  const float2* v_in;      // fwd A: v_{k-1} ; fwd B: v_k ; bwd: v_{k-1} (checkpoint)
+  float2* v_out;           // fwd A: v_k
+  const float* nsq_in;     // fwd A: |v_{k-1}|^2 per pixel ; fwd B: |v_k|^2 ; bwd: |v_{k-1}|^2
+  float* nsq_out;          // fwd A: accumulates |v_k|^2 (zeroed by the host)
+  const float2* vbar_in;
+  float2* vbar_out;
+  float2* bbar;
+  float* ip;               // bwd A accumulates <q, v_{k-1}> per pixel ; bwd B reads it
+  const float2* twM;
+  const float* lambda;
+  const float* rho;
+  double* acc;
+  int N, S, first;
+};
+
 // variants of k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)
 enum Dim2Variant {
   D2_C = 0,      // x C                                   (forward iteration, inference)
@@ -91,6 +111,8 @@ struct Dim1Launch {
   static int fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st);
   static int bwd(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
   static int bwd_last(const Geom& g, int mode, const Dim1BwdArgs& a, cudaStream_t st);
+  // pass: 0 fwd A, 1 fwd B, 2 bwd A, 3 bwd B ; flag: HAS_VPREV / HAS_VBAR
+  static int iso(const Geom& g, int pass, bool flag, const IsoArgs& a, cudaStream_t st);
 };
 template <int LN>
 struct Dim2Launch {

@@ -67,3 +67,21 @@ def test_emu_clamp_is_persisted(emu):
     r = E.forward(emu, y.numpy(), -1.0, 0.01, hh, False, 2, creg=0.05)
     assert r["lam"][0] == np.float32(0.05) and r["rho"][0] == np.float32(0.05)     # deconv_admm.jl:216-217
     assert r["h"][0, 0] == 0.0 and r["h"][1, 1] == 1.0                              # :219
+
+
+@pytest.mark.parametrize("M,N,P,B,kh,kw,K", [(32, 32, 1, 2, 0, 0, 2), (32, 64, 3, 1, 5, 4, 4), (64, 32, 1, 3, 3, 3, 5)])
+def test_emu_forward_iso_vs_oracle(emu, M, N, P, B, kh, kw, K):
+    """Isotropic (BT, ops.jl:10): ONE norm per pixel over both directions, all channels, all images."""
+    import harness
+    from parity import check_forward
+    y, h, _ = make_case(M, N, P, B, kh, kw, 50 + M + K)
+    check_forward(harness.EmuBackend(emu), y, h, 0.05, 0.3, True, K, fast=False)
+
+
+def test_emu_golden_forward_iso(emu):
+    for f in sorted(glob.glob(os.path.join(HERE, "golden", "iso_*.npz"))):
+        d = np.load(f)
+        h = d["h"][:, :, 0, 0] if "h" in d else None
+        r = E.forward(emu, d["y"], float(d["lam"]), float(d["rho"]), h, True, int(d["iters"]), act=str(d["act"]),
+                      bias=float(d["bias"]) if "bias" in d else None, creg=float(d["creg"]))
+        assert rel_l2(torch.from_numpy(np.ascontiguousarray(r["x"])), torch.from_numpy(d["x"])) < TOL, f

@@ -119,3 +119,21 @@ def test_layer_module_train_step_updates_parameters():
     opt.step()
     assert any(not torch.equal(a, b.detach()) for a, b in zip(before, layer.parameters()))
     assert layer.packed_grads().numel() == 49 + 3
+
+
+@pytest.mark.parametrize("M,N,P,B,kh,kw,K", [(32, 32, 1, 4, 0, 0, 5), (64, 64, 3, 2, 7, 7, 10), (256, 128, 3, 2, 9, 9, 8), (512, 512, 1, 2, 5, 5, 4)])
+def test_backward_iso_teacher_forced(be, M, N, P, B, kh, kw, K):
+    y, h, g = make_case(M, N, P, B, kh, kw, 600 + M + K)
+    xbar = 2.0 * (y - g) / y.numel() * 1e3
+    r = check_backward(be, y, h, 0.0041, 0.021, True, K, xbar, tol=1e-5, tol_scalar=2e-4, tol_e2e=1e-3)
+    print(r)
+
+
+def test_golden_backward_iso(be):
+    for f in sorted(glob.glob(os.path.join(HERE, "golden", "iso_*.npz"))):
+        d = np.load(f)
+        y = torch.from_numpy(d["y"]).double()
+        h = torch.from_numpy(d["h"]).double() if "h" in d else None
+        r = check_backward(be, y, h, float(d["lam"]), float(d["rho"]), True, int(d["iters"]), torch.from_numpy(d["xbar"]),
+                           str(d["act"]), None, float(d["creg"]), tol=1e-5, tol_scalar=2e-4)
+        print(os.path.basename(f), r)

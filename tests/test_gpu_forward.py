@@ -149,3 +149,42 @@ def test_error_codes_on_bad_shapes():
     with pytest.raises(A.AdmmTvError) as e:
         A.tvd_fft(y, torch.ones(1, device=d0), torch.ones(1, device=d0), None, False, 2)
     assert e.value.code == -3
+
+
+@pytest.mark.parametrize(
+    "M,N,P,B,kh,kw,K",
+    [(32, 32, 1, 2, 0, 0, 2), (64, 64, 3, 2, 5, 5, 15), (128, 256, 3, 2, 9, 9, 20), (256, 256, 3, 2, 15, 15, 50), (512, 512, 1, 2, 7, 7, 10)],
+)
+def test_forward_iso_vs_oracle(M, N, P, B, kh, kw, K):
+    """Isotropic TV (BT): the norm couples every plane of the call."""
+    y, h, _ = make_case(M, N, P, B, kh, kw, 500 + M + K)
+    x = run_gpu(y, h, 0.0041, 0.021, True, K)
+    xo = oracle(y, h, 0.0041, 0.021, True, K, fast=True)
+    assert rel_l2(x, xo) < TOL
+
+
+def test_golden_forward_iso():
+    d0 = dev()
+    n = 0
+    for f in sorted(glob.glob(os.path.join(HERE, "golden", "iso_*.npz"))):
+        d = np.load(f)
+        y = A.from_julia(torch.from_numpy(d["y"])).to(d0)
+        h = A.from_julia(torch.from_numpy(d["h"])).to(d0) if "h" in d else None
+        lam = torch.tensor([float(d["lam"])], dtype=torch.float32, device=d0)
+        rho = torch.tensor([float(d["rho"])], dtype=torch.float32, device=d0)
+        x = A.admm_layer_call(y, lam, rho, h, None, int(d["iters"]), True, str(d["act"]), float(d["creg"]))
+        torch.cuda.synchronize()
+        assert rel_l2(A.to_julia(x.cpu()), torch.from_numpy(d["x"])) < TOL, f
+        n += 1
+    assert n >= 2
+
+
+def test_iso_couples_the_batch():
+    """Reference semantics (a-9 iv): with BT an image's result depends on the other images of the call."""
+    d0 = dev()
+    torch.manual_seed(2)
+    y = torch.rand(2, 1, 64, 64, device=d0)
+    lam = torch.tensor([0.05], device=d0); rho = torch.tensor([0.3], device=d0)
+    both = A.tvd_fft(y, lam, rho, None, True, 10)
+    alone = A.tvd_fft(y[:1].contiguous(), lam, rho, None, True, 10)
+    assert rel_l2(both[:1].cpu(), alone.cpu()) > 1e-3
