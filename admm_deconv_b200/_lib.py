@@ -26,6 +26,7 @@ SYMBOLS = (
     "admmtv_backward",
     "admmtv_forward_host",
     "admmtv_profile_forward",
+    "admmtv_profile_backward",
     "admmtv_ckpt_layout",
     "admmtv_forward_launches",
     "admmtv_backward_launches",
@@ -71,6 +72,7 @@ class AdmmTvLib:
         L.admmtv_forward.argtypes = [C.POINTER(Desc)] + [vp] * 9
         L.admmtv_backward.argtypes = [C.POINTER(Desc)] + [vp] * 14
         L.admmtv_profile_forward.argtypes = [C.POINTER(Desc)] + [vp] * 10
+        L.admmtv_profile_backward.argtypes = [C.POINTER(Desc)] + [vp] * 15
         L.admmtv_forward_host.argtypes = [C.POINTER(Desc)] + [vp] * 6
         L.admmtv_ckpt_layout.argtypes = [C.POINTER(Desc), C.POINTER(sz)]
         L.admmtv_forward_launches.argtypes = [C.POINTER(Desc), C.c_int]
@@ -107,6 +109,12 @@ class AdmmTvLib:
         """Returns (total_ms, dim2_ms, dim1_ms, other_ms); synchronises."""
         ms = (C.c_float * 4)()
         self._raise(self.lib.admmtv_profile_forward(C.byref(d), y, h, lam, rho, bias, x_out, ws, ckpt, stream, ms))
+        return tuple(ms)
+
+    def profile_backward(self, d: Desc, xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar, biasbar, ws, stream=0):
+        ms = (C.c_float * 4)()
+        self._raise(self.lib.admmtv_profile_backward(C.byref(d), xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar,
+                                                     biasbar, ws, stream, ms))
         return tuple(ms)
 
     def forward_host(self, d: Desc, y, h, lam, rho, bias, x_out):

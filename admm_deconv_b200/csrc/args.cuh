@@ -55,6 +55,7 @@ struct Dim2Args {
   float* gacc;         // ACC 1: float [N][M] += Re(conj(Z) Z2) ; ACC 2: float2 [N][M] += conj(Z) Z2
   const float2* twN;
   int M;
+  int Q;               // number of plane pairs (blocks loop q = blockIdx.y, += gridDim.y)
 };
 
 struct Dim1BwdArgs {

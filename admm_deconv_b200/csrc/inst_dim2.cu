@@ -25,16 +25,39 @@ static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, con
 }
 
 constexpr int LN = ADMMTV_INST;
+#ifndef ADMMTV_D2_PERSIST
+#define ADMMTV_D2_PERSIST 0
+#endif
+#ifndef ADMMTV_D2_BLOCKS_PER_SM
+#define ADMMTV_D2_BLOCKS_PER_SM 2
+#endif
 
 template <>
-int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a, cudaStream_t st) {
+int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaStream_t st) {
   using Cfg = Dim2Cfg<LN>;
-  const dim3 grid((unsigned)(g.M / Cfg::TR), (unsigned)g.Q);
+  // One wave of persistent blocks: each block owns a row tile and loops over plane pairs, so the
+  // gradient accumulator stays in registers and the next tile can be prefetched into L2.
+  Dim2Args a = a_in;
+  a.Q = g.Q;
+  const int row_tiles = g.M / Cfg::TR;
+  int gy = g.Q;
+#if ADMMTV_D2_PERSIST
+  if (ADMMTV_D2_PERSIST == 1 || variant == D2_C_ACCG) {  // 2: persistent only where it saves atomics
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = sms * ADMMTV_D2_BLOCKS_PER_SM;
+    gy = slots / row_tiles;
+    if (gy < 1) gy = 1;
+    if (gy > g.Q) gy = g.Q;
+  }
+#endif
+  const dim3 grid((unsigned)row_tiles, (unsigned)gy);
   switch (variant) {
     case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_C_SAVE: return launch_k(k_dim2<LN, 0, true, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_KCONJ: return launch_k(k_dim2<LN, 1, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
-    case D2_C_ACCG: return launch_k(k_dim2<LN, 0, false, 1, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_C_ACCG: return launch_k(k_dim2<LN, 0, false, 1, false>, grid, Cfg::NT, Cfg::SMEM + Cfg::SMEM / 2, st, a);
     case D2_FWDONLY: return launch_k(k_dim2<LN, 0, false, 0, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_K_ACCP: return launch_k(k_dim2<LN, 2, false, 2, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_K: return launch_k(k_dim2<LN, 2, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);

@@ -98,10 +98,10 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #define ADMMTV_NT9 256
 #endif
 #ifndef ADMMTV_MINB9
-#define ADMMTV_MINB9 1
+#define ADMMTV_MINB9 3
 #endif
 #ifndef ADMMTV_CHUNK9
-#define ADMMTV_CHUNK9 (8 * ADMMTV_NT9 / 512)
+#define ADMMTV_CHUNK9 2
 #endif
 #ifndef ADMMTV_TR9
 #define ADMMTV_TR9 16
@@ -568,58 +568,87 @@ ADMMTV_DI void dim2_inv_mid(float2* tile, const float2* __restrict__ tw, int tid
   }
 }
 
+// Per-thread L2 prefetch of one 128-byte line (the next tile's first-pass loads hit L2).
+ADMMTV_DI void l2_prefetch_line(const void* p) {
+#if !defined(ADMMTV_EMU) && ADMMTV_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 template <int LN, int MUL, bool SAVE_Z, int ACC, bool FWD_ONLY>
 __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim2Args A) {
   using Cfg = Dim2Cfg<LN>;
   constexpr int N = Cfg::N, TR = Cfg::TR, NT = Cfg::NT, RP = TR / 2, NS = plan_stages(N);
-  ADMMTV_DYN_SMEM(float2, tile);  // [N][TR]
+  using StL = Stage<N, NS - 1>;
+  static_assert(StL::STRIDE == 1, "last plan stage must be contiguous");
+  constexpr int IPT = (RP * StL::ITEMS + NT - 1) / NT;  // fused-stage items per thread
+  // G = sum over pairs of Re(conj(Z) Z2) is accumulated in shared memory across this block's
+  // pairs (each element is owned by one thread) and flushed with one atomic per element at the
+  // end, instead of one global atomic per element per pair.
+  constexpr bool SMACC = ACC == 1;
+  ADMMTV_DYN_SMEM(float2, tile);  // [N][TR] (+ float [N][TR] accumulator when SMACC)
   const int tid = threadIdx.x, M = A.M;
   const int i0 = blockIdx.x * TR;
-  const size_t qoff = (size_t)blockIdx.y * N * M;
-  const float2* src = A.in + qoff + i0;
-
-  // forward stage 0: global -> registers -> shared
-  {
-    using St = Stage<N, 0>;
-    for (int item = tid; item < RP * St::ITEMS; item += NT) {
-      const int rp = item % RP, wi = item / RP;
-      float2 p[St::R];
-      stage_twiddles<N, 0, false>(wi, A.twN, p);
-      float2 a0[St::R], a1[St::R];
-#pragma unroll
-      for (int m = 0; m < St::R; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(wi + m * St::STRIDE) * M + 2 * rp);
-        a0[m] = make_float2(v.x, v.y);
-        a1[m] = make_float2(v.z, v.w);
-      }
-      stage_fwd<N, 0>(a0, p);
-      stage_fwd<N, 0>(a1, p);
-#pragma unroll
-      for (int m = 0; m < St::R; ++m)
-        *reinterpret_cast<float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
-    }
+  float* gsm = reinterpret_cast<float*>(tile + N * TR);
+  if (SMACC) {
+    for (int t = tid; t < N * TR; t += NT) gsm[t] = 0.f;  // ordered before the first use by the barriers of the forward passes
   }
-  __syncthreads();
-  dim2_fwd_mid<LN, 1>(tile, A.twN, tid);
+  (void)IPT;
 
-  // last forward stage fused with the spectral multiply and the first inverse stage
-  {
-    using St = Stage<N, NS - 1>;
-    static_assert(St::STRIDE == 1, "last plan stage must be contiguous");
-    for (int item = tid; item < RP * St::ITEMS; item += NT) {
-      const int rp = item % RP, wi = item / RP;
-      float2 a0[St::R], a1[St::R];
+  for (int q = blockIdx.y; q < A.Q; q += gridDim.y) {
+    const size_t qoff = (size_t)q * N * M;
+    const float2* src = A.in + qoff + i0;
+    if (ACC != 0) {
+      // the second spectrum is consumed in the fused stage: start pulling it into L2 now
+      for (int col = tid; col < N; col += NT) l2_prefetch_line(A.z2 + qoff + i0 + (size_t)col * M);
+    }
+    if (q + (int)gridDim.y < A.Q) {
+      // this block's next tile -> L2 (TR*8 bytes per column; one line covers 16 rows)
+      const float2* nxt = A.in + (size_t)(q + gridDim.y) * N * M + i0;
+      for (int col = tid; col < N; col += NT) l2_prefetch_line(nxt + (size_t)col * M);
+    }
+
+    // forward stage 0: global -> registers -> shared
+    {
+      using St = Stage<N, 0>;
+      for (int item = tid; item < RP * St::ITEMS; item += NT) {
+        const int rp = item % RP, wi = item / RP;
+        float2 p[St::R];
+        stage_twiddles<N, 0, false>(wi, A.twN, p);
+        float2 a0[St::R], a1[St::R];
 #pragma unroll
-      for (int m = 0; m < St::R; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + (wi * St::R + m) * TR + 2 * rp);
+        for (int m = 0; m < St::R; ++m) {
+          const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(wi + m * St::STRIDE) * M + 2 * rp);
+          a0[m] = make_float2(v.x, v.y);
+          a1[m] = make_float2(v.z, v.w);
+        }
+        stage_fwd<N, 0>(a0, p);
+        stage_fwd<N, 0>(a1, p);
+#pragma unroll
+        for (int m = 0; m < St::R; ++m)
+          *reinterpret_cast<float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+      }
+    }
+    __syncthreads();
+    dim2_fwd_mid<LN, 1>(tile, A.twN, tid);
+
+    // last forward stage fused with the spectral multiply and the first inverse stage
+    auto fused_item = [&](int item) {
+      const int rp = item % RP, wi = item / RP;
+      float2 a0[StL::R], a1[StL::R];
+#pragma unroll
+      for (int m = 0; m < StL::R; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + (wi * StL::R + m) * TR + 2 * rp);
         a0[m] = make_float2(v.x, v.y);
         a1[m] = make_float2(v.z, v.w);
       }
-      Dft<St::R, false>::run(a0);
-      Dft<St::R, false>::run(a1);
+      Dft<StL::R, false>::run(a0);
+      Dft<StL::R, false>::run(a1);
 #pragma unroll
-      for (int m = 0; m < St::R; ++m) {
-        const size_t g = (size_t)(wi * St::R + m) * M + i0 + 2 * rp;  // table / spectrum offset
+      for (int m = 0; m < StL::R; ++m) {
+        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;  // table / spectrum offset
         if (SAVE_Z || FWD_ONLY) {
           float2* zs = FWD_ONLY ? A.out : A.zsave;
           *reinterpret_cast<float4*>(zs + qoff + g) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
@@ -629,9 +658,12 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
           // conj(Z) * Z2
           const float re0 = a0[m].x * z2.x + a0[m].y * z2.y, im0 = a0[m].x * z2.y - a0[m].y * z2.x;
           const float re1 = a1[m].x * z2.z + a1[m].y * z2.w, im1 = a1[m].x * z2.w - a1[m].y * z2.z;
-          if (ACC == 1) {
-            atomicAdd(A.gacc + g, re0);
-            atomicAdd(A.gacc + g + 1, re1);
+          if (SMACC) {
+            float2* gp = reinterpret_cast<float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
+            float2 gv = *gp;
+            gv.x += re0;
+            gv.y += re1;
+            *gp = gv;
           } else {
             atomicAdd(A.gacc + 2 * g, re0);
             atomicAdd(A.gacc + 2 * g + 1, im0);
@@ -653,38 +685,55 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
         }
       }
       if (!FWD_ONLY) {
-        Dft<St::R, true>::run(a0);
-        Dft<St::R, true>::run(a1);
+        Dft<StL::R, true>::run(a0);
+        Dft<StL::R, true>::run(a1);
+#pragma unroll
+        for (int m = 0; m < StL::R; ++m)
+          *reinterpret_cast<float4*>(tile + (wi * StL::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+      }
+    };
+#pragma unroll 1
+    for (int item = tid; item < RP * StL::ITEMS; item += NT) fused_item(item);
+    __syncthreads();
+    if (FWD_ONLY) continue;
+    dim2_inv_mid<LN, NS - 2>(tile, A.twN, tid);
+
+    // inverse stage 0: shared -> registers -> global
+    {
+      using St = Stage<N, 0>;
+      float2* dst = A.out + qoff + i0;
+      for (int item = tid; item < RP * St::ITEMS; item += NT) {
+        const int rp = item % RP, wi = item / RP;
+        float2 p[St::R];
+        stage_twiddles<N, 0, true>(wi, A.twN, p);
+        float2 a0[St::R], a1[St::R];
+#pragma unroll
+        for (int m = 0; m < St::R; ++m) {
+          const float4 v = *reinterpret_cast<const float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp);
+          a0[m] = make_float2(v.x, v.y);
+          a1[m] = make_float2(v.z, v.w);
+        }
+        stage_inv<N, 0>(a0, p);
+        stage_inv<N, 0>(a1, p);
 #pragma unroll
         for (int m = 0; m < St::R; ++m)
-          *reinterpret_cast<float4*>(tile + (wi * St::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+          *reinterpret_cast<float4*>(dst + (size_t)(wi + m * St::STRIDE) * M + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
       }
     }
+    __syncthreads();  // the tile is rewritten by the next pair's first pass
   }
-  if (FWD_ONLY) return;
-  __syncthreads();
-  dim2_inv_mid<LN, NS - 2>(tile, A.twN, tid);
 
-  // inverse stage 0: shared -> registers -> global
-  {
-    using St = Stage<N, 0>;
-    float2* dst = A.out + qoff + i0;
-    for (int item = tid; item < RP * St::ITEMS; item += NT) {
+  if (SMACC) {
+    // same (thread -> element) ownership as the fused stage: no barrier needed
+    for (int item = tid; item < RP * StL::ITEMS; item += NT) {
       const int rp = item % RP, wi = item / RP;
-      float2 p[St::R];
-      stage_twiddles<N, 0, true>(wi, A.twN, p);
-      float2 a0[St::R], a1[St::R];
 #pragma unroll
-      for (int m = 0; m < St::R; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp);
-        a0[m] = make_float2(v.x, v.y);
-        a1[m] = make_float2(v.z, v.w);
+      for (int m = 0; m < StL::R; ++m) {
+        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;
+        const float2 gv = *reinterpret_cast<const float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
+        atomicAdd(A.gacc + g, gv.x);
+        atomicAdd(A.gacc + g + 1, gv.y);
       }
-      stage_inv<N, 0>(a0, p);
-      stage_inv<N, 0>(a1, p);
-#pragma unroll
-      for (int m = 0; m < St::R; ++m)
-        *reinterpret_cast<float4*>(dst + (size_t)(wi + m * St::STRIDE) * M + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
     }
   }
 }

@@ -142,42 +142,46 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
   }
 }
 
-// U[a][k2] = sum_k1 Wn[k2][k1] e^{+2 pi i k1 a / M}
+// U[a][k2] = sum_k1 Wn[k2][k1] e^{+2 pi i k1 a / M}        one block per (a, k2): the M terms are
+// spread over the block's threads (coalesced Wn row) and reduced in fp64
 static __global__ void k_grad_h_dim1(const double2* __restrict__ Wn, int kh, int M, int N, double2* U) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= kh * N) return;
-  const int a = idx / N, k2 = idx % N;
+  const int a = blockIdx.x / N, k2 = blockIdx.x % N;
   double re = 0.0, im = 0.0;
-  for (int k1 = 0; k1 < M; ++k1) {
+  for (int k1 = threadIdx.x; k1 < M; k1 += blockDim.x) {
     double s, c;
     sincospi(2.0 * ((long long)k1 * a % M) / M, &s, &c);
     const double2 w = Wn[(size_t)k2 * M + k1];
     re += w.x * c - w.y * s;
     im += w.x * s + w.y * c;
   }
-  U[idx] = make_double2(re, im);
+  re = block_sum(re);
+  im = block_sum(im);
+  if (threadIdx.x == 0) U[blockIdx.x] = make_double2(re, im);
+  (void)kh;
 }
 
-// hbar[a,b] = mask * Re sum_k2 U[a][k2] e^{+2 pi i k2 b / N}; thread 0 also finalises the scalars:
+// hbar[a,b] = mask * Re sum_k2 U[a][k2] e^{+2 pi i k2 b / N} (one block per tap); block 0 also
+// finalises the scalars:
 //   lambar = taubar / rho ; rhobar = direct + spectral - taubar lambda / rho^2   (tau = lambda ./ rho, ops.jl:102)
 // acc: [0] rho direct, [1] taubar, [2] biasbar, [3] rho spectral.  mask: [0] lambda, [1] rho, [2..] h.
 static __global__ void k_grad_finalize(const double2* __restrict__ U, int kh, int kw, int N, const float* __restrict__ mask,
                                        const double* __restrict__ acc, const float* __restrict__ lambda,
                                        const float* __restrict__ rho, float* hbar, float* lambar, float* rhobar,
                                        float* biasbar) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < kh * kw && hbar) {
+  const int t = blockIdx.x;
+  if (t < kh * kw && hbar) {   // block-uniform
     const int a = t % kh, b = t / kh;
     double re = 0.0;
-    for (int k2 = 0; k2 < N; ++k2) {
+    for (int k2 = threadIdx.x; k2 < N; k2 += blockDim.x) {
       double s, c;
       sincospi(2.0 * ((long long)k2 * b % N) / N, &s, &c);
       const double2 u = U[a * N + k2];
       re += u.x * c - u.y * s;
     }
-    hbar[t] = (float)(re * (double)mask[2 + t]);
+    re = block_sum(re);
+    if (threadIdx.x == 0) hbar[t] = (float)(re * (double)mask[2 + t]);
   }
-  if (t == 0) {
+  if (t == 0 && threadIdx.x == 0) {
     const double lam = (double)*lambda, r = (double)*rho, tb = acc[1];
     *lambar = (float)((double)mask[0] * tb / r);
     *rhobar = (float)((double)mask[1] * (acc[0] + acc[3] - tb * lam / (r * r)));

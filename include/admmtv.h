@@ -112,6 +112,13 @@ int admmtv_profile_forward(const admmtv_desc* desc, const float* y, float* h, fl
                            const float* bias, float* x_out, void* workspace, void* ckpt, void* stream,
                            float* ms_out);
 
+/* Profiling twin of admmtv_backward; ms_out[4] = {total, the iterations' dim-2 kernels, the
+ * iterations' dim-1 kernels, everything else}.  SYNCHRONISES. */
+int admmtv_profile_backward(const admmtv_desc* desc, const float* xbar, const float* x_out, const float* y,
+                            const float* h, const float* lambda, const float* rho, const void* ckpt,
+                            float* ybar, float* hbar, float* lambdabar, float* rhobar, float* biasbar,
+                            void* workspace, void* stream, float* ms_out);
+
 /* Byte offsets inside the checkpoint buffer (test / inspection use): out[0] = clamp masks
  * (2 + kh*kw floats), out[1] = v_k slots, k = 1..iters-1, each float2 [Q][2][N][M] (Q = ceil(P*B/2)
  * plane pairs: .x = plane 2q, .y = plane 2q+1; [2] = dim-2 / dim-1 difference channel),

@@ -37,5 +37,23 @@ for tag in tags:
         ref = x.clone()
     err = float((x - ref).norm() / ref.norm())
     it = t2 / iters + t1 / max(iters - 1, 1)
-    print(f"{tag:12s} dim2 {t2/iters*1e3:7.1f} us  dim1 {t1/max(iters-1,1)*1e3:7.1f} us  iter {it*1e3:7.1f} us  "
+    # forward with checkpoint + backward through the raw ABI
+    ck = torch.empty(ck_b, dtype=torch.uint8, device=dev)
+    wsb = torch.empty(bwd_b, dtype=torch.uint8, device=dev)
+    xbar = torch.ones_like(y); ybar = torch.empty_like(y); hbar = torch.empty_like(h)
+    lb = torch.empty(1, device=dev); rb = torch.empty(1, device=dev)
+    def train():
+        lib.forward(d, y.data_ptr(), h.data_ptr(), lam.data_ptr(), rho.data_ptr(), None, x.data_ptr(), ws.data_ptr(), ck.data_ptr(), st)
+        lib.backward(d, xbar.data_ptr(), x.data_ptr(), y.data_ptr(), h.data_ptr(), lam.data_ptr(), rho.data_ptr(), ck.data_ptr(),
+                     ybar.data_ptr(), hbar.data_ptr(), lb.data_ptr(), rb.data_ptr(), None, wsb.data_ptr(), st)
+    train(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); train(); train(); e1.record(); torch.cuda.synchronize()
+    tr = e0.elapsed_time(e1) / 2
+    pf = lib.profile_forward(d, y.data_ptr(), h.data_ptr(), lam.data_ptr(), rho.data_ptr(), None, x.data_ptr(), ws.data_ptr(), ck.data_ptr(), st)
+    pb = lib.profile_backward(d, xbar.data_ptr(), x.data_ptr(), y.data_ptr(), h.data_ptr(), lam.data_ptr(), rho.data_ptr(), ck.data_ptr(),
+                              ybar.data_ptr(), hbar.data_ptr(), lb.data_ptr(), rb.data_ptr(), None, wsb.data_ptr(), st)
+    print(f"{tag:12s} ckpt-fwd: dim2 {pf[1]/iters*1e3:6.1f} dim1 {pf[2]/max(iters-1,1)*1e3:6.1f} other {pf[3]:.3f} ms | bwd: dim2 {pb[1]/iters*1e3:6.1f} "
+          f"dim1 {pb[2]/max(iters-1,1)*1e3:6.1f} other {pb[3]:.3f} ms total {pb[0]:.2f} ms")
+    print(f"{tag:12s} train {tr:7.2f} ms ({108*px*iters/tr/1e6/6538.6:.3f})  dim2 {t2/iters*1e3:7.1f} us  dim1 {t1/max(iters-1,1)*1e3:7.1f} us  iter {it*1e3:7.1f} us  "
           f"alg {40*px/it/1e6:7.0f} GB/s ({40*px/it/1e6/6538.6:.3f})  other {oth:.3f} ms  diff_vs_first {err:.1e}", flush=True)

@@ -23,6 +23,16 @@ VARIANTS = {
     "t6p1": ("ADMMTV_TC9=6", "ADMMTV_PREFETCH=1"),
     "t6p1n128": ("ADMMTV_TC9=6", "ADMMTV_PREFETCH=1", "ADMMTV_NT9=128"),
     "t18p1n128": ("ADMMTV_TC9=18", "ADMMTV_PREFETCH=1", "ADMMTV_NT9=128"),
+    "d2p0": ("ADMMTV_D2_PERSIST=0",),
+    "d2pa": ("ADMMTV_D2_PERSIST=2",),
+    "d2pa3": ("ADMMTV_D2_PERSIST=2", "ADMMTV_D2_BLOCKS_PER_SM=3"),
+    "d2p2": ("ADMMTV_D2_BLOCKS_PER_SM=2",),
+    "d2p3": ("ADMMTV_D2_BLOCKS_PER_SM=3",),
+    "d2p3mb3": ("ADMMTV_D2_BLOCKS_PER_SM=3", "ADMMTV_MINB2=3"),
+    "d2p4mb4": ("ADMMTV_D2_BLOCKS_PER_SM=4", "ADMMTV_MINB2=4"),
+    "c2mb3": ("ADMMTV_CHUNK9=2", "ADMMTV_MINB9=3"),
+    "c4mb3": ("ADMMTV_CHUNK9=4", "ADMMTV_MINB9=3"),
+    "c2mb4": ("ADMMTV_CHUNK9=2", "ADMMTV_MINB9=4"),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
