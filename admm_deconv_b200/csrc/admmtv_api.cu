@@ -341,9 +341,10 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       tm_mark(tm, st, 1);
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::iso(g, 0, k > 1, a2, st); })
       if (rc) return rc;
-      IsoArgs b2 = a2;
-      b2.v_in = a2.v_out; b2.nsq_in = nsq_new;
-      ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::iso(g, 1, true, b2, st); })
+      Dim1FwdArgs f{};
+      f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM; f.lambda = lambda; f.rho = rho; f.N = g.N;
+      f.vprev = a2.v_out; f.nsq = nsq_new;
+      ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_b(g, f, st); })
       if (rc) return rc;
     }
   }

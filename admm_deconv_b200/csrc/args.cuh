@@ -39,6 +39,7 @@ struct Dim1FwdArgs {
   const float2* bpk;
   const float2* vprev;  // [Q][2][N][M]; ignored when !HAS_VPREV (v_0 = 0)
   float2* vnew;         // [Q][2][N][M]
+  const float* nsq;     // isotropic pass B: per-pixel |v|^2 [N][M]
   const float2* twM;
   const float* lambda;
   const float* rho;
@@ -70,6 +71,8 @@ struct Dim1BwdArgs {
   const float* lambda;
   const float* rho;
   double* acc;             // [0] rhobar (direct term), [1] taubar
+  const float* nsq;        // isotropic pass B: |v_{k-1}|^2 per pixel
+  const float* ip;         // isotropic pass B: <q, v_{k-1}> per pixel
   int N, S;
   int first;               // 1: bbar is written, not accumulated (k = K)
 };
@@ -110,6 +113,8 @@ struct Dim1Launch {
   static int pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st);
   static int out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st);
   static int fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st);
+  static int fwd_iso_b(const Geom& g, const Dim1FwdArgs& a, cudaStream_t st);
+  static int bwd_iso_b(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
   static int bwd(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
   static int bwd_last(const Geom& g, int mode, const Dim1BwdArgs& a, cudaStream_t st);
   // pass: 0 fwd A, 1 fwd B, 2 bwd A, 3 bwd B ; flag: HAS_VPREV / HAS_VBAR

@@ -378,7 +378,43 @@ ADMMTV_DI void store_rows(float2* __restrict__ p, const float2* v) {
   }
 }
 
-template <int LM, bool HAS_VPREV>
+template <int RPT>
+ADMMTV_DI void load_rows_f(const float* __restrict__ p, float* out) {
+  if constexpr (RPT % 4 == 0) {
+#pragma unroll
+    for (int r = 0; r < RPT / 4; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(p + 4 * r);
+      out[4 * r] = v.x; out[4 * r + 1] = v.y; out[4 * r + 2] = v.z; out[4 * r + 3] = v.w;
+    }
+  } else if constexpr (RPT % 2 == 0) {
+#pragma unroll
+    for (int r = 0; r < RPT / 2; ++r) {
+      const float2 v = *reinterpret_cast<const float2*>(p + 2 * r);
+      out[2 * r] = v.x; out[2 * r + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) out[r] = p[r];
+  }
+}
+
+// isotropic block thresholding (ops.jl:6,10): one scale per pixel, s = max(1 - tau/n, 0)
+ADMMTV_DI float iso_scale(float nsq, float tau) {
+  const float n = sqrtf(nsq);
+  return n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;  // n = 0: max(-Inf,0)*0 = 0
+}
+ADMMTV_DI Shrunk shrink_iso(float2 v, float s) {
+  const float2 z = make_float2(s * v.x, s * v.y);
+  Shrunk r;
+  r.u = csub(v, z);
+  r.w = csub(z, r.u);
+  return r;
+}
+
+// MODE 0: the fused anisotropic kernel described above.
+// MODE 1: isotropic pass B -- v_k (A.vprev) and the per-pixel |v_k|^2 (A.nsq) are given; no IFFT,
+//         no state write: s = max(1 - tau/n, 0), w = (2s-1) v, r = b + rho D^T w, dim-1 FFT.
+template <int LM, bool HAS_VPREV, int MODE = 0>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
@@ -407,7 +443,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     if (tid == 64 % NT) l2_prefetch_bulk(A.bpk + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
   }
   // 1. x_k for columns j0-1 .. j0+nout (one halo column each side)
-  dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+  if (MODE == 0) dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
   // 2. stencil sweep: this thread owns rows i0 .. i0+RPT-1 of every column
   const float rho = *A.rho;
@@ -420,7 +456,15 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   const float2* bq = A.bpk + (size_t)q * plane;
 
   float2 w1c[RPT];
-  {
+  if (MODE == 1) {
+    const int j = jcol(1);
+    float2 vv[RPT];
+    float nn[RPT];
+    load_rows<RPT>(vp1 + (size_t)j * M + i0, vv);
+    load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, nn);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) w1c[r] = shrink_iso(vv[r], iso_scale(nn[r], tau)).w;
+  } else {
     const int j = jcol(1);
     float2 up[RPT], vst[RPT];
     if (HAS_VPREV) load_rows<RPT>(vp1 + (size_t)j * M + i0, up);
@@ -438,9 +482,15 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   for (int c = 1; c <= nout; c += CHUNK) {
     // (a) every global load of the chunk is issued before any of them is consumed
     float2 g1[CHUNK][RPT], g2[CHUNK][RPT + 1], gb[CHUNK][RPT];
+    float n1[MODE == 1 ? CHUNK : 1][RPT], n2[MODE == 1 ? CHUNK : 1][RPT + 1];
 #pragma unroll
     for (int cc = 0; cc < CHUNK; ++cc) {
       const int j = jcol(c + cc), jn = jcol(c + cc + 1);
+      if (MODE == 1) {
+        load_rows_f<RPT>(A.nsq + (size_t)jn * M + i0, n1[cc]);
+        load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, n2[cc]);
+        n2[cc][RPT] = A.nsq[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+      }
       if (HAS_VPREV) {
         load_rows<RPT>(vp1 + (size_t)jn * M + i0, g1[cc]);
         load_rows<RPT>(vp2 + (size_t)j * M + i0, g2[cc]);
@@ -454,6 +504,14 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     for (int cc = 0; cc < CHUNK; ++cc) {
       const int col = c + cc;
       const int j = jcol(col), jn = jcol(col + 1);
+      float2 w1n[RPT];
+      float2 w2[RPT + 1];
+      if (MODE == 1) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) w1n[r] = shrink_iso(g1[cc][r], iso_scale(n1[cc][r], tau)).w;
+#pragma unroll
+        for (int r = 0; r <= RPT; ++r) w2[r] = shrink_iso(g2[cc][r], iso_scale(n2[cc][r], tau)).w;
+      } else {
       float2 xc[RPT + 2];  // rows i0-1 .. i0+RPT of column col
       xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];
 #pragma unroll
@@ -461,7 +519,6 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       xc[RPT + 1] = X[sidx<LM>(col, (i0 + RPT) & (M - 1))];
 
       // channel 1 (dim-2 difference) at column col+1
-      float2 w1n[RPT];
       {
         float2 vst[RPT];
 #pragma unroll
@@ -475,7 +532,6 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       }
       // channel 2 (dim-1 difference) at column col, rows i0 .. i0+RPT (the last is the
       // neighbour's first row, recomputed here instead of exchanged)
-      float2 w2[RPT + 1];
       {
         float2 vst[RPT];
 #pragma unroll
@@ -487,6 +543,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
         }
         store_rows<RPT>(vn2 + (size_t)j * M + i0, vst);
       }
+      }  // MODE 0
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
         const float2 dt = cadd(csub(w1c[r], w1n[r]), csub(w2[r], w2[r + 1]));  // D^T(z-u)

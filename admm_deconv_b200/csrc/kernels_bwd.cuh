@@ -37,7 +37,36 @@ ADMMTV_DI float2 bwd_point(float2 d, float2 v, float2 eb, float rho, float tau, 
   return make_float2(eb.x - gb.x + m.x * q.x, eb.y - gb.y + m.y * q.y);
 }
 
-template <int LM, bool HAS_VBAR>
+// isotropic: per-pixel shrink scale s, the coefficient of v in vbar (1[n>tau] tau ip / n^3) and the
+// pixel's taubar term (1[n>tau] ip / n)
+ADMMTV_DI void iso_pix(float nsq, float ip, float tau, float& s, float& coef, float& tterm) {
+  const float n = sqrtf(nsq);
+  s = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
+  const bool act = n > tau;
+  coef = act ? tau * ip / (n * n * n) : 0.f;
+  tterm = act ? ip / n : 0.f;
+}
+// one (pixel, channel) of the isotropic adjoint; returns vbar_{k-1}
+ADMMTV_DI float2 iso_bwd_point(float2 d, float2 v, float2 eb, float rho, float s, float coef) {
+  const float2 gb = make_float2(rho * d.x, rho * d.y);
+  const float2 qq = make_float2(2.f * gb.x - eb.x, 2.f * gb.y - eb.y);
+  return make_float2(eb.x - gb.x + s * qq.x + coef * v.x, eb.y - gb.y + s * qq.y + coef * v.y);
+}
+ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float tau, float nsq, float ip, bool own, bool count_tau,
+                              double& racc, double& tacc) {
+  float s, coef, tt;
+  iso_pix(nsq, ip, tau, s, coef, tt);
+  if (own) {
+    const Shrunk g = shrink_iso(v, s);
+    racc += (double)(d.x * g.w.x) + (double)(d.y * g.w.y);
+    if (count_tau) tacc -= (double)tt;
+  }
+  return iso_bwd_point(d, v, eb, rho, s, coef);
+}
+
+// MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel |v_{k-1}|^2 in A.nsq, <q,v> in A.ip; bbar was
+// accumulated by pass A).
+template <int LM, bool HAS_VBAR, int MODE = 0>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
@@ -87,12 +116,18 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
   {
     const int j = jcol(1);
     float2 vv[RPT], ee[RPT];
+    float nn[RPT], pp[RPT];
     load_rows<RPT>(v1 + (size_t)j * M + i0, vv);
     if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)j * M + i0, ee);
+    if (MODE == 1) {
+      load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, nn);
+      load_rows_f<RPT>(A.ip + (size_t)j * M + i0, pp);
+    }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       const float2 d = csub(X[sidx<LM>(1, i0 + r)], X[sidx<LM>(0, i0 + r)]);
-      n1c[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, true, racc, tacc);
+      if (MODE == 1) n1c[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], true, false, racc, tacc);
+      else n1c[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, true, racc, tacc);
     }
     store_rows<RPT>(o1 + (size_t)j * M + i0, n1c);
   }
@@ -110,7 +145,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
       xc[RPT + 1] = X[sidx<LM>(col, (i0 + RPT) & (M - 1))];
 
       // bbar += rbar_k
-      {
+      if (MODE == 0) {
         float2 bb[RPT];
         if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, bb);
 #pragma unroll
@@ -122,12 +157,18 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
       {
         const bool own = col + 1 <= nout;
         float2 vv[RPT], ee[RPT];
+        float nn[RPT], pp[RPT];
         load_rows<RPT>(v1 + (size_t)jn * M + i0, vv);
         if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)jn * M + i0, ee);
+        if (MODE == 1) {
+          load_rows_f<RPT>(A.nsq + (size_t)jn * M + i0, nn);
+          load_rows_f<RPT>(A.ip + (size_t)jn * M + i0, pp);
+        }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
           const float2 d = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
-          n1n[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, own, racc, tacc);
+          if (MODE == 1) n1n[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], own, false, racc, tacc);
+          else n1n[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, own, racc, tacc);
         }
         if (own) store_rows<RPT>(o1 + (size_t)jn * M + i0, n1n);
       }
@@ -135,16 +176,25 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
       float2 n2[RPT + 1];
       {
         float2 vv[RPT + 1], ee[RPT + 1];
+        float nn[RPT + 1], pp[RPT + 1];
         load_rows<RPT>(v2 + (size_t)j * M + i0, vv);
         vv[RPT] = v2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
         if (HAS_VBAR) {
           load_rows<RPT>(e2 + (size_t)j * M + i0, ee);
           ee[RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
         }
+        if (MODE == 1) {
+          load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, nn);
+          nn[RPT] = A.nsq[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+          load_rows_f<RPT>(A.ip + (size_t)j * M + i0, pp);
+          pp[RPT] = A.ip[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        }
 #pragma unroll
         for (int r = 0; r <= RPT; ++r) {
           const float2 d = csub(xc[r + 1], xc[r]);
-          n2[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, r < RPT, racc, tacc);
+          // the taubar term is per PIXEL: counted once, by pair 0, with the pixel's channel-2 point
+          if (MODE == 1) n2[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], r < RPT, q == 0, racc, tacc);
+          else n2[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, r < RPT, racc, tacc);
         }
         store_rows<RPT>(o2 + (size_t)j * M + i0, n2);
       }
