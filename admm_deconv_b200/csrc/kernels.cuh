@@ -103,11 +103,29 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_CHUNK9
 #define ADMMTV_CHUNK9 2
 #endif
+#ifndef ADMMTV_NT11
+#define ADMMTV_NT11 512
+#endif
+#ifndef ADMMTV_TC11
+#define ADMMTV_TC11 6
+#endif
+#ifndef ADMMTV_TR11
+#define ADMMTV_TR11 8
+#endif
+#ifndef ADMMTV_CHUNK8
+#define ADMMTV_CHUNK8 8
+#endif
+#ifndef ADMMTV_TC8
+#define ADMMTV_TC8 10
+#endif
 #ifndef ADMMTV_TR9
 #define ADMMTV_TR9 16
 #endif
 #ifndef ADMMTV_NT2
 #define ADMMTV_NT2 256
+#endif
+#ifndef ADMMTV_NT2_MAX
+#define ADMMTV_NT2_MAX 512
 #endif
 #ifndef ADMMTV_MINB2
 #define ADMMTV_MINB2 1
@@ -126,12 +144,12 @@ ADMMTV_DI void l2_prefetch_bulk(const void* p, unsigned bytes) {
 template <int LM>
 struct Dim1Cfg {
   static constexpr int M = 1 << LM;
-  static constexpr int NT = LM <= 8 ? M : (LM == 9 ? ADMMTV_NT9 : (LM <= 11 ? 256 : 512));
+  static constexpr int NT = LM <= 8 ? M : (LM == 9 ? ADMMTV_NT9 : (LM == 10 ? 256 : (LM == 11 ? ADMMTV_NT11 : 512)));
   static constexpr int MINB = LM == 9 ? ADMMTV_MINB9 : 1;
   static constexpr int RPT = M / NT;                  // rows per thread in the stencil sweep
-  static constexpr int CHUNK = LM == 9 ? ADMMTV_CHUNK9 : (RPT >= 8 ? 1 : 8 / RPT);  // columns between barriers
+  static constexpr int CHUNK = LM == 9 ? ADMMTV_CHUNK9 : (LM == 8 ? ADMMTV_CHUNK8 : (RPT >= 8 ? 1 : 8 / RPT));  // columns between barriers
   // tile columns including the 2 halo columns
-  static constexpr int TC = LM <= 7 ? 34 : (LM == 8 ? 18 : (LM == 9 ? ADMMTV_TC9 : 6));
+  static constexpr int TC = LM <= 7 ? 34 : (LM == 8 ? ADMMTV_TC8 : (LM == 9 ? ADMMTV_TC9 : (LM == 11 ? ADMMTV_TC11 : 6)));
   static constexpr int CO = TC - 2;                   // output columns per block
   static constexpr size_t SMEM = (size_t)TC * M * sizeof(float2);
 };
@@ -573,8 +591,11 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 template <int LN>
 struct Dim2Cfg {
   static constexpr int N = 1 << LN;
-  static constexpr int TR = LN <= 8 ? 16 : (LN == 9 ? ADMMTV_TR9 : (LN <= 11 ? 8 : 4));
-  static constexpr int NT = LN == 9 ? ADMMTV_NT2 : 256;
+  static constexpr int TR = LN <= 8 ? 16 : (LN == 9 ? ADMMTV_TR9 : (LN == 10 ? 8 : (LN == 11 ? ADMMTV_TR11 : 4)));
+  // block size = work items of the widest pass (row pairs x N / largest radix), within [32, 512]
+  static constexpr int ITEMS_MAX = (TR / 2) * (N / plan_radix(N, 0));
+  static constexpr int NT_AUTO = ITEMS_MAX < 32 ? 32 : (ITEMS_MAX > ADMMTV_NT2_MAX ? ADMMTV_NT2_MAX : ITEMS_MAX);
+  static constexpr int NT = LN == 9 ? ADMMTV_NT2 : NT_AUTO;
   static constexpr int MINB = LN == 9 ? ADMMTV_MINB2 : 1;
   static constexpr size_t SMEM = (size_t)N * TR * sizeof(float2);
 };

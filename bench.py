@@ -36,6 +36,8 @@ WORKLOADS = {
                  desc="BASELINE.json configs[3]: batch 16 x 2048x2048 gray, 31x31 PSF, 200-iteration forward"),
     "cfg5": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="fwd",
                  desc="BASELINE.json configs[4] (shared PSF variant): batch 1024 x 128x128, 50 iterations"),
+    "cfg3": dict(B=32, P=3, N=256, M=256, k=15, iters=10, mode="fwd+bwd",
+                 desc="BASELINE.json configs[2] per-GPU share: 32 x 256x256 RGB (256 images over 8 GPUs), Gaussian PSF 15x15, 10 unrolled iterations, forward+backward + gradient all-reduce"),
     "tiny": dict(B=2, P=3, N=64, M=64, k=7, iters=10, mode="fwd", desc="tiny debug workload"),
 }
 FWD_BYTES = 40.0   # algorithmic bytes / plane-pixel-iteration, forward  
@@ -164,7 +166,7 @@ def cpu_baseline(w):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sB, s_iters = 1, min(w["iters"], 50)
+    sB, s_iters = (2 if w["M"] <= 512 else 1), min(w["iters"], 100)
     y, hk = make_inputs(dict(w, B=sB), 1001)
     yj = y.permute(3, 2, 1, 0).contiguous(); hj = hk.permute(3, 2, 1, 0).contiguous()
     lam = torch.tensor([0.0041]); rho = torch.tensor([0.021])
@@ -244,16 +246,38 @@ def run_native(args, w):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    # end-to-end: host (pinned) -> device, hot path, device -> host, every step
-    yd = torch.empty_like(y)
-    step(yd.copy_(y_host, non_blocking=True))
+    # end-to-end: every step copies its input host(pinned) -> device and its result device -> host inside the
+    # timed region.  Copies run on a side stream and are double-buffered, so step i+1's upload and step i-1's
+    # download overlap step i's compute (what a serving loop would do); all of them finish before the clock stops.
+    cs = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    yd = [torch.empty_like(y) for _ in range(2)]
+    xd = [None, None]
+    up = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    down = [torch.cuda.Event() for _ in range(2)]
+    step(yd[0].copy_(y_host, non_blocking=True))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        yd.copy_(y_host, non_blocking=True)
-        x = step(yd)
-        x_host.copy_(x, non_blocking=True)
+    with torch.cuda.stream(cs):
+        yd[0].copy_(y_host, non_blocking=True); up[0].record(cs)
+    for i in range(args.steps):
+        b = i & 1
+        if i + 1 < args.steps:
+            with torch.cuda.stream(cs):
+                if i >= 1:
+                    cs.wait_event(done[1 - b])          # buffer 1-b was read by step i-1
+                yd[1 - b].copy_(y_host, non_blocking=True); up[1 - b].record(cs)
+        main.wait_event(up[b])
+        if i >= 2:
+            main.wait_event(down[b])                    # x buffer b fully downloaded before it is reused
+        xd[b] = step(yd[b])
+        done[b].record(main)
+        with torch.cuda.stream(cs):
+            cs.wait_event(done[b])
+            x_host.copy_(xd[b], non_blocking=True); down[b].record(cs)
+    main.wait_stream(cs)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)

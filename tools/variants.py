@@ -33,6 +33,16 @@ VARIANTS = {
     "c2mb3": ("ADMMTV_CHUNK9=2", "ADMMTV_MINB9=3"),
     "c4mb3": ("ADMMTV_CHUNK9=4", "ADMMTV_MINB9=3"),
     "c2mb4": ("ADMMTV_CHUNK9=2", "ADMMTV_MINB9=4"),
+    "n11_512": ("ADMMTV_NT11=512",),
+    "n11_512_t10": ("ADMMTV_NT11=512", "ADMMTV_TC11=10"),
+    "n11_256_t10": ("ADMMTV_NT11=256", "ADMMTV_TC11=10"),
+    "n2max256": ("ADMMTV_NT2_MAX=256",),
+    "tr11_4": ("ADMMTV_TR11=4",),
+    "c8_4": ("ADMMTV_CHUNK8=4",),
+    "c8_2": ("ADMMTV_CHUNK8=2",),
+    "c8_4_t10": ("ADMMTV_CHUNK8=4", "ADMMTV_TC8=10"),
+    "c8_8_t10": ("ADMMTV_CHUNK8=8", "ADMMTV_TC8=10"),
+    "c8_4_t34": ("ADMMTV_CHUNK8=4", "ADMMTV_TC8=34"),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
@@ -45,6 +55,7 @@ VARIANTS = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(VARIANTS)
+    SIZES = tuple(int(a[2:]) for a in sys.argv[1:] if a.startswith("-s")) or (9,)
+    names = [a for a in sys.argv[1:] if not a.startswith("-s")] or list(VARIANTS)
     for n in names:
-        print(B.build(tag=n, defines=VARIANTS[n], sizes=(9,)))
+        print(B.build(tag=n, defines=VARIANTS[n], sizes=SIZES))
