@@ -225,7 +225,7 @@ def run_native(args, w):
         if world > 1:
             buf = torch.cat([h.grad.reshape(-1), lam.grad, rho.grad])
             dist.all_reduce(buf)
-        return x
+        return x.detach()      # drop the graph (and its checkpoint buffer) as soon as the step is over
 
     def barrier():
         if world > 1:
