@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libadmmtv.so")
 ACT = {"identity": 0, "relu": 1, "relu6": 2, "relu1": 3}
 FLAG_NO_CLAMP = 1
 FLAG_NOGRAD_REPEAT = 2
+FLAG_SHARED_INPUT = 4
+FLAG_CHANNEL_CONCAT = 8
 
 # every symbol include/admmtv.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
@@ -41,7 +43,7 @@ class Desc(C.Structure):
         ("kh", C.c_int32), ("kw", C.c_int32),
         ("iters", C.c_int32), ("iso", C.c_int32), ("activation", C.c_int32), ("has_bias", C.c_int32),
         ("device", C.c_int32), ("flags", C.c_int32),
-        ("creg", C.c_float), ("reserved", C.c_int32),
+        ("creg", C.c_float), ("groups", C.c_int32),
     ]
 
 
@@ -144,6 +146,6 @@ def load() -> AdmmTvLib:
 
 
 def make_desc(M, N, P, B, kh, kw, iters, iso=False, activation="identity", has_bias=False, device=0, flags=0,
-              creg=0.0) -> Desc:
+              creg=0.0, groups=0) -> Desc:
     act = ACT[activation] if isinstance(activation, str) else int(activation)
-    return Desc(M, N, P, B, kh, kw, iters, int(bool(iso)), act, int(bool(has_bias)), device, flags, float(creg), 0)
+    return Desc(M, N, P, B, kh, kw, iters, int(bool(iso)), act, int(bool(has_bias)), device, flags, float(creg), int(groups))

@@ -24,6 +24,14 @@ static Geom geom(const admmtv_desc* d) {
   g.Q = (g.S + 1) / 2;
   g.LM = ilog2(d->M); g.LN = ilog2(d->N);
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
+  g.G = d->groups > 1 ? d->groups : 1;
+  g.Bg = d->B / g.G;
+  g.Sg = d->P * g.Bg;
+  g.Qg = (g.Sg + 1) / 2;
+  g.Q = g.G * g.Qg;
+  g.pm.P = d->P; g.pm.Sg = g.Sg; g.pm.Qg = g.Qg; g.pm.G = g.G;
+  g.pm.in_gstride = (d->flags & ADMMTV_FLAG_SHARED_INPUT) ? 0 : g.Sg;
+  g.pm.concat = (d->flags & ADMMTV_FLAG_CHANNEL_CONCAT) ? 1 : 0;
   g.plane = (size_t)d->N * d->M;
   g.pk = g.plane * g.Q;
   return g;
@@ -57,17 +65,17 @@ static FwdWs carve_fwd(const Geom& g, void* ws) {
   FwdWs w;
   w.twM = c.take<float2>(g.M);
   w.twN = c.take<float2>(g.N);
-  w.T = c.take<double2>((size_t)g.M * (g.kw > 0 ? g.kw : 1));
-  w.ctab = c.take<float>(g.plane);
-  w.ktab = c.take<float2>(g.plane);
-  w.mask = c.take<float>(g.nh + 2);
+  w.T = c.take<double2>((size_t)g.M * (g.kw > 0 ? g.kw : 1) * g.G);
+  w.ctab = c.take<float>(g.plane * g.G);
+  w.ktab = c.take<float2>(g.plane * g.G);
+  w.mask = c.take<float>((size_t)(g.nh + 2) * g.G);
   w.bpk = c.take<float2>(g.pk);
   w.specA = c.take<float2>(g.pk);
   w.specB = c.take<float2>(g.pk);
   w.v0 = c.take<float2>(2 * g.pk);
   w.v1 = c.take<float2>(2 * g.pk);
-  w.nsq0 = c.take<float>(g.plane);
-  w.nsq1 = c.take<float>(g.plane);
+  w.nsq0 = c.take<float>(g.plane * g.G);
+  w.nsq1 = c.take<float>(g.plane * g.G);
   w.bytes = c.off;
   return w;
 }
@@ -153,15 +161,16 @@ static int run_setup(const Geom& g, const float* h, const float* rho, float2* tw
     ADMMTV_LAUNCH(k_setup_twiddles, dim3((n + 255) / 256), dim3(256), 0, st, twM, g.M, twN, g.N);
     ADMMTV_CHECK_LAUNCH();
   }
+  // one table set per group (blockIdx.y = group)
   if (g.kh > 0) {
     const int n = g.M * g.kw;
-    ADMMTV_LAUNCH(k_setup_psf_dim1, dim3((n + 127) / 128), dim3(128), 0, st, h, g.kh, g.kw, g.M, T);
+    ADMMTV_LAUNCH(k_setup_psf_dim1, dim3((n + 127) / 128, (unsigned)g.G), dim3(128), 0, st, h, g.kh, g.kw, g.M, T);
     ADMMTV_CHECK_LAUNCH();
   }
   {
     const size_t n = g.plane;
-    ADMMTV_LAUNCH(k_setup_tables, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, (const double2*)T, g.kh, g.kw, g.M,
-                  g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig);
+    ADMMTV_LAUNCH(k_setup_tables, dim3((unsigned)((n + 127) / 128), (unsigned)g.G), dim3(128), 0, st, (const double2*)T, g.kh,
+                  g.kw, g.M, g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig);
     ADMMTV_CHECK_LAUNCH();
   }
   return 0;
@@ -202,8 +211,10 @@ int admmtv_check(const admmtv_desc* d) {
   if (d->iso != 0 && d->iso != 1) return ADMMTV_ERR_ENUM;
   if (d->activation < 0 || d->activation > 3) return ADMMTV_ERR_ENUM;
   if (d->has_bias != 0 && d->has_bias != 1) return ADMMTV_ERR_ENUM;
-  if (d->flags & ~(ADMMTV_FLAG_NO_CLAMP | ADMMTV_FLAG_NOGRAD_REPEAT)) return ADMMTV_ERR_ENUM;
-  if (d->reserved != 0) return ADMMTV_ERR_ENUM;
+  if (d->flags & ~(ADMMTV_FLAG_NO_CLAMP | ADMMTV_FLAG_NOGRAD_REPEAT | ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT))
+    return ADMMTV_ERR_ENUM;
+  if (d->groups < 0 || (d->groups > 1 && d->B % d->groups != 0)) return ADMMTV_ERR_SHAPE;
+  if (d->groups <= 1 && (d->flags & (ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT))) return ADMMTV_ERR_ENUM;
   if (d->device < 0) return ADMMTV_ERR_ENUM;
   return ADMMTV_OK;
 }
@@ -263,6 +274,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   if (d->kh > 0 && !h) return ADMMTV_ERR_NULL;
   if (d->has_bias && !bias) return ADMMTV_ERR_NULL;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ADMMTV_ERR_ALIGN;
+  if (d->groups > 1 && ckpt) return ADMMTV_ERR_UNSUPPORTED;  // grouped calls are forward-only
   DeviceGuard guard(d->device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -273,7 +285,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
 
   tm_mark(tm, st, 2);
   // deconv_admm.jl:216-219 (persisted clamp) + gradient masks for the pullback
-  ADMMTV_LAUNCH(k_clamp_params, dim3(1), dim3(128), 0, st, lambda, rho, h, g.nh, d->creg,
+  ADMMTV_LAUNCH(k_clamp_params, dim3((unsigned)g.G), dim3(128), 0, st, lambda, rho, h, g.nh, d->creg,
                 (d->flags & ADMMTV_FLAG_NO_CLAMP) ? 0 : 1, ckpt ? ck.mask : w.mask);
   ADMMTV_CHECK_LAUNCH();
   if ((rc = run_setup(g, h, rho, w.twM, w.twN, w.T, w.ctab, w.ktab, nullptr, st))) return rc;
@@ -281,7 +293,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   // y -> pair-pack -> dim-1 spectrum (ops.jl:101 + first FFT pass)
   {
     PackArgs a{};
-    a.src = y; a.spec = w.specA; a.twM = w.twM; a.N = g.N; a.S = g.S;
+    a.src = y; a.spec = w.specA; a.twM = w.twM; a.N = g.N; a.S = g.S; a.pm = g.pm;
     a.packed_out = g.kh > 0 ? nullptr : w.bpk;  // empty h: b = y (ops.jl:149-151)
     if ((rc = run_pack_fft1(g, 0, a, st))) return rc;
   }
@@ -289,12 +301,13 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
     // b = H^T y = F^-1( conj(K) F y )  (ops.jl:163,168; hoisted out of the loop)
     Dim2Args a{};
     a.in = w.specA; a.out = w.specB; a.ktab = w.ktab; a.twN = w.twN; a.M = g.M;
+    a.Qg = g.Qg; a.tab_stride = g.G > 1 ? g.plane : 0;
     if ((rc = run_dim2(g, D2_KCONJ, a, st))) return rc;
     OutArgs o{};
-    o.spec = w.specB; o.packed = w.bpk; o.twM = w.twM; o.N = g.N; o.S = g.S;
+    o.spec = w.specB; o.packed = w.bpk; o.twM = w.twM; o.N = g.N; o.S = g.S; o.pm = g.pm;
     if ((rc = run_dim1_out(g, 0, o, st))) return rc;
     PackArgs p{};
-    p.src_packed = w.bpk; p.spec = w.specA; p.twM = w.twM; p.N = g.N; p.S = g.S;
+    p.src_packed = w.bpk; p.spec = w.specA; p.twM = w.twM; p.N = g.N; p.S = g.S; p.pm = g.pm;
     if ((rc = run_pack_fft1(g, 2, p, st))) return rc;
   }
 
@@ -302,13 +315,14 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   for (int k = 1; k <= g.K; ++k) {
     Dim2Args a{};
     a.in = w.specA; a.out = w.specB; a.ctab = w.ctab; a.twN = w.twN; a.M = g.M;
+    a.Qg = g.Qg; a.tab_stride = g.G > 1 ? g.plane : 0;
     if (ckpt) a.zsave = ck.zck + (size_t)(k - 1) * g.pk;
     tm_mark(tm, st, 0);
     if ((rc = run_dim2(g, ckpt ? D2_C_SAVE : D2_C, a, st))) return rc;
     if (k < g.K && !d->iso) {
       Dim1FwdArgs f{};
       f.spec_in = w.specB; f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM;
-      f.lambda = lambda; f.rho = rho; f.N = g.N;
+      f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
       if (ckpt) {
         f.vprev = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
         f.vnew = ck.vck + (size_t)(k - 1) * 2 * g.pk;
@@ -322,7 +336,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       // isotropic: v_k and the per-pixel norm first (pass A), then shrink + D^T + FFT (pass B)
       IsoArgs a2{};
       a2.spec_in = w.specB; a2.spec_out = w.specA; a2.bpk = w.bpk; a2.twM = w.twM;
-      a2.lambda = lambda; a2.rho = rho; a2.N = g.N; a2.S = g.S;
+      a2.lambda = lambda; a2.rho = rho; a2.N = g.N; a2.S = g.S; a2.Qg = g.Qg;
       float* nsq_new;
       if (ckpt) {
         a2.v_in = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
@@ -336,13 +350,13 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
         nsq_new = (k & 1) ? w.nsq0 : w.nsq1;
       }
       a2.nsq_out = nsq_new;
-      cudaError_t e2 = cudaMemsetAsync(nsq_new, 0, g.plane * sizeof(float), st);
+      cudaError_t e2 = cudaMemsetAsync(nsq_new, 0, g.plane * g.G * sizeof(float), st);
       if (e2 != cudaSuccess) return (int)e2;
       tm_mark(tm, st, 1);
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::iso(g, 0, k > 1, a2, st); })
       if (rc) return rc;
       Dim1FwdArgs f{};
-      f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM; f.lambda = lambda; f.rho = rho; f.N = g.N;
+      f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM; f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
       f.vprev = a2.v_out; f.nsq = nsq_new;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_b(g, f, st); })
       if (rc) return rc;
@@ -353,7 +367,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   {
     OutArgs o{};
     o.spec = w.specB; o.planes = x_out; o.bias = d->has_bias ? bias : nullptr; o.twM = w.twM;
-    o.N = g.N; o.S = g.S; o.act = d->activation;
+    o.N = g.N; o.S = g.S; o.act = d->activation; o.pm = g.pm;
     if ((rc = run_dim1_out(g, 1, o, st))) return rc;
   }
   tm_mark(tm, st, -1);
@@ -408,6 +422,7 @@ int admmtv_forward_host(const admmtv_desc* d, const float* y, float* h, float* l
   size_t fwd = 0;
   admmtv_workspace_bytes(d, &fwd, nullptr, nullptr);
   const size_t nimg = g.plane * g.S * sizeof(float);
+  if (d->groups > 1) return ADMMTV_ERR_UNSUPPORTED;  // host convenience path: single call only
   unsigned char* dev = nullptr;
   const size_t o_y = 0, o_x = align256(nimg), o_h = o_x + align256(nimg), o_l = o_h + align256((g.nh + 1) * sizeof(float)),
                o_r = o_l + 256, o_b = o_r + 256, o_ws = o_b + 256;

@@ -7,8 +7,32 @@
 
 namespace admmtv {
 
+// Plane bookkeeping for grouped calls: G independent problems of identical shape batched into one
+// launch sequence (per-image PSFs / noise levels, or the 5 parallel branches of net_build.jl:113-128).
+// Pairs never straddle groups: group g owns pairs [g*Qg, (g+1)*Qg) and Sg = P*Bg planes.
+struct PlaneMap {
+  int P, Sg, Qg, G;
+  int in_gstride;  // planes between consecutive groups in the INPUT (Sg, or 0 when all groups share y)
+  int concat;      // 1: output is (M,N,G*P,Bg), group g in channels [g*P,(g+1)*P)  (Flux chcat)
+};
+// index (in planes of N*M floats) of plane c (0/1) of pair q, or -1 if the pair's second plane is padding
+ADMMTV_HD inline long pm_in(const PlaneMap& m, int q, int c) {
+  const int g = q / m.Qg, sl = 2 * (q % m.Qg) + c;
+  if (sl >= m.Sg) return -1;
+  return (long)g * m.in_gstride + sl;
+}
+ADMMTV_HD inline long pm_out(const PlaneMap& m, int q, int c) {
+  const int g = q / m.Qg, sl = 2 * (q % m.Qg) + c;
+  if (sl >= m.Sg) return -1;
+  if (!m.concat) return (long)g * m.Sg + sl;
+  const int bl = sl / m.P, pp = sl % m.P;
+  return (long)bl * (m.G * m.P) + g * m.P + pp;
+}
+
 struct Geom {
   int M, N, P, B, S, Q, LM, LN, K, kh, kw, nh;
+  int G, Bg, Sg, Qg;  // groups, images / planes / pairs per group (S = G*Sg planes, Q = G*Qg pairs)
+  PlaneMap pm;
   size_t plane;  // N*M
   size_t pk;     // Q*N*M  (pair-packed complex elements)
 };
@@ -21,6 +45,7 @@ struct PackArgs {
   float2* spec;        // [Q][N][M]
   const float2* twM;
   double* bias_acc;    // MODE 1, may be null
+  PlaneMap pm;
   int N, S, act;
 };
 
@@ -30,6 +55,7 @@ struct OutArgs {
   float* planes;       // MODE 1: (M,N,S)
   const float* bias;   // MODE 1, may be null
   const float2* twM;
+  PlaneMap pm;
   int N, S, act;
 };
 
@@ -41,9 +67,10 @@ struct Dim1FwdArgs {
   float2* vnew;         // [Q][2][N][M]
   const float* nsq;     // isotropic pass B: per-pixel |v|^2 [N][M]
   const float2* twM;
-  const float* lambda;
-  const float* rho;
+  const float* lambda;  // [G]
+  const float* rho;     // [G]
   int N;
+  int Qg;               // pairs per group: group of pair q = q / Qg
 };
 
 struct Dim2Args {
@@ -57,6 +84,8 @@ struct Dim2Args {
   const float2* twN;
   int M;
   int Q;               // number of plane pairs (blocks loop q = blockIdx.y, += gridDim.y)
+  int Qg;              // pairs per group
+  size_t tab_stride;   // elements between the tables of consecutive groups (N*M, or 0 for one group)
 };
 
 struct Dim1BwdArgs {
@@ -73,6 +102,7 @@ struct Dim1BwdArgs {
   double* acc;             // [0] rhobar (direct term), [1] taubar
   const float* nsq;        // isotropic pass B: |v_{k-1}|^2 per pixel
   const float* ip;         // isotropic pass B: <q, v_{k-1}> per pixel
+  PlaneMap pm;
   int N, S;
   int first;               // 1: bbar is written, not accumulated (k = K)
 };
@@ -95,6 +125,7 @@ struct IsoArgs {
   const float* rho;
   double* acc;
   int N, S, first;
+  int Qg;
 };
 
 // variants of k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)

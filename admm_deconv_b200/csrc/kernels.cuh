@@ -289,9 +289,12 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
   const int j0 = blockIdx.x * CO;
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
-  const bool has_b = 2 * q + 1 < A.S;
-  const float* pa = A.src + (size_t)(2 * q) * plane;
-  const float* pb = A.src + (size_t)(2 * q + 1) * plane;
+  // MODE 1 reads the layer OUTPUT's cotangent, so it uses the output plane map
+  const long ia = MODE == 1 ? pm_out(A.pm, q, 0) : pm_in(A.pm, q, 0);
+  const long ib = MODE == 1 ? pm_out(A.pm, q, 1) : pm_in(A.pm, q, 1);
+  const bool has_b = ib >= 0;
+  const float* pa = A.src + (size_t)ia * plane;
+  const float* pb = A.src + (size_t)(has_b ? ib : 0) * plane;
   double bsum = 0.0;
   for (int e = tid; e < nout * M; e += NT) {
     const int c = e / M, i = e % M;
@@ -303,8 +306,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
     float va = pa[off], vb = has_b ? pb[off] : 0.f;
     if (MODE == 0 && A.packed_out) A.packed_out[(size_t)q * plane + off] = make_float2(va, vb);
     if (MODE == 1) {
-      va *= act_grad_from_out(A.xout[(size_t)(2 * q) * plane + off], A.act);
-      if (has_b) vb *= act_grad_from_out(A.xout[(size_t)(2 * q + 1) * plane + off], A.act);
+      va *= act_grad_from_out(A.xout[(size_t)ia * plane + off], A.act);
+      if (has_b) vb *= act_grad_from_out(A.xout[(size_t)ib * plane + off], A.act);
       bsum += (double)va + (double)vb;
     }
     X[sidx<LM>(c, i)] = make_float2(va, vb);
@@ -342,10 +345,11 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
       dst[(size_t)(j0 + c) * M + i] = X[sidx<LM>(c, i)];
     }
   } else {
-    const bool has_b = 2 * q + 1 < A.S;
-    const float bias = A.bias ? *A.bias : 0.f;
-    float* pa = A.planes + (size_t)(2 * q) * plane;
-    float* pb = A.planes + (size_t)(2 * q + 1) * plane;
+    const long ia = pm_out(A.pm, q, 0), ib = pm_out(A.pm, q, 1);
+    const bool has_b = ib >= 0;
+    const float bias = A.bias ? A.bias[q / A.pm.Qg] : 0.f;
+    float* pa = A.planes + (size_t)ia * plane;
+    float* pb = A.planes + (size_t)(has_b ? ib : 0) * plane;
     for (int e = tid; e < nout * M; e += NT) {
       const int c = e / M, i = e % M;
       const float2 v = X[sidx<LM>(c, i)];
@@ -464,9 +468,11 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   if (MODE == 0) dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
   // 2. stencil sweep: this thread owns rows i0 .. i0+RPT-1 of every column
-  const float rho = *A.rho;
-  const float tau = *A.lambda / rho;  // ops.jl:102
+  const int grp = q / A.Qg;
+  const float rho = A.rho[grp];
+  const float tau = A.lambda[grp] / rho;  // ops.jl:102
   const int i0 = tid * RPT;
+  const float* nsq_g = MODE == 1 ? A.nsq + (size_t)grp * plane : nullptr;
   const float2* vp1 = A.vprev + ((size_t)q * 2 + 0) * plane;
   const float2* vp2 = A.vprev + ((size_t)q * 2 + 1) * plane;
   float2* vn1 = A.vnew + ((size_t)q * 2 + 0) * plane;
@@ -479,7 +485,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     float2 vv[RPT];
     float nn[RPT];
     load_rows<RPT>(vp1 + (size_t)j * M + i0, vv);
-    load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, nn);
+    load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
 #pragma unroll
     for (int r = 0; r < RPT; ++r) w1c[r] = shrink_iso(vv[r], iso_scale(nn[r], tau)).w;
   } else {
@@ -505,9 +511,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     for (int cc = 0; cc < CHUNK; ++cc) {
       const int j = jcol(c + cc), jn = jcol(c + cc + 1);
       if (MODE == 1) {
-        load_rows_f<RPT>(A.nsq + (size_t)jn * M + i0, n1[cc]);
-        load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, n2[cc]);
-        n2[cc][RPT] = A.nsq[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        load_rows_f<RPT>(nsq_g + (size_t)jn * M + i0, n1[cc]);
+        load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, n2[cc]);
+        n2[cc][RPT] = nsq_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
       }
       if (HAS_VPREV) {
         load_rows<RPT>(vp1 + (size_t)jn * M + i0, g1[cc]);
@@ -677,6 +683,7 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
 
   for (int q = blockIdx.y; q < A.Q; q += gridDim.y) {
     const size_t qoff = (size_t)q * N * M;
+    const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;  // this group's tables
     const float2* src = A.in + qoff + i0;
     if (ACC != 0) {
       // the second spectrum is consumed in the fused stage: start pulling it into L2 now
@@ -751,11 +758,11 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
         }
         if (!FWD_ONLY) {
           if (MUL == 0) {
-            const float2 cc = *reinterpret_cast<const float2*>(A.ctab + g);
+            const float2 cc = *reinterpret_cast<const float2*>(A.ctab + toff + g);
             a0[m] = cscale(a0[m], cc.x);
             a1[m] = cscale(a1[m], cc.y);
           } else {
-            const float4 kk = *reinterpret_cast<const float4*>(A.ktab + g);
+            const float4 kk = *reinterpret_cast<const float4*>(A.ktab + toff + g);
             const float sgn = MUL == 2 ? -1.f : 1.f;
             a0[m] = cmul(a0[m], make_float2(kk.x, sgn * kk.y));
             a1[m] = cmul(a1[m], make_float2(kk.z, sgn * kk.w));

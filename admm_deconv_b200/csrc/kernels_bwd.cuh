@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A
   const float2* sin_q = A.spec_in + (size_t)q * plane;
   dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sin_q + (size_t)(j0 + c) * M; }, A.twM, tid);
   const float2* bq = A.bbar + (size_t)q * plane;
-  const bool has_b = 2 * q + 1 < A.S;
+  const long ia = pm_in(A.pm, q, 0), ib = pm_in(A.pm, q, 1);  // ybar has y's layout
+  const bool has_b = ib >= 0;
   for (int e = tid; e < nout * M; e += NT) {
     const int c = e / M, i = e % M;
     const size_t off = (size_t)(j0 + c) * M + i;
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A
     if (!A.first) v = cadd(v, bq[off]);
     if (MODE == 0) X[sidx<LM>(c, i)] = v;
     else {
-      A.ybar[(size_t)(2 * q) * plane + off] = v.x;
-      if (has_b) A.ybar[(size_t)(2 * q + 1) * plane + off] = v.y;
+      A.ybar[(size_t)ia * plane + off] = v.x;
+      if (has_b) A.ybar[(size_t)ib * plane + off] = v.y;
     }
   }
   if (MODE == 0) {

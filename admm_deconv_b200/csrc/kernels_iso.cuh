@@ -36,8 +36,11 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_iso_fwd_a(IsoArgs A) {
   const float2* sin_q = A.spec_in + (size_t)q * plane;
   // columns c = 0..nout  <->  j = j0-1+c
   dim1_ifft_to_smem<LM, NT>(X, nout + 1, [&](int c) { return sin_q + (size_t)jwrap<LM>(j0 - 1 + c, N) * M; }, A.twM, tid);
-  const float rho = *A.rho;
-  const float tau = *A.lambda / rho;
+  const int grp = q / A.Qg;
+  const float rho = A.rho[grp];
+  const float tau = A.lambda[grp] / rho;
+  const float* nsq_in = A.nsq_in + (size_t)grp * plane;
+  float* nsq_out = A.nsq_out + (size_t)grp * plane;
   const float2* vp1 = A.v_in + ((size_t)q * 2 + 0) * plane;
   const float2* vp2 = A.v_in + ((size_t)q * 2 + 1) * plane;
   float2* vn1 = A.v_out + ((size_t)q * 2 + 0) * plane;
@@ -49,13 +52,13 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_iso_fwd_a(IsoArgs A) {
     float2 v1 = csub(x, X[sidx<LM>(c - 1, i)]);
     float2 v2 = csub(x, X[sidx<LM>(c, (i - 1) & (M - 1))]);
     if (HAS_VPREV) {
-      const float s = iso_scale(A.nsq_in[off], tau);
+      const float s = iso_scale(nsq_in[off], tau);
       v1 = cadd(v1, shrink_iso(vp1[off], s).u);
       v2 = cadd(v2, shrink_iso(vp2[off], s).u);
     }
     vn1[off] = v1;
     vn2[off] = v2;
-    atomicAdd(A.nsq_out + off, v1.x * v1.x + v1.y * v1.y + v2.x * v2.x + v2.y * v2.y);
+    atomicAdd(nsq_out + off, v1.x * v1.x + v1.y * v1.y + v2.x * v2.x + v2.y * v2.y);
   }
 }
 

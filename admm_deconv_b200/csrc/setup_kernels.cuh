@@ -28,6 +28,11 @@ static __global__ void k_setup_twiddles(float2* twM, int M, float2* twN, int N) 
 // clamp of deconv_admm.jl:216-219, in place; masks (1 = gradient passes) into `mask`:
 // mask[0] = lambda, mask[1] = rho, mask[2..2+kh*kw) = h
 static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int nh, float creg, int do_clamp, float* mask) {
+  // one block per group
+  lambda += blockIdx.x;
+  rho += blockIdx.x;
+  if (h) h += (size_t)blockIdx.x * nh;
+  if (mask) mask += (size_t)blockIdx.x * (nh + 2);
   for (int i = threadIdx.x; i < nh + 2; i += blockDim.x) {
     float* p = i == 0 ? lambda : (i == 1 ? rho : h + (i - 2));
     const float v = *p;
@@ -49,6 +54,8 @@ static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int n
 static __global__ void k_setup_psf_dim1(const float* __restrict__ h, int kh, int kw, int M, double2* T) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * kw) return;
+  h += (size_t)blockIdx.y * kh * kw;      // blockIdx.y = group
+  T += (size_t)blockIdx.y * M * kw;
   const int k1 = idx / kw, b = idx % kw;
   double re = 0.0, im = 0.0;
   for (int a = 0; a < kh; ++a) {
@@ -69,6 +76,14 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
                                       const float* __restrict__ rho_p, float* ctab, float2* ktab, float2* sig) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
+  {  // blockIdx.y = group: its own rho, PSF spectrum scratch and tables
+    const size_t grp = blockIdx.y;
+    T += grp * (size_t)M * (kw > 0 ? kw : 1);
+    rho_p += grp;
+    ctab += grp * (size_t)M * N;
+    if (ktab) ktab += grp * (size_t)M * N;
+    if (sig) sig += grp * (size_t)M * N;
+  }
   const int p1 = idx % M, p2 = idx / M;
   const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
   double sr = 1.0, si = 0.0;

@@ -43,7 +43,10 @@ enum { ADMMTV_ACT_IDENTITY = 0, ADMMTV_ACT_RELU = 1, ADMMTV_ACT_RELU6 = 2, ADMMT
 /* flags */
 enum {
   ADMMTV_FLAG_NO_CLAMP = 1,      /* skip deconv_admm.jl:216-219 (bare tvd_fft call) */
-  ADMMTV_FLAG_NOGRAD_REPEAT = 2  /* train.jl:10 variant: no ∂weight through the spatial H^T y path */
+  ADMMTV_FLAG_NOGRAD_REPEAT = 2, /* train.jl:10 variant: no ∂weight through the spatial H^T y path */
+  /* grouped calls (desc.groups > 1), see below */
+  ADMMTV_FLAG_SHARED_INPUT = 4,  /* every group reads the same y (M,N,P,B/groups) */
+  ADMMTV_FLAG_CHANNEL_CONCAT = 8 /* x_out is (M,N,groups*P,B/groups): group g in channels [gP,(g+1)P) */
 };
 
 /* error codes (<0) */
@@ -68,7 +71,12 @@ typedef struct admmtv_desc {
   int32_t device;          /* CUDA device ordinal */
   int32_t flags;           /* ADMMTV_FLAG_* */
   float creg;              /* clamp floor of λ, ρ                        deconv_admm.jl:216-217 */
-  int32_t reserved;        /* must be 0 */
+  int32_t groups;          /* 0/1: one call (the reference).  G > 1: G independent calls of identical shape
+                            * batched into one launch sequence -- an EXTENSION: image b of the
+                            * B images belongs to group b / (B/G); λ, ρ, bias hold G floats, h holds G kernels
+                            * (kh*kw each); the result equals G separate reference calls.  Used for per-image
+                            * PSFs / noise levels (G = B) and for the parallel branches of net_build.jl:113-128
+                            * (SHARED_INPUT | CHANNEL_CONCAT).  Forward only: admmtv_backward rejects G > 1. */
 } admmtv_desc;
 
 int admmtv_version(void);

@@ -77,6 +77,27 @@ class Backend:
         self.sync()
         return r
 
+    def forward_grouped(self, y, lam, rho, h=None, iso=False, iters=10, groups=1, shared_input=False, concat=False,
+                        act="identity"):
+        """y: (M,N,P,Bin) Julia-indexed; lam, rho: length-G; h: (kh,kw,G) or None."""
+        y = f32(y)
+        M, N, P, Bin = y.shape
+        Bg = Bin if shared_input else Bin // groups
+        kh, kw = (0, 0) if h is None else (h.shape[0], h.shape[1])
+        flags = _lib.FLAG_NO_CLAMP | (_lib.FLAG_SHARED_INPUT if shared_input else 0) | (_lib.FLAG_CHANNEL_CONCAT if concat else 0)
+        d = _lib.make_desc(M, N, P, groups * Bg, kh, kw, iters, iso, act, False, 0, flags, 0.0, groups)
+        fwd_b, _, _ = self.lib.workspace_bytes(d)
+        yb = self.buf(y)
+        hb = None if h is None else self.buf(f32(h))
+        lb = self.buf(np.asarray(lam, dtype=np.float32))
+        rb = self.buf(np.asarray(rho, dtype=np.float32))
+        shape = (M, N, groups * P, Bg) if concat else (M, N, P, groups * Bg)
+        x = self.zeros(shape)
+        ws = self.zeros((fwd_b,), np.uint8)
+        self.lib.forward(d, yb.ptr, None if hb is None else hb.ptr, lb.ptr, rb.ptr, None, x.ptr, ws.ptr, None, self.stream())
+        self.sync()
+        return x.get()
+
     def backward(self, fwd, xbar):
         d = fwd["desc"]
         M, N, P, B = d.M, d.N, d.P, d.B

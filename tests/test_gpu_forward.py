@@ -188,3 +188,51 @@ def test_iso_couples_the_batch():
     both = A.tvd_fft(y, lam, rho, None, True, 10)
     alone = A.tvd_fft(y[:1].contiguous(), lam, rho, None, True, 10)
     assert rel_l2(both[:1].cpu(), alone.cpu()) > 1e-3
+
+
+def test_grouped_per_image_psf_and_noise_level():
+    """BASELINE configs[4] semantics (EXTENSION): 128x128 images, each with its own 9x9 motion PSF
+    and (lambda, rho); must equal the reference semantics run once per image (oracle, B = 1) and the same
+    library called image by image."""
+    import math
+    d0 = dev()
+    B, K = 24, 20
+    rng = np.random.default_rng(5)
+    ys, hs, lams, rhos = [], [], [], []
+    for b in range(B):
+        h = O.motion_psf(9, float(rng.uniform(0, math.pi)), float(rng.uniform(5, 9)))
+        g = O.synthetic_truth(128, 128, 1, 1, 4000 + b)
+        sig = [0.005, 0.01, 0.02, 0.04][b % 4]
+        ys.append(O.synthetic_observation(g, h, sig, 4000 + b).float()); hs.append(h.float())
+        lams.append(0.2 * sig); rhos.append(1.0 * sig)
+    y = A.from_julia(torch.cat(ys, dim=3)).to(d0)                               # (B,1,128,128)
+    h = torch.stack([A.from_julia(hh)[0] for hh in hs]).to(d0).contiguous()      # (B,1,9,9)
+    lam = torch.tensor(lams, dtype=torch.float32, device=d0); rho = torch.tensor(rhos, dtype=torch.float32, device=d0)
+    x = A.tvd_fft_grouped(y, lam, rho, h, False, K, groups=B)
+    torch.cuda.synchronize()
+    for b in range(B):
+        one = A.tvd_fft(y[b:b + 1].contiguous(), lam[b:b + 1].clone(), rho[b:b + 1].clone(), h[b:b + 1].contiguous(), False, K)
+        assert rel_l2(x[b:b + 1].cpu(), one.cpu()) < 1e-5, b
+    for b in (0, 7, 23):
+        xo = O.tvd_fft_fast(ys[b].double(), torch.tensor([lams[b]], dtype=torch.float32).double(),
+                            torch.tensor([rhos[b]], dtype=torch.float32).double(), hs[b].double(), False, K)
+        assert rel_l2(A.to_julia(x[b:b + 1].cpu()), xo) < TOL, b
+
+
+@pytest.mark.parametrize("iso", [False, True])
+def test_grouped_parallel_branches_of_get_denoiser(iso):
+    """net_build.jl:113-128: 5 x ADMMDeconvF2((), 50, rho_i, relu1) on the same input + chcat, as ONE
+    grouped call (shared input, channel-concatenated output) == five separate layer calls concatenated."""
+    d0 = dev()
+    torch.manual_seed(3)
+    y = torch.rand(2, 3, 256, 256, device=d0)
+    rhos = [0.01, 0.03, 0.1, 0.3, 0.9]
+    lam = torch.full((5,), 0.02, device=d0); rho = torch.tensor(rhos, device=d0)
+    x = A.tvd_fft_grouped(y, lam, rho, None, iso, 50, groups=5, shared_input=True, channel_concat=True, activation="relu1")
+    parts = [A.admm_layer_call(y, lam[g:g + 1].clone(), rho[g:g + 1].clone(), None, None, 50, iso, "relu1", 0.0, False, clamp=False)
+             for g in range(5)]
+    ref = torch.cat(parts, dim=1)
+    assert x.shape == (2, 15, 256, 256)
+    assert rel_l2(x.cpu(), ref.cpu()) < 1e-5
+    xo = O.ACTIVATIONS["relu1"](O.tvd_fft_fast(A.to_julia(y.cpu()).double(), lam[2:3].cpu().double(), rho[2:3].cpu().double(), None, iso, 50))
+    assert rel_l2(A.to_julia(x[:, 6:9].cpu().contiguous()), xo) < TOL
