@@ -296,21 +296,40 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
   const float* pa = A.src + (size_t)ia * plane;
   const float* pb = A.src + (size_t)(has_b ? ib : 0) * plane;
   double bsum = 0.0;
-  for (int e = tid; e < nout * M; e += NT) {
-    const int c = e / M, i = e % M;
+  // 4 rows per thread: float4 loads from each plane (M is a multiple of 32)
+  for (int e = tid; e < nout * (M / 4); e += NT) {
+    const int c = e / (M / 4), i = (e % (M / 4)) * 4;
     const size_t off = (size_t)(j0 + c) * M + i;
     if (MODE == 2) {
-      X[sidx<LM>(c, i)] = A.src_packed[(size_t)q * plane + off];
+      const float4 lo = *reinterpret_cast<const float4*>(A.src_packed + (size_t)q * plane + off);
+      const float4 hi = *reinterpret_cast<const float4*>(A.src_packed + (size_t)q * plane + off + 2);
+      X[sidx<LM>(c, i)] = make_float2(lo.x, lo.y);
+      X[sidx<LM>(c, i + 1)] = make_float2(lo.z, lo.w);
+      X[sidx<LM>(c, i + 2)] = make_float2(hi.x, hi.y);
+      X[sidx<LM>(c, i + 3)] = make_float2(hi.z, hi.w);
       continue;
     }
-    float va = pa[off], vb = has_b ? pb[off] : 0.f;
-    if (MODE == 0 && A.packed_out) A.packed_out[(size_t)q * plane + off] = make_float2(va, vb);
-    if (MODE == 1) {
-      va *= act_grad_from_out(A.xout[(size_t)ia * plane + off], A.act);
-      if (has_b) vb *= act_grad_from_out(A.xout[(size_t)ib * plane + off], A.act);
-      bsum += (double)va + (double)vb;
+    const float4 a4 = *reinterpret_cast<const float4*>(pa + off);
+    const float4 b4 = has_b ? *reinterpret_cast<const float4*>(pb + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float va[4] = {a4.x, a4.y, a4.z, a4.w}, vb[4] = {b4.x, b4.y, b4.z, b4.w};
+    if (MODE == 0 && A.packed_out) {
+      float4* po = reinterpret_cast<float4*>(A.packed_out + (size_t)q * plane + off);
+      po[0] = make_float4(va[0], vb[0], va[1], vb[1]);
+      po[1] = make_float4(va[2], vb[2], va[3], vb[3]);
     }
-    X[sidx<LM>(c, i)] = make_float2(va, vb);
+    if (MODE == 1) {
+      const float4 oa = *reinterpret_cast<const float4*>(A.xout + (size_t)ia * plane + off);
+      const float4 ob = has_b ? *reinterpret_cast<const float4*>(A.xout + (size_t)ib * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float xa[4] = {oa.x, oa.y, oa.z, oa.w}, xb[4] = {ob.x, ob.y, ob.z, ob.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        va[t] *= act_grad_from_out(xa[t], A.act);
+        if (has_b) vb[t] *= act_grad_from_out(xb[t], A.act);
+        bsum += (double)va[t] + (double)vb[t];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) X[sidx<LM>(c, i + t)] = make_float2(va[t], vb[t]);
   }
   if (MODE == 1 && A.bias_acc) {
     const double tot = block_sum(bsum);
@@ -340,9 +359,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
   dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
   if (MODE == 0) {
     float2* dst = A.packed + (size_t)q * plane;
-    for (int e = tid; e < nout * M; e += NT) {
-      const int c = e / M, i = e % M;
-      dst[(size_t)(j0 + c) * M + i] = X[sidx<LM>(c, i)];
+    for (int e = tid; e < nout * (M / 2); e += NT) {
+      const int c = e / (M / 2), i = (e % (M / 2)) * 2;
+      const float2 v0 = X[sidx<LM>(c, i)], v1 = X[sidx<LM>(c, i + 1)];
+      *reinterpret_cast<float4*>(dst + (size_t)(j0 + c) * M + i) = make_float4(v0.x, v0.y, v1.x, v1.y);
     }
   } else {
     const long ia = pm_out(A.pm, q, 0), ib = pm_out(A.pm, q, 1);
@@ -350,12 +370,17 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
     const float bias = A.bias ? A.bias[q / A.pm.Qg] : 0.f;
     float* pa = A.planes + (size_t)ia * plane;
     float* pb = A.planes + (size_t)(has_b ? ib : 0) * plane;
-    for (int e = tid; e < nout * M; e += NT) {
-      const int c = e / M, i = e % M;
-      const float2 v = X[sidx<LM>(c, i)];
+    for (int e = tid; e < nout * (M / 4); e += NT) {
+      const int c = e / (M / 4), i = (e % (M / 4)) * 4;
+      float2 v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[t] = X[sidx<LM>(c, i + t)];
       const size_t off = (size_t)(j0 + c) * M + i;
-      pa[off] = act_apply(v.x + bias, A.act);
-      if (has_b) pb[off] = act_apply(v.y + bias, A.act);
+      *reinterpret_cast<float4*>(pa + off) = make_float4(act_apply(v[0].x + bias, A.act), act_apply(v[1].x + bias, A.act),
+                                                          act_apply(v[2].x + bias, A.act), act_apply(v[3].x + bias, A.act));
+      if (has_b)
+        *reinterpret_cast<float4*>(pb + off) = make_float4(act_apply(v[0].y + bias, A.act), act_apply(v[1].y + bias, A.act),
+                                                            act_apply(v[2].y + bias, A.act), act_apply(v[3].y + bias, A.act));
     }
   }
 }

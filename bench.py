@@ -38,6 +38,12 @@ WORKLOADS = {
                  desc="BASELINE.json configs[4] (shared PSF variant): batch 1024 x 128x128, 50 iterations"),
     "cfg3": dict(B=32, P=3, N=256, M=256, k=15, iters=10, mode="fwd+bwd",
                  desc="BASELINE.json configs[2] per-GPU share: 32 x 256x256 RGB (256 images over 8 GPUs), Gaussian PSF 15x15, 10 unrolled iterations, forward+backward + gradient all-reduce"),
+    "cfg5_mixed": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="grouped", groups="per_image",
+                       desc="BASELINE.json configs[4]: batch 1024 x 128x128, PER-IMAGE motion PSFs 9x9 and noise levels "
+                            "(lambda_i = 0.2 sigma_i, rho_i = 5 lambda_i), 50 iterations, one grouped call"),
+    "denoiser5": dict(B=32, P=3, N=256, M=256, k=0, iters=50, mode="grouped", groups=5, iso=True,
+                      desc="net_build.jl:113-128 get_denoiser: 5 parallel ADMMDeconvF2((),50,rho_i,relu1; iso) branches on the "
+                           "same 32 x 256x256 RGB input, channel-concatenated, one grouped call"),
     "tiny": dict(B=2, P=3, N=64, M=64, k=7, iters=10, mode="fwd", desc="tiny debug workload"),
 }
 FWD_BYTES = 40.0   # algorithmic bytes / plane-pixel-iteration, forward  
@@ -202,6 +208,8 @@ def run_native(args, w):
     y_host, h_host = make_inputs(w, 1001 + rank)
     y_host = y_host.pin_memory()
     x_host = torch.empty_like(y_host).pin_memory()
+    if w["mode"] == "grouped" and w["groups"] != "per_image":
+        x_host = torch.empty(w["B"], w["P"] * int(w["groups"]), w["N"], w["M"]).pin_memory()
     y = y_host.to(dev)
     h = h_host.to(dev)
     lam = torch.tensor([0.0041], device=dev)
@@ -215,7 +223,29 @@ def run_native(args, w):
         g_target = torch.rand_like(y)
         lam.requires_grad_(True); rho.requires_grad_(True); h.requires_grad_(True)
 
+    grouped = w["mode"] == "grouped"
+    if grouped:
+        import numpy as np
+        from oracle import admm_tv_oracle as O
+        if w["groups"] == "per_image":
+            G = w["B"]
+            rng = np.random.Generator(np.random.PCG64(7))
+            hs = [O.motion_psf(w["k"], float(rng.uniform(0, math.pi)), float(rng.uniform(5, w["k"])), dtype=torch.float32) for _ in range(16)]
+            hG = torch.stack([hs[i % 16].permute(3, 2, 1, 0)[0] for i in range(G)]).contiguous().to(dev)     # (G,1,kw,kh)
+            sig = torch.tensor([[0.005, 0.01, 0.02, 0.04][i % 4] for i in range(G)], device=dev)
+            lamG = (0.2 * sig).contiguous(); rhoG = (5 * lamG).contiguous()
+            gkw = dict(groups=G)
+        else:
+            G = int(w["groups"])
+            hG = None
+            lamG = torch.full((G,), 0.02, device=dev); rhoG = torch.tensor([0.01 * 3 ** i for i in range(G)], device=dev)
+            gkw = dict(groups=G, shared_input=True, channel_concat=True, activation="relu1")
+        px = px * (1 if w["groups"] == "per_image" else G)
+        units_per_step = px * K / 1e6
+
     def step(yin):
+        if grouped:
+            return ops.tvd_fft_grouped(yin, lamG, rhoG, hG, bool(w.get("iso", False)), K, **gkw)
         if not train:
             return ops.tvd_fft(yin, lam, rho, h, False, K)
         for p in (lam, rho, h):
@@ -288,7 +318,21 @@ def run_native(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    if rank == 0:
+    if rank == 0 and grouped:
+        pk, pk_src = peaks()
+        bytes_per = 44.0 if w.get("iso") else FWD_BYTES
+        line = {
+            "metric": METRIC, "value": units_per_step * args.steps * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "mode": w["mode"]},
+            "hbm_frac_whole_step": FWD_BYTES * px * K / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "e2e": {"value": units_per_step * args.steps * world / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    elif rank == 0:
         pk, pk_src = peaks()
         # per-kernel-class CUDA-event timing of one forward (profiling twin of the same call)
         d = ops.make_desc_for(y, h, K, False, "identity", False, _lib.FLAG_NO_CLAMP, 0.0)

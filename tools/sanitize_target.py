@@ -1,0 +1,31 @@
+"""Small end-to-end exercise of every kernel (aniso/iso, fwd/bwd, grouped, several FFT lengths) for
+compute-sanitizer:  compute-sanitizer --tool memcheck python tools/sanitize_target.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import admm_deconv_b200 as A  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+for (M, N, P, B, k) in [(32, 64, 3, 1, 5), (64, 32, 1, 3, 0), (128, 256, 2, 1, 7), (512, 32, 1, 2, 3), (32, 1024, 1, 1, 3), (2048, 32, 2, 1, 3)]:
+    for iso in (False, True):
+        y = torch.rand(B, P, N, M, device=dev, requires_grad=True)
+        h = None if k == 0 else (torch.rand(1, 1, k, k, device=dev) / (k * k)).requires_grad_(True)
+        lam = torch.tensor([0.02], device=dev, requires_grad=True)
+        rho = torch.tensor([0.1], device=dev, requires_grad=True)
+        bias = torch.tensor([0.01], device=dev, requires_grad=True)
+        x = A.admm_layer_call(y, lam, rho, h, bias, 3, iso, "relu1", 0.0)
+        x.sum().backward()
+        torch.cuda.synchronize()
+        print(M, N, P, B, k, iso, float(x.mean()), float(lam.grad), flush=True)
+y = torch.rand(4, 1, 64, 64, device=dev)
+h = torch.rand(4, 1, 5, 5, device=dev) / 25
+x = A.tvd_fft_grouped(y, torch.full((4,), 0.02, device=dev), torch.full((4,), 0.1, device=dev), h, False, 3, groups=4)
+x2 = A.tvd_fft_grouped(y[:2].contiguous(), torch.full((3,), 0.02, device=dev), torch.full((3,), 0.1, device=dev), None, True, 3, groups=3,
+                       shared_input=True, channel_concat=True, activation="relu1")
+torch.cuda.synchronize()
+print("grouped ok", float(x.mean()), float(x2.mean()))
