@@ -109,7 +109,7 @@ def make_inputs(w, seed):
     from oracle import admm_tv_oracle as O
 
     rng = np.random.Generator(np.random.PCG64(seed))
-    k = w["k"]
+    k = w["k"] if w["k"] > 0 else 9      # k = 0: the layer has no PSF (empty weight); the scene is still blurred
     h = O.motion_psf(k, float(rng.uniform(0, math.pi)), float(rng.uniform(5, k)), dtype=torch.float32)  # (k,k,1,1)
     # cheap synthetic scene: smooth field + rectangles, blurred through the reference's H, plus noise
     B, P, N, M = w["B"], w["P"], w["N"], w["M"]
