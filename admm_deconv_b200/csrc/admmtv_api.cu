@@ -90,10 +90,10 @@ struct Ckpt {
 static Ckpt carve_ckpt(const Geom& g, void* p) {
   Carver c(p);
   Ckpt k;
-  k.mask = c.take<float>(g.nh + 2);
+  k.mask = c.take<float>((size_t)(g.nh + 2) * g.G);
   k.vck = c.take<float2>((size_t)(g.K > 1 ? g.K - 1 : 0) * 2 * g.pk);
   k.zck = c.take<float2>((size_t)g.K * g.pk);
-  k.nck = c.take<float>((size_t)(g.K > 1 ? g.K - 1 : 0) * g.plane);
+  k.nck = c.take<float>((size_t)(g.K > 1 ? g.K - 1 : 0) * g.plane * g.G);
   k.bytes = c.off;
   return k;
 }
@@ -274,7 +274,6 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   if (d->kh > 0 && !h) return ADMMTV_ERR_NULL;
   if (d->has_bias && !bias) return ADMMTV_ERR_NULL;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ADMMTV_ERR_ALIGN;
-  if (d->groups > 1 && ckpt) return ADMMTV_ERR_UNSUPPORTED;  // grouped calls are forward-only
   DeviceGuard guard(d->device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -341,8 +340,8 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       if (ckpt) {
         a2.v_in = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
         a2.v_out = ck.vck + (size_t)(k - 1) * 2 * g.pk;
-        a2.nsq_in = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane : nullptr;
-        nsq_new = ck.nck + (size_t)(k - 1) * g.plane;
+        a2.nsq_in = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane * g.G : nullptr;
+        nsq_new = ck.nck + (size_t)(k - 1) * g.plane * g.G;
       } else {
         a2.v_in = (k & 1) ? w.v1 : w.v0;
         a2.v_out = (k & 1) ? w.v0 : w.v1;

@@ -48,6 +48,7 @@ int Dim1Launch<LM>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaSt
 template <>
 int Dim1Launch<LM>::out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st) {
   if (mode == 0) return launch_k(k_dim1_out<LM, 0>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+  if (mode == 2) return launch_k(k_dim1_out<LM, 2>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
   return launch_k(k_dim1_out<LM, 1>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
 }
 template <>

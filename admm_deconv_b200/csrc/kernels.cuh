@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
   }
   if (MODE == 1 && A.bias_acc) {
     const double tot = block_sum(bsum);
-    if (tid == 0) atomicAdd(A.bias_acc, tot);
+    if (tid == 0) atomicAdd(A.bias_acc + 8 * (q / A.pm.Qg), tot);  // one accumulator block of 8 doubles per group
   }
   __syncthreads();
   float2* sq = A.spec + (size_t)q * plane;
@@ -363,6 +363,22 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
       const int c = e / (M / 2), i = (e % (M / 2)) * 2;
       const float2 v0 = X[sidx<LM>(c, i)], v1 = X[sidx<LM>(c, i + 1)];
       *reinterpret_cast<float4*>(dst + (size_t)(j0 + c) * M + i) = make_float4(v0.x, v0.y, v1.x, v1.y);
+    }
+  } else if (MODE == 2) {
+    // cotangent of the INPUT: input plane map; groups sharing y accumulate (ybar zeroed by the host)
+    const long ia = pm_in(A.pm, q, 0), ib = pm_in(A.pm, q, 1);
+    const bool shared = A.pm.G > 1 && A.pm.in_gstride == 0;
+    for (int e = tid; e < nout * M; e += NT) {
+      const int c = e / M, i = e % M;
+      const float2 v = X[sidx<LM>(c, i)];
+      const size_t off = (size_t)(j0 + c) * M + i;
+      if (shared) {
+        atomicAdd(A.planes + (size_t)ia * plane + off, v.x);
+        if (ib >= 0) atomicAdd(A.planes + (size_t)ib * plane + off, v.y);
+      } else {
+        A.planes[(size_t)ia * plane + off] = v.x;
+        if (ib >= 0) A.planes[(size_t)ib * plane + off] = v.y;
+      }
     }
   } else {
     const long ia = pm_out(A.pm, q, 0), ib = pm_out(A.pm, q, 1);
@@ -701,15 +717,15 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
   const int tid = threadIdx.x, M = A.M;
   const int i0 = blockIdx.x * TR;
   float* gsm = reinterpret_cast<float*>(tile + N * TR);
-  if (SMACC) {
-    for (int t = tid; t < N * TR; t += NT) gsm[t] = 0.f;  // ordered before the first use by the barriers of the forward passes
-  }
   (void)IPT;
 
   for (int q = blockIdx.y; q < A.Q; q += gridDim.y) {
     const size_t qoff = (size_t)q * N * M;
-    const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;  // this group's tables
+    const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;  // this group's tables / accumulators
     const float2* src = A.in + qoff + i0;
+    if (SMACC) {
+      for (int t = tid; t < N * TR; t += NT) gsm[t] = 0.f;  // ordered before its first use by the barriers of the forward passes
+    }
     if (ACC != 0) {
       // the second spectrum is consumed in the fused stage: start pulling it into L2 now
       for (int col = tid; col < N; col += NT) l2_prefetch_line(A.z2 + qoff + i0 + (size_t)col * M);
@@ -775,10 +791,10 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
             gv.y += re1;
             *gp = gv;
           } else {
-            atomicAdd(A.gacc + 2 * g, re0);
-            atomicAdd(A.gacc + 2 * g + 1, im0);
-            atomicAdd(A.gacc + 2 * g + 2, re1);
-            atomicAdd(A.gacc + 2 * g + 3, im1);
+            atomicAdd(A.gacc + 2 * (toff + g), re0);
+            atomicAdd(A.gacc + 2 * (toff + g) + 1, im0);
+            atomicAdd(A.gacc + 2 * (toff + g) + 2, re1);
+            atomicAdd(A.gacc + 2 * (toff + g) + 3, im1);
           }
         }
         if (!FWD_ONLY) {
@@ -830,22 +846,22 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
           *reinterpret_cast<float4*>(dst + (size_t)(wi + m * St::STRIDE) * M + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
       }
     }
+    if (SMACC) {
+      // flush this pair's contribution (same thread -> element ownership as the fused stage)
+      for (int item = tid; item < RP * StL::ITEMS; item += NT) {
+        const int rp = item % RP, wi = item / RP;
+#pragma unroll
+        for (int m = 0; m < StL::R; ++m) {
+          const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;
+          const float2 gv = *reinterpret_cast<const float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
+          atomicAdd(A.gacc + toff + g, gv.x);
+          atomicAdd(A.gacc + toff + g + 1, gv.y);
+        }
+      }
+    }
     __syncthreads();  // the tile is rewritten by the next pair's first pass
   }
 
-  if (SMACC) {
-    // same (thread -> element) ownership as the fused stage: no barrier needed
-    for (int item = tid; item < RP * StL::ITEMS; item += NT) {
-      const int rp = item % RP, wi = item / RP;
-#pragma unroll
-      for (int m = 0; m < StL::R; ++m) {
-        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;
-        const float2 gv = *reinterpret_cast<const float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
-        atomicAdd(A.gacc + g, gv.x);
-        atomicAdd(A.gacc + g + 1, gv.y);
-      }
-    }
-  }
 }
 
 }  // namespace admmtv

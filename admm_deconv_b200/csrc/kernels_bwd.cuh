@@ -99,9 +99,13 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
   // 1. rbar_k for columns j0-1 .. j0+nout
   dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
-  const float rho = *A.rho;
-  const float tau = *A.lambda / rho;
+  const int grp = q / A.pm.Qg;
+  const float rho = A.rho[grp];
+  const float tau = A.lambda[grp] / rho;
   const int i0 = tid * RPT;
+  const float* nsq_g = MODE == 1 ? A.nsq + (size_t)grp * plane : nullptr;
+  const float* ip_g = MODE == 1 ? A.ip + (size_t)grp * plane : nullptr;
+  const bool tau_owner = (q % A.pm.Qg) == 0;  // the per-pixel taubar term is counted once per group
   const float2* v1 = A.vck + ((size_t)q * 2 + 0) * plane;
   const float2* v2 = A.vck + ((size_t)q * 2 + 1) * plane;
   const float2* e1 = A.vbar_in + ((size_t)q * 2 + 0) * plane;
@@ -120,8 +124,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
     load_rows<RPT>(v1 + (size_t)j * M + i0, vv);
     if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)j * M + i0, ee);
     if (MODE == 1) {
-      load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, nn);
-      load_rows_f<RPT>(A.ip + (size_t)j * M + i0, pp);
+      load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
+      load_rows_f<RPT>(ip_g + (size_t)j * M + i0, pp);
     }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
@@ -161,8 +165,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
         load_rows<RPT>(v1 + (size_t)jn * M + i0, vv);
         if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)jn * M + i0, ee);
         if (MODE == 1) {
-          load_rows_f<RPT>(A.nsq + (size_t)jn * M + i0, nn);
-          load_rows_f<RPT>(A.ip + (size_t)jn * M + i0, pp);
+          load_rows_f<RPT>(nsq_g + (size_t)jn * M + i0, nn);
+          load_rows_f<RPT>(ip_g + (size_t)jn * M + i0, pp);
         }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
@@ -184,16 +188,16 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
           ee[RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
         }
         if (MODE == 1) {
-          load_rows_f<RPT>(A.nsq + (size_t)j * M + i0, nn);
-          nn[RPT] = A.nsq[(size_t)j * M + ((i0 + RPT) & (M - 1))];
-          load_rows_f<RPT>(A.ip + (size_t)j * M + i0, pp);
-          pp[RPT] = A.ip[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+          load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
+          nn[RPT] = nsq_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+          load_rows_f<RPT>(ip_g + (size_t)j * M + i0, pp);
+          pp[RPT] = ip_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
         }
 #pragma unroll
         for (int r = 0; r <= RPT; ++r) {
           const float2 d = csub(xc[r + 1], xc[r]);
           // the taubar term is per PIXEL: counted once, by pair 0, with the pixel's channel-2 point
-          if (MODE == 1) n2[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], r < RPT, q == 0, racc, tacc);
+          if (MODE == 1) n2[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], r < RPT, tau_owner, racc, tacc);
           else n2[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, r < RPT, racc, tacc);
         }
         store_rows<RPT>(o2 + (size_t)j * M + i0, n2);
@@ -219,8 +223,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
   const double rsum = block_sum(racc);
   const double tsum = block_sum(tacc);
   if (tid == 0) {
-    atomicAdd(A.acc + 0, rsum);
-    atomicAdd(A.acc + 1, tsum);
+    atomicAdd(A.acc + 8 * grp + 0, rsum);
+    atomicAdd(A.acc + 8 * grp + 1, tsum);
   }
 }
 
@@ -248,8 +252,13 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A
     if (!A.first) v = cadd(v, bq[off]);
     if (MODE == 0) X[sidx<LM>(c, i)] = v;
     else {
-      A.ybar[(size_t)ia * plane + off] = v.x;
-      if (has_b) A.ybar[(size_t)ib * plane + off] = v.y;
+      if (A.pm.G > 1 && A.pm.in_gstride == 0) {   // groups share y: ybar (zeroed by the host) sums over groups
+        atomicAdd(A.ybar + (size_t)ia * plane + off, v.x);
+        if (has_b) atomicAdd(A.ybar + (size_t)ib * plane + off, v.y);
+      } else {
+        A.ybar[(size_t)ia * plane + off] = v.x;
+        if (has_b) A.ybar[(size_t)ib * plane + off] = v.y;
+      }
     }
   }
   if (MODE == 0) {

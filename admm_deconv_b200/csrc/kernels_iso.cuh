@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_iso_bwd_a(IsoArgs A) {
   const size_t plane = (size_t)N * M;
   const float2* sin_q = A.spec_in + (size_t)q * plane;
   dim1_ifft_to_smem<LM, NT>(X, nout + 1, [&](int c) { return sin_q + (size_t)jwrap<LM>(j0 - 1 + c, N) * M; }, A.twM, tid);
-  const float rho = *A.rho;
+  const int grp = q / A.Qg;
+  const float rho = A.rho[grp];
+  float* ip_g = A.ip + (size_t)grp * plane;
   const float2* v1 = A.v_in + ((size_t)q * 2 + 0) * plane;     // v_{k-1}
   const float2* v2 = A.v_in + ((size_t)q * 2 + 1) * plane;
   const float2* e1 = A.vbar_in + ((size_t)q * 2 + 0) * plane;  // vbar_k
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_iso_bwd_a(IsoArgs A) {
       q2 = csub(q2, e2[off]);
     }
     const float2 a1 = v1[off], a2 = v2[off];
-    atomicAdd(A.ip + off, q1.x * a1.x + q1.y * a1.y + q2.x * a2.x + q2.y * a2.y);
+    atomicAdd(ip_g + off, q1.x * a1.x + q1.y * a1.y + q2.x * a2.x + q2.y * a2.y);
   }
 }
 

@@ -130,6 +130,14 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
                                      const float* __restrict__ ctab, const float2* __restrict__ sig, int kh, int kw,
                                      int M, int N, int use_spatial, double2* Wn, double* acc) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // M*N is a multiple of the block size
+  {  // blockIdx.y = group
+    const size_t go = (size_t)blockIdx.y * M * N;
+    gacc += go; ctab += go;
+    if (pacc) pacc += go;
+    if (sig) sig += go;
+    if (Wn) Wn += go;
+    acc += 8 * blockIdx.y;
+  }
   const int p1 = idx % M, p2 = idx / M;
   const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
   const double mn = (double)M * (double)N;
@@ -161,6 +169,8 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
 // spread over the block's threads (coalesced Wn row) and reduced in fp64
 static __global__ void k_grad_h_dim1(const double2* __restrict__ Wn, int kh, int M, int N, double2* U) {
   const int a = blockIdx.x / N, k2 = blockIdx.x % N;
+  Wn += (size_t)blockIdx.y * M * N;    // blockIdx.y = group
+  U += (size_t)blockIdx.y * kh * N;
   double re = 0.0, im = 0.0;
   for (int k1 = threadIdx.x; k1 < M; k1 += blockDim.x) {
     double s, c;
@@ -184,6 +194,15 @@ static __global__ void k_grad_finalize(const double2* __restrict__ U, int kh, in
                                        const float* __restrict__ rho, float* hbar, float* lambar, float* rhobar,
                                        float* biasbar) {
   const int t = blockIdx.x;
+  {  // blockIdx.y = group
+    const int grp = blockIdx.y;
+    U += (size_t)grp * kh * N;
+    mask += (size_t)grp * (kh * kw + 2);
+    acc += 8 * grp;
+    lambda += grp; rho += grp; lambar += grp; rhobar += grp;
+    if (hbar) hbar += (size_t)grp * kh * kw;
+    if (biasbar) biasbar += grp;
+  }
   if (t < kh * kw && hbar) {   // block-uniform
     const int a = t % kh, b = t / kh;
     double re = 0.0;

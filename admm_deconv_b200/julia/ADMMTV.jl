@@ -26,7 +26,7 @@ struct Desc
     kh::Int32; kw::Int32
     iters::Int32; iso::Int32; activation::Int32; has_bias::Int32
     device::Int32; flags::Int32
-    creg::Float32; reserved::Int32
+    creg::Float32; groups::Int32
 end
 
 const FLAG_NO_CLAMP = Int32(1)

@@ -149,3 +149,39 @@ class ADMMDeconvF3(_AdmmBase):
 
 
 Admm = Union[ADMMDeconv, ADMMDeconvF1, ADMMDeconvF2, ADMMDeconvF3]   # :212
+
+
+class ADMMParallel(nn.Module):
+    """``Parallel(chcat, deconv_1, ..., deconv_G)`` of net_build.jl:113-128 (get_denoiser) as ONE grouped call:
+    the G ADMM layers read the same input, their results are concatenated on the channel dimension.
+    Requires layers of identical iters / iso / σ / creg, the same PSF size (or all without a PSF) and no bias
+    mix; falls back to nothing -- incompatible layers raise."""
+
+    def __init__(self, *layers: _AdmmBase):
+        super().__init__()
+        if len(layers) < 1:
+            raise ValueError("need at least one layer")
+        l0 = layers[0]
+        for l in layers:
+            same = (l.iters, l.iso, l.sigma, l.creg, tuple(l.weight.shape), l.bias is None) == \
+                (l0.iters, l0.iso, l0.sigma, l0.creg, tuple(l0.weight.shape), l0.bias is None)
+            if not same:
+                raise ValueError("ADMMParallel needs layers of identical shape / iterations / iso / activation")
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        L = list(self.layers)
+        G = len(L)
+        lam = torch.cat([l.lam for l in L])
+        rho = torch.cat([l.rho for l in L])
+        h = torch.cat([l.weight for l in L], dim=0).contiguous() if L[0].weight.numel() > 0 else None
+        bias = torch.cat([l.bias for l in L]) if L[0].bias is not None else None
+        out = ops.tvd_fft_grouped(x, lam, rho, h, L[0].iso, L[0].iters, groups=G, shared_input=True, channel_concat=True,
+                                  bias=bias, activation=L[0].sigma, creg=L[0].creg, clamp=True)
+        # the library clamped the packed copies in place: persist into the layers (deconv_admm.jl:216-219)
+        with torch.no_grad():
+            for g, l in enumerate(L):
+                l.lam.copy_(lam[g:g + 1]); l.rho.copy_(rho[g:g + 1])
+                if h is not None:
+                    l.weight.copy_(h[g:g + 1])
+        return out

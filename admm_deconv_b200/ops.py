@@ -149,10 +149,52 @@ def tvd_fft_host(y, lam: float, rho: float, h=None, isotropic=False, maxit=100):
     return x
 
 
+class _AdmmGroupedFunction(torch.autograd.Function):
+    """Grouped call (desc.groups > 1): forward = admmtv_forward, backward = admmtv_backward with per-group
+    parameter cotangents (and ybar summed over groups that share the input)."""
+
+    @staticmethod
+    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags, groups, shared_input, channel_concat):
+        lib = _lib.load()
+        Bin, P, N, M = y.shape
+        Bg = Bin if shared_input else Bin // groups
+        kh, kw = (0, 0) if h is None else (int(h.shape[-1]), int(h.shape[-2]))
+        need_grad = any(t is not None and t.requires_grad for t in (y, lam, rho, h, bias))
+        d = _lib.make_desc(M, N, P, groups * Bg, kh, kw, iters, iso, activation, bias is not None, y.device.index or 0,
+                           flags, creg, groups)
+        fwd_b, ck_b, _ = lib.workspace_bytes(d)
+        ws = _alloc(fwd_b, y.device)
+        ck = _alloc(ck_b, y.device) if need_grad else None
+        x = torch.empty((Bg, groups * P, N, M) if channel_concat else (groups * Bg, P, N, M), dtype=torch.float32,
+                        device=y.device)
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        lib.forward(d, _ptr(y), _ptr(h), _ptr(lam), _ptr(rho), _ptr(bias), _ptr(x), _ptr(ws), _ptr(ck), stream)
+        ctx.desc, ctx.ck, ctx.has_h, ctx.has_bias, ctx.groups = d, ck, h is not None, bias is not None, groups
+        ctx.save_for_backward(y, lam, rho, h if h is not None else torch.empty(0, device=y.device), x)
+        return x
+
+    @staticmethod
+    def backward(ctx, xbar):
+        lib = _lib.load()
+        y, lam, rho, h, x = ctx.saved_tensors
+        d = ctx.desc
+        xbar = xbar.contiguous()
+        _, _, bwd_b = lib.workspace_bytes(d)
+        ws = _alloc(bwd_b, y.device)
+        ybar = torch.empty_like(y)
+        hbar = torch.empty_like(h) if ctx.has_h else None
+        lbar, rbar = torch.empty_like(lam), torch.empty_like(rho)
+        bbar = torch.empty(ctx.groups, dtype=torch.float32, device=y.device) if ctx.has_bias else None
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        lib.backward(d, _ptr(xbar), _ptr(x), _ptr(y), _ptr(h) if ctx.has_h else None, _ptr(lam), _ptr(rho), _ptr(ctx.ck),
+                     _ptr(ybar), _ptr(hbar), _ptr(lbar), _ptr(rbar), _ptr(bbar), _ptr(ws), stream)
+        return (ybar, lbar, rbar, hbar, bbar) + (None,) * 8
+
+
 def tvd_fft_grouped(y, lam, rho, h=None, isotropic=False, maxit=100, *, groups: int, shared_input=False,
                     channel_concat=False, bias=None, activation="identity", creg=0.0, clamp=False):
     """EXTENSION: ``groups`` independent reference calls of identical shape batched
-    into one launch sequence -- forward only.
+    into one launch sequence (differentiable: per-group cotangents).
 
     * per-image PSFs / noise levels (BASELINE configs[4]): ``groups = B``; ``lam``, ``rho`` hold one value per
       image, ``h`` is ``(groups, 1, kw, kh)``; result == the reference run once per image with B = 1.
@@ -185,11 +227,5 @@ def tvd_fft_grouped(y, lam, rho, h=None, isotropic=False, maxit=100, *, groups: 
         _check_cuda_f32("bias", bias)
     flags = (0 if clamp else _lib.FLAG_NO_CLAMP) | (_lib.FLAG_SHARED_INPUT if shared_input else 0) | \
         (_lib.FLAG_CHANNEL_CONCAT if channel_concat else 0)
-    d = _lib.make_desc(M, N, P, groups * Bg, kh, kw, maxit, isotropic, activation, bias is not None, y.device.index or 0,
-                       flags, creg, groups)
-    fwd_b, _, _ = lib.workspace_bytes(d)
-    ws = _alloc(fwd_b, y.device)
-    x = torch.empty((Bg, groups * P, N, M) if channel_concat else (groups * Bg, P, N, M), dtype=torch.float32, device=y.device)
-    stream = torch.cuda.current_stream(y.device).cuda_stream
-    lib.forward(d, _ptr(y), _ptr(h), _ptr(lam), _ptr(rho), _ptr(bias), _ptr(x), _ptr(ws), None, stream)
-    return x
+    return _AdmmGroupedFunction.apply(y, lam, rho, h, bias, int(maxit), bool(isotropic), activation, float(creg), flags,
+                                      int(groups), bool(shared_input), bool(channel_concat))

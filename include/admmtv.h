@@ -76,7 +76,8 @@ typedef struct admmtv_desc {
                             * B images belongs to group b / (B/G); λ, ρ, bias hold G floats, h holds G kernels
                             * (kh*kw each); the result equals G separate reference calls.  Used for per-image
                             * PSFs / noise levels (G = B) and for the parallel branches of net_build.jl:113-128
-                            * (SHARED_INPUT | CHANNEL_CONCAT).  Forward only: admmtv_backward rejects G > 1. */
+                            * (SHARED_INPUT | CHANNEL_CONCAT).  admmtv_backward then returns G kernels / scalars
+                            * and, with SHARED_INPUT, ybar summed over the groups. */
 } admmtv_desc;
 
 int admmtv_version(void);

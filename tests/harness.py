@@ -78,15 +78,16 @@ class Backend:
         return r
 
     def forward_grouped(self, y, lam, rho, h=None, iso=False, iters=10, groups=1, shared_input=False, concat=False,
-                        act="identity"):
-        """y: (M,N,P,Bin) Julia-indexed; lam, rho: length-G; h: (kh,kw,G) or None."""
+                        act="identity", want_ckpt=False):
+        """y: (M,N,P,Bin) Julia-indexed; lam, rho: length-G; h: (kh,kw,G) or None.  Returns x, or with
+        want_ckpt the dict `backward_grouped` takes."""
         y = f32(y)
         M, N, P, Bin = y.shape
         Bg = Bin if shared_input else Bin // groups
         kh, kw = (0, 0) if h is None else (h.shape[0], h.shape[1])
         flags = _lib.FLAG_NO_CLAMP | (_lib.FLAG_SHARED_INPUT if shared_input else 0) | (_lib.FLAG_CHANNEL_CONCAT if concat else 0)
         d = _lib.make_desc(M, N, P, groups * Bg, kh, kw, iters, iso, act, False, 0, flags, 0.0, groups)
-        fwd_b, _, _ = self.lib.workspace_bytes(d)
+        fwd_b, ck_b, bwd_b = self.lib.workspace_bytes(d)
         yb = self.buf(y)
         hb = None if h is None else self.buf(f32(h))
         lb = self.buf(np.asarray(lam, dtype=np.float32))
@@ -94,9 +95,26 @@ class Backend:
         shape = (M, N, groups * P, Bg) if concat else (M, N, P, groups * Bg)
         x = self.zeros(shape)
         ws = self.zeros((fwd_b,), np.uint8)
-        self.lib.forward(d, yb.ptr, None if hb is None else hb.ptr, lb.ptr, rb.ptr, None, x.ptr, ws.ptr, None, self.stream())
+        ck = self.zeros((ck_b,), np.uint8) if want_ckpt else None
+        self.lib.forward(d, yb.ptr, None if hb is None else hb.ptr, lb.ptr, rb.ptr, None, x.ptr, ws.ptr,
+                         None if ck is None else ck.ptr, self.stream())
         self.sync()
-        return x.get()
+        if not want_ckpt:
+            return x.get()
+        return dict(desc=d, y=yb, h=hb, lam=lb, rho=rb, x=x, ckpt=ck, bwd_bytes=bwd_b, groups=groups, in_shape=y.shape)
+
+    def backward_grouped(self, fwd, xbar):
+        d, G = fwd["desc"], fwd["groups"]
+        xb = self.buf(f32(xbar))
+        ws = self.zeros((fwd["bwd_bytes"],), np.uint8)
+        ybar = self.zeros(fwd["in_shape"])
+        hbar = None if fwd["h"] is None else self.zeros(fwd["h"].shape)
+        lbar, rbar = self.zeros((G,)), self.zeros((G,))
+        p = lambda b: None if b is None else b.ptr
+        self.lib.backward(d, xb.ptr, fwd["x"].ptr, fwd["y"].ptr, p(fwd["h"]), fwd["lam"].ptr, fwd["rho"].ptr, fwd["ckpt"].ptr,
+                          ybar.ptr, p(hbar), lbar.ptr, rbar.ptr, None, ws.ptr, self.stream())
+        self.sync()
+        return dict(ybar=ybar.get(), hbar=None if hbar is None else hbar.get(), lambar=lbar.get(), rhobar=rbar.get())
 
     def backward(self, fwd, xbar):
         d = fwd["desc"]

@@ -137,3 +137,49 @@ def test_golden_backward_iso(be):
         r = check_backward(be, y, h, float(d["lam"]), float(d["rho"]), True, int(d["iters"]), torch.from_numpy(d["xbar"]),
                            str(d["act"]), None, float(d["creg"]), tol=1e-5, tol_scalar=2e-4)
         print(os.path.basename(f), r)
+
+
+def test_admm_parallel_denoiser_bank_trains_like_separate_layers():
+    """net_build.jl:113-128 (get_denoiser): Parallel(chcat, 5 x ADMMDeconvF2((), 50, rho_i, relu1; iso)) as one
+    grouped call -- output and per-layer lambda gradients equal the five layers called separately."""
+    d = torch.device("cuda:0")
+    torch.manual_seed(0)
+    rhos = [0.002, 0.02, 0.2, 2.0, 4.0]
+    mk = lambda: [A.ADMMDeconvF2((), 20, r, "relu1", iso=True).to(d) for r in rhos]
+    la, lb = mk(), mk()
+    for a, b in zip(la, lb):
+        with torch.no_grad():
+            a.lam.fill_(0.02); b.lam.fill_(0.02)
+    x = torch.rand(2, 3, 256, 256, device=d)
+    tgt = torch.rand(2, 15, 256, 256, device=d)
+    bank = A.ADMMParallel(*la)
+    out = bank(x)
+    ((out - tgt) ** 2).mean().backward()
+    ref = torch.cat([l(x) for l in lb], dim=1)
+    ((ref - tgt) ** 2).mean().backward()
+    assert out.shape == (2, 15, 256, 256)
+    assert rel_l2(out.detach().cpu(), ref.detach().cpu()) < 1e-5
+    for a, b in zip(la, lb):
+        ga, gb = float(a.lam.grad), float(b.lam.grad)
+        assert abs(ga - gb) <= 2e-4 * max(abs(gb), 1e-6), (ga, gb)
+        assert a.rho.grad is None          # F2: rho is fixed (deconv_admm.jl:107)
+
+
+def test_grouped_backward_per_image_psf(be):
+    M, N, P, B, K = 64, 64, 1, 4, 6
+    ys, hs = [], []
+    lams, rhos = [0.004, 0.008, 0.016, 0.03], [0.02, 0.04, 0.06, 0.1]
+    for b in range(B):
+        y, h, _ = make_case(M, N, P, 1, 7, 7, 1900 + b)
+        ys.append(y.float().double()); hs.append(h.float().double())
+    y = torch.cat(ys, dim=3)
+    h = torch.cat([hh[:, :, :, 0] for hh in hs], dim=2)
+    xbar = torch.from_numpy(np.random.default_rng(1).standard_normal((M, N, P, B)))
+    f = be.forward_grouped(y.numpy(), lams, rhos, h.numpy(), False, K, groups=B, want_ckpt=True)
+    g = be.backward_grouped(f, xbar.numpy())
+    for b in range(B):
+        f1 = be.forward(ys[b].numpy(), lams[b], rhos[b], hs[b].numpy()[:, :, 0, 0], False, K, flags=1, want_ckpt=True)
+        g1 = be.backward(f1, xbar[..., b:b + 1].numpy())
+        assert rel_l2(T(g["ybar"][..., b:b + 1]), T(g1["ybar"])) < 2e-6
+        assert rel_l2(T(g["hbar"][:, :, b]), T(g1["hbar"])) < 2e-5
+        assert close(float(g["lambar"][b]), float(g1["lambar"][0]), 1e-4) and close(float(g["rhobar"][b]), float(g1["rhobar"][0]), 1e-4)
