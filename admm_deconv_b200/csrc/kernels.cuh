@@ -94,6 +94,9 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_PREFETCH
 #define ADMMTV_PREFETCH 1
 #endif
+#ifndef ADMMTV_PF_NEXT
+#define ADMMTV_PF_NEXT 0  // L2 prefetch for the block that takes over the SM slot next (distance in blocks); measured SLOWER (cfg2: dim2 99 -> 136 us at 444), kept off
+#endif
 #ifndef ADMMTV_NT9
 #define ADMMTV_NT9 256
 #endif
@@ -504,6 +507,15 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     }
     if (HAS_VPREV && tid == 32 % NT) l2_prefetch_bulk(A.vprev + ((size_t)q * 2 + 1) * plane + (size_t)j0 * M, (unsigned)nout * colb);
     if (tid == 64 % NT) l2_prefetch_bulk(A.bpk + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
+    // the spectrum tile of the block that will be scheduled onto this SM slot when a resident block retires
+    if (MODE == 0 && ADMMTV_PF_NEXT > 0 && tid == 96 % NT) {
+      const long nid = (long)blockIdx.y * gridDim.x + blockIdx.x + ADMMTV_PF_NEXT;
+      if (nid < (long)gridDim.x * gridDim.y) {
+        const int nq = (int)(nid / gridDim.x), nj0 = (int)(nid % gridDim.x) * CO;
+        const int ncol = min(CO, N - nj0);
+        l2_prefetch_bulk(A.spec_in + (size_t)nq * plane + (size_t)nj0 * M, (unsigned)ncol * colb);
+      }
+    }
   }
   // 1. x_k for columns j0-1 .. j0+nout (one halo column each side)
   if (MODE == 0) dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
@@ -725,6 +737,14 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
     const float2* src = A.in + qoff + i0;
     if (SMACC) {
       for (int t = tid; t < N * TR; t += NT) gsm[t] = 0.f;  // ordered before its first use by the barriers of the forward passes
+    }
+    if (ADMMTV_PF_NEXT > 0 && gridDim.y == (unsigned)A.Q) {
+      // the input tile of the block that takes over this SM slot next
+      const long nid = (long)blockIdx.y * gridDim.x + blockIdx.x + ADMMTV_PF_NEXT;
+      if (nid < (long)gridDim.x * gridDim.y) {
+        const float2* nxt = A.in + (size_t)(nid / gridDim.x) * N * M + (size_t)(nid % gridDim.x) * TR;
+        for (int col = tid; col < N; col += NT) l2_prefetch_line(nxt + (size_t)col * M);
+      }
     }
     if (ACC != 0) {
       // the second spectrum is consumed in the fused stage: start pulling it into L2 now

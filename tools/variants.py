@@ -43,6 +43,9 @@ VARIANTS = {
     "c8_4_t10": ("ADMMTV_CHUNK8=4", "ADMMTV_TC8=10"),
     "c8_8_t10": ("ADMMTV_CHUNK8=8", "ADMMTV_TC8=10"),
     "c8_4_t34": ("ADMMTV_CHUNK8=4", "ADMMTV_TC8=34"),
+    "pfn0": ("ADMMTV_PF_NEXT=0",),
+    "pfn296": ("ADMMTV_PF_NEXT=296",),
+    "pfn592": ("ADMMTV_PF_NEXT=592",),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
