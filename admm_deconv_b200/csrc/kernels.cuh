@@ -97,6 +97,9 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_PF_NEXT
 #define ADMMTV_PF_NEXT 0  // L2 prefetch for the block that takes over the SM slot next (distance in blocks); measured SLOWER (cfg2: dim2 99 -> 136 us at 444), kept off
 #endif
+#ifndef ADMMTV_PRELOAD1
+#define ADMMTV_PRELOAD1 1
+#endif
 #ifndef ADMMTV_NT9
 #define ADMMTV_NT9 256
 #endif
@@ -243,16 +246,37 @@ ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const floa
   constexpr int M = 1 << LM, NS = plan_stages(M);
   using St = Stage<M, NS - 1>;
   static_assert(St::STRIDE == 1, "last plan stage must be contiguous");
-  for_items<St::ITEMS, NT>(
-      tid, ncols, [&](int) { return 0; },
-      [&](int wi, int c, int) {
-        float2 a[St::R];
-        load_contig<St::R>(colptr(c) + wi * St::R, a);
-        Dft<St::R, true>::run(a);
+  constexpr int TCMAX = Dim1Cfg<LM>::TC;
+  if constexpr (ADMMTV_PRELOAD1 && NT >= St::ITEMS && (TCMAX + NT / St::ITEMS - 1) / (NT / St::ITEMS) * St::R <= 24) {
+    // all of this thread's global loads of the pass are issued before the first butterfly
+    constexpr int CSTEP = NT / St::ITEMS, ROUNDS = (TCMAX + CSTEP - 1) / CSTEP;
+    const int wi = tid % St::ITEMS, c0 = tid / St::ITEMS;
+    float2 a[ROUNDS][St::R];
+#pragma unroll
+    for (int n = 0; n < ROUNDS; ++n)
+      if (c0 + n * CSTEP < ncols) load_contig<St::R>(colptr(c0 + n * CSTEP) + wi * St::R, a[n]);
+#pragma unroll
+    for (int n = 0; n < ROUNDS; ++n) {
+      const int c = c0 + n * CSTEP;
+      if (c < ncols) {
+        Dft<St::R, true>::run(a[n]);
         const int pb = sidx<LM>(c, wi * St::R);
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m)] = a[m];
-      });
+        for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m)] = a[n][m];
+      }
+    }
+  } else {
+    for_items<St::ITEMS, NT>(
+        tid, ncols, [&](int) { return 0; },
+        [&](int wi, int c, int) {
+          float2 a[St::R];
+          load_contig<St::R>(colptr(c) + wi * St::R, a);
+          Dft<St::R, true>::run(a);
+          const int pb = sidx<LM>(c, wi * St::R);
+#pragma unroll
+          for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m)] = a[m];
+        });
+  }
   __syncthreads();
   dim1_inv_stages_down<LM, NT, NS - 2>(X, ncols, tw, tid);
 }

@@ -102,30 +102,52 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def motion_psf(k: int, theta: float, length: float):
+    """Linear motion blur through the centre of a k x k support, bilinear rasterised, sum 1.
+    Returns a (k,k) torch tensor indexed [dim1, dim2]."""
+    import torch
+    p = torch.zeros(k, k, dtype=torch.float64)
+    c = (k - 1) / 2
+    n = max(int(math.ceil(length * 4)), 2)
+    for t in range(n):
+        s = -length / 2 + length * t / (n - 1)
+        a, b = c + s * math.sin(theta), c + s * math.cos(theta)
+        a0, b0 = int(math.floor(a)), int(math.floor(b))
+        for da in (0, 1):
+            for db in (0, 1):
+                aa, bb = a0 + da, b0 + db
+                if 0 <= aa < k and 0 <= bb < k:
+                    p[aa, bb] += (1 - abs(a - aa)) * (1 - abs(b - bb))
+    return (p / p.sum()).float()
+
+
 def make_inputs(w, seed):
-    """Synthetic blurred-noisy batch in the (B,P,N,M) layout + motion PSF."""
+    """Synthetic blurred-noisy batch in the (B,P,N,M) layout + motion PSF.  Plain torch; nothing
+    from oracle/ is used on the native arm."""
     import numpy as np
     import torch
-    from oracle import admm_tv_oracle as O
 
     rng = np.random.Generator(np.random.PCG64(seed))
     k = w["k"] if w["k"] > 0 else 9      # k = 0: the layer has no PSF (empty weight); the scene is still blurred
-    h = O.motion_psf(k, float(rng.uniform(0, math.pi)), float(rng.uniform(5, k)), dtype=torch.float32)  # (k,k,1,1)
-    # cheap synthetic scene: smooth field + rectangles, blurred through the reference's H, plus noise
+    h = motion_psf(k, float(rng.uniform(0, math.pi)), float(rng.uniform(5, k)))      # [dim1, dim2]
     B, P, N, M = w["B"], w["P"], w["N"], w["M"]
+    # scene: smooth field + rectangles
     g = torch.from_numpy(rng.random((min(B, 4), P, N, M), dtype=np.float32))
     g = torch.nn.functional.avg_pool2d(g, 9, stride=1, padding=4, count_include_pad=False)
     for b in range(g.shape[0]):
         for _ in range(8):
             i0, i1 = sorted(rng.integers(0, N, 2).tolist()); j0, j1 = sorted(rng.integers(0, M, 2).tolist())
             g[b, :, i0:i1 + 1, j0:j1 + 1] = float(rng.random())
-    yj = O.H_forward(g.permute(3, 2, 1, 0).contiguous(), h)            # (M,N,P,b)
-    y = yj.permute(3, 2, 1, 0).contiguous()
+    # circular blur with the reference's alignment (true convolution, centre at ceil((k-1)/2)): in the (.., N, M)
+    # layout dim 1 (M) is the last axis, dim 2 (N) the one before
+    pu, pd = math.ceil((k - 1) / 2), (k - 1) // 2
+    hk = h.t().contiguous()                                            # [dim2, dim1] == (kw, kh)
+    gp = torch.nn.functional.pad(g.reshape(-1, 1, N, M), (pu, pd, pu, pd), mode="circular")
+    y = torch.nn.functional.conv2d(gp, torch.flip(hk, dims=(0, 1)).reshape(1, 1, k, k)).reshape(g.shape)
     y = y + 0.02 * torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32))
     reps = (B + y.shape[0] - 1) // y.shape[0]
     y = y.repeat(reps, 1, 1, 1)[:B].contiguous()
-    hk = h.permute(3, 2, 1, 0).contiguous()                           # (1,1,kw,kh)
-    return y, hk
+    return y, hk.reshape(1, 1, k, k).contiguous()                      # (1,1,kw,kh)
 
 
 def run_reference(args, w):
@@ -226,12 +248,11 @@ def run_native(args, w):
     grouped = w["mode"] == "grouped"
     if grouped:
         import numpy as np
-        from oracle import admm_tv_oracle as O
         if w["groups"] == "per_image":
             G = w["B"]
             rng = np.random.Generator(np.random.PCG64(7))
-            hs = [O.motion_psf(w["k"], float(rng.uniform(0, math.pi)), float(rng.uniform(5, w["k"])), dtype=torch.float32) for _ in range(16)]
-            hG = torch.stack([hs[i % 16].permute(3, 2, 1, 0)[0] for i in range(G)]).contiguous().to(dev)     # (G,1,kw,kh)
+            hs = [motion_psf(w["k"], float(rng.uniform(0, math.pi)), float(rng.uniform(5, w["k"]))).t().contiguous() for _ in range(16)]
+            hG = torch.stack([hs[i % 16].reshape(1, w["k"], w["k"]) for i in range(G)]).contiguous().to(dev)  # (G,1,kw,kh)
             sig = torch.tensor([[0.005, 0.01, 0.02, 0.04][i % 4] for i in range(G)], device=dev)
             lamG = (0.2 * sig).contiguous(); rhoG = (5 * lamG).contiguous()
             gkw = dict(groups=G)

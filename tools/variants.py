@@ -46,6 +46,8 @@ VARIANTS = {
     "pfn0": ("ADMMTV_PF_NEXT=0",),
     "pfn296": ("ADMMTV_PF_NEXT=296",),
     "pfn592": ("ADMMTV_PF_NEXT=592",),
+    "pre1": ("ADMMTV_PRELOAD1=1",),
+    "pre1_mb2": ("ADMMTV_PRELOAD1=1", "ADMMTV_MINB9=2"),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
