@@ -236,3 +236,28 @@ def test_grouped_parallel_branches_of_get_denoiser(iso):
     assert rel_l2(x.cpu(), ref.cpu()) < 1e-5
     xo = O.ACTIVATIONS["relu1"](O.tvd_fft_fast(A.to_julia(y.cpu()).double(), lam[2:3].cpu().double(), rho[2:3].cpu().double(), None, iso, 50))
     assert rel_l2(A.to_julia(x[:, 6:9].cpu().contiguous()), xo) < TOL
+
+
+def test_fft_kernels_against_cufft_closed_form():
+    """cuFFT (torch.fft on the GPU) as the oracle for the hand-written FFT kernels: after ONE iteration the
+    solver's output is the closed form x_1 = F^-1( C conj(K) F y ), C = 1 / (|Sigma|^2 + rho |Lambda|^2)."""
+    import math
+    d0 = dev()
+    torch.manual_seed(4)
+    for (B, P, N, M, kh, kw) in [(2, 3, 512, 512, 15, 15), (1, 2, 2048, 128, 7, 10), (3, 1, 128, 1024, 4, 4), (2, 1, 4096, 32, 3, 3)]:
+        y = torch.rand(B, P, N, M, device=d0)
+        h = torch.rand(1, 1, kw, kh, device=d0) / (kh * kw)
+        rho = torch.tensor([0.05], device=d0); lam = torch.tensor([0.01], device=d0)
+        x = A.tvd_fft(y, lam, rho, h, False, 1)
+        # cuFFT closed form in fp64 (axes: last = dim 1 (M), second-to-last = dim 2 (N))
+        yd = y.double()
+        hh = torch.zeros(N, M, dtype=torch.float64, device=d0)
+        hh[:kw, :kh] = h[0, 0].double()
+        Sig = torch.fft.fft2(hh)
+        k1 = torch.arange(M, device=d0, dtype=torch.float64); k2 = torch.arange(N, device=d0, dtype=torch.float64).reshape(-1, 1)
+        pd, pr = (kh - 1) // 2, (kw - 1) // 2
+        K = Sig * torch.exp(2j * math.pi * (k1 * pd / M + k2 * pr / N))
+        L = 4 * torch.sin(math.pi * k1 / M) ** 2 + 4 * torch.sin(math.pi * k2 / N) ** 2
+        C = 1.0 / (Sig.abs() ** 2 + 0.05 * L)
+        ref = torch.fft.ifft2(C * K.conj() * torch.fft.fft2(yd)).real
+        assert rel_l2(x.cpu(), ref.cpu()) < 2e-6, (B, P, N, M)

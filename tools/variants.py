@@ -48,6 +48,7 @@ VARIANTS = {
     "pfn592": ("ADMMTV_PF_NEXT=592",),
     "pre1": ("ADMMTV_PRELOAD1=1",),
     "pre1_mb2": ("ADMMTV_PRELOAD1=1", "ADMMTV_MINB9=2"),
+    "isonoatom": ("ADMMTV_ISO_NOATOM=1",),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
