@@ -333,30 +333,32 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       if ((rc = run_dim1_fwd(g, k > 1, f, st))) return rc;
     } else if (k < g.K) {
       // isotropic: v_k and the per-pixel norm first (pass A), then shrink + D^T + FFT (pass B)
-      IsoArgs a2{};
-      a2.spec_in = w.specB; a2.spec_out = w.specA; a2.bpk = w.bpk; a2.twM = w.twM;
-      a2.lambda = lambda; a2.rho = rho; a2.N = g.N; a2.S = g.S; a2.Qg = g.Qg;
+      const float2* v_in;
+      float2* v_out;
+      const float* nsq_in;
       float* nsq_new;
       if (ckpt) {
-        a2.v_in = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
-        a2.v_out = ck.vck + (size_t)(k - 1) * 2 * g.pk;
-        a2.nsq_in = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane * g.G : nullptr;
+        v_in = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
+        v_out = ck.vck + (size_t)(k - 1) * 2 * g.pk;
+        nsq_in = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane * g.G : nullptr;
         nsq_new = ck.nck + (size_t)(k - 1) * g.plane * g.G;
       } else {
-        a2.v_in = (k & 1) ? w.v1 : w.v0;
-        a2.v_out = (k & 1) ? w.v0 : w.v1;
-        a2.nsq_in = (k & 1) ? w.nsq1 : w.nsq0;
+        v_in = (k & 1) ? w.v1 : w.v0;
+        v_out = (k & 1) ? w.v0 : w.v1;
+        nsq_in = (k & 1) ? w.nsq1 : w.nsq0;
         nsq_new = (k & 1) ? w.nsq0 : w.nsq1;
       }
-      a2.nsq_out = nsq_new;
       cudaError_t e2 = cudaMemsetAsync(nsq_new, 0, g.plane * g.G * sizeof(float), st);
       if (e2 != cudaSuccess) return (int)e2;
       tm_mark(tm, st, 1);
-      ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::iso(g, 0, k > 1, a2, st); })
+      Dim1FwdArgs fa{};
+      fa.spec_in = w.specB; fa.twM = w.twM; fa.lambda = lambda; fa.rho = rho; fa.N = g.N; fa.Qg = g.Qg;
+      fa.vprev = v_in; fa.vnew = v_out; fa.nsq = nsq_in; fa.nsq_out = nsq_new;
+      ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_a(g, k > 1, fa, st); })
       if (rc) return rc;
       Dim1FwdArgs f{};
       f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM; f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
-      f.vprev = a2.v_out; f.nsq = nsq_new;
+      f.vprev = v_out; f.nsq = nsq_new;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_b(g, f, st); })
       if (rc) return rc;
     }

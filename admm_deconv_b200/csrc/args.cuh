@@ -65,7 +65,8 @@ struct Dim1FwdArgs {
   const float2* bpk;
   const float2* vprev;  // [Q][2][N][M]; ignored when !HAS_VPREV (v_0 = 0)
   float2* vnew;         // [Q][2][N][M]
-  const float* nsq;     // isotropic pass B: per-pixel |v|^2 [N][M]
+  const float* nsq;     // isotropic: per-pixel |v|^2 [G][N][M] (pass B: of v_k ; pass A: of v_{k-1})
+  float* nsq_out;       // isotropic pass A: accumulates |v_k|^2 (zeroed by the host)
   const float2* twM;
   const float* lambda;  // [G]
   const float* rho;     // [G]
@@ -102,30 +103,10 @@ struct Dim1BwdArgs {
   double* acc;             // [0] rhobar (direct term), [1] taubar
   const float* nsq;        // isotropic pass B: |v_{k-1}|^2 per pixel
   const float* ip;         // isotropic pass B: <q, v_{k-1}> per pixel
+  float* ip_out;           // isotropic pass A: accumulates <q, v_{k-1}> (zeroed by the host)
   PlaneMap pm;
   int N, S;
   int first;               // 1: bbar is written, not accumulated (k = K)
-};
-
-// isotropic passes (kernels_iso.cuh); unused members are null
-struct IsoArgs {
-  const float2* spec_in;
-  float2* spec_out;
-  const float2* bpk;
-  const float2* v_in;      // fwd A: v_{k-1} ; fwd B: v_k ; bwd: v_{k-1} (checkpoint)
-  float2* v_out;           // fwd A: v_k
-  const float* nsq_in;     // fwd A: |v_{k-1}|^2 per pixel ; fwd B: |v_k|^2 ; bwd: |v_{k-1}|^2
-  float* nsq_out;          // fwd A: accumulates |v_k|^2 (zeroed by the host)
-  const float2* vbar_in;
-  float2* vbar_out;
-  float2* bbar;
-  float* ip;               // bwd A accumulates <q, v_{k-1}> per pixel ; bwd B reads it
-  const float2* twM;
-  const float* lambda;
-  const float* rho;
-  double* acc;
-  int N, S, first;
-  int Qg;
 };
 
 // variants of k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)
@@ -145,11 +126,11 @@ struct Dim1Launch {
   static int out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st);
   static int fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st);
   static int fwd_iso_b(const Geom& g, const Dim1FwdArgs& a, cudaStream_t st);
+  static int fwd_iso_a(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st);
   static int bwd_iso_b(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
+  static int bwd_iso_a(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
   static int bwd(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
   static int bwd_last(const Geom& g, int mode, const Dim1BwdArgs& a, cudaStream_t st);
-  // pass: 0 fwd A, 1 fwd B, 2 bwd A, 3 bwd B ; flag: HAS_VPREV / HAS_VBAR
-  static int iso(const Geom& g, int pass, bool flag, const IsoArgs& a, cudaStream_t st);
 };
 template <int LN>
 struct Dim2Launch {

@@ -9,14 +9,14 @@ template <> int Dim1Launch<LM_>::out(const Geom&, int, const OutArgs&, cudaStrea
 template <> int Dim1Launch<LM_>::fwd(const Geom&, bool, const Dim1FwdArgs&, cudaStream_t) { return -3; }
 template <> int Dim1Launch<LM_>::bwd(const Geom&, bool, const Dim1BwdArgs&, cudaStream_t) { return -3; }
 template <> int Dim1Launch<LM_>::bwd_last(const Geom&, int, const Dim1BwdArgs&, cudaStream_t) { return -3; }
-template <> int Dim1Launch<LM_>::iso(const Geom&, int, bool, const IsoArgs&, cudaStream_t) { return -3; }
 template <> int Dim1Launch<LM_>::fwd_iso_b(const Geom&, const Dim1FwdArgs&, cudaStream_t) { return -3; }
+template <> int Dim1Launch<LM_>::fwd_iso_a(const Geom&, bool, const Dim1FwdArgs&, cudaStream_t) { return -3; }
 template <> int Dim1Launch<LM_>::bwd_iso_b(const Geom&, bool, const Dim1BwdArgs&, cudaStream_t) { return -3; }
+template <> int Dim1Launch<LM_>::bwd_iso_a(const Geom&, bool, const Dim1BwdArgs&, cudaStream_t) { return -3; }
 }
 #else
 #include "kernels.cuh"
 #include "kernels_bwd.cuh"
-#include "kernels_iso.cuh"
 
 #ifndef ADMMTV_INST
 #error "compile with -DADMMTV_INST=<log2 M>"

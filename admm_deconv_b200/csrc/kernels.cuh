@@ -504,6 +504,8 @@ ADMMTV_DI Shrunk shrink_iso(float2 v, float s) {
 // MODE 0: the fused anisotropic kernel described above.
 // MODE 1: isotropic pass B -- v_k (A.vprev) and the per-pixel |v_k|^2 (A.nsq) are given; no IFFT,
 //         no state write: s = max(1 - tau/n, 0), w = (2s-1) v, r = b + rho D^T w, dim-1 FFT.
+// MODE 2: isotropic pass A -- dim-1 IFFT -> x_k ; v_k = D x_k + u_{k-1} with u_{k-1} from v_{k-1} (A.vprev) and
+//         |v_{k-1}|^2 (A.nsq) ; store v_k ; A.nsq_out[pixel] += |v_k|^2 (float atomics) ; no FFT.
 template <int LM, bool HAS_VPREV, int MODE = 0>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       l2_prefetch_bulk(A.vprev + ((size_t)q * 2 + 0) * plane + (size_t)jcol(nout + 1) * M, colb);
     }
     if (HAS_VPREV && tid == 32 % NT) l2_prefetch_bulk(A.vprev + ((size_t)q * 2 + 1) * plane + (size_t)j0 * M, (unsigned)nout * colb);
-    if (tid == 64 % NT) l2_prefetch_bulk(A.bpk + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
+    if (MODE != 2 && tid == 64 % NT) l2_prefetch_bulk(A.bpk + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
     // the spectrum tile of the block that will be scheduled onto this SM slot when a resident block retires
     if (MODE == 0 && ADMMTV_PF_NEXT > 0 && tid == 96 % NT) {
       const long nid = (long)blockIdx.y * gridDim.x + blockIdx.x + ADMMTV_PF_NEXT;
@@ -543,21 +545,38 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   }
   // 1. x_k for columns j0-1 .. j0+nout (one halo column each side)
   if (MODE == 0) dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+  if (MODE == 2) dim1_ifft_to_smem<LM, NT>(X, nout + 1, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
   // 2. stencil sweep: this thread owns rows i0 .. i0+RPT-1 of every column
   const int grp = q / A.Qg;
   const float rho = A.rho[grp];
   const float tau = A.lambda[grp] / rho;  // ops.jl:102
   const int i0 = tid * RPT;
-  const float* nsq_g = MODE == 1 ? A.nsq + (size_t)grp * plane : nullptr;
+  const float* nsq_g = MODE != 0 ? A.nsq + (size_t)grp * plane : nullptr;
+  float* nsq_o = MODE == 2 ? A.nsq_out + (size_t)grp * plane : nullptr;
   const float2* vp1 = A.vprev + ((size_t)q * 2 + 0) * plane;
   const float2* vp2 = A.vprev + ((size_t)q * 2 + 1) * plane;
   float2* vn1 = A.vnew + ((size_t)q * 2 + 0) * plane;
   float2* vn2 = A.vnew + ((size_t)q * 2 + 1) * plane;
   const float2* bq = A.bpk + (size_t)q * plane;
 
-  float2 w1c[RPT];
-  if (MODE == 1) {
+  float2 w1c[RPT];   // MODE 0/1: w1 of the current column ; MODE 2: v1 of the current column
+  if (MODE == 2) {
+    const int j = jcol(1);
+    float2 up[RPT];
+    float nn[RPT];
+    if (HAS_VPREV) {
+      load_rows<RPT>(vp1 + (size_t)j * M + i0, up);
+      load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      float2 v = csub(X[sidx<LM>(1, i0 + r)], X[sidx<LM>(0, i0 + r)]);
+      if (HAS_VPREV) v = cadd(v, shrink_iso(up[r], iso_scale(nn[r], tau)).u);
+      w1c[r] = v;
+    }
+    store_rows<RPT>(vn1 + (size_t)j * M + i0, w1c);
+  } else if (MODE == 1) {
     const int j = jcol(1);
     float2 vv[RPT];
     float nn[RPT];
@@ -583,21 +602,24 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   for (int c = 1; c <= nout; c += CHUNK) {
     // (a) every global load of the chunk is issued before any of them is consumed
     float2 g1[CHUNK][RPT], g2[CHUNK][RPT + 1], gb[CHUNK][RPT];
-    float n1[MODE == 1 ? CHUNK : 1][RPT], n2[MODE == 1 ? CHUNK : 1][RPT + 1];
+    float n1[MODE != 0 ? CHUNK : 1][RPT], n2[MODE != 0 ? CHUNK : 1][RPT + 1];
 #pragma unroll
     for (int cc = 0; cc < CHUNK; ++cc) {
       const int j = jcol(c + cc), jn = jcol(c + cc + 1);
-      if (MODE == 1) {
+      if (MODE == 1 || (MODE == 2 && HAS_VPREV)) {
         load_rows_f<RPT>(nsq_g + (size_t)jn * M + i0, n1[cc]);
         load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, n2[cc]);
-        n2[cc][RPT] = nsq_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        if (MODE == 1) n2[cc][RPT] = nsq_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
       }
-      if (HAS_VPREV) {
+      if (MODE == 2 && HAS_VPREV) {
+        load_rows<RPT>(vp1 + (size_t)jn * M + i0, g1[cc]);
+        load_rows<RPT>(vp2 + (size_t)j * M + i0, g2[cc]);
+      } else if (HAS_VPREV) {
         load_rows<RPT>(vp1 + (size_t)jn * M + i0, g1[cc]);
         load_rows<RPT>(vp2 + (size_t)j * M + i0, g2[cc]);
         g2[cc][RPT] = vp2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
       }
-      load_rows<RPT>(bq + (size_t)j * M + i0, gb[cc]);
+      if (MODE != 2) load_rows<RPT>(bq + (size_t)j * M + i0, gb[cc]);
     }
     // (b) stencil
     float2 rr[CHUNK][RPT];
@@ -607,6 +629,35 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       const int j = jcol(col), jn = jcol(col + 1);
       float2 w1n[RPT];
       float2 w2[RPT + 1];
+      if (MODE == 2) {
+        float2 xc[RPT + 1];  // rows i0-1 .. i0+RPT-1 of column col
+        xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
+        if (col < nout) {   // channel 1 of the next own column
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            float2 v = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
+            if (HAS_VPREV) v = cadd(v, shrink_iso(g1[cc][r], iso_scale(n1[cc][r], tau)).u);
+            w1n[r] = v;
+          }
+          store_rows<RPT>(vn1 + (size_t)jn * M + i0, w1n);
+        }
+        float2 vst[RPT];
+        float sq[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          float2 v = csub(xc[r + 1], xc[r]);
+          if (HAS_VPREV) v = cadd(v, shrink_iso(g2[cc][r], iso_scale(n2[cc][r], tau)).u);
+          vst[r] = v;
+          sq[r] = w1c[r].x * w1c[r].x + w1c[r].y * w1c[r].y + v.x * v.x + v.y * v.y;
+          w1c[r] = w1n[r];
+        }
+        store_rows<RPT>(vn2 + (size_t)j * M + i0, vst);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) atomicAdd(nsq_o + (size_t)j * M + i0 + r, sq[r]);
+        continue;
+      }
       if (MODE == 1) {
 #pragma unroll
         for (int r = 0; r < RPT; ++r) w1n[r] = shrink_iso(g1[cc][r], iso_scale(n1[cc][r], tau)).w;
@@ -652,12 +703,14 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
         w1c[r] = w1n[r];
       }
     }
+    if (MODE == 2) continue;   // X is only read in pass A
     __syncthreads();  // every thread is done reading columns <= c+CHUNK-1 of this chunk
 #pragma unroll
     for (int cc = 0; cc < CHUNK; ++cc)
 #pragma unroll
       for (int r = 0; r < RPT; ++r) X[sidx<LM>(c + cc - 1, i0 + r)] = rr[cc][r];  // r column -> slot col-1
   }
+  if (MODE == 2) return;
   __syncthreads();
 
   // 3. dim-1 FFT of r_{k+1}: slot s holds output column j0+s

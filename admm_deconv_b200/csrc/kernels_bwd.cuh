@@ -64,6 +64,8 @@ ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float ta
   return iso_bwd_point(d, v, eb, rho, s, coef);
 }
 
+// MODE 2: isotropic pass A -- dim-1 IFFT -> rbar_k ; bbar += rbar_k ; q = 2 rho D rbar_k - vbar_k ;
+//         A.ip_out[pixel] += <q, v_{k-1}> (float atomics) ; nothing else is written.
 // MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel |v_{k-1}|^2 in A.nsq, <q,v> in A.ip; bbar was
 // accumulated by pass A).
 template <int LM, bool HAS_VBAR, int MODE = 0>
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
     if (!A.first && tid == 128 % NT) l2_prefetch_bulk(A.bbar + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
   }
   // 1. rbar_k for columns j0-1 .. j0+nout
-  dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+  dim1_ifft_to_smem<LM, NT>(X, MODE == 2 ? nout + 1 : nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
   const int grp = q / A.pm.Qg;
   const float rho = A.rho[grp];
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
   const int i0 = tid * RPT;
   const float* nsq_g = MODE == 1 ? A.nsq + (size_t)grp * plane : nullptr;
   const float* ip_g = MODE == 1 ? A.ip + (size_t)grp * plane : nullptr;
+  float* ip_o = MODE == 2 ? A.ip_out + (size_t)grp * plane : nullptr;
   const bool tau_owner = (q % A.pm.Qg) == 0;  // the per-pixel taubar term is counted once per group
   const float2* v1 = A.vck + ((size_t)q * 2 + 0) * plane;
   const float2* v2 = A.vck + ((size_t)q * 2 + 1) * plane;
@@ -117,7 +120,20 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
   double racc = 0.0, tacc = 0.0;
 
   float2 n1c[RPT];  // vbar_{k-1}, channel 1, current column
-  {
+  float p1c[RPT];   // MODE 2: <q1, v1> of the current column
+  if (MODE == 2) {
+    const int j = jcol(1);
+    float2 vv[RPT], ee[RPT];
+    load_rows<RPT>(v1 + (size_t)j * M + i0, vv);
+    if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)j * M + i0, ee);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const float2 d = csub(X[sidx<LM>(1, i0 + r)], X[sidx<LM>(0, i0 + r)]);
+      float2 qq = make_float2(2.f * rho * d.x, 2.f * rho * d.y);
+      if (HAS_VBAR) qq = csub(qq, ee[r]);
+      p1c[r] = qq.x * vv[r].x + qq.y * vv[r].y;
+    }
+  } else {
     const int j = jcol(1);
     float2 vv[RPT], ee[RPT];
     float nn[RPT], pp[RPT];
@@ -148,6 +164,35 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
       for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
       xc[RPT + 1] = X[sidx<LM>(col, (i0 + RPT) & (M - 1))];
 
+      if (MODE == 2) {
+        float2 bb[RPT], vv[RPT], ee[RPT], v2v[RPT], e2v[RPT];
+        float p1n[RPT];
+        if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, bb);
+        if (col < nout) {
+          load_rows<RPT>(v1 + (size_t)jn * M + i0, vv);
+          if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)jn * M + i0, ee);
+        }
+        load_rows<RPT>(v2 + (size_t)j * M + i0, v2v);
+        if (HAS_VBAR) load_rows<RPT>(e2 + (size_t)j * M + i0, e2v);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) bb[r] = A.first ? xc[r + 1] : cadd(bb[r], xc[r + 1]);
+        store_rows<RPT>(bq + (size_t)j * M + i0, bb);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          if (col < nout) {
+            const float2 d = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
+            float2 qq = make_float2(2.f * rho * d.x, 2.f * rho * d.y);
+            if (HAS_VBAR) qq = csub(qq, ee[r]);
+            p1n[r] = qq.x * vv[r].x + qq.y * vv[r].y;
+          }
+          const float2 d2 = csub(xc[r + 1], xc[r]);
+          float2 q2 = make_float2(2.f * rho * d2.x, 2.f * rho * d2.y);
+          if (HAS_VBAR) q2 = csub(q2, e2v[r]);
+          atomicAdd(ip_o + (size_t)j * M + i0 + r, p1c[r] + q2.x * v2v[r].x + q2.y * v2v[r].y);
+          p1c[r] = p1n[r];
+        }
+        continue;
+      }
       // bbar += rbar_k
       if (MODE == 0) {
         float2 bb[RPT];
@@ -208,12 +253,14 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
         n1c[r] = n1n[r];
       }
     }
+    if (MODE == 2) continue;
     __syncthreads();
 #pragma unroll
     for (int cc = 0; cc < CHUNK; ++cc)
 #pragma unroll
       for (int r = 0; r < RPT; ++r) X[sidx<LM>(c + cc - 1, i0 + r)] = rr[cc][r];
   }
+  if (MODE == 2) return;
   __syncthreads();
 
   float2* sout_q = A.spec_out + (size_t)q * plane;
