@@ -28,6 +28,9 @@ constexpr int LN = ADMMTV_INST;
 #ifndef ADMMTV_D2_PERSIST
 #define ADMMTV_D2_PERSIST 0
 #endif
+#ifndef ADMMTV_D2_ACC_QPB
+#define ADMMTV_D2_ACC_QPB 2
+#endif
 #ifndef ADMMTV_D2_BLOCKS_PER_SM
 #define ADMMTV_D2_BLOCKS_PER_SM 2
 #endif
@@ -52,6 +55,9 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
     if (gy > g.Q) gy = g.Q;
   }
 #endif
+  // the G-accumulating variant gives each block a few pairs so the shared-memory partial sums are flushed
+  // with one global atomic per element per ADMMTV_D2_ACC_QPB pairs
+  if (variant == D2_C_ACCG && gy == g.Q) gy = (g.Q + ADMMTV_D2_ACC_QPB - 1) / ADMMTV_D2_ACC_QPB;
   const dim3 grid((unsigned)row_tiles, (unsigned)gy);
   switch (variant) {
     case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);

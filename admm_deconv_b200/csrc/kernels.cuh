@@ -812,7 +812,9 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
     const size_t qoff = (size_t)q * N * M;
     const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;  // this group's tables / accumulators
     const float2* src = A.in + qoff + i0;
-    if (SMACC) {
+    const bool first_of_run = q == (int)blockIdx.y || (q - (int)gridDim.y) / A.Qg != q / A.Qg;
+    const bool last_of_run = q + (int)gridDim.y >= A.Q || (q + (int)gridDim.y) / A.Qg != q / A.Qg;
+    if (SMACC && first_of_run) {
       for (int t = tid; t < N * TR; t += NT) gsm[t] = 0.f;  // ordered before its first use by the barriers of the forward passes
     }
     if (ADMMTV_PF_NEXT > 0 && gridDim.y == (unsigned)A.Q) {
@@ -943,8 +945,8 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
           *reinterpret_cast<float4*>(dst + (size_t)(wi + m * St::STRIDE) * M + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
       }
     }
-    if (SMACC) {
-      // flush this pair's contribution (same thread -> element ownership as the fused stage)
+    if (SMACC && last_of_run) {
+      // flush this block's run of same-group pairs (same thread -> element ownership as the fused stage)
       for (int item = tid; item < RP * StL::ITEMS; item += NT) {
         const int rp = item % RP, wi = item / RP;
 #pragma unroll

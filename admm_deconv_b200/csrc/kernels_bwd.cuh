@@ -15,6 +15,13 @@
 
 #include "kernels.cuh"
 
+#ifndef ADMMTV_BWD_HOIST
+#define ADMMTV_BWD_HOIST 1
+#endif
+#ifndef ADMMTV_MINB9B
+#define ADMMTV_MINB9B 2
+#endif
+
 namespace admmtv {
 
 ADMMTV_DI float sgn_mask(float v, float tau) { return v > tau ? 1.f : (v < -tau ? -1.f : 0.f); }  // sign(v) * 1[|v|>tau]
@@ -69,7 +76,7 @@ ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float ta
 // MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel |v_{k-1}|^2 in A.nsq, <q,v> in A.ip; bbar was
 // accumulated by pass A).
 template <int LM, bool HAS_VBAR, int MODE = 0>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : 1) k_dim1_bwd(Dim1BwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
   ADMMTV_DYN_SMEM(float2, X);
@@ -153,6 +160,25 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
   }
 
   for (int c = 1; c <= nout; c += CHUNK) {
+    // (a) anisotropic: every global load of the chunk is issued before any of them is consumed
+    constexpr bool HOIST = ADMMTV_BWD_HOIST && MODE == 0;
+    float2 hv1[HOIST ? CHUNK : 1][RPT], he1[HOIST ? CHUNK : 1][RPT], hv2[HOIST ? CHUNK : 1][RPT + 1],
+        he2[HOIST ? CHUNK : 1][RPT + 1], hbb[HOIST ? CHUNK : 1][RPT];
+    if (HOIST) {
+#pragma unroll
+      for (int cc = 0; cc < CHUNK; ++cc) {
+        const int j = jcol(c + cc), jn = jcol(c + cc + 1);
+        load_rows<RPT>(v1 + (size_t)jn * M + i0, hv1[cc]);
+        load_rows<RPT>(v2 + (size_t)j * M + i0, hv2[cc]);
+        hv2[cc][RPT] = v2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        if (HAS_VBAR) {
+          load_rows<RPT>(e1 + (size_t)jn * M + i0, he1[cc]);
+          load_rows<RPT>(e2 + (size_t)j * M + i0, he2[cc]);
+          he2[cc][RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        }
+        if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, hbb[cc]);
+      }
+    }
     float2 rr[CHUNK][RPT];
 #pragma unroll
     for (int cc = 0; cc < CHUNK; ++cc) {
@@ -196,7 +222,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
       // bbar += rbar_k
       if (MODE == 0) {
         float2 bb[RPT];
-        if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, bb);
+        if (HOIST) {
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) bb[r] = hbb[cc][r];
+        } else if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, bb);
 #pragma unroll
         for (int r = 0; r < RPT; ++r) bb[r] = A.first ? xc[r + 1] : cadd(bb[r], xc[r + 1]);
         store_rows<RPT>(bq + (size_t)j * M + i0, bb);
@@ -207,8 +236,16 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
         const bool own = col + 1 <= nout;
         float2 vv[RPT], ee[RPT];
         float nn[RPT], pp[RPT];
-        load_rows<RPT>(v1 + (size_t)jn * M + i0, vv);
-        if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)jn * M + i0, ee);
+        if (HOIST) {
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            vv[r] = hv1[cc][r];
+            ee[r] = he1[cc][r];
+          }
+        } else {
+          load_rows<RPT>(v1 + (size_t)jn * M + i0, vv);
+          if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)jn * M + i0, ee);
+        }
         if (MODE == 1) {
           load_rows_f<RPT>(nsq_g + (size_t)jn * M + i0, nn);
           load_rows_f<RPT>(ip_g + (size_t)jn * M + i0, pp);
@@ -226,11 +263,19 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd(Dim1BwdArgs A) {
       {
         float2 vv[RPT + 1], ee[RPT + 1];
         float nn[RPT + 1], pp[RPT + 1];
-        load_rows<RPT>(v2 + (size_t)j * M + i0, vv);
-        vv[RPT] = v2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
-        if (HAS_VBAR) {
-          load_rows<RPT>(e2 + (size_t)j * M + i0, ee);
-          ee[RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        if (HOIST) {
+#pragma unroll
+          for (int r = 0; r <= RPT; ++r) {
+            vv[r] = hv2[cc][r];
+            ee[r] = he2[cc][r];
+          }
+        } else {
+          load_rows<RPT>(v2 + (size_t)j * M + i0, vv);
+          vv[RPT] = v2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+          if (HAS_VBAR) {
+            load_rows<RPT>(e2 + (size_t)j * M + i0, ee);
+            ee[RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+          }
         }
         if (MODE == 1) {
           load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);

@@ -49,6 +49,13 @@ VARIANTS = {
     "pre1": ("ADMMTV_PRELOAD1=1",),
     "pre1_mb2": ("ADMMTV_PRELOAD1=1", "ADMMTV_MINB9=2"),
     "isonoatom": ("ADMMTV_ISO_NOATOM=1",),
+    "bh1": ("ADMMTV_BWD_HOIST=1",),
+    "bh1_mb2": ("ADMMTV_BWD_HOIST=1", "ADMMTV_MINB9B=2"),
+    "bh1_mb3": ("ADMMTV_BWD_HOIST=1", "ADMMTV_MINB9B=3"),
+    "bh0_mb3": ("ADMMTV_BWD_HOIST=0", "ADMMTV_MINB9B=3"),
+    "qpb1": ("ADMMTV_D2_ACC_QPB=1",),
+    "qpb2": ("ADMMTV_D2_ACC_QPB=2",),
+    "qpb8": ("ADMMTV_D2_ACC_QPB=8",),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
