@@ -17,6 +17,8 @@ FLAG_NO_CLAMP = 1
 FLAG_NOGRAD_REPEAT = 2
 FLAG_SHARED_INPUT = 4
 FLAG_CHANNEL_CONCAT = 8
+FLAG_ISO_PRECOMPUTE = 16
+FLAG_ISO_INLINE = 32
 
 # every symbol include/admmtv.h declares (tests check the .so exports exactly these)
 SYMBOLS = (

@@ -58,6 +58,7 @@ struct FwdWs {
   float* mask;
   float2 *bpk, *specA, *specB, *v0, *v1;
   float *nsq0, *nsq1;  // isotropic: per-pixel |v_k|^2 ring
+  float *isc0, *isc1;  // isotropic: per-pixel shrink scale ring
   size_t bytes;
 };
 static FwdWs carve_fwd(const Geom& g, void* ws) {
@@ -76,6 +77,8 @@ static FwdWs carve_fwd(const Geom& g, void* ws) {
   w.v1 = c.take<float2>(2 * g.pk);
   w.nsq0 = c.take<float>(g.plane * g.G);
   w.nsq1 = c.take<float>(g.plane * g.G);
+  w.isc0 = c.take<float>(g.plane * g.G);
+  w.isc1 = c.take<float>(g.plane * g.G);
   w.bytes = c.off;
   return w;
 }
@@ -153,6 +156,14 @@ struct DeviceGuard {
   }
 };
 
+// Isotropic per-pixel terms are precomputed by a tiny kernel per iteration when the problem is large
+// (bandwidth-bound); small, latency-bound problems compute them inside the sweep kernels instead.
+static inline bool iso_precompute(const Geom& g, int flags) {
+  if (flags & ADMMTV_FLAG_ISO_PRECOMPUTE) return true;
+  if (flags & ADMMTV_FLAG_ISO_INLINE) return false;
+  return (size_t)g.S * g.plane >= ((size_t)6 << 20);
+}
+
 // Enqueue the setup kernels shared by forward and backward.
 static int run_setup(const Geom& g, const float* h, const float* rho, float2* twM, float2* twN, double2* T,
                      float* ctab, float2* ktab, float2* sig, cudaStream_t st) {
@@ -211,7 +222,8 @@ int admmtv_check(const admmtv_desc* d) {
   if (d->iso != 0 && d->iso != 1) return ADMMTV_ERR_ENUM;
   if (d->activation < 0 || d->activation > 3) return ADMMTV_ERR_ENUM;
   if (d->has_bias != 0 && d->has_bias != 1) return ADMMTV_ERR_ENUM;
-  if (d->flags & ~(ADMMTV_FLAG_NO_CLAMP | ADMMTV_FLAG_NOGRAD_REPEAT | ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT))
+  if (d->flags & ~(ADMMTV_FLAG_NO_CLAMP | ADMMTV_FLAG_NOGRAD_REPEAT | ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT |
+                   ADMMTV_FLAG_ISO_PRECOMPUTE | ADMMTV_FLAG_ISO_INLINE))
     return ADMMTV_ERR_ENUM;
   if (d->groups < 0 || (d->groups > 1 && d->B % d->groups != 0)) return ADMMTV_ERR_SHAPE;
   if (d->groups <= 1 && (d->flags & (ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT))) return ADMMTV_ERR_ENUM;
@@ -247,7 +259,7 @@ int admmtv_forward_launches(const admmtv_desc* d, int with_ckpt) {
   (void)with_ckpt;
   if (admmtv_check(d)) return 0;
   int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 3 : 0);
-  n += d->iters + (d->iters - 1) * (d->iso ? 2 : 1) + 1;
+  n += d->iters + (d->iters - 1) * (d->iso ? 3 : 1) + 1;
   return n;
 }
 
@@ -335,30 +347,42 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       // isotropic: v_k and the per-pixel norm first (pass A), then shrink + D^T + FFT (pass B)
       const float2* v_in;
       float2* v_out;
-      const float* nsq_in;
       float* nsq_new;
+      const bool pre = iso_precompute(g, d->flags);
+      const float* s_prev = (k & 1) ? w.isc1 : w.isc0;   // s_{k-1}
+      float* s_new = (k & 1) ? w.isc0 : w.isc1;          // s_k
+      const float* nsq_prev;                             // |v_{k-1}|^2
       if (ckpt) {
         v_in = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
         v_out = ck.vck + (size_t)(k - 1) * 2 * g.pk;
-        nsq_in = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane * g.G : nullptr;
         nsq_new = ck.nck + (size_t)(k - 1) * g.plane * g.G;
+        nsq_prev = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane * g.G : nullptr;
       } else {
         v_in = (k & 1) ? w.v1 : w.v0;
         v_out = (k & 1) ? w.v0 : w.v1;
-        nsq_in = (k & 1) ? w.nsq1 : w.nsq0;
         nsq_new = (k & 1) ? w.nsq0 : w.nsq1;
+        nsq_prev = (k & 1) ? w.nsq1 : w.nsq0;
       }
-      cudaError_t e2 = cudaMemsetAsync(nsq_new, 0, g.plane * g.G * sizeof(float), st);
-      if (e2 != cudaSuccess) return (int)e2;
+      if (k == 1 || !pre) {   // with precompute, later iterations' accumulators are zeroed by the previous k_iso_scale
+        cudaError_t e2 = cudaMemsetAsync(nsq_new, 0, g.plane * g.G * sizeof(float), st);
+        if (e2 != cudaSuccess) return (int)e2;
+      }
+      float* nsq_next = nullptr;
+      if (k + 1 < g.K) nsq_next = ckpt ? ck.nck + (size_t)k * g.plane * g.G : (((k + 1) & 1) ? w.nsq0 : w.nsq1);
       tm_mark(tm, st, 1);
       Dim1FwdArgs fa{};
       fa.spec_in = w.specB; fa.twM = w.twM; fa.lambda = lambda; fa.rho = rho; fa.N = g.N; fa.Qg = g.Qg;
-      fa.vprev = v_in; fa.vnew = v_out; fa.nsq = nsq_in; fa.nsq_out = nsq_new;
+      fa.vprev = v_in; fa.vnew = v_out; fa.nsq = pre ? s_prev : nsq_prev; fa.pre = pre ? 1 : 0; fa.nsq_out = nsq_new;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_a(g, k > 1, fa, st); })
       if (rc) return rc;
+      if (pre) {
+        ADMMTV_LAUNCH(k_iso_scale, dim3((unsigned)((g.plane + 255) / 256), (unsigned)g.G), dim3(256), 0, st, (const float*)nsq_new,
+                      (const float*)lambda, (const float*)rho, s_new, nsq_next, (int)g.plane);
+        ADMMTV_CHECK_LAUNCH();
+      }
       Dim1FwdArgs f{};
       f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM; f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
-      f.vprev = v_out; f.nsq = nsq_new;
+      f.vprev = v_out; f.nsq = pre ? (const float*)s_new : (const float*)nsq_new; f.pre = pre ? 1 : 0;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_b(g, f, st); })
       if (rc) return rc;
     }

@@ -65,8 +65,9 @@ struct Dim1FwdArgs {
   const float2* bpk;
   const float2* vprev;  // [Q][2][N][M]; ignored when !HAS_VPREV (v_0 = 0)
   float2* vnew;         // [Q][2][N][M]
-  const float* nsq;     // isotropic: per-pixel |v|^2 [G][N][M] (pass B: of v_k ; pass A: of v_{k-1})
+  const float* nsq;     // isotropic: per-pixel shrink scale s [G][N][M] (pass B: s_k ; pass A: s_{k-1}), k_iso_scale
   float* nsq_out;       // isotropic pass A: accumulates |v_k|^2 (zeroed by the host)
+  int pre;              // 1: `nsq` holds the precomputed scale s; 0: it holds |v|^2 and s is computed in the kernel
   const float2* twM;
   const float* lambda;  // [G]
   const float* rho;     // [G]
@@ -101,8 +102,9 @@ struct Dim1BwdArgs {
   const float* lambda;
   const float* rho;
   double* acc;             // [0] rhobar (direct term), [1] taubar
-  const float* nsq;        // isotropic pass B: |v_{k-1}|^2 per pixel
-  const float* ip;         // isotropic pass B: <q, v_{k-1}> per pixel
+  const float2* sc;        // isotropic pass B: per-pixel (s, tau ip / n^3) [G][N][M] (k_iso_coef), or null:
+  const float* nsq;        //   then |v_{k-1}|^2 and
+  const float* ip;         //   <q, v_{k-1}> per pixel, and the terms are computed in the kernel
   float* ip_out;           // isotropic pass A: accumulates <q, v_{k-1}> (zeroed by the host)
   PlaneMap pm;
   int N, S;

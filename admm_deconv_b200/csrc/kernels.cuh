@@ -502,10 +502,10 @@ ADMMTV_DI Shrunk shrink_iso(float2 v, float s) {
 }
 
 // MODE 0: the fused anisotropic kernel described above.
-// MODE 1: isotropic pass B -- v_k (A.vprev) and the per-pixel |v_k|^2 (A.nsq) are given; no IFFT,
-//         no state write: s = max(1 - tau/n, 0), w = (2s-1) v, r = b + rho D^T w, dim-1 FFT.
-// MODE 2: isotropic pass A -- dim-1 IFFT -> x_k ; v_k = D x_k + u_{k-1} with u_{k-1} from v_{k-1} (A.vprev) and
-//         |v_{k-1}|^2 (A.nsq) ; store v_k ; A.nsq_out[pixel] += |v_k|^2 (float atomics) ; no FFT.
+// MODE 1: isotropic pass B -- v_k (A.vprev) and the per-pixel shrink scale s_k = max(1 - tau/n_k, 0) (A.nsq,
+//         precomputed by k_iso_scale) are given; no IFFT, no state write: w = (2s-1) v, r = b + rho D^T w, FFT.
+// MODE 2: isotropic pass A -- dim-1 IFFT -> x_k ; v_k = D x_k + u_{k-1} with u_{k-1} = (1 - s_{k-1}) v_{k-1}
+//         (A.vprev, A.nsq = s_{k-1}) ; store v_k ; A.nsq_out[pixel] += |v_k|^2 (float atomics) ; no FFT.
 template <int LM, bool HAS_VPREV, int MODE = 0>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
@@ -553,6 +553,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   const float tau = A.lambda[grp] / rho;  // ops.jl:102
   const int i0 = tid * RPT;
   const float* nsq_g = MODE != 0 ? A.nsq + (size_t)grp * plane : nullptr;
+  const bool pre = A.pre != 0;  // A.nsq holds the precomputed scale s (large problems) or |v|^2 (small, latency-bound ones)
+  auto SC = [&](float t) { return pre ? t : iso_scale(t, tau); };
   float* nsq_o = MODE == 2 ? A.nsq_out + (size_t)grp * plane : nullptr;
   const float2* vp1 = A.vprev + ((size_t)q * 2 + 0) * plane;
   const float2* vp2 = A.vprev + ((size_t)q * 2 + 1) * plane;
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       float2 v = csub(X[sidx<LM>(1, i0 + r)], X[sidx<LM>(0, i0 + r)]);
-      if (HAS_VPREV) v = cadd(v, shrink_iso(up[r], iso_scale(nn[r], tau)).u);
+      if (HAS_VPREV) v = cadd(v, shrink_iso(up[r], SC(nn[r])).u);
       w1c[r] = v;
     }
     store_rows<RPT>(vn1 + (size_t)j * M + i0, w1c);
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     load_rows<RPT>(vp1 + (size_t)j * M + i0, vv);
     load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) w1c[r] = shrink_iso(vv[r], iso_scale(nn[r], tau)).w;
+    for (int r = 0; r < RPT; ++r) w1c[r] = shrink_iso(vv[r], SC(nn[r])).w;
   } else {
     const int j = jcol(1);
     float2 up[RPT], vst[RPT];
@@ -638,7 +640,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
           for (int r = 0; r < RPT; ++r) {
             float2 v = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
-            if (HAS_VPREV) v = cadd(v, shrink_iso(g1[cc][r], iso_scale(n1[cc][r], tau)).u);
+            if (HAS_VPREV) v = cadd(v, shrink_iso(g1[cc][r], SC(n1[cc][r])).u);
             w1n[r] = v;
           }
           store_rows<RPT>(vn1 + (size_t)jn * M + i0, w1n);
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
           float2 v = csub(xc[r + 1], xc[r]);
-          if (HAS_VPREV) v = cadd(v, shrink_iso(g2[cc][r], iso_scale(n2[cc][r], tau)).u);
+          if (HAS_VPREV) v = cadd(v, shrink_iso(g2[cc][r], SC(n2[cc][r])).u);
           vst[r] = v;
           sq[r] = w1c[r].x * w1c[r].x + w1c[r].y * w1c[r].y + v.x * v.x + v.y * v.y;
           w1c[r] = w1n[r];
@@ -660,9 +662,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       }
       if (MODE == 1) {
 #pragma unroll
-        for (int r = 0; r < RPT; ++r) w1n[r] = shrink_iso(g1[cc][r], iso_scale(n1[cc][r], tau)).w;
+        for (int r = 0; r < RPT; ++r) w1n[r] = shrink_iso(g1[cc][r], SC(n1[cc][r])).w;
 #pragma unroll
-        for (int r = 0; r <= RPT; ++r) w2[r] = shrink_iso(g2[cc][r], iso_scale(n2[cc][r], tau)).w;
+        for (int r = 0; r <= RPT; ++r) w2[r] = shrink_iso(g2[cc][r], SC(n2[cc][r])).w;
       } else {
       float2 xc[RPT + 2];  // rows i0-1 .. i0+RPT of column col
       xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];

@@ -59,22 +59,18 @@ ADMMTV_DI float2 iso_bwd_point(float2 d, float2 v, float2 eb, float rho, float s
   const float2 qq = make_float2(2.f * gb.x - eb.x, 2.f * gb.y - eb.y);
   return make_float2(eb.x - gb.x + s * qq.x + coef * v.x, eb.y - gb.y + s * qq.y + coef * v.y);
 }
-ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float tau, float nsq, float ip, bool own, bool count_tau,
-                              double& racc, double& tacc) {
-  float s, coef, tt;
-  iso_pix(nsq, ip, tau, s, coef, tt);
+ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float2 sc /* (s, coef) */, bool own, double& racc) {
   if (own) {
-    const Shrunk g = shrink_iso(v, s);
+    const Shrunk g = shrink_iso(v, sc.x);
     racc += (double)(d.x * g.w.x) + (double)(d.y * g.w.y);
-    if (count_tau) tacc -= (double)tt;
   }
-  return iso_bwd_point(d, v, eb, rho, s, coef);
+  return iso_bwd_point(d, v, eb, rho, sc.x, sc.y);
 }
 
 // MODE 2: isotropic pass A -- dim-1 IFFT -> rbar_k ; bbar += rbar_k ; q = 2 rho D rbar_k - vbar_k ;
 //         A.ip_out[pixel] += <q, v_{k-1}> (float atomics) ; nothing else is written.
-// MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel |v_{k-1}|^2 in A.nsq, <q,v> in A.ip; bbar was
-// accumulated by pass A).
+// MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel (s, tau ip / n^3) in A.sc from k_iso_coef, which also
+// adds the per-pixel taubar terms; bbar was accumulated by pass A).
 template <int LM, bool HAS_VBAR, int MODE = 0>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : 1) k_dim1_bwd(Dim1BwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
@@ -112,10 +108,21 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   const float rho = A.rho[grp];
   const float tau = A.lambda[grp] / rho;
   const int i0 = tid * RPT;
-  const float* nsq_g = MODE == 1 ? A.nsq + (size_t)grp * plane : nullptr;
-  const float* ip_g = MODE == 1 ? A.ip + (size_t)grp * plane : nullptr;
+  double racc = 0.0, tacc = 0.0;
+  const bool pre = MODE == 1 && A.sc != nullptr;  // per-pixel (s, tau ip / n^3) precomputed by k_iso_coef
+  const float2* sc_g = pre ? A.sc + (size_t)grp * plane : nullptr;
+  const float* nsq_g = (MODE == 1 && !pre) ? A.nsq + (size_t)grp * plane : nullptr;
+  const float* ip_g = (MODE == 1 && !pre) ? A.ip + (size_t)grp * plane : nullptr;
+  const bool tau_owner = (q % A.pm.Qg) == 0;  // inline path: the per-pixel taubar term is counted once per group
+  // (s, coef) of one pixel: loaded, or computed here (small, latency-bound problems skip the extra launch)
+  auto PIX = [&](const float2* scp, size_t off, bool count) {
+    if (pre) return scp[off];
+    float s_, c_, t_;
+    iso_pix(nsq_g[off], ip_g[off], tau, s_, c_, t_);
+    if (count && tau_owner) tacc -= (double)t_;
+    return make_float2(s_, c_);
+  };
   float* ip_o = MODE == 2 ? A.ip_out + (size_t)grp * plane : nullptr;
-  const bool tau_owner = (q % A.pm.Qg) == 0;  // the per-pixel taubar term is counted once per group
   const float2* v1 = A.vck + ((size_t)q * 2 + 0) * plane;
   const float2* v2 = A.vck + ((size_t)q * 2 + 1) * plane;
   const float2* e1 = A.vbar_in + ((size_t)q * 2 + 0) * plane;
@@ -124,7 +131,6 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   float2* o2 = A.vbar_out + ((size_t)q * 2 + 1) * plane;
   float2* bq = A.bbar + (size_t)q * plane;
   const float2 zero2 = make_float2(0.f, 0.f);
-  double racc = 0.0, tacc = 0.0;
 
   float2 n1c[RPT];  // vbar_{k-1}, channel 1, current column
   float p1c[RPT];   // MODE 2: <q1, v1> of the current column
@@ -143,17 +149,17 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   } else {
     const int j = jcol(1);
     float2 vv[RPT], ee[RPT];
-    float nn[RPT], pp[RPT];
+    float2 ss[RPT];
     load_rows<RPT>(v1 + (size_t)j * M + i0, vv);
     if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)j * M + i0, ee);
     if (MODE == 1) {
-      load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
-      load_rows_f<RPT>(ip_g + (size_t)j * M + i0, pp);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) ss[r] = PIX(sc_g, (size_t)j * M + i0 + r, false);
     }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       const float2 d = csub(X[sidx<LM>(1, i0 + r)], X[sidx<LM>(0, i0 + r)]);
-      if (MODE == 1) n1c[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], true, false, racc, tacc);
+      if (MODE == 1) n1c[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, ss[r], true, racc);
       else n1c[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, true, racc, tacc);
     }
     store_rows<RPT>(o1 + (size_t)j * M + i0, n1c);
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
       {
         const bool own = col + 1 <= nout;
         float2 vv[RPT], ee[RPT];
-        float nn[RPT], pp[RPT];
+        float2 ss[RPT];
         if (HOIST) {
 #pragma unroll
           for (int r = 0; r < RPT; ++r) {
@@ -247,13 +253,13 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
           if (HAS_VBAR) load_rows<RPT>(e1 + (size_t)jn * M + i0, ee);
         }
         if (MODE == 1) {
-          load_rows_f<RPT>(nsq_g + (size_t)jn * M + i0, nn);
-          load_rows_f<RPT>(ip_g + (size_t)jn * M + i0, pp);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) ss[r] = PIX(sc_g, (size_t)jn * M + i0 + r, false);
         }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
           const float2 d = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
-          if (MODE == 1) n1n[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], own, false, racc, tacc);
+          if (MODE == 1) n1n[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, ss[r], own, racc);
           else n1n[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, own, racc, tacc);
         }
         if (own) store_rows<RPT>(o1 + (size_t)jn * M + i0, n1n);
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
       float2 n2[RPT + 1];
       {
         float2 vv[RPT + 1], ee[RPT + 1];
-        float nn[RPT + 1], pp[RPT + 1];
+        float2 ss[RPT + 1];
         if (HOIST) {
 #pragma unroll
           for (int r = 0; r <= RPT; ++r) {
@@ -278,16 +284,14 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
           }
         }
         if (MODE == 1) {
-          load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
-          nn[RPT] = nsq_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
-          load_rows_f<RPT>(ip_g + (size_t)j * M + i0, pp);
-          pp[RPT] = ip_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) ss[r] = PIX(sc_g, (size_t)j * M + i0 + r, true);   // own pixels: counted once
+          ss[RPT] = PIX(sc_g, (size_t)j * M + ((i0 + RPT) & (M - 1)), false);
         }
 #pragma unroll
         for (int r = 0; r <= RPT; ++r) {
           const float2 d = csub(xc[r + 1], xc[r]);
-          // the taubar term is per PIXEL: counted once, by pair 0, with the pixel's channel-2 point
-          if (MODE == 1) n2[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, nn[r], pp[r], r < RPT, tau_owner, racc, tacc);
+          if (MODE == 1) n2[r] = iso_bwd_full(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, ss[r], r < RPT, racc);
           else n2[r] = bwd_point(d, vv[r], HAS_VBAR ? ee[r] : zero2, rho, tau, r < RPT, racc, tacc);
         }
         store_rows<RPT>(o2 + (size_t)j * M + i0, n2);

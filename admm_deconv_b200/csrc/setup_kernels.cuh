@@ -121,6 +121,38 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
 
 
 // ------------------------------------------------------------------------------------------
+// isotropic per-pixel terms (one thread per pixel of one group; blockIdx.y = group)
+// ------------------------------------------------------------------------------------------
+// s = max(1 - tau / n, 0), n = sqrt(nsq)                                   (BT, ops.jl:10; n = 0 -> 0)
+// also zeroes `zero_next` (the accumulator of the NEXT iteration), which replaces a memset launch
+static __global__ void k_iso_scale(const float* __restrict__ nsq, const float* __restrict__ lambda, const float* __restrict__ rho,
+                                   float* __restrict__ s_out, float* __restrict__ zero_next, int npix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (i >= npix) return;
+  if (zero_next) zero_next[(size_t)g * npix + i] = 0.f;
+  const float tau = lambda[g] / rho[g];
+  const float n = sqrtf(nsq[(size_t)g * npix + i]);
+  s_out[(size_t)g * npix + i] = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
+}
+// backward: (s, 1[n>tau] tau ip / n^3) per pixel, and taubar -= sum_pixels 1[n>tau] ip / n   (acc[8g+1])
+// re-zeroes ip for the next iteration's accumulation (replaces a memset launch)
+static __global__ void k_iso_coef(const float* __restrict__ nsq, float* __restrict__ ip, const float* __restrict__ lambda,
+                                  const float* __restrict__ rho, float2* __restrict__ sc, double* acc, int npix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // npix is a multiple of the block size
+  const int g = blockIdx.y;
+  const float tau = lambda[g] / rho[g];
+  const float n = sqrtf(nsq[(size_t)g * npix + i]);
+  const float p = ip[(size_t)g * npix + i];
+  ip[(size_t)g * npix + i] = 0.f;
+  const bool act = n > tau;
+  const float s = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
+  sc[(size_t)g * npix + i] = make_float2(s, act ? tau * p / (n * n * n) : 0.f);
+  const double tot = block_sum(act ? (double)(p / n) : 0.0);
+  if (threadIdx.x == 0) atomicAdd(acc + 8 * g + 1, -tot);
+}
+
+// ------------------------------------------------------------------------------------------
 // parameter gradients from the spectral accumulators ("after the loop")
 //   Cbar = G/(MN) ; Sbar = -Cbar C^2 (cotangent of |Sigma|^2) ; rhobar += sum Sbar (|Lx|^2+|Ly|^2)
 //   hbar[a,b] = Re sum_k W[k] e^{+2 pi i (k1 a/M + k2 b/N)},

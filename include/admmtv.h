@@ -46,7 +46,11 @@ enum {
   ADMMTV_FLAG_NOGRAD_REPEAT = 2, /* train.jl:10 variant: no ∂weight through the spatial H^T y path */
   /* grouped calls (desc.groups > 1), see below */
   ADMMTV_FLAG_SHARED_INPUT = 4,  /* every group reads the same y (M,N,P,B/groups) */
-  ADMMTV_FLAG_CHANNEL_CONCAT = 8 /* x_out is (M,N,groups*P,B/groups): group g in channels [gP,(g+1)P) */
+  ADMMTV_FLAG_CHANNEL_CONCAT = 8, /* x_out is (M,N,groups*P,B/groups): group g in channels [gP,(g+1)P) */
+  /* isotropic per-pixel terms: precomputed by a tiny kernel per iteration (default for >= 6 Mi plane-pixels)
+   * or computed inside the sweep kernels (default below that, where launches dominate).  Overrides: */
+  ADMMTV_FLAG_ISO_PRECOMPUTE = 16,
+  ADMMTV_FLAG_ISO_INLINE = 32
 };
 
 /* error codes (<0) */

@@ -40,7 +40,7 @@ def test_desc_layout_matches_header():
         (dict(M=48), -3), (dict(N=16), -3), (dict(M=8192), -3),
         (dict(M=0), -2), (dict(kh=3, kw=0), -2), (dict(kh=65, kw=3, M=64), -2),
         (dict(iters=0), -4),
-        (dict(iso=2), -5), (dict(activation=7), -5), (dict(flags=64), -5),
+        (dict(iso=2), -5), (dict(activation=7), -5), (dict(flags=128), -5),
     ],
 )
 def test_check_error_codes(lib, kw, code):

@@ -63,8 +63,9 @@ def test_emu_golden_backward(be):
         print(os.path.basename(f), r)
 
 
+@pytest.mark.parametrize("iso_flag", [16, 32])   # ADMMTV_FLAG_ISO_PRECOMPUTE / ADMMTV_FLAG_ISO_INLINE: both code paths
 @pytest.mark.parametrize("M,N,P,B,kh,kw,K", [(32, 32, 1, 4, 0, 0, 5), (32, 64, 3, 1, 5, 4, 4)])
-def test_emu_backward_iso(be, M, N, P, B, kh, kw, K):
+def test_emu_backward_iso(be, M, N, P, B, kh, kw, K, iso_flag):
     y, h, _ = make_case(M, N, P, B, kh, kw, 50 + M + K)
     xbar = torch.from_numpy(np.random.default_rng(K).standard_normal((M, N, P, B)))
-    check_backward(be, y, h, 0.05, 0.3, True, K, xbar, tol=1e-5, tol_scalar=1e-4, tol_e2e=1e-4)
+    check_backward(be, y, h, 0.05, 0.3, True, K, xbar, flags=1 | iso_flag, tol=1e-5, tol_scalar=1e-4, tol_e2e=1e-4)

@@ -121,11 +121,12 @@ def test_layer_module_train_step_updates_parameters():
     assert layer.packed_grads().numel() == 49 + 3
 
 
+@pytest.mark.parametrize("iso_flag", [16, 32])   # ADMMTV_FLAG_ISO_PRECOMPUTE / ADMMTV_FLAG_ISO_INLINE: both code paths
 @pytest.mark.parametrize("M,N,P,B,kh,kw,K", [(32, 32, 1, 4, 0, 0, 5), (64, 64, 3, 2, 7, 7, 10), (256, 128, 3, 2, 9, 9, 8), (512, 512, 1, 2, 5, 5, 4)])
-def test_backward_iso_teacher_forced(be, M, N, P, B, kh, kw, K):
+def test_backward_iso_teacher_forced(be, M, N, P, B, kh, kw, K, iso_flag):
     y, h, g = make_case(M, N, P, B, kh, kw, 600 + M + K)
     xbar = 2.0 * (y - g) / y.numel() * 1e3
-    r = check_backward(be, y, h, 0.0041, 0.021, True, K, xbar, tol=1e-5, tol_scalar=2e-4, tol_e2e=1e-3)
+    r = check_backward(be, y, h, 0.0041, 0.021, True, K, xbar, flags=1 | iso_flag, tol=1e-5, tol_scalar=2e-4, tol_e2e=1e-3)
     print(r)
 
 
