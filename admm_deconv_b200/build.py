@@ -19,7 +19,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_OBJ = os.path.join(EMU_DIR, "_build")
 EMU_LIB = os.path.join(EMU_OBJ, "libadmmtv_emu.so")
 
-LOG2_SIZES = tuple(range(5, 13))  # FFT lengths 32 .. 4096
+LOG2_SIZES = tuple(range(5, 13)) + tuple(range(20, 32))  # size ids: 2^5..2^12, then 96,160,...,1920 (fft_core.cuh dim_len)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

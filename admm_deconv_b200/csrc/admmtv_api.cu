@@ -22,7 +22,7 @@ static Geom geom(const admmtv_desc* d) {
   g.M = d->M; g.N = d->N; g.P = d->P; g.B = d->B;
   g.S = d->P * d->B;
   g.Q = (g.S + 1) / 2;
-  g.LM = ilog2(d->M); g.LN = ilog2(d->N);
+  g.LM = dim_id(d->M); g.LN = dim_id(d->N);
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
   g.G = d->groups > 1 ? d->groups : 1;
   g.Bg = d->B / g.G;
@@ -114,6 +114,18 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
     case 10: { constexpr int NAME = 10; __VA_ARGS__ } break;                 \
     case 11: { constexpr int NAME = 11; __VA_ARGS__ } break;                 \
     case 12: { constexpr int NAME = 12; __VA_ARGS__ } break;                 \
+    case 20: { constexpr int NAME = 20; __VA_ARGS__ } break;                 \
+    case 21: { constexpr int NAME = 21; __VA_ARGS__ } break;                 \
+    case 22: { constexpr int NAME = 22; __VA_ARGS__ } break;                 \
+    case 23: { constexpr int NAME = 23; __VA_ARGS__ } break;                 \
+    case 24: { constexpr int NAME = 24; __VA_ARGS__ } break;                 \
+    case 25: { constexpr int NAME = 25; __VA_ARGS__ } break;                 \
+    case 26: { constexpr int NAME = 26; __VA_ARGS__ } break;                 \
+    case 27: { constexpr int NAME = 27; __VA_ARGS__ } break;                 \
+    case 28: { constexpr int NAME = 28; __VA_ARGS__ } break;                 \
+    case 29: { constexpr int NAME = 29; __VA_ARGS__ } break;                 \
+    case 30: { constexpr int NAME = 30; __VA_ARGS__ } break;                 \
+    case 31: { constexpr int NAME = 31; __VA_ARGS__ } break;                 \
     default: break;                                                          \
   }                                                                          \
   return ADMMTV_ERR_UNSUPPORTED;
@@ -128,6 +140,18 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
     case 10: { constexpr int NAME = 10; __VA_ARGS__ } break;                 \
     case 11: { constexpr int NAME = 11; __VA_ARGS__ } break;                 \
     case 12: { constexpr int NAME = 12; __VA_ARGS__ } break;                 \
+    case 20: { constexpr int NAME = 20; __VA_ARGS__ } break;                 \
+    case 21: { constexpr int NAME = 21; __VA_ARGS__ } break;                 \
+    case 22: { constexpr int NAME = 22; __VA_ARGS__ } break;                 \
+    case 23: { constexpr int NAME = 23; __VA_ARGS__ } break;                 \
+    case 24: { constexpr int NAME = 24; __VA_ARGS__ } break;                 \
+    case 25: { constexpr int NAME = 25; __VA_ARGS__ } break;                 \
+    case 26: { constexpr int NAME = 26; __VA_ARGS__ } break;                 \
+    case 27: { constexpr int NAME = 27; __VA_ARGS__ } break;                 \
+    case 28: { constexpr int NAME = 28; __VA_ARGS__ } break;                 \
+    case 29: { constexpr int NAME = 29; __VA_ARGS__ } break;                 \
+    case 30: { constexpr int NAME = 30; __VA_ARGS__ } break;                 \
+    case 31: { constexpr int NAME = 31; __VA_ARGS__ } break;                 \
     default: RC = ADMMTV_ERR_UNSUPPORTED; break;                             \
   }
 
@@ -200,7 +224,7 @@ const char* admmtv_strerror(int code) {
     case ADMMTV_OK: return "ok";
     case ADMMTV_ERR_NULL: return "admmtv: null pointer argument";
     case ADMMTV_ERR_SHAPE: return "admmtv: invalid shape (dims must be positive, PSF no larger than the image)";
-    case ADMMTV_ERR_UNSUPPORTED: return "admmtv: unsupported size (M and N must be powers of two in 32..4096)";
+    case ADMMTV_ERR_UNSUPPORTED: return "admmtv: unsupported size (M and N must be a power of two in 32..4096 or one of 96, 160, 192, 320, 384, 480, 640, 768, 960, 1280, 1536, 1920)";
     case ADMMTV_ERR_ITERS: return "admmtv: iters must be >= 1";
     case ADMMTV_ERR_ENUM: return "admmtv: invalid enum / flag value in descriptor";
     case ADMMTV_ERR_ALIGN: return "admmtv: workspace and checkpoint must be 256-byte aligned";
@@ -216,8 +240,7 @@ int admmtv_check(const admmtv_desc* d) {
   if (d->M <= 0 || d->N <= 0 || d->P <= 0 || d->B <= 0) return ADMMTV_ERR_SHAPE;
   if (d->kh < 0 || d->kw < 0 || ((d->kh == 0) != (d->kw == 0))) return ADMMTV_ERR_SHAPE;
   if (d->kh > d->M || d->kw > d->N) return ADMMTV_ERR_SHAPE;
-  if ((d->M & (d->M - 1)) || (d->N & (d->N - 1)) || d->M < 32 || d->N < 32 || d->M > 4096 || d->N > 4096)
-    return ADMMTV_ERR_UNSUPPORTED;
+  if (dim_id(d->M) < 0 || dim_id(d->N) < 0) return ADMMTV_ERR_UNSUPPORTED;
   if (d->iters < 1) return ADMMTV_ERR_ITERS;
   if (d->iso != 0 && d->iso != 1) return ADMMTV_ERR_ENUM;
   if (d->activation < 0 || d->activation > 3) return ADMMTV_ERR_ENUM;

@@ -28,6 +28,20 @@ ADMMTV_HD constexpr int plan_radix(int L, int s) {
     case 1024: return s == 0 ? 16 : (s < 3 ? 8 : 1);
     case 2048: return s < 2 ? 16 : (s == 2 ? 8 : 1);
     case 4096: return s < 3 ? 16 : 1;
+    // mixed radix: odd factors first (power-of-two strides for the remaining passes), the last pass
+    // contiguous with an even radix
+    case 96:   return s == 0 ? 3 : (s == 1 ? 8 : (s == 2 ? 4 : 1));
+    case 160:  return s == 0 ? 5 : (s == 1 ? 8 : (s == 2 ? 4 : 1));
+    case 192:  return s == 0 ? 3 : (s < 3 ? 8 : 1);
+    case 320:  return s == 0 ? 5 : (s < 3 ? 8 : 1);
+    case 384:  return s == 0 ? 3 : (s == 1 ? 16 : (s == 2 ? 8 : 1));
+    case 480:  return s == 0 ? 3 : (s == 1 ? 5 : (s == 2 ? 8 : (s == 3 ? 4 : 1)));
+    case 640:  return s == 0 ? 5 : (s == 1 ? 16 : (s == 2 ? 8 : 1));
+    case 768:  return s == 0 ? 3 : (s < 3 ? 16 : 1);
+    case 960:  return s == 0 ? 3 : (s == 1 ? 5 : (s < 4 ? 8 : 1));
+    case 1280: return s == 0 ? 5 : (s < 3 ? 16 : 1);
+    case 1536: return s == 0 ? 3 : (s < 4 ? 8 : 1);
+    case 1920: return s == 0 ? 3 : (s == 1 ? 5 : (s == 2 ? 16 : (s == 3 ? 8 : 1)));
     default:   return 1;
   }
 }
@@ -43,6 +57,25 @@ ADMMTV_HD constexpr int plan_sublen(int L, int s) {
   return len;
 }
 ADMMTV_HD constexpr bool plan_supported(int L) { return plan_stages(L) >= 2; }
+
+// Supported transform lengths are addressed by a small id so that kernels stay templated on one int:
+// ids 5..12 are the powers of two 32..4096, ids 20..31 the 3- and 5-smooth lengths below.
+ADMMTV_HD constexpr int dim_len(int id) {
+  switch (id) {
+    case 20: return 96;   case 21: return 160;  case 22: return 192;  case 23: return 320;
+    case 24: return 384;  case 25: return 480;  case 26: return 640;  case 27: return 768;
+    case 28: return 960;  case 29: return 1280; case 30: return 1536; case 31: return 1920;
+    default: return (id >= 5 && id <= 12) ? (1 << id) : 0;
+  }
+}
+ADMMTV_HD constexpr bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+ADMMTV_HD inline int dim_id(int L) {
+  for (int id = 5; id <= 12; ++id)
+    if (dim_len(id) == L) return id;
+  for (int id = 20; id <= 31; ++id)
+    if (dim_len(id) == L) return id;
+  return -1;
+}
 
 // frequency index held at storage position p after the forward (DIF) passes
 ADMMTV_HD inline int pos_to_freq(int L, int p) {
@@ -123,6 +156,39 @@ struct Dft {
 template <bool INV>
 struct Dft<1, INV> {
   static ADMMTV_DI void run(float2*) {}
+};
+// radix 3:  X1,2 = a0 - (a1+a2)/2 -+ i (sqrt3/2)(a1-a2)   (forward; the inverse swaps them)
+template <bool INV>
+struct Dft<3, INV> {
+  static ADMMTV_DI void run(float2* a) {
+    constexpr float S = 0.86602540378443865f;
+    const float2 t1 = cadd(a[1], a[2]);
+    const float2 t2 = make_float2(a[0].x - 0.5f * t1.x, a[0].y - 0.5f * t1.y);
+    const float2 d = csub(a[1], a[2]);
+    const float2 r = make_float2(S * d.y, -S * d.x);  // -i S d
+    a[0] = cadd(a[0], t1);
+    a[1] = INV ? csub(t2, r) : cadd(t2, r);
+    a[2] = INV ? cadd(t2, r) : csub(t2, r);
+  }
+};
+// radix 5
+template <bool INV>
+struct Dft<5, INV> {
+  static ADMMTV_DI void run(float2* a) {
+    constexpr float C1 = 0.30901699437494742f, C2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
+    constexpr float S1 = 0.95105651629515357f, S2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
+    const float2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+    const float2 m1 = make_float2(a[0].x + C1 * t1.x + C2 * t2.x, a[0].y + C1 * t1.y + C2 * t2.y);
+    const float2 m2 = make_float2(a[0].x + C2 * t1.x + C1 * t2.x, a[0].y + C2 * t1.y + C1 * t2.y);
+    const float2 n1 = make_float2(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
+    const float2 n2 = make_float2(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y);
+    const float2 r1 = make_float2(n1.y, -n1.x), r2 = make_float2(n2.y, -n2.x);  // -i n
+    a[0] = cadd(a[0], cadd(t1, t2));
+    a[1] = INV ? csub(m1, r1) : cadd(m1, r1);
+    a[4] = INV ? cadd(m1, r1) : csub(m1, r1);
+    a[2] = INV ? csub(m2, r2) : cadd(m2, r2);
+    a[3] = INV ? cadd(m2, r2) : csub(m2, r2);
+  }
 };
 
 // p[m] = w^m, m = 0..R-1, product tree of depth log2(m)

@@ -40,8 +40,14 @@ struct TwP {
 // same wi (hence the same twiddles) whenever the block is at least one line wide.
 template <int ITEMS, int NT, class Prep, class Body>
 ADMMTV_DI void for_items(int tid, int nlines, Prep prep, Body body) {
-  if constexpr (NT >= ITEMS) {
-    static_assert(NT % ITEMS == 0, "block must be a multiple of the line's work items");
+  if constexpr (NT % ITEMS != 0 && ITEMS % NT != 0) {
+    // generic mapping (non-power-of-two lengths): flat (line, item) index, twiddles per item
+    for (int it = tid; it < nlines * ITEMS; it += NT) {
+      const int wi = it % ITEMS, c = it / ITEMS;
+      const auto ctx = prep(wi);
+      body(wi, c, ctx);
+    }
+  } else if constexpr (NT >= ITEMS) {
     const int wi = tid % ITEMS;
     const auto ctx = prep(wi);
 #pragma unroll(kUnrollItems)
@@ -147,18 +153,39 @@ ADMMTV_DI void l2_prefetch_bulk(const void* p, unsigned bytes) {
 #endif
 }
 
+// block size of the dim-1 kernels for a non-power-of-two length: M / RPT threads, a multiple of 32, at most 320
+ADMMTV_HD constexpr int dim1_nt_generic(int M) {
+  for (int r = 1; r <= 16; ++r)
+    if (M % r == 0 && (M / r) % 32 == 0 && M / r <= 320) return M / r;
+  return 32;
+}
+ADMMTV_HD constexpr int dim1_tc_generic(int M) {  // tile columns (incl. 2 halo) within ~64 KB of shared memory
+  return M <= 192 ? 34 : (M <= 384 ? 18 : (M <= 768 ? 10 : 6));
+}
+
 template <int LM>
 struct Dim1Cfg {
-  static constexpr int M = 1 << LM;
-  static constexpr int NT = LM <= 8 ? M : (LM == 9 ? ADMMTV_NT9 : (LM == 10 ? 256 : (LM == 11 ? ADMMTV_NT11 : 512)));
+  static constexpr int M = dim_len(LM);
+  static constexpr bool POW2 = is_pow2(M);
+  static constexpr int NT = !POW2 ? dim1_nt_generic(M)
+                                  : (LM <= 8 ? M : (LM == 9 ? ADMMTV_NT9 : (LM == 10 ? 256 : (LM == 11 ? ADMMTV_NT11 : 512))));
   static constexpr int MINB = LM == 9 ? ADMMTV_MINB9 : 1;
   static constexpr int RPT = M / NT;                  // rows per thread in the stencil sweep
   static constexpr int CHUNK = LM == 9 ? ADMMTV_CHUNK9 : (LM == 8 ? ADMMTV_CHUNK8 : (RPT >= 8 ? 1 : 8 / RPT));  // columns between barriers
   // tile columns including the 2 halo columns
-  static constexpr int TC = LM <= 7 ? 34 : (LM == 8 ? ADMMTV_TC8 : (LM == 9 ? ADMMTV_TC9 : (LM == 11 ? ADMMTV_TC11 : 6)));
+  static constexpr int TC = !POW2 ? dim1_tc_generic(M)
+                                  : (LM <= 7 ? 34 : (LM == 8 ? ADMMTV_TC8 : (LM == 9 ? ADMMTV_TC9 : (LM == 11 ? ADMMTV_TC11 : 6))));
   static constexpr int CO = TC - 2;                   // output columns per block
   static constexpr size_t SMEM = (size_t)TC * M * sizeof(float2);
+  static_assert(M % NT == 0 && NT % 32 == 0, "dim-1 block must tile the column in whole warps");
 };
+
+// row index modulo M (circular boundary of the difference operators)
+template <int M>
+ADMMTV_DI int wrapm(int i) {
+  if constexpr (is_pow2(M)) return i & (M - 1);
+  else return i < 0 ? i + M : (i >= M ? i - M : i);
+}
 
 // Shared-memory placement of (column c, row i): X[c*M + (i ^ swz_row(i) ^ swz_col(c))].
 // The XOR swizzle folds higher index bits into the 4 bits that select the 8-byte bank pair, so
@@ -172,6 +199,7 @@ struct Dim1Cfg {
 template <int LM>
 ADMMTV_HD constexpr int swz_row(int i) {
 #if ADMMTV_SWZ
+  if (LM >= 20) return 0;   // non-power-of-two lengths: plain layout
   if (LM == 5) return ((i >> 2) & 15) ^ ((i >> 3) & 15);
   if (LM == 6 || LM == 7) return (i >> 3) & 15;
   if (LM == 8) return (i >> 4) & 15;
@@ -184,6 +212,7 @@ ADMMTV_HD constexpr int swz_row(int i) {
 template <int LM>
 ADMMTV_HD constexpr int swz_col(int c) {
 #if ADMMTV_SWZ
+  if (LM >= 20) return 0;
   if (LM == 5) return (c << 2) & 15;
   if (LM == 6 || LM == 7) return (c << 3) & 15;
 #endif
@@ -191,17 +220,24 @@ ADMMTV_HD constexpr int swz_col(int c) {
 }
 template <int LM>
 ADMMTV_DI int sidx(int c, int i) {
-  return c * (1 << LM) + (i ^ swz_row<LM>(i) ^ swz_col<LM>(c));
+  return c * dim_len(LM) + (i ^ swz_row<LM>(i) ^ swz_col<LM>(c));
 }
 // placement of a compile-time offset whose bits are disjoint from the base it is combined with
 template <int LM>
 ADMMTV_HD constexpr int soff(int off) {
   return off ^ swz_row<LM>(off);
 }
+// element (base + off) of a butterfly given the placed base: XOR-combine under the swizzle (power-of-two
+// lengths, disjoint bit fields), plain addition otherwise
+template <int LM>
+ADMMTV_DI int scomb(int pb, int off) {
+  if constexpr (is_pow2(dim_len(LM))) return pb ^ (off ^ swz_row<LM>(off));
+  else return pb + off;
+}
 
 template <int LM, int NT, int S, bool INV>
 ADMMTV_DI void dim1_smem_stage(float2* X, int ncols, const float2* __restrict__ tw, int tid) {
-  constexpr int M = 1 << LM;
+  constexpr int M = dim_len(LM);
   using St = Stage<M, S>;
   for_items<St::ITEMS, NT>(
       tid, ncols,
@@ -214,11 +250,11 @@ ADMMTV_DI void dim1_smem_stage(float2* X, int ncols, const float2* __restrict__ 
         float2 a[St::R];
         const int pb = sidx<LM>(c, St::base(wi));
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) a[m] = X[pb ^ soff<LM>(m * St::STRIDE)];
+        for (int m = 0; m < St::R; ++m) a[m] = X[scomb<LM>(pb, m * St::STRIDE)];
         if (INV) stage_inv<M, S>(a, t.p);
         else stage_fwd<M, S>(a, t.p);
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m * St::STRIDE)] = a[m];
+        for (int m = 0; m < St::R; ++m) X[scomb<LM>(pb, m * St::STRIDE)] = a[m];
       });
 }
 
@@ -232,7 +268,7 @@ ADMMTV_DI void dim1_inv_stages_down(float2* X, int ncols, const float2* __restri
 }
 template <int LM, int NT, int S>
 ADMMTV_DI void dim1_fwd_stages_up(float2* X, int ncols, const float2* __restrict__ tw, int tid) {
-  if constexpr (S < plan_stages(1 << LM) - 1) {
+  if constexpr (S < plan_stages(dim_len(LM)) - 1) {
     dim1_smem_stage<LM, NT, S, false>(X, ncols, tw, tid);
     __syncthreads();
     dim1_fwd_stages_up<LM, NT, S + 1>(X, ncols, tw, tid);
@@ -243,7 +279,7 @@ ADMMTV_DI void dim1_fwd_stages_up(float2* X, int ncols, const float2* __restrict
 // in X.  The first pass reads global memory directly (contiguous R-element runs).  Ends synced.
 template <int LM, int NT, class ColPtr>
 ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const float2* __restrict__ tw, int tid) {
-  constexpr int M = 1 << LM, NS = plan_stages(M);
+  constexpr int M = dim_len(LM), NS = plan_stages(M);
   using St = Stage<M, NS - 1>;
   static_assert(St::STRIDE == 1, "last plan stage must be contiguous");
   constexpr int TCMAX = Dim1Cfg<LM>::TC;
@@ -262,7 +298,7 @@ ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const floa
         Dft<St::R, true>::run(a[n]);
         const int pb = sidx<LM>(c, wi * St::R);
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m)] = a[n][m];
+        for (int m = 0; m < St::R; ++m) X[scomb<LM>(pb, m)] = a[n][m];
       }
     }
   } else {
@@ -274,7 +310,7 @@ ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const floa
           Dft<St::R, true>::run(a);
           const int pb = sidx<LM>(c, wi * St::R);
 #pragma unroll
-          for (int m = 0; m < St::R; ++m) X[pb ^ soff<LM>(m)] = a[m];
+          for (int m = 0; m < St::R; ++m) X[scomb<LM>(pb, m)] = a[m];
         });
   }
   __syncthreads();
@@ -285,7 +321,7 @@ ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const floa
 // columns (digit-reversed rows).  The last pass writes global memory directly.
 template <int LM, int NT, class ColPtr>
 ADMMTV_DI void dim1_fft_from_smem(float2* X, int ncols, ColPtr colptr, const float2* __restrict__ tw, int tid) {
-  constexpr int M = 1 << LM, NS = plan_stages(M);
+  constexpr int M = dim_len(LM), NS = plan_stages(M);
   dim1_fwd_stages_up<LM, NT, 0>(X, ncols, tw, tid);
   using St = Stage<M, NS - 1>;
   for_items<St::ITEMS, NT>(
@@ -294,7 +330,7 @@ ADMMTV_DI void dim1_fft_from_smem(float2* X, int ncols, ColPtr colptr, const flo
         float2 a[St::R];
         const int pb = sidx<LM>(c, wi * St::R);
 #pragma unroll
-        for (int m = 0; m < St::R; ++m) a[m] = X[pb ^ soff<LM>(m)];
+        for (int m = 0; m < St::R; ++m) a[m] = X[scomb<LM>(pb, m)];
         Dft<St::R, false>::run(a);
         store_contig<St::R>(colptr(c) + wi * St::R, a);
       });
@@ -611,7 +647,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       if (MODE == 1 || (MODE == 2 && HAS_VPREV)) {
         load_rows_f<RPT>(nsq_g + (size_t)jn * M + i0, n1[cc]);
         load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, n2[cc]);
-        if (MODE == 1) n2[cc][RPT] = nsq_g[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        if (MODE == 1) n2[cc][RPT] = nsq_g[(size_t)j * M + wrapm<M>(i0 + RPT)];
       }
       if (MODE == 2 && HAS_VPREV) {
         load_rows<RPT>(vp1 + (size_t)jn * M + i0, g1[cc]);
@@ -619,7 +655,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       } else if (HAS_VPREV) {
         load_rows<RPT>(vp1 + (size_t)jn * M + i0, g1[cc]);
         load_rows<RPT>(vp2 + (size_t)j * M + i0, g2[cc]);
-        g2[cc][RPT] = vp2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        g2[cc][RPT] = vp2[(size_t)j * M + wrapm<M>(i0 + RPT)];
       }
       if (MODE != 2) load_rows<RPT>(bq + (size_t)j * M + i0, gb[cc]);
     }
@@ -633,7 +669,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
       float2 w2[RPT + 1];
       if (MODE == 2) {
         float2 xc[RPT + 1];  // rows i0-1 .. i0+RPT-1 of column col
-        xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];
+        xc[0] = X[sidx<LM>(col, wrapm<M>(i0 - 1))];
 #pragma unroll
         for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
         if (col < nout) {   // channel 1 of the next own column
@@ -667,10 +703,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
         for (int r = 0; r <= RPT; ++r) w2[r] = shrink_iso(g2[cc][r], SC(n2[cc][r])).w;
       } else {
       float2 xc[RPT + 2];  // rows i0-1 .. i0+RPT of column col
-      xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];
+      xc[0] = X[sidx<LM>(col, wrapm<M>(i0 - 1))];
 #pragma unroll
       for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
-      xc[RPT + 1] = X[sidx<LM>(col, (i0 + RPT) & (M - 1))];
+      xc[RPT + 1] = X[sidx<LM>(col, wrapm<M>(i0 + RPT))];
 
       // channel 1 (dim-2 difference) at column col+1
       {
@@ -728,8 +764,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 
 template <int LN>
 struct Dim2Cfg {
-  static constexpr int N = 1 << LN;
-  static constexpr int TR = LN <= 8 ? 16 : (LN == 9 ? ADMMTV_TR9 : (LN == 10 ? 8 : (LN == 11 ? ADMMTV_TR11 : 4)));
+  static constexpr int N = dim_len(LN);
+  static constexpr int TR = !is_pow2(N) ? (N <= 640 ? 16 : 8)
+                                        : (LN <= 8 ? 16 : (LN == 9 ? ADMMTV_TR9 : (LN == 10 ? 8 : (LN == 11 ? ADMMTV_TR11 : 4))));
   // block size = work items of the widest pass (row pairs x N / largest radix), within [32, 512]
   static constexpr int ITEMS_MAX = (TR / 2) * (N / plan_radix(N, 0));
   static constexpr int NT_AUTO = ITEMS_MAX < 32 ? 32 : (ITEMS_MAX > ADMMTV_NT2_MAX ? ADMMTV_NT2_MAX : ITEMS_MAX);
@@ -769,7 +806,7 @@ ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int 
 }
 template <int LN, int S>
 ADMMTV_DI void dim2_fwd_mid(float2* tile, const float2* __restrict__ tw, int tid) {
-  if constexpr (S < plan_stages(1 << LN) - 1) {
+  if constexpr (S < plan_stages(dim_len(LN)) - 1) {
     dim2_smem_stage<LN, S, false>(tile, tw, tid);
     __syncthreads();
     dim2_fwd_mid<LN, S + 1>(tile, tw, tid);

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
 
   for (int c = 1; c <= nout; c += CHUNK) {
     // (a) anisotropic: every global load of the chunk is issued before any of them is consumed
-    constexpr bool HOIST = ADMMTV_BWD_HOIST && MODE == 0;
+    constexpr bool HOIST = ADMMTV_BWD_HOIST && MODE == 0 && RPT * CHUNK <= 4;  // larger tiles would spill
     float2 hv1[HOIST ? CHUNK : 1][RPT], he1[HOIST ? CHUNK : 1][RPT], hv2[HOIST ? CHUNK : 1][RPT + 1],
         he2[HOIST ? CHUNK : 1][RPT + 1], hbb[HOIST ? CHUNK : 1][RPT];
     if (HOIST) {
@@ -176,11 +176,11 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
         const int j = jcol(c + cc), jn = jcol(c + cc + 1);
         load_rows<RPT>(v1 + (size_t)jn * M + i0, hv1[cc]);
         load_rows<RPT>(v2 + (size_t)j * M + i0, hv2[cc]);
-        hv2[cc][RPT] = v2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+        hv2[cc][RPT] = v2[(size_t)j * M + wrapm<M>(i0 + RPT)];
         if (HAS_VBAR) {
           load_rows<RPT>(e1 + (size_t)jn * M + i0, he1[cc]);
           load_rows<RPT>(e2 + (size_t)j * M + i0, he2[cc]);
-          he2[cc][RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+          he2[cc][RPT] = e2[(size_t)j * M + wrapm<M>(i0 + RPT)];
         }
         if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, hbb[cc]);
       }
@@ -191,10 +191,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
       const int col = c + cc;
       const int j = jcol(col), jn = jcol(col + 1);
       float2 xc[RPT + 2];  // rbar rows i0-1 .. i0+RPT of column col
-      xc[0] = X[sidx<LM>(col, (i0 - 1) & (M - 1))];
+      xc[0] = X[sidx<LM>(col, wrapm<M>(i0 - 1))];
 #pragma unroll
       for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
-      xc[RPT + 1] = X[sidx<LM>(col, (i0 + RPT) & (M - 1))];
+      xc[RPT + 1] = X[sidx<LM>(col, wrapm<M>(i0 + RPT))];
 
       if (MODE == 2) {
         float2 bb[RPT], vv[RPT], ee[RPT], v2v[RPT], e2v[RPT];
@@ -277,16 +277,16 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
           }
         } else {
           load_rows<RPT>(v2 + (size_t)j * M + i0, vv);
-          vv[RPT] = v2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+          vv[RPT] = v2[(size_t)j * M + wrapm<M>(i0 + RPT)];
           if (HAS_VBAR) {
             load_rows<RPT>(e2 + (size_t)j * M + i0, ee);
-            ee[RPT] = e2[(size_t)j * M + ((i0 + RPT) & (M - 1))];
+            ee[RPT] = e2[(size_t)j * M + wrapm<M>(i0 + RPT)];
           }
         }
         if (MODE == 1) {
 #pragma unroll
           for (int r = 0; r < RPT; ++r) ss[r] = PIX(sc_g, (size_t)j * M + i0 + r, true);   // own pixels: counted once
-          ss[RPT] = PIX(sc_g, (size_t)j * M + ((i0 + RPT) & (M - 1)), false);
+          ss[RPT] = PIX(sc_g, (size_t)j * M + wrapm<M>(i0 + RPT), false);
         }
 #pragma unroll
         for (int r = 0; r <= RPT; ++r) {

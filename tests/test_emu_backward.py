@@ -69,3 +69,10 @@ def test_emu_backward_iso(be, M, N, P, B, kh, kw, K, iso_flag):
     y, h, _ = make_case(M, N, P, B, kh, kw, 50 + M + K)
     xbar = torch.from_numpy(np.random.default_rng(K).standard_normal((M, N, P, B)))
     check_backward(be, y, h, 0.05, 0.3, True, K, xbar, flags=1 | iso_flag, tol=1e-5, tol_scalar=1e-4, tol_e2e=1e-4)
+
+
+@pytest.mark.parametrize("iso", [False, True])
+def test_emu_backward_mixed_radix(be, iso):
+    y, h, _ = make_case(96, 160, 3, 1, 5, 4, 7)
+    xbar = torch.from_numpy(np.random.default_rng(1).standard_normal((96, 160, 3, 1)))
+    check_backward(be, y, h, 0.05, 0.3, iso, 3, xbar, tol=1e-5, tol_scalar=2e-4)

@@ -85,3 +85,12 @@ def test_emu_golden_forward_iso(emu):
         r = E.forward(emu, d["y"], float(d["lam"]), float(d["rho"]), h, True, int(d["iters"]), act=str(d["act"]),
                       bias=float(d["bias"]) if "bias" in d else None, creg=float(d["creg"]))
         assert rel_l2(torch.from_numpy(np.ascontiguousarray(r["x"])), torch.from_numpy(d["x"])) < TOL, f
+
+
+@pytest.mark.parametrize("M,N", [(96, 32), (32, 160), (192, 96), (320, 32), (32, 384), (480, 32), (32, 640), (768, 32)])
+def test_emu_mixed_radix_lengths(emu, M, N):
+    """3- and 5-smooth lengths (radix-3 / radix-5 first passes): 96, 160, 192, 320, 384, 480, 640, 768, ..."""
+    import harness
+    from parity import check_forward
+    y, h, _ = make_case(M, N, 1, 2, 3, 3, 50 + M + N)
+    check_forward(harness.EmuBackend(emu), y, h, 0.05, 0.3, False, 3)

@@ -184,3 +184,11 @@ def test_grouped_backward_per_image_psf(be):
         assert rel_l2(T(g["ybar"][..., b:b + 1]), T(g1["ybar"])) < 2e-6
         assert rel_l2(T(g["hbar"][:, :, b]), T(g1["hbar"])) < 2e-5
         assert close(float(g["lambar"][b]), float(g1["lambar"][0]), 1e-4) and close(float(g["rhobar"][b]), float(g1["rhobar"][0]), 1e-4)
+
+
+@pytest.mark.parametrize("M,N,iso", [(96, 160, False), (480, 640, False), (384, 192, True), (960, 96, False)])
+def test_backward_mixed_radix(be, M, N, iso):
+    y, h, g = make_case(M, N, 3, 1, 7, 7, 800 + M + N)
+    xbar = 2.0 * (y - g) / y.numel() * 1e3
+    r = check_backward(be, y, h, 0.0041, 0.021, iso, 6, xbar, tol=1e-5, tol_scalar=2e-4)
+    print(r)

@@ -261,3 +261,22 @@ def test_fft_kernels_against_cufft_closed_form():
         C = 1.0 / (Sig.abs() ** 2 + 0.05 * L)
         ref = torch.fft.ifft2(C * K.conj() * torch.fft.fft2(yd)).real
         assert rel_l2(x.cpu(), ref.cpu()) < 2e-6, (B, P, N, M)
+
+
+@pytest.mark.parametrize("L", [96, 160, 192, 320, 384, 480, 640, 768, 960, 1280, 1536, 1920])
+def test_mixed_radix_lengths_both_dims(L):
+    """Non-power-of-two lengths (the reference's FFTW path takes any size; here 3- and 5-smooth ones)."""
+    for (M, N) in ((L, 64), (96, L)):
+        y, h, _ = make_case(M, N, 2, 1, 5, 5, L)
+        x = run_gpu(y, h, 0.02, 0.1, False, 6)
+        xo = oracle(y, h, 0.02, 0.1, False, 6, fast=True)
+        assert rel_l2(x, xo) < TOL, (M, N)
+
+
+def test_video_frame_sizes():
+    """640x480 and 1280x960 RGB frames, 15x15 PSF, 30 iterations."""
+    for (M, N) in ((640, 480), (1280, 960)):
+        y, h, _ = make_case(M, N, 3, 1, 15, 15, M + N)
+        x = run_gpu(y, h, 0.0041, 0.021, False, 30)
+        xo = oracle(y, h, 0.0041, 0.021, False, 30, fast=True)
+        assert rel_l2(x, xo) < TOL, (M, N)

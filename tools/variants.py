@@ -56,6 +56,11 @@ VARIANTS = {
     "qpb1": ("ADMMTV_D2_ACC_QPB=1",),
     "qpb2": ("ADMMTV_D2_ACC_QPB=2",),
     "qpb8": ("ADMMTV_D2_ACC_QPB=8",),
+    "d2n512": ("ADMMTV_NT2=512",),
+    "d2n512mb2": ("ADMMTV_NT2=512", "ADMMTV_MINB2=2"),
+    "d2n128": ("ADMMTV_NT2=128",),
+    "d2n128mb6": ("ADMMTV_NT2=128", "ADMMTV_MINB2=6"),
+    "d2mb3": ("ADMMTV_MINB2=3",),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
