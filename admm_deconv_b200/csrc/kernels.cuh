@@ -172,6 +172,7 @@ struct Dim1Cfg {
   static constexpr int MINB = LM == 9 ? ADMMTV_MINB9 : 1;
   static constexpr int RPT = M / NT;                  // rows per thread in the stencil sweep
   static constexpr int CHUNK = LM == 9 ? ADMMTV_CHUNK9 : (LM == 8 ? ADMMTV_CHUNK8 : (RPT >= 8 ? 1 : 8 / RPT));  // columns between barriers
+  static constexpr int CHUNKB = RPT >= 4 ? 1 : 4 / RPT;  // backward sweep: RPT * CHUNKB <= 4 keeps its hoisted loads in registers
   // tile columns including the 2 halo columns
   static constexpr int TC = !POW2 ? dim1_tc_generic(M)
                                   : (LM <= 7 ? 34 : (LM == 8 ? ADMMTV_TC8 : (LM == 9 ? ADMMTV_TC9 : (LM == 11 ? ADMMTV_TC11 : 6))));

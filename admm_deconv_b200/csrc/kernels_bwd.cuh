@@ -74,7 +74,8 @@ ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float2 s
 template <int LM, bool HAS_VBAR, int MODE = 0>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : 1) k_dim1_bwd(Dim1BwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
-  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
+  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNKB;
+  static_assert(CO % CHUNK == 0, "chunking must divide the tile");
   ADMMTV_DYN_SMEM(float2, X);
   const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
   const int j0 = blockIdx.x * CO;
