@@ -58,7 +58,8 @@ enum {
   ADMMTV_OK = 0,
   ADMMTV_ERR_NULL = -1,
   ADMMTV_ERR_SHAPE = -2,        /* non-positive dims, kernel larger than image, ... */
-  ADMMTV_ERR_UNSUPPORTED = -3,  /* M or N not a supported FFT length (power of two, 16..4096) */
+  ADMMTV_ERR_UNSUPPORTED = -3,  /* M or N not a supported FFT length: 32, 64, ..., 4096 or
+                                 * 96, 160, 192, 320, 384, 480, 640, 768, 960, 1280, 1536, 1920 */
   ADMMTV_ERR_ITERS = -4,
   ADMMTV_ERR_ENUM = -5,
   ADMMTV_ERR_ALIGN = -6,        /* workspace / checkpoint not 256-byte aligned */
