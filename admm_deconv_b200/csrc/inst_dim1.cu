@@ -37,7 +37,7 @@ static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, con
 
 constexpr int LM = ADMMTV_INST;
 using Cfg = Dim1Cfg<LM>;
-static dim3 dim1_grid(const Geom& g) { return dim3((unsigned)((g.N + Cfg::CO - 1) / Cfg::CO), (unsigned)g.Q); }
+static dim3 dim1_grid(const Geom& g) { return dim3((unsigned)((g.N + Cfg::CO - 1) / Cfg::CO) * (unsigned)g.Q); }
 
 template <>
 int Dim1Launch<LM>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {

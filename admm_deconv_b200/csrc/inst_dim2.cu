@@ -58,6 +58,7 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
   // the G-accumulating variant gives each block a few pairs so the shared-memory partial sums are flushed
   // with one global atomic per element per ADMMTV_D2_ACC_QPB pairs
   if (variant == D2_C_ACCG && gy == g.Q) gy = (g.Q + ADMMTV_D2_ACC_QPB - 1) / ADMMTV_D2_ACC_QPB;
+  if (gy > 65535) gy = 65535;  // blocks loop over pairs with stride gridDim.y
   const dim3 grid((unsigned)row_tiles, (unsigned)gy);
   switch (variant) {
     case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);

@@ -349,8 +349,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
   ADMMTV_DYN_SMEM(float2, X);
-  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
-  const int j0 = blockIdx.x * CO;
+  // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
+  const int tid = threadIdx.x, N = A.N, ntile = (A.N + CO - 1) / CO;
+  const int q = blockIdx.x / ntile;
+  const int j0 = (blockIdx.x % ntile) * CO;
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   // MODE 1 reads the layer OUTPUT's cotangent, so it uses the output plane map
@@ -415,8 +417,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
   ADMMTV_DYN_SMEM(float2, X);
-  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
-  const int j0 = blockIdx.x * CO;
+  // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
+  const int tid = threadIdx.x, N = A.N, ntile = (A.N + CO - 1) / CO;
+  const int q = blockIdx.x / ntile;
+  const int j0 = (blockIdx.x % ntile) * CO;
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   const float2* sq = A.spec + (size_t)q * plane;
@@ -549,8 +553,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
   static_assert(CO % CHUNK == 0, "chunking must divide the tile");
   ADMMTV_DYN_SMEM(float2, X);
-  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
-  const int j0 = blockIdx.x * CO;
+  // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
+  const int tid = threadIdx.x, N = A.N, ntile = (A.N + CO - 1) / CO;
+  const int q = blockIdx.x / ntile;
+  const int j0 = (blockIdx.x % ntile) * CO;
   const int nout = min(CO, N - j0);  // N and CO are powers of two: nout % CHUNK == 0
   const size_t plane = (size_t)N * M;
   const float2* sin_q = A.spec_in + (size_t)q * plane;
@@ -572,9 +578,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     if (MODE != 2 && tid == 64 % NT) l2_prefetch_bulk(A.bpk + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
     // the spectrum tile of the block that will be scheduled onto this SM slot when a resident block retires
     if (MODE == 0 && ADMMTV_PF_NEXT > 0 && tid == 96 % NT) {
-      const long nid = (long)blockIdx.y * gridDim.x + blockIdx.x + ADMMTV_PF_NEXT;
-      if (nid < (long)gridDim.x * gridDim.y) {
-        const int nq = (int)(nid / gridDim.x), nj0 = (int)(nid % gridDim.x) * CO;
+      const long nid = (long)blockIdx.x + ADMMTV_PF_NEXT;
+      if (nid < (long)gridDim.x) {
+        const int nq = (int)(nid / ntile), nj0 = (int)(nid % ntile) * CO;
         const int ncol = min(CO, N - nj0);
         l2_prefetch_bulk(A.spec_in + (size_t)nq * plane + (size_t)nj0 * M, (unsigned)ncol * colb);
       }

@@ -77,8 +77,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNKB;
   static_assert(CO % CHUNK == 0, "chunking must divide the tile");
   ADMMTV_DYN_SMEM(float2, X);
-  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
-  const int j0 = blockIdx.x * CO;
+  // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
+  const int tid = threadIdx.x, N = A.N, ntile = (A.N + CO - 1) / CO;
+  const int q = blockIdx.x / ntile;
+  const int j0 = (blockIdx.x % ntile) * CO;
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   const float2* sin_q = A.spec_in + (size_t)q * plane;
@@ -333,8 +335,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
   ADMMTV_DYN_SMEM(float2, X);
-  const int tid = threadIdx.x, N = A.N, q = blockIdx.y;
-  const int j0 = blockIdx.x * CO;
+  // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
+  const int tid = threadIdx.x, N = A.N, ntile = (A.N + CO - 1) / CO;
+  const int q = blockIdx.x / ntile;
+  const int j0 = (blockIdx.x % ntile) * CO;
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   const float2* sin_q = A.spec_in + (size_t)q * plane;

@@ -44,6 +44,8 @@ WORKLOADS = {
     "denoiser5": dict(B=32, P=3, N=256, M=256, k=0, iters=50, mode="grouped", groups=5, iso=True,
                       desc="net_build.jl:113-128 get_denoiser: 5 parallel ADMMDeconvF2((),50,rho_i,relu1; iso) branches on the "
                            "same 32 x 256x256 RGB input, channel-concatenated, one grouped call"),
+    "vga": dict(B=64, P=3, N=480, M=640, k=15, iters=50, mode="fwd",
+                desc="64 x 640x480 RGB frames (mixed-radix lengths 640 = 5*16*8, 480 = 3*5*8*4), motion PSF 15x15, 50 iterations"),
     "tiny": dict(B=2, P=3, N=64, M=64, k=7, iters=10, mode="fwd", desc="tiny debug workload"),
 }
 FWD_BYTES = 40.0   # algorithmic bytes / plane-pixel-iteration, forward  

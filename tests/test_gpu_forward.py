@@ -280,3 +280,19 @@ def test_video_frame_sizes():
         x = run_gpu(y, h, 0.0041, 0.021, False, 30)
         xo = oracle(y, h, 0.0041, 0.021, False, 30, fast=True)
         assert rel_l2(x, xo) < TOL, (M, N)
+
+
+def test_huge_plane_count_exceeds_grid_y_limit():
+    """140001 independent 32x32 planes (70001 pairs > the 65535 gridDim.y limit; odd count -> padded last pair)."""
+    d0 = dev()
+    torch.manual_seed(9)
+    B = 140001
+    y = torch.rand(B, 1, 32, 32, device=d0)
+    h = A.from_julia(O.gaussian_psf(5, 1.0).float()).to(d0)
+    lam = torch.tensor([0.02], device=d0); rho = torch.tensor([0.1], device=d0)
+    x = A.tvd_fft(y, lam, rho, h, False, 3)
+    torch.cuda.synchronize()
+    for sl in (slice(0, 3), slice(70000, 70003), slice(B - 3, B)):
+        yj = A.to_julia(y[sl].cpu()).double()
+        xo = O.tvd_fft_fast(yj, lam.cpu().double(), rho.cpu().double(), O.gaussian_psf(5, 1.0).float().double(), False, 3)
+        assert rel_l2(A.to_julia(x[sl].cpu()), xo) < TOL
