@@ -296,3 +296,24 @@ def test_huge_plane_count_exceeds_grid_y_limit():
         yj = A.to_julia(y[sl].cpu()).double()
         xo = O.tvd_fft_fast(yj, lam.cpu().double(), rho.cpu().double(), O.gaussian_psf(5, 1.0).float().double(), False, 3)
         assert rel_l2(A.to_julia(x[sl].cpu()), xo) < TOL
+
+
+def test_full_cfg2_size_shift_equivariance_and_fixed_point():
+    """Size-independent properties at the FULL BASELINE configs[1] size (64 x 512x512 RGB, 15x15 PSF): with circular
+    boundaries the solver commutes with circular shifts of the input, and a constant image is a fixed point when
+    the PSF sums to one."""
+    d0 = dev()
+    torch.manual_seed(11)
+    B, P, N, M, K = 64, 3, 512, 512, 20
+    h = A.from_julia(O.motion_psf(15, 0.7, 11.0).float()).to(d0)
+    lam = torch.tensor([0.0041], device=d0); rho = torch.tensor([0.021], device=d0)
+    y = torch.rand(B, P, N, M, device=d0)
+    x = A.tvd_fft(y, lam, rho, h, False, K)
+    xs = A.tvd_fft(torch.roll(y, shifts=(37, -5), dims=(2, 3)).contiguous(), lam, rho, h, False, K)
+    ref = torch.roll(x, shifts=(37, -5), dims=(2, 3))
+    err = float((xs - ref).norm() / ref.norm())
+    assert err < 1e-5, err
+    del xs, ref, x
+    c = torch.full((B, P, N, M), 0.37, device=d0)
+    xc = A.tvd_fft(c, lam, rho, h, False, K)
+    assert float((xc - 0.37).abs().max()) < 2e-5
