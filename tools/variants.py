@@ -61,6 +61,10 @@ VARIANTS = {
     "d2n128": ("ADMMTV_NT2=128",),
     "d2n128mb6": ("ADMMTV_NT2=128", "ADMMTV_MINB2=6"),
     "d2mb3": ("ADMMTV_MINB2=3",),
+    "n512_t18_c4": ("ADMMTV_NT9=512", "ADMMTV_TC9=18", "ADMMTV_CHUNK9=4", "ADMMTV_MINB9=2", "ADMMTV_MINB9B=1"),
+    "n512_t10_c4": ("ADMMTV_NT9=512", "ADMMTV_TC9=10", "ADMMTV_CHUNK9=4", "ADMMTV_MINB9=2", "ADMMTV_MINB9B=1"),
+    "n512_t10_c8": ("ADMMTV_NT9=512", "ADMMTV_TC9=10", "ADMMTV_CHUNK9=8", "ADMMTV_MINB9=2", "ADMMTV_MINB9B=1"),
+    "n512_t10_c2": ("ADMMTV_NT9=512", "ADMMTV_TC9=10", "ADMMTV_CHUNK9=2", "ADMMTV_MINB9=3", "ADMMTV_MINB9B=1"),
     "t10": ("ADMMTV_TC9=10",),
     "t6": ("ADMMTV_TC9=6",),
     "t10_n128": ("ADMMTV_TC9=10", "ADMMTV_NT9=128"),
