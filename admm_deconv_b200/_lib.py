@@ -35,6 +35,15 @@ SYMBOLS = (
     "admmtv_forward_launches",
     "admmtv_backward_launches",
 )
+# every symbol include/admmtv_loss.h declares
+LOSS_SYMBOLS = (
+    "admmtv_gmsd_workspace_bytes",
+    "admmtv_gmsd_forward",
+    "admmtv_gmsd_backward",
+    "admmtv_ssim_workspace_bytes",
+    "admmtv_ssim_forward",
+    "admmtv_ssim_backward",
+)
 
 
 class Desc(C.Structure):
@@ -81,7 +90,14 @@ class AdmmTvLib:
         L.admmtv_ckpt_layout.argtypes = [C.POINTER(Desc), C.POINTER(sz)]
         L.admmtv_forward_launches.argtypes = [C.POINTER(Desc), C.c_int]
         L.admmtv_backward_launches.argtypes = [C.POINTER(Desc)]
-        for name in SYMBOLS:
+        i, f = C.c_int, C.c_float
+        L.admmtv_gmsd_workspace_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
+        L.admmtv_gmsd_forward.argtypes = [i, i, i, i, i, vp, vp, f, f, vp, vp, vp]
+        L.admmtv_gmsd_backward.argtypes = [i, i, i, i, i, vp, vp, f, f, vp, vp, vp, vp]
+        L.admmtv_ssim_workspace_bytes.argtypes = [i, i, i, i, i, i, C.POINTER(sz)]
+        L.admmtv_ssim_forward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, f, i, vp, vp, i, vp]
+        L.admmtv_ssim_backward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, i, vp, vp, vp, vp]
+        for name in SYMBOLS + LOSS_SYMBOLS:
             getattr(L, name)  # AttributeError if a declared symbol is not exported
 
     def strerror(self, code: int) -> str:
@@ -134,6 +150,39 @@ class AdmmTvLib:
 
     def backward_launches(self, d: Desc) -> int:
         return self.lib.admmtv_backward_launches(C.byref(d))
+
+    # ---- include/admmtv_loss.h ----------------------------------------------------------------
+    @staticmethod
+    def _taps(taps):
+        if taps is None:
+            return None, 0
+        arr = (C.c_float * len(taps))(*[float(t) for t in taps])
+        return arr, len(taps)
+
+    def gmsd_workspace_bytes(self, M, N, Cc, B) -> int:
+        n = C.c_size_t()
+        self._raise(self.lib.admmtv_gmsd_workspace_bytes(M, N, Cc, B, C.byref(n)))
+        return n.value
+
+    def gmsd_forward(self, M, N, Cc, B, device, x, y, t, alpha, loss_out, ws, stream=0):
+        self._raise(self.lib.admmtv_gmsd_forward(M, N, Cc, B, device, x, y, t, alpha, loss_out, ws, stream))
+
+    def gmsd_backward(self, M, N, Cc, B, device, x, y, t, alpha, lossbar, ws, xbar, stream=0):
+        self._raise(self.lib.admmtv_gmsd_backward(M, N, Cc, B, device, x, y, t, alpha, lossbar, ws, xbar, stream))
+
+    def ssim_workspace_bytes(self, M, N, Cc, B, taps=None, with_grad=True) -> int:
+        n = C.c_size_t()
+        self._raise(self.lib.admmtv_ssim_workspace_bytes(M, N, Cc, B, 0 if taps is None else len(taps), int(with_grad), C.byref(n)))
+        return n.value
+
+    def ssim_forward(self, M, N, Cc, B, device, x, y, taps, peakval, as_loss, out, ws, with_grad, stream=0):
+        arr, L = self._taps(taps)
+        self._raise(self.lib.admmtv_ssim_forward(M, N, Cc, B, device, x, y, arr, L, peakval, int(as_loss), out, ws,
+                                                 int(with_grad), stream))
+
+    def ssim_backward(self, M, N, Cc, B, device, x, y, taps, as_loss, outbar, ws, xbar, stream=0):
+        arr, L = self._taps(taps)
+        self._raise(self.lib.admmtv_ssim_backward(M, N, Cc, B, device, x, y, arr, L, int(as_loss), outbar, ws, xbar, stream))
 
 
 _LIB: Optional[AdmmTvLib] = None

@@ -1,0 +1,179 @@
+// loss_api.cu -- the C ABI of include/admmtv_loss.h: argument checks, workspace carving, launches.
+#include "../../include/admmtv.h"
+#include "../../include/admmtv_loss.h"
+#include "loss_kernels.cuh"
+
+namespace admmtv {
+namespace {
+
+inline size_t up256(size_t n) { return (n + 255) & ~size_t(255); }
+
+struct DevGuard {
+  int prev;
+  bool ok;
+  explicit DevGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int check_shape(int M, int N, int C, int B) {
+  if (M <= 0 || N <= 0 || C <= 0 || B <= 0) return ADMMTV_ERR_SHAPE;
+  return ADMMTV_OK;
+}
+
+// sigma = 1.5, length 11 (src/metrics/ssim.jl:6-17)
+const float kSsimGauss[11] = {0.00102838008447911f, 0.007598758135239185f, 0.03600077212843083f, 0.10936068950970002f,
+                              0.2130055377112537f,  0.26601172486179436f,  0.2130055377112537f,  0.10936068950970002f,
+                              0.03600077212843083f, 0.007598758135239185f, 0.00102838008447911f};
+
+int ssim_args(SsimArgs& a, int M, int N, int C, int B, const float* taps, int L) {
+  int rc = check_shape(M, N, C, B);
+  if (rc) return rc;
+  if (!taps) {
+    taps = kSsimGauss;
+    L = 11;
+  }
+  if (L < 1 || L > SS_LMAX) return ADMMTV_ERR_UNSUPPORTED;
+  if (L > M || L > N) return ADMMTV_ERR_SHAPE;  // crop=true: the valid-size map would be empty
+  a.M = M; a.N = N; a.C = C; a.B = B; a.L = L;
+  a.Mo = M - L + 1; a.No = N - L + 1;
+  for (int k = 0; k < SS_LMAX; ++k) a.f[k] = k < L ? taps[L - 1 - k] : 0.f;
+  return ADMMTV_OK;
+}
+
+}  // namespace
+}  // namespace admmtv
+
+using namespace admmtv;
+
+extern "C" {
+
+int admmtv_gmsd_workspace_bytes(int M, int N, int C, int B, size_t* bytes) {
+  int rc = check_shape(M, N, C, B);
+  if (rc) return rc;
+  if (bytes) *bytes = 2 * up256(2 * (size_t)B * sizeof(double));
+  return ADMMTV_OK;
+}
+
+int admmtv_gmsd_forward(int M, int N, int C, int B, int device, const float* x, const float* y, float t, float alpha,
+                        float* loss_out, void* workspace, void* stream) {
+  int rc = check_shape(M, N, C, B);
+  if (rc) return rc;
+  if (!x || !y || !loss_out || !workspace) return ADMMTV_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return ADMMTV_ERR_ALIGN;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GmsdArgs a{};
+  a.x = x; a.y = y; a.M = M; a.N = N; a.C = C; a.B = B; a.t = t; a.alpha = alpha;
+  a.tiles_i = (M + GM_TH - 1) / GM_TH; a.tiles_j = (N + GM_TW - 1) / GM_TW;
+  a.acc = reinterpret_cast<double*>(workspace);
+  a.stats = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + up256(2 * (size_t)B * sizeof(double)));
+  a.out = loss_out;
+  cudaError_t e = cudaMemsetAsync(a.acc, 0, 2 * (size_t)B * sizeof(double), st);
+  if (e != cudaSuccess) return (int)e;
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_gmsd_fwd, dim3((unsigned)nblk), dim3(GM_NT), 0, st, a);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  ADMMTV_LAUNCH(k_gmsd_finalize, dim3(1), dim3(128), 0, st, a);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  return ADMMTV_OK;
+}
+
+int admmtv_gmsd_backward(int M, int N, int C, int B, int device, const float* x, const float* y, float t, float alpha,
+                         const float* lossbar, const void* workspace, float* xbar, void* stream) {
+  int rc = check_shape(M, N, C, B);
+  if (rc) return rc;
+  if (!x || !y || !lossbar || !workspace || !xbar) return ADMMTV_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return ADMMTV_ERR_ALIGN;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GmsdArgs a{};
+  a.x = x; a.y = y; a.M = M; a.N = N; a.C = C; a.B = B; a.t = t; a.alpha = alpha;
+  a.tiles_i = (M + GM_TH - 1) / GM_TH; a.tiles_j = (N + GM_TW - 1) / GM_TW;
+  unsigned char* ws = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(workspace));
+  a.acc = reinterpret_cast<double*>(ws);
+  a.stats = reinterpret_cast<double*>(ws + up256(2 * (size_t)B * sizeof(double)));
+  a.lossbar = lossbar;
+  a.out = xbar;
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_gmsd_bwd, dim3((unsigned)nblk), dim3(GM_NT), 0, st, a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADMMTV_OK : (int)e;
+}
+
+int admmtv_ssim_workspace_bytes(int M, int N, int C, int B, int L, int with_grad, size_t* bytes) {
+  SsimArgs a{};
+  const float dummy[SS_LMAX] = {0};
+  int rc = ssim_args(a, M, N, C, B, L > 0 ? dummy : nullptr, L);
+  if (rc) return rc;
+  size_t n = up256(sizeof(double));
+  if (with_grad) n += up256(3 * (size_t)a.Mo * a.No * C * B * sizeof(float));
+  if (bytes) *bytes = n;
+  return ADMMTV_OK;
+}
+
+int admmtv_ssim_forward(int M, int N, int C, int B, int device, const float* x, const float* y, const float* taps, int L,
+                        float peakval, int as_loss, float* out, void* workspace, int with_grad, void* stream) {
+  SsimArgs a{};
+  int rc = ssim_args(a, M, N, C, B, taps, L);
+  if (rc) return rc;
+  if (!x || !y || !out || !workspace) return ADMMTV_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return ADMMTV_ERR_ALIGN;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  a.x = x; a.y = y;
+  a.C1 = (peakval * 0.01f) * (peakval * 0.01f);  // ssim.jl:101-102
+  a.C2 = (peakval * 0.03f) * (peakval * 0.03f);
+  a.tiles_i = (a.Mo + SS_T - 1) / SS_T; a.tiles_j = (a.No + SS_T - 1) / SS_T;
+  a.acc = reinterpret_cast<double*>(workspace);
+  a.maps = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + up256(sizeof(double)));
+  a.with_grad = with_grad ? 1 : 0;
+  a.as_loss = as_loss ? 1 : 0;
+  a.out = out;
+  cudaError_t e = cudaMemsetAsync(a.acc, 0, sizeof(double), st);
+  if (e != cudaSuccess) return (int)e;
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_ssim_fwd, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  ADMMTV_LAUNCH(k_ssim_finalize, dim3(1), dim3(1), 0, st, a);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  return ADMMTV_OK;
+}
+
+int admmtv_ssim_backward(int M, int N, int C, int B, int device, const float* x, const float* y, const float* taps, int L,
+                         int as_loss, const float* outbar, const void* workspace, float* xbar, void* stream) {
+  SsimArgs a{};
+  int rc = ssim_args(a, M, N, C, B, taps, L);
+  if (rc) return rc;
+  if (!x || !y || !outbar || !workspace || !xbar) return ADMMTV_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return ADMMTV_ERR_ALIGN;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  a.x = x; a.y = y;
+  a.tiles_i = (M + SS_T - 1) / SS_T; a.tiles_j = (N + SS_T - 1) / SS_T;
+  unsigned char* ws = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(workspace));
+  a.acc = reinterpret_cast<double*>(ws);
+  a.maps = reinterpret_cast<float*>(ws + up256(sizeof(double)));
+  a.with_grad = 1;
+  a.as_loss = as_loss ? 1 : 0;
+  a.outbar = outbar;
+  a.out = xbar;
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_ssim_bwd, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADMMTV_OK : (int)e;
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+// loss_kernels.cuh -- GMSD and SSIM, forward and hand-written backward.
+//
+// Replaces the cuDNN grouped convolutions + CUDA.jl broadcasts + Zygote tape of
+//   /root/reference/src/metrics/gmsd.jl:13-27 (+ iqa_utils.jl:24-55) and src/metrics/ssim.jl:84-124
+// by one tiled kernel per direction: the image tile (plus stencil halo) is staged in shared memory once,
+// every intermediate map lives in shared memory or registers, and the only HBM traffic is x, y in and
+// xbar out (GMSD: 8 B/pixel forward, 12 B/pixel backward; SSIM additionally keeps three derivative maps,
+// 12 B/output pixel, between forward and backward instead of redoing five 11x11 windows).
+// Arrays are Julia (M,N,C,B) column-major: plane s = c + C*b, element (i,j) at i + M*j.
+#pragma once
+
+#include "compat.cuh"
+#include "launch_macros.cuh"
+#include "reduce.cuh"
+
+namespace admmtv {
+
+ADMMTV_DI int wrapi(int i, int n) {
+  i %= n;
+  return i < 0 ? i + n : i;
+}
+
+// ------------------------------------------------------------------------------------------
+// GMSD
+// ------------------------------------------------------------------------------------------
+constexpr int GM_TH = 64, GM_TW = 32, GM_NT = 256;
+
+struct GmsdArgs {
+  const float* x;
+  const float* y;
+  int M, N, C, B;
+  int tiles_i, tiles_j;
+  float t, alpha;
+  double* acc;           // [2B]  sum (g-1), sum (g-1)^2 per image
+  double* stats;         // [2B]  mean g, sqrt(score) per image
+  const float* lossbar;  // backward
+  float* out;            // forward: loss ; backward: xbar
+};
+
+// Sobel/8 gradients (iqa_utils.jl:15-20,46-47; NNlib conv = true convolution of the circularly padded
+// image) at interior position (li, lj) of a column-major shared tile with leading dimension LD:
+//   gx[i,j] = sum_dj w(dj) (x[i+1,j+dj] - x[i-1,j+dj]),  gy[i,j] = sum_di w(di) (x[i+di,j+1] - x[i+di,j-1]),  w = (1,2,1)/8
+template <int LD>
+ADMMTV_DI void sobel_at(const float* T, int li, int lj, float& gx, float& gy) {
+  const float* c0 = T + (lj - 1) * LD + li;
+  const float* c1 = c0 + LD;
+  const float* c2 = c1 + LD;
+  gx = ((c0[1] - c0[-1]) + 2.f * (c1[1] - c1[-1]) + (c2[1] - c2[-1])) * 0.125f;
+  gy = ((c2[-1] - c0[-1]) + 2.f * (c2[0] - c0[0]) + (c2[1] - c0[1])) * 0.125f;
+}
+ADMMTV_DI float gradmag(float gx, float gy) { return sqrtf(gx * gx + gy * gy + 1e-16f); }  // iqa_utils.jl:53-55
+
+template <int HALO, int LD>
+ADMMTV_DI void gm_load_tile(const float* __restrict__ p, float* T, int i0, int j0, int M, int N, int tid) {
+  for (int e = tid; e < LD * (GM_TW + 2 * HALO); e += GM_NT) {
+    const int li = e % LD, lj = e / LD;
+    T[e] = p[(size_t)wrapi(j0 - HALO + lj, N) * M + wrapi(i0 - HALO + li, M)];  // pad_circular, iqa_utils.jl:46
+  }
+}
+
+__global__ void __launch_bounds__(GM_NT) k_gmsd_fwd(GmsdArgs A) {
+  constexpr int LD = GM_TH + 2;
+  __shared__ float xs[LD * (GM_TW + 2)], ys[LD * (GM_TW + 2)];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * GM_TH, j0 = (tl / A.tiles_i) * GM_TW;
+  const size_t plane = (size_t)A.M * A.N;
+  gm_load_tile<1, LD>(A.x + (size_t)s * plane, xs, i0, j0, A.M, A.N, tid);
+  gm_load_tile<1, LD>(A.y + (size_t)s * plane, ys, i0, j0, A.M, A.N, tid);
+  __syncthreads();
+  double s1 = 0.0, s2 = 0.0;
+  for (int e = tid; e < GM_TH * GM_TW; e += GM_NT) {
+    const int li = e % GM_TH, lj = e / GM_TH;
+    if (i0 + li < A.M && j0 + lj < A.N) {
+      float gx, gy;
+      sobel_at<LD>(xs, li + 1, lj + 1, gx, gy);
+      const float mx = gradmag(gx, gy);
+      sobel_at<LD>(ys, li + 1, lj + 1, gx, gy);
+      const float my = gradmag(gx, gy);
+      const float mm = mx * my;
+      const float g = (2.f * mm - A.alpha * mm + A.t) / (mx * mx + my * my - A.alpha * mm + A.t);  // gmsd.jl:5-10
+      const double d = (double)g - 1.0;  // sums of (g-1): well conditioned when x ~ y
+      s1 += d;
+      s2 += d * d;
+    }
+  }
+  const double t1 = block_sum(s1);
+  const double t2 = block_sum(s2);
+  if (tid == 0) {
+    const int b = s / A.C;
+    atomicAdd(A.acc + 2 * b, t1);
+    atomicAdd(A.acc + 2 * b + 1, t2);
+  }
+}
+
+// per-image mean / deviation (gmsd.jl:21-24) and the batch mean (reduction = mean, :26)
+__global__ void __launch_bounds__(128) k_gmsd_finalize(GmsdArgs A) {
+  const double n = (double)A.M * A.N * A.C;
+  double tot = 0.0;
+  for (int b = threadIdx.x; b < A.B; b += 128) {
+    const double m = A.acc[2 * b] / n;
+    double var = A.acc[2 * b + 1] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    const double sc = sqrt(var);
+    A.stats[2 * b] = 1.0 + m;
+    A.stats[2 * b + 1] = sc;
+    tot += sc;
+  }
+  tot = block_sum(tot);
+  if (threadIdx.x == 0) A.out[0] = (float)(tot / A.B);
+}
+
+__global__ void __launch_bounds__(GM_NT) k_gmsd_bwd(GmsdArgs A) {
+  constexpr int LD4 = GM_TH + 4, LD2 = GM_TH + 2;
+  __shared__ float xs[LD4 * (GM_TW + 4)], ys[LD4 * (GM_TW + 4)];
+  __shared__ float p1[LD2 * (GM_TW + 2)], p2[LD2 * (GM_TW + 2)];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * GM_TH, j0 = (tl / A.tiles_i) * GM_TW;
+  const size_t plane = (size_t)A.M * A.N;
+  gm_load_tile<2, LD4>(A.x + (size_t)s * plane, xs, i0, j0, A.M, A.N, tid);
+  gm_load_tile<2, LD4>(A.y + (size_t)s * plane, ys, i0, j0, A.M, A.N, tid);
+  const int b = s / A.C;
+  const float mean = (float)A.stats[2 * b];
+  // d loss / d g[p] = lossbar (g[p] - mean_b) / (B n sqrt(score_b))
+  const float scale = (float)((double)A.lossbar[0] / ((double)A.B * ((double)A.M * A.N * A.C) * A.stats[2 * b + 1]));
+  __syncthreads();
+  // cotangents of the two gradient fields on the tile + 1 halo
+  for (int e = tid; e < LD2 * (GM_TW + 2); e += GM_NT) {
+    const int li = e % LD2, lj = e / LD2;
+    float gx, gy, hx, hy;
+    sobel_at<LD4>(xs, li + 1, lj + 1, gx, gy);
+    const float mx = gradmag(gx, gy);
+    sobel_at<LD4>(ys, li + 1, lj + 1, hx, hy);
+    const float my = gradmag(hx, hy);
+    const float mm = mx * my;
+    const float den = mx * mx + my * my - A.alpha * mm + A.t;
+    const float g = (2.f * mm - A.alpha * mm + A.t) / den;
+    const float dgdmx = ((2.f - A.alpha) * my - g * (2.f * mx - A.alpha * my)) / den;
+    const float c = scale * (g - mean) * dgdmx / mx;
+    p1[e] = c * gx;
+    p2[e] = c * gy;
+  }
+  __syncthreads();
+  // adjoint of the two circular stencils
+  float* xb = A.out + (size_t)s * plane;
+  for (int e = tid; e < GM_TH * GM_TW; e += GM_NT) {
+    const int li = e % GM_TH, lj = e / GM_TH;
+    if (i0 + li < A.M && j0 + lj < A.N) {
+      const float* a0 = p1 + lj * LD2 + li + 1;  // column j-1 (tile coords are offset by the 1-halo)
+      const float* a1 = a0 + LD2;
+      const float* a2 = a1 + LD2;
+      const float* b0 = p2 + lj * LD2 + li + 1;
+      const float* b2 = b0 + 2 * LD2;
+      const float v = ((a0[-1] - a0[1]) + 2.f * (a1[-1] - a1[1]) + (a2[-1] - a2[1])) * 0.125f +
+                      ((b0[-1] - b2[-1]) + 2.f * (b0[0] - b2[0]) + (b0[1] - b2[1])) * 0.125f;
+      xb[(size_t)(j0 + lj) * A.M + i0 + li] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SSIM
+// ------------------------------------------------------------------------------------------
+constexpr int SS_T = 32, SS_NT = 256, SS_LMAX = 11, SS_IN = SS_T + SS_LMAX - 1;
+
+struct SsimArgs {
+  const float* x;
+  const float* y;
+  int M, N, C, B, L, Mo, No;
+  int tiles_i, tiles_j;
+  float f[SS_LMAX];  // flipped taps: NNlib conv is a true convolution (ssim.jl:112-119)
+  float C1, C2;
+  double* acc;        // [1] sum of the ssim map
+  float* maps;        // [3][planes][No][Mo] dS/dmu_x, dS/dE[x^2], dS/dE[xy]  (with_grad)
+  int with_grad, as_loss;
+  const float* outbar;
+  float* out;         // forward: ssim or 1-ssim ; backward: xbar
+};
+
+__global__ void __launch_bounds__(SS_NT) k_ssim_fwd(SsimArgs A) {
+  __shared__ float xs[SS_IN * SS_IN], ys[SS_IN * SS_IN];
+  __shared__ float P[5][SS_IN * SS_T];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L = A.L;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
+  const size_t plane = (size_t)A.M * A.N;
+  const float* xp = A.x + (size_t)s * plane;
+  const float* yp = A.y + (size_t)s * plane;
+  const int ext = SS_T + L - 1;
+  for (int e = tid; e < ext * ext; e += SS_NT) {
+    const int li = e % ext, lj = e / ext;
+    const int gi = i0 + li, gj = j0 + lj;
+    const bool ok = gi < A.M && gj < A.N;
+    xs[lj * SS_IN + li] = ok ? xp[(size_t)gj * A.M + gi] : 0.f;
+    ys[lj * SS_IN + li] = ok ? yp[(size_t)gj * A.M + gi] : 0.f;
+  }
+  __syncthreads();
+  // window along dim 1 for x, y, x^2, y^2, xy
+  for (int e = tid; e < SS_T * ext; e += SS_NT) {
+    const int li = e % SS_T, lj = e / SS_T;
+    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+    for (int a = 0; a < L; ++a) {
+      const float w = A.f[a], xv = xs[lj * SS_IN + li + a], yv = ys[lj * SS_IN + li + a];
+      sx += w * xv; sy += w * yv; sxx += w * xv * xv; syy += w * yv * yv; sxy += w * xv * yv;
+    }
+    P[0][e] = sx; P[1][e] = sy; P[2][e] = sxx; P[3][e] = syy; P[4][e] = sxy;
+  }
+  __syncthreads();
+  double tot = 0.0;
+  const size_t oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
+  for (int e = tid; e < SS_T * SS_T; e += SS_NT) {
+    const int li = e % SS_T, lj = e / SS_T;
+    if (i0 + li < A.Mo && j0 + lj < A.No) {
+      float mx = 0.f, my = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+      for (int a = 0; a < L; ++a) {
+        const float w = A.f[a];
+        const int o = (lj + a) * SS_T + li;
+        mx += w * P[0][o]; my += w * P[1][o]; exx += w * P[2][o]; eyy += w * P[3][o]; exy += w * P[4][o];
+      }
+      const float mxy = mx * my, mx2 = mx * mx, my2 = my * my;
+      const float sx2 = exx - mx2, sy2 = eyy - my2, sxy = exy - mxy;                   // ssim.jl:117-119
+      const float A1 = 2.f * mxy + A.C1, A2 = 2.f * sxy + A.C2, B1 = mx2 + my2 + A.C1, B2 = sx2 + sy2 + A.C2;
+      const float S = A1 * A2 / (B1 * B2);                                             // ssim.jl:121
+      tot += (double)S;
+      if (A.with_grad) {
+        const float ib = 1.f / (B1 * B2);
+        const size_t o = (size_t)s * oplane + (size_t)(j0 + lj) * A.Mo + i0 + li;
+        A.maps[o] = 2.f * my * (A2 - A1) * ib - 2.f * mx * S * (1.f / B1 - 1.f / B2);   // dS/dmu_x
+        A.maps[nplanes * oplane + o] = -S / B2;                                        // dS/dE[x^2]
+        A.maps[2 * nplanes * oplane + o] = 2.f * A1 * ib;                              // dS/dE[xy]
+      }
+    }
+  }
+  tot = block_sum(tot);
+  if (tid == 0) atomicAdd(A.acc, tot);
+}
+
+__global__ void k_ssim_finalize(SsimArgs A) {
+  // mean over (1,2,3) then over the batch: equal-sized images => the global mean (ssim.jl:122-123)
+  const double m = A.acc[0] / ((double)A.Mo * A.No * A.C * A.B);
+  A.out[0] = (float)(A.as_loss ? 1.0 - m : m);
+}
+
+__global__ void __launch_bounds__(SS_NT) k_ssim_bwd(SsimArgs A) {
+  __shared__ float ms[3][SS_IN * SS_IN];
+  __shared__ float T[3][SS_IN * SS_T];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L = A.L;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
+  const size_t plane = (size_t)A.M * A.N, oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
+  const int ext = SS_T + L - 1;
+  // derivative maps over output positions [i0-L+1, i0+T) x [j0-L+1, j0+T), zero outside the valid region
+  for (int e = tid; e < ext * ext; e += SS_NT) {
+    const int li = e % ext, lj = e / ext;
+    const int pi = i0 - (L - 1) + li, pj = j0 - (L - 1) + lj;
+    const bool ok = pi >= 0 && pj >= 0 && pi < A.Mo && pj < A.No;
+    const size_t o = (size_t)s * oplane + (size_t)(ok ? pj : 0) * A.Mo + (ok ? pi : 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ms[k][lj * SS_IN + li] = ok ? A.maps[k * nplanes * oplane + o] : 0.f;
+  }
+  __syncthreads();
+  // transposed window along dim 1: t[qi, pj] = sum_a f[a] map[qi - a, pj]
+  for (int e = tid; e < SS_T * ext; e += SS_NT) {
+    const int li = e % SS_T, lj = e / SS_T;
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    for (int a = 0; a < L; ++a) {
+      const float w = A.f[a];
+      const int o = lj * SS_IN + li + (L - 1) - a;
+      r0 += w * ms[0][o]; r1 += w * ms[1][o]; r2 += w * ms[2][o];
+    }
+    T[0][e] = r0; T[1][e] = r1; T[2][e] = r2;
+  }
+  __syncthreads();
+  const float scale = (float)((double)A.outbar[0] * (A.as_loss ? -1.0 : 1.0) / ((double)A.Mo * A.No * A.C * A.B));
+  const float* xp = A.x + (size_t)s * plane;
+  const float* yp = A.y + (size_t)s * plane;
+  float* xb = A.out + (size_t)s * plane;
+  for (int e = tid; e < SS_T * SS_T; e += SS_NT) {
+    const int li = e % SS_T, lj = e / SS_T;
+    const int gi = i0 + li, gj = j0 + lj;
+    if (gi < A.M && gj < A.N) {
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      for (int a = 0; a < L; ++a) {
+        const float w = A.f[a];
+        const int o = (lj + (L - 1) - a) * SS_T + li;
+        r0 += w * T[0][o]; r1 += w * T[1][o]; r2 += w * T[2][o];
+      }
+      const size_t g = (size_t)gj * A.M + gi;
+      xb[g] = scale * (r0 + 2.f * xp[g] * r1 + yp[g] * r2);
+    }
+  }
+}
+
+}  // namespace admmtv

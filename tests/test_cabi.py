@@ -28,6 +28,27 @@ def test_header_symbols_all_exported(lib):
     assert lib.version() == 100
 
 
+def test_loss_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "admmtv_loss.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(admmtv_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.LOSS_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib.lib, name), name
+    # argument validation without a GPU
+    assert lib.gmsd_workspace_bytes(64, 64, 3, 2) > 0
+    assert lib.ssim_workspace_bytes(64, 64, 3, 2, None, True) >= 3 * 54 * 54 * 6 * 4
+    with pytest.raises(_lib.AdmmTvError):
+        lib.ssim_workspace_bytes(8, 8, 1, 1, None, True)
+
+
+def test_loss_cpu_tensor_is_rejected():
+    import torch
+    from admm_deconv_b200 import losses
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.gmsd(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+
+
 def test_desc_layout_matches_header():
     import ctypes
     assert ctypes.sizeof(_lib.Desc) == 14 * 4
