@@ -44,6 +44,8 @@ LOSS_SYMBOLS = (
     "admmtv_ssim_forward",
     "admmtv_ssim_backward",
 )
+# every symbol include/admmtv_batch.h declares
+BATCH_SYMBOLS = ("admmtv_batch_from_n0f8",)
 
 
 class Desc(C.Structure):
@@ -97,7 +99,8 @@ class AdmmTvLib:
         L.admmtv_ssim_workspace_bytes.argtypes = [i, i, i, i, i, i, C.POINTER(sz)]
         L.admmtv_ssim_forward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, f, i, vp, vp, i, vp]
         L.admmtv_ssim_backward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, i, vp, vp, vp, vp]
-        for name in SYMBOLS + LOSS_SYMBOLS:
+        L.admmtv_batch_from_n0f8.argtypes = [i, i, i, i, i, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp]
+        for name in SYMBOLS + LOSS_SYMBOLS + BATCH_SYMBOLS:
             getattr(L, name)  # AttributeError if a declared symbol is not exported
 
     def strerror(self, code: int) -> str:
@@ -179,6 +182,9 @@ class AdmmTvLib:
         arr, L = self._taps(taps)
         self._raise(self.lib.admmtv_ssim_forward(M, N, Cc, B, device, x, y, arr, L, peakval, int(as_loss), out, ws,
                                                  int(with_grad), stream))
+
+    def batch_from_n0f8(self, M, N, Cc, B, device, src, sc, si, sj, sb, dst, stream=0):
+        self._raise(self.lib.admmtv_batch_from_n0f8(M, N, Cc, B, device, src, sc, si, sj, sb, dst, stream))
 
     def ssim_backward(self, M, N, Cc, B, device, x, y, taps, as_loss, outbar, ws, xbar, stream=0):
         arr, L = self._taps(taps)

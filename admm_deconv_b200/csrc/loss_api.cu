@@ -1,5 +1,6 @@
 // loss_api.cu -- the C ABI of include/admmtv_loss.h: argument checks, workspace carving, launches.
 #include "../../include/admmtv.h"
+#include "../../include/admmtv_batch.h"
 #include "../../include/admmtv_loss.h"
 #include "loss_kernels.cuh"
 
@@ -172,6 +173,25 @@ int admmtv_ssim_backward(int M, int N, int C, int B, int device, const float* x,
   const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
   if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
   ADMMTV_LAUNCH(k_ssim_bwd, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADMMTV_OK : (int)e;
+}
+
+int admmtv_batch_from_n0f8(int M, int N, int C, int B, int device, const uint8_t* src, int64_t stride_c, int64_t stride_i,
+                           int64_t stride_j, int64_t stride_b, float* dst, void* stream) {
+  int rc = check_shape(M, N, C, B);
+  if (rc) return rc;
+  if (!src || !dst) return ADMMTV_ERR_NULL;
+  if (stride_c < 0 || stride_i < 0 || stride_j < 0 || stride_b < 0) return ADMMTV_ERR_SHAPE;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  BatchArgs a{};
+  a.src = src; a.dst = dst; a.M = M; a.N = N; a.C = C; a.B = B;
+  a.tiles_i = (M + BA_T - 1) / BA_T; a.tiles_j = (N + BA_T - 1) / BA_T;
+  a.sc = stride_c; a.si = stride_i; a.sj = stride_j; a.sb = stride_b;
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_batch_from_n0f8, dim3((unsigned)nblk), dim3(BA_NT), 0, reinterpret_cast<cudaStream_t>(stream), a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ADMMTV_OK : (int)e;
 }

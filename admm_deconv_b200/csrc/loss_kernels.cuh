@@ -52,9 +52,20 @@ ADMMTV_DI float gradmag(float gx, float gy) { return sqrtf(gx * gx + gy * gy + 1
 
 template <int HALO, int LD>
 ADMMTV_DI void gm_load_tile(const float* __restrict__ p, float* T, int i0, int j0, int M, int N, int tid) {
+  if (M >= LD && N >= GM_TW + 2 * HALO) {
+    // common case: one conditional add/subtract wraps (the tile overshoots the image by less than one period)
+    for (int e = tid; e < LD * (GM_TW + 2 * HALO); e += GM_NT) {
+      const int li = e % LD, lj = e / LD;
+      int gi = i0 - HALO + li, gj = j0 - HALO + lj;
+      gi = gi < 0 ? gi + M : (gi >= M ? gi - M : gi);
+      gj = gj < 0 ? gj + N : (gj >= N ? gj - N : gj);
+      T[e] = p[(size_t)gj * M + gi];  // pad_circular, iqa_utils.jl:46
+    }
+    return;
+  }
   for (int e = tid; e < LD * (GM_TW + 2 * HALO); e += GM_NT) {
     const int li = e % LD, lj = e / LD;
-    T[e] = p[(size_t)wrapi(j0 - HALO + lj, N) * M + wrapi(i0 - HALO + li, M)];  // pad_circular, iqa_utils.jl:46
+    T[e] = p[(size_t)wrapi(j0 - HALO + lj, N) * M + wrapi(i0 - HALO + li, M)];
   }
 }
 
@@ -289,6 +300,48 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_bwd(SsimArgs A) {
       const size_t g = (size_t)gj * A.M + gi;
       xb[g] = scale * (r0 + 2.f * xp[g] * r1 + yp[g] * r2);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// batch assembly: N0f8 channel-interleaved crops -> fp32 (M,N,C,B)
+//   replaces img2tensor (base_funcs.jl:29-35) + cat(dims=4) (datafeeder.jl:54-68) + the fp32 upload
+// One block = one 32x32 pixel tile of one image, four channels at a time; the tile is transposed through shared
+// memory so that both the byte reads (source's fastest pixel dimension) and the float writes (dim 1) coalesce.
+// ------------------------------------------------------------------------------------------
+constexpr int BA_T = 32, BA_NT = 256, BA_CC = 4;
+
+struct BatchArgs {
+  const uint8_t* src;
+  float* dst;
+  int M, N, C, B;
+  int tiles_i, tiles_j;
+  long long sc, si, sj, sb;
+};
+
+__global__ void __launch_bounds__(BA_NT) k_batch_from_n0f8(BatchArgs A) {
+  __shared__ uint8_t tile[BA_CC][BA_T][BA_T + 1];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
+  const int b = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * BA_T, j0 = (tl / A.tiles_i) * BA_T;
+  const uint8_t* sp = A.src + (long long)b * A.sb;
+  const bool i_fast = A.si <= A.sj;
+  for (int c0 = 0; c0 < A.C; c0 += BA_CC) {
+    const int nc = min(BA_CC, A.C - c0);
+    for (int e = tid; e < BA_T * BA_T * nc; e += BA_NT) {
+      const int c = e % nc, r = e / nc;
+      const int li = i_fast ? r % BA_T : r / BA_T, lj = i_fast ? r / BA_T : r % BA_T;
+      const int gi = i0 + li, gj = j0 + lj;
+      if (gi < A.M && gj < A.N) tile[c][lj][li] = sp[(c0 + c) * A.sc + gi * A.si + gj * A.sj];
+    }
+    __syncthreads();
+    for (int e = tid; e < BA_T * BA_T * nc; e += BA_NT) {
+      const int li = e % BA_T, lj = (e / BA_T) % BA_T, c = e / (BA_T * BA_T);
+      const int gi = i0 + li, gj = j0 + lj;
+      if (gi < A.M && gj < A.N)
+        A.dst[gi + (size_t)A.M * (gj + (size_t)A.N * ((c0 + c) + (size_t)A.C * b))] = (float)tile[c][lj][li] / 255.f;
+    }
+    __syncthreads();
   }
 }
 

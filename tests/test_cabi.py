@@ -42,6 +42,17 @@ def test_loss_header_symbols_all_exported(lib):
         lib.ssim_workspace_bytes(8, 8, 1, 1, None, True)
 
 
+def test_batch_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "admmtv_batch.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(admmtv_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.BATCH_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib.lib, name), name
+    with pytest.raises(_lib.AdmmTvError):
+        lib.batch_from_n0f8(0, 4, 3, 1, 0, 256, 1, 3, 12, 48, 256)   # invalid shape is rejected before any launch
+
+
 def test_loss_cpu_tensor_is_rejected():
     import torch
     from admm_deconv_b200 import losses
