@@ -34,6 +34,8 @@ SYMBOLS = (
     "admmtv_ckpt_layout",
     "admmtv_forward_launches",
     "admmtv_backward_launches",
+    "admmtv_forward_ex",
+    "admmtv_backward_ex",
 )
 # every symbol include/admmtv_loss.h declares
 LOSS_SYMBOLS = (
@@ -58,6 +60,16 @@ class Desc(C.Structure):
         ("device", C.c_int32), ("flags", C.c_int32),
         ("creg", C.c_float), ("groups", C.c_int32),
     ]
+
+
+# int (*admmtv_allreduce_fn)(float* buf, size_t count, void* stream, void* user)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)
+
+
+class Hooks(C.Structure):
+    """struct admmtv_hooks (include/admmtv.h)."""
+
+    _fields_ = [("allreduce_sum", ALLREDUCE_FN), ("user", C.c_void_p), ("tau_owner", C.c_int32)]
 
 
 class AdmmTvError(RuntimeError):
@@ -86,6 +98,8 @@ class AdmmTvLib:
         L.admmtv_workspace_bytes.argtypes = [C.POINTER(Desc), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
         L.admmtv_forward.argtypes = [C.POINTER(Desc)] + [vp] * 9
         L.admmtv_backward.argtypes = [C.POINTER(Desc)] + [vp] * 14
+        L.admmtv_forward_ex.argtypes = [C.POINTER(Desc)] + [vp] * 9 + [C.POINTER(Hooks)]
+        L.admmtv_backward_ex.argtypes = [C.POINTER(Desc)] + [vp] * 14 + [C.POINTER(Hooks)]
         L.admmtv_profile_forward.argtypes = [C.POINTER(Desc)] + [vp] * 10
         L.admmtv_profile_backward.argtypes = [C.POINTER(Desc)] + [vp] * 15
         L.admmtv_forward_host.argtypes = [C.POINTER(Desc)] + [vp] * 6
@@ -127,6 +141,14 @@ class AdmmTvLib:
     def backward(self, d: Desc, xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar, biasbar, ws, stream=0):
         self._raise(self.lib.admmtv_backward(C.byref(d), xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar,
                                              biasbar, ws, stream))
+
+    def forward_ex(self, d: Desc, y, h, lam, rho, bias, x_out, ws, ckpt, stream, hooks: "Hooks"):
+        self._raise(self.lib.admmtv_forward_ex(C.byref(d), y, h, lam, rho, bias, x_out, ws, ckpt, stream, C.byref(hooks)))
+
+    def backward_ex(self, d: Desc, xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar, biasbar, ws, stream,
+                    hooks: "Hooks"):
+        self._raise(self.lib.admmtv_backward_ex(C.byref(d), xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar,
+                                                biasbar, ws, stream, C.byref(hooks)))
 
     def profile_forward(self, d: Desc, y, h, lam, rho, bias, x_out, ws, ckpt, stream=0):
         """Returns (total_ms, dim2_ms, dim1_ms, other_ms); synchronises."""

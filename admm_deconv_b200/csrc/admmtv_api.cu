@@ -302,7 +302,8 @@ static void tm_mark(Timing* tm, cudaStream_t st, int cls_of_next) {
 }
 
 static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
-                        float* x_out, void* workspace, void* ckpt, void* stream, Timing* tm) {
+                        float* x_out, void* workspace, void* ckpt, void* stream, Timing* tm,
+                        const admmtv_hooks* hk = nullptr) {
   int rc = admmtv_check(d);
   if (rc) return rc;
   if (!y || !lambda || !rho || !x_out || !workspace) return ADMMTV_ERR_NULL;
@@ -398,6 +399,9 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       fa.vprev = v_in; fa.vnew = v_out; fa.nsq = pre ? s_prev : nsq_prev; fa.pre = pre ? 1 : 0; fa.nsq_out = nsq_new;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_a(g, k > 1, fa, st); })
       if (rc) return rc;
+      if (hk && hk->allreduce_sum) {   // exact global-batch norm across ranks (admmtv_forward_ex)
+        if ((rc = hk->allreduce_sum(nsq_new, g.plane * g.G, stream, hk->user))) return rc;
+      }
       if (pre) {
         ADMMTV_LAUNCH(k_iso_scale, dim3((unsigned)((g.plane + 255) / 256), (unsigned)g.G), dim3(256), 0, st, (const float*)nsq_new,
                       (const float*)lambda, (const float*)rho, s_new, nsq_next, (int)g.plane);
@@ -425,6 +429,11 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
 int admmtv_forward(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
                    float* x_out, void* workspace, void* ckpt, void* stream) {
   return forward_impl(d, y, h, lambda, rho, bias, x_out, workspace, ckpt, stream, nullptr);
+}
+
+int admmtv_forward_ex(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,
+                      float* x_out, void* workspace, void* ckpt, void* stream, const admmtv_hooks* hooks) {
+  return forward_impl(d, y, h, lambda, rho, bias, x_out, workspace, ckpt, stream, nullptr, hooks);
 }
 
 int admmtv_profile_forward(const admmtv_desc* d, const float* y, float* h, float* lambda, float* rho, const float* bias,

@@ -109,6 +109,7 @@ struct Dim1BwdArgs {
   PlaneMap pm;
   int N, S;
   int first;               // 1: bbar is written, not accumulated (k = K)
+  int count_tau;           // isotropic inline path: 0 = another rank adds the per-pixel taubar terms (admmtv_backward_ex)
 };
 
 // variants of k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   const float2* sc_g = pre ? A.sc + (size_t)grp * plane : nullptr;
   const float* nsq_g = (MODE == 1 && !pre) ? A.nsq + (size_t)grp * plane : nullptr;
   const float* ip_g = (MODE == 1 && !pre) ? A.ip + (size_t)grp * plane : nullptr;
-  const bool tau_owner = (q % A.pm.Qg) == 0;  // inline path: the per-pixel taubar term is counted once per group
+  const bool tau_owner = (q % A.pm.Qg) == 0 && A.count_tau != 0;  // inline path: the per-pixel taubar term is counted once per group
   // (s, coef) of one pixel: loaded, or computed here (small, latency-bound problems skip the extra launch)
   auto PIX = [&](const float2* scp, size_t off, bool count) {
     if (pre) return scp[off];

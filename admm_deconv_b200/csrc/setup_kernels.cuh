@@ -138,7 +138,8 @@ static __global__ void k_iso_scale(const float* __restrict__ nsq, const float* _
 // backward: (s, 1[n>tau] tau ip / n^3) per pixel, and taubar -= sum_pixels 1[n>tau] ip / n   (acc[8g+1])
 // re-zeroes ip for the next iteration's accumulation (replaces a memset launch)
 static __global__ void k_iso_coef(const float* __restrict__ nsq, float* __restrict__ ip, const float* __restrict__ lambda,
-                                  const float* __restrict__ rho, float2* __restrict__ sc, double* acc, int npix) {
+                                  const float* __restrict__ rho, float2* __restrict__ sc, double* acc, int npix,
+                                  int count_tau) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // npix is a multiple of the block size
   const int g = blockIdx.y;
   const float tau = lambda[g] / rho[g];
@@ -149,7 +150,7 @@ static __global__ void k_iso_coef(const float* __restrict__ nsq, float* __restri
   const float s = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
   sc[(size_t)g * npix + i] = make_float2(s, act ? tau * p / (n * n * n) : 0.f);
   const double tot = block_sum(act ? (double)(p / n) : 0.0);
-  if (threadIdx.x == 0) atomicAdd(acc + 8 * g + 1, -tot);
+  if (threadIdx.x == 0 && count_tau) atomicAdd(acc + 8 * g + 1, -tot);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -8,7 +8,10 @@ they are packed into ONE buffer and summed with ONE all-reduce (NCCL over NVLink
 gloo in the CPU tests).  The message is < 4 KB: latency-bound, never bandwidth-bound.
 
 Isotropic TV couples the planes of a call through the per-pixel norm; sharded, each rank uses its
-own shard's norm ("per-shard batch" semantics == running the reference on each shard).
+own shard's norm by default ("per-shard batch" semantics == running the reference on each shard).
+``IsoCoupling`` restores the reference's single-device semantics (one norm per pixel over the WHOLE batch,
+ops.jl:6,10) across ranks: the library calls back once per iteration with the per-pixel partial sums and
+this module all-reduces them -- an (M,N) float image per iteration, 1 MB at 512^2.
 """
 from __future__ import annotations
 
@@ -16,6 +19,47 @@ from typing import Iterable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+class IsoCoupling:
+    """Builds the ``admmtv_hooks`` (include/admmtv.h) whose ``allreduce_sum`` sums a device buffer over ``group``.
+
+    The callback receives a raw pointer into one of the caller-owned buffers (workspace / checkpoint);
+    ``register`` tells the object about those buffers so the pointer can be turned back into a tensor view.
+    torch.distributed collectives are stream-ordered with respect to the current stream, which is the stream the
+    library launches on, so no host synchronisation is added."""
+
+    def __init__(self, group=None):
+        from . import _lib
+        self.group = group
+        self._bufs = []
+        self.calls = 0
+        self.floats = 0
+        self._cb = _lib.ALLREDUCE_FN(self._allreduce)       # keep the ctypes thunk alive
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.hooks = _lib.Hooks(self._cb, None, 1 if rank == 0 else 0)
+
+    def register(self, *tensors):
+        self._bufs = [t for t in tensors if t is not None]
+
+    def _view(self, ptr: int, count: int) -> torch.Tensor:
+        for t in self._bufs:
+            base = t.data_ptr()
+            if base <= ptr and ptr + 4 * count <= base + t.numel() * t.element_size():
+                off = ptr - base
+                return t.view(torch.uint8).reshape(-1)[off:off + 4 * count].view(torch.float32)
+        raise RuntimeError("IsoCoupling: pointer outside the registered buffers")
+
+    def _allreduce(self, buf, count, stream, user) -> int:
+        try:
+            dist.all_reduce(self._view(int(buf), int(count)), op=dist.ReduceOp.SUM, group=self.group)
+            self.calls += 1
+            self.floats += int(count)
+            return 0
+        except Exception as e:   # never let an exception cross the C boundary
+            import sys
+            print(f"IsoCoupling all-reduce failed: {e!r}", file=sys.stderr)
+            return -8
 
 
 def shard_range(B: int, rank: int, world: int) -> Tuple[int, int]:

@@ -69,7 +69,7 @@ class _AdmmFunction(torch.autograd.Function):
     Zygote's tape through ops.jl:166-174)."""
 
     @staticmethod
-    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags):
+    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags, coupling=None):
         lib = _lib.load()
         _check_cuda_f32("y", y)
         for n, t in (("lambda", lam), ("rho", rho)):
@@ -88,7 +88,14 @@ class _AdmmFunction(torch.autograd.Function):
         x = torch.empty_like(y)
         stream = torch.cuda.current_stream(y.device).cuda_stream
         # lam / rho / h are clamped IN PLACE (deconv_admm.jl:216-219 persists the clamp)
-        lib.forward(d, _ptr(y), _ptr(h), _ptr(lam), _ptr(rho), _ptr(bias), _ptr(x), _ptr(ws), _ptr(ck), stream)
+        if coupling is not None and iso:
+            coupling.register(ws, ck)
+            lib.forward_ex(d, _ptr(y), _ptr(h), _ptr(lam), _ptr(rho), _ptr(bias), _ptr(x), _ptr(ws), _ptr(ck), stream,
+                           coupling.hooks)
+        else:
+            coupling = None
+            lib.forward(d, _ptr(y), _ptr(h), _ptr(lam), _ptr(rho), _ptr(bias), _ptr(x), _ptr(ws), _ptr(ck), stream)
+        ctx.coupling = coupling
         ctx.desc = d
         ctx.ck = ck
         ctx.has_h = h is not None
@@ -110,21 +117,30 @@ class _AdmmFunction(torch.autograd.Function):
         rbar = torch.empty_like(rho)
         bbar = torch.empty(1, dtype=torch.float32, device=y.device) if ctx.has_bias else None
         stream = torch.cuda.current_stream(y.device).cuda_stream
-        lib.backward(d, _ptr(xbar), _ptr(x), _ptr(y), _ptr(h) if ctx.has_h else None, _ptr(lam), _ptr(rho), _ptr(ctx.ck),
-                     _ptr(ybar), _ptr(hbar), _ptr(lbar), _ptr(rbar), _ptr(bbar), _ptr(ws), stream)
-        return ybar, lbar, rbar, hbar, bbar, None, None, None, None, None
+        args = (d, _ptr(xbar), _ptr(x), _ptr(y), _ptr(h) if ctx.has_h else None, _ptr(lam), _ptr(rho), _ptr(ctx.ck),
+                _ptr(ybar), _ptr(hbar), _ptr(lbar), _ptr(rbar), _ptr(bbar), _ptr(ws), stream)
+        if ctx.coupling is not None:
+            ctx.coupling.register(ws, ctx.ck)
+            lib.backward_ex(*args, ctx.coupling.hooks)
+        else:
+            lib.backward(*args)
+        return ybar, lbar, rbar, hbar, bbar, None, None, None, None, None, None
 
 
 def admm_layer_call(y, lam, rho, h=None, bias=None, iters=100, iso=False, activation="identity", creg=0.0,
-                    nograd_repeat=False, clamp=True):
-    """The full layer call (d::Admm)(x), deconv_admm.jl:215-225, differentiable."""
+                    nograd_repeat=False, clamp=True, iso_coupling=None):
+    """The full layer call (d::Admm)(x), deconv_admm.jl:215-225, differentiable.
+
+    ``iso_coupling`` (a ``dist.IsoCoupling``, EXTENSION): with a batch sharded over ranks, makes the
+    isotropic per-pixel norm span every rank's images, i.e. the reference's single-device result on the whole batch."""
     flags = (0 if clamp else _lib.FLAG_NO_CLAMP) | (_lib.FLAG_NOGRAD_REPEAT if nograd_repeat else 0)
-    return _AdmmFunction.apply(y, lam, rho, h, bias, int(iters), bool(iso), activation, float(creg), flags)
+    return _AdmmFunction.apply(y, lam, rho, h, bias, int(iters), bool(iso), activation, float(creg), flags, iso_coupling)
 
 
-def tvd_fft(y, lam, rho, h=None, isotropic=False, maxit=100):
+def tvd_fft(y, lam, rho, h=None, isotropic=False, maxit=100, iso_coupling=None):
     """tvd_fft(y, λ, ρ, h, isotropic, maxit) -- ops.jl:181: no clamp, no bias, no activation."""
-    return admm_layer_call(y, lam, rho, h, None, maxit, isotropic, "identity", 0.0, False, clamp=False)
+    return admm_layer_call(y, lam, rho, h, None, maxit, isotropic, "identity", 0.0, False, clamp=False,
+                           iso_coupling=iso_coupling)
 
 
 tvd_fft_gpu = tvd_fft  # ops.jl:99 (tests/admm_deconv_test.jl:76 calls it directly)

@@ -112,6 +112,31 @@ int admmtv_backward(const admmtv_desc* desc, const float* xbar, const float* x_o
                     float* ybar, float* hbar, float* lambdabar, float* rhobar, float* biasbar,
                     void* workspace, void* stream);
 
+/* ---- cross-rank isotropic coupling (EXTENSION) --------------------------------------
+ * The reference's isotropic norm spans every image of the call (ops.jl:6,10).  When the batch is sharded over
+ * several GPUs, admmtv_forward / admmtv_backward use each shard's own norm.  The _ex entry points restore the
+ * single-device semantics: after the kernel that accumulates the per-pixel sum of squares (forward) or the
+ * per-pixel inner products (backward) they call `allreduce_sum` on that (groups x N x M) float buffer, once per
+ * iteration; the caller implements it with its communicator (ncclAllReduce on `stream`, or torch.distributed).
+ * It must be stream-ordered on `stream` and return 0 on success (any other value aborts the call and is returned).
+ * `tau_owner`: the per-pixel part of the lambda / rho cotangents is identical on every rank; exactly one rank
+ * (tau_owner = 1) adds it, so that the usual sum all-reduce of the parameter gradients stays correct.
+ * hooks = NULL behaves like admmtv_forward / admmtv_backward. */
+typedef int (*admmtv_allreduce_fn)(float* buf, size_t count, void* stream, void* user);
+typedef struct admmtv_hooks {
+  admmtv_allreduce_fn allreduce_sum;
+  void* user;
+  int32_t tau_owner;
+} admmtv_hooks;
+
+int admmtv_forward_ex(const admmtv_desc* desc, const float* y, float* h, float* lambda, float* rho,
+                      const float* bias, float* x_out, void* workspace, void* ckpt, void* stream,
+                      const admmtv_hooks* hooks);
+int admmtv_backward_ex(const admmtv_desc* desc, const float* xbar, const float* x_out, const float* y,
+                       const float* h, const float* lambda, const float* rho, const void* ckpt,
+                       float* ybar, float* hbar, float* lambdabar, float* rhobar, float* biasbar,
+                       void* workspace, void* stream, const admmtv_hooks* hooks);
+
 /* Host-buffer convenience (the reference's tvd_fft on a CPU Array): allocates device memory,
  * copies y/h/λ/ρ/bias in, runs admmtv_forward, copies x_out (and the clamped h/λ/ρ) back,
  * frees, synchronises.  All pointers are HOST pointers. */

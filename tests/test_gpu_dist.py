@@ -1,0 +1,41 @@
+"""GPU tests of the cross-rank isotropic coupling (admmtv_forward_ex / admmtv_backward_ex) on ONE GPU:
+a world-size-1 NCCL group drives the per-iteration callback path; results must be bit-identical to the plain call.
+The two-rank exactness check runs on CPU (tests/test_dist_gloo.py, emulated kernels + gloo) and on two GPUs with
+tools/iso_coupling_check.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+
+import admm_deconv_b200 as A
+from admm_deconv_b200 import dist as D
+
+pytestmark = pytest.mark.gpu
+
+
+def test_iso_coupling_world1_is_identity():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1")
+    dev = torch.device("cuda:0")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        torch.manual_seed(0)
+        y = torch.rand(3, 2, 64, 64, device=dev)
+        h = torch.rand(1, 1, 3, 3, device=dev) / 9
+        outs = []
+        for cp in (None, D.IsoCoupling()):
+            lam = torch.tensor([0.05], device=dev, requires_grad=True); rho = torch.tensor([0.3], device=dev, requires_grad=True)
+            hh = h.clone().requires_grad_(True)
+            x = A.admm_layer_call(y, lam, rho, hh, None, 5, True, "identity", 0.0, False, clamp=False, iso_coupling=cp)
+            x.backward(torch.ones_like(x))
+            torch.cuda.synchronize()
+            outs.append((x.detach(), hh.grad, lam.grad, rho.grad))
+            if cp is not None:
+                assert cp.calls == 2 * 4          # K-1 forward + K-1 backward all-reduces
+        # float atomics make the per-pixel norm reproducible to rounding only
+        for a, b in zip(*outs):
+            assert float((a - b).norm() / b.norm()) < 1e-5
+    finally:
+        dist.destroy_process_group()
