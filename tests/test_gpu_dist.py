@@ -25,11 +25,12 @@ def test_iso_coupling_world1_is_identity():
         y = torch.rand(3, 2, 64, 64, device=dev)
         h = torch.rand(1, 1, 3, 3, device=dev) / 9
         outs = []
+        xbar = torch.randn(3, 2, 64, 64, device=dev)      # (a constant cotangent has zero λ/ρ gradient: the mean of x is fixed)
         for cp in (None, D.IsoCoupling()):
             lam = torch.tensor([0.05], device=dev, requires_grad=True); rho = torch.tensor([0.3], device=dev, requires_grad=True)
             hh = h.clone().requires_grad_(True)
             x = A.admm_layer_call(y, lam, rho, hh, None, 5, True, "identity", 0.0, False, clamp=False, iso_coupling=cp)
-            x.backward(torch.ones_like(x))
+            x.backward(xbar)
             torch.cuda.synchronize()
             outs.append((x.detach(), hh.grad, lam.grad, rho.grad))
             if cp is not None:
