@@ -30,7 +30,7 @@ GXX_FLAGS = ["-std=c++20", "-O1", "-fPIC", "-pthread", "-DADMMTV_EMU", "-x", "c+
 
 def _units():
     """(source, define, object stem)"""
-    u = [("admmtv_api.cu", None, "admmtv_api"), ("loss_api.cu", None, "loss_api")]
+    u = [("admmtv_api.cu", None, "admmtv_api"), ("loss_api.cu", None, "loss_api"), ("inst_generic.cu", None, "inst_generic")]
     for l in LOG2_SIZES:
         u.append(("inst_dim1.cu", l, f"inst_dim1_{l}"))
         u.append(("inst_dim2.cu", l, f"inst_dim2_{l}"))

@@ -23,6 +23,7 @@ static Geom geom(const admmtv_desc* d) {
   g.S = d->P * d->B;
   g.Q = (g.S + 1) / 2;
   g.LM = dim_id(d->M); g.LN = dim_id(d->N);
+  if (g.LM <= 0 || g.LN <= 0) g.LM = g.LN = 0;   // no register-FFT plan for one of the lengths: generic kernels for both
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
   g.G = d->groups > 1 ? d->groups : 1;
   g.Bg = d->B / g.G;
@@ -106,6 +107,7 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
 // ---- per-size dispatch (definitions live in inst_dim1.cu / inst_dim2.cu) ------------------------
 #define ADMMTV_SWITCH_LOG2(val, NAME, ...)                                   \
   switch (val) {                                                             \
+    case 0: { constexpr int NAME = 0; __VA_ARGS__ } break;                   \
     case 5: { constexpr int NAME = 5; __VA_ARGS__ } break;                   \
     case 6: { constexpr int NAME = 6; __VA_ARGS__ } break;                   \
     case 7: { constexpr int NAME = 7; __VA_ARGS__ } break;                   \
@@ -132,6 +134,7 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
 
 #define ADMMTV_SWITCH_LOG2_RC(val, NAME, RC, ...)                            \
   switch (val) {                                                             \
+    case 0: { constexpr int NAME = 0; __VA_ARGS__ } break;                   \
     case 5: { constexpr int NAME = 5; __VA_ARGS__ } break;                   \
     case 6: { constexpr int NAME = 6; __VA_ARGS__ } break;                   \
     case 7: { constexpr int NAME = 7; __VA_ARGS__ } break;                   \
@@ -205,7 +208,7 @@ static int run_setup(const Geom& g, const float* h, const float* rho, float2* tw
   {
     const size_t n = g.plane;
     ADMMTV_LAUNCH(k_setup_tables, dim3((unsigned)((n + 127) / 128), (unsigned)g.G), dim3(128), 0, st, (const double2*)T, g.kh,
-                  g.kw, g.M, g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig);
+                  g.kw, g.M, g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig, g.LM > 0 ? 1 : 0);
     ADMMTV_CHECK_LAUNCH();
   }
   return 0;
@@ -224,7 +227,7 @@ const char* admmtv_strerror(int code) {
     case ADMMTV_OK: return "ok";
     case ADMMTV_ERR_NULL: return "admmtv: null pointer argument";
     case ADMMTV_ERR_SHAPE: return "admmtv: invalid shape (dims must be positive, PSF no larger than the image)";
-    case ADMMTV_ERR_UNSUPPORTED: return "admmtv: unsupported size (M and N must be a power of two in 32..4096 or one of 96, 160, 192, 320, 384, 480, 640, 768, 960, 1280, 1536, 1920)";
+    case ADMMTV_ERR_UNSUPPORTED: return "admmtv: unsupported size (M and N must be at most 4096; SSIM windows at most 11 taps)";
     case ADMMTV_ERR_ITERS: return "admmtv: iters must be >= 1";
     case ADMMTV_ERR_ENUM: return "admmtv: invalid enum / flag value in descriptor";
     case ADMMTV_ERR_ALIGN: return "admmtv: workspace and checkpoint must be 256-byte aligned";
@@ -281,6 +284,11 @@ int admmtv_ckpt_layout(const admmtv_desc* d, size_t out[4]) {
 int admmtv_forward_launches(const admmtv_desc* d, int with_ckpt) {
   (void)with_ckpt;
   if (admmtv_check(d)) return 0;
+  if (geom(d).LM == 0) {   // generic sizes: every dim-1 contract is [DFT] sweep [DFT] (inst_generic.cu)
+    int n = 1 + 2 + (d->kh > 0 ? 1 : 0) + 2 /*pack, DFT*/ + (d->kh > 0 ? 1 + 2 + 2 : 0);
+    n += d->iters + (d->iters - 1) * (d->iso ? 5 : 3) + 2;
+    return n;
+  }
   int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 3 : 0);
   n += d->iters + (d->iters - 1) * (d->iso ? 3 : 1) + 1;
   return n;

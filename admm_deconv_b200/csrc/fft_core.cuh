@@ -69,16 +69,20 @@ ADMMTV_HD constexpr int dim_len(int id) {
   }
 }
 ADMMTV_HD constexpr bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+// id 0 = no register plan: the generic kernels (generic_kernels.cuh) handle any length 1..kMaxGenericLen
+constexpr int kMaxGenericLen = 4096;
 ADMMTV_HD inline int dim_id(int L) {
   for (int id = 5; id <= 12; ++id)
     if (dim_len(id) == L) return id;
   for (int id = 20; id <= 31; ++id)
     if (dim_len(id) == L) return id;
-  return -1;
+  return (L >= 1 && L <= kMaxGenericLen) ? 0 : -1;
 }
 
 // frequency index held at storage position p after the forward (DIF) passes
-ADMMTV_HD inline int pos_to_freq(int L, int p) {
+// (`planned` = false: the generic path keeps spectra in natural order)
+ADMMTV_HD inline int pos_to_freq(int L, int p, bool planned = true) {
+  if (!planned || !plan_supported(L)) return p;
   int k = 0, mult = 1, len = L;
   for (int s = 0; s < 4; ++s) {
     int R = plan_radix(L, s);

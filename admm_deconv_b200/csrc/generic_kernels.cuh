@@ -1,0 +1,368 @@
+// generic_kernels.cuh -- the ADMM-TV path for image sizes that have no register-FFT plan (fft_core.cuh).
+//
+// The reference accepts every (M,N) because FFTW does (/root/reference/src/ops/ops.jl:26,86).  The tuned kernels
+// of kernels.cuh / kernels_bwd.cuh exist for the 20 planned lengths; any other size 1..4096 runs through the
+// kernels below, which implement the SAME launcher contracts (args.cuh: Dim1Launch / Dim2Launch, size id 0)
+// with run-time sizes, so the launch sequences, workspace layout, checkpoint and gradient code of
+// admmtv_api.cu / bwd_api.inc are shared.  Differences from the tuned path:
+//   * spectra are in NATURAL order (pos_to_freq is the identity for unplanned lengths);
+//   * a length-L DFT is a two-factor Cooley-Tukey step L = L1*L2 (L1 the largest divisor <= sqrt(L)) with
+//     direct sub-transforms in shared memory: O(L (L1+L2)) per line, O(L^2) for a prime length;
+//   * the stencil sweeps are separate, unfused per-pixel kernels (neighbour values are recomputed, not exchanged).
+// Same arithmetic per pixel (shrink_aniso / bwd_point / iso_* are the tuned path's functions), same results
+// to fp32 rounding; correct and bandwidth-reasonable, not roofline-tuned.
+#pragma once
+
+#include "kernels_bwd.cuh"
+
+namespace admmtv {
+
+constexpr int GK_NT = 256;
+
+ADMMTV_HD inline int small_factor(int L) {
+  int f = 1;
+  for (int d = 1; d * d <= L; ++d)
+    if (L % d == 0) f = d;
+  return f;
+}
+ADMMTV_HD inline int gk_lines_dim1(int M) { return M <= 64 ? 8 : (M <= 256 ? 4 : (M <= 1024 ? 2 : 1)); }
+ADMMTV_HD inline int gk_rows_dim2(int N) { return N <= 1024 ? 8 : (N <= 2048 ? 4 : 2); }
+
+ADMMTV_DI float2 cfma(float2 acc, float2 a, float2 w) {
+  return make_float2(acc.x + a.x * w.x - a.y * w.y, acc.y + a.x * w.y + a.y * w.x);
+}
+
+// In-place DFT of `nl` lines xs[l*L .. l*L+L) held in shared memory (natural order in and out), scratch ys of the
+// same size, tw[n] = exp(-2 pi i n / L) in shared memory; `inv` conjugates the twiddles (no 1/L: the tables carry
+// the normalisation).  Every thread of the block must call; ends with a barrier.
+ADMMTV_DI void line_dft(float2* xs, float2* ys, const float2* tw, int L, int L1, int L2, int nl, bool inv, int tid) {
+  const float sg = inv ? -1.f : 1.f;
+  // ys[k1*L2 + n2] = W^(n2 k1) * sum_n1 xs[L2 n1 + n2] W^(L2 n1 k1)
+  for (int e = tid; e < nl * L; e += GK_NT) {
+    const int l = e / L, r = e % L, k1 = r / L2, n2 = r % L2;
+    const float2* x = xs + l * L + n2;
+    float2 acc = make_float2(0.f, 0.f);
+    const int step = (int)(((long long)L2 * k1) % L);
+    int idx = 0;
+    for (int n1 = 0; n1 < L1; ++n1) {
+      const float2 w = tw[idx];
+      acc = cfma(acc, x[n1 * L2], make_float2(w.x, sg * w.y));
+      idx += step;
+      if (idx >= L) idx -= L;
+    }
+    const float2 w = tw[(int)(((long long)n2 * k1) % L)];
+    ys[e] = cmul(acc, make_float2(w.x, sg * w.y));
+  }
+  __syncthreads();
+  // xs[k1 + L1 k2] = sum_n2 ys[k1*L2 + n2] W^(L1 n2 k2)
+  for (int e = tid; e < nl * L; e += GK_NT) {
+    const int l = e / L, r = e % L, k1 = r % L1, k2 = r / L1;
+    const float2* y = ys + l * L + k1 * L2;
+    float2 acc = make_float2(0.f, 0.f);
+    const int step = (int)(((long long)L1 * k2) % L);
+    int idx = 0;
+    for (int n2 = 0; n2 < L2; ++n2) {
+      const float2 w = tw[idx];
+      acc = cfma(acc, y[n2], make_float2(w.x, sg * w.y));
+      idx += step;
+      if (idx >= L) idx -= L;
+    }
+    xs[e] = acc;
+  }
+  __syncthreads();
+}
+
+// ---- dim-1 DFT of contiguous lines, in place or out of place ------------------------------------------
+struct GDft1Args {
+  const float2* in;
+  float2* out;
+  const float2* tw;
+  int M, M1, M2, LB, inv;
+  long long nlines;
+};
+__global__ void __launch_bounds__(GK_NT) gk_dft1(GDft1Args A) {
+  ADMMTV_DYN_SMEM(float2, sm);
+  float2* tw = sm;
+  float2* xs = sm + A.M;
+  float2* ys = xs + (size_t)A.LB * A.M;
+  const int tid = threadIdx.x;
+  const long long l0 = (long long)blockIdx.x * A.LB;
+  const int nl = (int)(A.nlines - l0 < A.LB ? A.nlines - l0 : A.LB);
+  for (int e = tid; e < A.M; e += GK_NT) tw[e] = A.tw[e];
+  for (int e = tid; e < nl * A.M; e += GK_NT) xs[e] = A.in[l0 * A.M + e];
+  __syncthreads();
+  line_dft(xs, ys, tw, A.M, A.M1, A.M2, nl, A.inv != 0, tid);
+  for (int e = tid; e < nl * A.M; e += GK_NT) A.out[l0 * A.M + e] = xs[e];
+}
+
+// ---- dim-2: forward DFT -> [save Z] -> [accumulate] -> x table -> inverse DFT  (the contract of k_dim2) -----
+struct GDim2Cfg {
+  int N, N1, N2, TR, mul, save_z, acc, fwd_only;
+};
+__global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
+  ADMMTV_DYN_SMEM(float2, sm);
+  float2* tw = sm;
+  float2* xs = sm + C.N;
+  float2* ys = xs + (size_t)C.TR * C.N;
+  const int tid = threadIdx.x, M = A.M, N = C.N, TR = C.TR;
+  const int row_tiles = (M + TR - 1) / TR;
+  const int q = blockIdx.x / row_tiles, i0 = (blockIdx.x % row_tiles) * TR;
+  const int nr = min(TR, M - i0);
+  const size_t qoff = (size_t)q * N * M;
+  const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;
+  for (int e = tid; e < N; e += GK_NT) tw[e] = A.twN[e];
+  for (int e = tid; e < nr * N; e += GK_NT) {
+    const int ll = e % nr, col = e / nr;
+    xs[ll * N + col] = A.in[qoff + (size_t)col * M + i0 + ll];
+  }
+  __syncthreads();
+  line_dft(xs, ys, tw, N, C.N1, C.N2, nr, false, tid);
+  for (int e = tid; e < nr * N; e += GK_NT) {
+    const int ll = e % nr, col = e / nr;
+    const size_t g = (size_t)col * M + i0 + ll;
+    float2 z = xs[ll * N + col];
+    if (C.save_z || C.fwd_only) (C.fwd_only ? A.out : A.zsave)[qoff + g] = z;
+    if (C.acc) {
+      const float2 z2 = A.z2[qoff + g];
+      const float re = z.x * z2.x + z.y * z2.y, im = z.x * z2.y - z.y * z2.x;  // conj(Z) Z2
+      if (C.acc == 1) atomicAdd(A.gacc + toff + g, re);
+      else {
+        atomicAdd(A.gacc + 2 * (toff + g), re);
+        atomicAdd(A.gacc + 2 * (toff + g) + 1, im);
+      }
+    }
+    if (!C.fwd_only) {
+      if (C.mul == 0) z = cscale(z, A.ctab[toff + g]);
+      else {
+        const float2 kk = A.ktab[toff + g];
+        z = cmul(z, make_float2(kk.x, C.mul == 2 ? -kk.y : kk.y));
+      }
+      xs[ll * N + col] = z;
+    }
+  }
+  if (C.fwd_only) return;
+  __syncthreads();
+  line_dft(xs, ys, tw, N, C.N1, C.N2, nr, true, tid);
+  for (int e = tid; e < nr * N; e += GK_NT) {
+    const int ll = e % nr, col = e / nr;
+    A.out[qoff + (size_t)col * M + i0 + ll] = xs[ll * N + col];
+  }
+}
+
+// ---- per-pixel helpers ---------------------------------------------------------------------------------
+struct Pix {
+  int i, j, q, ip1, im1, jp1, jm1;  // circular neighbours
+  size_t plane, o;                  // o = j*M + i
+};
+ADMMTV_DI bool gk_pix(size_t idx, int M, int N, int Q, Pix& p) {
+  p.plane = (size_t)M * N;
+  if (idx >= p.plane * Q) return false;
+  p.i = (int)(idx % M);
+  p.j = (int)((idx / M) % N);
+  p.q = (int)(idx / p.plane);
+  p.ip1 = p.i + 1 == M ? 0 : p.i + 1;
+  p.im1 = p.i == 0 ? M - 1 : p.i - 1;
+  p.jp1 = p.j + 1 == N ? 0 : p.j + 1;
+  p.jm1 = p.j == 0 ? N - 1 : p.j - 1;
+  p.o = (size_t)p.j * M + p.i;
+  return true;
+}
+
+// ---- pack (the elementwise part of k_pack_fft1; the dim-1 DFT follows as gk_dft1 in place) -------------------
+__global__ void __launch_bounds__(GK_NT) gk_pack(PackArgs A, int M, int Q, int mode) {
+  const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
+  Pix p;
+  double bsum = 0.0;
+  int grp = 0;
+  if (gk_pix(idx, M, A.N, Q, p)) {
+    grp = p.q / A.pm.Qg;
+    if (mode == 2) A.spec[idx] = A.src_packed[idx];
+    else {
+      const long ia = mode == 1 ? pm_out(A.pm, p.q, 0) : pm_in(A.pm, p.q, 0);
+      const long ib = mode == 1 ? pm_out(A.pm, p.q, 1) : pm_in(A.pm, p.q, 1);
+      float va = A.src[(size_t)ia * p.plane + p.o], vb = ib >= 0 ? A.src[(size_t)ib * p.plane + p.o] : 0.f;
+      if (mode == 0 && A.packed_out) A.packed_out[idx] = make_float2(va, vb);
+      if (mode == 1) {
+        va *= act_grad_from_out(A.xout[(size_t)ia * p.plane + p.o], A.act);
+        if (ib >= 0) vb *= act_grad_from_out(A.xout[(size_t)ib * p.plane + p.o], A.act);
+        bsum = (double)va + (double)vb;
+      }
+      A.spec[idx] = make_float2(va, vb);
+    }
+  }
+  if (mode == 1 && A.bias_acc) {
+    // a block may straddle two groups only when a group is smaller than a block: fall back to per-thread atomics then
+    const size_t per_group = (size_t)A.pm.Qg * M * A.N;
+    if (per_group % GK_NT == 0) {
+      const double tot = block_sum(bsum);
+      if (threadIdx.x == 0) atomicAdd(A.bias_acc + 8 * (int)(((size_t)blockIdx.x * GK_NT) / per_group), tot);
+    } else if (bsum != 0.0) {
+      atomicAdd(A.bias_acc + 8 * grp, bsum);
+    }
+  }
+}
+
+// ---- out (the elementwise part of k_dim1_out; the inverse dim-1 DFT ran in place before) ---------------------
+__global__ void __launch_bounds__(GK_NT) gk_out(OutArgs A, int M, int Q, int mode) {
+  const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
+  Pix p;
+  if (!gk_pix(idx, M, A.N, Q, p)) return;
+  const float2 v = A.spec[idx];
+  if (mode == 0) {
+    A.packed[idx] = v;
+  } else if (mode == 2) {
+    const long ia = pm_in(A.pm, p.q, 0), ib = pm_in(A.pm, p.q, 1);
+    if (A.pm.G > 1 && A.pm.in_gstride == 0) {
+      atomicAdd(A.planes + (size_t)ia * p.plane + p.o, v.x);
+      if (ib >= 0) atomicAdd(A.planes + (size_t)ib * p.plane + p.o, v.y);
+    } else {
+      A.planes[(size_t)ia * p.plane + p.o] = v.x;
+      if (ib >= 0) A.planes[(size_t)ib * p.plane + p.o] = v.y;
+    }
+  } else {
+    const long ia = pm_out(A.pm, p.q, 0), ib = pm_out(A.pm, p.q, 1);
+    const float bias = A.bias ? A.bias[p.q / A.pm.Qg] : 0.f;
+    A.planes[(size_t)ia * p.plane + p.o] = act_apply(v.x + bias, A.act);
+    if (ib >= 0) A.planes[(size_t)ib * p.plane + p.o] = act_apply(v.y + bias, A.act);
+  }
+}
+
+// ---- forward sweep (the stencil of k_dim1_fwd; X = x_k, spatial, [Q][N][M]) --------------------------------------
+//   mode 0: v_k = D x_k + u_{k-1} (stored) ; r = b + rho D^T (z_k - u_k) -> rout           (ops.jl:168-173)
+//   mode 2: isotropic pass A: v_k stored, nsq_out += |v_k|^2
+//   mode 1: isotropic pass B: r = b + rho D^T ((2 s_k - 1) v_k) -> rout   (v_k in A.vprev, s_k or |v_k|^2 in A.nsq)
+__global__ void __launch_bounds__(GK_NT) gk_sweep_fwd(Dim1FwdArgs A, const float2* X, float2* rout, int M, int Q, int mode,
+                                                      int has_vprev) {
+  const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
+  Pix p;
+  if (!gk_pix(idx, M, A.N, Q, p)) return;
+  const int grp = p.q / A.Qg;
+  const float rho = A.rho[grp], tau = A.lambda[grp] / rho;
+  const size_t q1 = ((size_t)p.q * 2 + 0) * p.plane, q2 = ((size_t)p.q * 2 + 1) * p.plane, qx = (size_t)p.q * p.plane;
+  const size_t o = p.o, oj = (size_t)p.jp1 * M + p.i, oi = (size_t)p.j * M + p.ip1;   // (i,j), (i,j+1), (i+1,j)
+  const float* ng = mode != 0 ? A.nsq + (size_t)grp * p.plane : nullptr;
+  const bool pre = A.pre != 0;
+  auto SC = [&](float t) { return pre ? t : iso_scale(t, tau); };
+  if (mode == 1) {
+    const float2 w1 = shrink_iso(A.vprev[q1 + o], SC(ng[o])).w, w1n = shrink_iso(A.vprev[q1 + oj], SC(ng[oj])).w;
+    const float2 w2 = shrink_iso(A.vprev[q2 + o], SC(ng[o])).w, w2n = shrink_iso(A.vprev[q2 + oi], SC(ng[oi])).w;
+    const float2 dt = cadd(csub(w1, w1n), csub(w2, w2n));
+    const float2 b = A.bpk[qx + o];
+    rout[qx + o] = make_float2(b.x + rho * dt.x, b.y + rho * dt.y);
+    return;
+  }
+  const float2 x0 = X[qx + o];
+  // u_{k-1} at a pixel / channel
+  auto U = [&](size_t base, size_t off) {
+    if (!has_vprev) return make_float2(0.f, 0.f);
+    const float2 vp = A.vprev[base + off];
+    return mode == 2 ? shrink_iso(vp, SC(ng[off])).u : shrink_aniso(vp, tau).u;
+  };
+  const float2 v1 = cadd(csub(x0, X[qx + (size_t)p.jm1 * M + p.i]), U(q1, o));   // channel 1: dim-2 difference
+  const float2 v2 = cadd(csub(x0, X[qx + (size_t)p.j * M + p.im1]), U(q2, o));   // channel 2: dim-1 difference
+  A.vnew[q1 + o] = v1;
+  A.vnew[q2 + o] = v2;
+  if (mode == 2) {
+    atomicAdd(A.nsq_out + (size_t)grp * p.plane + o, v1.x * v1.x + v1.y * v1.y + v2.x * v2.x + v2.y * v2.y);
+    return;
+  }
+  const float2 v1n = cadd(csub(X[qx + oj], x0), U(q1, oj));   // channel 1 at (i, j+1)
+  const float2 v2n = cadd(csub(X[qx + oi], x0), U(q2, oi));   // channel 2 at (i+1, j)
+  const float2 dt = cadd(csub(shrink_aniso(v1, tau).w, shrink_aniso(v1n, tau).w),
+                         csub(shrink_aniso(v2, tau).w, shrink_aniso(v2n, tau).w));   // D^T (z - u)
+  const float2 b = A.bpk[qx + o];
+  rout[qx + o] = make_float2(b.x + rho * dt.x, b.y + rho * dt.y);
+}
+
+// ---- backward sweep (the stencil of k_dim1_bwd; R = rbar_k, spatial) ---------------------------------------------
+//   mode 0 / 1: bbar (+)= R (mode 0) ; vbar_{k-1} stored ; xbar_{k-1} = D^T vbar_{k-1} -> xout ; rhobar / taubar sums
+//   mode 2: isotropic pass A: bbar (+)= R ; ip_out += <q, v_{k-1}>
+__global__ void __launch_bounds__(GK_NT) gk_sweep_bwd(Dim1BwdArgs A, const float2* R, float2* xout, int M, int Q, int mode,
+                                                      int has_vbar) {
+  const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
+  Pix p;
+  const bool live = gk_pix(idx, M, A.N, Q, p);
+  double racc = 0.0, tacc = 0.0;
+  int grp = 0;
+  if (live) {
+    grp = p.q / A.pm.Qg;
+    const float rho = A.rho[grp], tau = A.lambda[grp] / rho;
+    const size_t q1 = ((size_t)p.q * 2 + 0) * p.plane, q2 = ((size_t)p.q * 2 + 1) * p.plane, qx = (size_t)p.q * p.plane;
+    const size_t o = p.o, oj = (size_t)p.jp1 * M + p.i, oi = (size_t)p.j * M + p.ip1;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    const float2 r0 = R[qx + o];
+    auto E = [&](size_t base, size_t off) { return has_vbar ? A.vbar_in[base + off] : zero2; };
+    const float2 d1 = csub(r0, R[qx + (size_t)p.jm1 * M + p.i]), d2 = csub(r0, R[qx + (size_t)p.j * M + p.im1]);
+    if (mode != 1) A.bbar[qx + o] = A.first ? r0 : cadd(A.bbar[qx + o], r0);
+    if (mode == 2) {
+      const float2 qa = csub(make_float2(2.f * rho * d1.x, 2.f * rho * d1.y), E(q1, o));
+      const float2 qb = csub(make_float2(2.f * rho * d2.x, 2.f * rho * d2.y), E(q2, o));
+      const float2 va = A.vck[q1 + o], vb = A.vck[q2 + o];
+      atomicAdd(A.ip_out + (size_t)grp * p.plane + o, qa.x * va.x + qa.y * va.y + qb.x * vb.x + qb.y * vb.y);
+    } else {
+      const float2 d1n = csub(R[qx + oj], r0), d2n = csub(R[qx + oi], r0);   // channel 1 at (i,j+1), channel 2 at (i+1,j)
+      float2 n1, n2, n1n, n2n;
+      if (mode == 0) {
+        n1 = bwd_point(d1, A.vck[q1 + o], E(q1, o), rho, tau, true, racc, tacc);
+        n2 = bwd_point(d2, A.vck[q2 + o], E(q2, o), rho, tau, true, racc, tacc);
+        n1n = bwd_point(d1n, A.vck[q1 + oj], E(q1, oj), rho, tau, false, racc, tacc);
+        n2n = bwd_point(d2n, A.vck[q2 + oi], E(q2, oi), rho, tau, false, racc, tacc);
+      } else {
+        const bool pre = A.sc != nullptr;
+        const bool tau_owner = (p.q % A.pm.Qg) == 0 && A.count_tau != 0;
+        auto PIX = [&](size_t off, bool count) {
+          if (pre) return A.sc[(size_t)grp * p.plane + off];
+          float s_, c_, t_;
+          iso_pix(A.nsq[(size_t)grp * p.plane + off], A.ip[(size_t)grp * p.plane + off], tau, s_, c_, t_);
+          if (count && tau_owner) tacc -= (double)t_;
+          return make_float2(s_, c_);
+        };
+        const float2 s0 = PIX(o, true), sj = PIX(oj, false), si = PIX(oi, false);
+        n1 = iso_bwd_full(d1, A.vck[q1 + o], E(q1, o), rho, s0, true, racc);
+        n2 = iso_bwd_full(d2, A.vck[q2 + o], E(q2, o), rho, s0, true, racc);
+        n1n = iso_bwd_full(d1n, A.vck[q1 + oj], E(q1, oj), rho, sj, false, racc);
+        n2n = iso_bwd_full(d2n, A.vck[q2 + oi], E(q2, oi), rho, si, false, racc);
+      }
+      A.vbar_out[q1 + o] = n1;
+      A.vbar_out[q2 + o] = n2;
+      xout[qx + o] = cadd(csub(n1, n1n), csub(n2, n2n));   // xbar_{k-1} = D^T vbar_{k-1}
+    }
+  }
+  if (mode == 2) return;
+  // scalar partial sums: per block when blocks cannot straddle groups, else per thread
+  const size_t per_group = (size_t)A.pm.Qg * M * A.N;
+  if (per_group % GK_NT == 0) {
+    const double rs = block_sum(racc), ts = block_sum(tacc);
+    if (threadIdx.x == 0) {
+      const int g0 = (int)(((size_t)blockIdx.x * GK_NT) / per_group);
+      atomicAdd(A.acc + 8 * g0 + 0, rs);
+      atomicAdd(A.acc + 8 * g0 + 1, ts);
+    }
+  } else if (live) {
+    if (racc != 0.0) atomicAdd(A.acc + 8 * grp + 0, racc);
+    if (tacc != 0.0) atomicAdd(A.acc + 8 * grp + 1, tacc);
+  }
+}
+
+// ---- last backward step (k_dim1_bwd_last): bbar_total = bbar + rbar_1 -> spectrum input (mode 0) or ybar (mode 1) ----
+__global__ void __launch_bounds__(GK_NT) gk_bwd_last(Dim1BwdArgs A, const float2* R, float2* xout, int M, int Q, int mode) {
+  const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
+  Pix p;
+  if (!gk_pix(idx, M, A.N, Q, p)) return;
+  float2 v = R[idx];
+  if (!A.first) v = cadd(v, A.bbar[idx]);
+  if (mode == 0) {
+    xout[idx] = v;
+    return;
+  }
+  const long ia = pm_in(A.pm, p.q, 0), ib = pm_in(A.pm, p.q, 1);
+  if (A.pm.G > 1 && A.pm.in_gstride == 0) {
+    atomicAdd(A.ybar + (size_t)ia * p.plane + p.o, v.x);
+    if (ib >= 0) atomicAdd(A.ybar + (size_t)ib * p.plane + p.o, v.y);
+  } else {
+    A.ybar[(size_t)ia * p.plane + p.o] = v.x;
+    if (ib >= 0) A.ybar[(size_t)ib * p.plane + p.o] = v.y;
+  }
+}
+
+}  // namespace admmtv

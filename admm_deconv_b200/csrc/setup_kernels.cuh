@@ -73,7 +73,7 @@ static __global__ void k_setup_psf_dim1(const float* __restrict__ h, int kh, int
 // sig [p2][p1] = Sigma (only written when sig != nullptr; the backward needs it)
 // (p1,p2) are storage positions; (k1,k2) = pos_to_freq of them.
 static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int kw, int M, int N,
-                                      const float* __restrict__ rho_p, float* ctab, float2* ktab, float2* sig) {
+                                      const float* __restrict__ rho_p, float* ctab, float2* ktab, float2* sig, int planned) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
   {  // blockIdx.y = group: its own rho, PSF spectrum scratch and tables
@@ -85,7 +85,7 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
     if (sig) sig += grp * (size_t)M * N;
   }
   const int p1 = idx % M, p2 = idx / M;
-  const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
+  const int k1 = pos_to_freq(M, p1, planned != 0), k2 = pos_to_freq(N, p2, planned != 0);
   double sr = 1.0, si = 0.0;
   if (kh > 0) {
     sr = 0.0;
@@ -140,15 +140,19 @@ static __global__ void k_iso_scale(const float* __restrict__ nsq, const float* _
 static __global__ void k_iso_coef(const float* __restrict__ nsq, float* __restrict__ ip, const float* __restrict__ lambda,
                                   const float* __restrict__ rho, float2* __restrict__ sc, double* acc, int npix,
                                   int count_tau) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // npix is a multiple of the block size
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i0 < npix;
+  const int i = live ? i0 : 0;   // every thread takes part in the block reduction
   const int g = blockIdx.y;
   const float tau = lambda[g] / rho[g];
   const float n = sqrtf(nsq[(size_t)g * npix + i]);
   const float p = ip[(size_t)g * npix + i];
-  ip[(size_t)g * npix + i] = 0.f;
-  const bool act = n > tau;
-  const float s = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
-  sc[(size_t)g * npix + i] = make_float2(s, act ? tau * p / (n * n * n) : 0.f);
+  const bool act = live && n > tau;
+  if (live) {
+    ip[(size_t)g * npix + i] = 0.f;
+    const float s = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
+    sc[(size_t)g * npix + i] = make_float2(s, act ? tau * p / (n * n * n) : 0.f);
+  }
   const double tot = block_sum(act ? (double)(p / n) : 0.0);
   if (threadIdx.x == 0 && count_tau) atomicAdd(acc + 8 * g + 1, -tot);
 }
@@ -161,8 +165,10 @@ static __global__ void k_iso_coef(const float* __restrict__ nsq, float* __restri
 // ------------------------------------------------------------------------------------------
 static __global__ void k_grad_tables(const float* __restrict__ gacc, const float2* __restrict__ pacc,
                                      const float* __restrict__ ctab, const float2* __restrict__ sig, int kh, int kw,
-                                     int M, int N, int use_spatial, double2* Wn, double* acc) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // M*N is a multiple of the block size
+                                     int M, int N, int use_spatial, double2* Wn, double* acc, int planned) {
+  const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = idx0 < M * N;
+  const int idx = live ? idx0 : 0;   // every thread takes part in the block reduction
   {  // blockIdx.y = group
     const size_t go = (size_t)blockIdx.y * M * N;
     gacc += go; ctab += go;
@@ -172,7 +178,7 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
     acc += 8 * blockIdx.y;
   }
   const int p1 = idx % M, p2 = idx / M;
-  const int k1 = pos_to_freq(M, p1), k2 = pos_to_freq(N, p2);
+  const int k1 = pos_to_freq(M, p1, planned != 0), k2 = pos_to_freq(N, p2, planned != 0);
   const double mn = (double)M * (double)N;
   const double C = (double)ctab[idx] * mn;
   const double Sbar = -((double)gacc[idx] / mn) * C * C;
@@ -180,9 +186,9 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
   sincospi((double)k2 / N, &s2, &c2);
   sincospi((double)k1 / M, &s1, &c1);
   const double lap = 4.0 * s2 * s2 + 4.0 * s1 * s1;
-  const double tot = block_sum(Sbar * lap);
+  const double tot = block_sum(live ? Sbar * lap : 0.0);
   if (threadIdx.x == 0) atomicAdd(acc + 3, tot);
-  if (kh > 0) {
+  if (kh > 0 && live) {
     const float2 sg = sig[idx];
     double wr = 2.0 * Sbar * (double)sg.x, wi = 2.0 * Sbar * (double)sg.y;
     if (use_spatial) {

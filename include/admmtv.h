@@ -58,8 +58,10 @@ enum {
   ADMMTV_OK = 0,
   ADMMTV_ERR_NULL = -1,
   ADMMTV_ERR_SHAPE = -2,        /* non-positive dims, kernel larger than image, ... */
-  ADMMTV_ERR_UNSUPPORTED = -3,  /* M or N not a supported FFT length: 32, 64, ..., 4096 or
-                                 * 96, 160, 192, 320, 384, 480, 640, 768, 960, 1280, 1536, 1920 */
+  ADMMTV_ERR_UNSUPPORTED = -3,  /* M or N above 4096.  Every size 1..4096 is accepted (the reference's FFTW path takes
+                                 * any size, ops.jl:26,86): when both M and N are planned FFT lengths -- 32, 64, ..., 4096
+                                 * or 96, 160, 192, 320, 384, 480, 640, 768, 960, 1280, 1536, 1920 -- the tuned fused
+                                 * kernels run; any other size takes the generic kernels (same results, slower) */
   ADMMTV_ERR_ITERS = -4,
   ADMMTV_ERR_ENUM = -5,
   ADMMTV_ERR_ALIGN = -6,        /* workspace / checkpoint not 256-byte aligned */

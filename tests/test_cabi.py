@@ -69,7 +69,8 @@ def test_desc_layout_matches_header():
     "kw,code",
     [
         (dict(), 0),
-        (dict(M=48), -3), (dict(N=16), -3), (dict(M=8192), -3), (dict(M=224), -3), (dict(M=96, N=1920), 0),
+        (dict(M=48), 0), (dict(N=16), 0), (dict(M=8192), -3), (dict(M=224), 0), (dict(M=96, N=1920), 0), (dict(M=481, N=321), 0),
+        (dict(N=4097), -3),
         (dict(M=0), -2), (dict(kh=3, kw=0), -2), (dict(kh=65, kw=3, M=64), -2),
         (dict(iters=0), -4),
         (dict(iso=2), -5), (dict(activation=7), -5), (dict(flags=128), -5),

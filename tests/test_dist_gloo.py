@@ -93,7 +93,7 @@ def _iso_worker(rank, world, port, out, iso_flag):
         from admm_deconv_b200 import _lib
         torch.set_num_threads(1)
         lib = E.emu_lib()
-        M, N, P, B, K = 32, 32, 2, 3, 4
+        M, N, P, B, K = 32, 32, 2, 3, 3
         y, h, g = make_case(M, N, P, B, 3, 3, 77)
         xbar = torch.from_numpy(np.random.default_rng(5).standard_normal((M, N, P, B)))
         lo, hi = D.shard_range(B, rank, world)
@@ -128,7 +128,7 @@ def test_two_rank_global_isotropic_equals_single_device(iso_flag):
     port = _free_port()
     out = mp.Manager().dict()
     mp.spawn(_iso_worker, args=(world, port, out, iso_flag), nprocs=world, join=True)
-    M, N, P, B, K = 32, 32, 2, 3, 4
+    M, N, P, B, K = 32, 32, 2, 3, 3
     y, h, g = make_case(M, N, P, B, 3, 3, 77)
     xbar = torch.from_numpy(np.random.default_rng(5).standard_normal((M, N, P, B)))
     y32, h32 = y.float().double(), h.float().double()

@@ -76,3 +76,17 @@ def test_emu_backward_mixed_radix(be, iso):
     y, h, _ = make_case(96, 160, 3, 1, 5, 4, 7)
     xbar = torch.from_numpy(np.random.default_rng(1).standard_normal((96, 160, 3, 1)))
     check_backward(be, y, h, 0.05, 0.3, iso, 3, xbar, tol=1e-5, tol_scalar=2e-4)
+
+
+# ---- sizes without a register-FFT plan (generic_kernels.cuh) ---------------------------------------------------------
+@pytest.mark.parametrize(
+    "M,N,P,B,kh,kw,K,iso,act,bias,flags",
+    [(20, 24, 1, 2, 3, 3, 4, False, "identity", None, 0), (33, 17, 3, 1, 5, 4, 3, False, "relu1", 0.02, 0),
+     (7, 5, 1, 1, 0, 0, 3, False, "identity", None, 0), (20, 24, 2, 2, 3, 3, 4, True, "identity", None, 1 | 16),
+     (31, 18, 1, 3, 0, 0, 3, True, "identity", None, 1 | 32), (30, 32, 1, 1, 3, 3, 3, False, "relu", None, 2)],
+)
+def test_emu_backward_generic_sizes(be, M, N, P, B, kh, kw, K, iso, act, bias, flags):
+    y, h, _ = make_case(M, N, P, B, kh, kw, 9 + M)
+    xbar = torch.from_numpy(np.random.default_rng(K).standard_normal((M, N, P, B)))
+    check_backward(be, y, h, 0.05, 0.3, iso, K, xbar, act, bias, 0.0, flags, tol=1e-5, tol_scalar=2e-4,
+                   tol_e2e=1e-4 if iso else 1e-3)

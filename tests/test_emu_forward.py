@@ -94,3 +94,22 @@ def test_emu_mixed_radix_lengths(emu, M, N):
     from parity import check_forward
     y, h, _ = make_case(M, N, 1, 2, 3, 3, 50 + M + N)
     check_forward(harness.EmuBackend(emu), y, h, 0.05, 0.3, False, 3)
+
+
+# ---- sizes without a register-FFT plan: the generic kernels (generic_kernels.cuh), same C ABI -----------------------
+@pytest.mark.parametrize(
+    "M,N,P,B,kh,kw,K,iso",
+    [(20, 24, 1, 2, 3, 3, 4, False), (33, 17, 3, 1, 5, 4, 3, False), (7, 5, 1, 1, 0, 0, 3, False), (31, 64, 1, 2, 3, 3, 3, False),
+     (20, 24, 2, 2, 3, 3, 4, True), (64, 50, 1, 3, 0, 0, 3, True), (3, 9, 1, 1, 0, 0, 2, False)],
+)
+def test_emu_forward_generic_sizes(emu, M, N, P, B, kh, kw, K, iso):
+    import harness
+    from cases import make_case, rel_l2
+    from oracle import admm_tv_oracle as O
+    be = harness.EmuBackend(emu)
+    y, h, _ = make_case(M, N, P, B, kh, kw, 5 + M)
+    f = be.forward(y.numpy(), 0.05, 0.3, None if h is None else h.numpy()[:, :, 0, 0], iso, K)
+    x = torch.from_numpy(f["x"].get()).double()
+    l = torch.tensor([0.05], dtype=torch.float32).double(); r = torch.tensor([0.3], dtype=torch.float32).double()
+    xo = O.tvd_fft_cpu(y.float().double(), l, r, None if h is None else h.float().double(), iso, K)
+    assert rel_l2(x, xo) <= 1e-5

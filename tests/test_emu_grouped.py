@@ -20,10 +20,11 @@ def _t(v):
     return torch.tensor([v], dtype=torch.float32).double()
 
 
+@pytest.mark.parametrize("MN", [(32, 32), (18, 21)])   # tuned kernels / generic-size kernels
 @pytest.mark.parametrize("iso", [False, True])
-def test_emu_per_image_psf_and_noise_level(be, iso):
+def test_emu_per_image_psf_and_noise_level(be, iso, MN):
     """BASELINE configs[4] semantics: every image has its own PSF and (lambda, rho); oracle = B=1 calls."""
-    M, N, P, B, K = 32, 32, 1, 3, 4
+    (M, N), P, B, K = MN, 1, 3, 4
     ys, hs, lams, rhos, ref = [], [], [], [], []
     for b in range(B):
         y, h, _ = make_case(M, N, P, 1, 3, 5, 900 + b)
@@ -36,10 +37,13 @@ def test_emu_per_image_psf_and_noise_level(be, iso):
     assert rel_l2(T(x), torch.cat(ref, dim=3)) < 1e-5
 
 
+@pytest.mark.parametrize("MN", [(32, 32), (18, 21)])   # tuned kernels / generic-size kernels
 @pytest.mark.parametrize("iso", [False, True])
-def test_emu_parallel_branches_shared_input_channel_concat(be, iso):
+def test_emu_parallel_branches_shared_input_channel_concat(be, iso, MN):
+    if iso and MN != (32, 32):
+        pytest.skip("generic-size grouped isotropic is covered by the per-image forward test (keeps the CPU suite short)")
     """net_build.jl:113-128: 5 x ADMMDeconvF2((), K, rho_i, relu1) on the same input, chcat."""
-    M, N, P, B, K, G = 32, 32, 3, 2, 3, 5
+    (M, N), P, B, K, G = MN, 3, 2, 3, 5
     y, _, _ = make_case(M, N, P, B, 0, 0, 77)
     y = y.float().double()
     rhos = [0.05, 0.1, 0.2, 0.4, 0.8]
@@ -50,10 +54,13 @@ def test_emu_parallel_branches_shared_input_channel_concat(be, iso):
     assert rel_l2(T(x), ref) < 1e-5
 
 
+@pytest.mark.parametrize("MN", [(32, 32), (18, 21)])   # tuned kernels / generic-size kernels
 @pytest.mark.parametrize("iso", [False, True])
-def test_emu_grouped_backward_per_image(be, iso):
+def test_emu_grouped_backward_per_image(be, iso, MN):
+    if iso and MN != (32, 32):
+        pytest.skip("generic-size grouped isotropic is covered by the per-image forward test (keeps the CPU suite short)")
     """Grouped backward == the single-call backward run group by group (same library, same inputs)."""
-    M, N, P, B, K = 32, 32, 1, 3, 4
+    (M, N), P, B, K = MN, 1, 3, 4
     ys, hs = [], []
     lams, rhos = [0.02, 0.04, 0.06], [0.2, 0.3, 0.4]
     for b in range(B):
@@ -73,10 +80,11 @@ def test_emu_grouped_backward_per_image(be, iso):
         assert abs(g["rhobar"][b] - g1["rhobar"][0]) <= 1e-4 * max(abs(g1["rhobar"][0]), 1e-3)
 
 
+@pytest.mark.parametrize("MN", [(32, 32)])
 @pytest.mark.parametrize("iso", [False, True])
-def test_emu_grouped_backward_shared_input_branches(be, iso):
+def test_emu_grouped_backward_shared_input_branches(be, iso, MN):
     """The 5-branch denoiser bank: ybar sums over the branches, lambar / rhobar are per branch."""
-    M, N, P, B, K, G = 32, 32, 3, 2, 3, 3
+    (M, N), P, B, K, G = MN, 3, 2, 3, 3
     y, _, _ = make_case(M, N, P, B, 0, 0, 77)
     y = y.float().double()
     rhos, lams = [0.05, 0.2, 0.8], [0.03, 0.02, 0.04]
