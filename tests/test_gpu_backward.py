@@ -192,3 +192,14 @@ def test_backward_mixed_radix(be, M, N, iso):
     xbar = 2.0 * (y - g) / y.numel() * 1e3
     r = check_backward(be, y, h, 0.0041, 0.021, iso, 6, xbar, tol=1e-5, tol_scalar=2e-4)
     print(r)
+
+
+# ---- any image size: generic-size kernels --------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,P,B,kh,kw,K,iso,flags", [(33, 17, 3, 1, 5, 4, 3, False, 0), (100, 100, 3, 2, 7, 7, 8, False, 0),
+                                                       (225, 64, 1, 2, 5, 5, 6, True, 1 | 16), (127, 131, 1, 2, 5, 5, 6, True, 1 | 32),
+                                                       (321, 481, 3, 1, 9, 9, 5, False, 0)])
+def test_backward_any_size(be, M, N, P, B, kh, kw, K, iso, flags):
+    y, h, g = make_case(M, N, P, B, kh, kw, 900 + M + N)
+    xbar = 2.0 * (y - g) / y.numel() * 1e3
+    r = check_backward(be, y, h, 0.0041, 0.021, iso, K, xbar, flags=flags, tol=1e-5, tol_scalar=5e-4)   # teacher-forced (mask flips make end-to-end looser); rhobar is a cancelling sum and the direct prime-length DFTs add sqrt(L) rounding
+    print(r)

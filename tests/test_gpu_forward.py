@@ -145,7 +145,7 @@ def test_host_buffer_entry_point():
 
 def test_error_codes_on_bad_shapes():
     d0 = dev()
-    y = torch.zeros(1, 1, 48, 64, device=d0)
+    y = torch.zeros(1, 1, 48, 4100, device=d0)      # dim 1 (M) = 4100 > 4096
     with pytest.raises(A.AdmmTvError) as e:
         A.tvd_fft(y, torch.ones(1, device=d0), torch.ones(1, device=d0), None, False, 2)
     assert e.value.code == -3
@@ -317,3 +317,32 @@ def test_full_cfg2_size_shift_equivariance_and_fixed_point():
     c = torch.full((B, P, N, M), 0.37, device=d0)
     xc = A.tvd_fft(c, lam, rho, h, False, K)
     assert float((xc - 0.37).abs().max()) < 2e-5
+
+
+# ---- any image size (the reference's FFTW path takes every size, ops.jl:26,86): generic-size kernels ---------------
+@pytest.mark.parametrize(
+    "M,N,P,B,kh,kw,K,iso",
+    [(20, 24, 1, 2, 3, 3, 4, False), (33, 17, 3, 1, 5, 4, 3, False), (7, 5, 1, 1, 0, 0, 3, False), (100, 100, 3, 2, 7, 7, 20, False),
+     (321, 481, 3, 1, 9, 9, 10, False), (225, 64, 1, 2, 5, 5, 10, True), (127, 131, 1, 2, 5, 5, 10, False),   # prime lengths
+     (64, 50, 1, 3, 0, 0, 5, True), (360, 640, 3, 1, 15, 15, 5, False)],
+)
+def test_forward_any_size_vs_oracle(M, N, P, B, kh, kw, K, iso):
+    y, h, _ = make_case(M, N, P, B, kh, kw, 300 + M + N, psf="random")
+    x = run_gpu(y, h, 0.0041, 0.021, iso, K)
+    xo = oracle(y, h, 0.0041, 0.021, iso, K, fast=M * N > 40000)
+    assert rel_l2(x.double(), xo) <= TOL
+
+
+def test_hd_frame_1080x1920_properties():
+    """A size the oracle would take minutes on: shift equivariance and the constant fixed point (size-independent)."""
+    d0 = dev()
+    torch.manual_seed(0)
+    y = torch.nn.functional.avg_pool2d(torch.rand(1, 1, 1920, 1080, device=d0), 5, 1, 2)   # image-like, not white noise
+    g1 = torch.exp(-0.5 * (torch.arange(5, device=d0) - 2.0) ** 2 / 1.5 ** 2)
+    h = torch.outer(g1, g1).reshape(1, 1, 5, 5); h /= h.sum()
+    lam = torch.tensor([0.0041], device=d0); rho = torch.tensor([0.021], device=d0)
+    x = A.tvd_fft(y, lam, rho, h, False, 4)
+    xs = A.tvd_fft(torch.roll(y, (37, 11), (2, 3)).contiguous(), lam, rho, h, False, 4)
+    assert rel_l2(xs.cpu(), torch.roll(x, (37, 11), (2, 3)).cpu()) <= 2e-5    # two fp32 results, each within 1e-5 of exact
+    c = A.tvd_fft(torch.full_like(y, 0.37), lam, rho, h, False, 4)
+    assert float((c - 0.37).abs().max()) <= 1e-5
