@@ -33,9 +33,12 @@ ADMMTV_DI float2 cfma(float2 acc, float2 a, float2 w) {
 }
 
 // In-place DFT of `nl` lines xs[l*L .. l*L+L) held in shared memory (natural order in and out), scratch ys of the
-// same size, tw[n] = exp(-2 pi i n / L) in shared memory; `inv` conjugates the twiddles (no 1/L: the tables carry
-// the normalisation).  Every thread of the block must call; ends with a barrier.
-ADMMTV_DI void line_dft(float2* xs, float2* ys, const float2* tw, int L, int L1, int L2, int nl, bool inv, int tid) {
+// same size, tw[n] = exp(-2 pi i n / L) and twb[m] = tw[L1 m] (m < L2) in shared memory; `inv` conjugates the twiddles
+// (no 1/L: the tables carry the normalisation).  Every thread of the block must call; ends with a barrier.
+// Thread mappings keep shared-memory reads contiguous or broadcast within a warp: step A walks n2 (contiguous x, one
+// twiddle per k1), step B walks k2 (one y per k1 broadcast, twiddles from the compact table twb).
+ADMMTV_DI void line_dft(float2* xs, float2* ys, const float2* tw, const float2* twb, int L, int L1, int L2, int nl, bool inv,
+                        int tid) {
   const float sg = inv ? -1.f : 1.f;
   // ys[k1*L2 + n2] = W^(n2 k1) * sum_n1 xs[L2 n1 + n2] W^(L2 n1 k1)
   for (int e = tid; e < nl * L; e += GK_NT) {
@@ -54,20 +57,19 @@ ADMMTV_DI void line_dft(float2* xs, float2* ys, const float2* tw, int L, int L1,
     ys[e] = cmul(acc, make_float2(w.x, sg * w.y));
   }
   __syncthreads();
-  // xs[k1 + L1 k2] = sum_n2 ys[k1*L2 + n2] W^(L1 n2 k2)
+  // xs[k1 + L1 k2] = sum_n2 ys[k1*L2 + n2] W_L2^(n2 k2),  W_L2^m = twb[m]
   for (int e = tid; e < nl * L; e += GK_NT) {
-    const int l = e / L, r = e % L, k1 = r % L1, k2 = r / L1;
+    const int l = e / L, r = e % L, k1 = r / L2, k2 = r % L2;
     const float2* y = ys + l * L + k1 * L2;
     float2 acc = make_float2(0.f, 0.f);
-    const int step = (int)(((long long)L1 * k2) % L);
-    int idx = 0;
+    int m = 0;
     for (int n2 = 0; n2 < L2; ++n2) {
-      const float2 w = tw[idx];
+      const float2 w = twb[m];
       acc = cfma(acc, y[n2], make_float2(w.x, sg * w.y));
-      idx += step;
-      if (idx >= L) idx -= L;
+      m += k2;
+      if (m >= L2) m -= L2;
     }
-    xs[e] = acc;
+    xs[l * L + k1 + L1 * k2] = acc;
   }
   __syncthreads();
 }
@@ -83,15 +85,17 @@ struct GDft1Args {
 __global__ void __launch_bounds__(GK_NT) gk_dft1(GDft1Args A) {
   ADMMTV_DYN_SMEM(float2, sm);
   float2* tw = sm;
-  float2* xs = sm + A.M;
+  float2* twb = sm + A.M;
+  float2* xs = twb + A.M2;
   float2* ys = xs + (size_t)A.LB * A.M;
   const int tid = threadIdx.x;
   const long long l0 = (long long)blockIdx.x * A.LB;
   const int nl = (int)(A.nlines - l0 < A.LB ? A.nlines - l0 : A.LB);
   for (int e = tid; e < A.M; e += GK_NT) tw[e] = A.tw[e];
+  for (int e = tid; e < A.M2; e += GK_NT) twb[e] = A.tw[e * A.M1];
   for (int e = tid; e < nl * A.M; e += GK_NT) xs[e] = A.in[l0 * A.M + e];
   __syncthreads();
-  line_dft(xs, ys, tw, A.M, A.M1, A.M2, nl, A.inv != 0, tid);
+  line_dft(xs, ys, tw, twb, A.M, A.M1, A.M2, nl, A.inv != 0, tid);
   for (int e = tid; e < nl * A.M; e += GK_NT) A.out[l0 * A.M + e] = xs[e];
 }
 
@@ -102,7 +106,8 @@ struct GDim2Cfg {
 __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
   ADMMTV_DYN_SMEM(float2, sm);
   float2* tw = sm;
-  float2* xs = sm + C.N;
+  float2* twb = sm + C.N;
+  float2* xs = twb + C.N2;
   float2* ys = xs + (size_t)C.TR * C.N;
   const int tid = threadIdx.x, M = A.M, N = C.N, TR = C.TR;
   const int row_tiles = (M + TR - 1) / TR;
@@ -111,12 +116,13 @@ __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
   const size_t qoff = (size_t)q * N * M;
   const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;
   for (int e = tid; e < N; e += GK_NT) tw[e] = A.twN[e];
+  for (int e = tid; e < C.N2; e += GK_NT) twb[e] = A.twN[e * C.N1];
   for (int e = tid; e < nr * N; e += GK_NT) {
     const int ll = e % nr, col = e / nr;
     xs[ll * N + col] = A.in[qoff + (size_t)col * M + i0 + ll];
   }
   __syncthreads();
-  line_dft(xs, ys, tw, N, C.N1, C.N2, nr, false, tid);
+  line_dft(xs, ys, tw, twb, N, C.N1, C.N2, nr, false, tid);
   for (int e = tid; e < nr * N; e += GK_NT) {
     const int ll = e % nr, col = e / nr;
     const size_t g = (size_t)col * M + i0 + ll;
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
   }
   if (C.fwd_only) return;
   __syncthreads();
-  line_dft(xs, ys, tw, N, C.N1, C.N2, nr, true, tid);
+  line_dft(xs, ys, tw, twb, N, C.N1, C.N2, nr, true, tid);
   for (int e = tid; e < nr * N; e += GK_NT) {
     const int ll = e % nr, col = e / nr;
     A.out[qoff + (size_t)col * M + i0 + ll] = xs[ll * N + col];
@@ -191,11 +197,13 @@ __global__ void __launch_bounds__(GK_NT) gk_pack(PackArgs A, int M, int Q, int m
     }
   }
   if (mode == 1 && A.bias_acc) {
-    // a block may straddle two groups only when a group is smaller than a block: fall back to per-thread atomics then
-    const size_t per_group = (size_t)A.pm.Qg * M * A.N;
-    if (per_group % GK_NT == 0) {
+    // one atomic per block when the whole block lies in one group, else (at most G-1 blocks) one per thread
+    const size_t per_group = (size_t)A.pm.Qg * M * A.N, first = (size_t)blockIdx.x * GK_NT;
+    size_t last = first + GK_NT - 1;
+    if (last >= per_group * A.pm.G) last = per_group * A.pm.G - 1;
+    if (first / per_group == last / per_group) {
       const double tot = block_sum(bsum);
-      if (threadIdx.x == 0) atomicAdd(A.bias_acc + 8 * (int)(((size_t)blockIdx.x * GK_NT) / per_group), tot);
+      if (threadIdx.x == 0) atomicAdd(A.bias_acc + 8 * (int)(first / per_group), tot);
     } else if (bsum != 0.0) {
       atomicAdd(A.bias_acc + 8 * grp, bsum);
     }
@@ -329,14 +337,15 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_bwd(Dim1BwdArgs A, const float
     }
   }
   if (mode == 2) return;
-  // scalar partial sums: per block when blocks cannot straddle groups, else per thread
-  const size_t per_group = (size_t)A.pm.Qg * M * A.N;
-  if (per_group % GK_NT == 0) {
+  // scalar partial sums: one atomic pair per block when the whole block lies in one group, else (at most G-1 blocks) per thread
+  const size_t per_group = (size_t)A.pm.Qg * M * A.N, first = (size_t)blockIdx.x * GK_NT;
+  size_t last = first + GK_NT - 1;
+  if (last >= per_group * A.pm.G) last = per_group * A.pm.G - 1;
+  if (first / per_group == last / per_group) {
     const double rs = block_sum(racc), ts = block_sum(tacc);
     if (threadIdx.x == 0) {
-      const int g0 = (int)(((size_t)blockIdx.x * GK_NT) / per_group);
-      atomicAdd(A.acc + 8 * g0 + 0, rs);
-      atomicAdd(A.acc + 8 * g0 + 1, ts);
+      atomicAdd(A.acc + 8 * (int)(first / per_group) + 0, rs);
+      atomicAdd(A.acc + 8 * (int)(first / per_group) + 1, ts);
     }
   } else if (live) {
     if (racc != 0.0) atomicAdd(A.acc + 8 * grp + 0, racc);

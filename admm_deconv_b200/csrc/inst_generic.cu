@@ -20,7 +20,7 @@ static int gk_run_dft1(const Geom& g, const float2* in, float2* out, const float
   GDft1Args a{};
   a.in = in; a.out = out; a.tw = tw; a.M = g.M; a.M1 = small_factor(g.M); a.M2 = g.M / a.M1;
   a.LB = gk_lines_dim1(g.M); a.inv = inv ? 1 : 0; a.nlines = (long long)g.N * g.Q;
-  const size_t smem = (size_t)(1 + 2 * a.LB) * g.M * sizeof(float2);
+  const size_t smem = ((size_t)(1 + 2 * a.LB) * g.M + a.M2) * sizeof(float2);
   int rc = gk_set_smem((const void*)gk_dft1, smem);
   if (rc) return rc;
   const long long nblk = (a.nlines + a.LB - 1) / a.LB;
@@ -102,7 +102,7 @@ int Dim2Launch<0>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaStr
     case D2_K: c.mul = 2; break;
     default: return -5;
   }
-  const size_t smem = (size_t)(1 + 2 * c.TR) * g.N * sizeof(float2);
+  const size_t smem = ((size_t)(1 + 2 * c.TR) * g.N + c.N2) * sizeof(float2);
   int rc = gk_set_smem((const void*)gk_dim2, smem);
   if (rc) return rc;
   const size_t nblk = (size_t)((g.M + c.TR - 1) / c.TR) * g.Q;

@@ -44,6 +44,10 @@ WORKLOADS = {
     "denoiser5": dict(B=32, P=3, N=256, M=256, k=0, iters=50, mode="grouped", groups=5, iso=True,
                       desc="net_build.jl:113-128 get_denoiser: 5 parallel ADMMDeconvF2((),50,rho_i,relu1; iso) branches on the "
                            "same 32 x 256x256 RGB input, channel-concatenated, one grouped call"),
+    "hd1080": dict(B=4, P=3, N=1920, M=1080, k=15, iters=20, mode="fwd",
+                   desc="4 x 1080x1920 RGB frames (1080 has no register-FFT plan: generic-size kernels), motion PSF 15x15, 20 iterations"),
+    "bsd481": dict(B=32, P=3, N=481, M=321, k=9, iters=20, mode="fwd",
+                   desc="32 x 321x481 RGB (BSD500 size; 481 = 13*37: generic-size kernels), motion PSF 9x9, 20 iterations"),
     "vga": dict(B=64, P=3, N=480, M=640, k=15, iters=50, mode="fwd",
                 desc="64 x 640x480 RGB frames (mixed-radix lengths 640 = 5*16*8, 480 = 3*5*8*4), motion PSF 15x15, 50 iterations"),
     "tiny": dict(B=2, P=3, N=64, M=64, k=7, iters=10, mode="fwd", desc="tiny debug workload"),
