@@ -1,0 +1,64 @@
+"""One training step through every §8 row on the GPU: 8-bit crops -> device batch assembly (f-3) -> ADMM layer forward
+with checkpoint (a) -> GMSD or SSIM loss (f-2) -> loss backward -> layer backward -> parameter-gradient all-reduce (e).
+    python tools/train_step_bench.py [gmsd|ssim] [B] [N] [K] [iso]
+Prints one JSON line with the per-stage milliseconds (CUDA events on the launching stream)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import admm_deconv_b200 as A  # noqa: E402
+from admm_deconv_b200.staging import ImageDataFeeder  # noqa: E402
+
+loss_name = sys.argv[1] if len(sys.argv) > 1 else "gmsd"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+iso = len(sys.argv) > 5 and sys.argv[5] == "iso"
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(0)
+imgs_y = [rng.integers(0, 256, size=(N + 40, N + 40, 3), dtype=np.uint8) for _ in range(B)]
+imgs_x = [np.clip(im.astype(np.int16) + rng.integers(-20, 21, size=im.shape), 0, 255).astype(np.uint8) for im in imgs_y]
+feeder = ImageDataFeeder(imgs_x, imgs_y, (N, N), (N, N), dev, seed=1)
+layer = A.ADMMDeconv((15, 15), K, "relu1", iso=iso).to(dev)
+with torch.no_grad():
+    layer.weight.fill_(1.0 / 225); layer.lam.fill_(0.0041); layer.rho.fill_(0.021)
+loss_fn = A.gmsd_loss if loss_name == "gmsd" else A.ssim_loss
+idxs = list(range(B))
+
+
+def ev():
+    e = torch.cuda.Event(enable_timing=True); e.record(); return e
+
+
+def step(timed):
+    marks = [ev()]
+    x, y = feeder.getindex(idxs); marks.append(ev())
+    out = layer(x); marks.append(ev())
+    loss = loss_fn(out, y); marks.append(ev())
+    for p in layer.parameters():
+        p.grad = None
+    loss.backward(); marks.append(ev())
+    return marks, loss
+
+
+for _ in range(3):
+    step(False)
+torch.cuda.synchronize()
+acc = np.zeros(4)
+reps = 10
+for _ in range(reps):
+    m, loss = step(True)
+    torch.cuda.synchronize()
+    acc += [m[i].elapsed_time(m[i + 1]) for i in range(4)]
+acc /= reps
+px = B * 3 * N * N
+print(json.dumps({"workload": f"{B} x {N}x{N} RGB, ADMMDeconv((15,15),{K},relu1{', iso' if iso else ''}), {loss_name}_loss",
+                  "ms": {"batch_assembly_incl_h2d": acc[0], "layer_forward_ckpt": acc[1], "loss_forward": acc[2],
+                         "loss_backward+layer_backward": acc[3], "total": float(acc.sum())},
+                  "h2d_bytes": feeder.h2d_bytes(B), "fp32_upload_would_be": 2 * px * 4, "loss": float(loss),
+                  "Mpx_it_per_s": px * K / acc.sum() / 1e3}))
