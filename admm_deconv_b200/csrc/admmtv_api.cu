@@ -17,13 +17,22 @@ static inline int ilog2(int v) {
   return l;
 }
 
+static int dim2_row_tile(int LN);
 static Geom geom(const admmtv_desc* d) {
   Geom g;
   g.M = d->M; g.N = d->N; g.P = d->P; g.B = d->B;
   g.S = d->P * d->B;
   g.Q = (g.S + 1) / 2;
   g.LM = dim_id(d->M); g.LN = dim_id(d->N);
-  if (g.LM <= 0 || g.LN <= 0) g.LM = g.LN = 0;   // no register-FFT plan for one of the lengths: generic kernels for both
+  if (g.LM <= 0 || g.LN <= 0) {
+    // No register-FFT plan for one of the lengths.  The dim-1 kernels (tiles of whole columns) go generic; the tuned
+    // dim-2 kernel only needs its row tile to divide M (16-byte aligned row pairs), so a planned N keeps it -- e.g.
+    // 720x1280, 1080x1920 frames (Julia (M,N) = (height, width)).
+    g.LM = 0;
+    const int tr = g.LN > 0 ? dim2_row_tile(g.LN) : 0;
+    if (tr <= 0 || d->M % tr != 0) g.LN = 0;
+  }
+  g.planned = (g.LM > 0 ? 1 : 0) | (g.LN > 0 ? 2 : 0);
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
   g.G = d->groups > 1 ? d->groups : 1;
   g.Bg = d->B / g.G;
@@ -171,6 +180,10 @@ static int run_dim2(const Geom& g, Dim2Variant v, const Dim2Args& a, cudaStream_
   ADMMTV_SWITCH_LOG2(g.LN, LN, { return Dim2Launch<LN>::run(g, (int)v, a, st); })
 }
 
+static int dim2_row_tile(int LN) {
+  ADMMTV_SWITCH_LOG2(LN, L, { return Dim2Launch<L>::row_tile(); })
+}
+
 struct DeviceGuard {
   int prev;
   bool ok;
@@ -208,7 +221,7 @@ static int run_setup(const Geom& g, const float* h, const float* rho, float2* tw
   {
     const size_t n = g.plane;
     ADMMTV_LAUNCH(k_setup_tables, dim3((unsigned)((n + 127) / 128), (unsigned)g.G), dim3(128), 0, st, (const double2*)T, g.kh,
-                  g.kw, g.M, g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig, g.LM > 0 ? 1 : 0);
+                  g.kw, g.M, g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig, g.planned);
     ADMMTV_CHECK_LAUNCH();
   }
   return 0;

@@ -30,7 +30,8 @@ ADMMTV_HD inline long pm_out(const PlaneMap& m, int q, int c) {
 }
 
 struct Geom {
-  int M, N, P, B, S, Q, LM, LN, K, kh, kw, nh;
+  int M, N, P, B, S, Q, LM, LN, K, kh, kw, nh;   // LM / LN: size ids (fft_core.cuh dim_id); 0 = generic-size kernels for that pass
+  int planned;   // bit 0: dim-1 spectra in the plan's digit-reversed order (else natural); bit 1: same for dim 2
   int G, Bg, Sg, Qg;  // groups, images / planes / pairs per group (S = G*Sg planes, Q = G*Qg pairs)
   PlaneMap pm;
   size_t plane;  // N*M
@@ -138,6 +139,7 @@ struct Dim1Launch {
 template <int LN>
 struct Dim2Launch {
   static int run(const Geom& g, int variant, const Dim2Args& a, cudaStream_t st);
+  static int row_tile();   // rows per block of the tuned kernel (M must be a multiple of it); 0 for the generic launcher
 };
 
 #define ADMMTV_CHECK_LAUNCH()                      \

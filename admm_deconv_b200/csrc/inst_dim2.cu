@@ -3,6 +3,7 @@
 #include "args.cuh"
 namespace admmtv {
 template <> int Dim2Launch<ADMMTV_INST>::run(const Geom&, int, const Dim2Args&, cudaStream_t) { return -3; }
+template <> int Dim2Launch<ADMMTV_INST>::row_tile() { return 0; }
 }
 #else
 #include "kernels.cuh"
@@ -34,6 +35,9 @@ constexpr int LN = ADMMTV_INST;
 #ifndef ADMMTV_D2_BLOCKS_PER_SM
 #define ADMMTV_D2_BLOCKS_PER_SM 2
 #endif
+
+template <>
+int Dim2Launch<LN>::row_tile() { return Dim2Cfg<LN>::TR; }
 
 template <>
 int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaStream_t st) {

@@ -87,6 +87,9 @@ int Dim1Launch<0>::bwd_last(const Geom& g, int mode, const Dim1BwdArgs& a, cudaS
 }
 
 template <>
+int Dim2Launch<0>::row_tile() { return 0; }
+
+template <>
 int Dim2Launch<0>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaStream_t st) {
   Dim2Args a = a_in;
   a.Q = g.Q;

@@ -85,7 +85,7 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
     if (sig) sig += grp * (size_t)M * N;
   }
   const int p1 = idx % M, p2 = idx / M;
-  const int k1 = pos_to_freq(M, p1, planned != 0), k2 = pos_to_freq(N, p2, planned != 0);
+  const int k1 = pos_to_freq(M, p1, (planned & 1) != 0), k2 = pos_to_freq(N, p2, (planned & 2) != 0);
   double sr = 1.0, si = 0.0;
   if (kh > 0) {
     sr = 0.0;
@@ -178,7 +178,7 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
     acc += 8 * blockIdx.y;
   }
   const int p1 = idx % M, p2 = idx / M;
-  const int k1 = pos_to_freq(M, p1, planned != 0), k2 = pos_to_freq(N, p2, planned != 0);
+  const int k1 = pos_to_freq(M, p1, (planned & 1) != 0), k2 = pos_to_freq(N, p2, (planned & 2) != 0);
   const double mn = (double)M * (double)N;
   const double C = (double)ctab[idx] * mn;
   const double Sbar = -((double)gacc[idx] / mn) * C * C;
