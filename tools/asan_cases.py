@@ -17,3 +17,23 @@ import torch
 h=torch.cat([make_case(32,32,1,1,3,5,900+b)[1][:,:,:,0] for b in range(3)],dim=2)
 x=be.forward_grouped(torch.cat(ys,dim=3).numpy(),[0.02,0.04,0.06],[0.2,0.3,0.4],h.numpy(),False,3,groups=3)
 print('grouped ok')
+
+# sizes without a register-FFT plan (generic kernels), mixed dispatch (generic dim-1 + tuned dim-2), 3-smooth length
+for iso in (False, True):
+    for (M,N,P,B,kh,kw,K) in [(20,24,1,2,3,3,3),(33,17,3,1,5,4,3),(7,5,1,1,0,0,2),(48,32,1,2,3,3,3),(96,32,1,1,3,3,2)]:
+        y,h,_=make_case(M,N,P,B,kh,kw,60+M+K)
+        xbar=torch.from_numpy(np.random.default_rng(K).standard_normal((M,N,P,B)))
+        print('generic',iso,M,N,P,B,kh,kw,K, check_backward(be,y,h,0.05,0.3,iso,K,xbar,act='relu1',bias=0.01,tol=1e-5,tol_scalar=5e-4), flush=True)
+# losses and batch assembly (include/admmtv_loss.h, admmtv_batch.h): ragged tiles
+import test_emu_losses as TL
+lib=be.lib
+for shp in [(70,37,1,2),(16,12,3,2),(5,3,2,1)]:
+    x,yy=TL._images(*shp,3); print('gmsd',shp,TL.run_gmsd(lib,x,yy)[0], flush=True)
+for shp in [(45,70,1,2),(24,20,3,2),(11,11,1,1)]:
+    x,yy=TL._images(*shp,3); print('ssim',shp,TL.run_ssim(lib,x,yy)[0], TL.run_ssim(lib,x,yy,taps=[0.2]*5)[0], flush=True)
+rng=np.random.default_rng(0)
+for (M,N,C,B) in [(40,33,3,2),(7,5,5,1)]:
+    img=rng.integers(0,256,size=(B,M,N,C),dtype=np.uint8); dst=np.asfortranarray(np.zeros((M,N,C,B),np.float32))
+    lib.batch_from_n0f8(M,N,C,B,0,img.ctypes.data,1,C*N,C,M*N*C,dst.ctypes.data)
+    assert np.array_equal(np.array(dst), img.transpose(1,2,3,0).astype(np.float32)/np.float32(255))
+print('losses / batch ok')
