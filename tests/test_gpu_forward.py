@@ -347,3 +347,31 @@ def test_hd_frame_1080x1920_properties():
     assert rel_l2(xs.cpu(), torch.roll(x, (37, 11), (2, 3)).cpu()) <= 2e-5    # two fp32 results, each within 1e-5 of exact
     c = A.tvd_fft(torch.full_like(y, 0.37), lam, rho, h, False, 4)
     assert float((c - 0.37).abs().max()) <= 1e-5
+
+
+def test_edge_sizes_and_psf_as_large_as_the_image():
+    """Smallest planes, an odd plane count (padded pair), a PSF covering the whole image, the longest generic length."""
+    for (M, N, P, B, kh, kw, K, iso) in [(2, 2, 1, 1, 0, 0, 3, False), (3, 2, 1, 3, 3, 2, 3, True), (16, 12, 1, 1, 16, 12, 2, False),
+                                         (32, 32, 1, 1, 32, 32, 2, False), (4095, 33, 1, 1, 3, 3, 2, False), (35, 4094, 1, 1, 3, 3, 2, False)]:
+        y, h, _ = make_case(M, N, P, B, kh, kw, 400 + M + N, psf="random")
+        if h is not None:
+            h = h / h.sum()
+        x = run_gpu(y, h, 0.0041, 0.021, iso, K)
+        xo = oracle(y, h, 0.0041, 0.021, iso, K, fast=M * N > 40000)
+        assert rel_l2(x.double(), xo) <= TOL, (M, N, kh, kw)
+
+
+def test_grouped_per_image_generic_size():
+    """BASELINE configs[4] semantics (per-image PSF / lambda / rho) at a size without a register-FFT plan."""
+    d0 = dev()
+    M, N, B, K = 50, 36, 4, 4
+    ys, hs, refs, lams, rhos = [], [], [], [], []
+    for b in range(B):
+        y, h, _ = make_case(M, N, 1, 1, 3, 5, 700 + b)
+        lams.append(0.01 * (b + 1)); rhos.append(0.05 * (b + 2))
+        ys.append(y); hs.append(h)
+        refs.append(oracle(y, h, lams[-1], rhos[-1], False, K))
+    yt = A.from_julia(torch.cat(ys, dim=3).float()).to(d0)
+    ht = torch.stack([A.from_julia(h.float()).reshape(1, 5, 3) for h in hs]).contiguous().to(d0)     # (G,1,kw,kh)
+    x = A.tvd_fft_grouped(yt, torch.tensor(lams, device=d0), torch.tensor(rhos, device=d0), ht, False, K, groups=B)
+    assert rel_l2(A.to_julia(x.cpu()).double(), torch.cat(refs, dim=3)) <= TOL
