@@ -133,6 +133,24 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_TR9
 #define ADMMTV_TR9 16
 #endif
+#ifndef ADMMTV_TC7
+#define ADMMTV_TC7 10   // 128-row planes: 8 + 2 columns, chunk 4, 8 blocks/SM: dim-1 111 -> 94 us on 1024 x 128^2 (gpurun_out/v4_128b.log)
+#endif
+#ifndef ADMMTV_CHUNK7
+#define ADMMTV_CHUNK7 4
+#endif
+#ifndef ADMMTV_MINB7
+#define ADMMTV_MINB7 8
+#endif
+#ifndef ADMMTV_TR7
+#define ADMMTV_TR7 16
+#endif
+#ifndef ADMMTV_MINB8
+#define ADMMTV_MINB8 3   // 256-row planes: 3 blocks/SM (<= 85 registers): dim-1 48.0 -> 46.0 us on 96 planes of 256^2 (gpurun_out/v6_mb8.log)
+#endif
+#ifndef ADMMTV_TR8
+#define ADMMTV_TR8 16
+#endif
 #ifndef ADMMTV_NT2
 #define ADMMTV_NT2 256
 #endif
@@ -169,13 +187,13 @@ struct Dim1Cfg {
   static constexpr bool POW2 = is_pow2(M);
   static constexpr int NT = !POW2 ? dim1_nt_generic(M)
                                   : (LM <= 8 ? M : (LM == 9 ? ADMMTV_NT9 : (LM == 10 ? 256 : (LM == 11 ? ADMMTV_NT11 : 512))));
-  static constexpr int MINB = LM == 9 ? ADMMTV_MINB9 : 1;
+  static constexpr int MINB = LM == 9 ? ADMMTV_MINB9 : (LM == 7 ? ADMMTV_MINB7 : (LM == 8 ? ADMMTV_MINB8 : 1));
   static constexpr int RPT = M / NT;                  // rows per thread in the stencil sweep
-  static constexpr int CHUNK = LM == 9 ? ADMMTV_CHUNK9 : (LM == 8 ? ADMMTV_CHUNK8 : (RPT >= 8 ? 1 : 8 / RPT));  // columns between barriers
+  static constexpr int CHUNK = LM == 9 ? ADMMTV_CHUNK9 : (LM == 8 ? ADMMTV_CHUNK8 : (LM == 7 ? ADMMTV_CHUNK7 : (RPT >= 8 ? 1 : 8 / RPT)));  // columns between barriers
   static constexpr int CHUNKB = RPT >= 4 ? 1 : 4 / RPT;  // backward sweep: RPT * CHUNKB <= 4 keeps its hoisted loads in registers
   // tile columns including the 2 halo columns
   static constexpr int TC = !POW2 ? dim1_tc_generic(M)
-                                  : (LM <= 7 ? 34 : (LM == 8 ? ADMMTV_TC8 : (LM == 9 ? ADMMTV_TC9 : (LM == 11 ? ADMMTV_TC11 : 6))));
+                                  : (LM <= 6 ? 34 : (LM == 7 ? ADMMTV_TC7 : (LM == 8 ? ADMMTV_TC8 : (LM == 9 ? ADMMTV_TC9 : (LM == 11 ? ADMMTV_TC11 : 6)))));
   static constexpr int CO = TC - 2;                   // output columns per block
   static constexpr size_t SMEM = (size_t)TC * M * sizeof(float2);
   static_assert(M % NT == 0 && NT % 32 == 0, "dim-1 block must tile the column in whole warps");
@@ -773,7 +791,7 @@ template <int LN>
 struct Dim2Cfg {
   static constexpr int N = dim_len(LN);
   static constexpr int TR = !is_pow2(N) ? (N <= 640 ? 16 : 8)
-                                        : (LN <= 8 ? 16 : (LN == 9 ? ADMMTV_TR9 : (LN == 10 ? 8 : (LN == 11 ? ADMMTV_TR11 : 4))));
+                                        : (LN <= 6 ? 16 : (LN == 7 ? ADMMTV_TR7 : (LN == 8 ? ADMMTV_TR8 : (LN == 9 ? ADMMTV_TR9 : (LN == 10 ? 8 : (LN == 11 ? ADMMTV_TR11 : 4))))));
   // block size = work items of the widest pass (row pairs x N / largest radix), within [32, 512]
   static constexpr int ITEMS_MAX = (TR / 2) * (N / plan_radix(N, 0));
   static constexpr int NT_AUTO = ITEMS_MAX < 32 ? 32 : (ITEMS_MAX > ADMMTV_NT2_MAX ? ADMMTV_NT2_MAX : ITEMS_MAX);
