@@ -47,7 +47,7 @@ LOSS_SYMBOLS = (
     "admmtv_ssim_backward",
 )
 # every symbol include/admmtv_batch.h declares
-BATCH_SYMBOLS = ("admmtv_batch_from_n0f8",)
+BATCH_SYMBOLS = ("admmtv_batch_from_n0f8", "admmtv_batch_gather_n0f8")
 
 
 class Desc(C.Structure):
@@ -114,6 +114,7 @@ class AdmmTvLib:
         L.admmtv_ssim_forward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, f, i, vp, vp, i, vp]
         L.admmtv_ssim_backward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, i, vp, vp, vp, vp]
         L.admmtv_batch_from_n0f8.argtypes = [i, i, i, i, i, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp]
+        L.admmtv_batch_gather_n0f8.argtypes = [i, i, i, i, i, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, vp]
         for name in SYMBOLS + LOSS_SYMBOLS + BATCH_SYMBOLS:
             getattr(L, name)  # AttributeError if a declared symbol is not exported
 
@@ -207,6 +208,9 @@ class AdmmTvLib:
 
     def batch_from_n0f8(self, M, N, Cc, B, device, src, sc, si, sj, sb, dst, stream=0):
         self._raise(self.lib.admmtv_batch_from_n0f8(M, N, Cc, B, device, src, sc, si, sj, sb, dst, stream))
+
+    def batch_gather_n0f8(self, M, N, Cc, B, device, base, offsets, sc, si, sj, dst, stream=0):
+        self._raise(self.lib.admmtv_batch_gather_n0f8(M, N, Cc, B, device, base, offsets, sc, si, sj, dst, stream))
 
     def ssim_backward(self, M, N, Cc, B, device, x, y, taps, as_loss, outbar, ws, xbar, stream=0):
         arr, L = self._taps(taps)

@@ -196,4 +196,24 @@ int admmtv_batch_from_n0f8(int M, int N, int C, int B, int device, const uint8_t
   return e == cudaSuccess ? ADMMTV_OK : (int)e;
 }
 
+int admmtv_batch_gather_n0f8(int M, int N, int C, int B, int device, const uint8_t* base, const int64_t* offsets,
+                             int64_t stride_c, int64_t stride_i, int64_t stride_j, float* dst, void* stream) {
+  int rc = check_shape(M, N, C, B);
+  if (rc) return rc;
+  if (!base || !offsets || !dst) return ADMMTV_ERR_NULL;
+  if (stride_c < 0 || stride_i < 0 || stride_j < 0) return ADMMTV_ERR_SHAPE;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  BatchArgs a{};
+  a.src = base; a.dst = dst; a.M = M; a.N = N; a.C = C; a.B = B;
+  a.tiles_i = (M + BA_T - 1) / BA_T; a.tiles_j = (N + BA_T - 1) / BA_T;
+  a.sc = stride_c; a.si = stride_i; a.sj = stride_j; a.sb = 0;
+  a.offsets = reinterpret_cast<const long long*>(offsets);
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_batch_from_n0f8, dim3((unsigned)nblk), dim3(BA_NT), 0, reinterpret_cast<cudaStream_t>(stream), a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADMMTV_OK : (int)e;
+}
+
 }  // extern "C"

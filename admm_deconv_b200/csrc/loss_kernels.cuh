@@ -318,6 +318,7 @@ struct BatchArgs {
   int M, N, C, B;
   int tiles_i, tiles_j;
   long long sc, si, sj, sb;
+  const long long* offsets;   // optional per-image element offsets (device-resident dataset gather); else b * sb
 };
 
 __global__ void __launch_bounds__(BA_NT) k_batch_from_n0f8(BatchArgs A) {
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(BA_NT) k_batch_from_n0f8(BatchArgs A) {
   const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
   const int b = blockIdx.x / tiles, tl = blockIdx.x % tiles;
   const int i0 = (tl % A.tiles_i) * BA_T, j0 = (tl / A.tiles_i) * BA_T;
-  const uint8_t* sp = A.src + (long long)b * A.sb;
+  const uint8_t* sp = A.src + (A.offsets ? A.offsets[b] : (long long)b * A.sb);
   const bool i_fast = A.si <= A.sj;
   for (int c0 = 0; c0 < A.C; c0 += BA_CC) {
     const int nc = min(BA_CC, A.C - c0);

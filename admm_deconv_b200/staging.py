@@ -28,7 +28,7 @@ class ImageDataFeeder:
 
     def __init__(self, x_data: Sequence[np.ndarray], y_data: Sequence[np.ndarray], x_shape: Tuple[int, int],
                  y_shape: Tuple[int, int], device="cuda:0", seed: Optional[int] = None, depth: int = 2,
-                 rank: int = 0, world: int = 1):
+                 rank: int = 0, world: int = 1, resident: bool = False):
         if len(x_data) != len(y_data):
             raise ValueError("x_data and y_data must pair up")
         self.x_data, self.y_data = list(x_data), list(y_data)
@@ -42,6 +42,26 @@ class ImageDataFeeder:
         self._bufs = {}
         self._stream = torch.cuda.Stream(device=self.device)
         self._free = [None] * self.depth   # event: the slot's pinned/device byte buffers were consumed
+        # resident=True: the decoded 8-bit dataset is uploaded ONCE and stays in HBM; a batch is then gathered on the device
+        # from per-image offsets (admmtv_batch_gather_n0f8) and the host sends 8 bytes per image per step
+        self.resident = bool(resident)
+        if self.resident:
+            self._res = {}
+            for which, data in (("x", self.x_data), ("y", self.y_data)):
+                widths = {im.shape[1] for im in data}
+                chans = {1 if im.ndim == 2 else im.shape[2] for im in data}
+                if len(widths) != 1 or len(chans) != 1:
+                    raise ValueError("resident=True needs images of one width and channel count (shared strides)")
+                starts, total = [], 0
+                for im in data:
+                    if im.dtype != np.uint8:
+                        raise TypeError("images must be uint8 (N0f8)")
+                    starts.append(total)
+                    total += im.size
+                flat = torch.empty(total, dtype=torch.uint8)
+                for st, im in zip(starts, data):
+                    flat[st:st + im.size] = torch.from_numpy(np.ascontiguousarray(im).reshape(-1))
+                self._res[which] = (flat.to(self.device), starts, widths.pop(), chans.pop())
 
     def __len__(self):                      # datafeeder.jl:49-51
         return len(self.y_data)
@@ -78,6 +98,17 @@ class ImageDataFeeder:
             self._free[slot].synchronize()                     # the host may overwrite the pinned buffer again
         out = []
         cur = torch.cuda.current_stream(self.device)
+        if self.resident:
+            for which, shape in (("x", self.x_shape), ("y", self.y_shape)):
+                base, starts, W, C = self._res[which]
+                M, N = shape
+                offs = torch.tensor([starts[i] + (h0 * W + w0) * C for i, (h0, w0) in zip(idxs, origins)], dtype=torch.int64)
+                dst = torch.empty(B, C, N, M, dtype=torch.float32, device=self.device)
+                offs_d = offs.to(self.device, non_blocking=True)
+                lib.batch_gather_n0f8(M, N, C, B, self.device.index or 0, base.data_ptr(), offs_d.data_ptr(), 1, C * W, C,
+                                      dst.data_ptr(), cur.cuda_stream)
+                out.append(dst)
+            return out[0], out[1]
         for which, data, shape in (("x", self.x_data, self.x_shape), ("y", self.y_data, self.y_shape)):
             C = 1 if data[idxs[0]].ndim == 2 else data[idxs[0]].shape[2]
             M, N = shape
@@ -109,6 +140,8 @@ class ImageDataFeeder:
         return len(self)
 
     def h2d_bytes(self, batch: int) -> int:
+        if self.resident:
+            return 2 * 8 * batch      # one int64 offset per image and array
         cx = 1 if self.x_data[0].ndim == 2 else self.x_data[0].shape[2]
         cy = 1 if self.y_data[0].ndim == 2 else self.y_data[0].shape[2]
         return batch * (self.x_shape[0] * self.x_shape[1] * cx + self.y_shape[0] * self.y_shape[1] * cy)

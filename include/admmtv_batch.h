@@ -31,6 +31,15 @@ extern "C" {
 int admmtv_batch_from_n0f8(int M, int N, int C, int B, int device, const uint8_t* src, int64_t stride_c,
                            int64_t stride_i, int64_t stride_j, int64_t stride_b, float* dst, void* stream);
 
+/* Device-resident dataset variant: the decoded 8-bit images stay in HBM (180 GB per B200 holds ~290k RGB 512x512
+ * frames) and a batch is gathered from them on the device -- per step the host only sends B offsets.
+ *   dst[i + M*(j + N*(c + C*b))] = base[offsets[b] + c*stride_c + i*stride_i + j*stride_j] / 255
+ * `offsets` is a DEVICE array of B int64 element offsets (image start + crop origin: h0*stride_i + w0*stride_j for the
+ * random aligned crops of datafeeder.jl:43-45); strides are those of the FULL images, e.g. row-major (H,W,C):
+ * (1, C*W, C).  All images of one call share the strides (same width); x and y batches are two calls. */
+int admmtv_batch_gather_n0f8(int M, int N, int C, int B, int device, const uint8_t* base, const int64_t* offsets,
+                             int64_t stride_c, int64_t stride_i, int64_t stride_j, float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,3 +20,15 @@ def test_batch_from_n0f8(emu, M, N, C, B, order):
     emu.batch_from_n0f8(M, N, C, B, 0, src.ctypes.data, sc, si, sj, sb, dst.ctypes.data)
     want = (img.transpose(1, 2, 3, 0).astype(np.float32) / np.float32(255.0))   # img2tensor: N0f8 -> Float32
     assert np.array_equal(np.array(dst), want)                         # bit-exact: integer -> correctly rounded i/255
+
+
+def test_batch_gather_from_resident_images(emu):
+    rng = np.random.default_rng(4)
+    H, W, C, B, M, N = 50, 44, 3, 3, 33, 20
+    imgs = rng.integers(0, 256, size=(4, H, W, C), dtype=np.uint8)            # row-major (H,W,C) images, back to back
+    pick, org = [2, 0, 3], [(0, 0), (17, 24), (5, 9)]
+    offs = np.array([i * H * W * C + (h0 * W + w0) * C for i, (h0, w0) in zip(pick, org)], dtype=np.int64)
+    dst = np.asfortranarray(np.full((M, N, C, B), np.nan, np.float32))
+    emu.batch_gather_n0f8(M, N, C, B, 0, imgs.ctypes.data, offs.ctypes.data, 1, C * W, C, dst.ctypes.data)
+    want = np.stack([imgs[i, h0:h0 + M, w0:w0 + N].astype(np.float32) / np.float32(255) for i, (h0, w0) in zip(pick, org)], axis=-1)
+    assert np.array_equal(np.array(dst), want)

@@ -46,3 +46,16 @@ def test_feeder_shards_and_feeds_the_layer():
     d = torch.device("cuda:0")
     x = A.tvd_fft(c, torch.tensor([0.0041], device=d), torch.tensor([0.021], device=d), None, False, 3)
     assert torch.isfinite(x).all() and float(A.gmsd_loss(x, cy)) > 0
+
+
+def test_resident_dataset_gather_matches_streaming_feeder():
+    """resident=True keeps the 8-bit dataset in HBM and gathers crops on the device: identical batches."""
+    xs, ys = _dataset(5, 150, 140, 3, 9)
+    a = ImageDataFeeder(xs, ys, (128, 96), (128, 96), "cuda:0", seed=2)
+    b = ImageDataFeeder(xs, ys, (128, 96), (128, 96), "cuda:0", seed=2, resident=True)
+    idxs = [3, 1, 4]
+    origins = [(0, 0), (22, 44), (5, 17)]
+    ax, ay = a.getindex(idxs, origins); bx, by = b.getindex(idxs, origins)
+    torch.cuda.synchronize()
+    assert torch.equal(ax, bx) and torch.equal(ay, by)
+    assert b.h2d_bytes(3) == 48 and a.h2d_bytes(3) == 2 * 3 * 128 * 96 * 3

@@ -18,12 +18,13 @@ loss_name = sys.argv[1] if len(sys.argv) > 1 else "gmsd"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-iso = len(sys.argv) > 5 and sys.argv[5] == "iso"
+iso = "iso" in sys.argv[5:]
+resident = "resident" in sys.argv[5:]
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(0)
 imgs_y = [rng.integers(0, 256, size=(N + 40, N + 40, 3), dtype=np.uint8) for _ in range(B)]
 imgs_x = [np.clip(im.astype(np.int16) + rng.integers(-20, 21, size=im.shape), 0, 255).astype(np.uint8) for im in imgs_y]
-feeder = ImageDataFeeder(imgs_x, imgs_y, (N, N), (N, N), dev, seed=1)
+feeder = ImageDataFeeder(imgs_x, imgs_y, (N, N), (N, N), dev, seed=1, resident=resident)
 layer = A.ADMMDeconv((15, 15), K, "relu1", iso=iso).to(dev)
 with torch.no_grad():
     layer.weight.fill_(1.0 / 225); layer.lam.fill_(0.0041); layer.rho.fill_(0.021)
@@ -65,7 +66,7 @@ e1 = ev()
 torch.cuda.synchronize()
 pipelined = e0.elapsed_time(e1) / reps
 px = B * 3 * N * N
-print(json.dumps({"workload": f"{B} x {N}x{N} RGB, ADMMDeconv((15,15),{K},relu1{', iso' if iso else ''}), {loss_name}_loss",
+print(json.dumps({"workload": f"{B} x {N}x{N} RGB, ADMMDeconv((15,15),{K},relu1{', iso' if iso else ''}), {loss_name}_loss{', device-resident dataset' if resident else ''}",
                   "ms": {"batch_assembly_incl_h2d": acc[0], "layer_forward_ckpt": acc[1], "loss_forward": acc[2],
                          "loss_backward+layer_backward": acc[3], "total": float(acc.sum()),
                          "pipelined_per_step": pipelined},
