@@ -18,6 +18,7 @@ static inline int ilog2(int v) {
 }
 
 static int dim2_row_tile(int LN);
+static int dim1_col_tile(int LM);
 static Geom geom(const admmtv_desc* d) {
   Geom g;
   g.M = d->M; g.N = d->N; g.P = d->P; g.B = d->B;
@@ -25,12 +26,16 @@ static Geom geom(const admmtv_desc* d) {
   g.Q = (g.S + 1) / 2;
   g.LM = dim_id(d->M); g.LN = dim_id(d->N);
   if (g.LM <= 0 || g.LN <= 0) {
-    // No register-FFT plan for one of the lengths.  The dim-1 kernels (tiles of whole columns) go generic; the tuned
-    // dim-2 kernel only needs its row tile to divide M (16-byte aligned row pairs), so a planned N keeps it -- e.g.
-    // 720x1280, 1080x1920 frames (Julia (M,N) = (height, width)).
-    g.LM = 0;
-    const int tr = g.LN > 0 ? dim2_row_tile(g.LN) : 0;
-    if (tr <= 0 || d->M % tr != 0) g.LN = 0;
+    // No register-FFT plan for one of the lengths: that pass runs the generic kernels.  The other pass keeps its tuned
+    // kernel when its tiling divides the unplanned length: the dim-2 kernel needs its row tile to divide M (16-byte
+    // aligned row pairs) -- 720x1280, 1080x1920 frames with Julia (M,N) = (height, width) -- and the dim-1 kernels
+    // need their column tile to divide N (1280x720).  Otherwise both passes are generic.
+    const int tr = (g.LM <= 0 && g.LN > 0) ? dim2_row_tile(g.LN) : 0;
+    const int co = (g.LN <= 0 && g.LM > 0) ? dim1_col_tile(g.LM) : 0;
+    const int lm = g.LM, ln = g.LN;
+    g.LM = g.LN = 0;
+    if (tr > 0 && d->M % tr == 0) g.LN = ln;
+    else if (co > 0 && d->N % co == 0) g.LM = lm;
   }
   g.planned = (g.LM > 0 ? 1 : 0) | (g.LN > 0 ? 2 : 0);
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
@@ -182,6 +187,9 @@ static int run_dim2(const Geom& g, Dim2Variant v, const Dim2Args& a, cudaStream_
 
 static int dim2_row_tile(int LN) {
   ADMMTV_SWITCH_LOG2(LN, L, { return Dim2Launch<L>::row_tile(); })
+}
+static int dim1_col_tile(int LM) {
+  ADMMTV_SWITCH_LOG2(LM, L, { return Dim1Launch<L>::col_tile(); })
 }
 
 struct DeviceGuard {

@@ -135,6 +135,7 @@ struct Dim1Launch {
   static int bwd_iso_a(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
   static int bwd(const Geom& g, bool has_vbar, const Dim1BwdArgs& a, cudaStream_t st);
   static int bwd_last(const Geom& g, int mode, const Dim1BwdArgs& a, cudaStream_t st);
+  static int col_tile();   // output columns per block of the tuned kernels (N must be a multiple of it); 0 for the generic launcher
 };
 template <int LN>
 struct Dim2Launch {

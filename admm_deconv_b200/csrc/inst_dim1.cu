@@ -13,6 +13,7 @@ template <> int Dim1Launch<LM_>::fwd_iso_b(const Geom&, const Dim1FwdArgs&, cuda
 template <> int Dim1Launch<LM_>::fwd_iso_a(const Geom&, bool, const Dim1FwdArgs&, cudaStream_t) { return -3; }
 template <> int Dim1Launch<LM_>::bwd_iso_b(const Geom&, bool, const Dim1BwdArgs&, cudaStream_t) { return -3; }
 template <> int Dim1Launch<LM_>::bwd_iso_a(const Geom&, bool, const Dim1BwdArgs&, cudaStream_t) { return -3; }
+template <> int Dim1Launch<LM_>::col_tile() { return 0; }
 }
 #else
 #include "kernels.cuh"
@@ -38,6 +39,9 @@ static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, con
 constexpr int LM = ADMMTV_INST;
 using Cfg = Dim1Cfg<LM>;
 static dim3 dim1_grid(const Geom& g) { return dim3((unsigned)((g.N + Cfg::CO - 1) / Cfg::CO) * (unsigned)g.Q); }
+
+template <>
+int Dim1Launch<LM>::col_tile() { return Cfg::CO; }
 
 template <>
 int Dim1Launch<LM>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {

@@ -31,6 +31,9 @@ static int gk_run_dft1(const Geom& g, const float2* in, float2* out, const float
 static unsigned gk_pixel_blocks(const Geom& g) { return (unsigned)((g.pk + GK_NT - 1) / GK_NT); }
 
 template <>
+int Dim1Launch<0>::col_tile() { return 0; }
+
+template <>
 int Dim1Launch<0>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {
   ADMMTV_LAUNCH(gk_pack, dim3(gk_pixel_blocks(g)), dim3(GK_NT), 0, st, a, g.M, g.Q, mode);
   ADMMTV_CHECK_LAUNCH();

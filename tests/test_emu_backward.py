@@ -84,7 +84,8 @@ def test_emu_backward_mixed_radix(be, iso):
     [(20, 24, 1, 2, 3, 3, 4, False, "identity", None, 0), (33, 17, 3, 1, 5, 4, 3, False, "relu1", 0.02, 0),
      (7, 5, 1, 1, 0, 0, 3, False, "identity", None, 0), (20, 24, 2, 2, 3, 3, 4, True, "identity", None, 1 | 16),
      (31, 18, 1, 3, 0, 0, 3, True, "identity", None, 1 | 32), (30, 32, 1, 1, 3, 3, 3, False, "relu", None, 2),
-     (48, 32, 1, 2, 3, 3, 3, False, "identity", None, 0), (48, 32, 2, 1, 3, 3, 3, True, "identity", None, 1 | 16)],   # mixed
+     (48, 32, 1, 2, 3, 3, 3, False, "identity", None, 0), (48, 32, 2, 1, 3, 3, 3, True, "identity", None, 1 | 16),   # mixed
+     (32, 224, 1, 1, 3, 3, 3, False, "identity", None, 0)],                                                          # mixed, other way
 )
 def test_emu_backward_generic_sizes(be, M, N, P, B, kh, kw, K, iso, act, bias, flags):
     y, h, _ = make_case(M, N, P, B, kh, kw, 9 + M)

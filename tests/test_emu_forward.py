@@ -101,7 +101,8 @@ def test_emu_mixed_radix_lengths(emu, M, N):
     "M,N,P,B,kh,kw,K,iso",
     [(20, 24, 1, 2, 3, 3, 4, False), (33, 17, 3, 1, 5, 4, 3, False), (7, 5, 1, 1, 0, 0, 3, False), (31, 64, 1, 2, 3, 3, 3, False),
      (20, 24, 2, 2, 3, 3, 4, True), (64, 50, 1, 3, 0, 0, 3, True), (3, 9, 1, 1, 0, 0, 2, False),
-     (48, 32, 1, 2, 3, 3, 3, False), (48, 64, 3, 1, 5, 4, 3, True)],    # M generic, N planned: generic dim-1 + tuned dim-2
+     (48, 32, 1, 2, 3, 3, 3, False), (48, 64, 3, 1, 5, 4, 3, True),     # M generic, N planned: generic dim-1 + tuned dim-2
+     (32, 224, 1, 2, 3, 3, 3, False), (64, 96 + 128, 1, 1, 0, 0, 3, True)],  # M planned, N = 224 = 7*32: tuned dim-1 + generic dim-2
 )
 def test_emu_forward_generic_sizes(emu, M, N, P, B, kh, kw, K, iso):
     import harness

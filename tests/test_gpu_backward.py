@@ -198,7 +198,8 @@ def test_backward_mixed_radix(be, M, N, iso):
 @pytest.mark.parametrize("M,N,P,B,kh,kw,K,iso,flags", [(33, 17, 3, 1, 5, 4, 3, False, 0), (100, 100, 3, 2, 7, 7, 8, False, 0),
                                                        (225, 64, 1, 2, 5, 5, 6, True, 1 | 16), (127, 131, 1, 2, 5, 5, 6, True, 1 | 32),
                                                        (321, 481, 3, 1, 9, 9, 5, False, 0), (360, 640, 3, 1, 7, 7, 5, False, 0),
-                                                       (720, 256, 1, 2, 5, 5, 5, True, 1 | 16)])
+                                                       (720, 256, 1, 2, 5, 5, 5, True, 1 | 16), (512, 200, 3, 1, 7, 7, 5, False, 0),
+                                                       (256, 360, 1, 2, 5, 5, 5, True, 1 | 32)])
 def test_backward_any_size(be, M, N, P, B, kh, kw, K, iso, flags):
     y, h, g = make_case(M, N, P, B, kh, kw, 900 + M + N)
     xbar = 2.0 * (y - g) / y.numel() * 1e3

@@ -325,7 +325,8 @@ def test_full_cfg2_size_shift_equivariance_and_fixed_point():
     [(20, 24, 1, 2, 3, 3, 4, False), (33, 17, 3, 1, 5, 4, 3, False), (7, 5, 1, 1, 0, 0, 3, False), (100, 100, 3, 2, 7, 7, 20, False),
      (321, 481, 3, 1, 9, 9, 10, False), (225, 64, 1, 2, 5, 5, 10, True), (127, 131, 1, 2, 5, 5, 10, False),   # prime lengths
      (64, 50, 1, 3, 0, 0, 5, True), (360, 640, 3, 1, 15, 15, 5, False),
-     (360, 1280, 1, 2, 9, 9, 6, False), (720, 256, 3, 1, 7, 7, 6, True)],     # M without a plan, N planned: generic dim-1 + tuned dim-2
+     (360, 1280, 1, 2, 9, 9, 6, False), (720, 256, 3, 1, 7, 7, 6, True),      # M without a plan, N planned: generic dim-1 + tuned dim-2
+     (512, 200, 1, 2, 7, 7, 6, False), (1280, 720, 1, 1, 9, 9, 4, True)],     # N without a plan, M planned: tuned dim-1 + generic dim-2
 )
 def test_forward_any_size_vs_oracle(M, N, P, B, kh, kw, K, iso):
     y, h, _ = make_case(M, N, P, B, kh, kw, 300 + M + N, psf="random")
