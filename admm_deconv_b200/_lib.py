@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadmmtv.so")
+LIB_PATH = os.environ.get("ADMMTV_LIB") or os.path.join(_HERE, "libadmmtv.so")   # same override as julia/ADMMTV.jl
 
 ACT = {"identity": 0, "relu": 1, "relu6": 2, "relu1": 3}
 FLAG_NO_CLAMP = 1

@@ -377,3 +377,24 @@ def test_grouped_per_image_generic_size():
     ht = torch.stack([A.from_julia(h.float()).reshape(1, 5, 3) for h in hs]).contiguous().to(d0)     # (G,1,kw,kh)
     x = A.tvd_fft_grouped(yt, torch.tensor(lams, device=d0), torch.tensor(rhos, device=d0), ht, False, K, groups=B)
     assert rel_l2(A.to_julia(x.cpu()).double(), torch.cat(refs, dim=3)) <= TOL
+
+
+def test_forward_is_cuda_graph_capturable():
+    """The library only enqueues stream-ordered kernels and memsets, so a call can be captured once and replayed
+    (serving small batches is launch-bound: tools/graph_bench.py)."""
+    d0 = dev()
+    y = torch.rand(2, 3, 64, 64, device=d0)
+    h = torch.rand(1, 1, 5, 5, device=d0); h /= h.sum()
+    lam = torch.tensor([0.0041], device=d0); rho = torch.tensor([0.021], device=d0)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        A.tvd_fft(y, lam, rho, h, True, 6)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        xg = A.tvd_fft(y, lam, rho, h, True, 6)
+    y.copy_(torch.rand_like(y))
+    g.replay()
+    torch.cuda.synchronize()
+    assert rel_l2(xg.cpu(), A.tvd_fft(y, lam, rho, h, True, 6).cpu()) <= 1e-6     # isotropic: float atomics, not bitwise
