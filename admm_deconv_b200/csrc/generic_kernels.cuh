@@ -6,8 +6,8 @@
 // with run-time sizes, so the launch sequences, workspace layout, checkpoint and gradient code of
 // admmtv_api.cu / bwd_api.inc are shared.  Differences from the tuned path:
 //   * spectra are in NATURAL order (pos_to_freq is the identity for unplanned lengths);
-//   * a length-L DFT is a two-factor Cooley-Tukey step L = L1*L2 (L1 the largest divisor <= sqrt(L)) with
-//     direct sub-transforms in shared memory: O(L (L1+L2)) per line, O(L^2) for a prime length;
+//   * a length-L DFT is a two- or three-factor Cooley-Tukey decomposition L = L1*La*Lb (the split minimising L1+La+Lb)
+//     with direct sub-transforms in shared memory: O(L (L1+La+Lb)) per line, O(L^2) for a prime length;
 //   * the stencil sweeps are separate, unfused per-pixel kernels (neighbour values are recomputed, not exchanged).
 // Same arithmetic per pixel (shrink_aniso / bwd_point / iso_* are the tuned path's functions), same results
 // to fp32 rounding; correct and bandwidth-reasonable, not roofline-tuned.
@@ -25,6 +25,33 @@ ADMMTV_HD inline int small_factor(int L) {
     if (L % d == 0) f = d;
   return f;
 }
+// L = L1 * La * Lb minimising L1 + La + Lb (the number of complex multiply-adds per element); La = 1 means a two-factor plan
+// L = L1 * Lb.  L1 <= La <= Lb, so a prime gives (1, 1, L).
+struct DftPlan {
+  int L1, La, Lb;
+};
+ADMMTV_HD inline DftPlan dft_plan(int L) {
+  DftPlan best{1, 1, L};
+  int cost = L + 2;
+  for (int a = 1; a * a * a <= L; ++a) {
+    if (L % a) continue;
+    const int r = L / a;
+    for (int b = a; b * b <= r; ++b) {
+      if (r % b) continue;
+      const int c = r / b;
+      const int cst = a + b + c - (a == 1 ? 1 : 0) - (b == 1 ? 1 : 0);   // a factor of 1 is no pass at all
+      if (cst < cost) {
+        cost = cst;
+        best = DftPlan{a, b, c};
+      }
+    }
+  }
+  if (best.L1 == 1 && best.La > 1) {   // two factors: make L1 the small one, no inner split
+    best.L1 = best.La;
+    best.La = 1;
+  }
+  return best;
+}
 ADMMTV_HD inline int gk_lines_dim1(int M) { return M <= 64 ? 8 : (M <= 256 ? 4 : (M <= 1024 ? 2 : 1)); }
 ADMMTV_HD inline int gk_rows_dim2(int N) { return N <= 1024 ? 8 : (N <= 2048 ? 4 : 2); }
 
@@ -32,15 +59,16 @@ ADMMTV_DI float2 cfma(float2 acc, float2 a, float2 w) {
   return make_float2(acc.x + a.x * w.x - a.y * w.y, acc.y + a.x * w.y + a.y * w.x);
 }
 
-// In-place DFT of `nl` lines xs[l*L .. l*L+L) held in shared memory (natural order in and out), scratch ys of the
-// same size, tw[n] = exp(-2 pi i n / L) and twb[m] = tw[L1 m] (m < L2) in shared memory; `inv` conjugates the twiddles
-// (no 1/L: the tables carry the normalisation).  Every thread of the block must call; ends with a barrier.
-// Thread mappings keep shared-memory reads contiguous or broadcast within a warp: step A walks n2 (contiguous x, one
-// twiddle per k1), step B walks k2 (one y per k1 broadcast, twiddles from the compact table twb).
-ADMMTV_DI void line_dft(float2* xs, float2* ys, const float2* tw, const float2* twb, int L, int L1, int L2, int nl, bool inv,
-                        int tid) {
+// DFT of `nl` lines xs[l*L .. l*L+L) held in shared memory (natural order in and out) with scratch ys of the same size;
+// RETURNS the buffer that holds the result (xs for a two-factor plan, ys for a three-factor one).  L = L1 * L2, L2 = La * Lb.
+// tw[n] = exp(-2 pi i n / L), twb[m] = tw[L1 m] (m < L2), twc[m] = twb[La m] (m < Lb), all in shared memory; `inv` conjugates
+// the twiddles (no 1/L: the tables carry the normalisation).  Every thread of the block must call; ends with a barrier.
+// Thread mappings keep shared-memory reads contiguous or broadcast within a warp.
+ADMMTV_DI float2* line_dft(float2* xs, float2* ys, const float2* tw, const float2* twb, const float2* twc, int L, DftPlan P, int nl,
+                           bool inv, int tid) {
   const float sg = inv ? -1.f : 1.f;
-  // ys[k1*L2 + n2] = W^(n2 k1) * sum_n1 xs[L2 n1 + n2] W^(L2 n1 k1)
+  const int L1 = P.L1, L2 = P.La * P.Lb;
+  // ys[k1*L2 + n2] = W_L^(n2 k1) * sum_n1 xs[L2 n1 + n2] W_L^(L2 n1 k1)
   for (int e = tid; e < nl * L; e += GK_NT) {
     const int l = e / L, r = e % L, k1 = r / L2, n2 = r % L2;
     const float2* x = xs + l * L + n2;
@@ -57,21 +85,60 @@ ADMMTV_DI void line_dft(float2* xs, float2* ys, const float2* tw, const float2* 
     ys[e] = cmul(acc, make_float2(w.x, sg * w.y));
   }
   __syncthreads();
-  // xs[k1 + L1 k2] = sum_n2 ys[k1*L2 + n2] W_L2^(n2 k2),  W_L2^m = twb[m]
-  for (int e = tid; e < nl * L; e += GK_NT) {
-    const int l = e / L, r = e % L, k1 = r / L2, k2 = r % L2;
-    const float2* y = ys + l * L + k1 * L2;
-    float2 acc = make_float2(0.f, 0.f);
-    int m = 0;
-    for (int n2 = 0; n2 < L2; ++n2) {
-      const float2 w = twb[m];
-      acc = cfma(acc, y[n2], make_float2(w.x, sg * w.y));
-      m += k2;
-      if (m >= L2) m -= L2;
+  if (P.La <= 1) {
+    // xs[k1 + L1 k2] = sum_n2 ys[k1*L2 + n2] W_L2^(n2 k2),  W_L2^m = twb[m]
+    for (int e = tid; e < nl * L; e += GK_NT) {
+      const int l = e / L, r = e % L, k1 = r / L2, k2 = r % L2;
+      const float2* y = ys + l * L + k1 * L2;
+      float2 acc = make_float2(0.f, 0.f);
+      int m = 0;
+      for (int n2 = 0; n2 < L2; ++n2) {
+        const float2 w = twb[m];
+        acc = cfma(acc, y[n2], make_float2(w.x, sg * w.y));
+        m += k2;
+        if (m >= L2) m -= L2;
+      }
+      xs[l * L + k1 + L1 * k2] = acc;
     }
-    xs[l * L + k1 + L1 * k2] = acc;
+    __syncthreads();
+    return xs;
+  }
+  // three factors: the nl*L1 length-L2 lines of ys get the same two-step treatment with (La, Lb), scratch = xs
+  const int La = P.La, Lb = P.Lb;
+  //   xs[lam*L2 + ka*Lb + nb] = W_L2^(nb ka) * sum_na ys[lam*L2 + Lb na + nb] W_L2^(Lb na ka)
+  for (int e = tid; e < nl * L; e += GK_NT) {
+    const int lam = e / L2, r = e % L2, ka = r / Lb, nb = r % Lb;
+    const float2* y = ys + lam * L2 + nb;
+    float2 acc = make_float2(0.f, 0.f);
+    const int step = (Lb * ka) % L2;
+    int idx = 0;
+    for (int na = 0; na < La; ++na) {
+      const float2 w = twb[idx];
+      acc = cfma(acc, y[na * Lb], make_float2(w.x, sg * w.y));
+      idx += step;
+      if (idx >= L2) idx -= L2;
+    }
+    const float2 w = twb[(nb * ka) % L2];
+    xs[e] = cmul(acc, make_float2(w.x, sg * w.y));
   }
   __syncthreads();
+  //   result[k1 + L1 (ka + La kb)] = sum_nb xs[lam*L2 + ka*Lb + nb] W_Lb^(nb kb),  W_Lb^m = twc[m];  lam = l*L1 + k1
+  for (int e = tid; e < nl * L; e += GK_NT) {
+    const int lam = e / L2, r = e % L2, ka = r / Lb, kb = r % Lb;
+    const float2* x = xs + lam * L2 + ka * Lb;
+    float2 acc = make_float2(0.f, 0.f);
+    int m = 0;
+    for (int nb = 0; nb < Lb; ++nb) {
+      const float2 w = twc[m];
+      acc = cfma(acc, x[nb], make_float2(w.x, sg * w.y));
+      m += kb;
+      if (m >= Lb) m -= Lb;
+    }
+    const int l = lam / L1, k1 = lam % L1;
+    ys[l * L + k1 + L1 * (ka + La * kb)] = acc;
+  }
+  __syncthreads();
+  return ys;
 }
 
 // ---- dim-1 DFT of contiguous lines, in place or out of place ------------------------------------------
@@ -79,35 +146,43 @@ struct GDft1Args {
   const float2* in;
   float2* out;
   const float2* tw;
-  int M, M1, M2, LB, inv;
+  int M, LB, inv;
+  DftPlan P;
   long long nlines;
 };
+ADMMTV_HD inline size_t gk_dft_smem_elems(int L, DftPlan P, int lines) { return (size_t)L + P.La * P.Lb + P.Lb + 2 * (size_t)lines * L; }
 __global__ void __launch_bounds__(GK_NT) gk_dft1(GDft1Args A) {
   ADMMTV_DYN_SMEM(float2, sm);
+  const int L2 = A.P.La * A.P.Lb;
   float2* tw = sm;
-  float2* twb = sm + A.M;
-  float2* xs = twb + A.M2;
+  float2* twb = tw + A.M;
+  float2* twc = twb + L2;
+  float2* xs = twc + A.P.Lb;
   float2* ys = xs + (size_t)A.LB * A.M;
   const int tid = threadIdx.x;
   const long long l0 = (long long)blockIdx.x * A.LB;
   const int nl = (int)(A.nlines - l0 < A.LB ? A.nlines - l0 : A.LB);
   for (int e = tid; e < A.M; e += GK_NT) tw[e] = A.tw[e];
-  for (int e = tid; e < A.M2; e += GK_NT) twb[e] = A.tw[e * A.M1];
+  for (int e = tid; e < L2; e += GK_NT) twb[e] = A.tw[e * A.P.L1];
+  for (int e = tid; e < A.P.Lb; e += GK_NT) twc[e] = A.tw[e * A.P.L1 * A.P.La];
   for (int e = tid; e < nl * A.M; e += GK_NT) xs[e] = A.in[l0 * A.M + e];
   __syncthreads();
-  line_dft(xs, ys, tw, twb, A.M, A.M1, A.M2, nl, A.inv != 0, tid);
-  for (int e = tid; e < nl * A.M; e += GK_NT) A.out[l0 * A.M + e] = xs[e];
+  const float2* res = line_dft(xs, ys, tw, twb, twc, A.M, A.P, nl, A.inv != 0, tid);
+  for (int e = tid; e < nl * A.M; e += GK_NT) A.out[l0 * A.M + e] = res[e];
 }
 
 // ---- dim-2: forward DFT -> [save Z] -> [accumulate] -> x table -> inverse DFT  (the contract of k_dim2) -----
 struct GDim2Cfg {
-  int N, N1, N2, TR, mul, save_z, acc, fwd_only;
+  int N, TR, mul, save_z, acc, fwd_only;
+  DftPlan P;
 };
 __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
   ADMMTV_DYN_SMEM(float2, sm);
+  const int N2 = C.P.La * C.P.Lb;
   float2* tw = sm;
-  float2* twb = sm + C.N;
-  float2* xs = twb + C.N2;
+  float2* twb = tw + C.N;
+  float2* twc = twb + N2;
+  float2* xs = twc + C.P.Lb;
   float2* ys = xs + (size_t)C.TR * C.N;
   const int tid = threadIdx.x, M = A.M, N = C.N, TR = C.TR;
   const int row_tiles = (M + TR - 1) / TR;
@@ -116,17 +191,19 @@ __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
   const size_t qoff = (size_t)q * N * M;
   const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;
   for (int e = tid; e < N; e += GK_NT) tw[e] = A.twN[e];
-  for (int e = tid; e < C.N2; e += GK_NT) twb[e] = A.twN[e * C.N1];
+  for (int e = tid; e < N2; e += GK_NT) twb[e] = A.twN[e * C.P.L1];
+  for (int e = tid; e < C.P.Lb; e += GK_NT) twc[e] = A.twN[e * C.P.L1 * C.P.La];
   for (int e = tid; e < nr * N; e += GK_NT) {
     const int ll = e % nr, col = e / nr;
     xs[ll * N + col] = A.in[qoff + (size_t)col * M + i0 + ll];
   }
   __syncthreads();
-  line_dft(xs, ys, tw, twb, N, C.N1, C.N2, nr, false, tid);
+  float2* zs = line_dft(xs, ys, tw, twb, twc, N, C.P, nr, false, tid);   // spectrum lines (xs or ys)
+  float2* sc = zs == xs ? ys : xs;                                        // the other buffer: scratch of the inverse
   for (int e = tid; e < nr * N; e += GK_NT) {
     const int ll = e % nr, col = e / nr;
     const size_t g = (size_t)col * M + i0 + ll;
-    float2 z = xs[ll * N + col];
+    float2 z = zs[ll * N + col];
     if (C.save_z || C.fwd_only) (C.fwd_only ? A.out : A.zsave)[qoff + g] = z;
     if (C.acc) {
       const float2 z2 = A.z2[qoff + g];
@@ -143,15 +220,15 @@ __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
         const float2 kk = A.ktab[toff + g];
         z = cmul(z, make_float2(kk.x, C.mul == 2 ? -kk.y : kk.y));
       }
-      xs[ll * N + col] = z;
+      zs[ll * N + col] = z;
     }
   }
   if (C.fwd_only) return;
   __syncthreads();
-  line_dft(xs, ys, tw, twb, N, C.N1, C.N2, nr, true, tid);
+  const float2* res = line_dft(zs, sc, tw, twb, twc, N, C.P, nr, true, tid);
   for (int e = tid; e < nr * N; e += GK_NT) {
     const int ll = e % nr, col = e / nr;
-    A.out[qoff + (size_t)col * M + i0 + ll] = xs[ll * N + col];
+    A.out[qoff + (size_t)col * M + i0 + ll] = res[ll * N + col];
   }
 }
 

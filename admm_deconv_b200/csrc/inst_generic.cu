@@ -18,9 +18,9 @@ static int gk_set_smem(const void* kern, size_t smem) {
 
 static int gk_run_dft1(const Geom& g, const float2* in, float2* out, const float2* tw, bool inv, cudaStream_t st) {
   GDft1Args a{};
-  a.in = in; a.out = out; a.tw = tw; a.M = g.M; a.M1 = small_factor(g.M); a.M2 = g.M / a.M1;
+  a.in = in; a.out = out; a.tw = tw; a.M = g.M; a.P = dft_plan(g.M);
   a.LB = gk_lines_dim1(g.M); a.inv = inv ? 1 : 0; a.nlines = (long long)g.N * g.Q;
-  const size_t smem = ((size_t)(1 + 2 * a.LB) * g.M + a.M2) * sizeof(float2);
+  const size_t smem = gk_dft_smem_elems(g.M, a.P, a.LB) * sizeof(float2);
   int rc = gk_set_smem((const void*)gk_dft1, smem);
   if (rc) return rc;
   const long long nblk = (a.nlines + a.LB - 1) / a.LB;
@@ -97,7 +97,7 @@ int Dim2Launch<0>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaStr
   Dim2Args a = a_in;
   a.Q = g.Q;
   GDim2Cfg c{};
-  c.N = g.N; c.N1 = small_factor(g.N); c.N2 = g.N / c.N1; c.TR = gk_rows_dim2(g.N);
+  c.N = g.N; c.P = dft_plan(g.N); c.TR = gk_rows_dim2(g.N);
   switch (variant) {   // (MUL, SAVE_Z, ACC, FWD_ONLY) as in inst_dim2.cu
     case D2_C: break;
     case D2_C_SAVE: c.save_z = 1; break;
@@ -108,7 +108,7 @@ int Dim2Launch<0>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaStr
     case D2_K: c.mul = 2; break;
     default: return -5;
   }
-  const size_t smem = ((size_t)(1 + 2 * c.TR) * g.N + c.N2) * sizeof(float2);
+  const size_t smem = gk_dft_smem_elems(g.N, c.P, c.TR) * sizeof(float2);
   int rc = gk_set_smem((const void*)gk_dim2, smem);
   if (rc) return rc;
   const size_t nblk = (size_t)((g.M + c.TR - 1) / c.TR) * g.Q;
