@@ -50,22 +50,24 @@ ADMMTV_DI void sobel_at(const float* T, int li, int lj, float& gx, float& gy) {
 }
 ADMMTV_DI float gradmag(float gx, float gy) { return sqrtf(gx * gx + gy * gy + 1e-16f); }  // iqa_utils.jl:53-55
 
+// Stage the tile plus its circular halo (pad_circular, iqa_utils.jl:46).  Thread (r, cg) = (tid % TH, tid / TH) loads row r
+// (and, for r < 2*HALO, the extra row r + TH) of every 4th column: no per-element division, the wrapped row index is computed once.
 template <int HALO, int LD>
 ADMMTV_DI void gm_load_tile(const float* __restrict__ p, float* T, int i0, int j0, int M, int N, int tid) {
-  if (M >= LD && N >= GM_TW + 2 * HALO) {
-    // common case: one conditional add/subtract wraps (the tile overshoots the image by less than one period)
-    for (int e = tid; e < LD * (GM_TW + 2 * HALO); e += GM_NT) {
-      const int li = e % LD, lj = e / LD;
-      int gi = i0 - HALO + li, gj = j0 - HALO + lj;
-      gi = gi < 0 ? gi + M : (gi >= M ? gi - M : gi);
-      gj = gj < 0 ? gj + N : (gj >= N ? gj - N : gj);
-      T[e] = p[(size_t)gj * M + gi];  // pad_circular, iqa_utils.jl:46
-    }
-    return;
-  }
-  for (int e = tid; e < LD * (GM_TW + 2 * HALO); e += GM_NT) {
-    const int li = e % LD, lj = e / LD;
-    T[e] = p[(size_t)wrapi(j0 - HALO + lj, N) * M + wrapi(i0 - HALO + li, M)];
+  static_assert(LD == GM_TH + 2 * HALO && GM_NT % GM_TH == 0, "tile geometry");
+  constexpr int W = GM_TW + 2 * HALO, CG = GM_NT / GM_TH;
+  const int r = tid % GM_TH, cg = tid / GM_TH;
+  const int gi0 = wrapi(i0 - HALO + r, M);
+  const bool extra = r < 2 * HALO;
+  const int gi1 = extra ? wrapi(i0 - HALO + r + GM_TH, M) : 0;
+  int gj = wrapi(j0 - HALO + cg, N);
+  const int dj = CG % N;
+  for (int lj = cg; lj < W; lj += CG) {
+    const float* col = p + (size_t)gj * M;
+    T[lj * LD + r] = col[gi0];
+    if (extra) T[lj * LD + r + GM_TH] = col[gi1];
+    gj += dj;
+    if (gj >= N) gj -= N;
   }
 }
 
