@@ -48,7 +48,12 @@ ADMMTV_DI void sobel_at(const float* T, int li, int lj, float& gx, float& gy) {
   gx = ((c0[1] - c0[-1]) + 2.f * (c1[1] - c1[-1]) + (c2[1] - c2[-1])) * 0.125f;
   gy = ((c2[-1] - c0[-1]) + 2.f * (c2[0] - c0[0]) + (c2[1] - c0[1])) * 0.125f;
 }
-ADMMTV_DI float gradmag(float gx, float gy) { return sqrtf(gx * gx + gy * gy + 1e-16f); }  // iqa_utils.jl:53-55
+// The loss kernels are instruction-bound, so the per-pixel square root and divisions use the 2-ulp hardware approximations
+// (MUFU.RSQ / MUFU.RCP); the error is far inside the loss tolerances (tests/test_gpu_losses.py).
+ADMMTV_DI float gradmag(float gx, float gy) {   // iqa_utils.jl:53-55
+  const float s = gx * gx + gy * gy + 1e-16f;
+  return s * rsqrtf(s);
+}
 
 // Stage the tile plus its circular halo (pad_circular, iqa_utils.jl:46).  Thread (r, cg) = (tid % TH, tid / TH) loads row r
 // (and, for r < 2*HALO, the extra row r + TH) of every 4th column: no per-element division, the wrapped row index is computed once.
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(GM_NT) k_gmsd_fwd(GmsdArgs A) {
         const float mx = gradmag((xd0 + 2.f * xd1 + xd2) * 0.125f, (xs2 - xs0) * 0.125f);
         const float my = gradmag((yd0 + 2.f * yd1 + yd2) * 0.125f, (ys2 - ys0) * 0.125f);
         const float mm = mx * my;
-        const float g = (2.f * mm - A.alpha * mm + A.t) / (mx * mx + my * my - A.alpha * mm + A.t);  // gmsd.jl:5-10
+        const float g = __fdividef(2.f * mm - A.alpha * mm + A.t, mx * mx + my * my - A.alpha * mm + A.t);  // gmsd.jl:5-10
         const float d = g - 1.f;  // sums of (g-1): well conditioned when x ~ y
         f1 += d;
         f2 += d * d;
@@ -168,9 +173,10 @@ __global__ void __launch_bounds__(GM_NT) k_gmsd_bwd(GmsdArgs A) {
     const float my = gradmag(hx, hy);
     const float mm = mx * my;
     const float den = mx * mx + my * my - A.alpha * mm + A.t;
-    const float g = (2.f * mm - A.alpha * mm + A.t) / den;
-    const float dgdmx = ((2.f - A.alpha) * my - g * (2.f * mx - A.alpha * my)) / den;
-    const float c = scale * (g - mean) * dgdmx / mx;
+    const float rden = __fdividef(1.f, den);
+    const float g = (2.f * mm - A.alpha * mm + A.t) * rden;
+    const float dgdmx = ((2.f - A.alpha) * my - g * (2.f * mx - A.alpha * my)) * rden;
+    const float c = __fdividef(scale * (g - mean) * dgdmx, mx);
     p1[e] = c * gx;
     p2[e] = c * gy;
   }

@@ -120,6 +120,7 @@ static inline void sincospi(double x, double* s, double* c) {
   *c = std::cos(M_PI * x);
 }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 
 // ---- host runtime subset ------------------------------------------------------------------
 typedef int cudaError_t;
