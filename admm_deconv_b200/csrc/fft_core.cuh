@@ -99,8 +99,36 @@ ADMMTV_HD inline int pos_to_freq(int L, int p, bool planned = true) {
 // ------------------------------------------------------------------------------------------
 // complex helpers (float2 = re, im)
 // ------------------------------------------------------------------------------------------
+// Blackwell has packed dual-fp32 arithmetic (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2): one issue slot for both
+// components of a complex add.  The butterflies are more than half additions and the iteration kernels are issue-slot-bound as much
+// as DRAM-bound, so complex add / subtract use it; results are bit-identical to the scalar form (same
+// round-to-nearest adds).  The mov.b64 packs below are register-pair renamings, not instructions.
+#ifndef ADMMTV_F32X2
+#define ADMMTV_F32X2 1
+#endif
+#if ADMMTV_F32X2 && !defined(ADMMTV_EMU)
+ADMMTV_DI float2 cadd(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+}
+ADMMTV_DI float2 csub(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+}
+#else
 ADMMTV_DI float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 ADMMTV_DI float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 ADMMTV_DI float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

@@ -62,7 +62,7 @@ def test_backward_no_threshold_crossing_end_to_end_1e5(be):
     agreement with fp64 autograd (which stands in for Zygote) is <= 1e-5 as well."""
     y, h, _ = make_case(128, 128, 3, 2, 9, 9, 41)
     xbar = torch.from_numpy(np.random.default_rng(3).standard_normal(tuple(y.shape)))
-    r = check_backward(be, y, h, 5.0, 0.05, False, 8, xbar, flags=1, tol=1e-5, tol_scalar=1e-4, tol_e2e=1e-5)
+    r = check_backward(be, y, h, 5.0, 0.05, False, 8, xbar, flags=1, tol=1e-5, tol_scalar=2e-4, tol_e2e=1e-5)   # rhobar is a cancelling sum (DESIGN section 2)
     assert r["flips"] == 0
 
 
