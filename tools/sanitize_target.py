@@ -29,3 +29,22 @@ x2 = A.tvd_fft_grouped(y[:2].contiguous(), torch.full((3,), 0.02, device=dev), t
                        shared_input=True, channel_concat=True, activation="relu1")
 torch.cuda.synchronize()
 print("grouped ok", float(x.mean()), float(x2.mean()))
+# sizes without a register-FFT plan (generic kernels, both mixed dispatches), losses, batch assembly
+for (M, N, P, B, k, iso) in [(20, 24, 1, 2, 3, False), (33, 17, 3, 1, 5, True), (48, 32, 1, 2, 3, False), (32, 224, 1, 1, 3, True), (7, 5, 1, 1, 0, False)]:
+    y = torch.rand(B, P, N, M, device=dev, requires_grad=True)
+    h = None if k == 0 else (torch.rand(1, 1, k, k, device=dev) / (k * k)).requires_grad_(True)
+    lam = torch.tensor([0.02], device=dev, requires_grad=True); rho = torch.tensor([0.1], device=dev, requires_grad=True)
+    x = A.admm_layer_call(y, lam, rho, h, None, 3, iso, "relu1", 0.0)
+    tgt = torch.rand_like(x)
+    (A.gmsd_loss(x, tgt) + (A.ssim_loss(x, tgt) if min(M, N) >= 11 else 0.0)).backward()
+    torch.cuda.synchronize()
+    print("generic", M, N, P, B, k, iso, float(x.mean()), float(lam.grad), flush=True)
+import numpy as np  # noqa: E402
+from admm_deconv_b200.staging import ImageDataFeeder  # noqa: E402
+rng = np.random.default_rng(0)
+xs = [rng.integers(0, 256, size=(70, 50, 3), dtype=np.uint8) for _ in range(3)]
+for resident in (False, True):
+    f = ImageDataFeeder(xs, xs, (33, 40), (33, 40), dev, seed=0, resident=resident)
+    bx, by = f.getindex([2, 0, 1])
+    torch.cuda.synchronize()
+    print("feeder", resident, float(bx.mean()))
