@@ -191,7 +191,7 @@ def run_reference(args, w):
                          "note": "restated reference (torch-CPU fp32, MKL FFT) -- Julia/FFTW cannot run in this image"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(w):
@@ -387,7 +387,7 @@ def run_native(args, w):
                     "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4},
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     elif rank == 0:
         pk, pk_src = peaks()
         # per-kernel-class CUDA-event timing of one forward (profiling twin of the same call)
@@ -446,12 +446,27 @@ def run_native(args, w):
                                "hbm_frac_whole_step": (FWD_BYTES + BWD_BYTES) * px * K_fb / (ms_fb * 1e-3) / 1e9 / pk["hbm_gbs"],
                                "note": "same batch, forward (checkpointed) + hand-written backward + gradient all-reduce, "
                                        "108 B/plane-pixel-iteration model"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else this process (or a library under it, e.g. NCCL's
+    version banner) writes to file descriptor 1 has been re-routed to stderr by main()."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
