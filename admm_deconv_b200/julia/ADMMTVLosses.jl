@@ -8,9 +8,10 @@
 #     # replace  include("metrics/gmsd.jl"); include("metrics/ssim.jl")  by  include("ADMMTVLosses.jl"); using .ADMMTVLosses
 #
 # Same names and argument order: gmsd(x, y, t, α), gmsd_loss, ssim(x, y; peakval), ssim_loss, ssim_loss_fast.
-# Results are 1-element CuArrays reduced on the device (`only(Array(l))` to read); the rrules return the
-# cotangent of the FIRST argument (the prediction) and NoTangent for the target, which is how train.jl:51-53
-# and train_v2.jl:69 use them.
+# The reduction happens on the device; the value is read back as a Float32 scalar (4 bytes), because
+# `Flux.withgradient` (train.jl:51-53) and FluxTraining (train_v2.jl:69) need a real-valued loss.  The rrules
+# return the cotangent of the FIRST argument (the prediction) and NoTangent for the target, which is how both
+# scripts use them.
 module ADMMTVLosses
 
 using CUDA, ChainRulesCore
@@ -38,19 +39,19 @@ function gmsd_fwd(x::CuArray{Float32,4}, y::CuArray{Float32,4}, t::Float32, α::
     out, ws
 end
 
-gmsd(x::CuArray{Float32,4}, y::CuArray{Float32,4}, t::Float32=0.0026f0, α::Float32=0.f0) = gmsd_fwd(x, y, t, α)[1]
+gmsd(x::CuArray{Float32,4}, y::CuArray{Float32,4}, t::Float32=0.0026f0, α::Float32=0.f0) = only(Array(gmsd_fwd(x, y, t, α)[1]))
 gmsd_loss(x, args...; kws...) = gmsd(x, args...; kws...)
 
 function ChainRulesCore.rrule(::typeof(gmsd), x::CuArray{Float32,4}, y::CuArray{Float32,4}, t::Float32=0.0026f0, α::Float32=0.f0)
     out, ws = gmsd_fwd(x, y, t, α)
     function pullback(l̄)
-        M, N, C, B = size(x); x̄ = similar(x); lb = CuArray(Float32[only(Array(unthunk(l̄)))])
+        M, N, C, B = size(x); x̄ = similar(x); lb = CuArray(Float32[unthunk(l̄)])
         check(ccall((:admmtv_gmsd_backward, libadmmtv), Cint,
                     (Cint, Cint, Cint, Cint, Cint, CuPtr{Cfloat}, CuPtr{Cfloat}, Cfloat, Cfloat, CuPtr{Cfloat}, CuPtr{Cvoid}, CuPtr{Cfloat}, Ptr{Cvoid}),
                     M, N, C, B, dev(), x, y, t, α, lb, ws, x̄, strm()))
         (NoTangent(), x̄, NoTangent(), NoTangent(), NoTangent())
     end
-    out, pullback
+    only(Array(out)), pullback
 end
 
 # ---- SSIM (ssim.jl:84-164) ---------------------------------------------------------------------
@@ -67,18 +68,18 @@ function ssim_fwd(x, y, taps, peakval, as_loss::Bool, with_grad::Bool)
     out, ws
 end
 
-_ssim(x, y, taps, peakval, as_loss) = ssim_fwd(x, y, taps, peakval, as_loss, false)[1]
+_ssim(x, y, taps, peakval, as_loss) = only(Array(ssim_fwd(x, y, taps, peakval, as_loss, false)[1]))
 function ChainRulesCore.rrule(::typeof(_ssim), x, y, taps, peakval, as_loss)
     out, ws = ssim_fwd(x, y, taps, peakval, as_loss, true)
     function pullback(ō)
-        M, N, C, B = size(x); x̄ = similar(x); ob = CuArray(Float32[only(Array(unthunk(ō)))])
+        M, N, C, B = size(x); x̄ = similar(x); ob = CuArray(Float32[unthunk(ō)])
         L = taps === nothing ? 0 : length(taps); tp = taps === nothing ? C_NULL : pointer(taps)
         GC.@preserve taps check(ccall((:admmtv_ssim_backward, libadmmtv), Cint,
                     (Cint, Cint, Cint, Cint, Cint, CuPtr{Cfloat}, CuPtr{Cfloat}, Ptr{Cfloat}, Cint, Cint, CuPtr{Cfloat}, CuPtr{Cvoid}, CuPtr{Cfloat}, Ptr{Cvoid}),
                     M, N, C, B, dev(), x, y, tp, L, as_loss, ob, ws, x̄, strm()))
         (NoTangent(), x̄, NoTangent(), NoTangent(), NoTangent(), NoTangent())
     end
-    out, pullback
+    only(Array(out)), pullback
 end
 
 ssim(x::CuArray{Float32,4}, y::CuArray{Float32,4}, taps=nothing; peakval=1f0) = _ssim(x, y, taps, peakval, false)
