@@ -144,7 +144,9 @@ int admmtv_ssim_forward(int M, int N, int C, int B, int device, const float* x, 
   if (e != cudaSuccess) return (int)e;
   const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
   if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
-  ADMMTV_LAUNCH(k_ssim_fwd, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  if (a.L == 11) ADMMTV_LAUNCH(k_ssim_fwd<11>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  else if (a.L == 5) ADMMTV_LAUNCH(k_ssim_fwd<5>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  else ADMMTV_LAUNCH(k_ssim_fwd<0>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
   ADMMTV_LAUNCH(k_ssim_finalize, dim3(1), dim3(1), 0, st, a);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
@@ -172,7 +174,9 @@ int admmtv_ssim_backward(int M, int N, int C, int B, int device, const float* x,
   a.out = xbar;
   const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
   if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
-  ADMMTV_LAUNCH(k_ssim_bwd, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  if (a.L == 11) ADMMTV_LAUNCH(k_ssim_bwd<11>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  else if (a.L == 5) ADMMTV_LAUNCH(k_ssim_bwd<5>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  else ADMMTV_LAUNCH(k_ssim_bwd<0>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ADMMTV_OK : (int)e;
 }

@@ -217,10 +217,12 @@ struct SsimArgs {
   float* out;         // forward: ssim or 1-ssim ; backward: xbar
 };
 
+// LC: compile-time number of taps (11 = the default Gaussian, 5 = ssim_loss_fast: window loops fully unrolled), 0 = run-time A.L
+template <int LC>
 __global__ void __launch_bounds__(SS_NT) k_ssim_fwd(SsimArgs A) {
   __shared__ float xs[SS_IN * SS_IN], ys[SS_IN * SS_IN];
   __shared__ float P[5][SS_IN * SS_T];
-  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L = A.L;
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L = LC > 0 ? LC : A.L;
   const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
   const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
   const size_t plane = (size_t)A.M * A.N;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_fwd(SsimArgs A) {
   for (int e = tid; e < SS_T * ext; e += SS_NT) {
     const int li = e % SS_T, lj = e / SS_T;
     float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
     for (int a = 0; a < L; ++a) {
       const float w = A.f[a], xv = xs[lj * SS_IN + li + a], yv = ys[lj * SS_IN + li + a];
       sx += w * xv; sy += w * yv; sxx += w * xv * xv; syy += w * yv * yv; sxy += w * xv * yv;
@@ -252,7 +255,8 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_fwd(SsimArgs A) {
     const int li = e % SS_T, lj = e / SS_T;
     if (i0 + li < A.Mo && j0 + lj < A.No) {
       float mx = 0.f, my = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
-      for (int a = 0; a < L; ++a) {
+  #pragma unroll
+    for (int a = 0; a < L; ++a) {
         const float w = A.f[a];
         const int o = (lj + a) * SS_T + li;
         mx += w * P[0][o]; my += w * P[1][o]; exx += w * P[2][o]; eyy += w * P[3][o]; exy += w * P[4][o];
@@ -281,10 +285,11 @@ __global__ void k_ssim_finalize(SsimArgs A) {
   A.out[0] = (float)(A.as_loss ? 1.0 - m : m);
 }
 
+template <int LC>
 __global__ void __launch_bounds__(SS_NT) k_ssim_bwd(SsimArgs A) {
   __shared__ float ms[3][SS_IN * SS_IN];
   __shared__ float T[3][SS_IN * SS_T];
-  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L = A.L;
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L = LC > 0 ? LC : A.L;
   const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
   const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
   const size_t plane = (size_t)A.M * A.N, oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_bwd(SsimArgs A) {
   for (int e = tid; e < SS_T * ext; e += SS_NT) {
     const int li = e % SS_T, lj = e / SS_T;
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
     for (int a = 0; a < L; ++a) {
       const float w = A.f[a];
       const int o = lj * SS_IN + li + (L - 1) - a;
@@ -320,7 +326,8 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_bwd(SsimArgs A) {
     const int gi = i0 + li, gj = j0 + lj;
     if (gi < A.M && gj < A.N) {
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-      for (int a = 0; a < L; ++a) {
+  #pragma unroll
+    for (int a = 0; a < L; ++a) {
         const float w = A.f[a];
         const int o = (lj + (L - 1) - a) * SS_T + li;
         r0 += w * T[0][o]; r1 += w * T[1][o]; r2 += w * T[2][o];
