@@ -389,12 +389,12 @@ def test_forward_is_cuda_graph_capturable():
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        A.tvd_fft(y, lam, rho, h, True, 6)
+        A.tvd_fft(y, lam, rho, h, False, 6)
     torch.cuda.current_stream().wait_stream(s)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        xg = A.tvd_fft(y, lam, rho, h, True, 6)
+        xg = A.tvd_fft(y, lam, rho, h, False, 6)
     y.copy_(torch.rand_like(y))
     g.replay()
     torch.cuda.synchronize()
-    assert rel_l2(xg.cpu(), A.tvd_fft(y, lam, rho, h, True, 6).cpu()) <= 1e-6     # isotropic: float atomics, not bitwise
+    assert torch.equal(xg, A.tvd_fft(y, lam, rho, h, False, 6))     # anisotropic path: no atomics, bitwise reproducible
