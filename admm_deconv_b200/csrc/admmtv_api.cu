@@ -40,6 +40,7 @@ static Geom geom(const admmtv_desc* d) {
   g.planned = (g.LM > 0 ? 1 : 0) | (g.LN > 0 ? 2 : 0);
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
   g.G = d->groups > 1 ? d->groups : 1;
+  g.iso = d->iso ? 1 : 0;
   g.Bg = d->B / g.G;
   g.Sg = d->P * g.Bg;
   g.Qg = (g.Sg + 1) / 2;
@@ -72,7 +73,8 @@ struct FwdWs {
   float2* ktab;
   float* mask;
   float2 *bpk, *specA, *specB, *v0, *v1;
-  float *nsq0, *nsq1;  // isotropic: per-pixel |v_k|^2 ring
+  float* npart;        // isotropic: per-pair shares of |v_k|^2 per pixel [Q][N][M]
+  float* nsq0;         // isotropic: per-pixel |v_k|^2 (inference; training keeps them in the checkpoint)
   float *isc0, *isc1;  // isotropic: per-pixel shrink scale ring
   size_t bytes;
 };
@@ -90,10 +92,11 @@ static FwdWs carve_fwd(const Geom& g, void* ws) {
   w.specB = c.take<float2>(g.pk);
   w.v0 = c.take<float2>(2 * g.pk);
   w.v1 = c.take<float2>(2 * g.pk);
-  w.nsq0 = c.take<float>(g.plane * g.G);
-  w.nsq1 = c.take<float>(g.plane * g.G);
-  w.isc0 = c.take<float>(g.plane * g.G);
-  w.isc1 = c.take<float>(g.plane * g.G);
+  const size_t ni = g.iso ? g.plane * g.G : 0;
+  w.npart = c.take<float>(g.iso ? g.pk : 0);
+  w.nsq0 = c.take<float>(ni);
+  w.isc0 = c.take<float>(ni);
+  w.isc1 = c.take<float>(ni);
   w.bytes = c.off;
   return w;
 }
@@ -111,7 +114,7 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
   k.mask = c.take<float>((size_t)(g.nh + 2) * g.G);
   k.vck = c.take<float2>((size_t)(g.K > 1 ? g.K - 1 : 0) * 2 * g.pk);
   k.zck = c.take<float2>((size_t)g.K * g.pk);
-  k.nck = c.take<float>((size_t)(g.K > 1 ? g.K - 1 : 0) * g.plane * g.G);
+  k.nck = c.take<float>(g.iso ? (size_t)(g.K > 1 ? g.K - 1 : 0) * g.plane * g.G : 0);
   k.bytes = c.off;
   return k;
 }
@@ -203,14 +206,6 @@ struct DeviceGuard {
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
-
-// Isotropic per-pixel terms are precomputed by a tiny kernel per iteration when the problem is large
-// (bandwidth-bound); small, latency-bound problems compute them inside the sweep kernels instead.
-static inline bool iso_precompute(const Geom& g, int flags) {
-  if (flags & ADMMTV_FLAG_ISO_PRECOMPUTE) return true;
-  if (flags & ADMMTV_FLAG_ISO_INLINE) return false;
-  return (size_t)g.S * g.plane >= ((size_t)6 << 20);
-}
 
 // Enqueue the setup kernels shared by forward and backward.
 static int run_setup(const Geom& g, const float* h, const float* rho, float2* twM, float2* twN, double2* T,
@@ -400,45 +395,39 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       // isotropic: v_k and the per-pixel norm first (pass A), then shrink + D^T + FFT (pass B)
       const float2* v_in;
       float2* v_out;
-      float* nsq_new;
-      const bool pre = iso_precompute(g, d->flags);
+      float* nsq_new;                                    // |v_k|^2 per pixel (checkpointed for the backward)
       const float* s_prev = (k & 1) ? w.isc1 : w.isc0;   // s_{k-1}
       float* s_new = (k & 1) ? w.isc0 : w.isc1;          // s_k
-      const float* nsq_prev;                             // |v_{k-1}|^2
       if (ckpt) {
         v_in = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
         v_out = ck.vck + (size_t)(k - 1) * 2 * g.pk;
         nsq_new = ck.nck + (size_t)(k - 1) * g.plane * g.G;
-        nsq_prev = k > 1 ? ck.nck + (size_t)(k - 2) * g.plane * g.G : nullptr;
       } else {
         v_in = (k & 1) ? w.v1 : w.v0;
         v_out = (k & 1) ? w.v0 : w.v1;
-        nsq_new = (k & 1) ? w.nsq0 : w.nsq1;
-        nsq_prev = (k & 1) ? w.nsq1 : w.nsq0;
+        nsq_new = w.nsq0;
       }
-      if (k == 1 || !pre) {   // with precompute, later iterations' accumulators are zeroed by the previous k_iso_scale
-        cudaError_t e2 = cudaMemsetAsync(nsq_new, 0, g.plane * g.G * sizeof(float), st);
-        if (e2 != cudaSuccess) return (int)e2;
-      }
-      float* nsq_next = nullptr;
-      if (k + 1 < g.K) nsq_next = ckpt ? ck.nck + (size_t)k * g.plane * g.G : (((k + 1) & 1) ? w.nsq0 : w.nsq1);
       tm_mark(tm, st, 1);
       Dim1FwdArgs fa{};
       fa.spec_in = w.specB; fa.twM = w.twM; fa.lambda = lambda; fa.rho = rho; fa.N = g.N; fa.Qg = g.Qg;
-      fa.vprev = v_in; fa.vnew = v_out; fa.nsq = pre ? s_prev : nsq_prev; fa.pre = pre ? 1 : 0; fa.nsq_out = nsq_new;
+      fa.vprev = v_in; fa.vnew = v_out; fa.nsq = s_prev; fa.nsq_out = w.npart;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_a(g, k > 1, fa, st); })
       if (rc) return rc;
-      if (hk && hk->allreduce_sum) {   // exact global-batch norm across ranks (admmtv_forward_ex)
+      // the pairs' shares -> |v_k|^2 per pixel in a fixed order (bit-reproducible), then the shrink scale s_k
+      const dim3 sgrid((unsigned)((g.plane + 255) / 256), (unsigned)g.G);
+      const bool xrank = hk && hk->allreduce_sum;   // exact global-batch norm across ranks (admmtv_forward_ex)
+      ADMMTV_LAUNCH(k_iso_scale, sgrid, dim3(256), 0, st, (const float*)w.npart, g.Qg, nsq_new, (const float*)lambda,
+                    (const float*)rho, xrank ? (float*)nullptr : s_new, (int)g.plane);
+      ADMMTV_CHECK_LAUNCH();
+      if (xrank) {
         if ((rc = hk->allreduce_sum(nsq_new, g.plane * g.G, stream, hk->user))) return rc;
-      }
-      if (pre) {
-        ADMMTV_LAUNCH(k_iso_scale, dim3((unsigned)((g.plane + 255) / 256), (unsigned)g.G), dim3(256), 0, st, (const float*)nsq_new,
-                      (const float*)lambda, (const float*)rho, s_new, nsq_next, (int)g.plane);
+        ADMMTV_LAUNCH(k_iso_scale, sgrid, dim3(256), 0, st, (const float*)nullptr, g.Qg, nsq_new, (const float*)lambda,
+                      (const float*)rho, s_new, (int)g.plane);
         ADMMTV_CHECK_LAUNCH();
       }
       Dim1FwdArgs f{};
       f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM; f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
-      f.vprev = v_out; f.nsq = pre ? (const float*)s_new : (const float*)nsq_new; f.pre = pre ? 1 : 0;
+      f.vprev = v_out; f.nsq = s_new;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_b(g, f, st); })
       if (rc) return rc;
     }

@@ -33,6 +33,7 @@ struct Geom {
   int M, N, P, B, S, Q, LM, LN, K, kh, kw, nh;   // LM / LN: size ids (fft_core.cuh dim_id); 0 = generic-size kernels for that pass
   int planned;   // bit 0: dim-1 spectra in the plan's digit-reversed order (else natural); bit 1: same for dim 2
   int G, Bg, Sg, Qg;  // groups, images / planes / pairs per group (S = G*Sg planes, Q = G*Qg pairs)
+  int iso;            // isotropic TV: the workspaces carry the per-pair partial sums of the per-pixel reductions
   PlaneMap pm;
   size_t plane;  // N*M
   size_t pk;     // Q*N*M  (pair-packed complex elements)
@@ -67,8 +68,7 @@ struct Dim1FwdArgs {
   const float2* vprev;  // [Q][2][N][M]; ignored when !HAS_VPREV (v_0 = 0)
   float2* vnew;         // [Q][2][N][M]
   const float* nsq;     // isotropic: per-pixel shrink scale s [G][N][M] (pass B: s_k ; pass A: s_{k-1}), k_iso_scale
-  float* nsq_out;       // isotropic pass A: accumulates |v_k|^2 (zeroed by the host)
-  int pre;              // 1: `nsq` holds the precomputed scale s; 0: it holds |v|^2 and s is computed in the kernel
+  float* nsq_out;       // isotropic pass A: [Q][N][M], pair q's share of |v_k|^2 per pixel (k_iso_scale adds them in order)
   const float2* twM;
   const float* lambda;  // [G]
   const float* rho;     // [G]
@@ -103,14 +103,11 @@ struct Dim1BwdArgs {
   const float* lambda;
   const float* rho;
   double* acc;             // [0] rhobar (direct term), [1] taubar
-  const float2* sc;        // isotropic pass B: per-pixel (s, tau ip / n^3) [G][N][M] (k_iso_coef), or null:
-  const float* nsq;        //   then |v_{k-1}|^2 and
-  const float* ip;         //   <q, v_{k-1}> per pixel, and the terms are computed in the kernel
-  float* ip_out;           // isotropic pass A: accumulates <q, v_{k-1}> (zeroed by the host)
+  const float2* sc;        // isotropic pass B: per-pixel (s, tau ip / n^3) [G][N][M] (k_iso_coef)
+  float* ip_out;           // isotropic pass A: [Q][N][M], pair q's share of <q, v_{k-1}> per pixel (k_iso_coef adds them in order)
   PlaneMap pm;
   int N, S;
   int first;               // 1: bbar is written, not accumulated (k = K)
-  int count_tau;           // isotropic inline path: 0 = another rank adds the per-pixel taubar terms (admmtv_backward_ex)
 };
 
 // variants of k_dim2: (MUL, SAVE_Z, ACC, FWD_ONLY)

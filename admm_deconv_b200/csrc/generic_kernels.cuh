@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(GK_NT) gk_out(OutArgs A, int M, int Q, int mod
 
 // ---- forward sweep (the stencil of k_dim1_fwd; X = x_k, spatial, [Q][N][M]) --------------------------------------
 //   mode 0: v_k = D x_k + u_{k-1} (stored) ; r = b + rho D^T (z_k - u_k) -> rout           (ops.jl:168-173)
-//   mode 2: isotropic pass A: v_k stored, nsq_out += |v_k|^2
-//   mode 1: isotropic pass B: r = b + rho D^T ((2 s_k - 1) v_k) -> rout   (v_k in A.vprev, s_k or |v_k|^2 in A.nsq)
+//   mode 2: isotropic pass A: v_k stored, nsq_out[q][pixel] = this pair's |v_k|^2 (summed in order by k_iso_scale)
+//   mode 1: isotropic pass B: r = b + rho D^T ((2 s_k - 1) v_k) -> rout   (v_k in A.vprev, s_k in A.nsq)
 __global__ void __launch_bounds__(GK_NT) gk_sweep_fwd(Dim1FwdArgs A, const float2* X, float2* rout, int M, int Q, int mode,
                                                       int has_vprev) {
   const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
@@ -326,8 +326,7 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_fwd(Dim1FwdArgs A, const float
   const size_t q1 = ((size_t)p.q * 2 + 0) * p.plane, q2 = ((size_t)p.q * 2 + 1) * p.plane, qx = (size_t)p.q * p.plane;
   const size_t o = p.o, oj = (size_t)p.jp1 * M + p.i, oi = (size_t)p.j * M + p.ip1;   // (i,j), (i,j+1), (i+1,j)
   const float* ng = mode != 0 ? A.nsq + (size_t)grp * p.plane : nullptr;
-  const bool pre = A.pre != 0;
-  auto SC = [&](float t) { return pre ? t : iso_scale(t, tau); };
+  auto SC = [&](float t) { return t; };   // A.nsq holds the shrink scale s (k_iso_scale)
   if (mode == 1) {
     const float2 w1 = shrink_iso(A.vprev[q1 + o], SC(ng[o])).w, w1n = shrink_iso(A.vprev[q1 + oj], SC(ng[oj])).w;
     const float2 w2 = shrink_iso(A.vprev[q2 + o], SC(ng[o])).w, w2n = shrink_iso(A.vprev[q2 + oi], SC(ng[oi])).w;
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_fwd(Dim1FwdArgs A, const float
   A.vnew[q1 + o] = v1;
   A.vnew[q2 + o] = v2;
   if (mode == 2) {
-    atomicAdd(A.nsq_out + (size_t)grp * p.plane + o, v1.x * v1.x + v1.y * v1.y + v2.x * v2.x + v2.y * v2.y);
+    A.nsq_out[qx + o] = v1.x * v1.x + v1.y * v1.y + v2.x * v2.x + v2.y * v2.y;
     return;
   }
   const float2 v1n = cadd(csub(X[qx + oj], x0), U(q1, oj));   // channel 1 at (i, j+1)
@@ -361,7 +360,7 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_fwd(Dim1FwdArgs A, const float
 
 // ---- backward sweep (the stencil of k_dim1_bwd; R = rbar_k, spatial) ---------------------------------------------
 //   mode 0 / 1: bbar (+)= R (mode 0) ; vbar_{k-1} stored ; xbar_{k-1} = D^T vbar_{k-1} -> xout ; rhobar / taubar sums
-//   mode 2: isotropic pass A: bbar (+)= R ; ip_out += <q, v_{k-1}>
+//   mode 2: isotropic pass A: bbar (+)= R ; ip_out[q][pixel] = this pair's <q, v_{k-1}> (summed in order by k_iso_coef)
 __global__ void __launch_bounds__(GK_NT) gk_sweep_bwd(Dim1BwdArgs A, const float2* R, float2* xout, int M, int Q, int mode,
                                                       int has_vbar) {
   const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
@@ -383,7 +382,7 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_bwd(Dim1BwdArgs A, const float
       const float2 qa = csub(make_float2(2.f * rho * d1.x, 2.f * rho * d1.y), E(q1, o));
       const float2 qb = csub(make_float2(2.f * rho * d2.x, 2.f * rho * d2.y), E(q2, o));
       const float2 va = A.vck[q1 + o], vb = A.vck[q2 + o];
-      atomicAdd(A.ip_out + (size_t)grp * p.plane + o, qa.x * va.x + qa.y * va.y + qb.x * vb.x + qb.y * vb.y);
+      A.ip_out[qx + o] = qa.x * va.x + qa.y * va.y + qb.x * vb.x + qb.y * vb.y;
     } else {
       const float2 d1n = csub(R[qx + oj], r0), d2n = csub(R[qx + oi], r0);   // channel 1 at (i,j+1), channel 2 at (i+1,j)
       float2 n1, n2, n1n, n2n;
@@ -393,15 +392,7 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_bwd(Dim1BwdArgs A, const float
         n1n = bwd_point(d1n, A.vck[q1 + oj], E(q1, oj), rho, tau, false, racc, tacc);
         n2n = bwd_point(d2n, A.vck[q2 + oi], E(q2, oi), rho, tau, false, racc, tacc);
       } else {
-        const bool pre = A.sc != nullptr;
-        const bool tau_owner = (p.q % A.pm.Qg) == 0 && A.count_tau != 0;
-        auto PIX = [&](size_t off, bool count) {
-          if (pre) return A.sc[(size_t)grp * p.plane + off];
-          float s_, c_, t_;
-          iso_pix(A.nsq[(size_t)grp * p.plane + off], A.ip[(size_t)grp * p.plane + off], tau, s_, c_, t_);
-          if (count && tau_owner) tacc -= (double)t_;
-          return make_float2(s_, c_);
-        };
+        auto PIX = [&](size_t off, bool) { return A.sc[(size_t)grp * p.plane + off]; };   // (s, tau ip / n^3), k_iso_coef
         const float2 s0 = PIX(o, true), sj = PIX(oj, false), si = PIX(oi, false);
         n1 = iso_bwd_full(d1, A.vck[q1 + o], E(q1, o), rho, s0, true, racc);
         n2 = iso_bwd_full(d2, A.vck[q2 + o], E(q2, o), rho, s0, true, racc);

@@ -547,6 +547,20 @@ ADMMTV_DI void load_rows_f(const float* __restrict__ p, float* out) {
   }
 }
 
+template <int RPT>
+ADMMTV_DI void store_rows_f(float* __restrict__ p, const float* v) {
+  if constexpr (RPT % 4 == 0) {
+#pragma unroll
+    for (int r = 0; r < RPT / 4; ++r) *reinterpret_cast<float4*>(p + 4 * r) = make_float4(v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]);
+  } else if constexpr (RPT % 2 == 0) {
+#pragma unroll
+    for (int r = 0; r < RPT / 2; ++r) *reinterpret_cast<float2*>(p + 2 * r) = make_float2(v[2 * r], v[2 * r + 1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) p[r] = v[r];
+  }
+}
+
 // isotropic block thresholding (ops.jl:6,10): one scale per pixel, s = max(1 - tau/n, 0)
 ADMMTV_DI float iso_scale(float nsq, float tau) {
   const float n = sqrtf(nsq);
@@ -562,9 +576,10 @@ ADMMTV_DI Shrunk shrink_iso(float2 v, float s) {
 
 // MODE 0: the fused anisotropic kernel described above.
 // MODE 1: isotropic pass B -- v_k (A.vprev) and the per-pixel shrink scale s_k = max(1 - tau/n_k, 0) (A.nsq,
-//         precomputed by k_iso_scale) are given; no IFFT, no state write: w = (2s-1) v, r = b + rho D^T w, FFT.
+//         computed by k_iso_scale) are given; no IFFT, no state write: w = (2s-1) v, r = b + rho D^T w, FFT.
 // MODE 2: isotropic pass A -- dim-1 IFFT -> x_k ; v_k = D x_k + u_{k-1} with u_{k-1} = (1 - s_{k-1}) v_{k-1}
-//         (A.vprev, A.nsq = s_{k-1}) ; store v_k ; A.nsq_out[pixel] += |v_k|^2 (float atomics) ; no FFT.
+//         (A.vprev, A.nsq = s_{k-1}) ; store v_k ; A.nsq_out[q][pixel] = this pair's share of |v_k|^2 (plain stores:
+//         k_iso_scale adds the pairs of a group in a fixed order, so the norm is bit-reproducible) ; no FFT.
 template <int LM, bool HAS_VPREV, int MODE = 0>
 __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
@@ -614,9 +629,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   const float tau = A.lambda[grp] / rho;  // ops.jl:102
   const int i0 = tid * RPT;
   const float* nsq_g = MODE != 0 ? A.nsq + (size_t)grp * plane : nullptr;
-  const bool pre = A.pre != 0;  // A.nsq holds the precomputed scale s (large problems) or |v|^2 (small, latency-bound ones)
-  auto SC = [&](float t) { return pre ? t : iso_scale(t, tau); };
-  float* nsq_o = MODE == 2 ? A.nsq_out + (size_t)grp * plane : nullptr;
+  float* nsq_o = MODE == 2 ? A.nsq_out + (size_t)q * plane : nullptr;   // per-pair partial sums
   const float2* vp1 = A.vprev + ((size_t)q * 2 + 0) * plane;
   const float2* vp2 = A.vprev + ((size_t)q * 2 + 1) * plane;
   float2* vn1 = A.vnew + ((size_t)q * 2 + 0) * plane;
@@ -635,7 +648,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       float2 v = csub(X[sidx<LM>(1, i0 + r)], X[sidx<LM>(0, i0 + r)]);
-      if (HAS_VPREV) v = cadd(v, shrink_iso(up[r], SC(nn[r])).u);
+      if (HAS_VPREV) v = cadd(v, shrink_iso(up[r], nn[r]).u);
       w1c[r] = v;
     }
     store_rows<RPT>(vn1 + (size_t)j * M + i0, w1c);
@@ -646,7 +659,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     load_rows<RPT>(vp1 + (size_t)j * M + i0, vv);
     load_rows_f<RPT>(nsq_g + (size_t)j * M + i0, nn);
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) w1c[r] = shrink_iso(vv[r], SC(nn[r])).w;
+    for (int r = 0; r < RPT; ++r) w1c[r] = shrink_iso(vv[r], nn[r]).w;
   } else {
     const int j = jcol(1);
     float2 up[RPT], vst[RPT];
@@ -701,7 +714,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
           for (int r = 0; r < RPT; ++r) {
             float2 v = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
-            if (HAS_VPREV) v = cadd(v, shrink_iso(g1[cc][r], SC(n1[cc][r])).u);
+            if (HAS_VPREV) v = cadd(v, shrink_iso(g1[cc][r], n1[cc][r]).u);
             w1n[r] = v;
           }
           store_rows<RPT>(vn1 + (size_t)jn * M + i0, w1n);
@@ -711,21 +724,20 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
           float2 v = csub(xc[r + 1], xc[r]);
-          if (HAS_VPREV) v = cadd(v, shrink_iso(g2[cc][r], SC(n2[cc][r])).u);
+          if (HAS_VPREV) v = cadd(v, shrink_iso(g2[cc][r], n2[cc][r]).u);
           vst[r] = v;
           sq[r] = w1c[r].x * w1c[r].x + w1c[r].y * w1c[r].y + v.x * v.x + v.y * v.y;
           w1c[r] = w1n[r];
         }
         store_rows<RPT>(vn2 + (size_t)j * M + i0, vst);
-#pragma unroll
-        for (int r = 0; r < RPT; ++r) atomicAdd(nsq_o + (size_t)j * M + i0 + r, sq[r]);
+        store_rows_f<RPT>(nsq_o + (size_t)j * M + i0, sq);
         continue;
       }
       if (MODE == 1) {
 #pragma unroll
-        for (int r = 0; r < RPT; ++r) w1n[r] = shrink_iso(g1[cc][r], SC(n1[cc][r])).w;
+        for (int r = 0; r < RPT; ++r) w1n[r] = shrink_iso(g1[cc][r], n1[cc][r]).w;
 #pragma unroll
-        for (int r = 0; r <= RPT; ++r) w2[r] = shrink_iso(g2[cc][r], SC(n2[cc][r])).w;
+        for (int r = 0; r <= RPT; ++r) w2[r] = shrink_iso(g2[cc][r], n2[cc][r]).w;
       } else {
       float2 xc[RPT + 2];  // rows i0-1 .. i0+RPT of column col
       xc[0] = X[sidx<LM>(col, wrapm<M>(i0 - 1))];

@@ -68,7 +68,8 @@ ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float2 s
 }
 
 // MODE 2: isotropic pass A -- dim-1 IFFT -> rbar_k ; bbar += rbar_k ; q = 2 rho D rbar_k - vbar_k ;
-//         A.ip_out[pixel] += <q, v_{k-1}> (float atomics) ; nothing else is written.
+//         A.ip_out[q][pixel] = this pair's share of <q, v_{k-1}> (plain stores; k_iso_coef adds the pairs of a group in
+//         a fixed order, so the result is bit-reproducible) ; nothing else is written.
 // MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel (s, tau ip / n^3) in A.sc from k_iso_coef, which also
 // adds the per-pixel taubar terms; bbar was accumulated by pass A).
 template <int LM, bool HAS_VBAR, int MODE = 0>
@@ -112,20 +113,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   const float tau = A.lambda[grp] / rho;
   const int i0 = tid * RPT;
   double racc = 0.0, tacc = 0.0;
-  const bool pre = MODE == 1 && A.sc != nullptr;  // per-pixel (s, tau ip / n^3) precomputed by k_iso_coef
-  const float2* sc_g = pre ? A.sc + (size_t)grp * plane : nullptr;
-  const float* nsq_g = (MODE == 1 && !pre) ? A.nsq + (size_t)grp * plane : nullptr;
-  const float* ip_g = (MODE == 1 && !pre) ? A.ip + (size_t)grp * plane : nullptr;
-  const bool tau_owner = (q % A.pm.Qg) == 0 && A.count_tau != 0;  // inline path: the per-pixel taubar term is counted once per group
-  // (s, coef) of one pixel: loaded, or computed here (small, latency-bound problems skip the extra launch)
-  auto PIX = [&](const float2* scp, size_t off, bool count) {
-    if (pre) return scp[off];
-    float s_, c_, t_;
-    iso_pix(nsq_g[off], ip_g[off], tau, s_, c_, t_);
-    if (count && tau_owner) tacc -= (double)t_;
-    return make_float2(s_, c_);
-  };
-  float* ip_o = MODE == 2 ? A.ip_out + (size_t)grp * plane : nullptr;
+  const float2* sc_g = MODE == 1 ? A.sc + (size_t)grp * plane : nullptr;   // per-pixel (s, tau ip / n^3) from k_iso_coef
+  auto PIX = [&](const float2* scp, size_t off, bool) { return scp[off]; };
+  float* ip_o = MODE == 2 ? A.ip_out + (size_t)q * plane : nullptr;   // per-pair partial sums
   const float2* v1 = A.vck + ((size_t)q * 2 + 0) * plane;
   const float2* v2 = A.vck + ((size_t)q * 2 + 1) * plane;
   const float2* e1 = A.vbar_in + ((size_t)q * 2 + 0) * plane;
@@ -201,7 +191,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
 
       if (MODE == 2) {
         float2 bb[RPT], vv[RPT], ee[RPT], v2v[RPT], e2v[RPT];
-        float p1n[RPT];
+        float p1n[RPT], ipv[RPT];
         if (!A.first) load_rows<RPT>(bq + (size_t)j * M + i0, bb);
         if (col < nout) {
           load_rows<RPT>(v1 + (size_t)jn * M + i0, vv);
@@ -223,9 +213,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
           const float2 d2 = csub(xc[r + 1], xc[r]);
           float2 q2 = make_float2(2.f * rho * d2.x, 2.f * rho * d2.y);
           if (HAS_VBAR) q2 = csub(q2, e2v[r]);
-          atomicAdd(ip_o + (size_t)j * M + i0 + r, p1c[r] + q2.x * v2v[r].x + q2.y * v2v[r].y);
+          ipv[r] = p1c[r] + q2.x * v2v[r].x + q2.y * v2v[r].y;
           p1c[r] = p1n[r];
         }
+        store_rows_f<RPT>(ip_o + (size_t)j * M + i0, ipv);
         continue;
       }
       // bbar += rbar_k

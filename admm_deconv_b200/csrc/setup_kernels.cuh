@@ -120,36 +120,54 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
 }
 
 
-// ------------------------------------------------------------------------------------------
-// isotropic per-pixel terms (one thread per pixel of one group; blockIdx.y = group)
-// ------------------------------------------------------------------------------------------
-// s = max(1 - tau / n, 0), n = sqrt(nsq)                                   (BT, ops.jl:10; n = 0 -> 0)
-// also zeroes `zero_next` (the accumulator of the NEXT iteration), which replaces a memset launch
-static __global__ void k_iso_scale(const float* __restrict__ nsq, const float* __restrict__ lambda, const float* __restrict__ rho,
-                                   float* __restrict__ s_out, float* __restrict__ zero_next, int npix) {
+// Isotropic TV (ops.jl:6,10): the per-pixel norm spans every plane of the call (a group).  The sweep kernels write each
+// pair's share per pixel with plain stores; these kernels add the Qg shares of a group IN A FIXED ORDER (pair 0, 1, ...),
+// so the norm -- and with it every threshold decision n > tau -- is bit-reproducible run to run (no float atomics).
+//   part != null : nsq[g][i] = sum_q part[g*Qg + q][i]       (else nsq is taken as given: after a cross-rank all-reduce)
+//   s_out != null: s_out[g][i] = max(1 - tau/n, 0), n = sqrt(nsq)
+static __global__ void k_iso_scale(const float* __restrict__ part, int Qg, float* __restrict__ nsq, const float* __restrict__ lambda,
+                                   const float* __restrict__ rho, float* __restrict__ s_out, int npix) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = blockIdx.y;
   if (i >= npix) return;
-  if (zero_next) zero_next[(size_t)g * npix + i] = 0.f;
-  const float tau = lambda[g] / rho[g];
-  const float n = sqrtf(nsq[(size_t)g * npix + i]);
-  s_out[(size_t)g * npix + i] = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
+  float t;
+  if (part) {
+    const float* pp = part + (size_t)g * Qg * npix + i;
+    t = 0.f;
+    for (int q = 0; q < Qg; ++q) t += pp[(size_t)q * npix];
+    nsq[(size_t)g * npix + i] = t;
+  } else {
+    t = nsq[(size_t)g * npix + i];
+  }
+  if (s_out) {
+    const float tau = lambda[g] / rho[g];
+    const float n = sqrtf(t);
+    s_out[(size_t)g * npix + i] = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
+  }
 }
-// backward: (s, 1[n>tau] tau ip / n^3) per pixel, and taubar -= sum_pixels 1[n>tau] ip / n   (acc[8g+1])
-// re-zeroes ip for the next iteration's accumulation (replaces a memset launch)
-static __global__ void k_iso_coef(const float* __restrict__ nsq, float* __restrict__ ip, const float* __restrict__ lambda,
-                                  const float* __restrict__ rho, float2* __restrict__ sc, double* acc, int npix,
-                                  int count_tau) {
+// backward: ip[g][i] = sum_q part[g*Qg + q][i] (fixed order; skipped when part is null), then, when sc != null,
+// (s, 1[n>tau] tau ip / n^3) per pixel and taubar -= sum_pixels 1[n>tau] ip / n   (acc[8g+1], when count_tau)
+static __global__ void k_iso_coef(const float* __restrict__ part, int Qg, const float* __restrict__ nsq, float* __restrict__ ip,
+                                  const float* __restrict__ lambda, const float* __restrict__ rho, float2* __restrict__ sc,
+                                  double* acc, int npix, int count_tau) {
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i0 < npix;
   const int i = live ? i0 : 0;   // every thread takes part in the block reduction
   const int g = blockIdx.y;
+  float p;
+  if (part) {
+    const float* pp = part + (size_t)g * Qg * npix + i;
+    p = 0.f;
+    for (int q = 0; q < Qg; ++q) p += pp[(size_t)q * npix];
+    if (live) ip[(size_t)g * npix + i] = p;
+  } else {
+    p = ip[(size_t)g * npix + i];
+  }
+  if (!sc) return;   // uniform over the block
   const float tau = lambda[g] / rho[g];
   const float n = sqrtf(nsq[(size_t)g * npix + i]);
-  const float p = ip[(size_t)g * npix + i];
   const bool act = live && n > tau;
   if (live) {
-    ip[(size_t)g * npix + i] = 0.f;
     const float s = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
     sc[(size_t)g * npix + i] = make_float2(s, act ? tau * p / (n * n * n) : 0.f);
   }

@@ -47,8 +47,9 @@ enum {
   /* grouped calls (desc.groups > 1), see below */
   ADMMTV_FLAG_SHARED_INPUT = 4,  /* every group reads the same y (M,N,P,B/groups) */
   ADMMTV_FLAG_CHANNEL_CONCAT = 8, /* x_out is (M,N,groups*P,B/groups): group g in channels [gP,(g+1)P) */
-  /* isotropic per-pixel terms: precomputed by a tiny kernel per iteration (default for >= 6 Mi plane-pixels)
-   * or computed inside the sweep kernels (default below that, where launches dominate).  Overrides: */
+  /* accepted and ignored (kept for ABI stability): the isotropic per-pixel terms are always reduced by a small
+   * kernel per iteration that adds the plane pairs' shares in a fixed order, so the isotropic path is
+   * bit-reproducible run to run (no floating-point atomics on it) */
   ADMMTV_FLAG_ISO_PRECOMPUTE = 16,
   ADMMTV_FLAG_ISO_INLINE = 32
 };

@@ -41,23 +41,40 @@ def forward_states(y, lam, rho, h, iso, K):
     return x, [(s[1], s[2]) for s in st[:-1]]
 
 
-def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, torch.Tensor]], nograd_repeat=False):
+def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, torch.Tensor]], nograd_repeat=False,
+             nsq_states: Optional[List[torch.Tensor]] = None, fp32_gate: bool = False):
     """Exact adjoint given the states v_1..v_{K-1} (each (M,N,P,B) fp64 pair).  Returns
-    dict(x=ybar, lam, rho, weight)."""
+    dict(x=ybar, lam, rho, weight, gate_margin).
+
+    Teacher forcing covers every DECISION of the replayed forward, not only its states:
+      * nsq_states -- isotropic: the per-pixel |v_k|^2 (M,N) that the device forward accumulated in fp32 and
+        checkpointed (k = 1..K-1).  The norm n = sqrt_fp32(nsq) and the gate n > tau are then the device's own; without
+        it the norm is recomputed in fp64 from v, and a pixel with n within rounding of tau can take the other branch
+        of BT (ops.jl:10), whose derivative coefficient tau <v,q> / n^3 is discontinuous there.
+      * fp32_gate -- the comparisons |v| > tau (ST) and n > tau (BT) use tau rounded as the device rounds it
+        (fp32 lambda / rho); the arithmetic keeps the fp64 tau.
+    gate_margin = the smallest relative distance of a decision variable from tau (how close a flip was)."""
     M, N, P, B = y.shape
     tau = lam / rho
+    tau_g = (lam.float() / rho.float()).double() if fp32_gate else tau
+    margin = float("inf")
     Sig, L, C = _full_tables(M, N, h, rho)
     C4 = C.reshape(M, N, 1, 1)
     fft2 = lambda t: torch.fft.fftn(t, dim=(0, 1))
     ifft2 = lambda T: torch.fft.ifftn(T, dim=(0, 1)).real
     b = y if h is None or h.numel() == 0 else O.Ht_roll(y, h)
 
-    def shrink(v1, v2):
+    def shrink(v1, v2, k):
         if iso:
-            n = torch.sqrt(torch.sum(v1 * v1 + v2 * v2, dim=(2, 3), keepdim=True))
+            if nsq_states is not None and k >= 1:
+                n = torch.sqrt(nsq_states[k - 1].float()).double().reshape(M, N, 1, 1)   # the device's fp32 norm
+            else:
+                n = torch.sqrt(torch.sum(v1 * v1 + v2 * v2, dim=(2, 3), keepdim=True))
             s = torch.where(n > 0, torch.clamp(1 - tau / n, min=0), torch.zeros_like(n))
+            s = torch.where(n > tau_g, s, torch.zeros_like(s))   # the gate as the device takes it
             return s * v1, s * v2, n, s
-        return O.ST(v1, tau), O.ST(v2, tau), None, None
+        m1, m2 = v1.abs() > tau_g, v2.abs() > tau_g
+        return torch.where(m1, v1 - torch.sign(v1) * tau, torch.zeros_like(v1)), torch.where(m2, v2 - torch.sign(v2) * tau, torch.zeros_like(v2)), None, None
 
     zero = torch.zeros_like(y)
     vs = [(zero, zero)] + list(v_states)          # vs[k] = v_k, v_0 = 0
@@ -69,7 +86,7 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
     for k in range(K, 0, -1):
         xk = (xbar if k == K else 0) + (O.Dt_roll(vb1, vb2) if k < K else 0)
         v1, v2 = vs[k - 1]
-        z1, z2, n, s = shrink(v1, v2)
+        z1, z2, n, s = shrink(v1, v2, k - 1)
         g1, g2 = 2 * z1 - v1, 2 * z2 - v2
         r = b + rho * O.Dt_roll(g1, g2)
         Zb = fft2(xk)
@@ -84,21 +101,23 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
         q1, q2 = 2 * gb1 - vb1, 2 * gb2 - vb2
         if iso:
             ip = torch.sum(q1 * v1 + q2 * v2, dim=(2, 3), keepdim=True)
-            act = n > tau
+            act = n > tau_g
+            margin = min(margin, float(((n - tau_g).abs() / tau_g).min()))
             coef = torch.where(act, tau * ip / n ** 3, torch.zeros_like(n))
             nv1 = vb1 - gb1 + s * q1 + coef * v1
             nv2 = vb2 - gb2 + s * q2 + coef * v2
             taubar = taubar - torch.where(act, ip / n, torch.zeros_like(n)).sum()
         else:
-            m1 = (v1.abs() > tau).to(DT)
-            m2 = (v2.abs() > tau).to(DT)
+            m1 = (v1.abs() > tau_g).to(DT)
+            m2 = (v2.abs() > tau_g).to(DT)
+            margin = min(margin, float(((v1.abs() - tau_g).abs() / tau_g).min()), float(((v2.abs() - tau_g).abs() / tau_g).min()))
             nv1 = vb1 - gb1 + m1 * q1
             nv2 = vb2 - gb2 + m2 * q2
             taubar = taubar - (torch.sign(v1) * m1 * q1).sum() - (torch.sign(v2) * m2 * q2).sum()
         vb1, vb2 = nv1, nv2
     Sbar = -(G / (M * N)) * C * C
     rhobar = rhobar + (Sbar * L).sum()
-    out = {"lam": (taubar / rho).reshape(1), "rho": (rhobar - taubar * lam / rho ** 2).reshape(1)}
+    out = {"lam": (taubar / rho).reshape(1), "rho": (rhobar - taubar * lam / rho ** 2).reshape(1), "gate_margin": margin}
     if h is None or h.numel() == 0:
         out["x"] = bbar
         out["weight"] = None
@@ -115,6 +134,16 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
                 hb[a, c] += (bbar * torch.roll(y, shifts=(-(a - pd), -(c - pr)), dims=(0, 1))).sum()
     out["weight"] = hb.reshape(kh, kw, 1, 1)
     return out
+
+
+def count_gate_flips_iso(nsq_dev: List[torch.Tensor], v_ref, tau: float) -> int:
+    """Isotropic: how many per-pixel decisions n > tau differ between the device's checkpointed norms and the
+    norms of a reference state list (one decision per pixel and iteration)."""
+    n = 0
+    for nd, (b1, b2) in zip(nsq_dev, v_ref):
+        nr = torch.sqrt(torch.sum(b1 * b1 + b2 * b2, dim=(2, 3)))
+        n += int(((torch.sqrt(nd.double()) > tau) != (nr > tau)).sum())
+    return n
 
 
 def count_mask_flips(v_a, v_b, tau: float) -> int:

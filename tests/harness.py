@@ -151,6 +151,19 @@ class Backend:
         return states
 
 
+    def ckpt_norms(self, fwd):
+        """Isotropic: the per-pixel |v_k|^2 the device accumulated (fp32, fixed-order sum over the plane pairs) and
+        checkpointed, k = 1..K-1, as (M,N) fp32 torch arrays (single-group calls)."""
+        d = fwd["desc"]
+        M, N, K = d.M, d.N, d.iters
+        off = self.lib.ckpt_layout(d)
+        raw = fwd["ckpt"].get()
+        n = (K - 1) * N * M
+        a = raw[off[3]:off[3] + 4 * n].view(np.float32).reshape(K - 1, N, M)
+        return [torch.from_numpy(np.ascontiguousarray(a[k].T)) for k in range(K - 1)]
+
+
+
 class EmuBackend(Backend):
     gpu = False
 

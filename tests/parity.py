@@ -54,9 +54,11 @@ def check_backward(be, y, h, lam, rho, iso, K, xbar, act="identity", bias=None, 
     hc = None if h is None else T(f["h"].get()).reshape(h.shape)
     x_dev = T(f["x"].get())
     states = be.ckpt_states(f)
+    # isotropic: the teacher-forced adjoint also replays the device's per-pixel norms, hence its gates n > tau
+    norms = be.ckpt_norms(f) if (iso and K > 1) else None
     xbar_eff = xbar * act_grad(x_dev, act)
-    tf = TF.backward(xbar_eff, y, lt, rt, hc, iso, K, states, nograd_repeat=bool(flags & 2))
-    res = {}
+    tf = TF.backward(xbar_eff, y, lt, rt, hc, iso, K, states, nograd_repeat=bool(flags & 2), nsq_states=norms, fp32_gate=True)
+    res = {"gate_margin": tf["gate_margin"]}
     res["ybar"] = rel_l2(T(g["ybar"]), tf["x"])
     assert res["ybar"] < tol, ("ybar", res["ybar"])
     if K > 1:
@@ -75,6 +77,8 @@ def check_backward(be, y, h, lam, rho, iso, K, xbar, act="identity", bias=None, 
     _, st64 = TF.forward_states(y, lt, rt, hc, iso, K)
     if not iso:
         res["flips"] = TF.count_mask_flips(states, st64, float(lt / rt))
+    elif K > 1:
+        res["flips"] = TF.count_gate_flips_iso(norms, st64, float(lt / rt))
     if tol_e2e is not None:
         bt = None if bias is None else torch.tensor([bias], dtype=torch.float32).double()
         _, go = O.layer_grads(y, xbar, None if h is None else T(f["h"].get()).reshape(h.shape), bt, lt, rt, K, iso, 0.0, act,

@@ -379,9 +379,11 @@ def test_grouped_per_image_generic_size():
     assert rel_l2(A.to_julia(x.cpu()).double(), torch.cat(refs, dim=3)) <= TOL
 
 
-def test_forward_is_cuda_graph_capturable():
+@pytest.mark.parametrize("iso", [False, True])
+def test_forward_is_cuda_graph_capturable(iso):
     """The library only enqueues stream-ordered kernels and memsets, so a call can be captured once and replayed
-    (serving small batches is launch-bound: tools/graph_bench.py)."""
+    (serving small batches is launch-bound: tools/graph_bench.py).  Neither TV variant uses floating-point atomics
+    (the isotropic per-pixel norm is summed over the plane pairs in a fixed order), so replay == eager bit for bit."""
     d0 = dev()
     y = torch.rand(2, 3, 64, 64, device=d0)
     h = torch.rand(1, 1, 5, 5, device=d0); h /= h.sum()
@@ -389,12 +391,12 @@ def test_forward_is_cuda_graph_capturable():
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        A.tvd_fft(y, lam, rho, h, False, 6)
+        A.tvd_fft(y, lam, rho, h, iso, 6)
     torch.cuda.current_stream().wait_stream(s)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        xg = A.tvd_fft(y, lam, rho, h, False, 6)
+        xg = A.tvd_fft(y, lam, rho, h, iso, 6)
     y.copy_(torch.rand_like(y))
     g.replay()
     torch.cuda.synchronize()
-    assert torch.equal(xg, A.tvd_fft(y, lam, rho, h, False, 6))     # anisotropic path: no atomics, bitwise reproducible
+    assert torch.equal(xg, A.tvd_fft(y, lam, rho, h, iso, 6))     # no atomics on either path: bitwise reproducible

@@ -76,7 +76,7 @@ def test_known_answers():
 def test_training_step_layer_then_loss():
     """ADMM layer -> gmsd_loss -> backward: the cotangent produced by the loss kernel feeds admmtv_backward; parameter
     gradients are compared with autograd through the fp64 oracles of both (teacher-free, so the tolerance is the
-    end-to-end one of tests/test_gpu_backward.py: mask flips allowed)."""
+    end-to-end one of tests/test_gpu_3_backward.py: mask flips allowed)."""
     from cases import make_case
     from oracle import admm_tv_oracle as O
     M, N, P, B, K = 64, 64, 3, 2, 6

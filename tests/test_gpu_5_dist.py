@@ -35,8 +35,10 @@ def test_iso_coupling_world1_is_identity():
             outs.append((x.detach(), hh.grad, lam.grad, rho.grad))
             if cp is not None:
                 assert cp.calls == 2 * 4          # K-1 forward + K-1 backward all-reduces
-        # float atomics make the per-pixel norm reproducible to rounding only; lambda / rho gradients are cancelling sums
-        for i, (a, b) in enumerate(zip(*outs)):
-            assert float((a - b).norm() / b.norm()) < (1e-5 if i == 0 else 2e-4)
+        # the per-pixel norm is a fixed-order sum (no float atomics): x is bit-identical with and without the callbacks;
+        # the parameter gradients pass through fp64 atomics and are compared to rounding
+        assert torch.equal(outs[0][0], outs[1][0])
+        for a, b in zip(outs[0][1:], outs[1][1:]):
+            assert float((a - b).norm() / b.norm()) < 1e-5
     finally:
         dist.destroy_process_group()
