@@ -7,7 +7,7 @@ reference's operator / layer interface.  Importing the package does not need a G
 does -- there is no CPU fallback.
 """
 from ._lib import AdmmTvError, AdmmTvLib, Desc, load, make_desc  # noqa: F401
-from . import dist, staging  # noqa: F401
+from . import dist, host, staging  # noqa: F401
 from .layers import ADMMDeconv, ADMMDeconvF1, ADMMDeconvF2, ADMMDeconvF3, ADMMParallel, Admm  # noqa: F401
 from .losses import gmsd, gmsd_loss, ssim, ssim_loss, ssim_loss_fast  # noqa: F401
 from .ops import (admm_layer_call, from_julia, to_julia, tvd_fft, tvd_fft_gpu, tvd_fft_grouped,  # noqa: F401

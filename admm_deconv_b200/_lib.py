@@ -46,6 +46,20 @@ LOSS_SYMBOLS = (
     "admmtv_ssim_forward",
     "admmtv_ssim_backward",
 )
+# every symbol include/admmtv_host.h declares
+HOST_SYMBOLS = (
+    "admmtv_host_session_bytes",
+    "admmtv_host_session_create",
+    "admmtv_host_session_destroy",
+    "admmtv_host_pin",
+    "admmtv_host_unpin",
+    "admmtv_host_forward_enqueue",
+    "admmtv_host_train_step_enqueue",
+    "admmtv_host_grad_floats",
+    "admmtv_host_wait",
+    "admmtv_host_launches",
+    "admmtv_mse_train_step",
+)
 # every symbol include/admmtv_batch.h declares
 BATCH_SYMBOLS = ("admmtv_batch_from_n0f8", "admmtv_batch_gather_n0f8")
 
@@ -115,7 +129,20 @@ class AdmmTvLib:
         L.admmtv_ssim_backward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, i, vp, vp, vp, vp]
         L.admmtv_batch_from_n0f8.argtypes = [i, i, i, i, i, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp]
         L.admmtv_batch_gather_n0f8.argtypes = [i, i, i, i, i, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, vp]
-        for name in SYMBOLS + LOSS_SYMBOLS + BATCH_SYMBOLS:
+        self.has_host = hasattr(L, "admmtv_host_wait")   # the test-only CPU emulation build has no host-buffer layer
+        if self.has_host:
+            L.admmtv_host_session_bytes.argtypes = [C.POINTER(Desc), i, C.POINTER(sz)]
+            L.admmtv_host_session_create.argtypes = [C.POINTER(Desc), i, vp, vp, C.POINTER(vp)]
+            L.admmtv_host_session_destroy.argtypes = [vp]
+            L.admmtv_host_pin.argtypes = [vp, sz]
+            L.admmtv_host_unpin.argtypes = [vp]
+            L.admmtv_host_forward_enqueue.argtypes = [vp, i] + [vp] * 6
+            L.admmtv_host_train_step_enqueue.argtypes = [vp, i] + [vp] * 9 + [C.POINTER(Hooks)]
+            L.admmtv_host_grad_floats.argtypes = [C.POINTER(Desc)]
+            L.admmtv_host_wait.argtypes = [vp, i]
+            L.admmtv_host_launches.argtypes = [vp, i]
+            L.admmtv_mse_train_step.argtypes = [C.POINTER(Desc)] + [vp] * 15 + [C.POINTER(Hooks)]
+        for name in SYMBOLS + LOSS_SYMBOLS + BATCH_SYMBOLS + (HOST_SYMBOLS if self.has_host else ()):
             getattr(L, name)  # AttributeError if a declared symbol is not exported
 
     def strerror(self, code: int) -> str:
@@ -176,6 +203,47 @@ class AdmmTvLib:
 
     def backward_launches(self, d: Desc) -> int:
         return self.lib.admmtv_backward_launches(C.byref(d))
+
+    # ---- include/admmtv_host.h ----------------------------------------------------------------
+    def host_session_bytes(self, d: Desc, training: bool) -> int:
+        n = C.c_size_t()
+        self._raise(self.lib.admmtv_host_session_bytes(C.byref(d), int(training), C.byref(n)))
+        return n.value
+
+    def host_session_create(self, d: Desc, training: bool, arena=None, compute_stream=None) -> int:
+        h = C.c_void_p()
+        self._raise(self.lib.admmtv_host_session_create(C.byref(d), int(training), arena, compute_stream, C.byref(h)))
+        return h.value
+
+    def host_session_destroy(self, sess):
+        self._raise(self.lib.admmtv_host_session_destroy(sess))
+
+    def host_pin(self, ptr, nbytes):
+        self._raise(self.lib.admmtv_host_pin(ptr, nbytes))
+
+    def host_unpin(self, ptr):
+        self._raise(self.lib.admmtv_host_unpin(ptr))
+
+    def host_forward_enqueue(self, sess, slot, y, h, lam, rho, bias, x_out):
+        self._raise(self.lib.admmtv_host_forward_enqueue(sess, slot, y, h, lam, rho, bias, x_out))
+
+    def host_train_step_enqueue(self, sess, slot, y, target, h, lam, rho, bias, grads_out, loss_out, ybar_out=None, hooks=None):
+        self._raise(self.lib.admmtv_host_train_step_enqueue(sess, slot, y, target, h, lam, rho, bias, grads_out, loss_out, ybar_out,
+                                                            None if hooks is None else C.byref(hooks)))
+
+    def mse_train_step(self, d: Desc, y, target, h, lam, rho, bias, x_out, xbar, ybar, grads, loss_sum, ws_fwd, ckpt, ws_bwd,
+                       stream=0, hooks=None):
+        self._raise(self.lib.admmtv_mse_train_step(C.byref(d), y, target, h, lam, rho, bias, x_out, xbar, ybar, grads, loss_sum,
+                                                   ws_fwd, ckpt, ws_bwd, stream, None if hooks is None else C.byref(hooks)))
+
+    def host_grad_floats(self, d: Desc) -> int:
+        return self.lib.admmtv_host_grad_floats(C.byref(d))
+
+    def host_wait(self, sess, slot):
+        self._raise(self.lib.admmtv_host_wait(sess, slot))
+
+    def host_launches(self, sess, training: bool) -> int:
+        return self.lib.admmtv_host_launches(sess, int(training))
 
     # ---- include/admmtv_loss.h ----------------------------------------------------------------
     @staticmethod

@@ -28,9 +28,11 @@ NVCC_FLAGS = [
 GXX_FLAGS = ["-std=c++20", "-O1", "-fPIC", "-pthread", "-DADMMTV_EMU", "-x", "c++"]
 
 
-def _units():
+def _units(emulate: bool = False):
     """(source, define, object stem)"""
     u = [("admmtv_api.cu", None, "admmtv_api"), ("loss_api.cu", None, "loss_api"), ("inst_generic.cu", None, "inst_generic")]
+    if not emulate:   # the host-buffer layer (streams, pinned memory) has no CPU emulation twin
+        u.append(("host_api.cu", None, "host_api"))
     for l in LOG2_SIZES:
         u.append(("inst_dim1.cu", l, f"inst_dim1_{l}"))
         u.append(("inst_dim2.cu", l, f"inst_dim2_{l}"))
@@ -39,7 +41,7 @@ def _units():
 
 def _deps():
     d = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc"))]
-    d.append(os.path.join(INCLUDE, "admmtv.h"))
+    d += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE) if f.endswith(".h")]
     return d
 
 
@@ -86,7 +88,7 @@ def build(emulate: bool = False, force: bool = False, jobs: int | None = None, v
         return obj
 
     with ThreadPoolExecutor(max_workers=jobs) as ex:
-        objs = list(ex.map(compile_one, _units()))
+        objs = list(ex.map(compile_one, _units(emulate)))
     if emulate:
         emu_obj = os.path.join(objdir, "cuda_emu.o")
         if force or _stale(emu_obj, deps):

@@ -41,6 +41,7 @@ static Geom geom(const admmtv_desc* d) {
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
   g.G = d->groups > 1 ? d->groups : 1;
   g.iso = d->iso ? 1 : 0;
+  g.spatial = (d->kh > 0 && !(d->flags & ADMMTV_FLAG_NOGRAD_REPEAT)) ? 1 : 0;
   g.Bg = d->B / g.G;
   g.Sg = d->P * g.Bg;
   g.Qg = (g.Sg + 1) / 2;
@@ -106,6 +107,11 @@ struct Ckpt {
   float2* vck;   // (K-1) slots of [Q][2][N][M]   : v_1 .. v_{K-1}
   float2* zck;   // K slots of [Q][N][M]          : F r_1 .. F r_K
   float* nck;    // isotropic: (K-1) slots of [N][M] : per-pixel |v_k|^2
+  // what the forward computed once and the backward would otherwise recompute:
+  float2 *twM, *twN;   // twiddles
+  float* ctab;         // C / (M N)
+  float2 *ktab, *sig;  // conj(K) / N and Sigma
+  float2* yck;         // [Q][N][M] : F y (only when the backward differentiates the spatial H^T y path)
   size_t bytes;
 };
 static Ckpt carve_ckpt(const Geom& g, void* p) {
@@ -115,6 +121,12 @@ static Ckpt carve_ckpt(const Geom& g, void* p) {
   k.vck = c.take<float2>((size_t)(g.K > 1 ? g.K - 1 : 0) * 2 * g.pk);
   k.zck = c.take<float2>((size_t)g.K * g.pk);
   k.nck = c.take<float>(g.iso ? (size_t)(g.K > 1 ? g.K - 1 : 0) * g.plane * g.G : 0);
+  k.twM = c.take<float2>(g.M);
+  k.twN = c.take<float2>(g.N);
+  k.ctab = c.take<float>(g.plane * g.G);
+  k.ktab = c.take<float2>(g.kh > 0 ? g.plane * g.G : 0);
+  k.sig = c.take<float2>(g.plane * g.G);
+  k.yck = c.take<float2>(g.spatial ? g.pk : 0);
   k.bytes = c.off;
   return k;
 }
@@ -305,7 +317,7 @@ int admmtv_forward_launches(const admmtv_desc* d, int with_ckpt) {
     n += d->iters + (d->iters - 1) * (d->iso ? 5 : 3) + 2;
     return n;
   }
-  int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 3 : 0);
+  int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 2 : 0);
   n += d->iters + (d->iters - 1) * (d->iso ? 3 : 1) + 1;
   return n;
 }
@@ -347,40 +359,56 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   ADMMTV_LAUNCH(k_clamp_params, dim3((unsigned)g.G), dim3(128), 0, st, lambda, rho, h, g.nh, d->creg,
                 (d->flags & ADMMTV_FLAG_NO_CLAMP) ? 0 : 1, ckpt ? ck.mask : w.mask);
   ADMMTV_CHECK_LAUNCH();
-  if ((rc = run_setup(g, h, rho, w.twM, w.twN, w.T, w.ctab, w.ktab, nullptr, st))) return rc;
+  // training: twiddles and tables go to the checkpoint, where the backward finds them (no second setup)
+  const float2 *twM = ckpt ? ck.twM : w.twM, *twN = ckpt ? ck.twN : w.twN;
+  const float* ctab = ckpt ? ck.ctab : w.ctab;
+  const float2* ktab = ckpt ? ck.ktab : w.ktab;
+  if ((rc = run_setup(g, h, rho, const_cast<float2*>(twM), const_cast<float2*>(twN), w.T, const_cast<float*>(ctab),
+                      const_cast<float2*>(ktab), ckpt ? ck.sig : nullptr, st)))
+    return rc;
 
+  // spectrum ping-pong: `cur` holds the dim-1 spectrum of r_k, `oth` receives the k_dim2 result
+  float2 *cur = w.specA, *oth = w.specB;
   // y -> pair-pack -> dim-1 spectrum (ops.jl:101 + first FFT pass)
   {
     PackArgs a{};
-    a.src = y; a.spec = w.specA; a.twM = w.twM; a.N = g.N; a.S = g.S; a.pm = g.pm;
+    a.src = y; a.spec = w.specA; a.twM = twM; a.N = g.N; a.S = g.S; a.pm = g.pm;
     a.packed_out = g.kh > 0 ? nullptr : w.bpk;  // empty h: b = y (ops.jl:149-151)
     if ((rc = run_pack_fft1(g, 0, a, st))) return rc;
   }
   if (g.kh > 0) {
     // b = H^T y = F^-1( conj(K) F y )  (ops.jl:163,168; hoisted out of the loop)
     Dim2Args a{};
-    a.in = w.specA; a.out = w.specB; a.ktab = w.ktab; a.twN = w.twN; a.M = g.M;
+    a.in = w.specA; a.out = w.specB; a.ktab = ktab; a.twN = twN; a.M = g.M;
     a.Qg = g.Qg; a.tab_stride = g.G > 1 ? g.plane : 0;
-    if ((rc = run_dim2(g, D2_KCONJ, a, st))) return rc;
+    const bool save_fy = ckpt && g.spatial;   // F y is the second factor of the PSF-gradient correlation
+    if (save_fy) a.zsave = ck.yck;
+    if ((rc = run_dim2(g, save_fy ? D2_KCONJ_SAVE : D2_KCONJ, a, st))) return rc;
     OutArgs o{};
-    o.spec = w.specB; o.packed = w.bpk; o.twM = w.twM; o.N = g.N; o.S = g.S; o.pm = g.pm;
+    o.spec = w.specB; o.packed = w.bpk; o.twM = twM; o.N = g.N; o.S = g.S; o.pm = g.pm; o.scale = 1.f / (float)g.M;
     if ((rc = run_dim1_out(g, 0, o, st))) return rc;
-    PackArgs p{};
-    p.src_packed = w.bpk; p.spec = w.specA; p.twM = w.twM; p.N = g.N; p.S = g.S; p.pm = g.pm;
-    if ((rc = run_pack_fft1(g, 2, p, st))) return rc;
+    if (g.LM > 0) {
+      // specB IS the dim-1 spectrum of b = r_1 (z_0 = u_0 = 0): the first x-update reads it directly
+      cur = w.specB; oth = w.specA;
+    } else {
+      // generic sizes transform in place (inst_generic.cu), which consumed specB: transform b again
+      PackArgs p{};
+      p.src_packed = w.bpk; p.spec = w.specA; p.twM = twM; p.N = g.N; p.S = g.S; p.pm = g.pm;
+      if ((rc = run_pack_fft1(g, 2, p, st))) return rc;
+    }
   }
 
   // the unrolled iterations (ops.jl:166-174)
   for (int k = 1; k <= g.K; ++k) {
     Dim2Args a{};
-    a.in = w.specA; a.out = w.specB; a.ctab = w.ctab; a.twN = w.twN; a.M = g.M;
+    a.in = cur; a.out = oth; a.ctab = ctab; a.twN = twN; a.M = g.M;
     a.Qg = g.Qg; a.tab_stride = g.G > 1 ? g.plane : 0;
     if (ckpt) a.zsave = ck.zck + (size_t)(k - 1) * g.pk;
     tm_mark(tm, st, 0);
     if ((rc = run_dim2(g, ckpt ? D2_C_SAVE : D2_C, a, st))) return rc;
     if (k < g.K && !d->iso) {
       Dim1FwdArgs f{};
-      f.spec_in = w.specB; f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM;
+      f.spec_in = oth; f.spec_out = cur; f.bpk = w.bpk; f.twM = twM;
       f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
       if (ckpt) {
         f.vprev = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
@@ -409,7 +437,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       }
       tm_mark(tm, st, 1);
       Dim1FwdArgs fa{};
-      fa.spec_in = w.specB; fa.twM = w.twM; fa.lambda = lambda; fa.rho = rho; fa.N = g.N; fa.Qg = g.Qg;
+      fa.spec_in = oth; fa.twM = twM; fa.lambda = lambda; fa.rho = rho; fa.N = g.N; fa.Qg = g.Qg;
       fa.vprev = v_in; fa.vnew = v_out; fa.nsq = s_prev; fa.nsq_out = w.npart;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_a(g, k > 1, fa, st); })
       if (rc) return rc;
@@ -426,7 +454,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
         ADMMTV_CHECK_LAUNCH();
       }
       Dim1FwdArgs f{};
-      f.spec_out = w.specA; f.bpk = w.bpk; f.twM = w.twM; f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
+      f.spec_out = cur; f.bpk = w.bpk; f.twM = twM; f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
       f.vprev = v_out; f.nsq = s_new;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_b(g, f, st); })
       if (rc) return rc;
@@ -436,7 +464,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   // x_K -> user layout, + bias, activation (ops.jl:175, deconv_admm.jl:222-224)
   {
     OutArgs o{};
-    o.spec = w.specB; o.planes = x_out; o.bias = d->has_bias ? bias : nullptr; o.twM = w.twM;
+    o.spec = oth; o.planes = x_out; o.bias = d->has_bias ? bias : nullptr; o.twM = twM;
     o.N = g.N; o.S = g.S; o.act = d->activation; o.pm = g.pm;
     if ((rc = run_dim1_out(g, 1, o, st))) return rc;
   }

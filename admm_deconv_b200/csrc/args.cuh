@@ -34,6 +34,7 @@ struct Geom {
   int planned;   // bit 0: dim-1 spectra in the plan's digit-reversed order (else natural); bit 1: same for dim 2
   int G, Bg, Sg, Qg;  // groups, images / planes / pairs per group (S = G*Sg planes, Q = G*Qg pairs)
   int iso;            // isotropic TV: the workspaces carry the per-pair partial sums of the per-pixel reductions
+  int spatial;        // the backward differentiates the spatial H^T y path (kh > 0 and no NOGRAD_REPEAT): F y is checkpointed
   PlaneMap pm;
   size_t plane;  // N*M
   size_t pk;     // Q*N*M  (pair-packed complex elements)
@@ -59,6 +60,7 @@ struct OutArgs {
   const float2* twM;
   PlaneMap pm;
   int N, S, act;
+  float scale;         // MODE 0 / 2: factor applied to the result (1/M: the K tables carry only the dim-2 round trip's 1/N)
 };
 
 struct Dim1FwdArgs {
@@ -114,11 +116,12 @@ struct Dim1BwdArgs {
 enum Dim2Variant {
   D2_C = 0,      // x C                                   (forward iteration, inference)
   D2_C_SAVE,     // save F r_k, then x C                  (forward iteration, training)
-  D2_KCONJ,      // x conj(K)/MN                          (b = H^T y)
+  D2_KCONJ,      // x conj(K)/N                           (b = H^T y)
   D2_C_ACCG,     // G += Re(conj(Z) Z2), then x C         (backward iteration)
   D2_FWDONLY,    // write the full 2-D spectrum, stop     (F y for the PSF-gradient correlation)
-  D2_K_ACCP,     // P += conj(Z) Z2, then x K/MN          (ybar = H bbar and hbar correlation)
-  D2_K           // x K/MN                                (ybar = H bbar only)
+  D2_K_ACCP,     // P += conj(Z) Z2, then x K/N           (ybar = H bbar and hbar correlation)
+  D2_K,          // x K/N                                 (ybar = H bbar only)
+  D2_KCONJ_SAVE  // save F y, then x conj(K)/N            (b = H^T y, training: F y feeds the PSF-gradient correlation)
 };
 
 template <int LM>

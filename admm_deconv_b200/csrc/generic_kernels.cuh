@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(GK_NT) gk_out(OutArgs A, int M, int Q, int mod
   const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
   Pix p;
   if (!gk_pix(idx, M, A.N, Q, p)) return;
-  const float2 v = A.spec[idx];
+  float2 v = A.spec[idx];
+  if (mode != 1) v = cscale(v, A.scale);
   if (mode == 0) {
     A.packed[idx] = v;
   } else if (mode == 2) {

@@ -1,0 +1,372 @@
+// host_api.cu -- the host-buffer entry points of include/admmtv_host.h: a thin, stream-pipelined layer over the
+// device-pointer C ABI (admmtv_forward / admmtv_backward).  Everything still runs on the GPU.
+#include "../../include/admmtv_host.h"
+
+#include <cuda_runtime.h>
+#include <new>
+#include <stdint.h>
+#include <string.h>
+
+namespace {
+
+inline size_t al256(size_t n) { return (n + 255) & ~size_t(255); }
+
+// loss = mean((x - t)^2) ; xbar = 2 (x - t) / n   (the MSE pullback seed of train.jl:51-53)
+__global__ void __launch_bounds__(256) k_mse_cotangent(const float* __restrict__ x, const float* __restrict__ t,
+                                                       float* __restrict__ xbar, size_t n, float scale, double* loss_acc) {
+  double acc = 0.0;
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i], b = reinterpret_cast<const float4*>(t)[i];
+    const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    reinterpret_cast<float4*>(xbar)[i] = make_float4(scale * d.x, scale * d.y, scale * d.z, scale * d.w);
+    acc += (double)(d.x * d.x + d.y * d.y) + (double)(d.z * d.z + d.w * d.w);
+  }
+  if (blockIdx.x == 0) {
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float d = x[i] - t[i];
+      xbar[i] = scale * d;
+      acc += (double)d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(loss_acc, s);
+  }
+}
+
+struct Slot {
+  float *y, *target, *x;       // device
+  cudaEvent_t in_ready, compute_done, out_done;
+  float* loss_out;             // host destination of the pending step's loss (or null)
+  bool pending;
+};
+
+}  // namespace
+
+struct admmtv_host_session {
+  admmtv_desc d;
+  int training, G, nh, ngrad;
+  size_t nimg;                 // floats per (M,N,P,B) array
+  size_t out_img;              // floats of x_out (== nimg unless channel-concat/shared input)
+  size_t in_img;               // floats of y
+  unsigned char* arena;
+  bool own_arena, own_compute;
+  cudaStream_t copy_in, compute, copy_out;
+  Slot slot[2];
+  float *h, *lambda, *rho, *bias;   // device parameters
+  float *xbar, *ybar, *packed;      // training
+  double* loss_acc;                 // device
+  double* loss_host[2];             // pinned
+  void *ws_fwd, *ws_bwd, *ckpt;
+  int prev_device;
+};
+
+namespace {
+
+struct Layout {
+  size_t y[2], t[2], x[2], h, lam, rho, bias, xbar, ybar, packed, loss, ws_fwd, ws_bwd, ckpt, total;
+};
+
+int plan(const admmtv_desc* d, int training, Layout& L, size_t& in_img, size_t& out_img, int& G, int& nh, int& ngrad) {
+  int rc = admmtv_check(d);
+  if (rc) return rc;
+  G = d->groups > 1 ? d->groups : 1;
+  nh = d->kh * d->kw;
+  ngrad = nh * G + 2 * G + (d->has_bias ? G : 0);
+  const size_t plane = (size_t)d->M * d->N;
+  out_img = plane * d->P * d->B;
+  in_img = (d->flags & ADMMTV_FLAG_SHARED_INPUT) ? plane * d->P * (d->B / G) : out_img;
+  size_t fwd = 0, ck = 0, bwd = 0;
+  if ((rc = admmtv_workspace_bytes(d, &fwd, &ck, &bwd))) return rc;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t r = o; o += al256(bytes); return r; };
+  for (int s = 0; s < 2; ++s) {
+    L.y[s] = take(in_img * 4);
+    L.t[s] = take(training ? out_img * 4 : 0);
+    L.x[s] = take(out_img * 4);
+  }
+  L.h = take((size_t)(nh > 0 ? nh : 1) * G * 4);
+  L.lam = take((size_t)G * 4);
+  L.rho = take((size_t)G * 4);
+  L.bias = take((size_t)G * 4);
+  L.xbar = take(training ? out_img * 4 : 0);
+  L.ybar = take(training ? in_img * 4 : 0);
+  L.packed = take((size_t)ngrad * 4);
+  L.loss = take(16);
+  L.ws_fwd = take(fwd);
+  L.ws_bwd = take(training ? bwd : 0);
+  L.ckpt = take(training ? ck : 0);
+  L.total = o;
+  return 0;
+}
+
+struct DevGuard {
+  int prev;
+  bool ok;
+  explicit DevGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+#define HCHECK(expr)                          \
+  do {                                        \
+    cudaError_t e__ = (expr);                 \
+    if (e__ != cudaSuccess) return (int)e__;  \
+  } while (0)
+
+// parameters host -> device on the compute stream (tiny), before the kernels that read them
+int upload_params(admmtv_host_session* s, const float* h, const float* lambda, const float* rho, const float* bias) {
+  if (s->nh > 0) HCHECK(cudaMemcpyAsync(s->h, h, (size_t)s->nh * s->G * 4, cudaMemcpyHostToDevice, s->compute));
+  HCHECK(cudaMemcpyAsync(s->lambda, lambda, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->compute));
+  HCHECK(cudaMemcpyAsync(s->rho, rho, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->compute));
+  if (s->d.has_bias) HCHECK(cudaMemcpyAsync(s->bias, bias, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->compute));
+  return 0;
+}
+// the persisted clamp (deconv_admm.jl:216-219) back to the caller's arrays.  These few bytes travel on the COMPUTE stream
+// (like the gradients and the loss): the next step's kernels overwrite the same device words, and stream order is the
+// cheapest way to keep them apart; only the image-sized transfers use the copy streams.
+int download_params(admmtv_host_session* s, float* h, float* lambda, float* rho) {
+  if (s->d.flags & ADMMTV_FLAG_NO_CLAMP) return 0;
+  if (s->nh > 0) HCHECK(cudaMemcpyAsync(h, s->h, (size_t)s->nh * s->G * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(lambda, s->lambda, (size_t)s->G * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(rho, s->rho, (size_t)s->G * 4, cudaMemcpyDeviceToHost, s->compute));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int admmtv_host_grad_floats(const admmtv_desc* d) {
+  if (admmtv_check(d)) return 0;
+  const int G = d->groups > 1 ? d->groups : 1;
+  return d->kh * d->kw * G + 2 * G + (d->has_bias ? G : 0);
+}
+
+int admmtv_host_session_bytes(const admmtv_desc* d, int training, size_t* device_bytes) {
+  if (!device_bytes) return ADMMTV_ERR_NULL;
+  Layout L;
+  size_t a, b;
+  int G, nh, ng;
+  int rc = plan(d, training, L, a, b, G, nh, ng);
+  if (rc) return rc;
+  *device_bytes = L.total;
+  return ADMMTV_OK;
+}
+
+int admmtv_host_session_create(const admmtv_desc* d, int training, void* device_arena, void* compute_stream,
+                               admmtv_host_session** out) {
+  if (!out) return ADMMTV_ERR_NULL;
+  *out = nullptr;
+  Layout L;
+  size_t in_img, out_img;
+  int G, nh, ng;
+  int rc = plan(d, training, L, in_img, out_img, G, nh, ng);
+  if (rc) return rc;
+  if (reinterpret_cast<uintptr_t>(device_arena) & 255) return ADMMTV_ERR_ALIGN;
+  DevGuard guard(d->device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  admmtv_host_session* s = new (std::nothrow) admmtv_host_session();
+  if (!s) return (int)cudaErrorMemoryAllocation;
+  memset(s, 0, sizeof(*s));
+  s->d = *d;
+  s->training = training ? 1 : 0;
+  s->G = G; s->nh = nh; s->ngrad = ng; s->in_img = in_img; s->out_img = out_img;
+  s->own_arena = device_arena == nullptr;
+  s->arena = reinterpret_cast<unsigned char*>(device_arena);
+  cudaError_t e = cudaSuccess;
+  if (s->own_arena) e = cudaMalloc((void**)&s->arena, L.total);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking);
+  s->own_compute = compute_stream == nullptr;
+  s->compute = reinterpret_cast<cudaStream_t>(compute_stream);
+  if (e == cudaSuccess && s->own_compute) e = cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    Slot& sl = s->slot[i];
+    sl.y = reinterpret_cast<float*>(s->arena + L.y[i]);
+    sl.target = reinterpret_cast<float*>(s->arena + L.t[i]);
+    sl.x = reinterpret_cast<float*>(s->arena + L.x[i]);
+    e = cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->loss_host[i], sizeof(double));
+  }
+  if (e != cudaSuccess) {
+    admmtv_host_session_destroy(s);
+    return (int)e;
+  }
+  s->h = reinterpret_cast<float*>(s->arena + L.h);
+  s->lambda = reinterpret_cast<float*>(s->arena + L.lam);
+  s->rho = reinterpret_cast<float*>(s->arena + L.rho);
+  s->bias = reinterpret_cast<float*>(s->arena + L.bias);
+  s->xbar = reinterpret_cast<float*>(s->arena + L.xbar);
+  s->ybar = reinterpret_cast<float*>(s->arena + L.ybar);
+  s->packed = reinterpret_cast<float*>(s->arena + L.packed);
+  s->loss_acc = reinterpret_cast<double*>(s->arena + L.loss);
+  s->ws_fwd = s->arena + L.ws_fwd;
+  s->ws_bwd = s->arena + L.ws_bwd;
+  s->ckpt = s->arena + L.ckpt;
+  *out = s;
+  return ADMMTV_OK;
+}
+
+int admmtv_host_session_destroy(admmtv_host_session* s) {
+  if (!s) return ADMMTV_OK;
+  DevGuard guard(s->d.device);
+  if (s->copy_in) cudaStreamSynchronize(s->copy_in);
+  if (s->compute) cudaStreamSynchronize(s->compute);
+  if (s->copy_out) cudaStreamSynchronize(s->copy_out);
+  for (int i = 0; i < 2; ++i) {
+    if (s->slot[i].in_ready) cudaEventDestroy(s->slot[i].in_ready);
+    if (s->slot[i].compute_done) cudaEventDestroy(s->slot[i].compute_done);
+    if (s->slot[i].out_done) cudaEventDestroy(s->slot[i].out_done);
+    if (s->loss_host[i]) cudaFreeHost(s->loss_host[i]);
+  }
+  if (s->copy_in) cudaStreamDestroy(s->copy_in);
+  if (s->copy_out) cudaStreamDestroy(s->copy_out);
+  if (s->own_compute && s->compute) cudaStreamDestroy(s->compute);
+  if (s->own_arena && s->arena) cudaFree(s->arena);
+  delete s;
+  return ADMMTV_OK;
+}
+
+int admmtv_host_pin(void* p, size_t bytes) {
+  if (!p) return ADMMTV_ERR_NULL;
+  return (int)cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+}
+int admmtv_host_unpin(void* p) {
+  if (!p) return ADMMTV_ERR_NULL;
+  return (int)cudaHostUnregister(p);
+}
+
+int admmtv_host_launches(const admmtv_host_session* s, int training) {
+  if (!s) return 0;
+  int n = admmtv_forward_launches(&s->d, training);
+  if (training) n += 1 + admmtv_backward_launches(&s->d);
+  return n;
+}
+
+int admmtv_host_forward_enqueue(admmtv_host_session* s, int slot, const float* y, float* h, float* lambda, float* rho,
+                                const float* bias, float* x_out) {
+  if (!s || !y || !lambda || !rho || !x_out) return ADMMTV_ERR_NULL;
+  if (s->nh > 0 && !h) return ADMMTV_ERR_NULL;   // checked before any copy
+  if (s->d.has_bias && !bias) return ADMMTV_ERR_NULL;
+  if (slot < 0 || slot > 1) return ADMMTV_ERR_ENUM;
+  DevGuard guard(s->d.device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  Slot& sl = s->slot[slot];
+  // the slot's previous use was waited for by the caller, so its device buffers are free
+  HCHECK(cudaMemcpyAsync(sl.y, y, s->in_img * 4, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
+  HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
+  int rc = upload_params(s, h, lambda, rho, bias);
+  if (rc) return rc;
+  rc = admmtv_forward(&s->d, sl.y, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho, s->d.has_bias ? s->bias : nullptr, sl.x,
+                      s->ws_fwd, nullptr, s->compute);
+  if (rc) return rc;
+  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  HCHECK(cudaEventRecord(sl.compute_done, s->compute));
+  HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
+  HCHECK(cudaMemcpyAsync(x_out, sl.x, s->out_img * 4, cudaMemcpyDeviceToHost, s->copy_out));
+  HCHECK(cudaEventRecord(sl.out_done, s->copy_out));
+  sl.loss_out = nullptr;
+  sl.pending = true;
+  return ADMMTV_OK;
+}
+
+int admmtv_host_train_step_enqueue(admmtv_host_session* s, int slot, const float* y, const float* target, float* h,
+                                   float* lambda, float* rho, const float* bias, float* grads_out, float* loss_out,
+                                   float* ybar_out, const admmtv_hooks* hooks) {
+  if (!s || !y || !target || !lambda || !rho || !grads_out) return ADMMTV_ERR_NULL;
+  if (!s->training) return ADMMTV_ERR_ENUM;
+  if (s->nh > 0 && !h) return ADMMTV_ERR_NULL;
+  if (s->d.has_bias && !bias) return ADMMTV_ERR_NULL;
+  if (slot < 0 || slot > 1) return ADMMTV_ERR_ENUM;
+  DevGuard guard(s->d.device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  Slot& sl = s->slot[slot];
+  HCHECK(cudaMemcpyAsync(sl.y, y, s->in_img * 4, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaMemcpyAsync(sl.target, target, s->out_img * 4, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
+  HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
+  int rc = upload_params(s, h, lambda, rho, bias);
+  if (rc) return rc;
+  if ((rc = admmtv_mse_train_step(&s->d, sl.y, sl.target, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho,
+                                  s->d.has_bias ? s->bias : nullptr, sl.x, s->xbar, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
+                                  s->ckpt, s->ws_bwd, s->compute, hooks)))
+    return rc;
+  HCHECK(cudaMemcpyAsync(grads_out, s->packed, (size_t)s->ngrad * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(s->loss_host[slot], s->loss_acc, sizeof(double), cudaMemcpyDeviceToHost, s->compute));
+  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  HCHECK(cudaEventRecord(sl.compute_done, s->compute));
+  HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
+  if (ybar_out) {
+    HCHECK(cudaMemcpyAsync(ybar_out, s->ybar, s->in_img * 4, cudaMemcpyDeviceToHost, s->copy_out));
+    HCHECK(cudaEventRecord(sl.out_done, s->copy_out));
+    HCHECK(cudaStreamWaitEvent(s->compute, sl.out_done, 0));   // the next step's backward overwrites ybar
+  } else {
+    HCHECK(cudaEventRecord(sl.out_done, s->copy_out));
+  }
+  sl.loss_out = loss_out;
+  sl.pending = true;
+  return ADMMTV_OK;
+}
+
+int admmtv_mse_train_step(const admmtv_desc* d, const float* y, const float* target, float* h, float* lambda, float* rho,
+                          const float* bias, float* x_out, float* xbar, float* ybar, float* grads_packed, double* loss_sum,
+                          void* ws_fwd, void* ckpt, void* ws_bwd, void* stream, const admmtv_hooks* hooks) {
+  int rc = admmtv_check(d);
+  if (rc) return rc;
+  if (!y || !target || !lambda || !rho || !x_out || !xbar || !ybar || !grads_packed || !loss_sum || !ws_fwd || !ckpt || !ws_bwd)
+    return ADMMTV_ERR_NULL;
+  DevGuard guard(d->device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int G = d->groups > 1 ? d->groups : 1, nh = d->kh * d->kw;
+  if ((rc = admmtv_forward(d, y, h, lambda, rho, bias, x_out, ws_fwd, ckpt, stream))) return rc;
+  HCHECK(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
+  {
+    const size_t n = (size_t)d->M * d->N * d->P * d->B;
+    const size_t want = (n / 4 + 255) / 256 + 1;
+    const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    k_mse_cotangent<<<blocks, 256, 0, st>>>(x_out, target, xbar, n, 2.0f / (float)n, loss_sum);
+    HCHECK(cudaGetLastError());
+  }
+  float* hbar = grads_packed;
+  float* lbar = grads_packed + (size_t)nh * G;
+  float* rbar = lbar + G;
+  float* bbar = d->has_bias ? rbar + G : nullptr;
+  if ((rc = admmtv_backward(d, xbar, x_out, y, h, lambda, rho, ckpt, ybar, nh > 0 ? hbar : nullptr, lbar, rbar, bbar, ws_bwd,
+                            stream)))
+    return rc;
+  if (hooks && hooks->allreduce_sum) {   // the data-parallel gradient all-reduce, stream-ordered
+    const size_t ng = (size_t)nh * G + 2 * G + (d->has_bias ? G : 0);
+    if ((rc = hooks->allreduce_sum(grads_packed, ng, stream, hooks->user))) return rc;
+  }
+  return ADMMTV_OK;
+}
+
+int admmtv_host_wait(admmtv_host_session* s, int slot) {
+  if (!s) return ADMMTV_ERR_NULL;
+  if (slot < 0 || slot > 1) return ADMMTV_ERR_ENUM;
+  Slot& sl = s->slot[slot];
+  if (!sl.pending) return ADMMTV_OK;
+  DevGuard guard(s->d.device);
+  HCHECK(cudaEventSynchronize(sl.out_done));
+  if (sl.loss_out) *sl.loss_out = (float)(*s->loss_host[slot] / (double)s->out_img);
+  sl.pending = false;
+  return ADMMTV_OK;
+}
+
+}  // extern "C"

@@ -32,9 +32,6 @@ constexpr int LN = ADMMTV_INST;
 #ifndef ADMMTV_D2_ACC_QPB
 #define ADMMTV_D2_ACC_QPB 2
 #endif
-#ifndef ADMMTV_D2_PIPE
-#define ADMMTV_D2_PIPE 0
-#endif
 #ifndef ADMMTV_D2_BLOCKS_PER_SM
 #define ADMMTV_D2_BLOCKS_PER_SM 2
 #endif
@@ -66,25 +63,6 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
   // with one global atomic per element per ADMMTV_D2_ACC_QPB pairs
   if (variant == D2_C_ACCG && gy == g.Q) gy = (g.Q + ADMMTV_D2_ACC_QPB - 1) / ADMMTV_D2_ACC_QPB;
   if (gy > 65535) gy = 65535;  // blocks loop over pairs with stride gridDim.y
-#if ADMMTV_D2_PIPE
-  // software-pipelined persistent variant for the passes without gradient accumulation (k_dim2p)
-  constexpr size_t kRing = (size_t)ADMMTV_D2P_NBUF * Cfg::SMEM;
-  if (kRing <= 200 * 1024 && variant != D2_C_ACCG && variant != D2_K_ACCP) {
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int total = row_tiles * g.Q;
-    const dim3 pgrid((unsigned)(total < sms ? total : sms));
-    switch (variant) {
-      case D2_C: return launch_k(k_dim2p<LN, 0, false, false>, pgrid, ADMMTV_D2P_NT, kRing, st, a);
-      case D2_C_SAVE: return launch_k(k_dim2p<LN, 0, true, false>, pgrid, ADMMTV_D2P_NT, kRing, st, a);
-      case D2_KCONJ: return launch_k(k_dim2p<LN, 1, false, false>, pgrid, ADMMTV_D2P_NT, kRing, st, a);
-      case D2_FWDONLY: return launch_k(k_dim2p<LN, 0, false, true>, pgrid, ADMMTV_D2P_NT, kRing, st, a);
-      case D2_K: return launch_k(k_dim2p<LN, 2, false, false>, pgrid, ADMMTV_D2P_NT, kRing, st, a);
-      default: break;
-    }
-  }
-#endif
   const dim3 grid((unsigned)row_tiles, (unsigned)gy);
   switch (variant) {
     case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
@@ -94,6 +72,7 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
     case D2_FWDONLY: return launch_k(k_dim2<LN, 0, false, 0, true>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_K_ACCP: return launch_k(k_dim2<LN, 2, false, 2, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
     case D2_K: return launch_k(k_dim2<LN, 2, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
+    case D2_KCONJ_SAVE: return launch_k(k_dim2<LN, 1, true, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);
   }
   return -5;
 }

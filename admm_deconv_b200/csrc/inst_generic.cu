@@ -106,6 +106,7 @@ int Dim2Launch<0>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaStr
     case D2_FWDONLY: c.fwd_only = 1; break;
     case D2_K_ACCP: c.mul = 2; c.acc = 2; break;
     case D2_K: c.mul = 2; break;
+    case D2_KCONJ_SAVE: c.mul = 1; c.save_z = 1; break;
     default: return -5;
   }
   const size_t smem = gk_dft_smem_elems(g.N, c.P, c.TR) * sizeof(float2);

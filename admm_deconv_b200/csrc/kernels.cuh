@@ -445,18 +445,20 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
   dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
   if (MODE == 0) {
     float2* dst = A.packed + (size_t)q * plane;
+    const float sc = A.scale;
     for (int e = tid; e < nout * (M / 2); e += NT) {
       const int c = e / (M / 2), i = (e % (M / 2)) * 2;
       const float2 v0 = X[sidx<LM>(c, i)], v1 = X[sidx<LM>(c, i + 1)];
-      *reinterpret_cast<float4*>(dst + (size_t)(j0 + c) * M + i) = make_float4(v0.x, v0.y, v1.x, v1.y);
+      *reinterpret_cast<float4*>(dst + (size_t)(j0 + c) * M + i) = make_float4(sc * v0.x, sc * v0.y, sc * v1.x, sc * v1.y);
     }
   } else if (MODE == 2) {
     // cotangent of the INPUT: input plane map; groups sharing y accumulate (ybar zeroed by the host)
     const long ia = pm_in(A.pm, q, 0), ib = pm_in(A.pm, q, 1);
     const bool shared = A.pm.G > 1 && A.pm.in_gstride == 0;
+    const float sc = A.scale;
     for (int e = tid; e < nout * M; e += NT) {
       const int c = e / M, i = e % M;
-      const float2 v = X[sidx<LM>(c, i)];
+      const float2 v = cscale(X[sidx<LM>(c, i)], sc);
       const size_t off = (size_t)(j0 + c) * M + i;
       if (shared) {
         atomicAdd(A.planes + (size_t)ia * plane + off, v.x);
@@ -1037,148 +1039,6 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
     __syncthreads();  // the tile is rewritten by the next pair's first pass
   }
 
-}
-
-// ------------------------------------------------------------------------------------------
-// k_dim2p: the same dim-2 pass as k_dim2 (no gradient accumulation), software-pipelined.
-// One persistent block per SM walks its tiles; the tiles are brought into a ring of NBUF shared-memory buffers with
-// asynchronous 16-byte global->shared copies (cp.async, SASS LDGSTS: no registers, no stall), so the loads of the next
-// NBUF-1 tiles are in flight while the current tile's FFT passes run -- k_dim2 can only overlap a tile's loads with the
-// passes of the one other block resident on the SM.  All FFT passes, stage 0 included, run in place in the buffer; the
-// last inverse pass still writes registers -> global memory.
-// ------------------------------------------------------------------------------------------
-#ifndef ADMMTV_D2P_NT
-#define ADMMTV_D2P_NT 512
-#endif
-#ifndef ADMMTV_D2P_NBUF
-#define ADMMTV_D2P_NBUF 3
-#endif
-ADMMTV_DI void cp_async16(void* smem_dst, const void* gsrc) {
-#ifndef ADMMTV_EMU
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-#else
-  *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gsrc);
-#endif
-}
-ADMMTV_DI void cp_async_commit() {
-#ifndef ADMMTV_EMU
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int PENDING>
-ADMMTV_DI void cp_async_wait() {
-#ifndef ADMMTV_EMU
-  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
-#endif
-}
-
-template <int LN, int MUL, bool SAVE_Z, bool FWD_ONLY>
-__global__ void __launch_bounds__(ADMMTV_D2P_NT, 1) k_dim2p(Dim2Args A) {
-  using Cfg = Dim2Cfg<LN>;
-  constexpr int N = Cfg::N, TR = Cfg::TR, NT = ADMMTV_D2P_NT, RP = TR / 2, NS = plan_stages(N), NBUF = ADMMTV_D2P_NBUF;
-  constexpr int TE = N * TR;  // float2 elements per tile
-  using StL = Stage<N, NS - 1>;
-  ADMMTV_DYN_SMEM(float2, ring);  // [NBUF][N][TR]
-  const int tid = threadIdx.x, M = A.M;
-  const int row_tiles = M / TR, total = row_tiles * A.Q;
-  auto issue = [&](int t, int buf) {   // every thread commits exactly one group per call (possibly empty)
-    if (t < total) {
-      const float2* src = A.in + (size_t)(t / row_tiles) * N * M + (size_t)(t % row_tiles) * TR;
-      float2* dst = ring + (size_t)buf * TE;
-      for (int c = tid; c < N * RP; c += NT) {
-        const int col = c / RP, rp = c % RP;
-        cp_async16(dst + col * TR + 2 * rp, src + (size_t)col * M + 2 * rp);
-      }
-    }
-    cp_async_commit();
-  };
-  const int t0 = blockIdx.x, dt = gridDim.x;
-#pragma unroll
-  for (int b = 0; b < NBUF - 1; ++b) issue(t0 + b * dt, b);
-  int buf = 0;
-  for (int t = t0; t < total; t += dt) {
-    // tile t has landed (at most NBUF-2 younger groups may still be in flight); the barrier also orders every
-    // thread's last use of the buffer that the prefetch below overwrites (it held tile t - dt)
-    cp_async_wait<NBUF - 2>();
-    __syncthreads();
-    issue(t + (NBUF - 1) * dt, (buf + NBUF - 1) % NBUF);
-    float2* tile = ring + (size_t)buf * TE;
-    const int q = t / row_tiles, i0 = (t % row_tiles) * TR;
-    const size_t qoff = (size_t)q * N * M;
-    const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;
-
-    dim2_smem_stage<LN, 0, false, NT>(tile, A.twN, tid);
-    __syncthreads();
-    dim2_fwd_mid<LN, 1, NT>(tile, A.twN, tid);
-    // last forward stage fused with the spectral multiply and the first inverse stage
-#pragma unroll 1
-    for (int item = tid; item < RP * StL::ITEMS; item += NT) {
-      const int rp = item % RP, wi = item / RP;
-      float2 a0[StL::R], a1[StL::R];
-#pragma unroll
-      for (int m = 0; m < StL::R; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + (wi * StL::R + m) * TR + 2 * rp);
-        a0[m] = make_float2(v.x, v.y);
-        a1[m] = make_float2(v.z, v.w);
-      }
-      Dft<StL::R, false>::run(a0);
-      Dft<StL::R, false>::run(a1);
-#pragma unroll
-      for (int m = 0; m < StL::R; ++m) {
-        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;
-        if (SAVE_Z || FWD_ONLY) {
-          float2* zs = FWD_ONLY ? A.out : A.zsave;
-          *reinterpret_cast<float4*>(zs + qoff + g) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
-        }
-        if (!FWD_ONLY) {
-          if (MUL == 0) {
-            const float2 cc = *reinterpret_cast<const float2*>(A.ctab + toff + g);
-            a0[m] = cscale(a0[m], cc.x);
-            a1[m] = cscale(a1[m], cc.y);
-          } else {
-            const float4 kk = *reinterpret_cast<const float4*>(A.ktab + toff + g);
-            const float sgn = MUL == 2 ? -1.f : 1.f;
-            a0[m] = cmul(a0[m], make_float2(kk.x, sgn * kk.y));
-            a1[m] = cmul(a1[m], make_float2(kk.z, sgn * kk.w));
-          }
-        }
-      }
-      if (!FWD_ONLY) {
-        Dft<StL::R, true>::run(a0);
-        Dft<StL::R, true>::run(a1);
-#pragma unroll
-        for (int m = 0; m < StL::R; ++m)
-          *reinterpret_cast<float4*>(tile + (wi * StL::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
-      }
-    }
-    if (!FWD_ONLY) {
-      __syncthreads();
-      dim2_inv_mid<LN, NS - 2, NT>(tile, A.twN, tid);
-      // inverse stage 0: shared -> registers -> global
-      using St = Stage<N, 0>;
-      float2* dst = A.out + qoff + i0;
-      for (int item = tid; item < RP * St::ITEMS; item += NT) {
-        const int rp = item % RP, wi = item / RP;
-        float2 p[St::R];
-        stage_twiddles<N, 0, true>(wi, A.twN, p);
-        float2 a0[St::R], a1[St::R];
-#pragma unroll
-        for (int m = 0; m < St::R; ++m) {
-          const float4 v = *reinterpret_cast<const float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp);
-          a0[m] = make_float2(v.x, v.y);
-          a1[m] = make_float2(v.z, v.w);
-        }
-        stage_inv<N, 0>(a0, p);
-        stage_inv<N, 0>(a1, p);
-#pragma unroll
-        for (int m = 0; m < St::R; ++m)
-          *reinterpret_cast<float4*>(dst + (size_t)(wi + m * St::STRIDE) * M + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
-      }
-    }
-    buf = (buf + 1) % NBUF;
-  }
-  cp_async_wait<0>();
 }
 
 }  // namespace admmtv

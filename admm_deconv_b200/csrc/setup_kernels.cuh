@@ -69,7 +69,9 @@ static __global__ void k_setup_psf_dim1(const float* __restrict__ h, int kh, int
 }
 
 // ctab[p2][p1] = C(k1,k2) / (M N),  C = 1 / (|Sigma|^2 + rho (4 sin^2(pi k2/N) + 4 sin^2(pi k1/M)))   ops.jl:119
-// ktab[p2][p1] = conj(K)(k1,k2) / (M N), K = Sigma exp(+2 pi i (k1 pd/M + k2 pr/N))                   SURVEY 8a-6
+// ktab[p2][p1] = conj(K)(k1,k2) / N, K = Sigma exp(+2 pi i (k1 pd/M + k2 pr/N))                       SURVEY 8a-6
+//   (only the dim-2 round trip's 1/N: the result of the k_dim2 pass is then the exact dim-1 spectrum of H^T y, which
+//    feeds the first x-update directly; the dim-1 inverse that brings it back to space applies the remaining 1/M)
 // sig [p2][p1] = Sigma (only written when sig != nullptr; the backward needs it)
 // (p1,p2) are storage positions; (k1,k2) = pos_to_freq of them.
 static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int kw, int M, int N,
@@ -114,7 +116,8 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
     sincospi(ph, &ps, &pc);
     // K = Sigma * (pc + i ps); store conj(K)/(MN)
     const double kr = sr * pc - si * ps, ki = sr * ps + si * pc;
-    ktab[idx] = make_float2((float)(kr * inv_mn), (float)(-ki * inv_mn));
+    const double inv_n = 1.0 / (double)N;
+    ktab[idx] = make_float2((float)(kr * inv_n), (float)(-ki * inv_n));
   }
   if (sig) sig[idx] = make_float2((float)sr, (float)si);
 }

@@ -177,7 +177,7 @@ class ADMMParallel(nn.Module):
         h = torch.cat([l.weight for l in L], dim=0).contiguous() if L[0].weight.numel() > 0 else None
         bias = torch.cat([l.bias for l in L]) if L[0].bias is not None else None
         out = ops.tvd_fft_grouped(x, lam, rho, h, L[0].iso, L[0].iters, groups=G, shared_input=True, channel_concat=True,
-                                  bias=bias, activation=L[0].sigma, creg=L[0].creg, clamp=True)
+                                  bias=bias, activation=L[0].sigma, creg=L[0].creg, clamp=True, inputs_owned=True)
         # the library clamped the packed copies in place: persist into the layers (deconv_admm.jl:216-219)
         with torch.no_grad():
             for g, l in enumerate(L):

@@ -69,7 +69,7 @@ class _AdmmFunction(torch.autograd.Function):
     Zygote's tape through ops.jl:166-174)."""
 
     @staticmethod
-    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags, coupling=None):
+    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags, coupling=None, need_grad=True):
         lib = _lib.load()
         _check_cuda_f32("y", y)
         for n, t in (("lambda", lam), ("rho", rho)):
@@ -80,7 +80,6 @@ class _AdmmFunction(torch.autograd.Function):
             h = None
         if bias is not None:
             _check_cuda_f32("bias", bias)
-        need_grad = any(t is not None and t.requires_grad for t in (y, lam, rho, h, bias))
         d = make_desc_for(y, h, iters, iso, activation, bias is not None, flags, creg)
         fwd_b, ck_b, _ = lib.workspace_bytes(d)
         ws = _alloc(fwd_b, y.device)
@@ -124,7 +123,24 @@ class _AdmmFunction(torch.autograd.Function):
             lib.backward_ex(*args, ctx.coupling.hooks)
         else:
             lib.backward(*args)
-        return ybar, lbar, rbar, hbar, bbar, None, None, None, None, None, None
+        return ybar, lbar, rbar, hbar, bbar, None, None, None, None, None, None, None
+
+
+def _needs_grad(*tensors) -> bool:
+    """Evaluated OUTSIDE autograd.Function.forward (grad mode is always off in there): under torch.no_grad() / eval
+    nothing is differentiated, so no per-iteration checkpoint is allocated or written (it is (3K-1)*8 bytes per
+    pair-pixel: 60 GB at 64 x 512^2 x 3, K = 100) and the faster inference kernels run."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _own_if_nonleaf(t, clamp: bool):
+    """The persisted clamp (deconv_admm.jl:216-219) writes into the parameter buffers.  That is the reference's
+    behaviour for the layer's own arrays (leaf tensors); a NON-leaf input (e.g. softplus(raw), a torch.cat of several
+    layers' scalars) may have been saved by the node that produced it, so the kernel gets a private differentiable
+    copy to clamp instead of mutating it behind autograd's back."""
+    if t is None or not clamp or t.grad_fn is None:
+        return t
+    return t.clone()
 
 
 def admm_layer_call(y, lam, rho, h=None, bias=None, iters=100, iso=False, activation="identity", creg=0.0,
@@ -134,7 +150,9 @@ def admm_layer_call(y, lam, rho, h=None, bias=None, iters=100, iso=False, activa
     ``iso_coupling`` (a ``dist.IsoCoupling``, EXTENSION): with a batch sharded over ranks, makes the
     isotropic per-pixel norm span every rank's images, i.e. the reference's single-device result on the whole batch."""
     flags = (0 if clamp else _lib.FLAG_NO_CLAMP) | (_lib.FLAG_NOGRAD_REPEAT if nograd_repeat else 0)
-    return _AdmmFunction.apply(y, lam, rho, h, bias, int(iters), bool(iso), activation, float(creg), flags, iso_coupling)
+    lam, rho, h = _own_if_nonleaf(lam, clamp), _own_if_nonleaf(rho, clamp), _own_if_nonleaf(h, clamp)
+    return _AdmmFunction.apply(y, lam, rho, h, bias, int(iters), bool(iso), activation, float(creg), flags, iso_coupling,
+                               _needs_grad(y, lam, rho, h, bias))
 
 
 def tvd_fft(y, lam, rho, h=None, isotropic=False, maxit=100, iso_coupling=None):
@@ -170,12 +188,12 @@ class _AdmmGroupedFunction(torch.autograd.Function):
     parameter cotangents (and ybar summed over groups that share the input)."""
 
     @staticmethod
-    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags, groups, shared_input, channel_concat):
+    def forward(ctx, y, lam, rho, h, bias, iters, iso, activation, creg, flags, groups, shared_input, channel_concat,
+                need_grad=True):
         lib = _lib.load()
         Bin, P, N, M = y.shape
         Bg = Bin if shared_input else Bin // groups
         kh, kw = (0, 0) if h is None else (int(h.shape[-1]), int(h.shape[-2]))
-        need_grad = any(t is not None and t.requires_grad for t in (y, lam, rho, h, bias))
         d = _lib.make_desc(M, N, P, groups * Bg, kh, kw, iters, iso, activation, bias is not None, y.device.index or 0,
                            flags, creg, groups)
         fwd_b, ck_b, _ = lib.workspace_bytes(d)
@@ -204,11 +222,11 @@ class _AdmmGroupedFunction(torch.autograd.Function):
         stream = torch.cuda.current_stream(y.device).cuda_stream
         lib.backward(d, _ptr(xbar), _ptr(x), _ptr(y), _ptr(h) if ctx.has_h else None, _ptr(lam), _ptr(rho), _ptr(ctx.ck),
                      _ptr(ybar), _ptr(hbar), _ptr(lbar), _ptr(rbar), _ptr(bbar), _ptr(ws), stream)
-        return (ybar, lbar, rbar, hbar, bbar) + (None,) * 8
+        return (ybar, lbar, rbar, hbar, bbar) + (None,) * 9
 
 
 def tvd_fft_grouped(y, lam, rho, h=None, isotropic=False, maxit=100, *, groups: int, shared_input=False,
-                    channel_concat=False, bias=None, activation="identity", creg=0.0, clamp=False):
+                    channel_concat=False, bias=None, activation="identity", creg=0.0, clamp=False, inputs_owned=False):
     """EXTENSION: ``groups`` independent reference calls of identical shape batched
     into one launch sequence (differentiable: per-group cotangents).
 
@@ -243,5 +261,7 @@ def tvd_fft_grouped(y, lam, rho, h=None, isotropic=False, maxit=100, *, groups: 
         _check_cuda_f32("bias", bias)
     flags = (0 if clamp else _lib.FLAG_NO_CLAMP) | (_lib.FLAG_SHARED_INPUT if shared_input else 0) | \
         (_lib.FLAG_CHANNEL_CONCAT if channel_concat else 0)
+    if not inputs_owned:   # inputs_owned: the caller built lam / rho / h just for this call and reads the clamp back from them
+        lam, rho, h = _own_if_nonleaf(lam, clamp), _own_if_nonleaf(rho, clamp), _own_if_nonleaf(h, clamp)
     return _AdmmGroupedFunction.apply(y, lam, rho, h, bias, int(maxit), bool(isotropic), activation, float(creg), flags,
-                                      int(groups), bool(shared_input), bool(channel_concat))
+                                      int(groups), bool(shared_input), bool(channel_concat), _needs_grad(y, lam, rho, h, bias))

@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- the hot-path benchmark (see the task contract, section 4 of DESIGN.md).
+"""bench.py -- the hot-path benchmark (task contract).
 
-    python bench.py --gpus 1 --steps K --warmup W            native arm (CUDA kernels, C ABI)
-    python bench.py --impl reference ...                      reference arm (restated CPU path)
+    python bench.py --gpus 1 --steps K --warmup W            native arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference ...                      reference arm (restated CPU path, same config)
 
-One "step" = one pass of the ADMM-TV hot path over one batch of synthetic input: BASELINE.json
-configs[1] (batch 64 x 512x512 RGB, motion PSF 15x15, 100 iterations).  Metric: plane-megapixel-
-iterations per second, whole job (all ranks).  Weak scaling: every rank gets its own batch of 64.
+Headline ("value"): BASELINE.json's metric -- ADMM megapixel-iterations/s, forward + backward + gradient all-reduce --
+on configs[1]'s batch (64 x 512x512 RGB, motion-blur PSF 15x15) with 10 unrolled iterations per step, inputs resident in
+HBM (admmtv_mse_train_step, include/admmtv_host.h).  "e2e" is the same step through the host-buffer C-ABI session
+(admmtv_host_train_step_enqueue / _wait): batch and target uploaded from pinned host memory and the gradients + loss
+downloaded inside the timed region, every step.  The "others" block carries short runs of every other BASELINE config
+(configs[1] forward-only with 100 iterations, configs[2] strong-scaled over the ranks, configs[3], configs[4] with
+per-image PSFs), each with its own time, roofline fraction and clock record.  Weak scaling: every rank gets its own
+batch of 64 for the headline.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import math
 import os
@@ -27,33 +33,52 @@ METRIC = "admm_tv_plane_megapixel_iterations_per_second"
 UNIT = "Mpx-it/s"
 
 WORKLOADS = {
-    # name: (B, P, N, M, k, iters, mode)
-    "cfg2": dict(B=64, P=3, N=512, M=512, k=15, iters=100, mode="fwd",
+    "cfg2_train": dict(B=64, P=3, N=512, M=512, k=15, iters=10, mode="fwd+bwd", psf="motion",
+                       desc="BASELINE.json configs[1] batch (64 x 512x512 RGB, motion-blur PSF 15x15), 10 unrolled ADMM-TV "
+                            "iterations, forward (checkpointed) + hand-written backward + gradient all-reduce, MSE loss"),
+    "cfg2": dict(B=64, P=3, N=512, M=512, k=15, iters=100, mode="fwd", psf="motion",
                  desc="BASELINE.json configs[1]: batch 64 x 512x512 RGB, motion-blur PSF 15x15, ADMM-TV forward 100 iterations"),
-    "cfg2_train": dict(B=64, P=3, N=512, M=512, k=15, iters=10, mode="fwd+bwd",
-                       desc="cfg2 shapes, 10 unrolled iterations, forward+backward (checkpointed)"),
-    "cfg4": dict(B=16, P=1, N=2048, M=2048, k=31, iters=200, mode="fwd",
+    "cfg3": dict(B=256, P=3, N=256, M=256, k=15, iters=10, mode="fwd+bwd", psf="gauss", strong=True,
+                 desc="BASELINE.json configs[2]: training step, 10 learned-rho/lambda iterations, fwd+bwd, GLOBAL batch "
+                      "256 x 256x256 RGB split over the ranks (strong scaling), Gaussian PSF 15x15, NCCL gradient all-reduce"),
+    "cfg4": dict(B=16, P=1, N=2048, M=2048, k=31, iters=200, mode="fwd", psf="motion",
                  desc="BASELINE.json configs[3]: batch 16 x 2048x2048 gray, 31x31 PSF, 200-iteration forward"),
-    "cfg5": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="fwd",
-                 desc="BASELINE.json configs[4] (shared PSF variant): batch 1024 x 128x128, 50 iterations"),
-    "cfg3": dict(B=32, P=3, N=256, M=256, k=15, iters=10, mode="fwd+bwd",
-                 desc="BASELINE.json configs[2] per-GPU share: 32 x 256x256 RGB (256 images over 8 GPUs), Gaussian PSF 15x15, 10 unrolled iterations, forward+backward + gradient all-reduce"),
-    "cfg5_mixed": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="grouped", groups="per_image",
+    "cfg5": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="fwd", psf="motion",
+                 desc="BASELINE.json configs[4], shared-PSF variant: batch 1024 x 128x128, 50 iterations"),
+    "cfg5_mixed": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="grouped", groups="per_image", psf="motion",
                        desc="BASELINE.json configs[4]: batch 1024 x 128x128, PER-IMAGE motion PSFs 9x9 and noise levels "
                             "(lambda_i = 0.2 sigma_i, rho_i = 5 lambda_i), 50 iterations, one grouped call"),
-    "denoiser5": dict(B=32, P=3, N=256, M=256, k=0, iters=50, mode="grouped", groups=5, iso=True,
+    "cfg2_iso": dict(B=64, P=3, N=512, M=512, k=15, iters=50, mode="fwd", psf="motion", iso=True,
+                     desc="configs[1] batch, ISOTROPIC TV (the reference's shipped use_iso = true), 50 iterations forward"),
+    "denoiser5": dict(B=32, P=3, N=256, M=256, k=0, iters=50, mode="grouped", groups=5, iso=True, psf="motion",
                       desc="net_build.jl:113-128 get_denoiser: 5 parallel ADMMDeconvF2((),50,rho_i,relu1; iso) branches on the "
                            "same 32 x 256x256 RGB input, channel-concatenated, one grouped call"),
-    "hd1080": dict(B=4, P=3, N=1920, M=1080, k=15, iters=20, mode="fwd",
+    "hd1080": dict(B=4, P=3, N=1920, M=1080, k=15, iters=20, mode="fwd", psf="motion",
                    desc="4 x 1080x1920 RGB frames (1080 has no register-FFT plan: generic-size kernels), motion PSF 15x15, 20 iterations"),
-    "bsd481": dict(B=32, P=3, N=481, M=321, k=9, iters=20, mode="fwd",
+    "bsd481": dict(B=32, P=3, N=481, M=321, k=9, iters=20, mode="fwd", psf="motion",
                    desc="32 x 321x481 RGB (BSD500 size; 481 = 13*37: generic-size kernels), motion PSF 9x9, 20 iterations"),
-    "vga": dict(B=64, P=3, N=480, M=640, k=15, iters=50, mode="fwd",
+    "vga": dict(B=64, P=3, N=480, M=640, k=15, iters=50, mode="fwd", psf="motion",
                 desc="64 x 640x480 RGB frames (mixed-radix lengths 640 = 5*16*8, 480 = 3*5*8*4), motion PSF 15x15, 50 iterations"),
-    "tiny": dict(B=2, P=3, N=64, M=64, k=7, iters=10, mode="fwd", desc="tiny debug workload"),
+    "tiny": dict(B=2, P=3, N=64, M=64, k=7, iters=4, mode="fwd+bwd", psf="motion", desc="tiny debug workload"),
 }
+OTHERS = ("cfg2", "cfg3", "cfg4", "cfg5_mixed", "cfg2_iso")
 FWD_BYTES = 40.0   # algorithmic bytes / plane-pixel-iteration, forward  
 BWD_BYTES = 68.0
+ISO_FWD_BYTES = 44.0   # + the per-pixel norm / scale
+
+
+def alg_bytes(w):
+    if w["mode"] == "fwd+bwd":
+        return FWD_BYTES + BWD_BYTES
+    return ISO_FWD_BYTES if w.get("iso") else FWD_BYTES
+
+
+def config_of(w, name):
+    """The `config` object of the JSON line: identical on the native and the reference arm."""
+    return {"workload": w["desc"], "name": name, "mode": w["mode"], "iters": w["iters"],
+            "image": f"{w['M']}x{w['N']}x{w['P']}", "per_gpu_batch": w["B"], "psf": f"{w['k']}x{w['k']} {w['psf']}",
+            "lambda": 0.0041, "rho": 0.021, "iso": bool(w.get("iso", False)), "loss": "mse" if w["mode"] == "fwd+bwd" else None,
+            "l2": "per-iteration state is larger than the 126 MB L2 (no flush needed)"}
 
 
 def peaks():
@@ -64,27 +89,31 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (exact PID is killed afterwards)."""
+    """nvidia-smi sampling during a timed region (the exact PID is terminated afterwards)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index = index
-        self.proc = None
+    def __init__(self, index: int, enabled: bool = True, period_ms: int = 50):
+        self.index, self.proc, self.enabled, self.period = index, None, enabled, period_ms
 
     def start(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period), "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+        return self
 
     def stop(self):
+        if not self.enabled:
+            return None
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -127,20 +156,32 @@ def motion_psf(k: int, theta: float, length: float):
     return (p / p.sum()).float()
 
 
-def make_inputs(w, seed):
-    """Synthetic blurred-noisy batch in the (B,P,N,M) layout + motion PSF.  Plain torch; nothing
-    from oracle/ is used on the native arm."""
+def gauss_psf(k: int, sigma: float):
+    import torch
+    x = torch.arange(k, dtype=torch.float64) - (k - 1) / 2
+    g = torch.exp(-x * x / (2 * sigma * sigma))
+    p = g[:, None] * g[None, :]
+    return (p / p.sum()).float()
+
+
+def make_inputs(w, seed, B=None):
+    """Synthetic blurred-noisy batch in the (B,P,N,M) layout, its ground truth, and the PSF (SURVEY.md 8d).  Plain torch;
+    nothing from oracle/ is used on the native arm.  Returns (y, g, h (1,1,kw,kh))."""
     import numpy as np
     import torch
 
     rng = np.random.Generator(np.random.PCG64(seed))
     k = w["k"] if w["k"] > 0 else 9      # k = 0: the layer has no PSF (empty weight); the scene is still blurred
-    h = motion_psf(k, float(rng.uniform(0, math.pi)), float(rng.uniform(5, k)))      # [dim1, dim2]
-    B, P, N, M = w["B"], w["P"], w["N"], w["M"]
-    # scene: smooth field + rectangles
-    g = torch.from_numpy(rng.random((min(B, 4), P, N, M), dtype=np.float32))
+    if w.get("psf") == "gauss":
+        h = gauss_psf(k, 2.0)
+    else:
+        h = motion_psf(k, float(rng.uniform(0, math.pi)), float(rng.uniform(5, k)))      # [dim1, dim2]
+    B = w["B"] if B is None else B
+    P, N, M = w["P"], w["N"], w["M"]
+    nb = min(B, 4)
+    g = torch.from_numpy(rng.random((nb, P, N, M), dtype=np.float32))
     g = torch.nn.functional.avg_pool2d(g, 9, stride=1, padding=4, count_include_pad=False)
-    for b in range(g.shape[0]):
+    for b in range(nb):
         for _ in range(8):
             i0, i1 = sorted(rng.integers(0, N, 2).tolist()); j0, j1 = sorted(rng.integers(0, M, 2).tolist())
             g[b, :, i0:i1 + 1, j0:j1 + 1] = float(rng.random())
@@ -151,111 +192,251 @@ def make_inputs(w, seed):
     gp = torch.nn.functional.pad(g.reshape(-1, 1, N, M), (pu, pd, pu, pd), mode="circular")
     y = torch.nn.functional.conv2d(gp, torch.flip(hk, dims=(0, 1)).reshape(1, 1, k, k)).reshape(g.shape)
     y = y + 0.02 * torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32))
-    reps = (B + y.shape[0] - 1) // y.shape[0]
+    reps = (B + nb - 1) // nb
     y = y.repeat(reps, 1, 1, 1)[:B].contiguous()
-    return y, hk.reshape(1, 1, k, k).contiguous()                      # (1,1,kw,kh)
+    g = g.repeat(reps, 1, 1, 1)[:B].contiguous()
+    return y, g, hk.reshape(1, 1, k, k).contiguous()                      # (1,1,kw,kh)
 
 
-def run_reference(args, w):
-    """Reference arm: the restated reference CPU path (oracle port of ops.jl:17-96, torch-CPU fp32,
-    MKL FFT, all host threads), on a bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the restated reference (oracle port of ops.jl:17-96, torch-CPU fp32, MKL FFT) -- the only place
+# bench.py touches oracle/.  fwd+bwd = torch.autograd through the literal restatement (stands in for Zygote).
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_step_fn(w, sB):
     import torch
     from oracle import admm_tv_oracle as O
 
+    y, g, hk = make_inputs(w, 1001, B=sB)
+    yj = y.permute(3, 2, 1, 0).contiguous(); gj = g.permute(3, 2, 1, 0).contiguous()
+    hj = hk.permute(3, 2, 1, 0).contiguous()
+    K, iso = w["iters"], bool(w.get("iso", False))
+    if w["mode"] == "fwd+bwd":
+        def step():
+            lam = torch.tensor([0.0041], requires_grad=True); rho = torch.tensor([0.021], requires_grad=True)
+            h = hj.clone().requires_grad_(True)
+            x = O.tvd_fft_cpu(yj, lam, rho, h, iso, K)
+            loss = ((x - gj) ** 2).mean()
+            loss.backward()
+            return float(loss.detach())
+    else:
+        lam = torch.tensor([0.0041]); rho = torch.tensor([0.021])
+
+        def step():
+            with torch.no_grad():
+                O.tvd_fft_cpu(yj, lam, rho, hj, iso, K)
+    units = sB * w["P"] * w["N"] * w["M"] * K / 1e6
+    what = "forward + torch.autograd backward" if w["mode"] == "fwd+bwd" else "forward"
+    sample = (f"{sB} x {w['M']}x{w['N']}x{w['P']} images of the workload, all {K} iterations, {what}, torch-CPU fp32 (MKL FFT), "
+              "faithful (H^T y recomputed every iteration as ops.jl:86 does)")
+    return step, units, sample
+
+
+def run_reference(args, w, name):
+    """Reference arm: the restated reference CPU path on every host thread, same config, bounded sample per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sB = 1
-    s_iters = max(1, min(w["iters"], 20))
-    y, hk = make_inputs(dict(w, B=sB), 1001)
-    yj = y.permute(3, 2, 1, 0).contiguous()
-    hj = hk.permute(3, 2, 1, 0).contiguous()
-    lam = torch.tensor([0.0041]); rho = torch.tensor([0.021])
-    for _ in range(max(args.warmup, 1)):
-        O.tvd_fft_cpu(yj, lam, rho, hj, False, 2)
+    sB = 2 if w["M"] * w["N"] <= 512 * 512 else 1
+    step, units, sample = cpu_step_fn(w, sB)
+    for _ in range(max(min(args.warmup, 2), 1)):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.tvd_fft_cpu(yj, lam, rho, hj, False, s_iters)
+        step()
     dt = time.perf_counter() - t0
-    units = sB * w["P"] * w["N"] * w["M"] * s_iters * args.steps / 1e6
-    val = units / dt
-    sample = f"{sB} x {w['M']}x{w['N']}x{w['P']} image, {s_iters} iterations per step (faithful: H^T y recomputed every iteration)"
-    line = {
+    val = units * args.steps / dt
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(w, name),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "restated reference (torch-CPU fp32, MKL FFT) -- Julia/FFTW cannot run in this image"},
+                         "note": "restated reference (oracle/admm_tv_oracle.py, torch-CPU fp32, MKL FFT); Julia/FFTW cannot run in this image"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+    })
 
 
 def cpu_baseline(w):
     import torch
-    from oracle import admm_tv_oracle as O
-
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sB, s_iters = (2 if w["M"] <= 512 else 1), min(w["iters"], 100)
-    y, hk = make_inputs(dict(w, B=sB), 1001)
-    yj = y.permute(3, 2, 1, 0).contiguous(); hj = hk.permute(3, 2, 1, 0).contiguous()
-    lam = torch.tensor([0.0041]); rho = torch.tensor([0.021])
-    O.tvd_fft_cpu(yj, lam, rho, hj, False, 2)
-    t0 = time.perf_counter()
-    O.tvd_fft_cpu(yj, lam, rho, hj, False, s_iters)
-    dt = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    O.tvd_fft_fast(yj, lam, rho, hj, False, s_iters, hoist=True)
-    dt_h = time.perf_counter() - t1
-    units = sB * w["P"] * w["N"] * w["M"] * s_iters / 1e6
-    return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sB} x {w['M']}x{w['N']}x{w['P']} image, {s_iters} iterations, torch-CPU fp32 (MKL FFT), faithful (H^T y per iteration)",
-            "hoisted_value": units / dt_h}
+    sB = 2 if w["M"] * w["N"] <= 512 * 512 else 1
+    step, units, sample = cpu_step_fn(w, sB)
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step(); n += 1
+        dt = time.perf_counter() - t0
+        if dt > 12.0 or n >= 20:
+            break
+    return {"value": units * n / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f"; {n} repetitions"}
 
 
-def run_native(args, w):
+# ---------------------------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def setup_dist():
     import torch
     import torch.distributed as dist
 
-    import admm_deconv_b200 as A
-    from admm_deconv_b200 import _lib, ops
+    c = Ctx()
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if c.world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the ONE JSON line
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{c.local}"))
+    torch.cuda.set_device(c.local)
+    c.dev = torch.device(f"cuda:{c.local}")
+    c.dist = dist
+    return c
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        # keep stdout for the ONE JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    lib = A.load()
 
-    y_host, h_host = make_inputs(w, 1001 + rank)
-    y_host = y_host.pin_memory()
-    x_host = torch.empty_like(y_host).pin_memory()
-    if w["mode"] == "grouped" and w["groups"] != "per_image":
-        x_host = torch.empty(w["B"], w["P"] * int(w["groups"]), w["N"], w["M"]).pin_memory()
-    y = y_host.to(dev)
-    h = h_host.to(dev)
-    lam = torch.tensor([0.0041], device=dev)
-    rho = torch.tensor([0.021], device=dev)
-    K = w["iters"]
-    train = w["mode"] == "fwd+bwd"
+def barrier(c):
+    import torch
+    if c.world > 1:
+        c.dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(c, vals):
+    import torch
+    t = torch.tensor(vals, device=c.dev, dtype=torch.float64)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def timed(c, fn, steps, warmup, clocks=True):
+    """W warm-up calls, then `steps` calls bracketed by barrier + synchronize, CUDA events on the launching stream;
+    returns (ms per step as the max over ranks, clock record of rank 0)."""
+    import torch
+    for _ in range(max(warmup, 3)):
+        fn()
+    barrier(c)
+    sampler = ClockSampler(c.local, enabled=clocks and c.rank == 0).start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(c)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier(c)
+    ms = e0.elapsed_time(e1) / steps
+    clk = sampler.stop()
+    return max_over_ranks(c, [ms])[0], clk
+
+
+class TrainStep:
+    """forward (checkpointed) + MSE + backward + gradient all-reduce on resident inputs: admmtv_mse_train_step."""
+
+    def __init__(self, c, w, B, seed):
+        import torch
+        import admm_deconv_b200 as A
+        from admm_deconv_b200 import _lib
+
+        self.c, self.w, self.B = c, w, B
+        self.lib = A.load()
+        y, g, h = make_inputs(w, seed, B=B)
+        self.y_host, self.g_host = y.pin_memory(), g.pin_memory()
+        self.h_host = h
+        dev = c.dev
+        self.y, self.g = y.to(dev), g.to(dev)
+        self.h = h.to(dev).contiguous()
+        self.lam = torch.tensor([0.0041], device=dev); self.rho = torch.tensor([0.021], device=dev)
+        k = w["k"]
+        self.d = _lib.make_desc(w["M"], w["N"], w["P"], B, k, k, w["iters"], bool(w.get("iso", False)), "identity", False,
+                                c.local, _lib.FLAG_NO_CLAMP, 0.0)
+        fwd_b, ck_b, bwd_b = self.lib.workspace_bytes(self.d)
+        u8 = lambda n: torch.empty(max(n, 256), dtype=torch.uint8, device=dev)
+        self.ws_f, self.ck, self.ws_b = u8(fwd_b), u8(ck_b), u8(bwd_b)
+        self.x, self.xbar, self.ybar = torch.empty_like(self.y), torch.empty_like(self.y), torch.empty_like(self.y)
+        self.ngrad = self.lib.host_grad_floats(self.d)
+        self.grads = torch.zeros(self.ngrad, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.px = B * w["P"] * w["N"] * w["M"]
+        self.launches = self.lib.forward_launches(self.d, True) + 1 + self.lib.backward_launches(self.d)
+
+    def __call__(self):
+        import torch
+        st = torch.cuda.current_stream().cuda_stream
+        p = lambda t: t.data_ptr()
+        self.lib.mse_train_step(self.d, p(self.y), p(self.g), p(self.h), p(self.lam), p(self.rho), None, p(self.x), p(self.xbar),
+                                p(self.ybar), p(self.grads), p(self.loss), p(self.ws_f), p(self.ck), p(self.ws_b), st)
+        if self.c.world > 1:
+            self.c.dist.all_reduce(self.grads)      # [hbar | lambdabar | rhobar]: ONE packed NCCL all-reduce over NVLink
+
+    def profile(self):
+        """Per-kernel-class CUDA-event times of one forward and one backward (profiling twins of the same calls)."""
+        import torch
+        st = torch.cuda.current_stream().cuda_stream
+        p = lambda t: t.data_ptr()
+        hb, lb, rb = torch.empty_like(self.h), torch.empty_like(self.lam), torch.empty_like(self.rho)
+        f = b = None
+        for _ in range(2):
+            f = self.lib.profile_forward(self.d, p(self.y), p(self.h), p(self.lam), p(self.rho), None, p(self.x), p(self.ws_f), p(self.ck), st)
+            b = self.lib.profile_backward(self.d, p(self.xbar), p(self.x), p(self.y), p(self.h), p(self.lam), p(self.rho), p(self.ck),
+                                          p(self.ybar), p(hb), p(lb), p(rb), None, p(self.ws_b), st)
+        return f, b
+
+
+def e2e_train(c, w, B, steps, warmup, ts: TrainStep):
+    """The same step through the host-buffer C-ABI session, two slots pipelined: H2D of batch + target and D2H of
+    gradients + loss inside the timed region, every step."""
+    import torch
+    from admm_deconv_b200 import host
+
+    k = w["k"]
+    s = host.HostSession(w["M"], w["N"], w["P"], B, k, k, iters=w["iters"], iso=bool(w.get("iso", False)), device=c.local,
+                         flags=1, training=True)
+    lam = torch.tensor([0.0041]).pin_memory(); rho = torch.tensor([0.021]).pin_memory()
+    h = ts.h_host.clone().pin_memory()
+    grads = [torch.empty(s.ngrad).pin_memory() for _ in range(2)]
+    loss = [torch.empty(1).pin_memory() for _ in range(2)]
+
+    def run(n):
+        for i in range(n):
+            sl = i & 1
+            if i >= 2:
+                s.wait(sl)
+            s.train_step_enqueue(sl, ts.y_host, ts.g_host, lam, rho, h, grads=grads[sl], loss=loss[sl])
+        s.wait(0); s.wait(1)
+
+    run(max(warmup, 3))
+    barrier(c)
+    t0 = time.perf_counter()
+    run(steps)
+    barrier(c)
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    ms = max_over_ranks(c, [ms])[0]
+    out = {"ms_per_step": ms, "h2d_bytes_per_step": (ts.y_host.numel() + ts.g_host.numel()) * 4 + (h.numel() + 2) * 4,
+           "d2h_bytes_per_step": s.ngrad * 4 + 8, "loss": float(loss[(steps - 1) & 1]), "launches_per_step": s.launches(),
+           "path": "admmtv_host_train_step_enqueue / admmtv_host_wait (include/admmtv_host.h), pinned host buffers, 2 slots",
+           "timer": "host wall clock around the blocking calls (max over ranks)"}
+    s.close()
+    return out
+
+
+def run_fwd(c, w, name, steps, warmup, e2e=True):
+    """Forward-only workloads (inference), plain or grouped."""
+    import numpy as np
+    import torch
+    from admm_deconv_b200 import host, ops
+
+    dev = c.dev
+    y_host, _, h_host = make_inputs(w, 1001 + c.rank)
+    y = y_host.to(dev); h = h_host.to(dev)
+    lam = torch.tensor([0.0041], device=dev); rho = torch.tensor([0.021], device=dev)
+    K, iso = w["iters"], bool(w.get("iso", False))
     px = w["B"] * w["P"] * w["N"] * w["M"]
-    units_per_step = px * K / 1e6
-
-    if train:
-        g_target = torch.rand_like(y)
-        lam.requires_grad_(True); rho.requires_grad_(True); h.requires_grad_(True)
-
     grouped = w["mode"] == "grouped"
     if grouped:
-        import numpy as np
         if w["groups"] == "per_image":
             G = w["B"]
             rng = np.random.Generator(np.random.PCG64(7))
@@ -269,186 +450,147 @@ def run_native(args, w):
             hG = None
             lamG = torch.full((G,), 0.02, device=dev); rhoG = torch.tensor([0.01 * 3 ** i for i in range(G)], device=dev)
             gkw = dict(groups=G, shared_input=True, channel_concat=True, activation="relu1")
-        px = px * (1 if w["groups"] == "per_image" else G)
-        units_per_step = px * K / 1e6
+            px *= G
 
-    def step(yin):
-        if grouped:
-            return ops.tvd_fft_grouped(yin, lamG, rhoG, hG, bool(w.get("iso", False)), K, **gkw)
-        if not train:
-            return ops.tvd_fft(yin, lam, rho, h, False, K)
-        for p in (lam, rho, h):
-            p.grad = None
-        x = ops.admm_layer_call(yin, lam, rho, h, None, K, False, "identity", 0.0, False, clamp=False)
-        x.backward(2.0 * (x.detach() - g_target) / x.numel())
-        if world > 1:
-            buf = torch.cat([h.grad.reshape(-1), lam.grad, rho.grad])
-            dist.all_reduce(buf)
-        return x.detach()      # drop the graph (and its checkpoint buffer) as soon as the step is over
+        def step():
+            with torch.no_grad():
+                return ops.tvd_fft_grouped(y, lamG, rhoG, hG, iso, K, **gkw)
+    else:
+        def step():
+            with torch.no_grad():
+                return ops.tvd_fft(y, lam, rho, h, iso, K)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    ms, clk = timed(c, step, steps, warmup)
+    pk, _ = peaks()
+    r = {"config": config_of(w, name), "n_gpus": c.world, "scaling": "weak", "steps": steps, "ms_per_step": ms,
+         "value": px * K * c.world / (ms * 1e-3) / 1e6, "unit": UNIT,
+         "algorithmic_bytes_per_plane_pixel_iteration": alg_bytes(w),
+         "frac": alg_bytes(w) * px * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "clocks": clk}
+    if e2e and not grouped:
+        k = w["k"]
+        s = host.HostSession(w["M"], w["N"], w["P"], w["B"], k, k, iters=K, iso=iso, device=c.local, flags=1)
+        yh = y_host.pin_memory(); xo = [torch.empty_like(y_host).pin_memory() for _ in range(2)]
+        lh = torch.tensor([0.0041]).pin_memory(); rh = torch.tensor([0.021]).pin_memory(); hh = h_host.clone().pin_memory()
 
-    for _ in range(max(args.warmup, 3)):
-        step(y)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step(y)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    # end-to-end: every step copies its input host(pinned) -> device and its result device -> host inside the
-    # timed region.  Copies run on a side stream and are double-buffered, so step i+1's upload and step i-1's
-    # download overlap step i's compute (what a serving loop would do); all of them finish before the clock stops.
-    cs = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
-    yd = [torch.empty_like(y) for _ in range(2)]
-    xd = [None, None]
-    up = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
-    down = [torch.cuda.Event() for _ in range(2)]
-    step(yd[0].copy_(y_host, non_blocking=True))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    with torch.cuda.stream(cs):
-        yd[0].copy_(y_host, non_blocking=True); up[0].record(cs)
-    for i in range(args.steps):
-        b = i & 1
-        if i + 1 < args.steps:
-            with torch.cuda.stream(cs):
-                if i >= 1:
-                    cs.wait_event(done[1 - b])          # buffer 1-b was read by step i-1
-                yd[1 - b].copy_(y_host, non_blocking=True); up[1 - b].record(cs)
-        main.wait_event(up[b])
-        if i >= 2:
-            main.wait_event(down[b])                    # x buffer b fully downloaded before it is reused
-        xd[b] = step(yd[b])
-        done[b].record(main)
-        with torch.cuda.stream(cs):
-            cs.wait_event(done[b])
-            x_host.copy_(xd[b], non_blocking=True); down[b].record(cs)
-    main.wait_stream(cs)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+        def run(n):
+            for i in range(n):
+                sl = i & 1
+                if i >= 2:
+                    s.wait(sl)
+                s.forward_enqueue(sl, yh, lh, rh, hh, out=xo[sl])
+            s.wait(0); s.wait(1)
 
-    # the same batch through forward(checkpointed)+backward(+gradient all-reduce), 10 unrolled iterations: the
-    # training-shaped number the metric's "fwd+bwd" refers to (reported beside the headline, not instead of it)
-    ms_fb, K_fb = 0.0, 10
-    if not train and not grouped:
-        lam_t = lam.clone().requires_grad_(True); rho_t = rho.clone().requires_grad_(True); h_t = h.clone().requires_grad_(True)
-        tgt = torch.rand_like(y)
+        run(2)
+        barrier(c)
+        t0 = time.perf_counter()
+        run(steps)
+        barrier(c)
+        ms_e = max_over_ranks(c, [(time.perf_counter() - t0) * 1e3 / steps])[0]
+        r["e2e"] = {"value": px * K * c.world / (ms_e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e,
+                    "h2d_bytes_per_step": yh.numel() * 4, "d2h_bytes_per_step": yh.numel() * 4,
+                    "path": "admmtv_host_forward_enqueue / admmtv_host_wait, pinned host buffers, 2 slots"}
+        s.close()
+    return r
 
-        def fb_step():
-            for p_ in (lam_t, rho_t, h_t):
-                p_.grad = None
-            xx = ops.admm_layer_call(y, lam_t, rho_t, h_t, None, K_fb, False, "identity", 0.0, False, clamp=False)
-            xx.backward(2.0 * (xx.detach() - tgt) / xx.numel())
-            if world > 1:
-                dist.all_reduce(torch.cat([h_t.grad.reshape(-1), lam_t.grad, rho_t.grad]))
 
-        for _ in range(3):
-            fb_step()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(5):
-            fb_step()
-        f1.record()
-        barrier()
-        ms_fb = f0.elapsed_time(f1) / 5
-        del tgt
+def run_train(c, w, name, steps, warmup, full):
+    """fwd+bwd workloads.  full: roofline + e2e + launch count (the headline); else a short `others` entry."""
+    import torch
 
-    t = torch.tensor([ms, ms_e2e, ms_fb], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_fb = float(t[0]), float(t[1]), float(t[2])
+    B = w["B"] // c.world if w.get("strong") else w["B"]
+    ts = TrainStep(c, w, B, 1001 + c.rank)
+    ms, clk = timed(c, ts, steps, warmup)
+    pk, pk_src = peaks()
+    K = w["iters"]
+    px_all = ts.px * c.world
+    r = {"config": config_of(w, name), "n_gpus": c.world, "scaling": "strong" if w.get("strong") else "weak", "steps": steps,
+         "ms_per_step": ms, "value": px_all * K / (ms * 1e-3) / 1e6, "unit": UNIT,
+         "algorithmic_bytes_per_plane_pixel_iteration": alg_bytes(w),
+         "frac": alg_bytes(w) * ts.px * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "clocks": clk,
+         "per_gpu_batch": B, "collective": "one packed NCCL all-reduce of %d floats per step" % ts.ngrad if c.world > 1 else None}
+    r["config"]["per_gpu_batch"] = B
+    if not full:
+        del ts
+        torch.cuda.empty_cache()
+        return r, None
+    f, b = ts.profile()
+    n2, n1 = K, max(K - 1, 1)
+    kt = {"k_dim2<save F r_k>": f[1] / n2, "k_dim1_fwd": f[2] / n1, "k_dim2<G += Re(conj Z Z2)>": b[1] / n2, "k_dim1_bwd": b[2] / n1}
+    actual = {"k_dim2<save F r_k>": 12.0, "k_dim1_fwd": 28.0, "k_dim2<G += Re(conj Z Z2)>": 12.0, "k_dim1_bwd": 40.0}
+    it_ms = sum(kt.values())
+    achieved = (FWD_BYTES + BWD_BYTES) * ts.px / (it_ms * 1e-3) / 1e9
+    traffic, tsrc = None, None
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(prof):
+        try:
+            j = json.load(open(prof)).get(name, {})
+            traffic, tsrc = j.get("iteration_dram_bytes"), j.get("source")
+        except Exception:
+            pass
+    roofline = {
+        "bound": "hbm", "kernel": "one fwd+bwd ADMM iteration = k_dim2<save> + k_dim1_fwd + k_dim2<accG> + k_dim1_bwd (4 launches)",
+        "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+        "traffic": traffic, "traffic_source": tsrc or "not measured in this run (ncu --set full capture under profiles/)",
+        "peak_source": pk_src, "algorithmic_bytes_per_plane_pixel_iteration": FWD_BYTES + BWD_BYTES,
+        "units_per_launch": ts.px,
+        "per_kernel": {k: {"ms": v, "actual_bytes_per_px": actual[k], "actual_GBs": actual[k] * ts.px / (v * 1e-3) / 1e9,
+                           "frac_of_peak": actual[k] * ts.px / (v * 1e-3) / 1e9 / pk["hbm_gbs"]} for k, v in kt.items()},
+        "other_ms_per_step": f[3] + b[3],
+        "timing": "CUDA events around every launch on the launching stream (admmtv_profile_forward / _backward)",
+    }
+    e2e = e2e_train(c, w, B, steps, warmup, ts)
+    extra = {"roofline": roofline, "e2e": e2e, "launches_per_step": ts.launches}
+    del ts
+    torch.cuda.empty_cache()
+    return r, extra
 
-    if rank == 0 and grouped:
-        pk, pk_src = peaks()
-        bytes_per = 44.0 if w.get("iso") else FWD_BYTES
-        line = {
-            "metric": METRIC, "value": units_per_step * args.steps * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "mode": w["mode"]},
-            "hbm_frac_whole_step": FWD_BYTES * px * K / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
-            "e2e": {"value": units_per_step * args.steps * world / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4},
-            "clocks": clocks,
-        }
-        emit(line)
-    elif rank == 0:
-        pk, pk_src = peaks()
-        # per-kernel-class CUDA-event timing of one forward (profiling twin of the same call)
-        d = ops.make_desc_for(y, h, K, False, "identity", False, _lib.FLAG_NO_CLAMP, 0.0)
-        fwd_b, ck_b, _ = lib.workspace_bytes(d)
-        ws = torch.empty(fwd_b, dtype=torch.uint8, device=dev)
-        xo = torch.empty_like(y)
-        st = torch.cuda.current_stream().cuda_stream
-        hh = h.detach().clone(); ll = lam.detach().clone(); rr = rho.detach().clone()
-        lib.profile_forward(d, y.data_ptr(), hh.data_ptr(), ll.data_ptr(), rr.data_ptr(), None, xo.data_ptr(), ws.data_ptr(), None, st)
-        tot, t2, t1, toth = lib.profile_forward(d, y.data_ptr(), hh.data_ptr(), ll.data_ptr(), rr.data_ptr(), None, xo.data_ptr(),
-                                                ws.data_ptr(), None, st)
-        n2, n1 = K, max(K - 1, 1)
-        it_ms = t2 / n2 + t1 / n1                         # one ADMM iteration = one dim-2 + one dim-1 launch
-        alg_bytes = FWD_BYTES * px                         # algorithmic bytes of one iteration over the batch
-        achieved = alg_bytes / (it_ms * 1e-3) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(prof):
+
+def run_native(args, w, name):
+    import torch
+
+    c = setup_dist()
+    pk, pk_src = peaks()
+    if w["mode"] == "fwd+bwd":
+        r, extra = run_train(c, w, name, args.steps, args.warmup, True)
+    else:
+        r, extra = run_fwd(c, w, name, args.steps, args.warmup), None
+    others = {}
+    if not args.no_others and name == "cfg2_train":
+        for on in OTHERS:
+            ow = WORKLOADS[on]
+            st = 3 if ow["iters"] * ow["M"] * ow["N"] * ow["B"] * ow["P"] > 2e9 else 10
             try:
-                traffic = json.load(open(prof)).get(args.workload, {}).get("iteration_dram_bytes")
-            except Exception:
-                traffic = None
-        roofline = {
-            "bound": "hbm", "kernel": "one ADMM iteration = k_dim2 + k_dim1_fwd (2 launches)",
-            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-            "traffic": traffic, "peak_source": pk_src,
-            "algorithmic_bytes_per_plane_pixel_iteration": FWD_BYTES,
-            "per_kernel": {
-                "k_dim2": {"ms": t2 / n2, "actual_bytes_per_px": 8.0, "actual_GBs": 8.0 * px / (t2 / n2 * 1e-3) / 1e9},
-                "k_dim1_fwd": {"ms": t1 / n1, "actual_bytes_per_px": 28.0, "actual_GBs": 28.0 * px / (t1 / n1 * 1e-3) / 1e9},
-                "other_ms_per_call": toth,
-            },
-        }
-        launches = lib.forward_launches(d, train) + (lib.backward_launches(d) if train else 0)
-        cb = cpu_baseline(w)
-        bytes_per = FWD_BYTES + (BWD_BYTES if train else 0.0)
+                if ow["mode"] == "fwd+bwd":
+                    others[on], _ = run_train(c, ow, on, st, 3, False)
+                else:
+                    others[on] = run_fwd(c, ow, on, st, 3, e2e=(on == "cfg2"))
+            except Exception as e:   # an auxiliary shape must never take the headline down
+                others[on] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+    if c.rank == 0:
         line = {
-            "metric": METRIC, "value": units_per_step * args.steps * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "mode": w["mode"], "per_gpu_batch": w["B"], "l2": "inputs larger than L2 "
-                       f"({px * 28 / 1e6:.0f} MB of per-iteration state vs 126 MB L2); no flush needed",
-                       "lambda": 0.0041, "rho": 0.021, "iso": False},
-            "hbm_frac_whole_step": bytes_per * px * K / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
-            "roofline": roofline,
-            "cpu_baseline": cb,
-            "e2e": {"value": units_per_step * args.steps * world / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": y_host.numel() * 4, "d2h_bytes_per_step": x_host.numel() * 4,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches * args.steps,
-            "clocks": clocks,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": c.world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": r["config"],
+            "hbm_frac_whole_step": r["frac"], "clocks": r["clocks"],
         }
-        if ms_fb > 0:
-            line["fwd_bwd"] = {"iters": K_fb, "ms_per_step": ms_fb, "value": px * K_fb * world / (ms_fb * 1e-3) / 1e6, "unit": UNIT,
-                               "hbm_frac_whole_step": (FWD_BYTES + BWD_BYTES) * px * K_fb / (ms_fb * 1e-3) / 1e9 / pk["hbm_gbs"],
-                               "note": "same batch, forward (checkpointed) + hand-written backward + gradient all-reduce, "
-                                       "108 B/plane-pixel-iteration model"}
+        if extra:
+            e = extra["e2e"]
+            px_all = w["B"] * w["P"] * w["N"] * w["M"] * c.world
+            line["roofline"] = extra["roofline"]
+            line["e2e"] = {"value": px_all * w["iters"] / (e["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT, **e}
+            line["gpu_launches"] = extra["launches_per_step"] * args.steps
+            if c.world > 1:
+                line["collective"] = r["collective"]
+        elif "e2e" in r:
+            line["e2e"] = r["e2e"]
+        if c.world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(w)
+        if others:
+            line["others"] = others
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    if c.world > 1:
+        c.dist.destroy_process_group()
 
 
 _REAL_STDOUT = None
@@ -469,16 +611,18 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2_train", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, w)
+        run_reference(args, w, args.workload)
     else:
-        run_native(args, w)
+        run_native(args, w, args.workload)
 
 
 if __name__ == "__main__":

@@ -42,6 +42,23 @@ def test_loss_header_symbols_all_exported(lib):
         lib.ssim_workspace_bytes(8, 8, 1, 1, None, True)
 
 
+def test_host_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "admmtv_host.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(admmtv_(?:host|mse)_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.HOST_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib.lib, name), name
+    # sizing and validation need no GPU
+    d = _lib.make_desc(64, 64, 3, 2, 5, 5, 10)
+    infer, train = lib.host_session_bytes(d, False), lib.host_session_bytes(d, True)
+    fwd_b, ck_b, bwd_b = lib.workspace_bytes(d)
+    assert infer >= fwd_b + 4 * 64 * 64 * 3 * 2 * 4 and train >= infer + ck_b + bwd_b
+    assert lib.host_grad_floats(d) == 25 + 2
+    with pytest.raises(_lib.AdmmTvError):
+        lib.host_session_bytes(_lib.make_desc(64, 64, 3, 2, 5, 5, 0), True)
+
+
 def test_batch_header_symbols_all_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "admmtv_batch.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)

@@ -185,3 +185,45 @@ def test_backward_any_size(be, M, N, P, B, kh, kw, K, iso, flags):
     xbar = 2.0 * (y - g) / y.numel() * 1e3
     r = check_backward(be, y, h, 0.0041, 0.021, iso, K, xbar, flags=flags, tol=1e-5, tol_scalar=5e-4)   # teacher-forced (mask flips make end-to-end looser); rhobar is a cancelling sum and the direct prime-length DFTs add sqrt(L) rounding
     print(r)
+
+
+def test_no_grad_inference_allocates_no_checkpoint(monkeypatch):
+    """Parameters keep requires_grad=True under torch.no_grad(): the layer must still take the inference path (no
+    per-iteration checkpoint -- 60 GB at the bench shape -- and the non-saving kernels)."""
+    from admm_deconv_b200 import ops
+    d = torch.device("cuda:0")
+    layer = A.ADMMDeconv((5, 5), 6, "relu1").to(d)
+    with torch.no_grad():
+        layer.weight.copy_(A.from_julia(O.gaussian_psf(5, 1.0).float()).to(d)); layer.lam.fill_(0.01); layer.rho.fill_(0.05)
+    x = torch.rand(2, 3, 64, 64, device=d)
+    seen = []
+    real = ops._lib.AdmmTvLib.forward
+
+    def spy(self, desc, y, h, lam, rho, bias, x_out, ws, ckpt, stream=0):
+        seen.append(ckpt)
+        return real(self, desc, y, h, lam, rho, bias, x_out, ws, ckpt, stream)
+
+    monkeypatch.setattr(ops._lib.AdmmTvLib, "forward", spy)
+    with torch.no_grad():
+        out_ng = layer(x)
+    out_g = layer(x)
+    assert seen[0] is None and seen[1] is not None
+    assert not out_ng.requires_grad and out_g.requires_grad
+    assert torch.equal(out_ng, out_g.detach())
+
+
+def test_nonleaf_parameters_are_not_mutated_by_the_clamp():
+    """lam = softplus(raw) etc.: the kernel clamps a private copy; leaf parameters are clamped in place (reference)."""
+    d = torch.device("cuda:0")
+    y = torch.rand(1, 1, 32, 32, device=d)
+    raw = torch.tensor([-8.0], device=d, requires_grad=True)
+    lam = torch.nn.functional.softplus(raw)            # ~3.4e-4 < creg
+    rho = torch.tensor([0.05], device=d, requires_grad=True)
+    before = lam.detach().clone()
+    x = A.admm_layer_call(y, lam, rho, None, None, 4, False, "identity", 1e-2, False, clamp=True)
+    x.sum().backward()
+    assert torch.equal(lam.detach(), before)            # untouched
+    assert raw.grad is not None and float(raw.grad) == 0.0   # clamped from below creg: Zygote's clamp gate gives 0
+    leaf = torch.tensor([1e-4], device=d, requires_grad=True)
+    A.admm_layer_call(y, leaf, rho, None, None, 4, False, "identity", 1e-2, False, clamp=True)
+    assert float(leaf) == pytest.approx(1e-2)           # persisted (deconv_admm.jl:216)
