@@ -317,7 +317,7 @@ int admmtv_forward_launches(const admmtv_desc* d, int with_ckpt) {
     n += d->iters + (d->iters - 1) * (d->iso ? 5 : 3) + 2;
     return n;
   }
-  int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 2 : 0);
+  int n = 1 /*clamp*/ + 2 /*twiddles, tables*/ + (d->kh > 0 ? 1 : 0) + 1 /*pack*/ + (d->kh > 0 ? 3 : 0);
   n += d->iters + (d->iters - 1) * (d->iso ? 3 : 1) + 1;
   return n;
 }
@@ -387,11 +387,11 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
     OutArgs o{};
     o.spec = w.specB; o.packed = w.bpk; o.twM = twM; o.N = g.N; o.S = g.S; o.pm = g.pm; o.scale = 1.f / (float)g.M;
     if ((rc = run_dim1_out(g, 0, o, st))) return rc;
-    if (g.LM > 0) {
-      // specB IS the dim-1 spectrum of b = r_1 (z_0 = u_0 = 0): the first x-update reads it directly
-      cur = w.specB; oth = w.specA;
-    } else {
-      // generic sizes transform in place (inst_generic.cu), which consumed specB: transform b again
+    // r_1 = b: its dim-1 spectrum is taken from the ROUNDED spatial b (one more dim-1 pass) rather than from specB, which
+    // already holds it before rounding.  Reusing specB saves a launch (104 us at 64 x 512^2 x 3) but makes r_1 inconsistent
+    // with the r_k = b + rho D^T(...) of the later iterations at the rounding level, and the teacher-forced parameter
+    // gradients then sit 1.7x further from the fp64 adjoint (hbar 4.4e-6 -> 1.25e-5 on 2 x 256^2, K = 10): not worth 1 %.
+    {
       PackArgs p{};
       p.src_packed = w.bpk; p.spec = w.specA; p.twM = twM; p.N = g.N; p.S = g.S; p.pm = g.pm;
       if ((rc = run_pack_fft1(g, 2, p, st))) return rc;

@@ -85,7 +85,8 @@ struct Dim2Args {
   const float2* ktab;  // MUL 1/2: complex table [N][M] (2 = use its conjugate)
   float2* zsave;       // SAVE_Z: [Q][N][M] full spectrum before the multiply
   const float2* z2;    // ACC: second spectrum [Q][N][M]
-  float* gacc;         // ACC 1: float [N][M] += Re(conj(Z) Z2) ; ACC 2: float2 [N][M] += conj(Z) Z2
+  double* gacc;        // ACC 1: double [N][M] += Re(conj(Z) Z2) ; ACC 2: double2 [N][M] += conj(Z) Z2  (fp64: hundreds of
+                       //        partial sums meet here; in fp32 their rounding would set the error of hbar / rhobar)
   const float2* twN;
   int M;
   int Q;               // number of plane pairs (blocks loop q = blockIdx.y, += gridDim.y)

@@ -18,7 +18,16 @@ namespace admmtv {
 // ------------------------------------------------------------------------------------------
 // stage plans (DIF order: stage 0 works on the whole line, the last stage on R-long blocks)
 // ------------------------------------------------------------------------------------------
-ADMMTV_HD constexpr int plan_radix(int L, int s) {
+// Plan ids: 0 = the plan of the dim-1 (contiguous) transforms, 1 = the plan of the dim-2 (strided) pass.  They differ
+// where the dim-2 kernels profit from fewer, larger passes: those kernels are bound by the shared-memory / L1 data path
+// (ncu: l1tex 73 % vs DRAM 45 %), every pass costs one read and one write of the tile, and their work-item mapping
+// (rows x N / R items for 256 threads) fits any radix.  512 = 16 x 32 makes their forward + inverse transform 3 passes
+// instead of 5.  The spectrum order along a dimension follows the plan of that dimension (pos_to_freq).
+#ifndef ADMMTV_PLAN2_512
+#define ADMMTV_PLAN2_512 0   // measured on B200 (64 x 512^2 x 3): 16 x 32 needs 128 registers (2 blocks/SM): k_dim2 97 -> 103 us, save variant 135 -> 120, accG 179 -> 192: net zero, off
+#endif
+ADMMTV_HD constexpr int plan_radix(int L, int s, int P = 0) {
+  if (P == 1 && ADMMTV_PLAN2_512 && L == 512) return s == 0 ? 16 : (s == 1 ? 32 : 1);
   switch (L) {
     case 32:   return s == 0 ? 8 : (s == 1 ? 4 : 1);
     case 64:   return s < 2 ? 8 : 1;
@@ -45,15 +54,15 @@ ADMMTV_HD constexpr int plan_radix(int L, int s) {
     default:   return 1;
   }
 }
-ADMMTV_HD constexpr int plan_stages(int L) {
+ADMMTV_HD constexpr int plan_stages(int L, int P = 0) {
   int n = 0;
-  while (n < 4 && plan_radix(L, n) > 1) ++n;
+  while (n < 4 && plan_radix(L, n, P) > 1) ++n;
   return n;
 }
 // length of the sub-transforms stage s works on: L / prod_{q<s} R_q
-ADMMTV_HD constexpr int plan_sublen(int L, int s) {
+ADMMTV_HD constexpr int plan_sublen(int L, int s, int P = 0) {
   int len = L;
-  for (int q = 0; q < s; ++q) len /= plan_radix(L, q);
+  for (int q = 0; q < s; ++q) len /= plan_radix(L, q, P);
   return len;
 }
 ADMMTV_HD constexpr bool plan_supported(int L) { return plan_stages(L) >= 2; }
@@ -81,11 +90,11 @@ ADMMTV_HD inline int dim_id(int L) {
 
 // frequency index held at storage position p after the forward (DIF) passes
 // (`planned` = false: the generic path keeps spectra in natural order)
-ADMMTV_HD inline int pos_to_freq(int L, int p, bool planned = true) {
+ADMMTV_HD inline int pos_to_freq(int L, int p, bool planned = true, int P = 0) {
   if (!planned || !plan_supported(L)) return p;
   int k = 0, mult = 1, len = L;
   for (int s = 0; s < 4; ++s) {
-    int R = plan_radix(L, s);
+    int R = plan_radix(L, s, P);
     if (R <= 1) break;
     len /= R;
     int m = p / len;
@@ -160,6 +169,22 @@ ADMMTV_DI float2 mul_w16(float2 a) {
   }
 }
 
+// multiply by exp(-+ 2*pi*i * E/32): even exponents are the W16 cases above (identical code, identical bits)
+template <int E, bool INV>
+ADMMTV_DI float2 mul_w32(float2 a) {
+  constexpr int e = E & 31;
+  if constexpr ((e & 1) == 0) return mul_w16<e / 2, INV>(a);
+  else {
+    constexpr float C1 = 0.98078528040323043f, S1 = 0.19509032201612825f;   // cos, sin (pi/16)
+    constexpr float C3 = 0.83146961230254524f, S3 = 0.55557023301960218f;   // cos, sin (3 pi/16)
+    // angle = e * pi/16, e odd in 1..15 (the DIF butterflies only use the upper half-plane exponents)
+    static_assert(e < 16, "mul_w32: exponent out of the butterfly range");
+    constexpr float c = e == 1 ? C1 : e == 3 ? C3 : e == 5 ? S3 : e == 7 ? S1 : e == 9 ? -S1 : e == 11 ? -S3 : e == 13 ? -C3 : -C1;
+    constexpr float s = e == 1 ? S1 : e == 3 ? S3 : e == 5 ? C3 : e == 7 ? C1 : e == 9 ? C1 : e == 11 ? C3 : e == 13 ? S3 : S1;
+    return INV ? make_float2(a.x * c - a.y * s, a.x * s + a.y * c) : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // size-R DFT in registers, natural order in -> natural order out (recursive radix-2 DIF)
 // ------------------------------------------------------------------------------------------
@@ -180,7 +205,7 @@ struct Dft {
   static ADMMTV_DI void unroll_half(const float2* a, float2* s, float2* d) {
     if constexpr (T < R / 2) {
       s[T] = cadd(a[T], a[T + R / 2]);
-      d[T] = mul_w16<T * (16 / R), INV>(csub(a[T], a[T + R / 2]));
+      d[T] = mul_w32<T * (32 / R), INV>(csub(a[T], a[T + R / 2]));
       unroll_half<T + 1>(a, s, d);
     }
   }
@@ -234,10 +259,10 @@ ADMMTV_DI void twiddle_powers(float2 w, float2* p) {
 
 // One stage's work item: which line elements it touches and its twiddle base.
 //   elements: base + m*stride, m = 0..R-1 ; twiddle W_LS^(t*m) = tw[t*(L/LS)]^m
-template <int L, int S>
+template <int L, int S, int P = 0>
 struct Stage {
-  static constexpr int R = plan_radix(L, S);
-  static constexpr int LS = plan_sublen(L, S);
+  static constexpr int R = plan_radix(L, S, P);
+  static constexpr int LS = plan_sublen(L, S, P);
   static constexpr int STRIDE = LS / R;  // also the number of distinct t
   static constexpr int ITEMS = L / R;    // work items per line
   static constexpr bool HAS_TW = STRIDE > 1;
@@ -246,9 +271,9 @@ struct Stage {
 };
 
 // forward pass on registers: a <- twiddle( DFT_R(a) )
-template <int L, int S>
+template <int L, int S, int P = 0>
 ADMMTV_DI void stage_fwd(float2* a, const float2* p /*powers, only if HAS_TW*/) {
-  using St = Stage<L, S>;
+  using St = Stage<L, S, P>;
   Dft<St::R, false>::run(a);
   if constexpr (St::HAS_TW) {
 #pragma unroll
@@ -256,9 +281,9 @@ ADMMTV_DI void stage_fwd(float2* a, const float2* p /*powers, only if HAS_TW*/) 
   }
 }
 // inverse pass on registers: a <- IDFT_R( conj-twiddle(a) )   (p holds conj powers)
-template <int L, int S>
+template <int L, int S, int P = 0>
 ADMMTV_DI void stage_inv(float2* a, const float2* p) {
-  using St = Stage<L, S>;
+  using St = Stage<L, S, P>;
   if constexpr (St::HAS_TW) {
 #pragma unroll
     for (int m = 1; m < St::R; ++m) a[m] = cmul(a[m], p[m]);
@@ -267,9 +292,9 @@ ADMMTV_DI void stage_inv(float2* a, const float2* p) {
 }
 
 // twiddle powers for work item wi of stage S (forward sign, or conjugated for the inverse)
-template <int L, int S, bool INV>
+template <int L, int S, bool INV, int P = 0>
 ADMMTV_DI void stage_twiddles(int wi, const float2* __restrict__ tw, float2* p) {
-  using St = Stage<L, S>;
+  using St = Stage<L, S, P>;
   if constexpr (St::HAS_TW) {
     float2 w = tw[St::tindex(wi)];
     if (INV) w.y = -w.y;

@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
     if (C.acc) {
       const float2 z2 = A.z2[qoff + g];
       const float re = z.x * z2.x + z.y * z2.y, im = z.x * z2.y - z.y * z2.x;  // conj(Z) Z2
-      if (C.acc == 1) atomicAdd(A.gacc + toff + g, re);
+      if (C.acc == 1) atomicAdd(A.gacc + toff + g, (double)re);
       else {
-        atomicAdd(A.gacc + 2 * (toff + g), re);
-        atomicAdd(A.gacc + 2 * (toff + g) + 1, im);
+        atomicAdd(A.gacc + 2 * (toff + g), (double)re);
+        atomicAdd(A.gacc + 2 * (toff + g) + 1, (double)im);
       }
     }
     if (!C.fwd_only) {

@@ -7,9 +7,14 @@ template <> int Dim2Launch<ADMMTV_INST>::row_tile() { return 0; }
 }
 #else
 #include "kernels.cuh"
+#include "kernels_tma.cuh"
 
 #ifndef ADMMTV_INST
 #error "compile with -DADMMTV_INST=<log2 N>"
+#endif
+// lengths whose dim-2 pass runs the TMA-pipelined kernel k_dim2t (kernels_tma.cuh): bit (LN - 5) of this mask
+#ifndef ADMMTV_D2_TMA_MASK
+#define ADMMTV_D2_TMA_MASK 0
 #endif
 
 namespace admmtv {
@@ -63,6 +68,44 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
   // with one global atomic per element per ADMMTV_D2_ACC_QPB pairs
   if (variant == D2_C_ACCG && gy == g.Q) gy = (g.Q + ADMMTV_D2_ACC_QPB - 1) / ADMMTV_D2_ACC_QPB;
   if (gy > 65535) gy = 65535;  // blocks loop over pairs with stride gridDim.y
+#ifndef ADMMTV_EMU
+  if constexpr (LN >= 5 && LN <= 12 && Dim2tCfg<LN>::OK && ((ADMMTV_D2_TMA_MASK >> (LN - 5)) & 1)) {
+    // TMA-pipelined persistent kernel for the variants without gradient accumulation
+    if (variant != D2_C_ACCG && variant != D2_K_ACCP) {
+      using T = Dim2tCfg<LN>;
+      CUtensorMap map;
+      if (tma_make_map(&map, a.in, g.M, g.N, g.Q, T::TR, T::BOXC) == 0) {
+        static int sms = 0;
+        if (sms == 0) {
+          int dev = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int total = row_tiles * g.Q;
+        const dim3 tgrid((unsigned)(total < sms ? total : sms));
+        constexpr int TNT = kD2tGroups * kD2tGroupNT;
+#define ADMMTV_LAUNCH_T(KERN)                                                                                          \
+  do {                                                                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);             \
+    if (e != cudaSuccess) return (int)e;                                                                               \
+    KERN<<<tgrid, dim3(TNT), T::SMEM, st>>>(a, map);                                                                   \
+    ADMMTV_CHECK_LAUNCH();                                                                                             \
+    return 0;                                                                                                          \
+  } while (0)
+        switch (variant) {
+          case D2_C: ADMMTV_LAUNCH_T((k_dim2t<LN, 0, false, false>));
+          case D2_C_SAVE: ADMMTV_LAUNCH_T((k_dim2t<LN, 0, true, false>));
+          case D2_KCONJ: ADMMTV_LAUNCH_T((k_dim2t<LN, 1, false, false>));
+          case D2_KCONJ_SAVE: ADMMTV_LAUNCH_T((k_dim2t<LN, 1, true, false>));
+          case D2_K: ADMMTV_LAUNCH_T((k_dim2t<LN, 2, false, false>));
+          case D2_FWDONLY: ADMMTV_LAUNCH_T((k_dim2t<LN, 0, false, true>));
+          default: break;
+        }
+#undef ADMMTV_LAUNCH_T
+      }
+    }
+  }
+#endif
   const dim3 grid((unsigned)row_tiles, (unsigned)gy);
   switch (variant) {
     case D2_C: return launch_k(k_dim2<LN, 0, false, 0, false>, grid, Cfg::NT, Cfg::SMEM, st, a);

@@ -160,6 +160,9 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_MINB2
 #define ADMMTV_MINB2 1
 #endif
+#ifndef ADMMTV_MINB2_11
+#define ADMMTV_MINB2_11 1
+#endif
 // Asynchronous bulk prefetch of a contiguous global range into L2 (TMA unit, no registers, no
 // shared memory): issued for the stencil phase's inputs while the FFT passes run.
 ADMMTV_DI void l2_prefetch_bulk(const void* p, unsigned bytes) {
@@ -801,28 +804,30 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 //   inverse FFT along dim 2                                  (ops.jl:168  C .* rfft(...))
 // ------------------------------------------------------------------------------------------
 
+constexpr int kP2 = 1;   // plan id of the dim-2 transforms (fft_core.cuh)
+
 template <int LN>
 struct Dim2Cfg {
   static constexpr int N = dim_len(LN);
   static constexpr int TR = !is_pow2(N) ? (N <= 640 ? 16 : 8)
                                         : (LN <= 6 ? 16 : (LN == 7 ? ADMMTV_TR7 : (LN == 8 ? ADMMTV_TR8 : (LN == 9 ? ADMMTV_TR9 : (LN == 10 ? 8 : (LN == 11 ? ADMMTV_TR11 : 4))))));
   // block size = work items of the widest pass (row pairs x N / largest radix), within [32, 512]
-  static constexpr int ITEMS_MAX = (TR / 2) * (N / plan_radix(N, 0));
+  static constexpr int ITEMS_MAX = (TR / 2) * (N / plan_radix(N, 0, kP2));
   static constexpr int NT_AUTO = ITEMS_MAX < 32 ? 32 : (ITEMS_MAX > ADMMTV_NT2_MAX ? ADMMTV_NT2_MAX : ITEMS_MAX);
   static constexpr int NT = LN == 9 ? ADMMTV_NT2 : NT_AUTO;
-  static constexpr int MINB = LN == 9 ? ADMMTV_MINB2 : 1;
+  static constexpr int MINB = LN == 9 ? ADMMTV_MINB2 : (LN == 11 ? ADMMTV_MINB2_11 : 1);
   static constexpr size_t SMEM = (size_t)N * TR * sizeof(float2);
 };
 
-template <int LN, int S, bool INV, int NTX = Dim2Cfg<LN>::NT>
+template <int LN, int S, bool INV, int NTX = Dim2Cfg<LN>::NT, int TRX = Dim2Cfg<LN>::TR>
 ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int tid) {
   using Cfg = Dim2Cfg<LN>;
-  constexpr int N = Cfg::N, TR = Cfg::TR, NT = NTX, RP = TR / 2;
-  using St = Stage<N, S>;
+  constexpr int N = Cfg::N, TR = TRX, NT = NTX, RP = TR / 2;
+  using St = Stage<N, S, kP2>;
   for (int item = tid; item < RP * St::ITEMS; item += NT) {
     const int rp = item % RP, wi = item / RP;
     float2 p[St::R];
-    stage_twiddles<N, S, INV>(wi, tw, p);
+    stage_twiddles<N, S, INV, kP2>(wi, tw, p);
     float2 a0[St::R], a1[St::R];
     const int base = St::base(wi);
 #pragma unroll
@@ -832,11 +837,11 @@ ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int 
       a1[m] = make_float2(v.z, v.w);
     }
     if (INV) {
-      stage_inv<N, S>(a0, p);
-      stage_inv<N, S>(a1, p);
+      stage_inv<N, S, kP2>(a0, p);
+      stage_inv<N, S, kP2>(a1, p);
     } else {
-      stage_fwd<N, S>(a0, p);
-      stage_fwd<N, S>(a1, p);
+      stage_fwd<N, S, kP2>(a0, p);
+      stage_fwd<N, S, kP2>(a1, p);
     }
 #pragma unroll
     for (int m = 0; m < St::R; ++m)
@@ -845,7 +850,7 @@ ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int 
 }
 template <int LN, int S, int NTX = Dim2Cfg<LN>::NT>
 ADMMTV_DI void dim2_fwd_mid(float2* tile, const float2* __restrict__ tw, int tid) {
-  if constexpr (S < plan_stages(dim_len(LN)) - 1) {
+  if constexpr (S < plan_stages(dim_len(LN), kP2) - 1) {
     dim2_smem_stage<LN, S, false, NTX>(tile, tw, tid);
     __syncthreads();
     dim2_fwd_mid<LN, S + 1, NTX>(tile, tw, tid);
@@ -869,13 +874,145 @@ ADMMTV_DI void l2_prefetch_line(const void* p) {
 #endif
 }
 
+// The last forward stage fused with [save Z] -> [accumulate conj(Z) Z2] -> spectral multiply -> first inverse stage,
+// over the whole tile.  Two mappings: radix <= 16 works on ROW PAIRS (float4 shared-memory accesses, both rows share the
+// index arithmetic); radix 32 works on single rows (32 complex values are all the registers a thread has).  Each tile
+// element is owned by exactly one thread in either mapping (dim2_fused_flush relies on it).
+template <int LN, int MUL, bool SAVE_Z, int ACC, bool FWD_ONLY, int NT, int TR>
+ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, size_t qoff, size_t toff, int i0, int tid) {
+  constexpr int N = dim_len(LN), NS = plan_stages(N, kP2), RP = TR / 2;
+  using StL = Stage<N, NS - 1, kP2>;
+  static_assert(StL::STRIDE == 1, "last plan stage must be contiguous");
+  constexpr bool SMACC = ACC == 1;
+  const int M = A.M;
+  if constexpr (StL::R <= 16) {
+#pragma unroll 1
+    for (int item = tid; item < RP * StL::ITEMS; item += NT) {
+      const int rp = item % RP, wi = item / RP;
+      float2 a0[StL::R], a1[StL::R];
+#pragma unroll
+      for (int m = 0; m < StL::R; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + (wi * StL::R + m) * TR + 2 * rp);
+        a0[m] = make_float2(v.x, v.y);
+        a1[m] = make_float2(v.z, v.w);
+      }
+      Dft<StL::R, false>::run(a0);
+      Dft<StL::R, false>::run(a1);
+#pragma unroll
+      for (int m = 0; m < StL::R; ++m) {
+        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;  // table / spectrum offset
+        if (SAVE_Z || FWD_ONLY) {
+          float2* zs = FWD_ONLY ? A.out : A.zsave;
+          *reinterpret_cast<float4*>(zs + qoff + g) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+        }
+        if (ACC != 0) {
+          const float4 z2 = *reinterpret_cast<const float4*>(A.z2 + qoff + g);
+          // conj(Z) * Z2
+          const float re0 = a0[m].x * z2.x + a0[m].y * z2.y, im0 = a0[m].x * z2.y - a0[m].y * z2.x;
+          const float re1 = a1[m].x * z2.z + a1[m].y * z2.w, im1 = a1[m].x * z2.w - a1[m].y * z2.z;
+          if (SMACC) {
+            float2* gp = reinterpret_cast<float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
+            float2 gv = *gp;
+            gv.x += re0;
+            gv.y += re1;
+            *gp = gv;
+          } else {
+            atomicAdd(A.gacc + 2 * (toff + g), (double)re0);
+            atomicAdd(A.gacc + 2 * (toff + g) + 1, (double)im0);
+            atomicAdd(A.gacc + 2 * (toff + g) + 2, (double)re1);
+            atomicAdd(A.gacc + 2 * (toff + g) + 3, (double)im1);
+          }
+        }
+        if (!FWD_ONLY) {
+          if (MUL == 0) {
+            const float2 cc = *reinterpret_cast<const float2*>(A.ctab + toff + g);
+            a0[m] = cscale(a0[m], cc.x);
+            a1[m] = cscale(a1[m], cc.y);
+          } else {
+            const float4 kk = *reinterpret_cast<const float4*>(A.ktab + toff + g);
+            const float sgn = MUL == 2 ? -1.f : 1.f;
+            a0[m] = cmul(a0[m], make_float2(kk.x, sgn * kk.y));
+            a1[m] = cmul(a1[m], make_float2(kk.z, sgn * kk.w));
+          }
+        }
+      }
+      if (!FWD_ONLY) {
+        Dft<StL::R, true>::run(a0);
+        Dft<StL::R, true>::run(a1);
+#pragma unroll
+        for (int m = 0; m < StL::R; ++m)
+          *reinterpret_cast<float4*>(tile + (wi * StL::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+      }
+    }
+  } else {
+    // single rows: lanes run along the TR contiguous rows of a column (conflict-free 8-byte accesses)
+#pragma unroll 1
+    for (int item = tid; item < TR * StL::ITEMS; item += NT) {
+      const int r = item % TR, wi = item / TR;
+      float2 a[StL::R];
+#pragma unroll
+      for (int m = 0; m < StL::R; ++m) a[m] = tile[(wi * StL::R + m) * TR + r];
+      Dft<StL::R, false>::run(a);
+#pragma unroll
+      for (int m = 0; m < StL::R; ++m) {
+        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + r;
+        if (SAVE_Z || FWD_ONLY) (FWD_ONLY ? A.out : A.zsave)[qoff + g] = a[m];
+        if (ACC != 0) {
+          const float2 z2 = A.z2[qoff + g];
+          const float re = a[m].x * z2.x + a[m].y * z2.y, im = a[m].x * z2.y - a[m].y * z2.x;   // conj(Z) * Z2
+          if (SMACC) gsm[(wi * StL::R + m) * TR + r] += re;
+          else {
+            atomicAdd(A.gacc + 2 * (toff + g), (double)re);
+            atomicAdd(A.gacc + 2 * (toff + g) + 1, (double)im);
+          }
+        }
+        if (!FWD_ONLY) {
+          if (MUL == 0) a[m] = cscale(a[m], A.ctab[toff + g]);
+          else {
+            const float2 kk = A.ktab[toff + g];
+            a[m] = cmul(a[m], make_float2(kk.x, MUL == 2 ? -kk.y : kk.y));
+          }
+        }
+      }
+      if (!FWD_ONLY) {
+        Dft<StL::R, true>::run(a);
+#pragma unroll
+        for (int m = 0; m < StL::R; ++m) tile[(wi * StL::R + m) * TR + r] = a[m];
+      }
+    }
+  }
+}
+// gacc += the block's shared-memory partial sums of G (same thread -> element ownership as dim2_fused_stage)
+template <int LN, int NT, int TR>
+ADMMTV_DI void dim2_fused_flush(const float* gsm, const Dim2Args& A, size_t toff, int i0, int tid) {
+  constexpr int N = dim_len(LN), NS = plan_stages(N, kP2), RP = TR / 2;
+  using StL = Stage<N, NS - 1, kP2>;
+  const int M = A.M;
+  if constexpr (StL::R <= 16) {
+    for (int item = tid; item < RP * StL::ITEMS; item += NT) {
+      const int rp = item % RP, wi = item / RP;
+#pragma unroll
+      for (int m = 0; m < StL::R; ++m) {
+        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;
+        const float2 gv = *reinterpret_cast<const float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
+        atomicAdd(A.gacc + toff + g, (double)gv.x);
+        atomicAdd(A.gacc + toff + g + 1, (double)gv.y);
+      }
+    }
+  } else {
+    for (int item = tid; item < TR * StL::ITEMS; item += NT) {
+      const int r = item % TR, wi = item / TR;
+#pragma unroll
+      for (int m = 0; m < StL::R; ++m)
+        atomicAdd(A.gacc + toff + (size_t)(wi * StL::R + m) * M + i0 + r, (double)gsm[(wi * StL::R + m) * TR + r]);
+    }
+  }
+}
+
 template <int LN, int MUL, bool SAVE_Z, int ACC, bool FWD_ONLY>
 __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim2Args A) {
   using Cfg = Dim2Cfg<LN>;
-  constexpr int N = Cfg::N, TR = Cfg::TR, NT = Cfg::NT, RP = TR / 2, NS = plan_stages(N);
-  using StL = Stage<N, NS - 1>;
-  static_assert(StL::STRIDE == 1, "last plan stage must be contiguous");
-  constexpr int IPT = (RP * StL::ITEMS + NT - 1) / NT;  // fused-stage items per thread
+  constexpr int N = Cfg::N, TR = Cfg::TR, NT = Cfg::NT, RP = TR / 2, NS = plan_stages(N, kP2);
   // G = sum over pairs of Re(conj(Z) Z2) is accumulated in shared memory across this block's
   // pairs (each element is owned by one thread) and flushed with one atomic per element at the
   // end, instead of one global atomic per element per pair.
@@ -884,7 +1021,6 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
   const int tid = threadIdx.x, M = A.M;
   const int i0 = blockIdx.x * TR;
   float* gsm = reinterpret_cast<float*>(tile + N * TR);
-  (void)IPT;
 
   for (int q = blockIdx.y; q < A.Q; q += gridDim.y) {
     const size_t qoff = (size_t)q * N * M;
@@ -915,11 +1051,11 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
 
     // forward stage 0: global -> registers -> shared
     {
-      using St = Stage<N, 0>;
+      using St = Stage<N, 0, kP2>;
       for (int item = tid; item < RP * St::ITEMS; item += NT) {
         const int rp = item % RP, wi = item / RP;
         float2 p[St::R];
-        stage_twiddles<N, 0, false>(wi, A.twN, p);
+        stage_twiddles<N, 0, false, kP2>(wi, A.twN, p);
         float2 a0[St::R], a1[St::R];
 #pragma unroll
         for (int m = 0; m < St::R; ++m) {
@@ -927,8 +1063,8 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
           a0[m] = make_float2(v.x, v.y);
           a1[m] = make_float2(v.z, v.w);
         }
-        stage_fwd<N, 0>(a0, p);
-        stage_fwd<N, 0>(a1, p);
+        stage_fwd<N, 0, kP2>(a0, p);
+        stage_fwd<N, 0, kP2>(a1, p);
 #pragma unroll
         for (int m = 0; m < St::R; ++m)
           *reinterpret_cast<float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
@@ -938,77 +1074,19 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
     dim2_fwd_mid<LN, 1>(tile, A.twN, tid);
 
     // last forward stage fused with the spectral multiply and the first inverse stage
-    auto fused_item = [&](int item) {
-      const int rp = item % RP, wi = item / RP;
-      float2 a0[StL::R], a1[StL::R];
-#pragma unroll
-      for (int m = 0; m < StL::R; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + (wi * StL::R + m) * TR + 2 * rp);
-        a0[m] = make_float2(v.x, v.y);
-        a1[m] = make_float2(v.z, v.w);
-      }
-      Dft<StL::R, false>::run(a0);
-      Dft<StL::R, false>::run(a1);
-#pragma unroll
-      for (int m = 0; m < StL::R; ++m) {
-        const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;  // table / spectrum offset
-        if (SAVE_Z || FWD_ONLY) {
-          float2* zs = FWD_ONLY ? A.out : A.zsave;
-          *reinterpret_cast<float4*>(zs + qoff + g) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
-        }
-        if (ACC != 0) {
-          const float4 z2 = *reinterpret_cast<const float4*>(A.z2 + qoff + g);
-          // conj(Z) * Z2
-          const float re0 = a0[m].x * z2.x + a0[m].y * z2.y, im0 = a0[m].x * z2.y - a0[m].y * z2.x;
-          const float re1 = a1[m].x * z2.z + a1[m].y * z2.w, im1 = a1[m].x * z2.w - a1[m].y * z2.z;
-          if (SMACC) {
-            float2* gp = reinterpret_cast<float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
-            float2 gv = *gp;
-            gv.x += re0;
-            gv.y += re1;
-            *gp = gv;
-          } else {
-            atomicAdd(A.gacc + 2 * (toff + g), re0);
-            atomicAdd(A.gacc + 2 * (toff + g) + 1, im0);
-            atomicAdd(A.gacc + 2 * (toff + g) + 2, re1);
-            atomicAdd(A.gacc + 2 * (toff + g) + 3, im1);
-          }
-        }
-        if (!FWD_ONLY) {
-          if (MUL == 0) {
-            const float2 cc = *reinterpret_cast<const float2*>(A.ctab + toff + g);
-            a0[m] = cscale(a0[m], cc.x);
-            a1[m] = cscale(a1[m], cc.y);
-          } else {
-            const float4 kk = *reinterpret_cast<const float4*>(A.ktab + toff + g);
-            const float sgn = MUL == 2 ? -1.f : 1.f;
-            a0[m] = cmul(a0[m], make_float2(kk.x, sgn * kk.y));
-            a1[m] = cmul(a1[m], make_float2(kk.z, sgn * kk.w));
-          }
-        }
-      }
-      if (!FWD_ONLY) {
-        Dft<StL::R, true>::run(a0);
-        Dft<StL::R, true>::run(a1);
-#pragma unroll
-        for (int m = 0; m < StL::R; ++m)
-          *reinterpret_cast<float4*>(tile + (wi * StL::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
-      }
-    };
-#pragma unroll 1
-    for (int item = tid; item < RP * StL::ITEMS; item += NT) fused_item(item);
+    dim2_fused_stage<LN, MUL, SAVE_Z, ACC, FWD_ONLY, NT, TR>(tile, gsm, A, qoff, toff, i0, tid);
     __syncthreads();
     if (FWD_ONLY) continue;
     dim2_inv_mid<LN, NS - 2>(tile, A.twN, tid);
 
     // inverse stage 0: shared -> registers -> global
     {
-      using St = Stage<N, 0>;
+      using St = Stage<N, 0, kP2>;
       float2* dst = A.out + qoff + i0;
       for (int item = tid; item < RP * St::ITEMS; item += NT) {
         const int rp = item % RP, wi = item / RP;
         float2 p[St::R];
-        stage_twiddles<N, 0, true>(wi, A.twN, p);
+        stage_twiddles<N, 0, true, kP2>(wi, A.twN, p);
         float2 a0[St::R], a1[St::R];
 #pragma unroll
         for (int m = 0; m < St::R; ++m) {
@@ -1016,29 +1094,16 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
           a0[m] = make_float2(v.x, v.y);
           a1[m] = make_float2(v.z, v.w);
         }
-        stage_inv<N, 0>(a0, p);
-        stage_inv<N, 0>(a1, p);
+        stage_inv<N, 0, kP2>(a0, p);
+        stage_inv<N, 0, kP2>(a1, p);
 #pragma unroll
         for (int m = 0; m < St::R; ++m)
           *reinterpret_cast<float4*>(dst + (size_t)(wi + m * St::STRIDE) * M + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
       }
     }
-    if (SMACC && last_of_run) {
-      // flush this block's run of same-group pairs (same thread -> element ownership as the fused stage)
-      for (int item = tid; item < RP * StL::ITEMS; item += NT) {
-        const int rp = item % RP, wi = item / RP;
-#pragma unroll
-        for (int m = 0; m < StL::R; ++m) {
-          const size_t g = (size_t)(wi * StL::R + m) * M + i0 + 2 * rp;
-          const float2 gv = *reinterpret_cast<const float2*>(gsm + (wi * StL::R + m) * TR + 2 * rp);
-          atomicAdd(A.gacc + toff + g, gv.x);
-          atomicAdd(A.gacc + toff + g + 1, gv.y);
-        }
-      }
-    }
+    if (SMACC && last_of_run) dim2_fused_flush<LN, NT, TR>(gsm, A, toff, i0, tid);
     __syncthreads();  // the tile is rewritten by the next pair's first pass
   }
-
 }
 
 }  // namespace admmtv

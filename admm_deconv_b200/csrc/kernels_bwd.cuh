@@ -21,6 +21,12 @@
 #ifndef ADMMTV_MINB9B
 #define ADMMTV_MINB9B 2
 #endif
+#ifndef ADMMTV_MINB8B
+#define ADMMTV_MINB8B 2   // 256-row planes: 148 -> 128 registers, 2 blocks/SM: backward sweep 612 -> 443 us on 768 planes of 256^2
+#endif
+#ifndef ADMMTV_MINB7B
+#define ADMMTV_MINB7B 4   // 128-row planes: 150 -> 136 us on 1024 planes of 128^2
+#endif
 
 namespace admmtv {
 
@@ -73,7 +79,8 @@ ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float2 s
 // MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel (s, tau ip / n^3) in A.sc from k_iso_coef, which also
 // adds the per-pixel taubar terms; bbar was accumulated by pass A).
 template <int LM, bool HAS_VBAR, int MODE = 0>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : 1) k_dim1_bwd(Dim1BwdArgs A) {
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : (LM == 8 ? ADMMTV_MINB8B : (LM == 7 ? ADMMTV_MINB7B : 1)))
+    k_dim1_bwd(Dim1BwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNKB;
   static_assert(CO % CHUNK == 0, "chunking must divide the tile");

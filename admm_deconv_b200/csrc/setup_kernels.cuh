@@ -87,7 +87,7 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
     if (sig) sig += grp * (size_t)M * N;
   }
   const int p1 = idx % M, p2 = idx / M;
-  const int k1 = pos_to_freq(M, p1, (planned & 1) != 0), k2 = pos_to_freq(N, p2, (planned & 2) != 0);
+  const int k1 = pos_to_freq(M, p1, (planned & 1) != 0), k2 = pos_to_freq(N, p2, (planned & 2) != 0, 1);
   double sr = 1.0, si = 0.0;
   if (kh > 0) {
     sr = 0.0;
@@ -184,7 +184,7 @@ static __global__ void k_iso_coef(const float* __restrict__ part, int Qg, const 
 //   hbar[a,b] = Re sum_k W[k] e^{+2 pi i (k1 a/M + k2 b/N)},
 //   W = 2 Sbar Sigma  +  (1/MN) P e^{-2 pi i (k1 pd/M + k2 pr/N)}   (spectral C path + spatial H^T y path)
 // ------------------------------------------------------------------------------------------
-static __global__ void k_grad_tables(const float* __restrict__ gacc, const float2* __restrict__ pacc,
+static __global__ void k_grad_tables(const double* __restrict__ gacc, const double2* __restrict__ pacc,
                                      const float* __restrict__ ctab, const float2* __restrict__ sig, int kh, int kw,
                                      int M, int N, int use_spatial, double2* Wn, double* acc, int planned) {
   const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,10 +199,10 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
     acc += 8 * blockIdx.y;
   }
   const int p1 = idx % M, p2 = idx / M;
-  const int k1 = pos_to_freq(M, p1, (planned & 1) != 0), k2 = pos_to_freq(N, p2, (planned & 2) != 0);
+  const int k1 = pos_to_freq(M, p1, (planned & 1) != 0), k2 = pos_to_freq(N, p2, (planned & 2) != 0, 1);
   const double mn = (double)M * (double)N;
   const double C = (double)ctab[idx] * mn;
-  const double Sbar = -((double)gacc[idx] / mn) * C * C;
+  const double Sbar = -(gacc[idx] / mn) * C * C;
   double s1, c1, s2, c2;
   sincospi((double)k2 / N, &s2, &c2);
   sincospi((double)k1 / M, &s1, &c1);
@@ -216,7 +216,7 @@ static __global__ void k_grad_tables(const float* __restrict__ gacc, const float
       const int pd = (kh - 1) / 2, pr = (kw - 1) / 2;
       double ps, pc;
       sincospi(2.0 * ((double)((long long)k1 * pd % M) / M + (double)((long long)k2 * pr % N) / N), &ps, &pc);
-      const double pr_ = (double)pacc[idx].x / mn, pi_ = (double)pacc[idx].y / mn;
+      const double pr_ = pacc[idx].x / mn, pi_ = pacc[idx].y / mn;
       // P * (pc - i ps)
       wr += pr_ * pc + pi_ * ps;
       wi += pi_ * pc - pr_ * ps;

@@ -41,6 +41,8 @@ WORKLOADS = {
     "cfg3": dict(B=256, P=3, N=256, M=256, k=15, iters=10, mode="fwd+bwd", psf="gauss", strong=True,
                  desc="BASELINE.json configs[2]: training step, 10 learned-rho/lambda iterations, fwd+bwd, GLOBAL batch "
                       "256 x 256x256 RGB split over the ranks (strong scaling), Gaussian PSF 15x15, NCCL gradient all-reduce"),
+    "cfg3_share": dict(B=32, P=3, N=256, M=256, k=15, iters=10, mode="fwd+bwd", psf="gauss",
+                       desc="one GPU's share of BASELINE.json configs[2] at 8 GPUs: 32 x 256x256 RGB, 10 iterations, fwd+bwd"),
     "cfg4": dict(B=16, P=1, N=2048, M=2048, k=31, iters=200, mode="fwd", psf="motion",
                  desc="BASELINE.json configs[3]: batch 16 x 2048x2048 gray, 31x31 PSF, 200-iteration forward"),
     "cfg5": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="fwd", psf="motion",

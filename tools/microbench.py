@@ -16,7 +16,7 @@ tags = [a for a in sys.argv[3:] if not a.startswith("--")]
 ISO = "--iso" in sys.argv
 NOPSF = "--nopsf" in sys.argv
 w = dict(bench.WORKLOADS[name], iters=iters)
-y, h = bench.make_inputs(w, 1001)
+y, _, h = bench.make_inputs(w, 1001)
 dev = torch.device("cuda:0")
 y = y.to(dev); h = None if NOPSF else h.to(dev)
 hp = None if h is None else h.data_ptr()
