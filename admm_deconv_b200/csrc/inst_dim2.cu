@@ -14,7 +14,11 @@ template <> int Dim2Launch<ADMMTV_INST>::row_tile() { return 0; }
 #endif
 // lengths whose dim-2 pass runs the TMA-pipelined kernel k_dim2t (kernels_tma.cuh): bit (LN - 5) of this mask
 #ifndef ADMMTV_D2_TMA_MASK
-#define ADMMTV_D2_TMA_MASK 0
+#define ADMMTV_D2_TMA_MASK (1 << (9 - 5))
+#endif
+// ... and which variants take it there: 0 = only the checkpoint-saving ones (training forward), 1 = all without accumulation
+#ifndef ADMMTV_D2_TMA_ALL
+#define ADMMTV_D2_TMA_ALL 0
 #endif
 
 namespace admmtv {
@@ -71,7 +75,7 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
 #ifndef ADMMTV_EMU
   if constexpr (LN >= 5 && LN <= 12 && Dim2tCfg<LN>::OK && ((ADMMTV_D2_TMA_MASK >> (LN - 5)) & 1)) {
     // TMA-pipelined persistent kernel for the variants without gradient accumulation
-    if (variant != D2_C_ACCG && variant != D2_K_ACCP) {
+    if (variant != D2_C_ACCG && variant != D2_K_ACCP && (ADMMTV_D2_TMA_ALL || variant == D2_C_SAVE || variant == D2_KCONJ_SAVE)) {
       using T = Dim2tCfg<LN>;
       CUtensorMap map;
       if (tma_make_map(&map, a.in, g.M, g.N, g.Q, T::TR, T::BOXC) == 0) {
@@ -83,7 +87,7 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
         }
         const int total = row_tiles * g.Q;
         const dim3 tgrid((unsigned)(total < sms ? total : sms));
-        constexpr int TNT = kD2tGroups * kD2tGroupNT;
+        constexpr int TNT = T::NT;
 #define ADMMTV_LAUNCH_T(KERN)                                                                                          \
   do {                                                                                                                 \
     cudaError_t e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);             \

@@ -23,22 +23,33 @@ namespace admmtv {
 #define ADMMTV_D2T_GROUPS 3
 #endif
 #ifndef ADMMTV_D2T_TR9
-#define ADMMTV_D2T_TR9 8
+#define ADMMTV_D2T_TR9 16
 #endif
-constexpr int kD2tGroups = ADMMTV_D2T_GROUPS;   // independent compute groups per block
-constexpr int kD2tGroupNT = 256;                // threads per group
-constexpr int kD2tPB = 2;                       // tile buffers per group (double buffering)
-constexpr int kD2tBufs = kD2tGroups * kD2tPB;
+#ifndef ADMMTV_D2T_TR11
+#define ADMMTV_D2T_TR11 4
+#endif
+constexpr int kD2tGroupNT = 256;                // threads per compute group
 
+// Two ring organisations:
+//   SHARED : G groups share NB buffers; local tile n lives in buffer n % NB and is worked on by group n % G; the group
+//            that finishes tile n hands its buffer to the TMA unit for tile n + NB.  (N = 2048: 64 KB tiles of 4 rows,
+//            2 groups, 3 buffers -- the plain kernel needs 8-row tiles there, i.e. ONE 128 KB block per SM with nothing
+//            to overlap its loads with, and 4-row tiles make its LDG.128 touch sixteen 32-byte sectors per request.)
+//   else   : every group owns two buffers (double buffering): its next tile loads while it works on the current one.
 template <int LN>
 struct Dim2tCfg {
   static constexpr int N = dim_len(LN);
-  static constexpr int TR = LN == 9 ? ADMMTV_D2T_TR9 : Dim2Cfg<LN>::TR;   // rows per tile (its own choice: smaller tiles, deeper ring)
+  static constexpr bool SHARED = LN >= 9;
+  static constexpr int TR = LN == 9 ? ADMMTV_D2T_TR9 : (LN == 11 ? ADMMTV_D2T_TR11 : Dim2Cfg<LN>::TR);   // rows per tile
+  static constexpr int G = SHARED ? 2 : ADMMTV_D2T_GROUPS;   // independent compute groups per block
+  static constexpr int NB = SHARED ? 3 : 2 * G;              // tile buffers
+  static constexpr int NT = G * kD2tGroupNT;
   static constexpr int BOXC = N < 256 ? N : 256;          // columns per TMA box (box dimensions are limited to 256)
   static constexpr int NBOX = N / BOXC;
   static constexpr size_t TILE_BYTES = (size_t)N * TR * sizeof(float2);
-  static constexpr size_t SMEM = kD2tBufs * TILE_BYTES + 128;   // + the mbarriers
-  static constexpr bool OK = is_pow2(N) && TR >= 2 && SMEM <= 227 * 1024 && ((TR / 2) * (N / plan_radix(N, 0, kP2))) % kD2tGroupNT == 0;
+  static constexpr size_t SMEM = NB * TILE_BYTES + 128;   // + the mbarriers
+  static constexpr bool OK = is_pow2(N) && TR >= 2 && SMEM <= 227 * 1024 && ((TR / 2) * (N / plan_radix(N, 0, kP2))) % kD2tGroupNT == 0 &&
+                             ((TR / 2) * (N / plan_radix(N, 0, kP2))) / kD2tGroupNT * plan_radix(N, 0, kP2) <= 16;
 };
 
 ADMMTV_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -69,7 +80,7 @@ ADMMTV_DI void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, in
       : "memory");
 }
 ADMMTV_DI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-ADMMTV_DI void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kD2tGroupNT) : "memory"); }
+ADMMTV_DI void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kD2tGroupNT) : "memory"); }   // named barrier of one group
 
 template <int LN, int S>
 ADMMTV_DI void dim2t_fwd_mid(float2* tile, const float2* __restrict__ tw, int lt, int bar) {
@@ -90,27 +101,29 @@ ADMMTV_DI void dim2t_inv_mid(float2* tile, const float2* __restrict__ tw, int lt
 
 // variants without gradient accumulation: (MUL, SAVE_Z, FWD_ONLY) as k_dim2
 template <int LN, int MUL, bool SAVE_Z, bool FWD_ONLY>
-__global__ void __launch_bounds__(kD2tGroups* kD2tGroupNT, 1) k_dim2t(Dim2Args A, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(Dim2tCfg<LN>::NT, 1) k_dim2t(Dim2Args A, const __grid_constant__ CUtensorMap tmap) {
   using Cfg = Dim2tCfg<LN>;
   constexpr int N = Cfg::N, TR = Cfg::TR, RP = TR / 2, NS = plan_stages(N, kP2), GNT = kD2tGroupNT;
   constexpr int TE = N * TR;   // float2 elements per tile
   using St0 = Stage<N, 0, kP2>;
   constexpr int IT0 = (RP * St0::ITEMS) / GNT;   // stage-0 items per thread
   static_assert((RP * St0::ITEMS) % GNT == 0 && IT0 >= 1 && IT0 * St0::R <= 16, "inverse stage 0 must fit in registers");
-  ADMMTV_DYN_SMEM(float2, ring);   // [kD2tBufs][N][TR], then the mbarriers
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)kD2tBufs * TE);
+  constexpr int G = Cfg::G, NB = Cfg::NB;
+  constexpr bool SHARED = Cfg::SHARED;
+  ADMMTV_DYN_SMEM(float2, ring);   // [NB][N][TR], then the mbarriers
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)NB * TE);
   const int tid = threadIdx.x, M = A.M;
   const int grp = tid / GNT, lt = tid % GNT, bar = 1 + grp;
   const int row_tiles = M / TR, total = row_tiles * A.Q;
-  // this block's tiles: t = blockIdx.x + n * gridDim.x, n = 0 .. nloc-1; group g takes n = g, g + G, ...: its j-th tile
-  // lives in the group's buffer j & 1, whose mbarrier completes phase j >> 1 when the tile has landed
+  // this block's tiles: t = blockIdx.x + n * gridDim.x, n = 0 .. nloc-1; group g takes n = g, g + G, ... (its j-th tile).
+  // buffer / mbarrier phase of local tile n:  SHARED: n % NB, (n / NB) & 1 ;  else: g*2 + (j & 1), (j >> 1) & 1
   const int nloc = ((int)blockIdx.x < total) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto issue = [&](int j) {   // one thread of the group: arm the buffer's mbarrier and start the box copies of its tile j
-    const int n = grp + j * kD2tGroups;
+  auto buf_of = [&](int n) { return SHARED ? n % NB : (n % G) * 2 + ((n / G) & 1); };
+  auto issue = [&](int n) {   // one thread: arm the buffer's mbarrier and start the box copies of local tile n
     if (n >= nloc) return;
     const int t = (int)blockIdx.x + n * (int)gridDim.x;
     const int q = t / row_tiles, i0 = (t % row_tiles) * TR;
-    const int b = grp * kD2tPB + (j & 1);
+    const int b = buf_of(n);
     mbar_expect_tx(full + b, (unsigned)Cfg::TILE_BYTES);
 #pragma unroll
     for (int x = 0; x < Cfg::NBOX; ++x)
@@ -118,24 +131,23 @@ __global__ void __launch_bounds__(kD2tGroups* kD2tGroupNT, 1) k_dim2t(Dim2Args A
   };
   if (tid == 0) {
 #pragma unroll
-    for (int b = 0; b < kD2tBufs; ++b) mbar_init(full + b, 1);
+    for (int b = 0; b < NB; ++b) mbar_init(full + b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
   __syncthreads();
-  if (lt == 0) {
-    issue(0);
-    issue(1);
+  if (tid == 0) {
+    for (int n = 0; n < NB; ++n) issue(n);   // the first NB tiles of the block
   }
 
-  for (int j = 0, n = grp; n < nloc; ++j, n += kD2tGroups) {
+  for (int n = grp; n < nloc; n += G) {
     const int t = (int)blockIdx.x + n * (int)gridDim.x;
     const int q = t / row_tiles, i0 = (t % row_tiles) * TR;
     const size_t qoff = (size_t)q * N * M;
     const size_t toff = (size_t)(q / A.Qg) * A.tab_stride;
-    const int b = grp * kD2tPB + (j & 1);
+    const int b = buf_of(n);
     float2* tile = ring + (size_t)b * TE;
-    mbar_wait(full + b, (unsigned)((j >> 1) & 1));   // the TMA bytes of this tile have landed
+    mbar_wait(full + b, (unsigned)((SHARED ? n / NB : n / (2 * G)) & 1));   // the TMA bytes of this tile have landed
 
     // forward stages 0 .. NS-2 in place
     dim2t_fwd_mid<LN, 0>(tile, A.twN, lt, bar);
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(kD2tGroups* kD2tGroupNT, 1) k_dim2t(Dim2Args A
     }
     fence_proxy_async();   // this group's generic-proxy accesses to the buffer are ordered before the async-proxy refill
     group_bar(bar);
-    if (lt == 0) issue(j + 2);
+    if (lt == 0) issue(n + NB);   // the tile that reuses this buffer (SHARED: another group's; else this group's next but one)
     if (!FWD_ONLY) {
       float2* dst = A.out + qoff + i0;
 #pragma unroll

@@ -119,13 +119,15 @@ class ImageDataFeeder:
                 if img.dtype != np.uint8:
                     raise TypeError("images must be uint8 (N0f8)")
                 view[k] = img.reshape(img.shape[0], img.shape[1], C)[h0:h0 + M, w0:w0 + N]
-            dst = torch.empty(B, C, N, M, dtype=torch.float32, device=self.device)
             with torch.cuda.stream(self._stream):
+                # allocated ON the copy stream: the caching allocator then never hands out a block that kernels still
+                # queued on the compute stream are reading (a block freed there is only reusable there until it drains)
+                dst = torch.empty(B, C, N, M, dtype=torch.float32, device=self.device)
                 devb.copy_(pin, non_blocking=True)
                 # row-major (H,W,C) crops: strides (c, i, j, b) = (1, C*N, C, M*N*C)
                 lib.batch_from_n0f8(M, N, C, B, self.device.index or 0, devb.data_ptr(), 1, C * N, C, M * N * C,
                                     dst.data_ptr(), self._stream.cuda_stream)
-            dst.record_stream(self._stream)
+            dst.record_stream(cur)             # consumed on the compute stream: its later free must wait for that stream
             out.append(dst)
         ev = torch.cuda.Event()
         ev.record(self._stream)

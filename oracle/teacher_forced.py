@@ -20,14 +20,14 @@ from . import admm_tv_oracle as O
 DT = torch.float64
 
 
-def _full_tables(M, N, h, rho):
+def _full_tables(M, N, h, rho, dt=DT):
     k1 = torch.arange(M, dtype=DT).reshape(-1, 1)
     k2 = torch.arange(N, dtype=DT).reshape(1, -1)
-    L = 4 * torch.sin(math.pi * k2 / N) ** 2 + 4 * torch.sin(math.pi * k1 / M) ** 2
+    L = (4 * torch.sin(math.pi * k2 / N) ** 2 + 4 * torch.sin(math.pi * k1 / M) ** 2).to(dt)
     if h is None or h.numel() == 0:
-        Sig = torch.ones(M, N, dtype=torch.complex128)
+        Sig = torch.ones(M, N, dtype=torch.complex128 if dt == DT else torch.complex64)
     else:
-        hh = torch.zeros(M, N, dtype=DT)
+        hh = torch.zeros(M, N, dtype=dt)
         hh[: h.shape[0], : h.shape[1]] = h[:, :, 0, 0]
         Sig = torch.fft.fftn(hh)
     C = 1.0 / (Sig.abs() ** 2 + rho * L)
@@ -42,7 +42,7 @@ def forward_states(y, lam, rho, h, iso, K):
 
 
 def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, torch.Tensor]], nograd_repeat=False,
-             nsq_states: Optional[List[torch.Tensor]] = None, fp32_gate: bool = False):
+             nsq_states: Optional[List[torch.Tensor]] = None, fp32_gate: bool = False, dtype=DT):
     """Exact adjoint given the states v_1..v_{K-1} (each (M,N,P,B) fp64 pair).  Returns
     dict(x=ybar, lam, rho, weight, gate_margin).
 
@@ -53,12 +53,21 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
         of BT (ops.jl:10), whose derivative coefficient tau <v,q> / n^3 is discontinuous there.
       * fp32_gate -- the comparisons |v| > tau (ST) and n > tau (BT) use tau rounded as the device rounds it
         (fp32 lambda / rho); the arithmetic keeps the fp64 tau.
-    gate_margin = the smallest relative distance of a decision variable from tau (how close a flip was)."""
+    gate_margin = the smallest relative distance of a decision variable from tau (how close a flip was).
+
+    dtype = torch.float32 evaluates the SAME recursion with fp32 arrays and complex64 FFTs (reductions included): its
+    distance from the fp64 result is the rounding floor of this computation in the device's working precision, which is
+    what the scalar gradients (cancelling sums) are compared against in tests/parity.py."""
     M, N, P, B = y.shape
+    dt = dtype
+    tau_g64 = (lam.float() / rho.float()).double() if fp32_gate else (lam / rho).double()
+    xbar, y, lam, rho = xbar.to(dt), y.to(dt), lam.to(dt), rho.to(dt)
+    h = None if h is None else h.to(dt)
+    v_states = [(a.to(dt), b.to(dt)) for a, b in v_states]
     tau = lam / rho
-    tau_g = (lam.float() / rho.float()).double() if fp32_gate else tau
+    tau_g = tau_g64.to(dt)
     margin = float("inf")
-    Sig, L, C = _full_tables(M, N, h, rho)
+    Sig, L, C = _full_tables(M, N, h, rho, dt)
     C4 = C.reshape(M, N, 1, 1)
     fft2 = lambda t: torch.fft.fftn(t, dim=(0, 1))
     ifft2 = lambda T: torch.fft.ifftn(T, dim=(0, 1)).real
@@ -67,7 +76,7 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
     def shrink(v1, v2, k):
         if iso:
             if nsq_states is not None and k >= 1:
-                n = torch.sqrt(nsq_states[k - 1].float()).double().reshape(M, N, 1, 1)   # the device's fp32 norm
+                n = torch.sqrt(nsq_states[k - 1].float()).to(dt).reshape(M, N, 1, 1)   # the device's fp32 norm
             else:
                 n = torch.sqrt(torch.sum(v1 * v1 + v2 * v2, dim=(2, 3), keepdim=True))
             s = torch.where(n > 0, torch.clamp(1 - tau / n, min=0), torch.zeros_like(n))
@@ -79,10 +88,10 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
     zero = torch.zeros_like(y)
     vs = [(zero, zero)] + list(v_states)          # vs[k] = v_k, v_0 = 0
     vb1, vb2 = zero, zero
-    G = torch.zeros(M, N, dtype=DT)
+    G = torch.zeros(M, N, dtype=dt)
     bbar = torch.zeros_like(y)
-    rhobar = torch.zeros((), dtype=DT)
-    taubar = torch.zeros((), dtype=DT)
+    rhobar = torch.zeros((), dtype=dt)
+    taubar = torch.zeros((), dtype=dt)
     for k in range(K, 0, -1):
         xk = (xbar if k == K else 0) + (O.Dt_roll(vb1, vb2) if k < K else 0)
         v1, v2 = vs[k - 1]
@@ -108,8 +117,8 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
             nv2 = vb2 - gb2 + s * q2 + coef * v2
             taubar = taubar - torch.where(act, ip / n, torch.zeros_like(n)).sum()
         else:
-            m1 = (v1.abs() > tau_g).to(DT)
-            m2 = (v2.abs() > tau_g).to(DT)
+            m1 = (v1.abs() > tau_g).to(dt)
+            m2 = (v2.abs() > tau_g).to(dt)
             margin = min(margin, float(((v1.abs() - tau_g).abs() / tau_g).min()), float(((v2.abs() - tau_g).abs() / tau_g).min()))
             nv1 = vb1 - gb1 + m1 * q1
             nv2 = vb2 - gb2 + m2 * q2
@@ -126,7 +135,7 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
     pd, pr = (kh - 1) // 2, (kw - 1) // 2
     out["x"] = O.H_forward(bbar, h)
     Fh = torch.fft.ifftn(2 * Sbar * Sig) * (M * N)
-    hb = torch.zeros(kh, kw, dtype=DT)
+    hb = torch.zeros(kh, kw, dtype=dt)
     for a in range(kh):
         for c in range(kw):
             hb[a, c] = Fh[a, c].real

@@ -58,7 +58,14 @@ def check_backward(be, y, h, lam, rho, iso, K, xbar, act="identity", bias=None, 
     norms = be.ckpt_norms(f) if (iso and K > 1) else None
     xbar_eff = xbar * act_grad(x_dev, act)
     tf = TF.backward(xbar_eff, y, lt, rt, hc, iso, K, states, nograd_repeat=bool(flags & 2), nsq_states=norms, fp32_gate=True)
-    res = {"gate_margin": tf["gate_margin"]}
+    # the same recursion evaluated in the device's working precision (fp32 arrays, complex64 FFTs, fp32 sums): its distance
+    # from the fp64 result is the rounding floor of the cancelling scalar sums (lambdabar, rhobar) and of hbar
+    tf32 = TF.backward(xbar_eff, y, lt, rt, hc, iso, K, states, nograd_repeat=bool(flags & 2), nsq_states=norms, fp32_gate=True,
+                       dtype=torch.float32)
+    relf = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-3)
+    res = {"gate_margin": tf["gate_margin"], "lam_floor32": relf(tf32["lam"], tf["lam"]), "rho_floor32": relf(tf32["rho"], tf["rho"])}
+    if h is not None:
+        res["hbar_floor32"] = rel_l2(tf32["weight"].double(), tf["weight"])
     res["ybar"] = rel_l2(T(g["ybar"]), tf["x"])
     assert res["ybar"] < tol, ("ybar", res["ybar"])
     if K > 1:

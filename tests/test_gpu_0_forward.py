@@ -71,6 +71,17 @@ def test_every_fft_length_both_dims(L):
         assert rel_l2(x, xo) < TOL, (M, N)
 
 
+def test_tma_pipelined_dim2_pass_full_ring(monkeypatch=None):
+    """N = 2048 runs the TMA-pipelined dim-2 kernel (kernels_tma.cuh: 2-D box copies, mbarrier ring of 3 buffers, two
+    compute groups per persistent block).  2 x 2048 x 2048: 512 tiles over <= 148 blocks, so every buffer of a ring is
+    re-armed and reused; plus a short plane (fewer tiles than SMs) and an odd number of plane pairs."""
+    for (M, N, P, B, K) in ((2048, 2048, 1, 2, 3), (32, 2048, 1, 1, 4), (128, 2048, 3, 1, 3)):
+        y, h, _ = make_case(M, N, P, B, 5, 5, 77 + M)
+        x = run_gpu(y, h, 0.02, 0.1, False, K)
+        xo = oracle(y, h, 0.02, 0.1, False, K, fast=True)
+        assert rel_l2(x, xo) < TOL, (M, N)
+
+
 def test_golden_forward_layer():
     """Committed fixtures (tests/golden/make_golden.py): full layer call incl. bias and activation."""
     d0 = dev()

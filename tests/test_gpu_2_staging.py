@@ -59,3 +59,29 @@ def test_resident_dataset_gather_matches_streaming_feeder():
     torch.cuda.synchronize()
     assert torch.equal(ax, bx) and torch.equal(ay, by)
     assert b.h2d_bytes(3) == 48 and a.h2d_bytes(3) == 2 * 3 * 128 * 96 * 3
+
+
+def test_feeder_back_to_back_without_synchronize():
+    """Streaming feeder, several batches in flight with work queued on the compute stream and NO host synchronisation
+    in between: every batch must still hold its own crops when it is consumed (the copy stream must not recycle a block
+    that queued kernels are reading)."""
+    xs, ys = _dataset(12, 140, 140, 3, 21)
+    f = ImageDataFeeder(xs, ys, (128, 128), (128, 128), "cuda:0", seed=4)
+    d = torch.device("cuda:0")
+    sums, want = [], []
+    burn = torch.rand(2048, 2048, device=d)
+    for step in range(8):
+        idxs = [(step * 3 + k) % 12 for k in range(4)]
+        origins = [(step % 7, (2 * step) % 9)] * 4
+        bx, by = f.getindex(idxs, origins)
+        for _ in range(6):                      # keep the compute stream busy so the next getindex overlaps it
+            burn = (burn @ burn).clamp_(-1, 1)
+        sums.append((bx.double().sum() + 2 * by.double().sum()).reshape(1))      # consumed late, on the compute stream
+        del bx, by                              # frees the blocks while their reads are still queued
+        w = 0.0
+        for data, m in ((xs, 1.0), (ys, 2.0)):
+            for i, (h, ww) in zip(idxs, origins):
+                w += m * float((data[i][h:h + 128, ww:ww + 128].astype(np.float32) / np.float32(255)).astype(np.float64).sum())
+        want.append(w)
+    got = torch.cat(sums).cpu().numpy()
+    assert np.allclose(got, np.array(want), rtol=1e-9)

@@ -227,3 +227,30 @@ def test_nonleaf_parameters_are_not_mutated_by_the_clamp():
     leaf = torch.tensor([1e-4], device=d, requires_grad=True)
     A.admm_layer_call(y, leaf, rho, None, None, 4, False, "identity", 1e-2, False, clamp=True)
     assert float(leaf) == pytest.approx(1e-2)           # persisted (deconv_admm.jl:216)
+
+
+def test_scalar_gradient_error_sits_at_the_fp32_rounding_floor(be):
+    """lambdabar / rhobar are cancelling sums (direct term + spectral term - taubar lambda / rho^2, each ~100x the result),
+    so their relative error is set by the fp32 rounding of the state arrays and FFTs, not by the reductions (fp64 on the
+    device).  Evidence for the scalar tolerance used in this file: the SAME adjoint recursion evaluated on the CPU in fp32
+    (oracle/teacher_forced.py, dtype=float32) is compared with its fp64 twin on the same replayed device states --
+    `*_floor32` -- next to the device's error.  Asserted: the device is within a small factor of that floor in aggregate,
+    the floor itself is above the 1e-5 that images and hbar meet (so 1e-5 is not attainable for rhobar in fp32), and every
+    case stays below the hand-set cap 2e-4 (about 3x the largest floor)."""
+    rows = []
+    for (M, N, P, B, kh, kw, K, iso) in [(64, 64, 3, 2, 7, 7, 10, False), (128, 128, 3, 2, 15, 15, 10, False), (256, 256, 1, 2, 15, 15, 10, False),
+                                         (512, 128, 1, 2, 9, 9, 6, False), (128, 256, 3, 2, 9, 9, 8, False), (64, 64, 3, 2, 7, 7, 10, True),
+                                         (256, 128, 3, 2, 9, 9, 8, True), (128, 128, 3, 4, 5, 5, 12, True)]:
+        y, h, g = make_case(M, N, P, B, kh, kw, 5000 + M + K)
+        xbar = 2.0 * (y - g) / y.numel() * 1e3
+        r = check_backward(be, y, h, 0.0041, 0.021, iso, K, xbar, flags=1, tol=1e-5, tol_scalar=2e-4)
+        rows.append(r)
+        print(f"{M}x{N}x{P}x{B} K={K} iso={iso}: rho {r['rho']:.2e} (fp32 floor {r['rho_floor32']:.2e})  lam {r['lam']:.2e} (floor {r['lam_floor32']:.2e})"
+              f"  hbar {r['hbar']:.2e} (floor {r['hbar_floor32']:.2e})")
+    med = lambda k: float(np.median([r[k] for r in rows]))
+    print("medians:", {k: med(k) for k in ("rho", "rho_floor32", "lam", "lam_floor32", "hbar", "hbar_floor32")})
+    # measured on the B200 (profiles/r2_scalar_gradient_floor.txt): medians rho 1.7e-5 vs 7.6e-6, lam 1.8e-7 vs 1.3e-7, hbar 2.8e-6 vs 9.4e-7
+    assert med("rho") <= 4.0 * med("rho_floor32") and med("lam") <= 4.0 * med("lam_floor32") and med("hbar") <= 4.0 * med("hbar_floor32")
+    assert max(r["hbar"] for r in rows) < 1e-5
+    assert max(r["rho_floor32"] for r in rows) > 1e-5          # the fp32 evaluation of the recursion itself misses 1e-5
+    assert max(r["rho"] for r in rows) < 2e-4 and max(r["lam"] for r in rows) < 2e-4
