@@ -109,6 +109,8 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+        if self.proc is not None:
+            self.first = self.proc.stdout.readline()      # block until nvidia-smi is up and has delivered its first sample
         return self
 
     def stop(self):
@@ -122,6 +124,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
+        out = getattr(self, "first", "") + out
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
@@ -315,13 +318,22 @@ def max_over_ranks(c, vals):
     return [float(v) for v in t]
 
 
-def timed(c, fn, steps, warmup, clocks=True):
+def timed(c, fn, steps, warmup, clocks=True, min_ms=0.0):
     """W warm-up calls, then `steps` calls bracketed by barrier + synchronize, CUDA events on the launching stream;
-    returns (ms per step as the max over ranks, clock record of rank 0)."""
+    returns (ms per step as the max over ranks, clock record of rank 0, steps timed).  min_ms > 0 raises the number of
+    timed steps so that the timed region lasts at least that long (enough nvidia-smi clock samples for short workloads)."""
     import torch
-    for _ in range(max(warmup, 3)):
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nw = max(warmup, 3)
+    fn()
+    w0.record()
+    for _ in range(nw - 1):
         fn()
+    w1.record()
     barrier(c)
+    if min_ms > 0:
+        est = max(w0.elapsed_time(w1) / max(nw - 1, 1), 1e-3)
+        steps = int(max_over_ranks(c, [max(steps, math.ceil(min_ms / est))])[0])
     sampler = ClockSampler(c.local, enabled=clocks and c.rank == 0).start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(c)
@@ -332,7 +344,7 @@ def timed(c, fn, steps, warmup, clocks=True):
     barrier(c)
     ms = e0.elapsed_time(e1) / steps
     clk = sampler.stop()
-    return max_over_ranks(c, [ms])[0], clk
+    return max_over_ranks(c, [ms])[0], clk, steps
 
 
 class TrainStep:
@@ -425,7 +437,7 @@ def e2e_train(c, w, B, steps, warmup, ts: TrainStep):
     return out
 
 
-def run_fwd(c, w, name, steps, warmup, e2e=True):
+def run_fwd(c, w, name, steps, warmup, e2e=True, min_ms=0.0):
     """Forward-only workloads (inference), plain or grouped."""
     import numpy as np
     import torch
@@ -462,7 +474,7 @@ def run_fwd(c, w, name, steps, warmup, e2e=True):
             with torch.no_grad():
                 return ops.tvd_fft(y, lam, rho, h, iso, K)
 
-    ms, clk = timed(c, step, steps, warmup)
+    ms, clk, steps = timed(c, step, steps, warmup, min_ms=min_ms)
     pk, _ = peaks()
     r = {"config": config_of(w, name), "n_gpus": c.world, "scaling": "weak", "steps": steps, "ms_per_step": ms,
          "value": px * K * c.world / (ms * 1e-3) / 1e6, "unit": UNIT,
@@ -495,13 +507,13 @@ def run_fwd(c, w, name, steps, warmup, e2e=True):
     return r
 
 
-def run_train(c, w, name, steps, warmup, full):
+def run_train(c, w, name, steps, warmup, full, min_ms=0.0):
     """fwd+bwd workloads.  full: roofline + e2e + launch count (the headline); else a short `others` entry."""
     import torch
 
     B = w["B"] // c.world if w.get("strong") else w["B"]
     ts = TrainStep(c, w, B, 1001 + c.rank)
-    ms, clk = timed(c, ts, steps, warmup)
+    ms, clk, steps = timed(c, ts, steps, warmup, min_ms=min_ms)
     pk, pk_src = peaks()
     K = w["iters"]
     px_all = ts.px * c.world
@@ -560,12 +572,11 @@ def run_native(args, w, name):
     if not args.no_others and name == "cfg2_train":
         for on in OTHERS:
             ow = WORKLOADS[on]
-            st = 3 if ow["iters"] * ow["M"] * ow["N"] * ow["B"] * ow["P"] > 2e9 else 10
-            try:
+            try:      # >= 3 steps and >= 0.6 s of timed region each (clock samples every 50 ms)
                 if ow["mode"] == "fwd+bwd":
-                    others[on], _ = run_train(c, ow, on, st, 3, False)
+                    others[on], _ = run_train(c, ow, on, 3, 3, False, min_ms=600.0)
                 else:
-                    others[on] = run_fwd(c, ow, on, st, 3, e2e=(on == "cfg2"))
+                    others[on] = run_fwd(c, ow, on, 3, 3, e2e=(on == "cfg2"), min_ms=600.0)
             except Exception as e:   # an auxiliary shape must never take the headline down
                 others[on] = {"error": repr(e)}
             torch.cuda.empty_cache()
