@@ -41,6 +41,8 @@ static Geom geom(const admmtv_desc* d) {
   g.K = d->iters; g.kh = d->kh; g.kw = d->kw; g.nh = d->kh * d->kw;
   g.G = d->groups > 1 ? d->groups : 1;
   g.iso = d->iso ? 1 : 0;
+  g.PS = (d->flags & ADMMTV_FLAG_PER_ITER_PARAMS) ? d->iters : 1;
+  g.AS = acc_stride(g.PS);
   g.spatial = (d->kh > 0 && !(d->flags & ADMMTV_FLAG_NOGRAD_REPEAT)) ? 1 : 0;
   g.Bg = d->B / g.G;
   g.Sg = d->P * g.Bg;
@@ -85,9 +87,9 @@ static FwdWs carve_fwd(const Geom& g, void* ws) {
   w.twM = c.take<float2>(g.M);
   w.twN = c.take<float2>(g.N);
   w.T = c.take<double2>((size_t)g.M * (g.kw > 0 ? g.kw : 1) * g.G);
-  w.ctab = c.take<float>(g.plane * g.G);
+  w.ctab = c.take<float>(g.plane * g.G * g.PS);
   w.ktab = c.take<float2>(g.plane * g.G);
-  w.mask = c.take<float>((size_t)(g.nh + 2) * g.G);
+  w.mask = c.take<float>((size_t)(g.nh + 2 * g.PS) * g.G);
   w.bpk = c.take<float2>(g.pk);
   w.specA = c.take<float2>(g.pk);
   w.specB = c.take<float2>(g.pk);
@@ -117,13 +119,13 @@ struct Ckpt {
 static Ckpt carve_ckpt(const Geom& g, void* p) {
   Carver c(p);
   Ckpt k;
-  k.mask = c.take<float>((size_t)(g.nh + 2) * g.G);
+  k.mask = c.take<float>((size_t)(g.nh + 2 * g.PS) * g.G);
   k.vck = c.take<float2>((size_t)(g.K > 1 ? g.K - 1 : 0) * 2 * g.pk);
   k.zck = c.take<float2>((size_t)g.K * g.pk);
   k.nck = c.take<float>(g.iso ? (size_t)(g.K > 1 ? g.K - 1 : 0) * g.plane * g.G : 0);
   k.twM = c.take<float2>(g.M);
   k.twN = c.take<float2>(g.N);
-  k.ctab = c.take<float>(g.plane * g.G);
+  k.ctab = c.take<float>(g.plane * g.G * g.PS);
   k.ktab = c.take<float2>(g.kh > 0 ? g.plane * g.G : 0);
   k.sig = c.take<float2>(g.plane * g.G);
   k.yck = c.take<float2>(g.spatial ? g.pk : 0);
@@ -235,7 +237,7 @@ static int run_setup(const Geom& g, const float* h, const float* rho, float2* tw
   }
   {
     const size_t n = g.plane;
-    ADMMTV_LAUNCH(k_setup_tables, dim3((unsigned)((n + 127) / 128), (unsigned)g.G), dim3(128), 0, st, (const double2*)T, g.kh,
+    ADMMTV_LAUNCH(k_setup_tables, dim3((unsigned)((n + 127) / 128), (unsigned)g.G, (unsigned)g.PS), dim3(128), 0, st, (const double2*)T, g.kh,
                   g.kw, g.M, g.N, rho, ctab, g.kh > 0 ? ktab : (float2*)nullptr, sig, g.planned);
     ADMMTV_CHECK_LAUNCH();
   }
@@ -277,7 +279,7 @@ int admmtv_check(const admmtv_desc* d) {
   if (d->activation < 0 || d->activation > 3) return ADMMTV_ERR_ENUM;
   if (d->has_bias != 0 && d->has_bias != 1) return ADMMTV_ERR_ENUM;
   if (d->flags & ~(ADMMTV_FLAG_NO_CLAMP | ADMMTV_FLAG_NOGRAD_REPEAT | ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT |
-                   ADMMTV_FLAG_ISO_PRECOMPUTE | ADMMTV_FLAG_ISO_INLINE))
+                   ADMMTV_FLAG_ISO_PRECOMPUTE | ADMMTV_FLAG_ISO_INLINE | ADMMTV_FLAG_PER_ITER_PARAMS))
     return ADMMTV_ERR_ENUM;
   if (d->groups < 0 || (d->groups > 1 && d->B % d->groups != 0)) return ADMMTV_ERR_SHAPE;
   if (d->groups <= 1 && (d->flags & (ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT))) return ADMMTV_ERR_ENUM;
@@ -356,7 +358,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
 
   tm_mark(tm, st, 2);
   // deconv_admm.jl:216-219 (persisted clamp) + gradient masks for the pullback
-  ADMMTV_LAUNCH(k_clamp_params, dim3((unsigned)g.G), dim3(128), 0, st, lambda, rho, h, g.nh, d->creg,
+  ADMMTV_LAUNCH(k_clamp_params, dim3((unsigned)g.G), dim3(128), 0, st, lambda, rho, h, g.nh, g.PS, d->creg,
                 (d->flags & ADMMTV_FLAG_NO_CLAMP) ? 0 : 1, ckpt ? ck.mask : w.mask);
   ADMMTV_CHECK_LAUNCH();
   // training: twiddles and tables go to the checkpoint, where the backward finds them (no second setup)
@@ -401,8 +403,9 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
   // the unrolled iterations (ops.jl:166-174)
   for (int k = 1; k <= g.K; ++k) {
     Dim2Args a{};
-    a.in = cur; a.out = oth; a.ctab = ctab; a.twN = twN; a.M = g.M;
-    a.Qg = g.Qg; a.tab_stride = g.G > 1 ? g.plane : 0;
+    const int pe = g.PS == 1 ? 0 : k - 1;   // parameter entry of iteration k
+    a.in = cur; a.out = oth; a.ctab = ctab + (size_t)pe * g.plane; a.twN = twN; a.M = g.M;
+    a.Qg = g.Qg; a.tab_stride = g.G > 1 ? g.plane * g.PS : 0;
     if (ckpt) a.zsave = ck.zck + (size_t)(k - 1) * g.pk;
     tm_mark(tm, st, 0);
     if ((rc = run_dim2(g, ckpt ? D2_C_SAVE : D2_C, a, st))) return rc;
@@ -410,6 +413,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       Dim1FwdArgs f{};
       f.spec_in = oth; f.spec_out = cur; f.bpk = w.bpk; f.twM = twM;
       f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
+      f.PS = g.PS; f.ic = pe; f.ip = (g.PS == 1 || k < 2) ? 0 : k - 2; f.in = g.PS == 1 ? 0 : k;   // k < K here: entry k exists
       if (ckpt) {
         f.vprev = k > 1 ? ck.vck + (size_t)(k - 2) * 2 * g.pk : nullptr;
         f.vnew = ck.vck + (size_t)(k - 1) * 2 * g.pk;
@@ -438,6 +442,7 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       tm_mark(tm, st, 1);
       Dim1FwdArgs fa{};
       fa.spec_in = oth; fa.twM = twM; fa.lambda = lambda; fa.rho = rho; fa.N = g.N; fa.Qg = g.Qg;
+      fa.PS = g.PS; fa.ic = pe; fa.ip = (g.PS == 1 || k < 2) ? 0 : k - 2; fa.in = g.PS == 1 ? 0 : k;
       fa.vprev = v_in; fa.vnew = v_out; fa.nsq = s_prev; fa.nsq_out = w.npart;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_a(g, k > 1, fa, st); })
       if (rc) return rc;
@@ -445,16 +450,17 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
       const dim3 sgrid((unsigned)((g.plane + 255) / 256), (unsigned)g.G);
       const bool xrank = hk && hk->allreduce_sum;   // exact global-batch norm across ranks (admmtv_forward_ex)
       ADMMTV_LAUNCH(k_iso_scale, sgrid, dim3(256), 0, st, (const float*)w.npart, g.Qg, nsq_new, (const float*)lambda,
-                    (const float*)rho, xrank ? (float*)nullptr : s_new, (int)g.plane);
+                    (const float*)rho, g.PS, pe, xrank ? (float*)nullptr : s_new, (int)g.plane);
       ADMMTV_CHECK_LAUNCH();
       if (xrank) {
         if ((rc = hk->allreduce_sum(nsq_new, g.plane * g.G, stream, hk->user))) return rc;
         ADMMTV_LAUNCH(k_iso_scale, sgrid, dim3(256), 0, st, (const float*)nullptr, g.Qg, nsq_new, (const float*)lambda,
-                      (const float*)rho, s_new, (int)g.plane);
+                      (const float*)rho, g.PS, pe, s_new, (int)g.plane);
         ADMMTV_CHECK_LAUNCH();
       }
       Dim1FwdArgs f{};
       f.spec_out = cur; f.bpk = w.bpk; f.twM = twM; f.lambda = lambda; f.rho = rho; f.N = g.N; f.Qg = g.Qg;
+      f.PS = g.PS; f.ic = pe; f.ip = fa.ip; f.in = fa.in;
       f.vprev = v_out; f.nsq = s_new;
       ADMMTV_SWITCH_LOG2_RC(g.LM, LM, rc, { rc = Dim1Launch<LM>::fwd_iso_b(g, f, st); })
       if (rc) return rc;

@@ -34,11 +34,22 @@ struct Geom {
   int planned;   // bit 0: dim-1 spectra in the plan's digit-reversed order (else natural); bit 1: same for dim 2
   int G, Bg, Sg, Qg;  // groups, images / planes / pairs per group (S = G*Sg planes, Q = G*Qg pairs)
   int iso;            // isotropic TV: the workspaces carry the per-pair partial sums of the per-pixel reductions
+  int PS;             // lambda / rho values per group: 1 (the reference: one value for all iterations) or K (per-iteration
+                      // learned parameters, ADMMTV_FLAG_PER_ITER_PARAMS); iteration k (1-based) uses entry PS == 1 ? 0 : k-1
+  int AS;             // doubles per group in the scalar accumulator block `acc` (see acc_* below)
   int spatial;        // the backward differentiates the spatial H^T y path (kh > 0 and no NOGRAD_REPEAT): F y is checkpointed
   PlaneMap pm;
   size_t plane;  // N*M
   size_t pk;     // Q*N*M  (pair-packed complex elements)
 };
+
+// Scalar accumulator block of the backward, per group AS = 4 + 3 PS doubles:
+//   [2] biasbar ; for parameter entry i: [4+3i] rhobar direct term, [5+3i] taubar, [6+3i] rhobar spectral term
+ADMMTV_HD inline int acc_stride(int PS) { return 4 + 3 * PS; }
+ADMMTV_HD inline int acc_bias() { return 2; }
+ADMMTV_HD inline int acc_rho(int i) { return 4 + 3 * i; }
+ADMMTV_HD inline int acc_tau(int i) { return 5 + 3 * i; }
+ADMMTV_HD inline int acc_rhos(int i) { return 6 + 3 * i; }
 
 struct PackArgs {
   const float* src;    // MODE 0/1: (M,N,S) planes
@@ -47,7 +58,8 @@ struct PackArgs {
   const float* xout;   // MODE 1
   float2* spec;        // [Q][N][M]
   const float2* twM;
-  double* bias_acc;    // MODE 1, may be null
+  double* bias_acc;    // MODE 1, may be null: biasbar slot of group 0 (groups are acc_stride apart)
+  int acc_stride;      // doubles between the groups' accumulator blocks
   PlaneMap pm;
   int N, S, act;
 };
@@ -72,8 +84,10 @@ struct Dim1FwdArgs {
   const float* nsq;     // isotropic: per-pixel shrink scale s [G][N][M] (pass B: s_k ; pass A: s_{k-1}), k_iso_scale
   float* nsq_out;       // isotropic pass A: [Q][N][M], pair q's share of |v_k|^2 per pixel (k_iso_scale adds them in order)
   const float2* twM;
-  const float* lambda;  // [G]
-  const float* rho;     // [G]
+  const float* lambda;  // [G][PS]
+  const float* rho;     // [G][PS]
+  int PS;               // parameter entries per group
+  int ip, ic, in;       // entries of the previous iteration (tau of v_{k-1}), this one (tau of v_k) and the next (rho of r_{k+1})
   int N;
   int Qg;               // pairs per group: group of pair q = q / Qg
 };
@@ -103,9 +117,11 @@ struct Dim1BwdArgs {
   float2* bbar;            // [Q][N][M] running sum of rbar_k
   float* ybar;             // last step, empty PSF: (M,N,S) planes
   const float2* twM;
-  const float* lambda;
+  const float* lambda;     // [G][PS]
   const float* rho;
-  double* acc;             // [0] rhobar (direct term), [1] taubar
+  int PS, ir, it;          // parameter entries per group; entry of rho_k (this step's x-update) and of tau_{k-1} (mask of v_{k-1})
+  int AS;                  // accumulator doubles per group
+  double* acc;             // scalar accumulator blocks (acc_* above)
   const float2* sc;        // isotropic pass B: per-pixel (s, tau ip / n^3) [G][N][M] (k_iso_coef)
   float* ip_out;           // isotropic pass A: [Q][N][M], pair q's share of <q, v_{k-1}> per pixel (k_iso_coef adds them in order)
   PlaneMap pm;

@@ -280,9 +280,9 @@ __global__ void __launch_bounds__(GK_NT) gk_pack(PackArgs A, int M, int Q, int m
     if (last >= per_group * A.pm.G) last = per_group * A.pm.G - 1;
     if (first / per_group == last / per_group) {
       const double tot = block_sum(bsum);
-      if (threadIdx.x == 0) atomicAdd(A.bias_acc + 8 * (int)(first / per_group), tot);
+      if (threadIdx.x == 0) atomicAdd(A.bias_acc + (size_t)A.acc_stride * (int)(first / per_group), tot);
     } else if (bsum != 0.0) {
-      atomicAdd(A.bias_acc + 8 * grp, bsum);
+      atomicAdd(A.bias_acc + (size_t)A.acc_stride * grp, bsum);
     }
   }
 }
@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_fwd(Dim1FwdArgs A, const float
   Pix p;
   if (!gk_pix(idx, M, A.N, Q, p)) return;
   const int grp = p.q / A.Qg;
-  const float rho = A.rho[grp], tau = A.lambda[grp] / rho;
+  const float rho = A.rho[grp * A.PS + A.in], tau = A.lambda[grp * A.PS + A.ic] / A.rho[grp * A.PS + A.ic];
+  const float tau_p = A.lambda[grp * A.PS + A.ip] / A.rho[grp * A.PS + A.ip];
   const size_t q1 = ((size_t)p.q * 2 + 0) * p.plane, q2 = ((size_t)p.q * 2 + 1) * p.plane, qx = (size_t)p.q * p.plane;
   const size_t o = p.o, oj = (size_t)p.jp1 * M + p.i, oi = (size_t)p.j * M + p.ip1;   // (i,j), (i,j+1), (i+1,j)
   const float* ng = mode != 0 ? A.nsq + (size_t)grp * p.plane : nullptr;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_fwd(Dim1FwdArgs A, const float
   auto U = [&](size_t base, size_t off) {
     if (!has_vprev) return make_float2(0.f, 0.f);
     const float2 vp = A.vprev[base + off];
-    return mode == 2 ? shrink_iso(vp, SC(ng[off])).u : shrink_aniso(vp, tau).u;
+    return mode == 2 ? shrink_iso(vp, SC(ng[off])).u : shrink_aniso(vp, tau_p).u;
   };
   const float2 v1 = cadd(csub(x0, X[qx + (size_t)p.jm1 * M + p.i]), U(q1, o));   // channel 1: dim-2 difference
   const float2 v2 = cadd(csub(x0, X[qx + (size_t)p.j * M + p.im1]), U(q2, o));   // channel 2: dim-1 difference
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_bwd(Dim1BwdArgs A, const float
   int grp = 0;
   if (live) {
     grp = p.q / A.pm.Qg;
-    const float rho = A.rho[grp], tau = A.lambda[grp] / rho;
+    const float rho = A.rho[grp * A.PS + A.ir], tau = A.lambda[grp * A.PS + A.it] / A.rho[grp * A.PS + A.it];
     const size_t q1 = ((size_t)p.q * 2 + 0) * p.plane, q2 = ((size_t)p.q * 2 + 1) * p.plane, qx = (size_t)p.q * p.plane;
     const size_t o = p.o, oj = (size_t)p.jp1 * M + p.i, oi = (size_t)p.j * M + p.ip1;
     const float2 zero2 = make_float2(0.f, 0.f);
@@ -413,12 +414,12 @@ __global__ void __launch_bounds__(GK_NT) gk_sweep_bwd(Dim1BwdArgs A, const float
   if (first / per_group == last / per_group) {
     const double rs = block_sum(racc), ts = block_sum(tacc);
     if (threadIdx.x == 0) {
-      atomicAdd(A.acc + 8 * (int)(first / per_group) + 0, rs);
-      atomicAdd(A.acc + 8 * (int)(first / per_group) + 1, ts);
+      atomicAdd(A.acc + (size_t)A.AS * (int)(first / per_group) + acc_rho(A.ir), rs);
+      atomicAdd(A.acc + (size_t)A.AS * (int)(first / per_group) + acc_tau(A.it), ts);
     }
   } else if (live) {
-    if (racc != 0.0) atomicAdd(A.acc + 8 * grp + 0, racc);
-    if (tacc != 0.0) atomicAdd(A.acc + 8 * grp + 1, tacc);
+    if (racc != 0.0) atomicAdd(A.acc + (size_t)A.AS * grp + acc_rho(A.ir), racc);
+    if (tacc != 0.0) atomicAdd(A.acc + (size_t)A.AS * grp + acc_tau(A.it), tacc);
   }
 }
 

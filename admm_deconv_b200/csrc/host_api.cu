@@ -52,7 +52,7 @@ struct Slot {
 
 struct admmtv_host_session {
   admmtv_desc d;
-  int training, G, nh, ngrad;
+  int training, G, nh, ngrad, PS;
   size_t nimg;                 // floats per (M,N,P,B) array
   size_t out_img;              // floats of x_out (== nimg unless channel-concat/shared input)
   size_t in_img;               // floats of y
@@ -74,12 +74,15 @@ struct Layout {
   size_t y[2], t[2], x[2], h, lam, rho, bias, xbar, ybar, packed, loss, ws_fwd, ws_bwd, ckpt, total;
 };
 
+inline int param_entries(const admmtv_desc* d) { return (d->flags & ADMMTV_FLAG_PER_ITER_PARAMS) ? d->iters : 1; }
+
 int plan(const admmtv_desc* d, int training, Layout& L, size_t& in_img, size_t& out_img, int& G, int& nh, int& ngrad) {
   int rc = admmtv_check(d);
   if (rc) return rc;
   G = d->groups > 1 ? d->groups : 1;
   nh = d->kh * d->kw;
-  ngrad = nh * G + 2 * G + (d->has_bias ? G : 0);
+  const int PS = param_entries(d);
+  ngrad = nh * G + 2 * G * PS + (d->has_bias ? G : 0);
   const size_t plane = (size_t)d->M * d->N;
   out_img = plane * d->P * d->B;
   in_img = (d->flags & ADMMTV_FLAG_SHARED_INPUT) ? plane * d->P * (d->B / G) : out_img;
@@ -93,8 +96,8 @@ int plan(const admmtv_desc* d, int training, Layout& L, size_t& in_img, size_t& 
     L.x[s] = take(out_img * 4);
   }
   L.h = take((size_t)(nh > 0 ? nh : 1) * G * 4);
-  L.lam = take((size_t)G * 4);
-  L.rho = take((size_t)G * 4);
+  L.lam = take((size_t)G * PS * 4);
+  L.rho = take((size_t)G * PS * 4);
   L.bias = take((size_t)G * 4);
   L.xbar = take(training ? out_img * 4 : 0);
   L.ybar = take(training ? in_img * 4 : 0);
@@ -128,8 +131,8 @@ struct DevGuard {
 // parameters host -> device on the compute stream (tiny), before the kernels that read them
 int upload_params(admmtv_host_session* s, const float* h, const float* lambda, const float* rho, const float* bias) {
   if (s->nh > 0) HCHECK(cudaMemcpyAsync(s->h, h, (size_t)s->nh * s->G * 4, cudaMemcpyHostToDevice, s->compute));
-  HCHECK(cudaMemcpyAsync(s->lambda, lambda, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->compute));
-  HCHECK(cudaMemcpyAsync(s->rho, rho, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->compute));
+  HCHECK(cudaMemcpyAsync(s->lambda, lambda, (size_t)s->G * s->PS * 4, cudaMemcpyHostToDevice, s->compute));
+  HCHECK(cudaMemcpyAsync(s->rho, rho, (size_t)s->G * s->PS * 4, cudaMemcpyHostToDevice, s->compute));
   if (s->d.has_bias) HCHECK(cudaMemcpyAsync(s->bias, bias, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->compute));
   return 0;
 }
@@ -139,8 +142,8 @@ int upload_params(admmtv_host_session* s, const float* h, const float* lambda, c
 int download_params(admmtv_host_session* s, float* h, float* lambda, float* rho) {
   if (s->d.flags & ADMMTV_FLAG_NO_CLAMP) return 0;
   if (s->nh > 0) HCHECK(cudaMemcpyAsync(h, s->h, (size_t)s->nh * s->G * 4, cudaMemcpyDeviceToHost, s->compute));
-  HCHECK(cudaMemcpyAsync(lambda, s->lambda, (size_t)s->G * 4, cudaMemcpyDeviceToHost, s->compute));
-  HCHECK(cudaMemcpyAsync(rho, s->rho, (size_t)s->G * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(lambda, s->lambda, (size_t)s->G * s->PS * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(rho, s->rho, (size_t)s->G * s->PS * 4, cudaMemcpyDeviceToHost, s->compute));
   return 0;
 }
 
@@ -151,7 +154,7 @@ extern "C" {
 int admmtv_host_grad_floats(const admmtv_desc* d) {
   if (admmtv_check(d)) return 0;
   const int G = d->groups > 1 ? d->groups : 1;
-  return d->kh * d->kw * G + 2 * G + (d->has_bias ? G : 0);
+  return d->kh * d->kw * G + 2 * G * param_entries(d) + (d->has_bias ? G : 0);
 }
 
 int admmtv_host_session_bytes(const admmtv_desc* d, int training, size_t* device_bytes) {
@@ -182,7 +185,7 @@ int admmtv_host_session_create(const admmtv_desc* d, int training, void* device_
   memset(s, 0, sizeof(*s));
   s->d = *d;
   s->training = training ? 1 : 0;
-  s->G = G; s->nh = nh; s->ngrad = ng; s->in_img = in_img; s->out_img = out_img;
+  s->G = G; s->nh = nh; s->ngrad = ng; s->in_img = in_img; s->out_img = out_img; s->PS = param_entries(d);
   s->own_arena = device_arena == nullptr;
   s->arena = reinterpret_cast<unsigned char*>(device_arena);
   cudaError_t e = cudaSuccess;
@@ -333,7 +336,7 @@ int admmtv_mse_train_step(const admmtv_desc* d, const float* y, const float* tar
   DevGuard guard(d->device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int G = d->groups > 1 ? d->groups : 1, nh = d->kh * d->kw;
+  const int G = d->groups > 1 ? d->groups : 1, nh = d->kh * d->kw, PS = param_entries(d);
   if ((rc = admmtv_forward(d, y, h, lambda, rho, bias, x_out, ws_fwd, ckpt, stream))) return rc;
   HCHECK(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
   {
@@ -345,13 +348,13 @@ int admmtv_mse_train_step(const admmtv_desc* d, const float* y, const float* tar
   }
   float* hbar = grads_packed;
   float* lbar = grads_packed + (size_t)nh * G;
-  float* rbar = lbar + G;
-  float* bbar = d->has_bias ? rbar + G : nullptr;
+  float* rbar = lbar + (size_t)G * PS;
+  float* bbar = d->has_bias ? rbar + (size_t)G * PS : nullptr;
   if ((rc = admmtv_backward(d, xbar, x_out, y, h, lambda, rho, ckpt, ybar, nh > 0 ? hbar : nullptr, lbar, rbar, bbar, ws_bwd,
                             stream)))
     return rc;
   if (hooks && hooks->allreduce_sum) {   // the data-parallel gradient all-reduce, stream-ordered
-    const size_t ng = (size_t)nh * G + 2 * G + (d->has_bias ? G : 0);
+    const size_t ng = (size_t)nh * G + 2 * (size_t)G * PS + (d->has_bias ? G : 0);
     if ((rc = hooks->allreduce_sum(grads_packed, ng, stream, hooks->user))) return rc;
   }
   return ADMMTV_OK;

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
   }
   if (MODE == 1 && A.bias_acc) {
     const double tot = block_sum(bsum);
-    if (tid == 0) atomicAdd(A.bias_acc + 8 * (q / A.pm.Qg), tot);  // one accumulator block of 8 doubles per group
+    if (tid == 0) atomicAdd(A.bias_acc + (size_t)A.acc_stride * (q / A.pm.Qg), tot);  // biasbar slot of this pair's group
   }
   __syncthreads();
   float2* sq = A.spec + (size_t)q * plane;
@@ -630,8 +630,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 
   // 2. stencil sweep: this thread owns rows i0 .. i0+RPT-1 of every column
   const int grp = q / A.Qg;
-  const float rho = A.rho[grp];
-  const float tau = A.lambda[grp] / rho;  // ops.jl:102
+  const float rho = A.rho[grp * A.PS + A.in];                                     // rho of r_{k+1}
+  const float tau = A.lambda[grp * A.PS + A.ic] / A.rho[grp * A.PS + A.ic];       // tau of v_k      (ops.jl:102)
+  const float tau_p = A.lambda[grp * A.PS + A.ip] / A.rho[grp * A.PS + A.ip];     // tau of v_{k-1}
   const int i0 = tid * RPT;
   const float* nsq_g = MODE != 0 ? A.nsq + (size_t)grp * plane : nullptr;
   float* nsq_o = MODE == 2 ? A.nsq_out + (size_t)q * plane : nullptr;   // per-pair partial sums
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     for (int r = 0; r < RPT; ++r) {
       const float2 xa = X[sidx<LM>(0, i0 + r)], xb = X[sidx<LM>(1, i0 + r)];
       float2 v = csub(xb, xa);
-      if (HAS_VPREV) v = cadd(v, shrink_aniso(up[r], tau).u);
+      if (HAS_VPREV) v = cadd(v, shrink_aniso(up[r], tau_p).u);
       vst[r] = v;
       w1c[r] = shrink_aniso(v, tau).w;
     }
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
           float2 v = csub(X[sidx<LM>(col + 1, i0 + r)], xc[r + 1]);
-          if (HAS_VPREV) v = cadd(v, shrink_aniso(g1[cc][r], tau).u);
+          if (HAS_VPREV) v = cadd(v, shrink_aniso(g1[cc][r], tau_p).u);
           vst[r] = v;
           w1n[r] = shrink_aniso(v, tau).w;
         }
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
         for (int r = 0; r <= RPT; ++r) {
           float2 v = csub(xc[r + 1], xc[r]);
-          if (HAS_VPREV) v = cadd(v, shrink_aniso(g2[cc][r], tau).u);
+          if (HAS_VPREV) v = cadd(v, shrink_aniso(g2[cc][r], tau_p).u);
           if (r < RPT) vst[r] = v;
           w2[r] = shrink_aniso(v, tau).w;
         }

@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   dim1_ifft_to_smem<LM, NT>(X, MODE == 2 ? nout + 1 : nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
   const int grp = q / A.pm.Qg;
-  const float rho = A.rho[grp];
-  const float tau = A.lambda[grp] / rho;
+  const float rho = A.rho[grp * A.PS + A.ir];                                     // rho_k
+  const float tau = A.lambda[grp * A.PS + A.it] / A.rho[grp * A.PS + A.it];       // tau_{k-1}
   const int i0 = tid * RPT;
   double racc = 0.0, tacc = 0.0;
   const float2* sc_g = MODE == 1 ? A.sc + (size_t)grp * plane : nullptr;   // per-pixel (s, tau ip / n^3) from k_iso_coef
@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   const double rsum = block_sum(racc);
   const double tsum = block_sum(tacc);
   if (tid == 0) {
-    atomicAdd(A.acc + 8 * grp + 0, rsum);
-    atomicAdd(A.acc + 8 * grp + 1, tsum);
+    atomicAdd(A.acc + (size_t)A.AS * grp + acc_rho(A.ir), rsum);
+    atomicAdd(A.acc + (size_t)A.AS * grp + acc_tau(A.it), tsum);
   }
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "fft_core.cuh"
+#include "args.cuh"
 #include "launch_macros.cuh"
 #include "reduce.cuh"
 
@@ -26,19 +27,19 @@ static __global__ void k_setup_twiddles(float2* twM, int M, float2* twN, int N) 
 }
 
 // clamp of deconv_admm.jl:216-219, in place; masks (1 = gradient passes) into `mask`:
-// mask[0] = lambda, mask[1] = rho, mask[2..2+kh*kw) = h
-static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int nh, float creg, int do_clamp, float* mask) {
+// mask[0..PS) = lambda entries, mask[PS..2PS) = rho entries, mask[2PS..2PS+kh*kw) = h
+static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int nh, int PS, float creg, int do_clamp, float* mask) {
   // one block per group
-  lambda += blockIdx.x;
-  rho += blockIdx.x;
+  lambda += (size_t)blockIdx.x * PS;
+  rho += (size_t)blockIdx.x * PS;
   if (h) h += (size_t)blockIdx.x * nh;
-  if (mask) mask += (size_t)blockIdx.x * (nh + 2);
-  for (int i = threadIdx.x; i < nh + 2; i += blockDim.x) {
-    float* p = i == 0 ? lambda : (i == 1 ? rho : h + (i - 2));
+  if (mask) mask += (size_t)blockIdx.x * (nh + 2 * PS);
+  for (int i = threadIdx.x; i < nh + 2 * PS; i += blockDim.x) {
+    float* p = i < PS ? lambda + i : (i < 2 * PS ? rho + (i - PS) : h + (i - 2 * PS));
     const float v = *p;
     float m = 1.f;
     if (do_clamp) {
-      if (i < 2) {
+      if (i < 2 * PS) {
         m = (v >= creg) ? 1.f : 0.f;
         *p = fmaxf(v, creg);
       } else {
@@ -74,15 +75,17 @@ static __global__ void k_setup_psf_dim1(const float* __restrict__ h, int kh, int
 //    feeds the first x-update directly; the dim-1 inverse that brings it back to space applies the remaining 1/M)
 // sig [p2][p1] = Sigma (only written when sig != nullptr; the backward needs it)
 // (p1,p2) are storage positions; (k1,k2) = pos_to_freq of them.
+// blockIdx.z = parameter entry (per-iteration rho): one C table per entry, [G][PS][N][M]; K and Sigma do not depend on rho
 static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int kw, int M, int N,
                                       const float* __restrict__ rho_p, float* ctab, float2* ktab, float2* sig, int planned) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
   {  // blockIdx.y = group: its own rho, PSF spectrum scratch and tables
-    const size_t grp = blockIdx.y;
+    const size_t grp = blockIdx.y, PS = gridDim.z, e = blockIdx.z;
     T += grp * (size_t)M * (kw > 0 ? kw : 1);
-    rho_p += grp;
-    ctab += grp * (size_t)M * N;
+    rho_p += grp * PS + e;
+    ctab += (grp * PS + e) * (size_t)M * N;
+    if (e != 0) { ktab = nullptr; sig = nullptr; }
     if (ktab) ktab += grp * (size_t)M * N;
     if (sig) sig += grp * (size_t)M * N;
   }
@@ -129,7 +132,7 @@ static __global__ void k_setup_tables(const double2* __restrict__ T, int kh, int
 //   part != null : nsq[g][i] = sum_q part[g*Qg + q][i]       (else nsq is taken as given: after a cross-rank all-reduce)
 //   s_out != null: s_out[g][i] = max(1 - tau/n, 0), n = sqrt(nsq)
 static __global__ void k_iso_scale(const float* __restrict__ part, int Qg, float* __restrict__ nsq, const float* __restrict__ lambda,
-                                   const float* __restrict__ rho, float* __restrict__ s_out, int npix) {
+                                   const float* __restrict__ rho, int PS, int pe, float* __restrict__ s_out, int npix) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = blockIdx.y;
   if (i >= npix) return;
@@ -143,7 +146,7 @@ static __global__ void k_iso_scale(const float* __restrict__ part, int Qg, float
     t = nsq[(size_t)g * npix + i];
   }
   if (s_out) {
-    const float tau = lambda[g] / rho[g];
+    const float tau = lambda[g * PS + pe] / rho[g * PS + pe];   // parameter entry of this iteration
     const float n = sqrtf(t);
     s_out[(size_t)g * npix + i] = n > 0.f ? fmaxf(1.f - tau / n, 0.f) : 0.f;
   }
@@ -151,8 +154,8 @@ static __global__ void k_iso_scale(const float* __restrict__ part, int Qg, float
 // backward: ip[g][i] = sum_q part[g*Qg + q][i] (fixed order; skipped when part is null), then, when sc != null,
 // (s, 1[n>tau] tau ip / n^3) per pixel and taubar -= sum_pixels 1[n>tau] ip / n   (acc[8g+1], when count_tau)
 static __global__ void k_iso_coef(const float* __restrict__ part, int Qg, const float* __restrict__ nsq, float* __restrict__ ip,
-                                  const float* __restrict__ lambda, const float* __restrict__ rho, float2* __restrict__ sc,
-                                  double* acc, int npix, int count_tau) {
+                                  const float* __restrict__ lambda, const float* __restrict__ rho, int PS, int pe, int AS,
+                                  float2* __restrict__ sc, double* acc, int npix, int count_tau) {
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i0 < npix;
   const int i = live ? i0 : 0;   // every thread takes part in the block reduction
@@ -167,7 +170,7 @@ static __global__ void k_iso_coef(const float* __restrict__ part, int Qg, const 
     p = ip[(size_t)g * npix + i];
   }
   if (!sc) return;   // uniform over the block
-  const float tau = lambda[g] / rho[g];
+  const float tau = lambda[g * PS + pe] / rho[g * PS + pe];
   const float n = sqrtf(nsq[(size_t)g * npix + i]);
   const bool act = live && n > tau;
   if (live) {
@@ -175,7 +178,7 @@ static __global__ void k_iso_coef(const float* __restrict__ part, int Qg, const 
     sc[(size_t)g * npix + i] = make_float2(s, act ? tau * p / (n * n * n) : 0.f);
   }
   const double tot = block_sum(act ? (double)(p / n) : 0.0);
-  if (threadIdx.x == 0 && count_tau) atomicAdd(acc + 8 * g + 1, -tot);
+  if (threadIdx.x == 0 && count_tau) atomicAdd(acc + (size_t)AS * g + acc_tau(pe), -tot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -184,31 +187,37 @@ static __global__ void k_iso_coef(const float* __restrict__ part, int Qg, const 
 //   hbar[a,b] = Re sum_k W[k] e^{+2 pi i (k1 a/M + k2 b/N)},
 //   W = 2 Sbar Sigma  +  (1/MN) P e^{-2 pi i (k1 pd/M + k2 pr/N)}   (spectral C path + spatial H^T y path)
 // ------------------------------------------------------------------------------------------
+// gacc and ctab hold one table per parameter entry ([G][PS][N][M]): Sbar_i from (G_i, C_i); rhobar_i gets its own spectral
+// term; the cotangent of |Sigma|^2 is their sum.
 static __global__ void k_grad_tables(const double* __restrict__ gacc, const double2* __restrict__ pacc,
                                      const float* __restrict__ ctab, const float2* __restrict__ sig, int kh, int kw,
-                                     int M, int N, int use_spatial, double2* Wn, double* acc, int planned) {
+                                     int M, int N, int use_spatial, double2* Wn, double* acc, int planned, int PS, int AS) {
   const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = idx0 < M * N;
   const int idx = live ? idx0 : 0;   // every thread takes part in the block reduction
   {  // blockIdx.y = group
     const size_t go = (size_t)blockIdx.y * M * N;
-    gacc += go; ctab += go;
+    gacc += go * PS; ctab += go * PS;
     if (pacc) pacc += go;
     if (sig) sig += go;
     if (Wn) Wn += go;
-    acc += 8 * blockIdx.y;
+    acc += (size_t)AS * blockIdx.y;
   }
   const int p1 = idx % M, p2 = idx / M;
   const int k1 = pos_to_freq(M, p1, (planned & 1) != 0), k2 = pos_to_freq(N, p2, (planned & 2) != 0, 1);
   const double mn = (double)M * (double)N;
-  const double C = (double)ctab[idx] * mn;
-  const double Sbar = -(gacc[idx] / mn) * C * C;
   double s1, c1, s2, c2;
   sincospi((double)k2 / N, &s2, &c2);
   sincospi((double)k1 / M, &s1, &c1);
   const double lap = 4.0 * s2 * s2 + 4.0 * s1 * s1;
-  const double tot = block_sum(live ? Sbar * lap : 0.0);
-  if (threadIdx.x == 0) atomicAdd(acc + 3, tot);
+  double Sbar = 0.0;
+  for (int e = 0; e < PS; ++e) {
+    const double C = (double)ctab[(size_t)e * M * N + idx] * mn;
+    const double Se = -(gacc[(size_t)e * M * N + idx] / mn) * C * C;
+    Sbar += Se;
+    const double tot = block_sum(live ? Se * lap : 0.0);
+    if (threadIdx.x == 0) atomicAdd(acc + acc_rhos(e), tot);
+  }
   if (kh > 0 && live) {
     const float2 sg = sig[idx];
     double wr = 2.0 * Sbar * (double)sg.x, wi = 2.0 * Sbar * (double)sg.y;
@@ -248,18 +257,18 @@ static __global__ void k_grad_h_dim1(const double2* __restrict__ Wn, int kh, int
 // hbar[a,b] = mask * Re sum_k2 U[a][k2] e^{+2 pi i k2 b / N} (one block per tap); block 0 also
 // finalises the scalars:
 //   lambar = taubar / rho ; rhobar = direct + spectral - taubar lambda / rho^2   (tau = lambda ./ rho, ops.jl:102)
-// acc: [0] rho direct, [1] taubar, [2] biasbar, [3] rho spectral.  mask: [0] lambda, [1] rho, [2..] h.
+// acc: args.cuh acc_*.  mask: [0..PS) lambda, [PS..2PS) rho, [2PS..) h.
 static __global__ void k_grad_finalize(const double2* __restrict__ U, int kh, int kw, int N, const float* __restrict__ mask,
                                        const double* __restrict__ acc, const float* __restrict__ lambda,
                                        const float* __restrict__ rho, float* hbar, float* lambar, float* rhobar,
-                                       float* biasbar) {
+                                       float* biasbar, int PS, int AS) {
   const int t = blockIdx.x;
   {  // blockIdx.y = group
     const int grp = blockIdx.y;
     U += (size_t)grp * kh * N;
-    mask += (size_t)grp * (kh * kw + 2);
-    acc += 8 * grp;
-    lambda += grp; rho += grp; lambar += grp; rhobar += grp;
+    mask += (size_t)grp * (kh * kw + 2 * PS);
+    acc += (size_t)AS * grp;
+    lambda += (size_t)grp * PS; rho += (size_t)grp * PS; lambar += (size_t)grp * PS; rhobar += (size_t)grp * PS;
     if (hbar) hbar += (size_t)grp * kh * kw;
     if (biasbar) biasbar += grp;
   }
@@ -273,13 +282,15 @@ static __global__ void k_grad_finalize(const double2* __restrict__ U, int kh, in
       re += u.x * c - u.y * s;
     }
     re = block_sum(re);
-    if (threadIdx.x == 0) hbar[t] = (float)(re * (double)mask[2 + t]);
+    if (threadIdx.x == 0) hbar[t] = (float)(re * (double)mask[2 * PS + t]);
   }
-  if (t == 0 && threadIdx.x == 0) {
-    const double lam = (double)*lambda, r = (double)*rho, tb = acc[1];
-    *lambar = (float)((double)mask[0] * tb / r);
-    *rhobar = (float)((double)mask[1] * (acc[0] + acc[3] - tb * lam / (r * r)));
-    if (biasbar) *biasbar = (float)acc[2];
+  if (t == 0) {
+    for (int e = threadIdx.x; e < PS; e += blockDim.x) {
+      const double lam = (double)lambda[e], r = (double)rho[e], tb = acc[acc_tau(e)];
+      lambar[e] = (float)((double)mask[e] * tb / r);
+      rhobar[e] = (float)((double)mask[PS + e] * (acc[acc_rho(e)] + acc[acc_rhos(e)] - tb * lam / (r * r)));
+    }
+    if (biasbar && threadIdx.x == 0) *biasbar = (float)acc[acc_bias()];
   }
 }
 

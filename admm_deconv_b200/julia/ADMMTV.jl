@@ -31,6 +31,9 @@ end
 
 const FLAG_NO_CLAMP = Int32(1)
 const FLAG_NOGRAD_REPEAT = Int32(2)
+const FLAG_PER_ITER_PARAMS = Int32(64)   # EXTENSION: λ, ρ hold `iters` values, entry k for iteration k (include/admmtv.h)
+per_iter_flag(λ, iters) = length(λ) > 1 ? (length(λ) == iters ? FLAG_PER_ITER_PARAMS :
+    error("ADMMTV: per-iteration parameters need exactly `iters` values")) : Int32(0)
 
 # train.jl:10 declares `Zygote.@nograd CUDA.repeat` (= Base.repeat): under it Zygote drops the gradient through
 # `h = repeat(h,1,1,1,B)` (ops.jl:153), i.e. ∂weight loses its spatial H^T y path.  train_v2.jl / ADMM_Deconv.jl do not.
@@ -109,14 +112,14 @@ end
 # Differentiable core shared by tvd_fft and the layer call.
 function admm_call(y::CuArray{Float32,4}, λ::CuArray{Float32,1}, ρ::CuArray{Float32,1}, h, bias,
                    iso::Bool, iters::Integer, act::Int32, creg, flags::Int32)
-    d = make_desc(y, h, iters, iso, act, bias isa CuArray, flags, creg)
+    d = make_desc(y, h, iters, iso, act, bias isa CuArray, flags | per_iter_flag(λ, iters), creg)
     x, _, ws = forward!(d, y, h, λ, ρ, bias; ckpt=false)
     CUDA.unsafe_free!(ws)          # stream-ordered: returns to the pool after the work enqueued above
     x
 end
 
 function ChainRulesCore.rrule(::typeof(admm_call), y, λ, ρ, h, bias, iso, iters, act, creg, flags)
-    d = make_desc(y, h, iters, iso, act, bias isa CuArray, flags | grad_flags(), creg)
+    d = make_desc(y, h, iters, iso, act, bias isa CuArray, flags | grad_flags() | per_iter_flag(λ, iters), creg)
     x, ckb, ws = forward!(d, y, h, λ, ρ, bias; ckpt=true)
     CUDA.unsafe_free!(ws)
     function admm_pullback(x̄)

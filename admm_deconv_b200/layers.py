@@ -84,6 +84,16 @@ class _AdmmBase(nn.Module):
         self.rho = nn.Parameter(torch.as_tensor(rho, dtype=torch.float32).reshape(1), requires_grad="rho" in cls._trainable)
         return self
 
+    def per_iteration_(self):
+        """EXTENSION (BASELINE configs[2] "learned-rho/lambda iterations"): give every unrolled iteration
+        its own (λ_k, ρ_k), initialised to the current values.  The reference has one pair for all iterations
+        (deconv_admm.jl:168-169, ops.jl:20); with equal entries the result is bit-identical to it.  In place; returns self."""
+        for n in ("lam", "rho"):
+            p = getattr(self, n)
+            if p.numel() == 1:
+                setattr(self, n, nn.Parameter(p.detach().repeat(self.iters).contiguous(), requires_grad=p.requires_grad))
+        return self
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """(d::Admm)(x), deconv_admm.jl:215-225.  λ, ρ, weight are clamped in place by the kernel
         library, which is the reference's write-back into the struct."""

@@ -150,6 +150,11 @@ def admm_layer_call(y, lam, rho, h=None, bias=None, iters=100, iso=False, activa
     ``iso_coupling`` (a ``dist.IsoCoupling``, EXTENSION): with a batch sharded over ranks, makes the
     isotropic per-pixel norm span every rank's images, i.e. the reference's single-device result on the whole batch."""
     flags = (0 if clamp else _lib.FLAG_NO_CLAMP) | (_lib.FLAG_NOGRAD_REPEAT if nograd_repeat else 0)
+    if lam.numel() > 1 or rho.numel() > 1:
+        # EXTENSION: one (lambda_k, rho_k) per unrolled iteration (ADMMTV_FLAG_PER_ITER_PARAMS, include/admmtv.h)
+        if lam.numel() != int(iters) or rho.numel() != int(iters):
+            raise ValueError("per-iteration parameters: lam and rho need exactly `iters` values each")
+        flags |= _lib.FLAG_PER_ITER_PARAMS
     lam, rho, h = _own_if_nonleaf(lam, clamp), _own_if_nonleaf(rho, clamp), _own_if_nonleaf(h, clamp)
     return _AdmmFunction.apply(y, lam, rho, h, bias, int(iters), bool(iso), activation, float(creg), flags, iso_coupling,
                                _needs_grad(y, lam, rho, h, bias))

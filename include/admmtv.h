@@ -51,7 +51,14 @@ enum {
    * kernel per iteration that adds the plane pairs' shares in a fixed order, so the isotropic path is
    * bit-reproducible run to run (no floating-point atomics on it) */
   ADMMTV_FLAG_ISO_PRECOMPUTE = 16,
-  ADMMTV_FLAG_ISO_INLINE = 32
+  ADMMTV_FLAG_ISO_INLINE = 32,
+  /* EXTENSION (BASELINE configs[2] "learned-rho/lambda iterations"): one (lambda_k, rho_k) per unrolled
+   * iteration instead of the reference's single pair (ops.jl:20: tau is one scalar for all iterations).  lambda and rho
+   * then hold `iters` floats per group, entry k-1 for iteration k: x_k = F^-1(C(rho_k) F(H^T y + rho_k D^T(z_{k-1} - u_{k-1}))),
+   * z_k = shrink(D x_k + u_{k-1}, lambda_k / rho_k).  admmtv_backward returns `iters` lambdabar / rhobar per group (the last
+   * lambdabar is 0: the final z-update is dead, ops.jl:89-91).  With every entry equal the result is bit-identical to the
+   * shared-parameter call. */
+  ADMMTV_FLAG_PER_ITER_PARAMS = 64
 };
 
 /* error codes (<0) */

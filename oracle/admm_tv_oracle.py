@@ -296,20 +296,28 @@ def tvd_fft_fast(
 ) -> torch.Tensor:
     """Same mathematics as tvd_fft_cpu, written independently: roll-based D / D^T, analytic
     |Lambda|^2, explicit shifted-sum H^T y (hoisted out of the loop when ``hoist``).
-    Works directly on (M,N,P,B) (no permute; the permute only regroups independent planes)."""
+    Works directly on (M,N,P,B) (no permute; the permute only regroups independent planes).
+
+    EXTENSION (not in the reference): when ``lam`` / ``rho`` hold ``maxit`` values, iteration k uses
+    (lam[k-1], rho[k-1]) for its x-update and its shrinkage -- "learned per-iteration parameters".  With one value each
+    this is exactly the reference recursion (ops.jl:84-92)."""
     M, N, P, B = y.shape
-    tau = lam / rho
-    _, C = spectral_tables(M, N, h, rho, y.dtype)
-    C = C.reshape(M // 2 + 1, N, 1, 1)
+    per_iter = lam.numel() > 1 or rho.numel() > 1
+    if per_iter:
+        assert lam.numel() == maxit and rho.numel() == maxit, "per-iteration parameters: one value per iteration"
+    lam_k = lambda k: lam[k:k + 1] if per_iter else lam
+    rho_k = lambda k: rho[k:k + 1] if per_iter else rho
+    C_all = [spectral_tables(M, N, h, rho_k(k), y.dtype)[1].reshape(M // 2 + 1, N, 1, 1) for k in range(maxit if per_iter else 1)]
     h_empty = h is None or h.numel() == 0
     Hty = (lambda: y) if h_empty else (lambda: Ht_roll(y, h))
     b = Hty() if hoist else None
     z1 = torch.zeros_like(y); z2 = torch.zeros_like(y)
     u1 = torch.zeros_like(y); u2 = torch.zeros_like(y)
     x = torch.zeros_like(y)
-    for _ in range(maxit):
+    for k in range(maxit):
         bb = b if hoist else Hty()
-        x = irfft12(C * rfft12(bb + rho * Dt_roll(z1 - u1, z2 - u2)), M)
+        rho_, tau, C = rho_k(k), lam_k(k) / rho_k(k), C_all[k if per_iter else 0]
+        x = irfft12(C * rfft12(bb + rho_ * Dt_roll(z1 - u1, z2 - u2)), M)
         d1, d2 = D_roll(x)
         v1, v2 = d1 + u1, d2 + u2
         if isotropic:

@@ -60,20 +60,22 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
     what the scalar gradients (cancelling sums) are compared against in tests/parity.py."""
     M, N, P, B = y.shape
     dt = dtype
-    tau_g64 = (lam.float() / rho.float()).double() if fp32_gate else (lam / rho).double()
+    PS = lam.numel()                  # 1, or K per-iteration values (EXTENSION: entry k-1 belongs to iteration k)
+    pe = lambda k: 0 if PS == 1 else k - 1
+    tau_g64_all = (lam.float() / rho.float()).double() if fp32_gate else (lam / rho).double()
     xbar, y, lam, rho = xbar.to(dt), y.to(dt), lam.to(dt), rho.to(dt)
     h = None if h is None else h.to(dt)
     v_states = [(a.to(dt), b.to(dt)) for a, b in v_states]
-    tau = lam / rho
-    tau_g = tau_g64.to(dt)
+    tau_all = lam / rho
     margin = float("inf")
-    Sig, L, C = _full_tables(M, N, h, rho, dt)
-    C4 = C.reshape(M, N, 1, 1)
+    tabs = [_full_tables(M, N, h, rho[e:e + 1], dt) for e in range(PS)]
+    Sig, L = tabs[0][0], tabs[0][1]
     fft2 = lambda t: torch.fft.fftn(t, dim=(0, 1))
     ifft2 = lambda T: torch.fft.ifftn(T, dim=(0, 1)).real
     b = y if h is None or h.numel() == 0 else O.Ht_roll(y, h)
 
     def shrink(v1, v2, k):
+        tau, tau_g = tau_all[pe(max(k, 1))], tau_g64_all[pe(max(k, 1))].to(dt)   # v_k was shrunk with tau_k
         if iso:
             if nsq_states is not None and k >= 1:
                 n = torch.sqrt(nsq_states[k - 1].float()).to(dt).reshape(M, N, 1, 1)   # the device's fp32 norm
@@ -88,25 +90,28 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
     zero = torch.zeros_like(y)
     vs = [(zero, zero)] + list(v_states)          # vs[k] = v_k, v_0 = 0
     vb1, vb2 = zero, zero
-    G = torch.zeros(M, N, dtype=dt)
+    G = torch.zeros(PS, M, N, dtype=dt)
     bbar = torch.zeros_like(y)
-    rhobar = torch.zeros((), dtype=dt)
-    taubar = torch.zeros((), dtype=dt)
+    rhobar = torch.zeros(PS, dtype=dt)
+    taubar = torch.zeros(PS, dtype=dt)
     for k in range(K, 0, -1):
         xk = (xbar if k == K else 0) + (O.Dt_roll(vb1, vb2) if k < K else 0)
         v1, v2 = vs[k - 1]
         z1, z2, n, s = shrink(v1, v2, k - 1)
         g1, g2 = 2 * z1 - v1, 2 * z2 - v2
-        r = b + rho * O.Dt_roll(g1, g2)
+        rho_k = rho[pe(k)]
+        r = b + rho_k * O.Dt_roll(g1, g2)
         Zb = fft2(xk)
-        G += (Zb.conj() * fft2(r)).real.sum(dim=(2, 3))
-        rb = ifft2(C4 * Zb)
+        G[pe(k)] += (Zb.conj() * fft2(r)).real.sum(dim=(2, 3))
+        rb = ifft2(tabs[pe(k)][2].reshape(M, N, 1, 1) * Zb)
         bbar = bbar + rb
         if k == 1:
             break
         d1, d2 = O.D_roll(rb)
-        rhobar = rhobar + (d1 * g1).sum() + (d2 * g2).sum()
-        gb1, gb2 = rho * d1, rho * d2
+        rhobar[pe(k)] = rhobar[pe(k)] + (d1 * g1).sum() + (d2 * g2).sum()
+        gb1, gb2 = rho_k * d1, rho_k * d2
+        tau, tau_g = tau_all[pe(k - 1)], tau_g64_all[pe(k - 1)].to(dt)     # the shrinkage of v_{k-1}
+        te = pe(k - 1)
         q1, q2 = 2 * gb1 - vb1, 2 * gb2 - vb2
         if iso:
             ip = torch.sum(q1 * v1 + q2 * v2, dim=(2, 3), keepdim=True)
@@ -115,18 +120,19 @@ def backward(xbar, y, lam, rho, h, iso, K, v_states: List[Tuple[torch.Tensor, to
             coef = torch.where(act, tau * ip / n ** 3, torch.zeros_like(n))
             nv1 = vb1 - gb1 + s * q1 + coef * v1
             nv2 = vb2 - gb2 + s * q2 + coef * v2
-            taubar = taubar - torch.where(act, ip / n, torch.zeros_like(n)).sum()
+            taubar[te] = taubar[te] - torch.where(act, ip / n, torch.zeros_like(n)).sum()
         else:
             m1 = (v1.abs() > tau_g).to(dt)
             m2 = (v2.abs() > tau_g).to(dt)
             margin = min(margin, float(((v1.abs() - tau_g).abs() / tau_g).min()), float(((v2.abs() - tau_g).abs() / tau_g).min()))
             nv1 = vb1 - gb1 + m1 * q1
             nv2 = vb2 - gb2 + m2 * q2
-            taubar = taubar - (torch.sign(v1) * m1 * q1).sum() - (torch.sign(v2) * m2 * q2).sum()
+            taubar[te] = taubar[te] - (torch.sign(v1) * m1 * q1).sum() - (torch.sign(v2) * m2 * q2).sum()
         vb1, vb2 = nv1, nv2
-    Sbar = -(G / (M * N)) * C * C
-    rhobar = rhobar + (Sbar * L).sum()
-    out = {"lam": (taubar / rho).reshape(1), "rho": (rhobar - taubar * lam / rho ** 2).reshape(1), "gate_margin": margin}
+    Sbar_e = torch.stack([-(G[e] / (M * N)) * tabs[e][2] * tabs[e][2] for e in range(PS)])
+    rhobar = rhobar + (Sbar_e * L).sum(dim=(1, 2))
+    Sbar = Sbar_e.sum(dim=0)
+    out = {"lam": (taubar / rho).reshape(PS), "rho": (rhobar - taubar * lam / rho ** 2).reshape(PS), "gate_margin": margin}
     if h is None or h.numel() == 0:
         out["x"] = bbar
         out["weight"] = None

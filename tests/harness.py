@@ -60,13 +60,17 @@ class Backend:
         y = f32(y)
         M, N, P, B = y.shape
         kh, kw = (0, 0) if h is None else (h.shape[0], h.shape[1])
+        lam = np.atleast_1d(np.asarray(lam, dtype=np.float32)); rho = np.atleast_1d(np.asarray(rho, dtype=np.float32))
+        if lam.size > 1 or rho.size > 1:      # one (lambda, rho) per iteration: ADMMTV_FLAG_PER_ITER_PARAMS
+            assert lam.size == iters and rho.size == iters
+            flags |= _lib.FLAG_PER_ITER_PARAMS
         d = _lib.make_desc(M, N, P, B, kh, kw, iters, iso, act, bias is not None, 0, flags, creg)
         fwd_b, ck_b, bwd_b = self.lib.workspace_bytes(d)
         r = dict(desc=d, bwd_bytes=bwd_b)
         r["y"] = self.buf(y)
         r["h"] = None if h is None else self.buf(f32(np.asarray(h).reshape(kh, kw)))
-        r["lam"] = self.buf(np.array([lam], dtype=np.float32))
-        r["rho"] = self.buf(np.array([rho], dtype=np.float32))
+        r["lam"] = self.buf(lam)
+        r["rho"] = self.buf(rho)
         r["bias"] = None if bias is None else self.buf(np.array([bias], dtype=np.float32))
         r["x"] = self.zeros((M, N, P, B))
         ws = self.zeros((fwd_b,), np.uint8)
@@ -122,7 +126,8 @@ class Backend:
         xb = self.buf(f32(xbar))
         ws = self.zeros((fwd["bwd_bytes"],), np.uint8)
         out = dict(ybar=self.zeros((M, N, P, B)), hbar=None if fwd["h"] is None else self.zeros(fwd["h"].shape),
-                   lambar=self.zeros((1,)), rhobar=self.zeros((1,)), biasbar=None if fwd["bias"] is None else self.zeros((1,)))
+                   lambar=self.zeros(fwd["lam"].shape), rhobar=self.zeros(fwd["rho"].shape),
+                   biasbar=None if fwd["bias"] is None else self.zeros((1,)))
         p = lambda b: None if b is None else b.ptr
         self.lib.backward(d, xb.ptr, fwd["x"].ptr, fwd["y"].ptr, p(fwd["h"]), fwd["lam"].ptr, fwd["rho"].ptr, fwd["ckpt"].ptr,
                           out["ybar"].ptr, p(out["hbar"]), out["lambar"].ptr, out["rhobar"].ptr, p(out["biasbar"]), ws.ptr,

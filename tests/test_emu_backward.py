@@ -92,3 +92,23 @@ def test_emu_backward_generic_sizes(be, M, N, P, B, kh, kw, K, iso, act, bias, f
     xbar = torch.from_numpy(np.random.default_rng(K).standard_normal((M, N, P, B)))
     check_backward(be, y, h, 0.05, 0.3, iso, K, xbar, act, bias, 0.0, flags, tol=1e-5, tol_scalar=2e-4,
                    tol_e2e=1e-4 if iso else 1e-3)
+
+
+@pytest.mark.parametrize("M,N,P,B,kh,kw,K,iso", [(32, 32, 1, 2, 3, 3, 5, False), (64, 32, 3, 1, 5, 4, 4, True), (33, 17, 1, 2, 3, 3, 4, False)])
+def test_emu_per_iteration_parameters(emu, M, N, P, B, kh, kw, K, iso):
+    """ADMMTV_FLAG_PER_ITER_PARAMS (EXTENSION): forward vs the fp64 oracle, backward teacher-forced with one
+    lambdabar / rhobar per iteration; equal entries reproduce the shared-parameter call bit for bit."""
+    import numpy as np
+    import harness
+    from parity import check_backward, check_forward
+    be = harness.EmuBackend(emu)
+    y, h, g = make_case(M, N, P, B, kh, kw, 1300 + M)
+    rng = np.random.default_rng(5)
+    lam = (0.004 * (1 + rng.random(K))).astype(np.float32); rho = (0.02 * (1 + 2 * rng.random(K))).astype(np.float32)
+    check_forward(be, y, h, lam, rho, iso, K)
+    xbar = 2.0 * (y - g) / y.numel() * 1e3
+    r = check_backward(be, y, h, lam, rho, iso, K, xbar, flags=1, tol=1e-5, tol_scalar=2e-4)
+    print(r)
+    a = be.forward(y.numpy(), float(lam[0]), float(rho[0]), h.numpy()[:, :, 0, 0], iso, K, flags=1)
+    b = be.forward(y.numpy(), np.full(K, lam[0]), np.full(K, rho[0]), h.numpy()[:, :, 0, 0], iso, K, flags=1)
+    assert np.array_equal(a["x"].get(), b["x"].get())

@@ -254,3 +254,44 @@ def test_scalar_gradient_error_sits_at_the_fp32_rounding_floor(be):
     assert max(r["hbar"] for r in rows) < 1e-5
     assert max(r["rho_floor32"] for r in rows) > 1e-5          # the fp32 evaluation of the recursion itself misses 1e-5
     assert max(r["rho"] for r in rows) < 2e-4 and max(r["lam"] for r in rows) < 2e-4
+
+
+@pytest.mark.parametrize("M,N,P,B,kh,kw,K,iso", [(64, 64, 3, 2, 7, 7, 10, False), (256, 256, 3, 2, 15, 15, 10, False), (128, 256, 1, 4, 5, 5, 6, True),
+                                                 (512, 512, 1, 2, 9, 9, 4, False), (100, 60, 3, 1, 5, 5, 5, False)])
+def test_per_iteration_parameters(be, M, N, P, B, kh, kw, K, iso):
+    """ADMMTV_FLAG_PER_ITER_PARAMS (EXTENSION, SURVEY.md 8f-4 / BASELINE configs[2] "learned-rho/lambda iterations"): forward
+    vs the fp64 oracle, backward teacher-forced with one lambdabar / rhobar per iteration; equal entries reproduce the
+    shared-parameter call bit for bit."""
+    from parity import check_forward
+    y, h, g = make_case(M, N, P, B, kh, kw, 1300 + M)
+    rng = np.random.default_rng(5)
+    lam = (0.004 * (1 + rng.random(K))).astype(np.float32); rho = (0.02 * (1 + 2 * rng.random(K))).astype(np.float32)
+    check_forward(be, y, h, lam, rho, iso, K)
+    xbar = 2.0 * (y - g) / y.numel() * 1e3
+    r = check_backward(be, y, h, lam, rho, iso, K, xbar, flags=1, tol=1e-5, tol_scalar=2e-4)
+    print(r)
+    a = be.forward(y.numpy(), float(lam[0]), float(rho[0]), h.numpy()[:, :, 0, 0], iso, K, flags=1)
+    b = be.forward(y.numpy(), np.full(K, lam[0]), np.full(K, rho[0]), h.numpy()[:, :, 0, 0], iso, K, flags=1)
+    assert np.array_equal(a["x"].get(), b["x"].get())
+
+
+def test_layer_with_per_iteration_parameters_trains():
+    d = torch.device("cuda:0")
+    torch.manual_seed(0)
+    layer = A.ADMMDeconv((5, 5), 8, "identity").per_iteration_().to(d)
+    with torch.no_grad():
+        layer.weight.copy_(A.from_julia(O.gaussian_psf(5, 1.0).float()).to(d)); layer.lam.fill_(0.0041); layer.rho.fill_(0.021)
+    assert layer.lam.shape == (8,) and layer.rho.shape == (8,)
+    y, _, g = make_case(64, 64, 3, 2, 5, 5, 5, psf="gauss")
+    yt = A.from_julia(y.float()).to(d); gt = A.from_julia(g.float()).to(d)
+    ref = A.ADMMDeconv((5, 5), 8, "identity").to(d)
+    with torch.no_grad():
+        ref.weight.copy_(layer.weight); ref.lam.fill_(0.0041); ref.rho.fill_(0.021)
+    out = layer(yt)
+    assert torch.equal(out, ref(yt))                      # equal entries == the reference's single pair
+    ((out - gt) ** 2).mean().backward()
+    assert layer.lam.grad.shape == (8,) and float(layer.lam.grad[-1]) == 0.0 and torch.isfinite(layer.rho.grad).all()
+    ((ref(yt) - gt) ** 2).mean().backward()
+    # d/d(shared) = sum over the per-iteration entries
+    assert abs(float(layer.rho.grad.sum()) - float(ref.rho.grad)) <= 2e-4 * abs(float(ref.rho.grad))
+    assert abs(float(layer.lam.grad.sum()) - float(ref.lam.grad)) <= 2e-4 * abs(float(ref.lam.grad))

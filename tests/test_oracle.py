@@ -151,3 +151,32 @@ def test_teacher_forced_recursion_equals_autograd(iso, kh, kw):
     assert abs(float(t["rho"]) - float(g["rho"])) < 1e-9 * max(1, abs(float(g["rho"])))
     if h is not None:
         assert rel_l2(t["weight"], g["weight"]) < 1e-12
+
+
+@pytest.mark.parametrize("iso", [False, True])
+def test_per_iteration_parameters_teacher_forced_equals_autograd(iso):
+    """EXTENSION: one (lambda_k, rho_k) per unrolled iteration.  The hand adjoint recursion with
+    per-iteration entries equals fp64 autograd through the roll/spectral formulation; with all entries equal both
+    reduce to the reference recursion."""
+    import torch
+    from oracle import admm_tv_oracle as O
+    from oracle import teacher_forced as TF
+    from cases import make_case
+    K = 6
+    y, h, g = make_case(24, 16, 2, 2, 3, 5, 17)
+    lam = torch.tensor([0.004, 0.006, 0.003, 0.008, 0.005, 0.007], dtype=torch.float64)
+    rho = torch.tensor([0.02, 0.05, 0.03, 0.04, 0.025, 0.06], dtype=torch.float64)
+    lv, rv, hv, yv = (t.clone().requires_grad_(True) for t in (lam, rho, h, y))
+    x = O.tvd_fft_fast(yv, lv, rv, hv, iso, K)
+    xbar = torch.from_numpy(__import__("numpy").random.default_rng(0).standard_normal(tuple(x.shape)))
+    gy, gl, gr, gh = torch.autograd.grad(x, [yv, lv, rv, hv], grad_outputs=xbar)
+    _, st = TF.forward_states(y, lam, rho, h, iso, K)
+    tf = TF.backward(xbar, y, lam, rho, h, iso, K, st)
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(tf["x"], gy) < 1e-12 and rel(tf["weight"], gh) < 1e-11
+    assert rel(tf["lam"][:-1], gl[:-1]) < 1e-11 and float(gl[-1]) == 0.0 and float(tf["lam"][-1]) == 0.0   # last z-update is dead
+    assert rel(tf["rho"], gr) < 1e-11
+    # equal entries == the shared-parameter recursion
+    xs = O.tvd_fft_fast(y, lam[:1], rho[:1], h, iso, K)
+    xe = O.tvd_fft_fast(y, lam[:1].repeat(K), rho[:1].repeat(K), h, iso, K)
+    assert torch.equal(xs, xe)
