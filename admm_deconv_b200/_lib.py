@@ -20,6 +20,7 @@ FLAG_CHANNEL_CONCAT = 8
 FLAG_ISO_PRECOMPUTE = 16
 FLAG_ISO_INLINE = 32
 FLAG_PER_ITER_PARAMS = 64
+FLAG_NO_SMALL = 128
 
 # every symbol include/admmtv.h declares (tests check the .so exports exactly these)
 SYMBOLS = (

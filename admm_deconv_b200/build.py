@@ -30,7 +30,8 @@ GXX_FLAGS = ["-std=c++20", "-O1", "-fPIC", "-pthread", "-DADMMTV_EMU", "-x", "c+
 
 def _units(emulate: bool = False):
     """(source, define, object stem)"""
-    u = [("admmtv_api.cu", None, "admmtv_api"), ("loss_api.cu", None, "loss_api"), ("inst_generic.cu", None, "inst_generic")]
+    u = [("admmtv_api.cu", None, "admmtv_api"), ("loss_api.cu", None, "loss_api"), ("inst_generic.cu", None, "inst_generic"),
+         ("inst_small.cu", None, "inst_small")]
     if not emulate:   # the host-buffer layer (streams, pinned memory) has no CPU emulation twin
         u.append(("host_api.cu", None, "host_api"))
     for l in LOG2_SIZES:

@@ -5,6 +5,7 @@
 #include "../../include/admmtv.h"
 #include "args.cuh"
 #include "setup_kernels.cuh"
+#include "kernels_small.cuh"
 
 #include <stdio.h>
 
@@ -279,7 +280,7 @@ int admmtv_check(const admmtv_desc* d) {
   if (d->activation < 0 || d->activation > 3) return ADMMTV_ERR_ENUM;
   if (d->has_bias != 0 && d->has_bias != 1) return ADMMTV_ERR_ENUM;
   if (d->flags & ~(ADMMTV_FLAG_NO_CLAMP | ADMMTV_FLAG_NOGRAD_REPEAT | ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT |
-                   ADMMTV_FLAG_ISO_PRECOMPUTE | ADMMTV_FLAG_ISO_INLINE | ADMMTV_FLAG_PER_ITER_PARAMS))
+                   ADMMTV_FLAG_ISO_PRECOMPUTE | ADMMTV_FLAG_ISO_INLINE | ADMMTV_FLAG_PER_ITER_PARAMS | ADMMTV_FLAG_NO_SMALL))
     return ADMMTV_ERR_ENUM;
   if (d->groups < 0 || (d->groups > 1 && d->B % d->groups != 0)) return ADMMTV_ERR_SHAPE;
   if (d->groups <= 1 && (d->flags & (ADMMTV_FLAG_SHARED_INPUT | ADMMTV_FLAG_CHANNEL_CONCAT))) return ADMMTV_ERR_ENUM;
@@ -369,6 +370,10 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
                       const_cast<float2*>(ktab), ckpt ? ck.sig : nullptr, st)))
     return rc;
 
+  // Planes that fit one SM (kernels_small.cuh): every iteration inside ONE persistent kernel, the spectrum never leaves
+  // shared memory.  Inference, anisotropic, enough pairs to occupy the GPU; ADMMTV_FLAG_NO_SMALL keeps the two-launch path.
+  const bool use_small = !ckpt && !d->iso && !hk && !(d->flags & ADMMTV_FLAG_NO_SMALL) && small_supported(g) && g.Q >= 64;
+
   // spectrum ping-pong: `cur` holds the dim-1 spectrum of r_k, `oth` receives the k_dim2 result
   float2 *cur = w.specA, *oth = w.specB;
   // y -> pair-pack -> dim-1 spectrum (ops.jl:101 + first FFT pass)
@@ -393,11 +398,22 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
     // already holds it before rounding.  Reusing specB saves a launch (104 us at 64 x 512^2 x 3) but makes r_1 inconsistent
     // with the r_k = b + rho D^T(...) of the later iterations at the rounding level, and the teacher-forced parameter
     // gradients then sit 1.7x further from the fp64 adjoint (hbar 4.4e-6 -> 1.25e-5 on 2 x 256^2, K = 10): not worth 1 %.
-    {
+    if (!use_small) {
       PackArgs p{};
       p.src_packed = w.bpk; p.spec = w.specA; p.twM = twM; p.N = g.N; p.S = g.S; p.pm = g.pm;
       if ((rc = run_pack_fft1(g, 2, p, st))) return rc;
     }
+  }
+
+  if (use_small) {
+    SmallArgs s{};
+    s.bpk = w.bpk; s.v0 = w.v0; s.v1 = w.v1; s.ctab = ctab; s.twM = twM; s.twN = twN; s.lambda = lambda; s.rho = rho;
+    s.planes = x_out; s.bias = d->has_bias ? bias : nullptr; s.pm = g.pm; s.tab_stride = g.G > 1 ? g.plane * g.PS : 0;
+    s.K = g.K; s.PS = g.PS; s.act = d->activation; s.Q = g.Q;
+    tm_mark(tm, st, 0);
+    if ((rc = run_small(g, s, st))) return rc;
+    tm_mark(tm, st, -1);
+    return ADMMTV_OK;
   }
 
   // the unrolled iterations (ops.jl:166-174)

@@ -58,7 +58,10 @@ enum {
    * z_k = shrink(D x_k + u_{k-1}, lambda_k / rho_k).  admmtv_backward returns `iters` lambdabar / rhobar per group (the last
    * lambdabar is 0: the final z-update is dead, ops.jl:89-91).  With every entry equal the result is bit-identical to the
    * shared-parameter call. */
-  ADMMTV_FLAG_PER_ITER_PARAMS = 64
+  ADMMTV_FLAG_PER_ITER_PARAMS = 64,
+  /* tuning / testing: planes of 32^2, 64^2, 128^2 normally run every iteration of an anisotropic inference call inside one
+   * persistent kernel per plane pair (kernels_small.cuh); this flag keeps the general two-launch-per-iteration path */
+  ADMMTV_FLAG_NO_SMALL = 128
 };
 
 /* error codes (<0) */

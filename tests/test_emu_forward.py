@@ -115,3 +115,31 @@ def test_emu_forward_generic_sizes(emu, M, N, P, B, kh, kw, K, iso):
     l = torch.tensor([0.05], dtype=torch.float32).double(); r = torch.tensor([0.3], dtype=torch.float32).double()
     xo = O.tvd_fft_cpu(y.float().double(), l, r, None if h is None else h.float().double(), iso, K)
     assert rel_l2(x, xo) <= 1e-5
+
+
+@pytest.mark.parametrize("M,P,B,kh,K,per_image", [(32, 1, 128, 3, 5, False), (32, 2, 64, 0, 4, False), (64, 1, 64, 5, 3, True)])
+def test_emu_small_plane_persistent_kernel(emu, M, P, B, kh, K, per_image):
+    """k_small (kernels_small.cuh): planes of 32^2 / 64^2 / 128^2 with >= 64 plane pairs run all iterations inside one
+    persistent kernel per pair.  Against the fp64 oracle, and bit-identical to... the two-launch path only to rounding
+    (different pass order), so both are compared with the oracle; per-image PSFs / parameters (groups = B) included."""
+    import numpy as np
+    import harness
+    from admm_deconv_b200 import _lib
+    from oracle import admm_tv_oracle as O
+    be = harness.EmuBackend(emu)
+    y, h, _ = make_case(M, M, P, B, kh, kh, 2100 + M)
+    if not per_image:
+        for flags in (1, 1 | _lib.FLAG_NO_SMALL):
+            r = be.forward(y.numpy(), 0.0041, 0.021, None if h is None else h.numpy()[:, :, 0, 0], False, K, flags=flags)
+            xo = O.tvd_fft_fast(y.float().double(), torch.tensor([0.0041]).float().double(), torch.tensor([0.021]).float().double(),
+                                None if h is None else h.float().double(), False, K)
+            assert rel_l2(torch.from_numpy(r["x"].get()), xo) < 1e-5
+        return
+    rng = np.random.default_rng(3)
+    hs = rng.random((kh, kh, B)); hs /= hs.sum(axis=(0, 1), keepdims=True)
+    lams = 0.002 + 0.004 * rng.random(B); rhos = 0.02 + 0.05 * rng.random(B)
+    x = be.forward_grouped(y.numpy(), lams, rhos, hs, False, K, groups=B)
+    for b in (0, 17, B - 1):
+        xo = O.tvd_fft_fast(y[..., b:b + 1].float().double(), torch.tensor([lams[b]]).float().double(), torch.tensor([rhos[b]]).float().double(),
+                            torch.from_numpy(hs[:, :, b]).float().double().reshape(kh, kh, 1, 1), False, K)
+        assert rel_l2(torch.from_numpy(x[..., b:b + 1]), xo) < 1e-5

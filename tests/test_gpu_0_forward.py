@@ -411,3 +411,44 @@ def test_forward_is_cuda_graph_capturable(iso):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(xg, A.tvd_fft(y, lam, rho, h, iso, 6))     # no atomics on either path: bitwise reproducible
+
+
+@pytest.mark.parametrize("M,P,B,kh,K", [(128, 1, 128, 9, 6), (128, 3, 64, 5, 4), (64, 1, 256, 0, 5), (32, 2, 200, 3, 7)])
+def test_small_plane_persistent_kernel(M, P, B, kh, K):
+    """k_small (kernels_small.cuh): >= 64 plane pairs of 32^2 / 64^2 / 128^2, anisotropic inference: every iteration inside one
+    persistent kernel per pair.  Checked against the fp64 oracle on a sample of images, and against the two-launch path."""
+    from admm_deconv_b200 import _lib
+    d0 = dev()
+    y, h, _ = make_case(M, M, P, B, kh, kh, 2200 + M)
+    yt = A.from_julia(y.float()).to(d0)
+    ht = None if h is None else A.from_julia(h.float()).to(d0)
+    lam = torch.tensor([0.0041], device=d0); rho = torch.tensor([0.021], device=d0)
+    x = A.tvd_fft(yt, lam, rho, ht, False, K)
+    sel = [0, B // 3, B - 1]
+    xo = oracle(y[..., sel], None if h is None else h, 0.0041, 0.021, False, K, fast=True)
+    assert rel_l2(A.to_julia(x.cpu())[..., sel], xo) < TOL
+    x2 = A.admm_layer_call(yt, lam, rho, ht, None, K, False, "identity", 0.0, False, clamp=False) if False else None
+    # the general path on the same input (flag ADMMTV_FLAG_NO_SMALL through the raw ABI)
+    import harness
+    be = harness.GpuBackend(A.load())
+    r = be.forward(y.float().numpy(), 0.0041, 0.021, None if h is None else h.float().numpy()[:, :, 0, 0], False, K, flags=1 | _lib.FLAG_NO_SMALL)
+    assert rel_l2(A.to_julia(x.cpu()), torch.from_numpy(r["x"].get())) < 2e-6
+
+
+def test_small_plane_kernel_per_image_psfs_and_activation():
+    """BASELINE configs[4] shape in miniature: per-image PSFs and (lambda, rho), groups = B, relu1, through k_small."""
+    d0 = dev()
+    M, B, K, k = 128, 96, 5, 7
+    rng = np.random.default_rng(4)
+    ys, hs, lams, rhos, refs = [], [], [], [], []
+    for b in range(B):
+        lams.append(0.002 + 0.004 * float(rng.random())); rhos.append(0.02 + 0.05 * float(rng.random()))
+    y, _, _ = make_case(M, M, 1, B, k, k, 31)
+    hh = rng.random((B, k, k)); hh /= hh.sum(axis=(1, 2), keepdims=True)
+    yt = A.from_julia(y.float()).to(d0)
+    ht = torch.from_numpy(hh).float().reshape(B, 1, k, k).transpose(2, 3).contiguous().to(d0)      # (G,1,kw,kh)
+    x = A.tvd_fft_grouped(yt, torch.tensor(lams, device=d0), torch.tensor(rhos, device=d0), ht, False, K, groups=B, activation="relu1")
+    for b in (0, 40, B - 1):
+        hb = torch.from_numpy(hh[b]).float().double().reshape(k, k, 1, 1)
+        xo = O.ACTIVATIONS["relu1"](oracle(y[..., b:b + 1], hb, lams[b], rhos[b], False, K, fast=True))
+        assert rel_l2(A.to_julia(x.cpu())[..., b:b + 1], xo) < TOL
