@@ -17,7 +17,7 @@ mode = sys.argv[3] if len(sys.argv) > 3 else "fwd"
 iso = len(sys.argv) > 4 and sys.argv[4] == "iso"
 nopsf = len(sys.argv) > 5 and sys.argv[5] == "nopsf"
 w = dict(bench.WORKLOADS[name], iters=iters)
-y, h = bench.make_inputs(w, 1001)
+y, _, h = bench.make_inputs(w, 1001)
 dev = torch.device("cuda:0")
 y = y.to(dev); h = None if nopsf else h.to(dev)
 lam = torch.tensor([0.0041], device=dev); rho = torch.tensor([0.021], device=dev)

@@ -90,7 +90,7 @@ def test_desc_layout_matches_header():
         (dict(N=4097), -3),
         (dict(M=0), -2), (dict(kh=3, kw=0), -2), (dict(kh=65, kw=3, M=64), -2),
         (dict(iters=0), -4),
-        (dict(iso=2), -5), (dict(activation=7), -5), (dict(flags=128), -5),
+        (dict(iso=2), -5), (dict(activation=7), -5), (dict(flags=256), -5), (dict(flags=64 | 128), 0),
     ],
 )
 def test_check_error_codes(lib, kw, code):
