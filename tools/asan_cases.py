@@ -37,3 +37,13 @@ for (M,N,C,B) in [(40,33,3,2),(7,5,5,1)]:
     lib.batch_from_n0f8(M,N,C,B,0,img.ctypes.data,1,C*N,C,M*N*C,dst.ctypes.data)
     assert np.array_equal(np.array(dst), img.transpose(1,2,3,0).astype(np.float32)/np.float32(255))
 print('losses / batch ok')
+
+# round 2: k_small (whole-call persistent kernel, >= 64 plane pairs), per-iteration parameters, isotropic fixed-order norm
+for (M,P,B,k,K) in [(32,1,128,3,3),(64,1,128,0,2)]:
+    y,h,_=make_case(M,M,P,B,k,k,70+M)
+    print('small', M, check_forward(be,y,h,0.02,0.1,False,K), flush=True)
+y,h,_=make_case(32,64,2,2,3,3,81)
+xbar=torch.from_numpy(np.random.default_rng(2).standard_normal((32,64,2,2)))
+for iso in (False, True):
+    print('per-iteration', iso, check_backward(be,y,h,np.array([0.02,0.03,0.04],np.float32),np.array([0.1,0.2,0.15],np.float32),iso,3,xbar,flags=1,tol=1e-5,tol_scalar=2e-4), flush=True)
+print('round-2 cases ok')

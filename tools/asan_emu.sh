@@ -10,6 +10,7 @@ F="-std=c++20 -O1 -g -fsanitize=address -fno-omit-frame-pointer -fPIC -pthread -
 g++ $F -c $ROOT/admm_deconv_b200/csrc/admmtv_api.cu -o api.o &
 g++ $F -c $ROOT/admm_deconv_b200/csrc/loss_api.cu -o loss.o &
 g++ $F -c $ROOT/admm_deconv_b200/csrc/inst_generic.cu -o generic.o &
+g++ $F -c $ROOT/admm_deconv_b200/csrc/inst_small.cu -o small.o &
 for l in 5 6 7 8 9 10 11 12 20 21 22 23 24 25 26 27 28 29 30 31; do
   S=""; case $l in 8|10|11|12|2[1-9]|3[01]) S="-DADMMTV_STUB";; esac
   g++ $F $S -DADMMTV_INST=$l -c $ROOT/admm_deconv_b200/csrc/inst_dim1.cu -o d1_$l.o &

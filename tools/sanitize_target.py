@@ -48,3 +48,22 @@ for resident in (False, True):
     bx, by = f.getindex([2, 0, 1])
     torch.cuda.synchronize()
     print("feeder", resident, float(bx.mean()))
+# round 2: TMA-pipelined dim-2 pass (training forward at N = 512), per-iteration parameters, k_small, host-buffer session
+y = torch.rand(2, 1, 512, 64, device=dev, requires_grad=True)
+h = (torch.rand(1, 1, 3, 3, device=dev) / 9).requires_grad_(True)
+lam = torch.full((3,), 0.02, device=dev, requires_grad=True); rho = torch.full((3,), 0.1, device=dev, requires_grad=True)
+x = A.admm_layer_call(y, lam, rho, h, None, 3, False, "identity", 0.0)
+x.sum().backward()
+torch.cuda.synchronize()
+print("tma + per-iteration ok", float(x.mean()), lam.grad.tolist(), flush=True)
+for (M, Bs) in ((32, 130), (64, 128)):
+    with torch.no_grad():
+        ys = torch.rand(Bs, 1, M, M, device=dev)
+        xs_ = A.tvd_fft(ys, torch.tensor([0.02], device=dev), torch.tensor([0.1], device=dev), torch.rand(1, 1, 3, 3, device=dev) / 9, False, 4)
+    torch.cuda.synchronize()
+    print("k_small ok", M, float(xs_.mean()), flush=True)
+sess = A.host.HostSession(64, 32, 1, 2, 3, 3, iters=3, training=True)
+yc = torch.rand(2, 1, 32, 64).pin_memory(); tc = torch.rand(2, 1, 32, 64).pin_memory()
+g, l = sess.train_step(yc, tc, torch.tensor([0.02]), torch.tensor([0.1]), torch.rand(1, 1, 3, 3) / 9)
+sess.close()
+print("host session ok", float(l), flush=True)
