@@ -103,6 +103,9 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_PF_NEXT
 #define ADMMTV_PF_NEXT 0  // L2 prefetch for the block that takes over the SM slot next (distance in blocks); measured SLOWER (cfg2: dim2 99 -> 136 us at 444), kept off
 #endif
+#ifndef ADMMTV_PF_NEXT2_11
+#define ADMMTV_PF_NEXT2_11 0  // the same for the dim-2 kernel at N = 2048 (one 128 KB block per SM: nothing else hides its loads)
+#endif
 #ifndef ADMMTV_PRELOAD1
 #define ADMMTV_PRELOAD1 1
 #endif
@@ -1032,9 +1035,10 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
     if (SMACC && first_of_run) {
       for (int t = tid; t < N * TR; t += NT) gsm[t] = 0.f;  // ordered before its first use by the barriers of the forward passes
     }
-    if (ADMMTV_PF_NEXT > 0 && gridDim.y == (unsigned)A.Q) {
+    constexpr int PFN = LN == 11 ? ADMMTV_PF_NEXT2_11 : ADMMTV_PF_NEXT;
+    if (PFN > 0 && gridDim.y == (unsigned)A.Q) {
       // the input tile of the block that takes over this SM slot next
-      const long nid = (long)blockIdx.y * gridDim.x + blockIdx.x + ADMMTV_PF_NEXT;
+      const long nid = (long)blockIdx.y * gridDim.x + blockIdx.x + PFN;
       if (nid < (long)gridDim.x * gridDim.y) {
         const float2* nxt = A.in + (size_t)(nid / gridDim.x) * N * M + (size_t)(nid % gridDim.x) * TR;
         for (int col = tid; col < N; col += NT) l2_prefetch_line(nxt + (size_t)col * M);

@@ -350,8 +350,10 @@ def timed(c, fn, steps, warmup, clocks=True, min_ms=0.0):
 class TrainStep:
     """forward (checkpointed) + MSE + backward + gradient all-reduce on resident inputs: admmtv_mse_train_step."""
 
-    def __init__(self, c, w, B, seed):
+    def __init__(self, c, w, B, seed, graph=False):
         import torch
+        self.graph = None
+        self.want_graph = graph
         import admm_deconv_b200 as A
         from admm_deconv_b200 import _lib
 
@@ -377,12 +379,35 @@ class TrainStep:
         self.px = B * w["P"] * w["N"] * w["M"]
         self.launches = self.lib.forward_launches(self.d, True) + 1 + self.lib.backward_launches(self.d)
 
-    def __call__(self):
+    def _enqueue(self):
         import torch
         st = torch.cuda.current_stream().cuda_stream
         p = lambda t: t.data_ptr()
         self.lib.mse_train_step(self.d, p(self.y), p(self.g), p(self.h), p(self.lam), p(self.rho), None, p(self.x), p(self.xbar),
                                 p(self.ybar), p(self.grads), p(self.loss), p(self.ws_f), p(self.ck), p(self.ws_b), st)
+
+    def capture(self):
+        """Launch-bound shares (strong scaling): the step's ~55 stream-ordered launches are captured once in a CUDA graph and
+        replayed (the library only enqueues kernels and memsets on the caller's stream; the TMA descriptors are by-value
+        kernel parameters).  The all-reduce stays outside the graph."""
+        import torch
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._enqueue()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+
+    def __call__(self):
+        if self.want_graph and self.graph is None:
+            self.capture()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
         if self.c.world > 1:
             self.c.dist.all_reduce(self.grads)      # [hbar | lambdabar | rhobar]: ONE packed NCCL all-reduce over NVLink
 
@@ -507,12 +532,16 @@ def run_fwd(c, w, name, steps, warmup, e2e=True, min_ms=0.0):
     return r
 
 
+args_graph = None   # --graph 0/1 overrides the default (CUDA-graph replay of the step when the per-GPU share is below 16 Mpx)
+
+
 def run_train(c, w, name, steps, warmup, full, min_ms=0.0):
     """fwd+bwd workloads.  full: roofline + e2e + launch count (the headline); else a short `others` entry."""
     import torch
 
     B = w["B"] // c.world if w.get("strong") else w["B"]
-    ts = TrainStep(c, w, B, 1001 + c.rank)
+    use_graph = bool(args_graph) if args_graph is not None else (B * w["P"] * w["N"] * w["M"] < (16 << 20))
+    ts = TrainStep(c, w, B, 1001 + c.rank, graph=use_graph)
     ms, clk, steps = timed(c, ts, steps, warmup, min_ms=min_ms)
     pk, pk_src = peaks()
     K = w["iters"]
@@ -521,7 +550,7 @@ def run_train(c, w, name, steps, warmup, full, min_ms=0.0):
          "ms_per_step": ms, "value": px_all * K / (ms * 1e-3) / 1e6, "unit": UNIT,
          "algorithmic_bytes_per_plane_pixel_iteration": alg_bytes(w),
          "frac": alg_bytes(w) * ts.px * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "clocks": clk,
-         "per_gpu_batch": B, "collective": "one packed NCCL all-reduce of %d floats per step" % ts.ngrad if c.world > 1 else None}
+         "per_gpu_batch": B, "cuda_graph": use_graph, "collective": "one packed NCCL all-reduce of %d floats per step" % ts.ngrad if c.world > 1 else None}
     r["config"]["per_gpu_batch"] = B
     if not full:
         del ts
@@ -630,7 +659,10 @@ def main():
     ap.add_argument("--workload", default="cfg2_train", choices=sorted(WORKLOADS))
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--graph", type=int, default=None, choices=[0, 1], help="force CUDA-graph replay of the training step off / on")
     args = ap.parse_args()
+    global args_graph
+    args_graph = args.graph
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w, args.workload)
