@@ -38,6 +38,7 @@ SYMBOLS = (
     "admmtv_backward_launches",
     "admmtv_forward_ex",
     "admmtv_backward_ex",
+    "admmtv_backward_mse",
 )
 # every symbol include/admmtv_loss.h declares
 LOSS_SYMBOLS = (
@@ -116,6 +117,7 @@ class AdmmTvLib:
         L.admmtv_backward.argtypes = [C.POINTER(Desc)] + [vp] * 14
         L.admmtv_forward_ex.argtypes = [C.POINTER(Desc)] + [vp] * 9 + [C.POINTER(Hooks)]
         L.admmtv_backward_ex.argtypes = [C.POINTER(Desc)] + [vp] * 14 + [C.POINTER(Hooks)]
+        L.admmtv_backward_mse.argtypes = [C.POINTER(Desc)] + [vp] * 15
         L.admmtv_profile_forward.argtypes = [C.POINTER(Desc)] + [vp] * 10
         L.admmtv_profile_backward.argtypes = [C.POINTER(Desc)] + [vp] * 15
         L.admmtv_forward_host.argtypes = [C.POINTER(Desc)] + [vp] * 6
@@ -143,7 +145,7 @@ class AdmmTvLib:
             L.admmtv_host_grad_floats.argtypes = [C.POINTER(Desc)]
             L.admmtv_host_wait.argtypes = [vp, i]
             L.admmtv_host_launches.argtypes = [vp, i]
-            L.admmtv_mse_train_step.argtypes = [C.POINTER(Desc)] + [vp] * 15 + [C.POINTER(Hooks)]
+            L.admmtv_mse_train_step.argtypes = [C.POINTER(Desc)] + [vp] * 14 + [C.POINTER(Hooks)]
         for name in SYMBOLS + LOSS_SYMBOLS + BATCH_SYMBOLS + (HOST_SYMBOLS if self.has_host else ()):
             getattr(L, name)  # AttributeError if a declared symbol is not exported
 
@@ -171,6 +173,10 @@ class AdmmTvLib:
     def backward(self, d: Desc, xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar, biasbar, ws, stream=0):
         self._raise(self.lib.admmtv_backward(C.byref(d), xbar, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar,
                                              biasbar, ws, stream))
+
+    def backward_mse(self, d: Desc, target, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar, biasbar, loss_sum, ws, stream=0):
+        self._raise(self.lib.admmtv_backward_mse(C.byref(d), target, x_out, y, h, lam, rho, ckpt, ybar, hbar, lambar, rhobar,
+                                                 biasbar, loss_sum, ws, stream))
 
     def forward_ex(self, d: Desc, y, h, lam, rho, bias, x_out, ws, ckpt, stream, hooks: "Hooks"):
         self._raise(self.lib.admmtv_forward_ex(C.byref(d), y, h, lam, rho, bias, x_out, ws, ckpt, stream, C.byref(hooks)))
@@ -233,9 +239,9 @@ class AdmmTvLib:
         self._raise(self.lib.admmtv_host_train_step_enqueue(sess, slot, y, target, h, lam, rho, bias, grads_out, loss_out, ybar_out,
                                                             None if hooks is None else C.byref(hooks)))
 
-    def mse_train_step(self, d: Desc, y, target, h, lam, rho, bias, x_out, xbar, ybar, grads, loss_sum, ws_fwd, ckpt, ws_bwd,
+    def mse_train_step(self, d: Desc, y, target, h, lam, rho, bias, x_out, ybar, grads, loss_sum, ws_fwd, ckpt, ws_bwd,
                        stream=0, hooks=None):
-        self._raise(self.lib.admmtv_mse_train_step(C.byref(d), y, target, h, lam, rho, bias, x_out, xbar, ybar, grads, loss_sum,
+        self._raise(self.lib.admmtv_mse_train_step(C.byref(d), y, target, h, lam, rho, bias, x_out, ybar, grads, loss_sum,
                                                    ws_fwd, ckpt, ws_bwd, stream, None if hooks is None else C.byref(hooks)))
 
     def host_grad_floats(self, d: Desc) -> int:

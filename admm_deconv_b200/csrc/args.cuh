@@ -58,7 +58,10 @@ struct PackArgs {
   const float* xout;   // MODE 1
   float2* spec;        // [Q][N][M]
   const float2* twM;
-  double* bias_acc;    // MODE 1, may be null: biasbar slot of group 0 (groups are acc_stride apart)
+  const float* target; // MODE 3: the cotangent is formed on the fly, xbar = mse_scale (x_out - target)  (MSE loss pullback seed)
+  float mse_scale;     //         2 / numel
+  double* loss_acc;    //         += sum (x_out - target)^2
+  double* bias_acc;    // MODE 1 / 3, may be null: biasbar slot of group 0 (groups are acc_stride apart)
   int acc_stride;      // doubles between the groups' accumulator blocks
   PlaneMap pm;
   int N, S, act;
@@ -99,8 +102,10 @@ struct Dim2Args {
   const float2* ktab;  // MUL 1/2: complex table [N][M] (2 = use its conjugate)
   float2* zsave;       // SAVE_Z: [Q][N][M] full spectrum before the multiply
   const float2* z2;    // ACC: second spectrum [Q][N][M]
-  double* gacc;        // ACC 1: double [N][M] += Re(conj(Z) Z2) ; ACC 2: double2 [N][M] += conj(Z) Z2  (fp64: hundreds of
-                       //        partial sums meet here; in fp32 their rounding would set the error of hbar / rhobar)
+  double* gacc;        // ACC 1: double [N][M] += Re(conj(Z) Z2): fp64, K x (pairs / block) partial sums meet here, one
+                       //        atomic per element and block after the shared-memory pre-sum
+  float2* pacc;        // ACC 2: float2 [N][M] += conj(Z) Z2: one launch, one term per pair and element; fp64 atomics made
+                       //        this pass 210 -> 290 us without moving hbar (its floor is the fp32 rounding of the spectra)
   const float2* twN;
   int M;
   int Q;               // number of plane pairs (blocks loop q = blockIdx.y, += gridDim.y)

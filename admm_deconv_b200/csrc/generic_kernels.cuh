@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(GK_NT) gk_dim2(Dim2Args A, GDim2Cfg C) {
       const float re = z.x * z2.x + z.y * z2.y, im = z.x * z2.y - z.y * z2.x;  // conj(Z) Z2
       if (C.acc == 1) atomicAdd(A.gacc + toff + g, (double)re);
       else {
-        atomicAdd(A.gacc + 2 * (toff + g), (double)re);
-        atomicAdd(A.gacc + 2 * (toff + g) + 1, (double)im);
+        atomicAdd(reinterpret_cast<float*>(A.pacc + toff + g), re);
+        atomicAdd(reinterpret_cast<float*>(A.pacc + toff + g) + 1, im);
       }
     }
     if (!C.fwd_only) {
@@ -255,17 +255,24 @@ ADMMTV_DI bool gk_pix(size_t idx, int M, int N, int Q, Pix& p) {
 __global__ void __launch_bounds__(GK_NT) gk_pack(PackArgs A, int M, int Q, int mode) {
   const size_t idx = (size_t)blockIdx.x * GK_NT + threadIdx.x;
   Pix p;
-  double bsum = 0.0;
+  double bsum = 0.0, lsum = 0.0;
   int grp = 0;
   if (gk_pix(idx, M, A.N, Q, p)) {
     grp = p.q / A.pm.Qg;
     if (mode == 2) A.spec[idx] = A.src_packed[idx];
     else {
-      const long ia = mode == 1 ? pm_out(A.pm, p.q, 0) : pm_in(A.pm, p.q, 0);
-      const long ib = mode == 1 ? pm_out(A.pm, p.q, 1) : pm_in(A.pm, p.q, 1);
-      float va = A.src[(size_t)ia * p.plane + p.o], vb = ib >= 0 ? A.src[(size_t)ib * p.plane + p.o] : 0.f;
+      const bool cot = mode == 1 || mode == 3;
+      const long ia = cot ? pm_out(A.pm, p.q, 0) : pm_in(A.pm, p.q, 0);
+      const long ib = cot ? pm_out(A.pm, p.q, 1) : pm_in(A.pm, p.q, 1);
+      const float* srcp = mode == 3 ? A.target : A.src;
+      float va = srcp[(size_t)ia * p.plane + p.o], vb = ib >= 0 ? srcp[(size_t)ib * p.plane + p.o] : 0.f;
       if (mode == 0 && A.packed_out) A.packed_out[idx] = make_float2(va, vb);
-      if (mode == 1) {
+      if (mode == 3) {   // xbar = mse_scale (x_out - target), loss += (x_out - target)^2
+        const float da = A.xout[(size_t)ia * p.plane + p.o] - va, db = ib >= 0 ? A.xout[(size_t)ib * p.plane + p.o] - vb : 0.f;
+        lsum = (double)(da * da + db * db);
+        va = A.mse_scale * da; vb = A.mse_scale * db;
+      }
+      if (cot) {
         va *= act_grad_from_out(A.xout[(size_t)ia * p.plane + p.o], A.act);
         if (ib >= 0) vb *= act_grad_from_out(A.xout[(size_t)ib * p.plane + p.o], A.act);
         bsum = (double)va + (double)vb;
@@ -273,7 +280,11 @@ __global__ void __launch_bounds__(GK_NT) gk_pack(PackArgs A, int M, int Q, int m
       A.spec[idx] = make_float2(va, vb);
     }
   }
-  if (mode == 1 && A.bias_acc) {
+  if (mode == 3) {
+    const double tot = block_sum(lsum);
+    if (threadIdx.x == 0) atomicAdd(A.loss_acc, tot);
+  }
+  if ((mode == 1 || mode == 3) && A.bias_acc) {
     // one atomic per block when the whole block lies in one group, else (at most G-1 blocks) one per thread
     const size_t per_group = (size_t)A.pm.Qg * M * A.N, first = (size_t)blockIdx.x * GK_NT;
     size_t last = first + GK_NT - 1;

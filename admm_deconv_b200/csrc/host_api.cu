@@ -11,36 +11,6 @@ namespace {
 
 inline size_t al256(size_t n) { return (n + 255) & ~size_t(255); }
 
-// loss = mean((x - t)^2) ; xbar = 2 (x - t) / n   (the MSE pullback seed of train.jl:51-53)
-__global__ void __launch_bounds__(256) k_mse_cotangent(const float* __restrict__ x, const float* __restrict__ t,
-                                                       float* __restrict__ xbar, size_t n, float scale, double* loss_acc) {
-  double acc = 0.0;
-  const size_t n4 = n / 4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 a = reinterpret_cast<const float4*>(x)[i], b = reinterpret_cast<const float4*>(t)[i];
-    const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
-    reinterpret_cast<float4*>(xbar)[i] = make_float4(scale * d.x, scale * d.y, scale * d.z, scale * d.w);
-    acc += (double)(d.x * d.x + d.y * d.y) + (double)(d.z * d.z + d.w * d.w);
-  }
-  if (blockIdx.x == 0) {
-    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
-      const float d = x[i] - t[i];
-      xbar[i] = scale * d;
-      acc += (double)d * d;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __shared__ double red[8];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    atomicAdd(loss_acc, s);
-  }
-}
-
 struct Slot {
   float *y, *target, *x;       // device
   cudaEvent_t in_ready, compute_done, out_done;
@@ -61,7 +31,7 @@ struct admmtv_host_session {
   cudaStream_t copy_in, compute, copy_out;
   Slot slot[2];
   float *h, *lambda, *rho, *bias;   // device parameters
-  float *xbar, *ybar, *packed;      // training
+  float *ybar, *packed;             // training
   double* loss_acc;                 // device
   double* loss_host[2];             // pinned
   void *ws_fwd, *ws_bwd, *ckpt;
@@ -71,7 +41,7 @@ struct admmtv_host_session {
 namespace {
 
 struct Layout {
-  size_t y[2], t[2], x[2], h, lam, rho, bias, xbar, ybar, packed, loss, ws_fwd, ws_bwd, ckpt, total;
+  size_t y[2], t[2], x[2], h, lam, rho, bias, ybar, packed, loss, ws_fwd, ws_bwd, ckpt, total;
 };
 
 inline int param_entries(const admmtv_desc* d) { return (d->flags & ADMMTV_FLAG_PER_ITER_PARAMS) ? d->iters : 1; }
@@ -99,7 +69,6 @@ int plan(const admmtv_desc* d, int training, Layout& L, size_t& in_img, size_t& 
   L.lam = take((size_t)G * PS * 4);
   L.rho = take((size_t)G * PS * 4);
   L.bias = take((size_t)G * 4);
-  L.xbar = take(training ? out_img * 4 : 0);
   L.ybar = take(training ? in_img * 4 : 0);
   L.packed = take((size_t)ngrad * 4);
   L.loss = take(16);
@@ -213,7 +182,6 @@ int admmtv_host_session_create(const admmtv_desc* d, int training, void* device_
   s->lambda = reinterpret_cast<float*>(s->arena + L.lam);
   s->rho = reinterpret_cast<float*>(s->arena + L.rho);
   s->bias = reinterpret_cast<float*>(s->arena + L.bias);
-  s->xbar = reinterpret_cast<float*>(s->arena + L.xbar);
   s->ybar = reinterpret_cast<float*>(s->arena + L.ybar);
   s->packed = reinterpret_cast<float*>(s->arena + L.packed);
   s->loss_acc = reinterpret_cast<double*>(s->arena + L.loss);
@@ -256,7 +224,7 @@ int admmtv_host_unpin(void* p) {
 int admmtv_host_launches(const admmtv_host_session* s, int training) {
   if (!s) return 0;
   int n = admmtv_forward_launches(&s->d, training);
-  if (training) n += 1 + admmtv_backward_launches(&s->d);
+  if (training) n += admmtv_backward_launches(&s->d);
   return n;
 }
 
@@ -306,7 +274,7 @@ int admmtv_host_train_step_enqueue(admmtv_host_session* s, int slot, const float
   int rc = upload_params(s, h, lambda, rho, bias);
   if (rc) return rc;
   if ((rc = admmtv_mse_train_step(&s->d, sl.y, sl.target, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho,
-                                  s->d.has_bias ? s->bias : nullptr, sl.x, s->xbar, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
+                                  s->d.has_bias ? s->bias : nullptr, sl.x, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
                                   s->ckpt, s->ws_bwd, s->compute, hooks)))
     return rc;
   HCHECK(cudaMemcpyAsync(grads_out, s->packed, (size_t)s->ngrad * 4, cudaMemcpyDeviceToHost, s->compute));
@@ -327,31 +295,23 @@ int admmtv_host_train_step_enqueue(admmtv_host_session* s, int slot, const float
 }
 
 int admmtv_mse_train_step(const admmtv_desc* d, const float* y, const float* target, float* h, float* lambda, float* rho,
-                          const float* bias, float* x_out, float* xbar, float* ybar, float* grads_packed, double* loss_sum,
+                          const float* bias, float* x_out, float* ybar, float* grads_packed, double* loss_sum,
                           void* ws_fwd, void* ckpt, void* ws_bwd, void* stream, const admmtv_hooks* hooks) {
   int rc = admmtv_check(d);
   if (rc) return rc;
-  if (!y || !target || !lambda || !rho || !x_out || !xbar || !ybar || !grads_packed || !loss_sum || !ws_fwd || !ckpt || !ws_bwd)
+  if (!y || !target || !lambda || !rho || !x_out || !ybar || !grads_packed || !loss_sum || !ws_fwd || !ckpt || !ws_bwd)
     return ADMMTV_ERR_NULL;
   DevGuard guard(d->device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int G = d->groups > 1 ? d->groups : 1, nh = d->kh * d->kw, PS = param_entries(d);
   if ((rc = admmtv_forward(d, y, h, lambda, rho, bias, x_out, ws_fwd, ckpt, stream))) return rc;
-  HCHECK(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
-  {
-    const size_t n = (size_t)d->M * d->N * d->P * d->B;
-    const size_t want = (n / 4 + 255) / 256 + 1;
-    const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
-    k_mse_cotangent<<<blocks, 256, 0, st>>>(x_out, target, xbar, n, 2.0f / (float)n, loss_sum);
-    HCHECK(cudaGetLastError());
-  }
+  // loss = mean((x - target)^2): its pullback seed 2 (x - target) / numel is formed inside the backward's first kernel
   float* hbar = grads_packed;
   float* lbar = grads_packed + (size_t)nh * G;
   float* rbar = lbar + (size_t)G * PS;
   float* bbar = d->has_bias ? rbar + (size_t)G * PS : nullptr;
-  if ((rc = admmtv_backward(d, xbar, x_out, y, h, lambda, rho, ckpt, ybar, nh > 0 ? hbar : nullptr, lbar, rbar, bbar, ws_bwd,
-                            stream)))
+  if ((rc = admmtv_backward_mse(d, target, x_out, y, h, lambda, rho, ckpt, ybar, nh > 0 ? hbar : nullptr, lbar, rbar, bbar, loss_sum,
+                                ws_bwd, stream)))
     return rc;
   if (hooks && hooks->allreduce_sum) {   // the data-parallel gradient all-reduce, stream-ordered
     const size_t ng = (size_t)nh * G + 2 * (size_t)G * PS + (d->has_bias ? G : 0);

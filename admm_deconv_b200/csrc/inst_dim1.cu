@@ -47,6 +47,7 @@ template <>
 int Dim1Launch<LM>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {
   if (mode == 0) return launch_k(k_pack_fft1<LM, 0>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
   if (mode == 1) return launch_k(k_pack_fft1<LM, 1>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+  if (mode == 3) return launch_k(k_pack_fft1<LM, 3>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
   return launch_k(k_pack_fft1<LM, 2>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
 }
 template <>

@@ -366,6 +366,8 @@ ADMMTV_DI void dim1_fft_from_smem(float2* X, int ncols, ColPtr colptr, const flo
 //   MODE 0: src = y                                  (ops.jl:101 permute + first rfft pass)
 //   MODE 1: src = xbar * act'(x_out); accumulates biasbar (deconv_admm.jl:222-224 pullback)
 //   MODE 2: src = already pair-packed spatial data (b = H^T y -> first x-update input)
+//   MODE 3: MODE 1 with the cotangent of the mean-squared-error loss formed on the fly: xbar = mse_scale (x_out - target);
+//           also accumulates the loss (admmtv_backward_mse: no xbar array, no separate loss kernel)
 // ------------------------------------------------------------------------------------------
 
 template <int LM, int MODE>
@@ -380,12 +382,14 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   // MODE 1 reads the layer OUTPUT's cotangent, so it uses the output plane map
-  const long ia = MODE == 1 ? pm_out(A.pm, q, 0) : pm_in(A.pm, q, 0);
-  const long ib = MODE == 1 ? pm_out(A.pm, q, 1) : pm_in(A.pm, q, 1);
+  constexpr bool COT = MODE == 1 || MODE == 3;   // reads the layer OUTPUT's cotangent
+  const long ia = COT ? pm_out(A.pm, q, 0) : pm_in(A.pm, q, 0);
+  const long ib = COT ? pm_out(A.pm, q, 1) : pm_in(A.pm, q, 1);
   const bool has_b = ib >= 0;
-  const float* pa = A.src + (size_t)ia * plane;
-  const float* pb = A.src + (size_t)(has_b ? ib : 0) * plane;
-  double bsum = 0.0;
+  const float* srcp = MODE == 3 ? A.target : A.src;
+  const float* pa = srcp + (size_t)ia * plane;
+  const float* pb = srcp + (size_t)(has_b ? ib : 0) * plane;
+  double bsum = 0.0, lsum = 0.0;
   // 4 rows per thread: float4 loads from each plane (M is a multiple of 32)
   for (int e = tid; e < nout * (M / 4); e += NT) {
     const int c = e / (M / 4), i = (e % (M / 4)) * 4;
@@ -407,10 +411,21 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
       po[0] = make_float4(va[0], vb[0], va[1], vb[1]);
       po[1] = make_float4(va[2], vb[2], va[3], vb[3]);
     }
-    if (MODE == 1) {
+    if (COT) {
       const float4 oa = *reinterpret_cast<const float4*>(A.xout + (size_t)ia * plane + off);
       const float4 ob = has_b ? *reinterpret_cast<const float4*>(A.xout + (size_t)ib * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float xa[4] = {oa.x, oa.y, oa.z, oa.w}, xb[4] = {ob.x, ob.y, ob.z, ob.w};
+      if (MODE == 3) {
+        float l = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float da = xa[t] - va[t], db = has_b ? xb[t] - vb[t] : 0.f;
+          l += da * da + db * db;
+          va[t] = A.mse_scale * da;
+          vb[t] = A.mse_scale * db;
+        }
+        lsum += (double)l;
+      }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         va[t] *= act_grad_from_out(xa[t], A.act);
@@ -421,9 +436,13 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) X[sidx<LM>(c, i + t)] = make_float2(va[t], vb[t]);
   }
-  if (MODE == 1 && A.bias_acc) {
+  if (COT && A.bias_acc) {
     const double tot = block_sum(bsum);
     if (tid == 0) atomicAdd(A.bias_acc + (size_t)A.acc_stride * (q / A.pm.Qg), tot);  // biasbar slot of this pair's group
+  }
+  if (MODE == 3) {
+    const double tot = block_sum(lsum);
+    if (tid == 0) atomicAdd(A.loss_acc, tot);
   }
   __syncthreads();
   float2* sq = A.spec + (size_t)q * plane;
@@ -921,10 +940,11 @@ ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, siz
             gv.y += re1;
             *gp = gv;
           } else {
-            atomicAdd(A.gacc + 2 * (toff + g), (double)re0);
-            atomicAdd(A.gacc + 2 * (toff + g) + 1, (double)im0);
-            atomicAdd(A.gacc + 2 * (toff + g) + 2, (double)re1);
-            atomicAdd(A.gacc + 2 * (toff + g) + 3, (double)im1);
+            float* pa = reinterpret_cast<float*>(A.pacc + toff + g);
+            atomicAdd(pa, re0);
+            atomicAdd(pa + 1, im0);
+            atomicAdd(pa + 2, re1);
+            atomicAdd(pa + 3, im1);
           }
         }
         if (!FWD_ONLY) {
@@ -966,8 +986,9 @@ ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, siz
           const float re = a[m].x * z2.x + a[m].y * z2.y, im = a[m].x * z2.y - a[m].y * z2.x;   // conj(Z) * Z2
           if (SMACC) gsm[(wi * StL::R + m) * TR + r] += re;
           else {
-            atomicAdd(A.gacc + 2 * (toff + g), (double)re);
-            atomicAdd(A.gacc + 2 * (toff + g) + 1, (double)im);
+            float* pa = reinterpret_cast<float*>(A.pacc + toff + g);
+            atomicAdd(pa, re);
+            atomicAdd(pa + 1, im);
           }
         }
         if (!FWD_ONLY) {

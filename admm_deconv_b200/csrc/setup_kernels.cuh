@@ -189,7 +189,7 @@ static __global__ void k_iso_coef(const float* __restrict__ part, int Qg, const 
 // ------------------------------------------------------------------------------------------
 // gacc and ctab hold one table per parameter entry ([G][PS][N][M]): Sbar_i from (G_i, C_i); rhobar_i gets its own spectral
 // term; the cotangent of |Sigma|^2 is their sum.
-static __global__ void k_grad_tables(const double* __restrict__ gacc, const double2* __restrict__ pacc,
+static __global__ void k_grad_tables(const double* __restrict__ gacc, const float2* __restrict__ pacc,
                                      const float* __restrict__ ctab, const float2* __restrict__ sig, int kh, int kw,
                                      int M, int N, int use_spatial, double2* Wn, double* acc, int planned, int PS, int AS) {
   const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,7 +225,7 @@ static __global__ void k_grad_tables(const double* __restrict__ gacc, const doub
       const int pd = (kh - 1) / 2, pr = (kw - 1) / 2;
       double ps, pc;
       sincospi(2.0 * ((double)((long long)k1 * pd % M) / M + (double)((long long)k2 * pr % N) / N), &ps, &pc);
-      const double pr_ = pacc[idx].x / mn, pi_ = pacc[idx].y / mn;
+      const double pr_ = (double)pacc[idx].x / mn, pi_ = (double)pacc[idx].y / mn;
       // P * (pc - i ps)
       wr += pr_ * pc + pi_ * ps;
       wi += pi_ * pc - pr_ * ps;

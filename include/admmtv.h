@@ -125,6 +125,14 @@ int admmtv_backward(const admmtv_desc* desc, const float* xbar, const float* x_o
                     float* ybar, float* hbar, float* lambdabar, float* rhobar, float* biasbar,
                     void* workspace, void* stream);
 
+/* Backward with the mean-squared-error loss fused in (train.jl:51-53 with loss = mean((m(x) - target)^2)): the cotangent
+ * xbar = 2 (x_out - target) / numel is formed inside the first kernel and loss_sum[0] = sum((x_out - target)^2) (fp64, device;
+ * the caller divides by numel) -- no xbar array and no separate loss kernel.  Everything else as admmtv_backward. */
+int admmtv_backward_mse(const admmtv_desc* desc, const float* target, const float* x_out, const float* y,
+                        const float* h, const float* lambda, const float* rho, const void* ckpt,
+                        float* ybar, float* hbar, float* lambdabar, float* rhobar, float* biasbar,
+                        double* loss_sum, void* workspace, void* stream);
+
 /* ---- cross-rank isotropic coupling (EXTENSION) --------------------------------------
  * The reference's isotropic norm spans every image of the call (ops.jl:6,10).  When the batch is sharded over
  * several GPUs, admmtv_forward / admmtv_backward use each shard's own norm.  The _ex entry points restore the

@@ -61,11 +61,12 @@ int admmtv_host_grad_floats(const admmtv_desc* desc);
 
 /* Device-pointer twin of the training step above (inputs already resident in HBM; every pointer is a DEVICE pointer,
  * caller-owned, stream-ordered on `stream`, returns after enqueueing): admmtv_forward with checkpoint ->
- * loss_sum[0] = sum((x - target)^2) (fp64; the caller divides by numel), xbar = 2 (x - target) / numel -> admmtv_backward
- * -> [hooks->allreduce_sum(grads_packed)].  xbar: (M,N,P,B) scratch; ybar: (M,N,P,B) cotangent of y; grads_packed as
- * grads_out above.  This is the step bench.py times with resident inputs; the host session calls exactly this. */
+ * admmtv_backward_mse (the pullback seed 2 (x - target) / numel is formed inside its first kernel; loss_sum[0] =
+ * sum((x - target)^2) in fp64, the caller divides by numel) -> [hooks->allreduce_sum(grads_packed)].
+ * ybar: (M,N,P,B) cotangent of y; grads_packed as grads_out above.  This is the step bench.py times with resident
+ * inputs; the host session calls exactly this. */
 int admmtv_mse_train_step(const admmtv_desc* desc, const float* y, const float* target, float* h, float* lambda,
-                          float* rho, const float* bias, float* x_out, float* xbar, float* ybar, float* grads_packed,
+                          float* rho, const float* bias, float* x_out, float* ybar, float* grads_packed,
                           double* loss_sum, void* ws_fwd, void* ckpt, void* ws_bwd, void* stream,
                           const admmtv_hooks* hooks);
 

@@ -135,6 +135,25 @@ class Backend:
         self.sync()
         return {k: (None if v is None else v.get()) for k, v in out.items()}
 
+    def backward_mse(self, fwd, target):
+        """admmtv_backward_mse: the MSE cotangent 2 (x - target) / numel is formed inside the first kernel; also returns the loss."""
+        d = fwd["desc"]
+        M, N, P, B = d.M, d.N, d.P, d.B
+        tb = self.buf(f32(target))
+        ws = self.zeros((fwd["bwd_bytes"],), np.uint8)
+        loss = self.zeros((1,), np.float64)
+        out = dict(ybar=self.zeros((M, N, P, B)), hbar=None if fwd["h"] is None else self.zeros(fwd["h"].shape),
+                   lambar=self.zeros(fwd["lam"].shape), rhobar=self.zeros(fwd["rho"].shape),
+                   biasbar=None if fwd["bias"] is None else self.zeros((1,)))
+        p = lambda b: None if b is None else b.ptr
+        self.lib.backward_mse(d, tb.ptr, fwd["x"].ptr, fwd["y"].ptr, p(fwd["h"]), fwd["lam"].ptr, fwd["rho"].ptr, fwd["ckpt"].ptr,
+                              out["ybar"].ptr, p(out["hbar"]), out["lambar"].ptr, out["rhobar"].ptr, p(out["biasbar"]), loss.ptr, ws.ptr,
+                              self.stream())
+        self.sync()
+        res = {k: (None if v is None else v.get()) for k, v in out.items()}
+        res["loss"] = float(loss.get()[0]) / (M * N * P * B)
+        return res
+
     def ckpt_states(self, fwd):
         """[(v1_k, v2_k)] for k = 1..K-1 as fp64 torch (M,N,P,B) arrays, read from the checkpoint."""
         d = fwd["desc"]

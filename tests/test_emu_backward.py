@@ -112,3 +112,18 @@ def test_emu_per_iteration_parameters(emu, M, N, P, B, kh, kw, K, iso):
     a = be.forward(y.numpy(), float(lam[0]), float(rho[0]), h.numpy()[:, :, 0, 0], iso, K, flags=1)
     b = be.forward(y.numpy(), np.full(K, lam[0]), np.full(K, rho[0]), h.numpy()[:, :, 0, 0], iso, K, flags=1)
     assert np.array_equal(a["x"].get(), b["x"].get())
+
+
+@pytest.mark.parametrize("M,N,P,B,act", [(32, 64, 3, 1, "relu1"), (33, 17, 1, 2, "identity")])
+def test_emu_backward_mse_equals_backward_with_explicit_cotangent(emu, M, N, P, B, act):
+    """admmtv_backward_mse (MSE pullback seed formed inside the first kernel) == admmtv_backward fed xbar = 2 (x - t) / numel."""
+    be = harness.EmuBackend(emu)
+    y, h, g = make_case(M, N, P, B, 3, 3, 700 + M)
+    f = be.forward(y.numpy(), 0.0041, 0.021, h.numpy()[:, :, 0, 0], False, 4, act=act, bias=0.02, want_ckpt=True)
+    x = f["x"].get().astype(np.float64)
+    t = g.numpy()
+    a = be.backward(f, 2.0 * (x - t.astype(np.float32)) / x.size)
+    b = be.backward_mse(f, t)
+    assert abs(b["loss"] - float(((x - t.astype(np.float32)) ** 2).mean())) <= 1e-6 * b["loss"]
+    for k in ("ybar", "hbar", "lambar", "rhobar", "biasbar"):
+        assert float(np.abs(a[k] - b[k]).max()) <= 2e-6 * float(np.abs(a[k]).max()) + 1e-12, k

@@ -295,3 +295,18 @@ def test_layer_with_per_iteration_parameters_trains():
     # d/d(shared) = sum over the per-iteration entries
     assert abs(float(layer.rho.grad.sum()) - float(ref.rho.grad)) <= 2e-4 * abs(float(ref.rho.grad))
     assert abs(float(layer.lam.grad.sum()) - float(ref.lam.grad)) <= 2e-4 * abs(float(ref.lam.grad))
+
+
+@pytest.mark.parametrize("M,N,P,B,act,iso", [(64, 64, 3, 2, "relu1", False), (512, 128, 1, 2, "identity", False), (100, 60, 3, 1, "relu6", False), (128, 128, 3, 2, "identity", True)])
+def test_backward_mse_equals_backward_with_explicit_cotangent(be, M, N, P, B, act, iso):
+    """admmtv_backward_mse (MSE pullback seed formed inside the first kernel, loss accumulated there) == admmtv_backward fed
+    xbar = 2 (x - t) / numel; this is the call bench.py's training step and the host-buffer session make."""
+    y, h, g = make_case(M, N, P, B, 5, 5, 700 + M)
+    f = be.forward(y.numpy(), 0.0041, 0.021, h.numpy()[:, :, 0, 0], iso, 6, act=act, bias=0.02, want_ckpt=True)
+    x = f["x"].get()
+    t = g.numpy().astype(np.float32)
+    a = be.backward(f, (2.0 * (x.astype(np.float64) - t) / x.size).astype(np.float32))
+    b = be.backward_mse(f, t)
+    assert abs(b["loss"] - float(((x.astype(np.float64) - t) ** 2).mean())) <= 1e-6 * b["loss"]
+    for k in ("ybar", "hbar", "lambar", "rhobar", "biasbar"):
+        assert float(np.abs(a[k] - b[k]).max()) <= 1e-5 * float(np.abs(a[k]).max()) + 1e-12, k
