@@ -42,3 +42,40 @@ def test_iso_coupling_world1_is_identity():
             assert float((a - b).norm() / b.norm()) < 1e-5
     finally:
         dist.destroy_process_group()
+
+
+def test_iso_coupling_is_cuda_graph_capturable():
+    """The per-iteration all-reduce hook is called while the library ENQUEUES (a host callback into torch.distributed).  Under
+    CUDA-graph capture that happens once, at capture time: NCCL's kernels are recorded into the graph and a replay runs the
+    whole coupled forward with no host round trip at all."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1")
+    dev = torch.device("cuda:0")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        torch.manual_seed(1)
+        y = torch.rand(3, 2, 64, 64, device=dev)
+        h = torch.rand(1, 1, 3, 3, device=dev) / 9
+        lam = torch.tensor([0.05], device=dev); rho = torch.tensor([0.3], device=dev)
+        cp = D.IsoCoupling()
+        run = lambda: A.admm_layer_call(y, lam, rho, h, None, 5, True, "identity", 0.0, False, clamp=False, iso_coupling=cp)
+        dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize()       # communicator up before the capture
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st), torch.no_grad():
+            run()
+        torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        calls = cp.calls
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g):
+            xg = run()
+        assert cp.calls == calls + 4            # K-1 hook calls, made once while capturing
+        y.copy_(torch.rand_like(y))
+        g.replay(); g.replay()
+        torch.cuda.synchronize()
+        assert cp.calls == calls + 4            # replays do not come back to the host
+        with torch.no_grad():
+            assert torch.equal(xg, run())
+    finally:
+        dist.destroy_process_group()

@@ -18,7 +18,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device(f"cuda:{local}")
 dist.init_process_group("nccl", device_id=dev)
-B, P, N, M, K = 8, 3, 256, 256, 20
+B, P, N, M, K = (int(os.environ.get("ISO_B", "8")), 3, 256, 256, int(os.environ.get("ISO_K", "20")))
 gen = torch.Generator().manual_seed(3)
 y = torch.rand(B, P, N, M, generator=gen).to(dev)
 xbar = torch.randn(B, P, N, M, generator=gen).to(dev)
@@ -45,11 +45,39 @@ dist.all_reduce(pk)
 e1.record(); torch.cuda.synchronize()
 xs_all = [torch.empty_like(xs) for _ in range(world)]; yb_all = [torch.empty_like(ybs) for _ in range(world)]
 dist.all_gather(xs_all, xs); dist.all_gather(yb_all, ybs)
+# timing at scale: forward + backward of this rank's share, uncoupled vs coupled (eager: one host callback per iteration and
+# direction) vs the coupled forward replayed from a CUDA graph (the callbacks ran once, at capture)
+def timed(fn, n=10):
+    fn(); torch.cuda.synchronize(); dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / n], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+ysh, xsh = y[lo:hi].contiguous(), xbar[lo:hi].contiguous()
+t_plain = timed(lambda: run(ysh, xsh, None))
+t_coupled = timed(lambda: run(ysh, xsh, cp))
+lam0 = torch.tensor([0.05], device=dev); rho0 = torch.tensor([0.3], device=dev)
+fwd = lambda c: A.admm_layer_call(ysh, lam0, rho0, h, None, K, True, "identity", 0.0, False, clamp=False, iso_coupling=c)
+with torch.no_grad():
+    t_fwd_plain = timed(lambda: fwd(None)); t_fwd_coupled = timed(lambda: fwd(cp))
+    st = torch.cuda.Stream(); st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        fwd(cp)
+    torch.cuda.current_stream().wait_stream(st); torch.cuda.synchronize(); dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        xg = fwd(cp)
+    t_fwd_graph = timed(g.replay)
 if rank == 0:
     xf, ybf, pkf = run(y, xbar, None)
     xs_shard, _, _ = run(y[lo:hi].contiguous(), xbar[lo:hi].contiguous(), None)
     rel = lambda a, b: float((a - b).norm() / b.norm())
     print({"x_rel": rel(torch.cat(xs_all), xf), "ybar_rel": rel(torch.cat(yb_all), ybf), "grads_rel": rel(pk, pkf),
            "x_rel_without_coupling": rel(xs_shard, xf[lo:hi]), "allreduce_calls": cp.calls,
-           "ms_fwd_bwd_coupled": e0.elapsed_time(e1)})
+           "ms_fwd_bwd_coupled_first": e0.elapsed_time(e1), "world": world, "images_per_rank": hi - lo, "K": K,
+           "ms_fwd_bwd_uncoupled": t_plain, "ms_fwd_bwd_coupled": t_coupled, "ms_fwd_uncoupled": t_fwd_plain,
+           "ms_fwd_coupled_eager": t_fwd_coupled, "ms_fwd_coupled_cuda_graph": t_fwd_graph})
 dist.destroy_process_group()
