@@ -411,7 +411,9 @@ static int forward_impl(const admmtv_desc* d, const float* y, float* h, float* l
     s.planes = x_out; s.bias = d->has_bias ? bias : nullptr; s.pm = g.pm; s.tab_stride = g.G > 1 ? g.plane * g.PS : 0;
     s.K = g.K; s.PS = g.PS; s.act = d->activation; s.Q = g.Q;
     tm_mark(tm, st, 0);
-    if ((rc = run_small(g, s, st))) return rc;
+    // per-image PSFs / parameters on single-plane images (groups of one plane): two images share one complex transform
+    const bool straddle = g.G > 1 && g.Sg == 1 && !g.pm.concat && g.pm.in_gstride != 0;
+    if ((rc = run_small(g, s, straddle, st))) return rc;
     tm_mark(tm, st, -1);
     return ADMMTV_OK;
   }

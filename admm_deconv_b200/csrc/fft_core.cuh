@@ -105,6 +105,20 @@ ADMMTV_HD inline int pos_to_freq(int L, int p, bool planned = true, int P = 0) {
   return k;
 }
 
+// storage position of frequency index k (inverse of pos_to_freq for a planned length)
+ADMMTV_HD inline int freq_to_pos(int L, int k, int P = 0) {
+  if (!plan_supported(L)) return k;
+  int p = 0, len = L;
+  for (int s = 0; s < 4; ++s) {
+    int R = plan_radix(L, s, P);
+    if (R <= 1) break;
+    len /= R;
+    p += (k % R) * len;
+    k /= R;
+  }
+  return p;
+}
+
 // ------------------------------------------------------------------------------------------
 // complex helpers (float2 = re, im)
 // ------------------------------------------------------------------------------------------

@@ -298,6 +298,21 @@ def setup_dist():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{c.local}"))
     torch.cuda.set_device(c.local)
+    if c.world > 1:
+        # one process per GPU: run (and first-touch the pinned host buffers) on the CPUs of the GPU's own NUMA node, so that the
+        # e2e uploads of eight ranks do not all cross the socket interconnect.  Not done at N = 1, where rank 0 also runs the
+        # CPU baseline on every host core.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:      # NVML enumerates physical devices: match by UUID when the runtime exposes it
+                hnd = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(c.local).uuid)).encode())
+            except Exception:
+                hnd = pynvml.nvmlDeviceGetHandleByIndex(c.local)
+            pynvml.nvmlDeviceSetCpuAffinity(hnd)
+            c.affinity = len(os.sched_getaffinity(0))
+        except Exception:
+            c.affinity = None
     c.dev = torch.device(f"cuda:{c.local}")
     c.dist = dist
     return c
@@ -625,6 +640,7 @@ def run_native(args, w, name):
             line["gpu_launches"] = extra["launches_per_step"] * args.steps
             if c.world > 1:
                 line["collective"] = r["collective"]
+                line["e2e"]["host_cpus_per_rank"] = getattr(c, "affinity", None)
         elif "e2e" in r:
             line["e2e"] = r["e2e"]
         if c.world == 1 and not args.no_cpu:

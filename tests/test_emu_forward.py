@@ -117,11 +117,12 @@ def test_emu_forward_generic_sizes(emu, M, N, P, B, kh, kw, K, iso):
     assert rel_l2(x, xo) <= 1e-5
 
 
-@pytest.mark.parametrize("M,P,B,kh,K,per_image", [(32, 1, 128, 3, 5, False), (32, 2, 64, 0, 4, False), (64, 1, 64, 5, 3, True)])
+@pytest.mark.parametrize("M,P,B,kh,K,per_image", [(32, 1, 128, 3, 5, False), (32, 2, 64, 0, 4, False), (64, 1, 64, 5, 3, True), (32, 1, 65, 3, 4, True)])
 def test_emu_small_plane_persistent_kernel(emu, M, P, B, kh, K, per_image):
     """k_small (kernels_small.cuh): planes of 32^2 / 64^2 / 128^2 with >= 64 plane pairs run all iterations inside one
-    persistent kernel per pair.  Against the fp64 oracle, and bit-identical to... the two-launch path only to rounding
-    (different pass order), so both are compared with the oracle; per-image PSFs / parameters (groups = B) included."""
+    persistent kernel per pair (the two-launch path agrees to rounding only -- different pass order -- so both are compared
+    with the fp64 oracle).  per_image: groups = B single-plane images with their own PSF / lambda / rho: images 2q, 2q+1
+    share one complex transform (mirrored spectral division); an odd B leaves the last pair half empty."""
     import numpy as np
     import harness
     from admm_deconv_b200 import _lib
