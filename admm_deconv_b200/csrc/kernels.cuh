@@ -163,6 +163,9 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_MINB2
 #define ADMMTV_MINB2 1
 #endif
+#ifndef ADMMTV_D2_CPRE
+#define ADMMTV_D2_CPRE 0   // hoist the C-table loads of the fused dim-2 stage above its butterflies
+#endif
 #ifndef ADMMTV_MINB2_11
 #define ADMMTV_MINB2_11 1
 #endif
@@ -913,6 +916,12 @@ ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, siz
     for (int item = tid; item < RP * StL::ITEMS; item += NT) {
       const int rp = item % RP, wi = item / RP;
       float2 a0[StL::R], a1[StL::R];
+      float2 cpre[(ADMMTV_D2_CPRE && MUL == 0 && !FWD_ONLY) ? StL::R : 1];
+      if (ADMMTV_D2_CPRE && MUL == 0 && !FWD_ONLY) {   // table values in flight while the butterflies run
+#pragma unroll
+        for (int m = 0; m < StL::R; ++m)
+          cpre[m] = *reinterpret_cast<const float2*>(A.ctab + toff + (size_t)(wi * StL::R + m) * M + i0 + 2 * rp);
+      }
 #pragma unroll
       for (int m = 0; m < StL::R; ++m) {
         const float4 v = *reinterpret_cast<const float4*>(tile + (wi * StL::R + m) * TR + 2 * rp);
@@ -949,7 +958,7 @@ ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, siz
         }
         if (!FWD_ONLY) {
           if (MUL == 0) {
-            const float2 cc = *reinterpret_cast<const float2*>(A.ctab + toff + g);
+            const float2 cc = ADMMTV_D2_CPRE ? cpre[m] : *reinterpret_cast<const float2*>(A.ctab + toff + g);
             a0[m] = cscale(a0[m], cc.x);
             a1[m] = cscale(a1[m], cc.y);
           } else {
