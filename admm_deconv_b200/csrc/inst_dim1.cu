@@ -58,8 +58,8 @@ int Dim1Launch<LM>::out(const Geom& g, int mode, const OutArgs& a, cudaStream_t 
 }
 template <>
 int Dim1Launch<LM>::fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st) {
-  if (has_vprev) return launch_k(k_dim1_fwd<LM, true>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
-  return launch_k(k_dim1_fwd<LM, false>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
+  if (has_vprev) return launch_k(k_dim1_fwd<LM, true>, dim1_grid(g), Dim1FwdCfg<LM, 0>::NT, Cfg::SMEM, st, a);
+  return launch_k(k_dim1_fwd<LM, false>, dim1_grid(g), Dim1FwdCfg<LM, 0>::NT, Cfg::SMEM, st, a);
 }
 #include "inst_dim1_bwd.inc"
 

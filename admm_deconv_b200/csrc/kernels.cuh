@@ -169,6 +169,20 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_MINB2_11
 #define ADMMTV_MINB2_11 1
 #endif
+#ifndef ADMMTV_D2_SWZ
+#define ADMMTV_D2_SWZ 1   // XOR column swizzle of dim-2 tiles narrower than 16 rows (Dim2Cfg::SWZ)
+#endif
+#ifndef ADMMTV_REV1
+#define ADMMTV_REV1 0   // iteration dim-1 kernels walk (pair, tile) in DESCENDING order: they start on the spectra the dim-2 kernel wrote last (still in L2)
+#endif
+// block index of the iteration dim-1 kernels (k_dim1_fwd / k_dim1_bwd); the dim-2 kernels always ascend
+ADMMTV_DI int dim1_bid() {
+#if ADMMTV_REV1
+  return (int)(gridDim.x - 1 - blockIdx.x);
+#else
+  return (int)blockIdx.x;
+#endif
+}
 // Asynchronous bulk prefetch of a contiguous global range into L2 (TMA unit, no registers, no
 // shared memory): issued for the stencil phase's inputs while the FFT passes run.
 ADMMTV_DI void l2_prefetch_bulk(const void* p, unsigned bytes) {
@@ -206,6 +220,23 @@ struct Dim1Cfg {
   static constexpr int CO = TC - 2;                   // output columns per block
   static constexpr size_t SMEM = (size_t)TC * M * sizeof(float2);
   static_assert(M % NT == 0 && NT % 32 == 0, "dim-1 block must tile the column in whole warps");
+};
+
+// k_dim1_fwd, anisotropic (MODE 0): block size and row blocks per thread.  At M = 2048 the tile (6 columns = 96 KB) and the
+// 118-128 registers of the sweep allow ONE 512-thread block per SM, whose IFFT-load / stencil / FFT-store phases then run
+// back to back with nothing to overlap them (ncu: 24 % warps active, DRAM 45 %, issue 37 %).  With RB = 2 the block has half
+// the threads; every thread sweeps rows [tid*RPT, +RPT) and then [M/2 + tid*RPT, +RPT): same registers per thread, two
+// blocks per SM out of phase with each other, and the FFT passes (2 columns per round) leave no thread idle.
+#ifndef ADMMTV_RB11
+#define ADMMTV_RB11 2
+#endif
+template <int LM, int MODE>
+struct Dim1FwdCfg {
+  using C = Dim1Cfg<LM>;
+  static constexpr int RB = (LM == 11 && MODE == 0) ? ADMMTV_RB11 : 1;
+  static constexpr int NT = C::NT / RB;
+  static constexpr int MINB = RB > 1 ? RB : C::MINB;
+  static_assert(RB == 1 || RB == 2, "row blocks: 1 or 2");
 };
 
 // row index modulo M (circular boundary of the difference operators)
@@ -611,15 +642,20 @@ ADMMTV_DI Shrunk shrink_iso(float2 v, float s) {
 //         (A.vprev, A.nsq = s_{k-1}) ; store v_k ; A.nsq_out[q][pixel] = this pair's share of |v_k|^2 (plain stores:
 //         k_iso_scale adds the pairs of a group in a fixed order, so the norm is bit-reproducible) ; no FFT.
 template <int LM, bool HAS_VPREV, int MODE = 0>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
+__global__ void __launch_bounds__(Dim1FwdCfg<LM, MODE>::NT, Dim1FwdCfg<LM, MODE>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
   using Cfg = Dim1Cfg<LM>;
-  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
+  constexpr int M = Cfg::M, NT = Dim1FwdCfg<LM, MODE>::NT, RB = Dim1FwdCfg<LM, MODE>::RB, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
+  static_assert(RPT * NT * RB == M, "row blocks tile the column");
+  // x at the rows either side of the row-block boundary (rows 0 and M/2 - 1) of every tile column: the second sweep needs
+  // them after the first one has overwritten its half of the tile with r_{k+1}
+  __shared__ float2 xedge[RB > 1 ? 2 : 1][RB > 1 ? Cfg::TC : 1];
   static_assert(CO % CHUNK == 0, "chunking must divide the tile");
   ADMMTV_DYN_SMEM(float2, X);
   // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
   const int tid = threadIdx.x, N = A.N, ntile = (A.N + CO - 1) / CO;
-  const int q = blockIdx.x / ntile;
-  const int j0 = (blockIdx.x % ntile) * CO;
+  const int bid = dim1_bid();
+  const int q = bid / ntile;
+  const int j0 = (bid % ntile) * CO;
   const int nout = min(CO, N - j0);  // N and CO are powers of two: nout % CHUNK == 0
   const size_t plane = (size_t)N * M;
   const float2* sin_q = A.spec_in + (size_t)q * plane;
@@ -641,7 +677,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
     if (MODE != 2 && tid == 64 % NT) l2_prefetch_bulk(A.bpk + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
     // the spectrum tile of the block that will be scheduled onto this SM slot when a resident block retires
     if (MODE == 0 && ADMMTV_PF_NEXT > 0 && tid == 96 % NT) {
-      const long nid = (long)blockIdx.x + ADMMTV_PF_NEXT;
+      const long nid = (long)bid + ADMMTV_PF_NEXT;
       if (nid < (long)gridDim.x) {
         const int nq = (int)(nid / ntile), nj0 = (int)(nid % ntile) * CO;
         const int ncol = min(CO, N - nj0);
@@ -658,7 +694,12 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   const float rho = A.rho[grp * A.PS + A.in];                                     // rho of r_{k+1}
   const float tau = A.lambda[grp * A.PS + A.ic] / A.rho[grp * A.PS + A.ic];       // tau of v_k      (ops.jl:102)
   const float tau_p = A.lambda[grp * A.PS + A.ip] / A.rho[grp * A.PS + A.ip];     // tau of v_{k-1}
-  const int i0 = tid * RPT;
+  if constexpr (RB > 1) {
+    if (tid < nout + 2) {
+      xedge[0][tid] = X[sidx<LM>(tid, 0)];
+      xedge[1][tid] = X[sidx<LM>(tid, M / 2 - 1)];
+    }   // read in the second sweep only: the first sweep's chunk barriers order these stores before it
+  }
   const float* nsq_g = MODE != 0 ? A.nsq + (size_t)grp * plane : nullptr;
   float* nsq_o = MODE == 2 ? A.nsq_out + (size_t)q * plane : nullptr;   // per-pair partial sums
   const float2* vp1 = A.vprev + ((size_t)q * 2 + 0) * plane;
@@ -667,6 +708,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
   float2* vn2 = A.vnew + ((size_t)q * 2 + 1) * plane;
   const float2* bq = A.bpk + (size_t)q * plane;
 
+#pragma unroll 1
+  for (int rb = 0; rb < RB; ++rb) {
+  const int i0 = tid * RPT + rb * (M / RB);
   float2 w1c[RPT];   // MODE 0/1: w1 of the current column ; MODE 2: v1 of the current column
   if (MODE == 2) {
     const int j = jcol(1);
@@ -775,6 +819,10 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
       for (int r = 0; r < RPT; ++r) xc[r + 1] = X[sidx<LM>(col, i0 + r)];
       xc[RPT + 1] = X[sidx<LM>(col, wrapm<M>(i0 + RPT))];
+      if constexpr (RB > 1) {   // second sweep: the first one has replaced rows < M/2 of the slots behind it
+        if (rb == 1 && tid == 0) xc[0] = xedge[1][col];
+        if (rb == 1 && tid == NT - 1) xc[RPT + 1] = xedge[0][col];
+      }
 
       // channel 1 (dim-2 difference) at column col+1
       {
@@ -816,6 +864,7 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, Dim1Cfg<LM>::MINB) k_dim1_fwd
 #pragma unroll
       for (int r = 0; r < RPT; ++r) X[sidx<LM>(c + cc - 1, i0 + r)] = rr[cc][r];  // r column -> slot col-1
   }
+  }  // row blocks
   if (MODE == 2) return;
   __syncthreads();
 
@@ -843,9 +892,24 @@ struct Dim2Cfg {
   static constexpr int NT = LN == 9 ? ADMMTV_NT2 : NT_AUTO;
   static constexpr int MINB = LN == 9 ? ADMMTV_MINB2 : (LN == 11 ? ADMMTV_MINB2_11 : 1);
   static constexpr size_t SMEM = (size_t)N * TR * sizeof(float2);
+  // Tiles narrower than 16 rows (a column = 64 or 32 bytes of the 128-byte bank span): the last plan stage reads columns
+  // R apart, which land on the same banks (ncu, N = 2048: 20 % of the shared-memory wavefronts are conflicts at TR = 8,
+  // 43 % at TR = 4).  Column c is therefore stored at c ^ ((c >> log2 R_last) & (16/TR - 1)): the R-apart columns of a
+  // warp's work items rotate through the 16/TR column slots of a bank span, and every other stage (whose lanes hold
+  // consecutive columns with constant high bits) sees a permutation inside aligned groups, i.e. stays conflict-free.
+  static constexpr bool SWZ = ADMMTV_D2_SWZ && is_pow2(N) && TR < 16;
 };
+template <int LN, int TR, bool SWZ>
+ADMMTV_DI int d2col(int c) {
+  if constexpr (!SWZ) return c;
+  else {
+    constexpr int N = dim_len(LN), RL = plan_radix(N, plan_stages(N, kP2) - 1, kP2);
+    constexpr int SH = RL == 32 ? 5 : (RL == 16 ? 4 : (RL == 8 ? 3 : 2));
+    return c ^ ((c >> SH) & (16 / TR - 1));
+  }
+}
 
-template <int LN, int S, bool INV, int NTX = Dim2Cfg<LN>::NT, int TRX = Dim2Cfg<LN>::TR>
+template <int LN, int S, bool INV, int NTX = Dim2Cfg<LN>::NT, int TRX = Dim2Cfg<LN>::TR, bool SWZ = false>
 ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int tid) {
   using Cfg = Dim2Cfg<LN>;
   constexpr int N = Cfg::N, TR = TRX, NT = NTX, RP = TR / 2;
@@ -858,7 +922,7 @@ ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int 
     const int base = St::base(wi);
 #pragma unroll
     for (int m = 0; m < St::R; ++m) {
-      const float4 v = *reinterpret_cast<const float4*>(tile + (base + m * St::STRIDE) * TR + 2 * rp);
+      const float4 v = *reinterpret_cast<const float4*>(tile + d2col<LN, TR, SWZ>(base + m * St::STRIDE) * TR + 2 * rp);
       a0[m] = make_float2(v.x, v.y);
       a1[m] = make_float2(v.z, v.w);
     }
@@ -871,13 +935,13 @@ ADMMTV_DI void dim2_smem_stage(float2* tile, const float2* __restrict__ tw, int 
     }
 #pragma unroll
     for (int m = 0; m < St::R; ++m)
-      *reinterpret_cast<float4*>(tile + (base + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+      *reinterpret_cast<float4*>(tile + d2col<LN, TR, SWZ>(base + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
   }
 }
 template <int LN, int S, int NTX = Dim2Cfg<LN>::NT>
 ADMMTV_DI void dim2_fwd_mid(float2* tile, const float2* __restrict__ tw, int tid) {
   if constexpr (S < plan_stages(dim_len(LN), kP2) - 1) {
-    dim2_smem_stage<LN, S, false, NTX>(tile, tw, tid);
+    dim2_smem_stage<LN, S, false, NTX, Dim2Cfg<LN>::TR, Dim2Cfg<LN>::SWZ>(tile, tw, tid);
     __syncthreads();
     dim2_fwd_mid<LN, S + 1, NTX>(tile, tw, tid);
   }
@@ -885,7 +949,7 @@ ADMMTV_DI void dim2_fwd_mid(float2* tile, const float2* __restrict__ tw, int tid
 template <int LN, int S, int NTX = Dim2Cfg<LN>::NT>
 ADMMTV_DI void dim2_inv_mid(float2* tile, const float2* __restrict__ tw, int tid) {
   if constexpr (S >= 1) {
-    dim2_smem_stage<LN, S, true, NTX>(tile, tw, tid);
+    dim2_smem_stage<LN, S, true, NTX, Dim2Cfg<LN>::TR, Dim2Cfg<LN>::SWZ>(tile, tw, tid);
     __syncthreads();
     dim2_inv_mid<LN, S - 1, NTX>(tile, tw, tid);
   }
@@ -904,7 +968,7 @@ ADMMTV_DI void l2_prefetch_line(const void* p) {
 // over the whole tile.  Two mappings: radix <= 16 works on ROW PAIRS (float4 shared-memory accesses, both rows share the
 // index arithmetic); radix 32 works on single rows (32 complex values are all the registers a thread has).  Each tile
 // element is owned by exactly one thread in either mapping (dim2_fused_flush relies on it).
-template <int LN, int MUL, bool SAVE_Z, int ACC, bool FWD_ONLY, int NT, int TR>
+template <int LN, int MUL, bool SAVE_Z, int ACC, bool FWD_ONLY, int NT, int TR, bool SWZ = false>
 ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, size_t qoff, size_t toff, int i0, int tid) {
   constexpr int N = dim_len(LN), NS = plan_stages(N, kP2), RP = TR / 2;
   using StL = Stage<N, NS - 1, kP2>;
@@ -924,7 +988,7 @@ ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, siz
       }
 #pragma unroll
       for (int m = 0; m < StL::R; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + (wi * StL::R + m) * TR + 2 * rp);
+        const float4 v = *reinterpret_cast<const float4*>(tile + d2col<LN, TR, SWZ>(wi * StL::R + m) * TR + 2 * rp);
         a0[m] = make_float2(v.x, v.y);
         a1[m] = make_float2(v.z, v.w);
       }
@@ -974,10 +1038,11 @@ ADMMTV_DI void dim2_fused_stage(float2* tile, float* gsm, const Dim2Args& A, siz
         Dft<StL::R, true>::run(a1);
 #pragma unroll
         for (int m = 0; m < StL::R; ++m)
-          *reinterpret_cast<float4*>(tile + (wi * StL::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+          *reinterpret_cast<float4*>(tile + d2col<LN, TR, SWZ>(wi * StL::R + m) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
       }
     }
   } else {
+    static_assert(!SWZ, "the single-row mapping (radix 32) is only used with 16-row tiles");
     // single rows: lanes run along the TR contiguous rows of a column (conflict-free 8-byte accesses)
 #pragma unroll 1
     for (int item = tid; item < TR * StL::ITEMS; item += NT) {
@@ -1102,14 +1167,14 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
         stage_fwd<N, 0, kP2>(a1, p);
 #pragma unroll
         for (int m = 0; m < St::R; ++m)
-          *reinterpret_cast<float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
+          *reinterpret_cast<float4*>(tile + d2col<LN, TR, Cfg::SWZ>(wi + m * St::STRIDE) * TR + 2 * rp) = make_float4(a0[m].x, a0[m].y, a1[m].x, a1[m].y);
       }
     }
     __syncthreads();
     dim2_fwd_mid<LN, 1>(tile, A.twN, tid);
 
     // last forward stage fused with the spectral multiply and the first inverse stage
-    dim2_fused_stage<LN, MUL, SAVE_Z, ACC, FWD_ONLY, NT, TR>(tile, gsm, A, qoff, toff, i0, tid);
+    dim2_fused_stage<LN, MUL, SAVE_Z, ACC, FWD_ONLY, NT, TR, Cfg::SWZ>(tile, gsm, A, qoff, toff, i0, tid);
     __syncthreads();
     if (FWD_ONLY) continue;
     dim2_inv_mid<LN, NS - 2>(tile, A.twN, tid);
@@ -1125,7 +1190,7 @@ __global__ void __launch_bounds__(Dim2Cfg<LN>::NT, Dim2Cfg<LN>::MINB) k_dim2(Dim
         float2 a0[St::R], a1[St::R];
 #pragma unroll
         for (int m = 0; m < St::R; ++m) {
-          const float4 v = *reinterpret_cast<const float4*>(tile + (wi + m * St::STRIDE) * TR + 2 * rp);
+          const float4 v = *reinterpret_cast<const float4*>(tile + d2col<LN, TR, Cfg::SWZ>(wi + m * St::STRIDE) * TR + 2 * rp);
           a0[m] = make_float2(v.x, v.y);
           a1[m] = make_float2(v.z, v.w);
         }

@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   ADMMTV_DYN_SMEM(float2, X);
   // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
   const int tid = threadIdx.x, N = A.N, ntile = (A.N + CO - 1) / CO;
-  const int q = blockIdx.x / ntile;
-  const int j0 = (blockIdx.x % ntile) * CO;
+  const int bid = dim1_bid();
+  const int q = bid / ntile;
+  const int j0 = (bid % ntile) * CO;
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   const float2* sin_q = A.spec_in + (size_t)q * plane;
