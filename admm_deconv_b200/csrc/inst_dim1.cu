@@ -27,7 +27,7 @@ namespace admmtv {
 
 template <class K, class Args>
 static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, const Args& a) {
-  if (smem > 48 * 1024) {
+  if (smem + 2048 > 48 * 1024) {   // + the kernel's static shared memory (padded to the 1 KB tile alignment)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
@@ -39,6 +39,32 @@ static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, con
 constexpr int LM = ADMMTV_INST;
 using Cfg = Dim1Cfg<LM>;
 static dim3 dim1_grid(const Geom& g) { return dim3((unsigned)((g.N + Cfg::CO - 1) / Cfg::CO) * (unsigned)g.Q); }
+
+// TMA variants of the iteration kernels: launched when the column maps of the two spectra can be encoded (a null pointer =
+// the kernel does not touch that side), else the caller falls through to the LDG / STG kernels.
+#ifndef ADMMTV_EMU
+template <class K, class Args>
+static int launch_tma(K kern, const Geom& g, int nt, const float2* in, const float2* out, cudaStream_t st, const Args& a) {
+  Dim1Tma tm;
+  const size_t ncols = (size_t)g.Q * g.N;
+  if (g.N % Cfg::CO != 0 || ncols >= 0x7fffffffull) return -100;
+  if (tma_make_colmap(&tm.in, in ? in : out, g.M, ncols) != 0 || tma_make_colmap(&tm.out, out ? out : in, g.M, ncols) != 0) return -100;
+  if (Cfg::SMEM + 2048 > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<dim1_grid(g), dim3(nt), Cfg::SMEM, st>>>(a, tm);
+  ADMMTV_CHECK_LAUNCH();
+  return 0;
+}
+#define ADMMTV_TRY_TMA(KERN, NT_, IN, OUT)                             \
+  if constexpr (kDim1TmaOk<LM>) {                                      \
+    const int rc__ = launch_tma(KERN, g, NT_, IN, OUT, st, a);         \
+    if (rc__ != -100) return rc__;                                     \
+  }
+#else
+#define ADMMTV_TRY_TMA(KERN, NT_, IN, OUT)
+#endif
 
 template <>
 int Dim1Launch<LM>::col_tile() { return Cfg::CO; }
@@ -58,6 +84,7 @@ int Dim1Launch<LM>::out(const Geom& g, int mode, const OutArgs& a, cudaStream_t 
 }
 template <>
 int Dim1Launch<LM>::fwd(const Geom& g, bool has_vprev, const Dim1FwdArgs& a, cudaStream_t st) {
+  ADMMTV_TRY_TMA((has_vprev ? k_dim1_fwd_tma<LM, true> : k_dim1_fwd_tma<LM, false>), (Dim1FwdCfg<LM, 0>::NT), a.spec_in, a.spec_out);
   if (has_vprev) return launch_k(k_dim1_fwd<LM, true>, dim1_grid(g), Dim1FwdCfg<LM, 0>::NT, Cfg::SMEM, st, a);
   return launch_k(k_dim1_fwd<LM, false>, dim1_grid(g), Dim1FwdCfg<LM, 0>::NT, Cfg::SMEM, st, a);
 }

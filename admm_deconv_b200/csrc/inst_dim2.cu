@@ -25,7 +25,7 @@ namespace admmtv {
 
 template <class K, class Args>
 static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, const Args& a) {
-  if (smem > 48 * 1024) {
+  if (smem + 2048 > 48 * 1024) {   // + the kernel's static shared memory (padded to the 1 KB tile alignment)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }

@@ -9,7 +9,7 @@
 namespace admmtv {
 
 static int gk_set_smem(const void* kern, size_t smem) {
-  if (smem > 48 * 1024) {
+  if (smem + 2048 > 48 * 1024) {   // + the kernel's static shared memory (padded to the 1 KB tile alignment)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }

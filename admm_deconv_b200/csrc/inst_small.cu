@@ -8,7 +8,7 @@ template <int LM, int LN, bool STR>
 static int launch_small(const Geom& g, const SmallArgs& a, cudaStream_t st) {
   using Cfg = SmallCfg<LM, LN>;
   static_assert(Cfg::OK, "k_small: unsupported plane size");
-  if (Cfg::SMEM > 48 * 1024) {
+  if (Cfg::SMEM + 2048 > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_small<LM, LN, STR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return (int)e;
   }

@@ -19,6 +19,7 @@
 #include "args.cuh"
 #include "launch_macros.cuh"
 #include "reduce.cuh"
+#include "tma_prims.cuh"
 
 #ifndef ADMMTV_UNROLL_ITEMS
 #define ADMMTV_UNROLL_ITEMS 1
@@ -396,6 +397,127 @@ ADMMTV_DI void dim1_fft_from_smem(float2* X, int ncols, ColPtr colptr, const flo
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA column loads / stores for the dim-1 transforms (north_star: "FFT staged in shared memory, TMA tile loads").
+// The stride-1 radix pass of a dim-1 transform gives every thread a contiguous run of R = 8 or 16 elements of a column.
+// Straight from / to global memory (dim1_ifft_to_smem / dim1_fft_from_smem above) that is R/2 LDG.128 / STG.128 per
+// thread whose lanes sit 64 or 128 bytes apart: every warp request touches 16 or 32 different 128-byte lines, and ncu
+// shows these two passes producing about half of the L1 data-pipe wavefronts of the iteration kernels, which run at
+// 62-72 % of that pipe (their tightest resource; profiles/r2b_*).  Here the TMA unit moves whole columns
+// (cp.async.bulk.tensor, one box = M/16 lines of 128 bytes, 128-byte swizzle) between global and shared memory, and the
+// radix pass reads / writes its runs in shared memory: with the swizzle (16-byte chunk ^= line mod 8) the 8 lanes of a
+// quarter-warp hit 8 different chunk slots, i.e. 4 wavefronts per 512-byte request, the minimum.  Both layouts (the TMA
+// swizzle and the pass-conflict-free XOR placement sidx) permute elements inside one 128-byte line, so the pass runs in place;
+// the lanes that share a line (two for R = 8) are neighbours in a warp and separated by __syncwarp.
+// ------------------------------------------------------------------------------------------
+#ifdef ADMMTV_EMU
+struct Dim1Tma {};
+#else
+#ifndef ADMMTV_D1_TMA
+#define ADMMTV_D1_TMA 1
+#endif
+template <int LM>
+constexpr bool kDim1TmaOk = ADMMTV_D1_TMA && LM >= 7 && LM <= 12;   // 128 .. 4096: stride-1 pass of radix 8 or 16, M/16 <= 256 lines
+
+// byte offset (from the tile base) of logical 16-byte chunk g of the 128-byte line at byte offset lineoff
+ADMMTV_DI unsigned tma_chunk_off(unsigned xbase, unsigned lineoff, int g) {
+  return lineoff + ((unsigned)(g ^ (int)(((xbase + lineoff) >> 7) & 7u)) << 4);
+}
+// (work item, column) pairs of the stride-1 pass with a warp-uniform trip count: body(wi, c, active)
+template <int ITEMS, int NT, class Body>
+ADMMTV_DI void for_items_uniform(int tid, int ncols, Body body) {
+  if constexpr (NT >= ITEMS) {
+    constexpr int CSTEP = NT / ITEMS;
+    const int wi = tid % ITEMS, c0 = tid / ITEMS;
+    for (int cb = 0; cb < ncols; cb += CSTEP) body(wi, cb + c0, cb + c0 < ncols);
+  } else {
+    static_assert(ITEMS % NT == 0, "items tile the block");
+    for (int wi = tid; wi < ITEMS; wi += NT)
+      for (int c = 0; c < ncols; ++c) body(wi, c, true);
+  }
+}
+
+// Inverse dim-1 FFT of `ncols` spectrum columns -> natural-order columns in X; colidx(c) = index of tile column c among
+// the columns of the map.  Ends synced.
+template <int LM, int NT, class ColIdx>
+ADMMTV_DI void dim1_ifft_to_smem_tma(float2* X, int ncols, const CUtensorMap* map, ColIdx colidx, unsigned long long* bar,
+                                     const float2* __restrict__ tw, int tid) {
+  constexpr int M = dim_len(LM), NS = plan_stages(M);
+  using St = Stage<M, NS - 1>;
+  constexpr int R = St::R, CPI = R / 2;   // 16-byte chunks per work item
+  static_assert(St::STRIDE == 1 && (R == 8 || R == 16), "stride-1 pass of radix 8 or 16");
+  const unsigned xbase = smem_u32(X);
+  if (tid == 0) {
+    if (xbase & 127u) __trap();   // TMA destination alignment
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, (unsigned)(ncols * M * sizeof(float2)));
+    for (int c = 0; c < ncols; ++c) tma_load_3d(X + (size_t)c * M, map, 0, 0, colidx(c), bar);
+  }
+  __syncthreads();   // the barrier is initialised before anyone waits on it
+  mbar_wait(bar, 0);
+  char* Xb = reinterpret_cast<char*>(X);
+  for_items_uniform<St::ITEMS, NT>(tid, ncols, [&](int wi, int c, bool act) {
+    float2 a[R];
+    if (act) {
+      const unsigned lineoff = ((unsigned)(c * M + wi * R) >> 4) << 7;
+      const int g0 = (wi * CPI) & 7;
+#pragma unroll
+      for (int k = 0; k < CPI; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(Xb + tma_chunk_off(xbase, lineoff, g0 + k));
+        a[2 * k] = make_float2(v.x, v.y);
+        a[2 * k + 1] = make_float2(v.z, v.w);
+      }
+      Dft<R, true>::run(a);
+    }
+    __syncwarp();   // the lanes sharing this 128-byte line have read it
+    if (act) {
+      const int pb = sidx<LM>(c, wi * R);
+#pragma unroll
+      for (int m = 0; m < R; ++m) X[scomb<LM>(pb, m)] = a[m];
+    }
+  });
+  __syncthreads();
+  dim1_inv_stages_down<LM, NT, NS - 2>(X, ncols, tw, tid);
+}
+
+// Forward dim-1 FFT of `ncols` natural-order columns in X (must be synced) -> columns col0 .. col0+ncols-1 of the map.
+// Thread 0 returns once the TMA unit has read the tile (the block may then exit).
+template <int LM, int NT, bool WAIT = true>
+ADMMTV_DI void dim1_fft_from_smem_tma(float2* X, int ncols, const CUtensorMap* map, int col0, const float2* __restrict__ tw, int tid) {
+  constexpr int M = dim_len(LM), NS = plan_stages(M);
+  dim1_fwd_stages_up<LM, NT, 0>(X, ncols, tw, tid);
+  using St = Stage<M, NS - 1>;
+  constexpr int R = St::R, CPI = R / 2;
+  const unsigned xbase = smem_u32(X);
+  char* Xb = reinterpret_cast<char*>(X);
+  for_items_uniform<St::ITEMS, NT>(tid, ncols, [&](int wi, int c, bool act) {
+    float2 a[R];
+    if (act) {
+      const int pb = sidx<LM>(c, wi * R);
+#pragma unroll
+      for (int m = 0; m < R; ++m) a[m] = X[scomb<LM>(pb, m)];
+      Dft<R, false>::run(a);
+    }
+    __syncwarp();
+    if (act) {
+      const unsigned lineoff = ((unsigned)(c * M + wi * R) >> 4) << 7;
+      const int g0 = (wi * CPI) & 7;
+#pragma unroll
+      for (int k = 0; k < CPI; ++k)
+        *reinterpret_cast<float4*>(Xb + tma_chunk_off(xbase, lineoff, g0 + k)) = make_float4(a[2 * k].x, a[2 * k].y, a[2 * k + 1].x, a[2 * k + 1].y);
+    }
+  });
+  fence_proxy_async();   // this thread's generic-proxy stores are visible to the async proxy
+  __syncthreads();
+  if (tid == 0) {
+    for (int c = 0; c < ncols; ++c) tma_store_3d(map, 0, 0, col0 + c, X + (size_t)c * M);
+    tma_store_commit();
+    if (WAIT) tma_store_wait_read();   // else the caller's thread 0 waits before it exits
+  }
+}
+#endif  // !ADMMTV_EMU
+
+// ------------------------------------------------------------------------------------------
 // k_pack_fft1: user-layout planes -> pair-pack -> dim-1 FFT -> spectrum
 //   MODE 0: src = y                                  (ops.jl:101 permute + first rfft pass)
 //   MODE 1: src = xbar * act'(x_out); accumulates biasbar (deconv_admm.jl:222-224 pullback)
@@ -641,8 +763,8 @@ ADMMTV_DI Shrunk shrink_iso(float2 v, float s) {
 // MODE 2: isotropic pass A -- dim-1 IFFT -> x_k ; v_k = D x_k + u_{k-1} with u_{k-1} = (1 - s_{k-1}) v_{k-1}
 //         (A.vprev, A.nsq = s_{k-1}) ; store v_k ; A.nsq_out[q][pixel] = this pair's share of |v_k|^2 (plain stores:
 //         k_iso_scale adds the pairs of a group in a fixed order, so the norm is bit-reproducible) ; no FFT.
-template <int LM, bool HAS_VPREV, int MODE = 0>
-__global__ void __launch_bounds__(Dim1FwdCfg<LM, MODE>::NT, Dim1FwdCfg<LM, MODE>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
+template <int LM, bool HAS_VPREV, int MODE, bool TMA>
+ADMMTV_DI void dim1_fwd_body(const Dim1FwdArgs& A, const Dim1Tma* tm) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Dim1FwdCfg<LM, MODE>::NT, RB = Dim1FwdCfg<LM, MODE>::RB, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNK;
   static_assert(RPT * NT * RB == M, "row blocks tile the column");
@@ -686,8 +808,16 @@ __global__ void __launch_bounds__(Dim1FwdCfg<LM, MODE>::NT, Dim1FwdCfg<LM, MODE>
     }
   }
   // 1. x_k for columns j0-1 .. j0+nout (one halo column each side)
-  if (MODE == 0) dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
-  if (MODE == 2) dim1_ifft_to_smem<LM, NT>(X, nout + 1, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+  __shared__ unsigned long long tbar[1];
+  if constexpr (TMA) {
+    if (MODE != 1) dim1_ifft_to_smem_tma<LM, NT>(X, MODE == 2 ? nout + 1 : nout + 2, &tm->in, [&](int c) { return q * N + jcol(c); }, tbar, A.twM, tid);
+  } else
+#endif
+  {
+    if (MODE == 0) dim1_ifft_to_smem<LM, NT>(X, nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+    if (MODE == 2) dim1_ifft_to_smem<LM, NT>(X, nout + 1, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+  }
 
   // 2. stencil sweep: this thread owns rows i0 .. i0+RPT-1 of every column
   const int grp = q / A.Qg;
@@ -870,8 +1000,24 @@ __global__ void __launch_bounds__(Dim1FwdCfg<LM, MODE>::NT, Dim1FwdCfg<LM, MODE>
 
   // 3. dim-1 FFT of r_{k+1}: slot s holds output column j0+s
   float2* sout_q = A.spec_out + (size_t)q * plane;
-  dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+  if constexpr (TMA) dim1_fft_from_smem_tma<LM, NT>(X, nout, &tm->out, q * N + j0, A.twM, tid);
+  else
+#endif
+    dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
 }
+template <int LM, bool HAS_VPREV, int MODE = 0>
+__global__ void __launch_bounds__(Dim1FwdCfg<LM, MODE>::NT, Dim1FwdCfg<LM, MODE>::MINB) k_dim1_fwd(Dim1FwdArgs A) {
+  dim1_fwd_body<LM, HAS_VPREV, MODE, false>(A, nullptr);
+}
+#ifndef ADMMTV_EMU
+// the iteration kernel with TMA column loads / stores of the spectra (Dim1Tma: maps of spec_in / spec_out; isotropic pass A
+// only loads, pass B only stores)
+template <int LM, bool HAS_VPREV, int MODE = 0>
+__global__ void __launch_bounds__(Dim1FwdCfg<LM, MODE>::NT, Dim1FwdCfg<LM, MODE>::MINB) k_dim1_fwd_tma(Dim1FwdArgs A, const __grid_constant__ Dim1Tma tm) {
+  dim1_fwd_body<LM, HAS_VPREV, MODE, true>(A, &tm);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // k_dim2: dim-2 (strided) pass over a tile of TR contiguous rows x all N columns

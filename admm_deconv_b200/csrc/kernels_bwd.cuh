@@ -78,9 +78,11 @@ ADMMTV_DI float2 iso_bwd_full(float2 d, float2 v, float2 eb, float rho, float2 s
 //         a fixed order, so the result is bit-reproducible) ; nothing else is written.
 // MODE 0: anisotropic.  MODE 1: isotropic pass B (per-pixel (s, tau ip / n^3) in A.sc from k_iso_coef, which also
 // adds the per-pixel taubar terms; bbar was accumulated by pass A).
-template <int LM, bool HAS_VBAR, int MODE = 0>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : (LM == 8 ? ADMMTV_MINB8B : (LM == 7 ? ADMMTV_MINB7B : 1)))
-    k_dim1_bwd(Dim1BwdArgs A) {
+template <int LM, int MODE>
+constexpr int kDim1BwdMinB = (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : (LM == 8 ? ADMMTV_MINB8B : (LM == 7 ? ADMMTV_MINB7B : 1));
+
+template <int LM, bool HAS_VBAR, int MODE, bool TMA>
+ADMMTV_DI void dim1_bwd_body(const Dim1BwdArgs& A, const Dim1Tma* tm) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNKB;
   static_assert(CO % CHUNK == 0, "chunking must divide the tile");
@@ -114,7 +116,13 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
     if (!A.first && tid == 128 % NT) l2_prefetch_bulk(A.bbar + (size_t)q * plane + (size_t)j0 * M, (unsigned)nout * colb);
   }
   // 1. rbar_k for columns j0-1 .. j0+nout
-  dim1_ifft_to_smem<LM, NT>(X, MODE == 2 ? nout + 1 : nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+  __shared__ unsigned long long tbar[1];
+  if constexpr (TMA) {
+    dim1_ifft_to_smem_tma<LM, NT>(X, MODE == 2 ? nout + 1 : nout + 2, &tm->in, [&](int c) { return q * N + jcol(c); }, tbar, A.twM, tid);
+  } else
+#endif
+    dim1_ifft_to_smem<LM, NT>(X, MODE == 2 ? nout + 1 : nout + 2, [&](int c) { return sin_q + (size_t)jcol(c) * M; }, A.twM, tid);
 
   const int grp = q / A.pm.Qg;
   const float rho = A.rho[grp * A.PS + A.ir];                                     // rho_k
@@ -315,7 +323,11 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   __syncthreads();
 
   float2* sout_q = A.spec_out + (size_t)q * plane;
-  dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+  if constexpr (TMA) dim1_fft_from_smem_tma<LM, NT, false>(X, nout, &tm->out, q * N + j0, A.twM, tid);
+  else
+#endif
+    dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
 
   // scalar partial sums -> fp64 accumulators (one atomic pair per block)
   const double rsum = block_sum(racc);
@@ -323,8 +335,22 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, (LM == 9 && MODE == 0) ? ADMM
   if (tid == 0) {
     atomicAdd(A.acc + (size_t)A.AS * grp + acc_rho(A.ir), rsum);
     atomicAdd(A.acc + (size_t)A.AS * grp + acc_tau(A.it), tsum);
+#ifndef ADMMTV_EMU
+    if constexpr (TMA) tma_store_wait_read();   // the TMA unit has read the tile: the block may exit
+#endif
   }
 }
+template <int LM, bool HAS_VBAR, int MODE = 0>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, kDim1BwdMinB<LM, MODE>) k_dim1_bwd(Dim1BwdArgs A) {
+  dim1_bwd_body<LM, HAS_VBAR, MODE, false>(A, nullptr);
+}
+#ifndef ADMMTV_EMU
+// the backward iteration kernel with TMA column loads / stores of the spectra (isotropic pass A only loads)
+template <int LM, bool HAS_VBAR, int MODE = 0>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT, kDim1BwdMinB<LM, MODE>) k_dim1_bwd_tma(Dim1BwdArgs A, const __grid_constant__ Dim1Tma tm) {
+  dim1_bwd_body<LM, HAS_VBAR, MODE, true>(A, &tm);
+}
+#endif
 
 // Last backward iteration (k = 1): rbar_1 -> bbar_total = bbar + rbar_1, then either its dim-1
 // FFT (MODE 0, feeds ybar = H bbar and the PSF correlation) or, with an empty PSF, ybar = bbar

@@ -52,34 +52,6 @@ struct Dim2tCfg {
                              ((TR / 2) * (N / plan_radix(N, 0, kP2))) / kD2tGroupNT * plan_radix(N, 0, kP2) <= 16;
 };
 
-ADMMTV_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-ADMMTV_DI void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-ADMMTV_DI void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-ADMMTV_DI void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// 3-D tiled TMA load: box at (c0 = float index along dim 1, c1 = column, c2 = pair) -> shared memory, completes on `bar`
-ADMMTV_DI void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-ADMMTV_DI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 ADMMTV_DI void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kD2tGroupNT) : "memory"); }   // named barrier of one group
 
 template <int LN, int S>
@@ -194,19 +166,6 @@ __global__ void __launch_bounds__(Dim2tCfg<LN>::NT, 1) k_dim2t(Dim2Args A, const
 }
 
 // Host side: the 3-D tensor map of a [Q][N][M] float2 array, viewed as fp32 [Q][N][2M], box = (2 TR, BOXC, 1).
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-inline PFN_encodeTiled tma_encode_fn() {
-  static PFN_encodeTiled fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<PFN_encodeTiled>(p);
-  }();
-  return fn;
-}
 inline int tma_make_map(CUtensorMap* map, const float2* base, int M, int N, int Q, int TR, int BOXC) {
   PFN_encodeTiled enc = tma_encode_fn();
   if (!enc) return -3;
