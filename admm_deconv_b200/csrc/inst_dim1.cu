@@ -71,6 +71,12 @@ int Dim1Launch<LM>::col_tile() { return Cfg::CO; }
 
 template <>
 int Dim1Launch<LM>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaStream_t st) {
+  switch (mode) {
+    case 0: { ADMMTV_TRY_TMA((k_pack_fft1_tma<LM, 0>), Cfg::NT, (const float2*)nullptr, a.spec); break; }
+    case 1: { ADMMTV_TRY_TMA((k_pack_fft1_tma<LM, 1>), Cfg::NT, (const float2*)nullptr, a.spec); break; }
+    case 3: { ADMMTV_TRY_TMA((k_pack_fft1_tma<LM, 3>), Cfg::NT, (const float2*)nullptr, a.spec); break; }
+    default: { ADMMTV_TRY_TMA((k_pack_fft1_tma<LM, 2>), Cfg::NT, (const float2*)nullptr, a.spec); break; }
+  }
   if (mode == 0) return launch_k(k_pack_fft1<LM, 0>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
   if (mode == 1) return launch_k(k_pack_fft1<LM, 1>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
   if (mode == 3) return launch_k(k_pack_fft1<LM, 3>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
@@ -78,6 +84,11 @@ int Dim1Launch<LM>::pack_fft1(const Geom& g, int mode, const PackArgs& a, cudaSt
 }
 template <>
 int Dim1Launch<LM>::out(const Geom& g, int mode, const OutArgs& a, cudaStream_t st) {
+  switch (mode) {
+    case 0: { ADMMTV_TRY_TMA((k_dim1_out_tma<LM, 0>), Cfg::NT, a.spec, (const float2*)nullptr); break; }
+    case 2: { ADMMTV_TRY_TMA((k_dim1_out_tma<LM, 2>), Cfg::NT, a.spec, (const float2*)nullptr); break; }
+    default: { ADMMTV_TRY_TMA((k_dim1_out_tma<LM, 1>), Cfg::NT, a.spec, (const float2*)nullptr); break; }
+  }
   if (mode == 0) return launch_k(k_dim1_out<LM, 0>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
   if (mode == 2) return launch_k(k_dim1_out<LM, 2>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);
   return launch_k(k_dim1_out<LM, 1>, dim1_grid(g), Cfg::NT, Cfg::SMEM, st, a);

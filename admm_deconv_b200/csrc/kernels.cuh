@@ -174,7 +174,8 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #define ADMMTV_D2_SWZ 1   // XOR column swizzle of dim-2 tiles narrower than 16 rows (Dim2Cfg::SWZ)
 #endif
 #ifndef ADMMTV_REV1
-#define ADMMTV_REV1 0   // iteration dim-1 kernels walk (pair, tile) in DESCENDING order: they start on the spectra the dim-2 kernel wrote last (still in L2)
+#define ADMMTV_REV1 1   // iteration dim-1 kernels walk (pair, tile) in DESCENDING order: they start on the spectra the dim-2 kernel wrote last (still in L2),
+                        // and the ascending dim-2 kernel that follows starts on what they wrote last: cfg2 iteration 342 -> 336 us, 256^2 348 -> 344, 2048^2 604 -> 599
 #endif
 // block index of the iteration dim-1 kernels (k_dim1_fwd / k_dim1_bwd); the dim-2 kernels always ascend
 ADMMTV_DI int dim1_bid() {
@@ -526,8 +527,8 @@ ADMMTV_DI void dim1_fft_from_smem_tma(float2* X, int ncols, const CUtensorMap* m
 //           also accumulates the loss (admmtv_backward_mse: no xbar array, no separate loss kernel)
 // ------------------------------------------------------------------------------------------
 
-template <int LM, int MODE>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
+template <int LM, int MODE, bool TMA>
+ADMMTV_DI void pack_fft1_body(const PackArgs& A, const Dim1Tma* tm) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
   ADMMTV_DYN_SMEM(float2, X);
@@ -602,8 +603,22 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
   }
   __syncthreads();
   float2* sq = A.spec + (size_t)q * plane;
-  dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+  if constexpr (TMA) dim1_fft_from_smem_tma<LM, NT>(X, nout, &tm->out, q * N + j0, A.twM, tid);
+  else
+#endif
+    dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
 }
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
+  pack_fft1_body<LM, MODE, false>(A, nullptr);
+}
+#ifndef ADMMTV_EMU
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1_tma(PackArgs A, const __grid_constant__ Dim1Tma tm) {
+  pack_fft1_body<LM, MODE, true>(A, &tm);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // k_dim1_out: spectrum -> dim-1 IFFT -> spatial
@@ -611,8 +626,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_pack_fft1(PackArgs A) {
 //   MODE 1: user-layout planes, + bias, activation           (deconv_admm.jl:222-224, ops.jl:175)
 // ------------------------------------------------------------------------------------------
 
-template <int LM, int MODE>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
+template <int LM, int MODE, bool TMA>
+ADMMTV_DI void dim1_out_body(const OutArgs& A, const Dim1Tma* tm) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
   ADMMTV_DYN_SMEM(float2, X);
@@ -623,7 +638,12 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   const float2* sq = A.spec + (size_t)q * plane;
-  dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+  __shared__ unsigned long long tbar[1];
+  if constexpr (TMA) dim1_ifft_to_smem_tma<LM, NT>(X, nout, &tm->in, [&](int c) { return q * N + j0 + c; }, tbar, A.twM, tid);
+  else
+#endif
+    dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sq + (size_t)(j0 + c) * M; }, A.twM, tid);
   if (MODE == 0) {
     float2* dst = A.packed + (size_t)q * plane;
     const float sc = A.scale;
@@ -669,6 +689,16 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
     }
   }
 }
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out(OutArgs A) {
+  dim1_out_body<LM, MODE, false>(A, nullptr);
+}
+#ifndef ADMMTV_EMU
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_out_tma(OutArgs A, const __grid_constant__ Dim1Tma tm) {
+  dim1_out_body<LM, MODE, true>(A, &tm);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // k_dim1_fwd: the fused per-iteration kernel (anisotropic)

@@ -355,8 +355,8 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT, kDim1BwdMinB<LM, MODE>) k_dim
 // Last backward iteration (k = 1): rbar_1 -> bbar_total = bbar + rbar_1, then either its dim-1
 // FFT (MODE 0, feeds ybar = H bbar and the PSF correlation) or, with an empty PSF, ybar = bbar
 // straight to the user layout (MODE 1).
-template <int LM, int MODE>
-__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A) {
+template <int LM, int MODE, bool TMA>
+ADMMTV_DI void dim1_bwd_last_body(const Dim1BwdArgs& A, const Dim1Tma* tm) {
   using Cfg = Dim1Cfg<LM>;
   constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO;
   ADMMTV_DYN_SMEM(float2, X);
@@ -367,7 +367,12 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A
   const int nout = min(CO, N - j0);
   const size_t plane = (size_t)N * M;
   const float2* sin_q = A.spec_in + (size_t)q * plane;
-  dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sin_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+  __shared__ unsigned long long tbar[1];
+  if constexpr (TMA) dim1_ifft_to_smem_tma<LM, NT>(X, nout, &tm->in, [&](int c) { return q * N + j0 + c; }, tbar, A.twM, tid);
+  else
+#endif
+    dim1_ifft_to_smem<LM, NT>(X, nout, [&](int c) { return sin_q + (size_t)(j0 + c) * M; }, A.twM, tid);
   const float2* bq = A.bbar + (size_t)q * plane;
   const long ia = pm_in(A.pm, q, 0), ib = pm_in(A.pm, q, 1);  // ybar has y's layout
   const bool has_b = ib >= 0;
@@ -390,8 +395,22 @@ __global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A
   if (MODE == 0) {
     __syncthreads();
     float2* sout_q = A.spec_out + (size_t)q * plane;
-    dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
+#ifndef ADMMTV_EMU
+    if constexpr (TMA) dim1_fft_from_smem_tma<LM, NT>(X, nout, &tm->out, q * N + j0, A.twM, tid);
+    else
+#endif
+      dim1_fft_from_smem<LM, NT>(X, nout, [&](int c) { return sout_q + (size_t)(j0 + c) * M; }, A.twM, tid);
   }
 }
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last(Dim1BwdArgs A) {
+  dim1_bwd_last_body<LM, MODE, false>(A, nullptr);
+}
+#ifndef ADMMTV_EMU
+template <int LM, int MODE>
+__global__ void __launch_bounds__(Dim1Cfg<LM>::NT) k_dim1_bwd_last_tma(Dim1BwdArgs A, const __grid_constant__ Dim1Tma tm) {
+  dim1_bwd_last_body<LM, MODE, true>(A, &tm);
+}
+#endif
 
 }  // namespace admmtv
