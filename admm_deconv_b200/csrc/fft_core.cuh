@@ -26,8 +26,13 @@ namespace admmtv {
 #ifndef ADMMTV_PLAN2_512
 #define ADMMTV_PLAN2_512 0   // measured on B200 (64 x 512^2 x 3): 16 x 32 needs 128 registers (2 blocks/SM): k_dim2 97 -> 103 us, save variant 135 -> 120, accG 179 -> 192: net zero, off
 #endif
+#ifndef ADMMTV_PLAN2_2048
+#define ADMMTV_PLAN2_2048 0   // dim-2 plan of 2048: 0 = 16 x 16 x 8 (as dim 1), 1 = 8 x 8 x 8 x 4, 2 = 4 x 8 x 8 x 8 (radix-8 passes: fewer registers, more threads)
+#endif
 ADMMTV_HD constexpr int plan_radix(int L, int s, int P = 0) {
   if (P == 1 && ADMMTV_PLAN2_512 && L == 512) return s == 0 ? 16 : (s == 1 ? 32 : 1);
+  if (P == 1 && ADMMTV_PLAN2_2048 == 1 && L == 2048) return s < 3 ? 8 : (s == 3 ? 4 : 1);
+  if (P == 1 && ADMMTV_PLAN2_2048 == 2 && L == 2048) return s == 0 ? 4 : (s < 4 ? 8 : 1);
   switch (L) {
     case 32:   return s == 0 ? 8 : (s == 1 ? 4 : 1);
     case 64:   return s < 2 ? 8 : 1;

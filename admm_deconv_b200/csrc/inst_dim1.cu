@@ -38,32 +38,33 @@ static int launch_k(K kern, dim3 grid, int nt, size_t smem, cudaStream_t st, con
 
 constexpr int LM = ADMMTV_INST;
 using Cfg = Dim1Cfg<LM>;
-static dim3 dim1_grid(const Geom& g) { return dim3((unsigned)((g.N + Cfg::CO - 1) / Cfg::CO) * (unsigned)g.Q); }
+static dim3 dim1_grid(const Geom& g, int co = Cfg::CO) { return dim3((unsigned)((g.N + co - 1) / co) * (unsigned)g.Q); }
 
 // TMA variants of the iteration kernels: launched when the column maps of the two spectra can be encoded (a null pointer =
 // the kernel does not touch that side), else the caller falls through to the LDG / STG kernels.
 #ifndef ADMMTV_EMU
 template <class K, class Args>
-static int launch_tma(K kern, const Geom& g, int nt, const float2* in, const float2* out, cudaStream_t st, const Args& a) {
+static int launch_tma(K kern, const Geom& g, int nt, const float2* in, const float2* out, cudaStream_t st, const Args& a, int co = Cfg::CO,
+                      size_t smem = Cfg::SMEM) {
   Dim1Tma tm;
   const size_t ncols = (size_t)g.Q * g.N;
-  if (g.N % Cfg::CO != 0 || ncols >= 0x7fffffffull) return -100;
+  if (g.N % co != 0 || ncols >= 0x7fffffffull) return -100;
   if (tma_make_colmap(&tm.in, in ? in : out, g.M, ncols) != 0 || tma_make_colmap(&tm.out, out ? out : in, g.M, ncols) != 0) return -100;
-  if (Cfg::SMEM + 2048 > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (smem + 2048 > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<dim1_grid(g), dim3(nt), Cfg::SMEM, st>>>(a, tm);
+  kern<<<dim1_grid(g, co), dim3(nt), smem, st>>>(a, tm);
   ADMMTV_CHECK_LAUNCH();
   return 0;
 }
-#define ADMMTV_TRY_TMA(KERN, NT_, IN, OUT)                             \
-  if constexpr (kDim1TmaOk<LM>) {                                      \
-    const int rc__ = launch_tma(KERN, g, NT_, IN, OUT, st, a);         \
-    if (rc__ != -100) return rc__;                                     \
+#define ADMMTV_TRY_TMA(KERN, NT_, IN, OUT, ...)                                 \
+  if constexpr (kDim1TmaOk<LM>) {                                               \
+    const int rc__ = launch_tma(KERN, g, NT_, IN, OUT, st, a, ##__VA_ARGS__);   \
+    if (rc__ != -100) return rc__;                                              \
   }
 #else
-#define ADMMTV_TRY_TMA(KERN, NT_, IN, OUT)
+#define ADMMTV_TRY_TMA(KERN, NT_, IN, OUT, ...)
 #endif
 
 template <>

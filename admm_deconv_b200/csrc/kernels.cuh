@@ -137,6 +137,9 @@ ADMMTV_DI float act_grad_from_out(float o, int act) {
 #ifndef ADMMTV_TR9
 #define ADMMTV_TR9 16
 #endif
+#ifndef ADMMTV_TC8B
+#define ADMMTV_TC8B 18   // backward tile at M = 256: 16 + 2 columns (12 % halo instead of 25 %): k_dim1_bwd_tma<8> 392 -> 365 us on 256 x 256^2 x 3
+#endif
 #ifndef ADMMTV_TC7
 #define ADMMTV_TC7 10   // 128-row planes: 8 + 2 columns, chunk 4, 8 blocks/SM: dim-1 111 -> 94 us on 1024 x 128^2 (gpurun_out/v4_128b.log)
 #endif
@@ -221,6 +224,10 @@ struct Dim1Cfg {
                                   : (LM <= 6 ? 34 : (LM == 7 ? ADMMTV_TC7 : (LM == 8 ? ADMMTV_TC8 : (LM == 9 ? ADMMTV_TC9 : (LM == 11 ? ADMMTV_TC11 : 6)))));
   static constexpr int CO = TC - 2;                   // output columns per block
   static constexpr size_t SMEM = (size_t)TC * M * sizeof(float2);
+  // the backward iteration kernel (k_dim1_bwd, 2 blocks of 128 registers per SM at M = 256) may use a wider tile
+  static constexpr int TCB = LM == 8 ? ADMMTV_TC8B : TC;
+  static constexpr int COB = TCB - 2;
+  static constexpr size_t SMEMB = (size_t)TCB * M * sizeof(float2);
   static_assert(M % NT == 0 && NT % 32 == 0, "dim-1 block must tile the column in whole warps");
 };
 
@@ -343,7 +350,7 @@ ADMMTV_DI void dim1_ifft_to_smem(float2* X, int ncols, ColPtr colptr, const floa
   constexpr int M = dim_len(LM), NS = plan_stages(M);
   using St = Stage<M, NS - 1>;
   static_assert(St::STRIDE == 1, "last plan stage must be contiguous");
-  constexpr int TCMAX = Dim1Cfg<LM>::TC;
+  constexpr int TCMAX = Dim1Cfg<LM>::TC > Dim1Cfg<LM>::TCB ? Dim1Cfg<LM>::TC : Dim1Cfg<LM>::TCB;   // widest tile any caller passes
   if constexpr (ADMMTV_PRELOAD1 && NT >= St::ITEMS && (TCMAX + NT / St::ITEMS - 1) / (NT / St::ITEMS) * St::R <= 24) {
     // all of this thread's global loads of the pass are issued before the first butterfly
     constexpr int CSTEP = NT / St::ITEMS, ROUNDS = (TCMAX + CSTEP - 1) / CSTEP;

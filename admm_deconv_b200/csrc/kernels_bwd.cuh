@@ -84,7 +84,7 @@ constexpr int kDim1BwdMinB = (LM == 9 && MODE == 0) ? ADMMTV_MINB9B : (LM == 8 ?
 template <int LM, bool HAS_VBAR, int MODE, bool TMA>
 ADMMTV_DI void dim1_bwd_body(const Dim1BwdArgs& A, const Dim1Tma* tm) {
   using Cfg = Dim1Cfg<LM>;
-  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::CO, RPT = Cfg::RPT, CHUNK = Cfg::CHUNKB;
+  constexpr int M = Cfg::M, NT = Cfg::NT, CO = Cfg::COB, RPT = Cfg::RPT, CHUNK = Cfg::CHUNKB;
   static_assert(CO % CHUNK == 0, "chunking must divide the tile");
   ADMMTV_DYN_SMEM(float2, X);
   // 1-D grid: block = (pair q, column tile), tiles fastest (no 65535 limit on the number of pairs)
