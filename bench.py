@@ -574,8 +574,8 @@ def run_train(c, w, name, steps, warmup, full, min_ms=0.0):
         return r, None
     f, b = ts.profile()
     n2, n1 = K, max(K - 1, 1)
-    kt = {"k_dim2<save F r_k>": f[1] / n2, "k_dim1_fwd": f[2] / n1, "k_dim2<G += Re(conj Z Z2)>": b[1] / n2, "k_dim1_bwd": b[2] / n1}
-    actual = {"k_dim2<save F r_k>": 12.0, "k_dim1_fwd": 28.0, "k_dim2<G += Re(conj Z Z2)>": 12.0, "k_dim1_bwd": 40.0}
+    kt = {"k_dim2t<save F r_k>": f[1] / n2, "k_dim1_fwd_tma": f[2] / n1, "k_dim2<G += Re(conj Z Z2)>": b[1] / n2, "k_dim1_bwd_tma": b[2] / n1}
+    actual = {"k_dim2t<save F r_k>": 12.0, "k_dim1_fwd_tma": 28.0, "k_dim2<G += Re(conj Z Z2)>": 12.0, "k_dim1_bwd_tma": 40.0}
     it_ms = sum(kt.values())
     achieved = (FWD_BYTES + BWD_BYTES) * ts.px / (it_ms * 1e-3) / 1e9
     traffic, tsrc = None, None
@@ -587,7 +587,7 @@ def run_train(c, w, name, steps, warmup, full, min_ms=0.0):
         except Exception:
             pass
     roofline = {
-        "bound": "hbm", "kernel": "one fwd+bwd ADMM iteration = k_dim2<save> + k_dim1_fwd + k_dim2<accG> + k_dim1_bwd (4 launches)",
+        "bound": "hbm", "kernel": "one fwd+bwd ADMM iteration = k_dim2t<save> + k_dim1_fwd_tma + k_dim2<accG> + k_dim1_bwd_tma (4 launches)",
         "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
         "traffic": traffic, "traffic_source": tsrc or "not measured in this run (ncu --set full capture under profiles/)",
         "peak_source": pk_src, "algorithmic_bytes_per_plane_pixel_iteration": FWD_BYTES + BWD_BYTES,
