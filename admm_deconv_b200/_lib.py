@@ -48,6 +48,11 @@ LOSS_SYMBOLS = (
     "admmtv_ssim_workspace_bytes",
     "admmtv_ssim_forward",
     "admmtv_ssim_backward",
+    "admmtv_ssim_window_workspace_bytes",
+    "admmtv_ssim_window_forward",
+    "admmtv_ssim_window_backward",
+    "admmtv_pad_symmetric",
+    "admmtv_pad_symmetric_adjoint",
 )
 # every symbol include/admmtv_host.h declares
 HOST_SYMBOLS = (
@@ -131,6 +136,12 @@ class AdmmTvLib:
         L.admmtv_ssim_workspace_bytes.argtypes = [i, i, i, i, i, i, C.POINTER(sz)]
         L.admmtv_ssim_forward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, f, i, vp, vp, i, vp]
         L.admmtv_ssim_backward.argtypes = [i, i, i, i, i, vp, vp, C.POINTER(f), i, i, vp, vp, vp, vp]
+        fp = C.POINTER(f)
+        L.admmtv_ssim_window_workspace_bytes.argtypes = [i, i, i, i, i, i, i, C.POINTER(sz)]
+        L.admmtv_ssim_window_forward.argtypes = [i, i, i, i, i, vp, vp, fp, fp, i, i, i, f, i, vp, vp, i, vp]
+        L.admmtv_ssim_window_backward.argtypes = [i, i, i, i, i, vp, vp, fp, fp, i, i, i, i, vp, vp, vp, vp]
+        L.admmtv_pad_symmetric.argtypes = [i, i, i, i, i, i, i, i, vp, vp, vp]
+        L.admmtv_pad_symmetric_adjoint.argtypes = [i, i, i, i, i, i, i, i, vp, vp, vp]
         L.admmtv_batch_from_n0f8.argtypes = [i, i, i, i, i, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp]
         L.admmtv_batch_gather_n0f8.argtypes = [i, i, i, i, i, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, vp]
         self.has_host = hasattr(L, "admmtv_host_wait")   # the test-only CPU emulation build has no host-buffer layer
@@ -281,6 +292,37 @@ class AdmmTvLib:
         arr, L = self._taps(taps)
         self._raise(self.lib.admmtv_ssim_forward(M, N, Cc, B, device, x, y, arr, L, peakval, int(as_loss), out, ws,
                                                  int(with_grad), stream))
+
+    @staticmethod
+    def _factors(u, v):
+        """u: R x L1, v: R x L2 nested sequences -> (float arrays, L1, L2, R)"""
+        R, L1, L2 = len(u), len(u[0]), len(v[0])
+        ua = (C.c_float * (R * L1))(*[float(t) for row in u for t in row])
+        va = (C.c_float * (R * L2))(*[float(t) for row in v for t in row])
+        return ua, va, L1, L2, R
+
+    def ssim_window_workspace_bytes(self, M, N, Cc, B, L1, L2, with_grad=True) -> int:
+        n = C.c_size_t()
+        self._raise(self.lib.admmtv_ssim_window_workspace_bytes(M, N, Cc, B, L1, L2, int(with_grad), C.byref(n)))
+        return n.value
+
+    def ssim_window_forward(self, M, N, Cc, B, device, x, y, u, v, peakval, as_loss, out, ws, with_grad, stream=0):
+        ua, va, L1, L2, R = self._factors(u, v)
+        self._raise(self.lib.admmtv_ssim_window_forward(M, N, Cc, B, device, x, y, ua, va, L1, L2, R, peakval, int(as_loss),
+                                                        out, ws, int(with_grad), stream))
+
+    def ssim_window_backward(self, M, N, Cc, B, device, x, y, u, v, as_loss, outbar, ws, xbar, stream=0):
+        ua, va, L1, L2, R = self._factors(u, v)
+        self._raise(self.lib.admmtv_ssim_window_backward(M, N, Cc, B, device, x, y, ua, va, L1, L2, R, int(as_loss), outbar,
+                                                         ws, xbar, stream))
+
+    def pad_symmetric(self, M, N, planes, pads, device, src, dst, stream=0):
+        lo1, hi1, lo2, hi2 = pads
+        self._raise(self.lib.admmtv_pad_symmetric(M, N, planes, lo1, hi1, lo2, hi2, device, src, dst, stream))
+
+    def pad_symmetric_adjoint(self, M, N, planes, pads, device, padded_bar, src_bar, stream=0):
+        lo1, hi1, lo2, hi2 = pads
+        self._raise(self.lib.admmtv_pad_symmetric_adjoint(M, N, planes, lo1, hi1, lo2, hi2, device, padded_bar, src_bar, stream))
 
     def batch_from_n0f8(self, M, N, Cc, B, device, src, sc, si, sj, sb, dst, stream=0):
         self._raise(self.lib.admmtv_batch_from_n0f8(M, N, Cc, B, device, src, sc, si, sj, sb, dst, stream))

@@ -29,7 +29,12 @@ namespace admmtv {
 #ifndef ADMMTV_PLAN2_2048
 #define ADMMTV_PLAN2_2048 0   // dim-2 plan of 2048: 0 = 16 x 16 x 8 (as dim 1), 1 = 8 x 8 x 8 x 4, 2 = 4 x 8 x 8 x 8 (radix-8 passes: fewer registers, more threads)
 #endif
+#ifndef ADMMTV_PLANC_1024
+#define ADMMTV_PLANC_1024 0   // plan id 2 = the half-line transforms of the 2-CTA-cluster dim-2 pass (kernels_cluster.cuh); 1024: 0 = 16 x 8 x 8, 1 = 8 x 8 x 16, 2 = 8 x 16 x 8
+#endif
 ADMMTV_HD constexpr int plan_radix(int L, int s, int P = 0) {
+  if (P == 2 && ADMMTV_PLANC_1024 == 1 && L == 1024) return s < 2 ? 8 : (s == 2 ? 16 : 1);
+  if (P == 2 && ADMMTV_PLANC_1024 == 2 && L == 1024) return s == 0 ? 8 : (s == 1 ? 16 : (s == 2 ? 8 : 1));
   if (P == 1 && ADMMTV_PLAN2_512 && L == 512) return s == 0 ? 16 : (s == 1 ? 32 : 1);
   if (P == 1 && ADMMTV_PLAN2_2048 == 1 && L == 2048) return s < 3 ? 8 : (s == 3 ? 4 : 1);
   if (P == 1 && ADMMTV_PLAN2_2048 == 2 && L == 2048) return s == 0 ? 4 : (s < 4 ? 8 : 1);

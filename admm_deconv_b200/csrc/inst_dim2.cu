@@ -8,6 +8,7 @@ template <> int Dim2Launch<ADMMTV_INST>::row_tile() { return 0; }
 #else
 #include "kernels.cuh"
 #include "kernels_tma.cuh"
+#include "kernels_cluster.cuh"
 
 #ifndef ADMMTV_INST
 #error "compile with -DADMMTV_INST=<log2 N>"
@@ -19,6 +20,12 @@ template <> int Dim2Launch<ADMMTV_INST>::row_tile() { return 0; }
 // ... and which variants take it there: 0 = only the checkpoint-saving ones (training forward), 1 = all without accumulation
 #ifndef ADMMTV_D2_TMA_ALL
 #define ADMMTV_D2_TMA_ALL 0
+#endif
+
+// lengths whose inference dim-2 pass (no checkpoint, no gradient accumulation) runs the 2-CTA-cluster kernel k_dim2c
+// (kernels_cluster.cuh): bit (LN - 5) of this mask
+#ifndef ADMMTV_D2_CLUSTER_MASK
+#define ADMMTV_D2_CLUSTER_MASK (1 << (12 - 5))   // measured (profiles/r2c_experiments.md): N = 4096 293 -> 287 us; N = 2048 216 -> 221 us (off)
 #endif
 
 namespace admmtv {
@@ -73,6 +80,34 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
   if (variant == D2_C_ACCG && gy == g.Q) gy = (g.Q + ADMMTV_D2_ACC_QPB - 1) / ADMMTV_D2_ACC_QPB;
   if (gy > 65535) gy = 65535;  // blocks loop over pairs with stride gridDim.y
 #ifndef ADMMTV_EMU
+  if constexpr (LN >= 10 && LN <= 12 && ((ADMMTV_D2_CLUSTER_MASK >> (LN - 5)) & 1)) {
+    if constexpr (Dim2cCfg<LN>::OK) {
+      using CC = Dim2cCfg<LN>;
+      const dim3 cgrid((unsigned)(CC::CS * (g.M / CC::TR)), (unsigned)gy);   // x = CS * row tile + rank in the cluster
+      // once per process: can a cluster of CS such blocks be co-scheduled at all on this device / partition?
+      static const bool cluster_ok = [] {
+        int n = 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CC::CS, 1, 1); cfg.blockDim = dim3(CC::NT, 1, 1); cfg.dynamicSmemBytes = CC::SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CC::CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaFuncSetAttribute(k_dim2c<LN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC::SMEM) != cudaSuccess ||
+            cudaOccupancyMaxActiveClusters(&n, k_dim2c<LN, 0>, &cfg) != cudaSuccess) {
+          cudaGetLastError();
+          return false;
+        }
+        return n > 0;
+      }();
+      if (cluster_ok && g.M % CC::TR == 0) switch (variant) {
+        case D2_C: return launch_k(k_dim2c<LN, 0>, cgrid, CC::NT, CC::SMEM, st, a);
+        case D2_KCONJ: return launch_k(k_dim2c<LN, 1>, cgrid, CC::NT, CC::SMEM, st, a);
+        case D2_K: return launch_k(k_dim2c<LN, 2>, cgrid, CC::NT, CC::SMEM, st, a);
+        default: break;
+      }
+    }
+  }
   if constexpr (LN >= 5 && LN <= 12 && Dim2tCfg<LN>::OK && ((ADMMTV_D2_TMA_MASK >> (LN - 5)) & 1)) {
     // TMA-pipelined persistent kernel for the variants without gradient accumulation
     if (variant != D2_C_ACCG && variant != D2_K_ACCP && (ADMMTV_D2_TMA_ALL || variant == D2_C_SAVE || variant == D2_KCONJ_SAVE)) {

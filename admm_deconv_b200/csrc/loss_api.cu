@@ -46,6 +46,38 @@ int ssim_args(SsimArgs& a, int M, int N, int C, int B, const float* taps, int L)
   return ADMMTV_OK;
 }
 
+// general window: R separable terms u_r (L1 taps, dim 1) x v_r (L2 taps, dim 2), row-major [R][L]
+int ssim_gen_args(SsimGenArgs& g, int M, int N, int C, int B, const float* u, const float* v, int L1, int L2, int R) {
+  int rc = check_shape(M, N, C, B);
+  if (rc) return rc;
+  if (L1 < 1 || L1 > SS_LMAX || L2 < 1 || L2 > SS_LMAX || R < 1 || R > SS_LMAX) return ADMMTV_ERR_UNSUPPORTED;
+  if (L1 > M || L2 > N) return ADMMTV_ERR_SHAPE;  // the valid-size map would be empty
+  SsimArgs& a = g.a;
+  a.M = M; a.N = N; a.C = C; a.B = B; a.L = 0;
+  a.Mo = M - L1 + 1; a.No = N - L2 + 1;
+  g.L1 = L1; g.L2 = L2; g.R = R;
+  for (int r = 0; r < R; ++r) {   // flipped: NNlib conv is a true convolution (ssim.jl:112-119)
+    for (int k = 0; k < SS_LMAX; ++k) {
+      g.fu[r * SS_LMAX + k] = (u && k < L1) ? u[r * L1 + (L1 - 1 - k)] : 0.f;
+      g.fv[r * SS_LMAX + k] = (v && k < L2) ? v[r * L2 + (L2 - 1 - k)] : 0.f;
+    }
+  }
+  return ADMMTV_OK;
+}
+
+int pad_args(PadArgs& a, int M, int N, int planes, int lo1, int hi1, int lo2, int hi2) {
+  if (M <= 0 || N <= 0 || planes <= 0) return ADMMTV_ERR_SHAPE;
+  if (lo1 < 0 || hi1 < 0 || lo2 < 0 || hi2 < 0) return ADMMTV_ERR_SHAPE;
+  if (lo1 > M || hi1 > M || lo2 > N || hi2 > N) return ADMMTV_ERR_SHAPE;   // NNlib: the pad cannot exceed the array size
+  a.M = M; a.N = N; a.planes = planes; a.lo1 = lo1; a.hi1 = hi1; a.lo2 = lo2; a.hi2 = hi2;
+  return ADMMTV_OK;
+}
+
+unsigned pad_grid(size_t total) {
+  size_t nb = (total + 255) / 256;
+  return (unsigned)(nb > 148 * 64 ? 148 * 64 : (nb ? nb : 1));
+}
+
 }  // namespace
 }  // namespace admmtv
 
@@ -177,6 +209,108 @@ int admmtv_ssim_backward(int M, int N, int C, int B, int device, const float* x,
   if (a.L == 11) ADMMTV_LAUNCH(k_ssim_bwd<11>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   else if (a.L == 5) ADMMTV_LAUNCH(k_ssim_bwd<5>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   else ADMMTV_LAUNCH(k_ssim_bwd<0>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADMMTV_OK : (int)e;
+}
+
+int admmtv_ssim_window_workspace_bytes(int M, int N, int C, int B, int L1, int L2, int with_grad, size_t* bytes) {
+  SsimGenArgs g{};
+  int rc = ssim_gen_args(g, M, N, C, B, nullptr, nullptr, L1, L2, 1);
+  if (rc) return rc;
+  size_t n = up256(sizeof(double));
+  if (with_grad) n += up256(3 * (size_t)g.a.Mo * g.a.No * C * B * sizeof(float));
+  if (bytes) *bytes = n;
+  return ADMMTV_OK;
+}
+
+int admmtv_ssim_window_forward(int M, int N, int C, int B, int device, const float* x, const float* y, const float* u,
+                               const float* v, int L1, int L2, int R, float peakval, int as_loss, float* out, void* workspace,
+                               int with_grad, void* stream) {
+  if (!u || !v) return ADMMTV_ERR_NULL;
+  SsimGenArgs g{};
+  int rc = ssim_gen_args(g, M, N, C, B, u, v, L1, L2, R);
+  if (rc) return rc;
+  if (!x || !y || !out || !workspace) return ADMMTV_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return ADMMTV_ERR_ALIGN;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SsimArgs& a = g.a;
+  a.x = x; a.y = y;
+  a.C1 = (peakval * 0.01f) * (peakval * 0.01f);  // ssim.jl:101-102
+  a.C2 = (peakval * 0.03f) * (peakval * 0.03f);
+  a.tiles_i = (a.Mo + SS_T - 1) / SS_T; a.tiles_j = (a.No + SS_T - 1) / SS_T;
+  a.acc = reinterpret_cast<double*>(workspace);
+  a.maps = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + up256(sizeof(double)));
+  a.with_grad = with_grad ? 1 : 0;
+  a.as_loss = as_loss ? 1 : 0;
+  a.out = out;
+  cudaError_t e = cudaMemsetAsync(a.acc, 0, sizeof(double), st);
+  if (e != cudaSuccess) return (int)e;
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_ssim_fwd_gen, dim3((unsigned)nblk), dim3(SS_NT), 0, st, g);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  ADMMTV_LAUNCH(k_ssim_finalize, dim3(1), dim3(1), 0, st, a);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  return ADMMTV_OK;
+}
+
+int admmtv_ssim_window_backward(int M, int N, int C, int B, int device, const float* x, const float* y, const float* u,
+                                const float* v, int L1, int L2, int R, int as_loss, const float* outbar, const void* workspace,
+                                float* xbar, void* stream) {
+  if (!u || !v) return ADMMTV_ERR_NULL;
+  SsimGenArgs g{};
+  int rc = ssim_gen_args(g, M, N, C, B, u, v, L1, L2, R);
+  if (rc) return rc;
+  if (!x || !y || !outbar || !workspace || !xbar) return ADMMTV_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return ADMMTV_ERR_ALIGN;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SsimArgs& a = g.a;
+  a.x = x; a.y = y;
+  a.tiles_i = (M + SS_T - 1) / SS_T; a.tiles_j = (N + SS_T - 1) / SS_T;
+  unsigned char* ws = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(workspace));
+  a.acc = reinterpret_cast<double*>(ws);
+  a.maps = reinterpret_cast<float*>(ws + up256(sizeof(double)));
+  a.with_grad = 1;
+  a.as_loss = as_loss ? 1 : 0;
+  a.outbar = outbar;
+  a.out = xbar;
+  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
+  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_ssim_bwd_gen, dim3((unsigned)nblk), dim3(SS_NT), 0, st, g);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADMMTV_OK : (int)e;
+}
+
+int admmtv_pad_symmetric(int M, int N, int planes, int lo1, int hi1, int lo2, int hi2, int device, const float* src,
+                         float* dst, void* stream) {
+  PadArgs a{};
+  int rc = pad_args(a, M, N, planes, lo1, hi1, lo2, hi2);
+  if (rc) return rc;
+  if (!src || !dst) return ADMMTV_ERR_NULL;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  a.src = src; a.dst = dst;
+  const size_t total = (size_t)(M + lo1 + hi1) * (N + lo2 + hi2) * planes;
+  ADMMTV_LAUNCH(k_pad_symmetric, dim3(pad_grid(total)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADMMTV_OK : (int)e;
+}
+
+int admmtv_pad_symmetric_adjoint(int M, int N, int planes, int lo1, int hi1, int lo2, int hi2, int device,
+                                 const float* padded_bar, float* src_bar, void* stream) {
+  PadArgs a{};
+  int rc = pad_args(a, M, N, planes, lo1, hi1, lo2, hi2);
+  if (rc) return rc;
+  if (!padded_bar || !src_bar) return ADMMTV_ERR_NULL;
+  DevGuard guard(device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  a.src = padded_bar; a.dst = src_bar;
+  const size_t total = (size_t)M * N * planes;
+  ADMMTV_LAUNCH(k_pad_symmetric_adj, dim3(pad_grid(total)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ADMMTV_OK : (int)e;
 }

@@ -217,6 +217,21 @@ struct SsimArgs {
   float* out;         // forward: ssim or 1-ssim ; backward: xbar
 };
 
+// One output pixel of the SSIM map from the five window means (ssim.jl:114-121); with_grad: its three derivative maps.
+ADMMTV_DI float ssim_point(const SsimArgs& A, float mx, float my, float exx, float eyy, float exy, size_t o, size_t mapstride) {
+  const float mxy = mx * my, mx2 = mx * mx, my2 = my * my;
+  const float sx2 = exx - mx2, sy2 = eyy - my2, sxy = exy - mxy;                   // ssim.jl:117-119
+  const float A1 = 2.f * mxy + A.C1, A2 = 2.f * sxy + A.C2, B1 = mx2 + my2 + A.C1, B2 = sx2 + sy2 + A.C2;
+  const float S = A1 * A2 / (B1 * B2);                                             // ssim.jl:121
+  if (A.with_grad) {
+    const float ib = 1.f / (B1 * B2);
+    A.maps[o] = 2.f * my * (A2 - A1) * ib - 2.f * mx * S * (1.f / B1 - 1.f / B2);   // dS/dmu_x
+    A.maps[mapstride + o] = -S / B2;                                               // dS/dE[x^2]
+    A.maps[2 * mapstride + o] = 2.f * A1 * ib;                                     // dS/dE[xy]
+  }
+  return S;
+}
+
 // LC: compile-time number of taps (11 = the default Gaussian, 5 = ssim_loss_fast: window loops fully unrolled), 0 = run-time A.L
 template <int LC>
 __global__ void __launch_bounds__(SS_NT) k_ssim_fwd(SsimArgs A) {
@@ -261,18 +276,7 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_fwd(SsimArgs A) {
         const int o = (lj + a) * SS_T + li;
         mx += w * P[0][o]; my += w * P[1][o]; exx += w * P[2][o]; eyy += w * P[3][o]; exy += w * P[4][o];
       }
-      const float mxy = mx * my, mx2 = mx * mx, my2 = my * my;
-      const float sx2 = exx - mx2, sy2 = eyy - my2, sxy = exy - mxy;                   // ssim.jl:117-119
-      const float A1 = 2.f * mxy + A.C1, A2 = 2.f * sxy + A.C2, B1 = mx2 + my2 + A.C1, B2 = sx2 + sy2 + A.C2;
-      const float S = A1 * A2 / (B1 * B2);                                             // ssim.jl:121
-      tot += (double)S;
-      if (A.with_grad) {
-        const float ib = 1.f / (B1 * B2);
-        const size_t o = (size_t)s * oplane + (size_t)(j0 + lj) * A.Mo + i0 + li;
-        A.maps[o] = 2.f * my * (A2 - A1) * ib - 2.f * mx * S * (1.f / B1 - 1.f / B2);   // dS/dmu_x
-        A.maps[nplanes * oplane + o] = -S / B2;                                        // dS/dE[x^2]
-        A.maps[2 * nplanes * oplane + o] = 2.f * A1 * ib;                              // dS/dE[xy]
-      }
+      tot += (double)ssim_point(A, mx, my, exx, eyy, exy, (size_t)s * oplane + (size_t)(j0 + lj) * A.Mo + i0 + li, nplanes * oplane);
     }
   }
   tot = block_sum(tot);
@@ -335,6 +339,186 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_bwd(SsimArgs A) {
       const size_t g = (size_t)gj * A.M + gi;
       xb[g] = scale * (r0 + 2.f * xp[g] * r1 + yp[g] * r2);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SSIM with an ARBITRARY 2-D window (ssim.jl:84 `kernel_ref`: any (L1, L2) array, e.g. a non-separable or non-square one).
+// The host factors the window into R <= min(L1, L2) separable terms  W[a,b] = sum_r u_r[a] v_r[b]  (SVD); convolution is linear
+// in the window, so each of the five window means is the sum of R separable passes through the same shared-memory tile.
+// ------------------------------------------------------------------------------------------
+struct SsimGenArgs {
+  SsimArgs a;                      // f[] unused; Mo = M - L1 + 1, No = N - L2 + 1
+  int L1, L2, R;
+  float fu[SS_LMAX * SS_LMAX];     // [R][SS_LMAX] flipped dim-1 factors
+  float fv[SS_LMAX * SS_LMAX];     // [R][SS_LMAX] flipped dim-2 factors
+};
+constexpr int SS_PT = SS_T * SS_T / SS_NT;   // output pixels per thread
+
+__global__ void __launch_bounds__(SS_NT) k_ssim_fwd_gen(SsimGenArgs G) {
+  const SsimArgs& A = G.a;
+  __shared__ float xs[SS_IN * SS_IN], ys[SS_IN * SS_IN];
+  __shared__ float P[5][SS_IN * SS_T];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L1 = G.L1, L2 = G.L2;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
+  const size_t plane = (size_t)A.M * A.N;
+  const float* xp = A.x + (size_t)s * plane;
+  const float* yp = A.y + (size_t)s * plane;
+  const int ext_i = SS_T + L1 - 1, ext_j = SS_T + L2 - 1;
+  for (int e = tid; e < ext_i * ext_j; e += SS_NT) {
+    const int li = e % ext_i, lj = e / ext_i;
+    const int gi = i0 + li, gj = j0 + lj;
+    const bool ok = gi < A.M && gj < A.N;
+    xs[lj * SS_IN + li] = ok ? xp[(size_t)gj * A.M + gi] : 0.f;
+    ys[lj * SS_IN + li] = ok ? yp[(size_t)gj * A.M + gi] : 0.f;
+  }
+  float acc[SS_PT][5];
+#pragma unroll
+  for (int k = 0; k < SS_PT; ++k)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) acc[k][c] = 0.f;
+  for (int r = 0; r < G.R; ++r) {
+    __syncthreads();   // the tile is loaded / the previous term's second pass has read P
+    const float* fu = G.fu + r * SS_LMAX;
+    const float* fv = G.fv + r * SS_LMAX;
+    for (int e = tid; e < SS_T * ext_j; e += SS_NT) {
+      const int li = e % SS_T, lj = e / SS_T;
+      float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+      for (int a = 0; a < L1; ++a) {
+        const float w = fu[a], xv = xs[lj * SS_IN + li + a], yv = ys[lj * SS_IN + li + a];
+        sx += w * xv; sy += w * yv; sxx += w * xv * xv; syy += w * yv * yv; sxy += w * xv * yv;
+      }
+      P[0][e] = sx; P[1][e] = sy; P[2][e] = sxx; P[3][e] = syy; P[4][e] = sxy;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SS_PT; ++k) {
+      const int e = tid + k * SS_NT, li = e % SS_T, lj = e / SS_T;
+      for (int b = 0; b < L2; ++b) {
+        const float w = fv[b];
+        const int o = (lj + b) * SS_T + li;
+        acc[k][0] += w * P[0][o]; acc[k][1] += w * P[1][o]; acc[k][2] += w * P[2][o]; acc[k][3] += w * P[3][o]; acc[k][4] += w * P[4][o];
+      }
+    }
+  }
+  double tot = 0.0;
+  const size_t oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
+#pragma unroll
+  for (int k = 0; k < SS_PT; ++k) {
+    const int e = tid + k * SS_NT, li = e % SS_T, lj = e / SS_T;
+    if (i0 + li < A.Mo && j0 + lj < A.No)
+      tot += (double)ssim_point(A, acc[k][0], acc[k][1], acc[k][2], acc[k][3], acc[k][4],
+                                (size_t)s * oplane + (size_t)(j0 + lj) * A.Mo + i0 + li, nplanes * oplane);
+  }
+  tot = block_sum(tot);
+  if (tid == 0) atomicAdd(A.acc, tot);
+}
+
+__global__ void __launch_bounds__(SS_NT) k_ssim_bwd_gen(SsimGenArgs G) {
+  const SsimArgs& A = G.a;
+  __shared__ float ms[3][SS_IN * SS_IN];
+  __shared__ float T[3][SS_IN * SS_T];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j, L1 = G.L1, L2 = G.L2;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
+  const size_t plane = (size_t)A.M * A.N, oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
+  const int ext_i = SS_T + L1 - 1, ext_j = SS_T + L2 - 1;
+  // derivative maps over output positions [i0-L1+1, i0+T) x [j0-L2+1, j0+T), zero outside the valid region
+  for (int e = tid; e < ext_i * ext_j; e += SS_NT) {
+    const int li = e % ext_i, lj = e / ext_i;
+    const int pi = i0 - (L1 - 1) + li, pj = j0 - (L2 - 1) + lj;
+    const bool ok = pi >= 0 && pj >= 0 && pi < A.Mo && pj < A.No;
+    const size_t o = (size_t)s * oplane + (size_t)(ok ? pj : 0) * A.Mo + (ok ? pi : 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ms[k][lj * SS_IN + li] = ok ? A.maps[k * nplanes * oplane + o] : 0.f;
+  }
+  float acc[SS_PT][3];
+#pragma unroll
+  for (int k = 0; k < SS_PT; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+  for (int r = 0; r < G.R; ++r) {
+    __syncthreads();
+    const float* fu = G.fu + r * SS_LMAX;
+    const float* fv = G.fv + r * SS_LMAX;
+    // transposed window along dim 1: t[qi, pj] = sum_a fu[a] map[qi - a, pj]
+    for (int e = tid; e < SS_T * ext_j; e += SS_NT) {
+      const int li = e % SS_T, lj = e / SS_T;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      for (int a = 0; a < L1; ++a) {
+        const float w = fu[a];
+        const int o = lj * SS_IN + li + (L1 - 1) - a;
+        r0 += w * ms[0][o]; r1 += w * ms[1][o]; r2 += w * ms[2][o];
+      }
+      T[0][e] = r0; T[1][e] = r1; T[2][e] = r2;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SS_PT; ++k) {
+      const int e = tid + k * SS_NT, li = e % SS_T, lj = e / SS_T;
+      for (int b = 0; b < L2; ++b) {
+        const float w = fv[b];
+        const int o = (lj + (L2 - 1) - b) * SS_T + li;
+        acc[k][0] += w * T[0][o]; acc[k][1] += w * T[1][o]; acc[k][2] += w * T[2][o];
+      }
+    }
+  }
+  const float scale = (float)((double)A.outbar[0] * (A.as_loss ? -1.0 : 1.0) / ((double)A.Mo * A.No * A.C * A.B));
+  const float* xp = A.x + (size_t)s * plane;
+  const float* yp = A.y + (size_t)s * plane;
+  float* xb = A.out + (size_t)s * plane;
+#pragma unroll
+  for (int k = 0; k < SS_PT; ++k) {
+    const int e = tid + k * SS_NT, li = e % SS_T, lj = e / SS_T;
+    const int gi = i0 + li, gj = j0 + lj;
+    if (gi < A.M && gj < A.N) {
+      const size_t g = (size_t)gj * A.M + gi;
+      xb[g] = scale * (acc[k][0] + 2.f * xp[g] * acc[k][1] + yp[g] * acc[k][2]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pad_symmetric (NNlib; ssim.jl:104-110 `crop = false`): the border values are mirrored INCLUDING the edge sample,
+//   dst[i, j] = src[mir(i - lo1, M), mir(j - lo2, N)],   mir(t, n) = t < 0 ? -1 - t : (t >= n ? 2n - 1 - t : t)
+// and its adjoint (the pullback Zygote derives): every source pixel collects the cotangents of its mirror images.
+// ------------------------------------------------------------------------------------------
+struct PadArgs {
+  const float* src;
+  float* dst;
+  int M, N, planes;       // unpadded plane size
+  int lo1, hi1, lo2, hi2;
+};
+ADMMTV_DI int mir_sym(int t, int n) { return t < 0 ? -1 - t : (t >= n ? 2 * n - 1 - t : t); }
+
+__global__ void __launch_bounds__(256) k_pad_symmetric(PadArgs A) {
+  const int Mp = A.M + A.lo1 + A.hi1, Np = A.N + A.lo2 + A.hi2;
+  const size_t total = (size_t)Mp * Np * A.planes;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int i = (int)(e % Mp), j = (int)((e / Mp) % Np);
+    const size_t s = e / ((size_t)Mp * Np);
+    A.dst[e] = A.src[s * A.M * A.N + (size_t)mir_sym(j - A.lo2, A.N) * A.M + mir_sym(i - A.lo1, A.M)];
+  }
+}
+// src = the PADDED cotangent, dst = the unpadded one (fully overwritten)
+__global__ void __launch_bounds__(256) k_pad_symmetric_adj(PadArgs A) {
+  const int Mp = A.M + A.lo1 + A.hi1, Np = A.N + A.lo2 + A.hi2;
+  const size_t total = (size_t)A.M * A.N * A.planes;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int i = (int)(e % A.M), j = (int)((e / A.M) % A.N);
+    const size_t s = e / ((size_t)A.M * A.N);
+    const float* p = A.src + s * Mp * Np;
+    // padded positions along each dimension that mirror onto (i, j): itself, the low pad, the high pad
+    int pi[3], pj[3], ni = 0, nj = 0;
+    pi[ni++] = A.lo1 + i;
+    if (i < A.lo1) pi[ni++] = A.lo1 - 1 - i;
+    if (A.M - 1 - i < A.hi1) pi[ni++] = A.lo1 + 2 * A.M - 1 - i;
+    pj[nj++] = A.lo2 + j;
+    if (j < A.lo2) pj[nj++] = A.lo2 - 1 - j;
+    if (A.N - 1 - j < A.hi2) pj[nj++] = A.lo2 + 2 * A.N - 1 - j;
+    float v = 0.f;
+    for (int b = 0; b < nj; ++b)
+      for (int a = 0; a < ni; ++a) v += p[(size_t)pj[b] * Mp + pi[a]];
+    A.dst[e] = v;
   }
 }
 

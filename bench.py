@@ -45,6 +45,8 @@ WORKLOADS = {
                        desc="one GPU's share of BASELINE.json configs[2] at 8 GPUs: 32 x 256x256 RGB, 10 iterations, fwd+bwd"),
     "cfg4": dict(B=16, P=1, N=2048, M=2048, k=31, iters=200, mode="fwd", psf="motion",
                  desc="BASELINE.json configs[3]: batch 16 x 2048x2048 gray, 31x31 PSF, 200-iteration forward"),
+    "w4096": dict(B=4, P=1, N=4096, M=4096, k=31, iters=50, mode="fwd", psf="motion",
+                  desc="largest planned FFT length: batch 4 x 4096x4096 gray, 31x31 PSF, 50-iteration forward (tuning workload)"),
     "cfg5": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="fwd", psf="motion",
                  desc="BASELINE.json configs[4], shared-PSF variant: batch 1024 x 128x128, 50 iterations"),
     "cfg5_mixed": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="grouped", groups="per_image", psf="motion",

@@ -18,8 +18,13 @@
  * cudaStream_t, calls only enqueue, caller-owned 256-byte aligned workspace, 0 / <0 / >0 return codes
  * (admmtv_strerror).  Any image size is accepted (no FFT on this path).  The scalar result and its
  * cotangent are 1-float DEVICE buffers, so a training step needs no host synchronisation.
- * Only `crop=true`, `dims=:` (the defaults, the only forms the reference calls) are implemented, and
- * only separable windows (the 11-tap Gaussian of ssim.jl:6-17 and the box of ssim_loss_fast).
+ * admmtv_ssim_forward / _backward take a separable window with equal taps in both dimensions (the 11-tap
+ * Gaussian of ssim.jl:6-17, the box of ssim_loss_fast: the forms the reference's scripts use, fully unrolled
+ * kernels); admmtv_ssim_window_* take ANY (L1, L2) window `kernel_ref` of ssim.jl:84 as a sum of R separable
+ * terms (the host side factors it, e.g. by an SVD); `crop=false` (ssim.jl:104-110) is admmtv_pad_symmetric on
+ * both images followed by the valid-size call, its pullback admmtv_pad_symmetric_adjoint.  `dims` is accepted
+ * and ignored by the reference (ssim.jl:84-124 never reads it).  Both losses are symmetric in (x, y), so the
+ * pullback w.r.t. the SECOND argument is the same entry points with the two images swapped.
  */
 #ifndef ADMMTV_LOSS_H
 #define ADMMTV_LOSS_H
@@ -62,6 +67,29 @@ int admmtv_ssim_forward(int M, int N, int C, int B, int device, const float* x, 
 int admmtv_ssim_backward(int M, int N, int C, int B, int device, const float* x, const float* y,
                          const float* taps, int L, int as_loss, const float* outbar, const void* workspace,
                          float* xbar, void* stream);
+
+/* ---- SSIM with an arbitrary window (ssim.jl:84 `kernel_ref`, any (L1, L2) <= 11 x 11 array) ------------- */
+/* The window is given as R <= 11 separable terms, W[a,b] = sum_r u[r*L1 + a] * v[r*L2 + b] (HOST pointers; a
+ * rank-1 window has R = 1, an SVD gives R = min(L1, L2) for any other).  Output map (M-L1+1, N-L2+1). */
+int admmtv_ssim_window_workspace_bytes(int M, int N, int C, int B, int L1, int L2, int with_grad, size_t* bytes);
+
+int admmtv_ssim_window_forward(int M, int N, int C, int B, int device, const float* x, const float* y,
+                               const float* u, const float* v, int L1, int L2, int R, float peakval, int as_loss,
+                               float* out, void* workspace, int with_grad, void* stream);
+
+int admmtv_ssim_window_backward(int M, int N, int C, int B, int device, const float* x, const float* y,
+                                const float* u, const float* v, int L1, int L2, int R, int as_loss,
+                                const float* outbar, const void* workspace, float* xbar, void* stream);
+
+/* ---- pad_symmetric (NNlib; ssim.jl:104-110, `crop = false`) --------------------------------------------- */
+/* dst (M+lo1+hi1, N+lo2+hi2, planes) = src (M, N, planes) mirrored across its borders INCLUDING the edge sample;
+ * ssim.jl:107 pads by (cld(L-1,2), fld(L-1,2)) per dimension.  Pads may not exceed the array size (NNlib). */
+int admmtv_pad_symmetric(int M, int N, int planes, int lo1, int hi1, int lo2, int hi2, int device, const float* src,
+                         float* dst, void* stream);
+
+/* src_bar (M, N, planes), fully overwritten = the pullback of the padding applied to padded_bar. */
+int admmtv_pad_symmetric_adjoint(int M, int N, int planes, int lo1, int hi1, int lo2, int hi2, int device,
+                                 const float* padded_bar, float* src_bar, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,8 @@ line-by-line restatement of
     src/metrics/gmsd.jl:13-27        gmsd            (:30 gmsd_loss = gmsd)
     src/metrics/ssim.jl:6-17         SSIM_KERNEL
     src/metrics/ssim.jl:25-47        ssim_kernel
-    src/metrics/ssim.jl:84-124       ssim            (:148 ssim_loss = 1 - ssim, :160-164 ssim_loss_fast)
+    src/metrics/ssim.jl:84-124       ssim            (:148 ssim_loss = 1 - ssim, :160-164 ssim_loss_fast),
+                                     incl. crop=false (:104-110, NNlib pad_symmetric) and arbitrary windows
 
 pinned by self-consistency only (tests/test_losses_oracle.py): gmsd(x,x) = 0, ssim(x,x) = 1, symmetry,
 shift invariance of gmsd (circular padding), an independent roll-based formulation, finite differences
@@ -101,13 +102,33 @@ def ssim_kernel(dtype=torch.float64, length=None):
     return torch.outer(g, g).reshape(11, 11, 1, 1)
 
 
-def ssim(x: torch.Tensor, y: torch.Tensor, kernel: torch.Tensor | None = None, peakval: float = 1.0) -> torch.Tensor:
-    """ssim.jl:84-124 with the defaults crop=true, dims=: (valid-size grouped convolutions)."""
+def pad_symmetric(x: torch.Tensor, pads) -> torch.Tensor:
+    """NNlib.pad_symmetric(x, (d1_lo, d1_hi, d2_lo, d2_hi)) on an (M,N,C,B) array: the values are mirrored across the
+    border INCLUDING the border sample ([b a | a b c d | d c] for pads (2, 2)), unlike pad_reflect."""
+    lo1, hi1, lo2, hi2 = pads
+    M, N = x.shape[0], x.shape[1]
+
+    def mirror(lo, hi, n):
+        idx = []
+        for t in range(-lo, n + hi):
+            idx.append(-1 - t if t < 0 else (2 * n - 1 - t if t >= n else t))
+        return torch.tensor(idx, dtype=torch.long)
+    return x.index_select(0, mirror(lo1, hi1, M)).index_select(1, mirror(lo2, hi2, N))
+
+
+def ssim(x: torch.Tensor, y: torch.Tensor, kernel: torch.Tensor | None = None, peakval: float = 1.0,
+         crop: bool = True) -> torch.Tensor:
+    """ssim.jl:84-124 (``dims`` is never read by the reference's body).  ``kernel``: (L1, L2, 1, C or 1)."""
     C = x.shape[2]
     kernel = ssim_kernel(x.dtype) if kernel is None else kernel
     if kernel.shape[3] != C:
         kernel = kernel.repeat(1, 1, 1, C)               # :96-98
     C1, C2 = (peakval * 0.01) ** 2, (peakval * 0.03) ** 2  # :101-102
+    if not crop:                                          # :104-110  calc_padding of Flux's conv.jl
+        k1, k2 = kernel.shape[0] - 1, kernel.shape[1] - 1
+        padding = (-(-k1 // 2), k1 // 2, -(-k2 // 2), k2 // 2)   # (cld, fld) per dimension
+        x = pad_symmetric(x, padding)
+        y = pad_symmetric(y, padding)
     conv = lambda a: nnlib_conv(a, kernel, groups=C)
     mx, my = conv(x), conv(y)                             # :112-113
     mx2, my2, mxy = mx ** 2, my ** 2, mx * my
@@ -118,11 +139,11 @@ def ssim(x: torch.Tensor, y: torch.Tensor, kernel: torch.Tensor | None = None, p
     return smap.mean(dim=(0, 1, 2)).mean()                # :122-123
 
 
-def ssim_loss(x, y, kernel=None, peakval: float = 1.0):
+def ssim_loss(x, y, kernel=None, peakval: float = 1.0, crop: bool = True):
     """ssim.jl:148"""
-    return 1.0 - ssim(x, y, kernel, peakval)
+    return 1.0 - ssim(x, y, kernel, peakval, crop)
 
 
-def ssim_loss_fast(x, y, kernel_length: int = 5, peakval: float = 1.0):
+def ssim_loss_fast(x, y, kernel_length: int = 5, peakval: float = 1.0, crop: bool = True):
     """ssim.jl:160-164"""
-    return ssim_loss(x, y, ssim_kernel(x.dtype, kernel_length), peakval)
+    return ssim_loss(x, y, ssim_kernel(x.dtype, kernel_length), peakval, crop)
