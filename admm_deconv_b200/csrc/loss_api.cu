@@ -103,15 +103,15 @@ int admmtv_gmsd_forward(int M, int N, int C, int B, int device, const float* x, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GmsdArgs a{};
   a.x = x; a.y = y; a.M = M; a.N = N; a.C = C; a.B = B; a.t = t; a.alpha = alpha;
-  a.tiles_i = (M + GM_TH - 1) / GM_TH; a.tiles_j = (N + GM_TW - 1) / GM_TW;
   a.acc = reinterpret_cast<double*>(workspace);
   a.stats = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + up256(2 * (size_t)B * sizeof(double)));
   a.out = loss_out;
   cudaError_t e = cudaMemsetAsync(a.acc, 0, 2 * (size_t)B * sizeof(double), st);
   if (e != cudaSuccess) return (int)e;
-  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
-  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
-  ADMMTV_LAUNCH(k_gmsd_fwd, dim3((unsigned)nblk), dim3(GM_NT), 0, st, a);
+  a.tiles_i = (M + GS_RF - 1) / GS_RF; a.tiles_j = (N + GS_CW - 1) / GS_CW;
+  const size_t nwarp = (size_t)a.tiles_i * a.tiles_j * C * B, nblk_s = (nwarp + GS_NT / 32 - 1) / (GS_NT / 32);
+  if (nblk_s > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_gmsd_fwd_s, dim3((unsigned)nblk_s), dim3(GS_NT), 0, st, a);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
   ADMMTV_LAUNCH(k_gmsd_finalize, dim3(1), dim3(128), 0, st, a);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
@@ -129,15 +129,15 @@ int admmtv_gmsd_backward(int M, int N, int C, int B, int device, const float* x,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   GmsdArgs a{};
   a.x = x; a.y = y; a.M = M; a.N = N; a.C = C; a.B = B; a.t = t; a.alpha = alpha;
-  a.tiles_i = (M + GM_TH - 1) / GM_TH; a.tiles_j = (N + GM_TW - 1) / GM_TW;
   unsigned char* ws = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(workspace));
   a.acc = reinterpret_cast<double*>(ws);
   a.stats = reinterpret_cast<double*>(ws + up256(2 * (size_t)B * sizeof(double)));
   a.lossbar = lossbar;
   a.out = xbar;
-  const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
-  if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
-  ADMMTV_LAUNCH(k_gmsd_bwd, dim3((unsigned)nblk), dim3(GM_NT), 0, st, a);
+  a.tiles_i = (M + GS_RB - 1) / GS_RB; a.tiles_j = (N + GS_CW - 1) / GS_CW;
+  const size_t nwarp = (size_t)a.tiles_i * a.tiles_j * C * B, nblk_s = (nwarp + GS_NT / 32 - 1) / (GS_NT / 32);
+  if (nblk_s > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
+  ADMMTV_LAUNCH(k_gmsd_bwd_s, dim3((unsigned)nblk_s), dim3(GS_NT), 0, st, a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ADMMTV_OK : (int)e;
 }
@@ -176,8 +176,8 @@ int admmtv_ssim_forward(int M, int N, int C, int B, int device, const float* x, 
   if (e != cudaSuccess) return (int)e;
   const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
   if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
-  if (a.L == 11) ADMMTV_LAUNCH(k_ssim_fwd<11>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
-  else if (a.L == 5) ADMMTV_LAUNCH(k_ssim_fwd<5>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  if (a.L == 11) ADMMTV_LAUNCH(k_ssim_fwd4<11>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  else if (a.L == 5) ADMMTV_LAUNCH(k_ssim_fwd4<5>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   else ADMMTV_LAUNCH(k_ssim_fwd<0>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
   ADMMTV_LAUNCH(k_ssim_finalize, dim3(1), dim3(1), 0, st, a);
@@ -206,8 +206,8 @@ int admmtv_ssim_backward(int M, int N, int C, int B, int device, const float* x,
   a.out = xbar;
   const size_t nblk = (size_t)a.tiles_i * a.tiles_j * C * B;
   if (nblk > 0x7fffffffu) return ADMMTV_ERR_SHAPE;
-  if (a.L == 11) ADMMTV_LAUNCH(k_ssim_bwd<11>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
-  else if (a.L == 5) ADMMTV_LAUNCH(k_ssim_bwd<5>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  if (a.L == 11) ADMMTV_LAUNCH(k_ssim_bwd4<11>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
+  else if (a.L == 5) ADMMTV_LAUNCH(k_ssim_bwd4<5>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   else ADMMTV_LAUNCH(k_ssim_bwd<0>, dim3((unsigned)nblk), dim3(SS_NT), 0, st, a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ADMMTV_OK : (int)e;

@@ -2,10 +2,10 @@
 //
 // Replaces the cuDNN grouped convolutions + CUDA.jl broadcasts + Zygote tape of
 //   /root/reference/src/metrics/gmsd.jl:13-27 (+ iqa_utils.jl:24-55) and src/metrics/ssim.jl:84-124
-// by one tiled kernel per direction: the image tile (plus stencil halo) is staged in shared memory once,
-// every intermediate map lives in shared memory or registers, and the only HBM traffic is x, y in and
-// xbar out (GMSD: 8 B/pixel forward, 12 B/pixel backward; SSIM additionally keeps three derivative maps,
-// 12 B/output pixel, between forward and backward instead of redoing five 11x11 windows).
+// by one kernel per direction: every intermediate map lives in registers (GMSD: warp strips marching along dim 2,
+// neighbours by SHFL) or shared memory (SSIM: 32 x 32 output tiles, register-blocked separable windows), and the
+// only HBM traffic is x, y in and xbar out (GMSD: 8 B/pixel forward, 12 B/pixel backward; SSIM additionally keeps
+// three derivative maps, 12 B/output pixel, between forward and backward instead of redoing five 11x11 windows).
 // Arrays are Julia (M,N,C,B) column-major: plane s = c + C*b, element (i,j) at i + M*j.
 #pragma once
 
@@ -23,8 +23,6 @@ ADMMTV_DI int wrapi(int i, int n) {
 // ------------------------------------------------------------------------------------------
 // GMSD
 // ------------------------------------------------------------------------------------------
-constexpr int GM_TH = 64, GM_TW = 32, GM_NT = 256;
-
 struct GmsdArgs {
   const float* x;
   const float* y;
@@ -37,98 +35,14 @@ struct GmsdArgs {
   float* out;            // forward: loss ; backward: xbar
 };
 
-// Sobel/8 gradients (iqa_utils.jl:15-20,46-47; NNlib conv = true convolution of the circularly padded
-// image) at interior position (li, lj) of a column-major shared tile with leading dimension LD:
+// Sobel/8 gradients (iqa_utils.jl:15-20,46-47; NNlib conv = true convolution of the circularly padded image):
 //   gx[i,j] = sum_dj w(dj) (x[i+1,j+dj] - x[i-1,j+dj]),  gy[i,j] = sum_di w(di) (x[i+di,j+1] - x[i+di,j-1]),  w = (1,2,1)/8
-template <int LD>
-ADMMTV_DI void sobel_at(const float* T, int li, int lj, float& gx, float& gy) {
-  const float* c0 = T + (lj - 1) * LD + li;
-  const float* c1 = c0 + LD;
-  const float* c2 = c1 + LD;
-  gx = ((c0[1] - c0[-1]) + 2.f * (c1[1] - c1[-1]) + (c2[1] - c2[-1])) * 0.125f;
-  gy = ((c2[-1] - c0[-1]) + 2.f * (c2[0] - c0[0]) + (c2[1] - c0[1])) * 0.125f;
-}
+// evaluated from the separable column parts cs = x[i-1] + 2 x[i] + x[i+1], cd = x[i+1] - x[i-1] (gs_col below).
 // The loss kernels are instruction-bound, so the per-pixel square root and divisions use the 2-ulp hardware approximations
 // (MUFU.RSQ / MUFU.RCP); the error is far inside the loss tolerances (tests/test_gpu_losses.py).
 ADMMTV_DI float gradmag(float gx, float gy) {   // iqa_utils.jl:53-55
   const float s = gx * gx + gy * gy + 1e-16f;
   return s * rsqrtf(s);
-}
-
-// Stage the tile plus its circular halo (pad_circular, iqa_utils.jl:46).  Thread (r, cg) = (tid % TH, tid / TH) loads row r
-// (and, for r < 2*HALO, the extra row r + TH) of every 4th column: no per-element division, the wrapped row index is computed once.
-template <int HALO, int LD>
-ADMMTV_DI void gm_load_tile(const float* __restrict__ p, float* T, int i0, int j0, int M, int N, int tid) {
-  static_assert(LD == GM_TH + 2 * HALO && GM_NT % GM_TH == 0, "tile geometry");
-  constexpr int W = GM_TW + 2 * HALO, CG = GM_NT / GM_TH;
-  const int r = tid % GM_TH, cg = tid / GM_TH;
-  const int gi0 = wrapi(i0 - HALO + r, M);
-  const bool extra = r < 2 * HALO;
-  const int gi1 = extra ? wrapi(i0 - HALO + r + GM_TH, M) : 0;
-  int gj = wrapi(j0 - HALO + cg, N);
-  const int dj = CG % N;
-  for (int lj = cg; lj < W; lj += CG) {
-    const float* col = p + (size_t)gj * M;
-    T[lj * LD + r] = col[gi0];
-    if (extra) T[lj * LD + r + GM_TH] = col[gi1];
-    gj += dj;
-    if (gj >= N) gj -= N;
-  }
-}
-
-__global__ void __launch_bounds__(GM_NT) k_gmsd_fwd(GmsdArgs A) {
-  constexpr int LD = GM_TH + 2;
-  __shared__ float xs[LD * (GM_TW + 2)], ys[LD * (GM_TW + 2)];
-  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
-  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
-  const int i0 = (tl % A.tiles_i) * GM_TH, j0 = (tl / A.tiles_i) * GM_TW;
-  const size_t plane = (size_t)A.M * A.N;
-  gm_load_tile<1, LD>(A.x + (size_t)s * plane, xs, i0, j0, A.M, A.N, tid);
-  gm_load_tile<1, LD>(A.y + (size_t)s * plane, ys, i0, j0, A.M, A.N, tid);
-  __syncthreads();
-  // Each thread owns one row of an 8-column strip and marches along it with a 3-column sliding window of the separable
-  // Sobel parts (cs = x[i-1] + 2 x[i] + x[i+1], cd = x[i+1] - x[i-1]): 3 shared loads per image and pixel instead of 8.
-  // Its 8 pixels are summed in fp32 (g - 1 is exact in fp32 for g in [1/2, 2]); fp64 from the block up.
-  float f1 = 0.f, f2 = 0.f;
-  {
-    static_assert(GM_NT == GM_TH * (GM_TW / 8), "one thread per (row, 8-column strip)");
-    const int li = tid % GM_TH, lj0 = (tid / GM_TH) * 8;
-    const float* px = xs + lj0 * LD + li;   // smem column lj0 = image column j0 + lj0 - 1, rows li .. li+2 = image rows i-1 .. i+1
-    const float* py = ys + lj0 * LD + li;
-    float xs0, xd0, xs1, xd1, ys0, yd0, ys1, yd1;
-    auto col = [&](const float* p, float& cs, float& cd) {
-      const float a = p[0], b = p[1], c = p[2];
-      cs = a + 2.f * b + c;
-      cd = c - a;
-    };
-    col(px, xs0, xd0); col(px + LD, xs1, xd1);
-    col(py, ys0, yd0); col(py + LD, ys1, yd1);
-    const bool row_ok = i0 + li < A.M;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float xs2, xd2, ys2, yd2;
-      col(px + (k + 2) * LD, xs2, xd2);
-      col(py + (k + 2) * LD, ys2, yd2);
-      if (row_ok && j0 + lj0 + k < A.N) {
-        const float mx = gradmag((xd0 + 2.f * xd1 + xd2) * 0.125f, (xs2 - xs0) * 0.125f);
-        const float my = gradmag((yd0 + 2.f * yd1 + yd2) * 0.125f, (ys2 - ys0) * 0.125f);
-        const float mm = mx * my;
-        const float g = __fdividef(2.f * mm - A.alpha * mm + A.t, mx * mx + my * my - A.alpha * mm + A.t);  // gmsd.jl:5-10
-        const float d = g - 1.f;  // sums of (g-1): well conditioned when x ~ y
-        f1 += d;
-        f2 += d * d;
-      }
-      xs0 = xs1; xd0 = xd1; xs1 = xs2; xd1 = xd2;
-      ys0 = ys1; yd0 = yd1; ys1 = ys2; yd1 = yd2;
-    }
-  }
-  const double t1 = block_sum((double)f1);
-  const double t2 = block_sum((double)f2);
-  if (tid == 0) {
-    const int b = s / A.C;
-    atomicAdd(A.acc + 2 * b, t1);
-    atomicAdd(A.acc + 2 * b + 1, t2);
-  }
 }
 
 // per-image mean / deviation (gmsd.jl:21-24) and the batch mean (reduction = mean, :26)
@@ -148,53 +62,136 @@ __global__ void __launch_bounds__(128) k_gmsd_finalize(GmsdArgs A) {
   if (threadIdx.x == 0) A.out[0] = (float)(tot / A.B);
 }
 
-__global__ void __launch_bounds__(GM_NT) k_gmsd_bwd(GmsdArgs A) {
-  constexpr int LD4 = GM_TH + 4, LD2 = GM_TH + 2;
-  __shared__ float xs[LD4 * (GM_TW + 4)], ys[LD4 * (GM_TW + 4)];
-  __shared__ float p1[LD2 * (GM_TW + 2)], p2[LD2 * (GM_TW + 2)];
-  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
-  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
-  const int i0 = (tl % A.tiles_i) * GM_TH, j0 = (tl / A.tiles_i) * GM_TW;
+// ------------------------------------------------------------------------------------------
+// GMSD kernels, streaming form: no shared memory, no block barrier (round 1's 64 x 32 shared-memory tile kernels ran at
+// 0.29 + 0.48 ms on 64 x 512^2 x 3; these at 0.18 + 0.29 ms, issue-bound at 75 % by the arithmetic of the metric itself).  A warp owns a strip of rows (one row per lane, the outer
+// lanes are the circular halo) and marches along dim 2: each step is one coalesced load of a column of x and of y, the
+// row neighbours come from the adjacent lanes (SHFL), the column neighbours from a three-column sliding window in
+// registers.  The backward carries a second window (the adjoint stencil of the two cotangent fields) two columns behind.
+// ------------------------------------------------------------------------------------------
+#ifndef ADMMTV_GS_UNROLL_F
+#define ADMMTV_GS_UNROLL_F 4
+#endif
+#ifndef ADMMTV_GS_UNROLL_B
+#define ADMMTV_GS_UNROLL_B 2
+#endif
+#ifndef ADMMTV_GS_CW
+#define ADMMTV_GS_CW 64
+#endif
+#ifndef ADMMTV_GS_NT
+#define ADMMTV_GS_NT 256
+#endif
+constexpr int GS_NT = ADMMTV_GS_NT, GS_CW = ADMMTV_GS_CW;        // threads per block, columns per strip
+constexpr int GS_UF = ADMMTV_GS_UNROLL_F, GS_UB = ADMMTV_GS_UNROLL_B;
+constexpr int GS_RF = 30, GS_RB = 28;         // useful rows per warp: forward (1-row halo), backward (2-row halo)
+
+// separable Sobel parts of one column at this lane's row: cs = up + 2 mid + down, cd = down - up
+ADMMTV_DI void gs_col(float v, int lane, float& cs, float& cd) {
+  const float up = __shfl_sync(0xffffffffu, v, (lane + 31) & 31), dn = __shfl_sync(0xffffffffu, v, (lane + 1) & 31);
+  cs = up + 2.f * v + dn;
+  cd = dn - up;
+}
+
+__global__ void __launch_bounds__(GS_NT) k_gmsd_fwd_s(GmsdArgs A) {
+  const int lane = threadIdx.x & 31, strips = A.tiles_i * A.tiles_j;
+  const long long wid = (long long)blockIdx.x * (GS_NT / 32) + (threadIdx.x >> 5);
+  if (wid >= (long long)strips * A.C * A.B) return;   // warp-uniform
+  const int s = (int)(wid / strips), st = (int)(wid % strips);
+  const int r0 = (st % A.tiles_i) * GS_RF, c0 = (st / A.tiles_i) * GS_CW;
+  const int row = r0 - 1 + lane;
+  const bool row_ok = lane >= 1 && lane <= GS_RF && row < A.M;
   const size_t plane = (size_t)A.M * A.N;
-  gm_load_tile<2, LD4>(A.x + (size_t)s * plane, xs, i0, j0, A.M, A.N, tid);
-  gm_load_tile<2, LD4>(A.y + (size_t)s * plane, ys, i0, j0, A.M, A.N, tid);
+  const float* xp = A.x + (size_t)s * plane + wrapi(row, A.M);
+  const float* yp = A.y + (size_t)s * plane + wrapi(row, A.M);
+  int gj = wrapi(c0 - 1, A.N);
+  auto next = [&](int j) { return j + 1 >= A.N ? j + 1 - A.N : j + 1; };
+  float xs0, xd0, xs1, xd1, ys0, yd0, ys1, yd1;
+  gs_col(xp[(size_t)gj * A.M], lane, xs0, xd0); gs_col(yp[(size_t)gj * A.M], lane, ys0, yd0);
+  gj = next(gj);
+  gs_col(xp[(size_t)gj * A.M], lane, xs1, xd1); gs_col(yp[(size_t)gj * A.M], lane, ys1, yd1);
+  float f1 = 0.f, f2 = 0.f;
+  double d1 = 0.0, d2 = 0.0;
+#pragma unroll GS_UF
+  for (int k = 0; k < GS_CW; ++k) {
+    gj = next(gj);
+    float xs2, xd2, ys2, yd2;
+    gs_col(xp[(size_t)gj * A.M], lane, xs2, xd2);
+    gs_col(yp[(size_t)gj * A.M], lane, ys2, yd2);
+    if (row_ok && c0 + k < A.N) {
+      const float mx = gradmag((xd0 + 2.f * xd1 + xd2) * 0.125f, (xs2 - xs0) * 0.125f);
+      const float my = gradmag((yd0 + 2.f * yd1 + yd2) * 0.125f, (ys2 - ys0) * 0.125f);
+      const float mm = mx * my;
+      const float g = __fdividef(2.f * mm - A.alpha * mm + A.t, mx * mx + my * my - A.alpha * mm + A.t);  // gmsd.jl:5-10
+      const float d = g - 1.f;  // sums of (g-1): well conditioned when x ~ y
+      f1 += d;
+      f2 += d * d;
+    }
+    if ((k & 7) == 7) {   // fp32 over 8 pixels, fp64 beyond
+      d1 += (double)f1; d2 += (double)f2;
+      f1 = 0.f; f2 = 0.f;
+    }
+    xs0 = xs1; xd0 = xd1; xs1 = xs2; xd1 = xd2;
+    ys0 = ys1; yd0 = yd1; ys1 = ys2; yd1 = yd2;
+  }
+  d1 = warp_sum(d1);
+  d2 = warp_sum(d2);
+  if (lane == 0) {
+    const int b = s / A.C;
+    atomicAdd(A.acc + 2 * b, d1);
+    atomicAdd(A.acc + 2 * b + 1, d2);
+  }
+}
+
+__global__ void __launch_bounds__(GS_NT) k_gmsd_bwd_s(GmsdArgs A) {
+  const int lane = threadIdx.x & 31, strips = A.tiles_i * A.tiles_j;
+  const long long wid = (long long)blockIdx.x * (GS_NT / 32) + (threadIdx.x >> 5);
+  if (wid >= (long long)strips * A.C * A.B) return;   // warp-uniform
+  const int s = (int)(wid / strips), st = (int)(wid % strips);
+  const int r0 = (st % A.tiles_i) * GS_RB, c0 = (st / A.tiles_i) * GS_CW;
+  const int row = r0 - 2 + lane;
+  const bool row_ok = lane >= 2 && lane <= GS_RB + 1 && row < A.M;
+  const size_t plane = (size_t)A.M * A.N;
+  const float* xp = A.x + (size_t)s * plane + wrapi(row, A.M);
+  const float* yp = A.y + (size_t)s * plane + wrapi(row, A.M);
+  float* xb = A.out + (size_t)s * plane + (row_ok ? row : 0);
   const int b = s / A.C;
   const float mean = (float)A.stats[2 * b];
   // d loss / d g[p] = lossbar (g[p] - mean_b) / (B n sqrt(score_b))
   const float scale = (float)((double)A.lossbar[0] / ((double)A.B * ((double)A.M * A.N * A.C) * A.stats[2 * b + 1]));
-  __syncthreads();
-  // cotangents of the two gradient fields on the tile + 1 halo
-  for (int e = tid; e < LD2 * (GM_TW + 2); e += GM_NT) {
-    const int li = e % LD2, lj = e / LD2;
-    float gx, gy, hx, hy;
-    sobel_at<LD4>(xs, li + 1, lj + 1, gx, gy);
+  int gj = wrapi(c0 - 2, A.N);
+  auto next = [&](int j) { return j + 1 >= A.N ? j + 1 - A.N : j + 1; };
+  float xs0, xd0, xs1, xd1, ys0, yd0, ys1, yd1;
+  gs_col(xp[(size_t)gj * A.M], lane, xs0, xd0); gs_col(yp[(size_t)gj * A.M], lane, ys0, yd0);
+  gj = next(gj);
+  gs_col(xp[(size_t)gj * A.M], lane, xs1, xd1); gs_col(yp[(size_t)gj * A.M], lane, ys1, yd1);
+  float A0 = 0.f, B0 = 0.f, A1 = 0.f, B1 = 0.f;   // adjoint-stencil parts of the two previous cotangent columns
+#pragma unroll GS_UB
+  for (int t = 2; t < GS_CW + 4; ++t) {
+    gj = next(gj);                       // image column c0 - 2 + t
+    float xs2, xd2, ys2, yd2;
+    gs_col(xp[(size_t)gj * A.M], lane, xs2, xd2);
+    gs_col(yp[(size_t)gj * A.M], lane, ys2, yd2);
+    // cotangents of the two gradient fields at column c0 + t - 3 (this lane's row)
+    const float gx = (xd0 + 2.f * xd1 + xd2) * 0.125f, gy = (xs2 - xs0) * 0.125f;
     const float mx = gradmag(gx, gy);
-    sobel_at<LD4>(ys, li + 1, lj + 1, hx, hy);
-    const float my = gradmag(hx, hy);
+    const float my = gradmag((yd0 + 2.f * yd1 + yd2) * 0.125f, (ys2 - ys0) * 0.125f);
     const float mm = mx * my;
     const float den = mx * mx + my * my - A.alpha * mm + A.t;
     const float rden = __fdividef(1.f, den);
     const float g = (2.f * mm - A.alpha * mm + A.t) * rden;
     const float dgdmx = ((2.f - A.alpha) * my - g * (2.f * mx - A.alpha * my)) * rden;
     const float c = __fdividef(scale * (g - mean) * dgdmx, mx);
-    p1[e] = c * gx;
-    p2[e] = c * gy;
-  }
-  __syncthreads();
-  // adjoint of the two circular stencils
-  float* xb = A.out + (size_t)s * plane;
-  for (int e = tid; e < GM_TH * GM_TW; e += GM_NT) {
-    const int li = e % GM_TH, lj = e / GM_TH;
-    if (i0 + li < A.M && j0 + lj < A.N) {
-      const float* a0 = p1 + lj * LD2 + li + 1;  // column j-1 (tile coords are offset by the 1-halo)
-      const float* a1 = a0 + LD2;
-      const float* a2 = a1 + LD2;
-      const float* b0 = p2 + lj * LD2 + li + 1;
-      const float* b2 = b0 + 2 * LD2;
-      const float v = ((a0[-1] - a0[1]) + 2.f * (a1[-1] - a1[1]) + (a2[-1] - a2[1])) * 0.125f +
-                      ((b0[-1] - b2[-1]) + 2.f * (b0[0] - b2[0]) + (b0[1] - b2[1])) * 0.125f;
-      xb[(size_t)(j0 + lj) * A.M + i0 + li] = v;
-    }
+    const float p1 = c * gx, p2 = c * gy;
+    // adjoint of the two circular stencils: row parts of this column ...
+    const float p1u = __shfl_sync(0xffffffffu, p1, (lane + 31) & 31), p1d = __shfl_sync(0xffffffffu, p1, (lane + 1) & 31);
+    const float p2u = __shfl_sync(0xffffffffu, p2, (lane + 31) & 31), p2d = __shfl_sync(0xffffffffu, p2, (lane + 1) & 31);
+    const float A2 = p1u - p1d, B2 = p2u + 2.f * p2 + p2d;
+    // ... column parts over the three-column window: xbar at column c0 + t - 4
+    const int oc = c0 + t - 4;
+    if (t >= 4 && row_ok && oc < A.N) xb[(size_t)oc * A.M] = ((A0 + 2.f * A1 + A2) + (B0 - B2)) * 0.125f;
+    A0 = A1; B0 = B1; A1 = A2; B1 = B2;
+    xs0 = xs1; xd0 = xd1; xs1 = xs2; xd1 = xd2;
+    ys0 = ys1; yd0 = yd1; ys1 = ys2; yd1 = yd2;
   }
 }
 
@@ -232,7 +229,7 @@ ADMMTV_DI float ssim_point(const SsimArgs& A, float mx, float my, float exx, flo
   return S;
 }
 
-// LC: compile-time number of taps (11 = the default Gaussian, 5 = ssim_loss_fast: window loops fully unrolled), 0 = run-time A.L
+// Equal separable taps with a RUN-TIME count (LC = 0: A.L taps); the 11- and 5-tap windows of the reference take k_ssim_fwd4 / k_ssim_bwd4 below.
 template <int LC>
 __global__ void __launch_bounds__(SS_NT) k_ssim_fwd(SsimArgs A) {
   __shared__ float xs[SS_IN * SS_IN], ys[SS_IN * SS_IN];
@@ -338,6 +335,157 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_bwd(SsimArgs A) {
       }
       const size_t g = (size_t)gj * A.M + gi;
       xb[g] = scale * (r0 + 2.f * xp[g] * r1 + yp[g] * r2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Register-blocked SSIM kernels for a compile-time tap count (11 = the default Gaussian, 5 = ssim_loss_fast).
+// k_ssim_fwd / k_ssim_bwd above spend most of their time on shared-memory loads: L per window sum, 84 per output pixel in the
+// forward.  Here every thread produces FOUR adjacent outputs of a window pass from the L + 3 inputs they share: along dim 1
+// (contiguous in shared memory) the inputs come in as aligned LDS.128, along dim 2 as L + 3 conflict-free scalar loads, and the
+// 4 x L products are register FMAs with the taps as constant-bank operands -- 2.6x fewer shared-memory wavefronts per pixel.
+// The row stride SS_LD = 44 floats keeps every row 16-byte aligned.
+// ------------------------------------------------------------------------------------------
+constexpr int SS_LD = 44;
+// out[k] = sum_a f[a] v[k + a] (REV: v[k + L-1-a]),  k = 0..3
+template <int L, bool REV>
+ADMMTV_DI void win4(const float* v, const float* f, float* out) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float r = 0.f;
+#pragma unroll
+    for (int a = 0; a < L; ++a) r += f[a] * v[k + (REV ? L - 1 - a : a)];
+    out[k] = r;
+  }
+}
+// v[0 .. 4 NV) = row[0 .. 4 NV), row 16-byte aligned
+template <int NV>
+ADMMTV_DI void load_row4(const float* row, float* v) {
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(row + 4 * q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(SS_NT) k_ssim_fwd4(SsimArgs A) {
+  constexpr int ext = SS_T + L - 1, NV = (L + 3 + 3) / 4;
+  static_assert(4 * NV + SS_T - 4 <= SS_LD && ext <= SS_IN, "a thread's aligned run stays inside its row");
+  __shared__ __align__(16) float xs[SS_IN * SS_LD], ys[SS_IN * SS_LD];
+  __shared__ __align__(16) float P[5][SS_IN * SS_T];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
+  const size_t plane = (size_t)A.M * A.N;
+  const float* xp = A.x + (size_t)s * plane;
+  const float* yp = A.y + (size_t)s * plane;
+  for (int e = tid; e < SS_LD * ext; e += SS_NT) {   // whole rows incl. the alignment padding (zeros)
+    const int li = e % SS_LD, lj = e / SS_LD;
+    const int gi = i0 + li, gj = j0 + lj;
+    const bool ok = li < ext && gi < A.M && gj < A.N;
+    xs[e] = ok ? xp[(size_t)gj * A.M + gi] : 0.f;
+    ys[e] = ok ? yp[(size_t)gj * A.M + gi] : 0.f;
+  }
+  __syncthreads();
+  // window along dim 1 for x, y, x^2, y^2, xy: item = (4 adjacent rows li0.., column lj)
+  for (int e = tid; e < (SS_T / 4) * ext; e += SS_NT) {
+    const int li0 = 4 * (e % (SS_T / 4)), lj = e / (SS_T / 4);
+    float xv[4 * NV], yv[4 * NV], pv[4 * NV], o[4];
+    load_row4<NV>(xs + lj * SS_LD + li0, xv);
+    load_row4<NV>(ys + lj * SS_LD + li0, yv);
+    float* dst = &P[0][lj * SS_T + li0];
+    win4<L, false>(xv, A.f, o);
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    win4<L, false>(yv, A.f, o);
+    *reinterpret_cast<float4*>(dst + SS_IN * SS_T) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int q = 0; q < L + 3; ++q) pv[q] = xv[q] * xv[q];
+    win4<L, false>(pv, A.f, o);
+    *reinterpret_cast<float4*>(dst + 2 * SS_IN * SS_T) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int q = 0; q < L + 3; ++q) pv[q] = yv[q] * yv[q];
+    win4<L, false>(pv, A.f, o);
+    *reinterpret_cast<float4*>(dst + 3 * SS_IN * SS_T) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int q = 0; q < L + 3; ++q) pv[q] = xv[q] * yv[q];
+    win4<L, false>(pv, A.f, o);
+    *reinterpret_cast<float4*>(dst + 4 * SS_IN * SS_T) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  // window along dim 2: thread = (row li, 4 adjacent columns lj0..)
+  static_assert(SS_NT == SS_T * (SS_T / 4), "one thread per (row, 4-column group)");
+  const int li = tid % SS_T, lj0 = 4 * (tid / SS_T);
+  float m[5][4];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    float v[L + 3];
+#pragma unroll
+    for (int q = 0; q < L + 3; ++q) v[q] = P[c][(lj0 + q) * SS_T + li];
+    win4<L, false>(v, A.f, m[c]);
+  }
+  double tot = 0.0;
+  const size_t oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (i0 + li < A.Mo && j0 + lj0 + k < A.No)
+      tot += (double)ssim_point(A, m[0][k], m[1][k], m[2][k], m[3][k], m[4][k],
+                                (size_t)s * oplane + (size_t)(j0 + lj0 + k) * A.Mo + i0 + li, nplanes * oplane);
+  tot = block_sum(tot);
+  if (tid == 0) atomicAdd(A.acc, tot);
+}
+
+template <int L>
+__global__ void __launch_bounds__(SS_NT) k_ssim_bwd4(SsimArgs A) {
+  constexpr int ext = SS_T + L - 1, NV = (L + 3 + 3) / 4;
+  __shared__ __align__(16) float ms[3][SS_IN * SS_LD];
+  __shared__ __align__(16) float T[3][SS_IN * SS_T];
+  const int tid = threadIdx.x, tiles = A.tiles_i * A.tiles_j;
+  const int s = blockIdx.x / tiles, tl = blockIdx.x % tiles;
+  const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
+  const size_t plane = (size_t)A.M * A.N, oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
+  // derivative maps over output positions [i0-L+1, i0+T) x [j0-L+1, j0+T), zero outside the valid region
+  for (int e = tid; e < SS_LD * ext; e += SS_NT) {
+    const int li = e % SS_LD, lj = e / SS_LD;
+    const int pi = i0 - (L - 1) + li, pj = j0 - (L - 1) + lj;
+    const bool ok = li < ext && pi >= 0 && pj >= 0 && pi < A.Mo && pj < A.No;
+    const size_t o = (size_t)s * oplane + (size_t)(ok ? pj : 0) * A.Mo + (ok ? pi : 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ms[k][e] = ok ? A.maps[k * nplanes * oplane + o] : 0.f;
+  }
+  __syncthreads();
+  // transposed window along dim 1: t[qi, pj] = sum_a f[a] map[qi - a, pj]  (tile index li + L-1 - a)
+  for (int e = tid; e < (SS_T / 4) * ext; e += SS_NT) {
+    const int li0 = 4 * (e % (SS_T / 4)), lj = e / (SS_T / 4);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v[4 * NV], o[4];
+      load_row4<NV>(ms[c] + lj * SS_LD + li0, v);
+      win4<L, true>(v, A.f, o);
+      *reinterpret_cast<float4*>(&T[c][lj * SS_T + li0]) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  const float scale = (float)((double)A.outbar[0] * (A.as_loss ? -1.0 : 1.0) / ((double)A.Mo * A.No * A.C * A.B));
+  const float* xp = A.x + (size_t)s * plane;
+  const float* yp = A.y + (size_t)s * plane;
+  float* xb = A.out + (size_t)s * plane;
+  const int li = tid % SS_T, lj0 = 4 * (tid / SS_T);
+  float r[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[L + 3];
+#pragma unroll
+    for (int q = 0; q < L + 3; ++q) v[q] = T[c][(lj0 + q) * SS_T + li];
+    win4<L, true>(v, A.f, r[c]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int gi = i0 + li, gj = j0 + lj0 + k;
+    if (gi < A.M && gj < A.N) {
+      const size_t g = (size_t)gj * A.M + gi;
+      xb[g] = scale * (r[0][k] + 2.f * xp[g] * r[1][k] + yp[g] * r[2][k]);
     }
   }
 }
