@@ -219,11 +219,12 @@ ADMMTV_DI float ssim_point(const SsimArgs& A, float mx, float my, float exx, flo
   const float mxy = mx * my, mx2 = mx * mx, my2 = my * my;
   const float sx2 = exx - mx2, sy2 = eyy - my2, sxy = exy - mxy;                   // ssim.jl:117-119
   const float A1 = 2.f * mxy + A.C1, A2 = 2.f * sxy + A.C2, B1 = mx2 + my2 + A.C1, B2 = sx2 + sy2 + A.C2;
-  const float S = A1 * A2 / (B1 * B2);                                             // ssim.jl:121
+  // the kernels are instruction-bound: the reciprocals are the 1-ulp hardware approximation (MUFU.RCP), far inside the tolerances
+  const float r1 = __fdividef(1.f, B1), r2 = __fdividef(1.f, B2), ib = r1 * r2;
+  const float S = A1 * A2 * ib;                                                    // ssim.jl:121
   if (A.with_grad) {
-    const float ib = 1.f / (B1 * B2);
-    A.maps[o] = 2.f * my * (A2 - A1) * ib - 2.f * mx * S * (1.f / B1 - 1.f / B2);   // dS/dmu_x
-    A.maps[mapstride + o] = -S / B2;                                               // dS/dE[x^2]
+    A.maps[o] = 2.f * my * (A2 - A1) * ib - 2.f * mx * S * (r1 - r2);               // dS/dmu_x
+    A.maps[mapstride + o] = -S * r2;                                               // dS/dE[x^2]
     A.maps[2 * mapstride + o] = 2.f * A1 * ib;                                     // dS/dE[xy]
   }
   return S;
@@ -381,12 +382,19 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_fwd4(SsimArgs A) {
   const size_t plane = (size_t)A.M * A.N;
   const float* xp = A.x + (size_t)s * plane;
   const float* yp = A.y + (size_t)s * plane;
-  for (int e = tid; e < SS_LD * ext; e += SS_NT) {   // whole rows incl. the alignment padding (zeros)
-    const int li = e % SS_LD, lj = e / SS_LD;
-    const int gi = i0 + li, gj = j0 + lj;
-    const bool ok = li < ext && gi < A.M && gj < A.N;
-    xs[e] = ok ? xp[(size_t)gj * A.M + gi] : 0.f;
-    ys[e] = ok ? yp[(size_t)gj * A.M + gi] : 0.f;
+  {   // whole rows incl. the alignment padding (zeros): thread = (element lc of a row, every 4th row from lr)
+    const int lc = tid % 64, lr = tid / 64;
+    const bool col_ok = lc < ext && i0 + lc < A.M;
+    if (lc < SS_LD) {
+      const float* xq = xp + (size_t)(j0 + lr) * A.M + i0 + lc;
+      const float* yq = yp + (size_t)(j0 + lr) * A.M + i0 + lc;
+#pragma unroll 4
+      for (int lj = lr; lj < ext; lj += 4, xq += 4 * (size_t)A.M, yq += 4 * (size_t)A.M) {
+        const bool ok = col_ok && j0 + lj < A.N;
+        xs[lj * SS_LD + lc] = ok ? *xq : 0.f;
+        ys[lj * SS_LD + lc] = ok ? *yq : 0.f;
+      }
+    }
   }
   __syncthreads();
   // window along dim 1 for x, y, x^2, y^2, xy: item = (4 adjacent rows li0.., column lj)
@@ -446,13 +454,21 @@ __global__ void __launch_bounds__(SS_NT) k_ssim_bwd4(SsimArgs A) {
   const int i0 = (tl % A.tiles_i) * SS_T, j0 = (tl / A.tiles_i) * SS_T;
   const size_t plane = (size_t)A.M * A.N, oplane = (size_t)A.Mo * A.No, nplanes = (size_t)A.C * A.B;
   // derivative maps over output positions [i0-L+1, i0+T) x [j0-L+1, j0+T), zero outside the valid region
-  for (int e = tid; e < SS_LD * ext; e += SS_NT) {
-    const int li = e % SS_LD, lj = e / SS_LD;
-    const int pi = i0 - (L - 1) + li, pj = j0 - (L - 1) + lj;
-    const bool ok = li < ext && pi >= 0 && pj >= 0 && pi < A.Mo && pj < A.No;
-    const size_t o = (size_t)s * oplane + (size_t)(ok ? pj : 0) * A.Mo + (ok ? pi : 0);
+  {
+    const int lc = tid % 64, lr = tid / 64;
+    const int pi = i0 - (L - 1) + lc;
+    const bool col_ok = lc < ext && pi >= 0 && pi < A.Mo;
+    if (lc < SS_LD) {
+      const float* mq = A.maps + (size_t)s * oplane + (col_ok ? pi : 0);
+#pragma unroll 2
+      for (int lj = lr; lj < ext; lj += 4) {
+        const int pj = j0 - (L - 1) + lj;
+        const bool ok = col_ok && pj >= 0 && pj < A.No;
+        const float* m0 = mq + (size_t)(ok ? pj : 0) * A.Mo;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) ms[k][e] = ok ? A.maps[k * nplanes * oplane + o] : 0.f;
+        for (int k = 0; k < 3; ++k) ms[k][lj * SS_LD + lc] = ok ? m0[k * nplanes * oplane] : 0.f;
+      }
+    }
   }
   __syncthreads();
   // transposed window along dim 1: t[qi, pj] = sum_a f[a] map[qi - a, pj]  (tile index li + L-1 - a)

@@ -41,10 +41,10 @@ static __global__ void k_clamp_params(float* lambda, float* rho, float* h, int n
     if (do_clamp) {
       if (i < 2 * PS) {
         m = (v >= creg) ? 1.f : 0.f;
-        *p = fmaxf(v, creg);
+        *p = (v != v) ? v : fmaxf(v, creg);   // Julia's clamp propagates NaN (fmaxf would replace it by the bound)
       } else {
         m = (v >= 0.f && v <= 1.f) ? 1.f : 0.f;
-        *p = fminf(fmaxf(v, 0.f), 1.f);
+        *p = (v != v) ? v : fminf(fmaxf(v, 0.f), 1.f);
       }
     }
     if (mask) mask[i] = m;

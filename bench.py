@@ -45,6 +45,8 @@ WORKLOADS = {
                        desc="one GPU's share of BASELINE.json configs[2] at 8 GPUs: 32 x 256x256 RGB, 10 iterations, fwd+bwd"),
     "cfg4": dict(B=16, P=1, N=2048, M=2048, k=31, iters=200, mode="fwd", psf="motion",
                  desc="BASELINE.json configs[3]: batch 16 x 2048x2048 gray, 31x31 PSF, 200-iteration forward"),
+    "vga": dict(B=64, P=3, N=640, M=480, k=15, iters=50, mode="fwd", psf="motion",
+                desc="mixed-radix lengths: batch 64 x 480x640 RGB (Julia (M, N) = (480, 640)), 15x15 PSF, 50-iteration forward (tuning workload)"),
     "w4096": dict(B=4, P=1, N=4096, M=4096, k=31, iters=50, mode="fwd", psf="motion",
                   desc="largest planned FFT length: batch 4 x 4096x4096 gray, 31x31 PSF, 50-iteration forward (tuning workload)"),
     "cfg5": dict(B=1024, P=1, N=128, M=128, k=9, iters=50, mode="fwd", psf="motion",

@@ -67,6 +67,9 @@ def test_emu_clamp_is_persisted(emu):
     r = E.forward(emu, y.numpy(), -1.0, 0.01, hh, False, 2, creg=0.05)
     assert r["lam"][0] == np.float32(0.05) and r["rho"][0] == np.float32(0.05)     # deconv_admm.jl:216-217
     assert r["h"][0, 0] == 0.0 and r["h"][1, 1] == 1.0                              # :219
+    # Julia's clamp(NaN, lo, hi) is NaN: a diverged parameter stays visible instead of being reset to the bound
+    r = E.forward(emu, y.numpy(), float("nan"), 0.01, hh, False, 2, creg=0.05)
+    assert np.isnan(r["lam"][0]) and r["rho"][0] == np.float32(0.05)
 
 
 @pytest.mark.parametrize("M,N,P,B,kh,kw,K", [(32, 32, 1, 2, 0, 0, 2), (32, 64, 3, 1, 5, 4, 4), (64, 32, 1, 3, 3, 3, 5)])
