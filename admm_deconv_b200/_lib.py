@@ -63,6 +63,7 @@ HOST_SYMBOLS = (
     "admmtv_host_unpin",
     "admmtv_host_forward_enqueue",
     "admmtv_host_train_step_enqueue",
+    "admmtv_host_train_step_enqueue_n0f8",
     "admmtv_host_grad_floats",
     "admmtv_host_wait",
     "admmtv_host_launches",
@@ -153,6 +154,7 @@ class AdmmTvLib:
             L.admmtv_host_unpin.argtypes = [vp]
             L.admmtv_host_forward_enqueue.argtypes = [vp, i] + [vp] * 6
             L.admmtv_host_train_step_enqueue.argtypes = [vp, i] + [vp] * 9 + [C.POINTER(Hooks)]
+            L.admmtv_host_train_step_enqueue_n0f8.argtypes = [vp, i, vp, vp] + [C.c_int64] * 4 + [vp] * 6 + [C.POINTER(Hooks)]
             L.admmtv_host_grad_floats.argtypes = [C.POINTER(Desc)]
             L.admmtv_host_wait.argtypes = [vp, i]
             L.admmtv_host_launches.argtypes = [vp, i]
@@ -249,6 +251,11 @@ class AdmmTvLib:
     def host_train_step_enqueue(self, sess, slot, y, target, h, lam, rho, bias, grads_out, loss_out, ybar_out=None, hooks=None):
         self._raise(self.lib.admmtv_host_train_step_enqueue(sess, slot, y, target, h, lam, rho, bias, grads_out, loss_out, ybar_out,
                                                             None if hooks is None else C.byref(hooks)))
+
+    def host_train_step_enqueue_n0f8(self, sess, slot, y, target, strides, h, lam, rho, bias, grads_out, loss_out, hooks=None):
+        sc, si, sj, sb = strides
+        self._raise(self.lib.admmtv_host_train_step_enqueue_n0f8(sess, slot, y, target, sc, si, sj, sb, h, lam, rho, bias, grads_out,
+                                                                 loss_out, None if hooks is None else C.byref(hooks)))
 
     def mse_train_step(self, d: Desc, y, target, h, lam, rho, bias, x_out, ybar, grads, loss_sum, ws_fwd, ckpt, ws_bwd,
                        stream=0, hooks=None):

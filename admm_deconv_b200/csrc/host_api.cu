@@ -1,6 +1,7 @@
 // host_api.cu -- the host-buffer entry points of include/admmtv_host.h: a thin, stream-pipelined layer over the
 // device-pointer C ABI (admmtv_forward / admmtv_backward).  Everything still runs on the GPU.
 #include "../../include/admmtv_host.h"
+#include "../../include/admmtv_batch.h"
 
 #include <cuda_runtime.h>
 #include <new>
@@ -289,6 +290,55 @@ int admmtv_host_train_step_enqueue(admmtv_host_session* s, int slot, const float
   } else {
     HCHECK(cudaEventRecord(sl.out_done, s->copy_out));
   }
+  sl.loss_out = loss_out;
+  sl.pending = true;
+  return ADMMTV_OK;
+}
+
+int admmtv_host_train_step_enqueue_n0f8(admmtv_host_session* s, int slot, const uint8_t* y, const uint8_t* target,
+                                        int64_t stride_c, int64_t stride_i, int64_t stride_j, int64_t stride_b, float* h,
+                                        float* lambda, float* rho, const float* bias, float* grads_out, float* loss_out,
+                                        const admmtv_hooks* hooks) {
+  if (!s || !y || !target || !lambda || !rho || !grads_out) return ADMMTV_ERR_NULL;
+  if (!s->training) return ADMMTV_ERR_ENUM;
+  if (s->nh > 0 && !h) return ADMMTV_ERR_NULL;
+  if (s->d.has_bias && !bias) return ADMMTV_ERR_NULL;
+  if (slot < 0 || slot > 1) return ADMMTV_ERR_ENUM;
+  if (stride_c < 0 || stride_i < 0 || stride_j < 0 || stride_b < 0) return ADMMTV_ERR_SHAPE;
+  DevGuard guard(s->d.device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  Slot& sl = s->slot[slot];
+  // The slot's output buffer x (4 bytes per sample, written by the forward only after the conversion kernels have run) stages
+  // the two byte arrays: in_img + out_img <= 4 out_img bytes.  The byte extent of a strided source is its largest offset + 1.
+  const int Bin = (int)(s->in_img / ((size_t)s->d.M * s->d.N * s->d.P));
+  auto extent = [&](int B) {
+    return (size_t)((int64_t)(s->d.P - 1) * stride_c + (int64_t)(s->d.M - 1) * stride_i + (int64_t)(s->d.N - 1) * stride_j +
+                    (int64_t)(B - 1) * stride_b + 1);
+  };
+  const size_t ny = extent(Bin), nt = extent(s->d.B);
+  if (al256(ny) + nt > s->out_img * 4) return ADMMTV_ERR_SHAPE;   // padded strides larger than 4 bytes per sample
+  uint8_t* sy = reinterpret_cast<uint8_t*>(sl.x);
+  uint8_t* st = sy + al256(ny);
+  HCHECK(cudaMemcpyAsync(sy, y, ny, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaMemcpyAsync(st, target, nt, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
+  HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
+  int rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, Bin, s->d.device, sy, stride_c, stride_i, stride_j, stride_b, sl.y, s->compute);
+  if (rc) return rc;
+  if ((rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, s->d.B, s->d.device, st, stride_c, stride_i, stride_j, stride_b, sl.target,
+                                   s->compute)))
+    return rc;
+  if ((rc = upload_params(s, h, lambda, rho, bias))) return rc;
+  if ((rc = admmtv_mse_train_step(&s->d, sl.y, sl.target, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho,
+                                  s->d.has_bias ? s->bias : nullptr, sl.x, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
+                                  s->ckpt, s->ws_bwd, s->compute, hooks)))
+    return rc;
+  HCHECK(cudaMemcpyAsync(grads_out, s->packed, (size_t)s->ngrad * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(s->loss_host[slot], s->loss_acc, sizeof(double), cudaMemcpyDeviceToHost, s->compute));
+  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  HCHECK(cudaEventRecord(sl.compute_done, s->compute));
+  HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
+  HCHECK(cudaEventRecord(sl.out_done, s->copy_out));
   sl.loss_out = loss_out;
   sl.pending = true;
   return ADMMTV_OK;

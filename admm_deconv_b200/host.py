@@ -77,6 +77,27 @@ class HostSession:
                                          _hptr(bias), _hptr(grads), _hptr(loss), _hptr(ybar), self._hooks)
         return grads, loss
 
+    def train_step_enqueue_n0f8(self, slot, y_u8, target_u8, lam, rho, h=None, bias=None, grads=None, loss=None, layout="BCNM"):
+        """The same step fed with 8-bit samples (value / 255), the dataset's own format: 1 byte per sample crosses PCIe and the
+        conversion to the fp32 (M,N,P,B) batch runs on the device (``admmtv_host_train_step_enqueue_n0f8``).
+        ``layout``: "BCNM" = planar uint8 (B,P,N,M) like the float tensors; "BNMC" = channel-interleaved images (B,N,M,P) as
+        decoded image files are (``staging.ImageDataFeeder``'s convention)."""
+        for t in (y_u8, target_u8):
+            if t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous():
+                raise TypeError("n0f8 host arguments must be contiguous CPU uint8 tensors")
+        M, N, P = self.desc.M, self.desc.N, self.desc.P
+        if layout == "BCNM":
+            strides = (M * N, 1, M, M * N * P)          # channel, dim 1 (M), dim 2 (N), image
+        elif layout == "BNMC":
+            strides = (1, P, P * M, M * N * P)
+        else:
+            raise ValueError("layout must be 'BCNM' or 'BNMC'")
+        grads = torch.empty(self.ngrad, dtype=torch.float32) if grads is None else grads
+        loss = torch.empty(1, dtype=torch.float32) if loss is None else loss
+        self.lib.host_train_step_enqueue_n0f8(self._sess, slot, y_u8.data_ptr(), target_u8.data_ptr(), strides, _hptr(h), _hptr(lam),
+                                              _hptr(rho), _hptr(bias), _hptr(grads), _hptr(loss), self._hooks)
+        return grads, loss
+
     def wait(self, slot):
         self.lib.host_wait(self._sess, slot)
 

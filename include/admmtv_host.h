@@ -57,6 +57,17 @@ int admmtv_host_forward_enqueue(admmtv_host_session* s, int slot, const float* y
 int admmtv_host_train_step_enqueue(admmtv_host_session* s, int slot, const float* y, const float* target, float* h,
                                    float* lambda, float* rho, const float* bias, float* grads_out, float* loss_out,
                                    float* ybar_out, const admmtv_hooks* hooks);
+
+/* The same step fed with the dataset's own sample format: `y` and `target` are HOST arrays of 8-bit samples (N0f8, value / 255:
+ * what `load(img)` yields before `img2tensor`, base_funcs.jl:29-35) of the batch's (M,N,P,B) images with ELEMENT strides
+ * stride_c / stride_i / stride_j / stride_b (channel, dim 1, dim 2, image) as in admmtv_batch_from_n0f8 (admmtv_batch.h).
+ * One byte per sample crosses PCIe instead of four; conversion, de-interleave and placement run on the device (the kernel
+ * of admmtv_batch_from_n0f8) in front of the forward.  Replaces datafeeder.jl:54-68 + `|> gpu` (train.jl:50) + the step.
+ * Bit-identical to admmtv_host_train_step_enqueue on the float arrays value / 255.  No cotangent of the input is returned. */
+int admmtv_host_train_step_enqueue_n0f8(admmtv_host_session* s, int slot, const uint8_t* y, const uint8_t* target,
+                                        int64_t stride_c, int64_t stride_i, int64_t stride_j, int64_t stride_b, float* h,
+                                        float* lambda, float* rho, const float* bias, float* grads_out, float* loss_out,
+                                        const admmtv_hooks* hooks);
 int admmtv_host_grad_floats(const admmtv_desc* desc);
 
 /* Device-pointer twin of the training step above (inputs already resident in HBM; every pointer is a DEVICE pointer,

@@ -45,7 +45,7 @@ def test_loss_header_symbols_all_exported(lib):
 def test_host_header_symbols_all_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "admmtv_host.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(admmtv_(?:host|mse)_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(admmtv_(?:host|mse)_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.HOST_SYMBOLS)
     for name in declared:
         assert hasattr(lib.lib, name), name

@@ -100,3 +100,29 @@ def test_host_session_rejects_device_tensors():
     with pytest.raises(RuntimeError, match="CPU tensors"):
         s.forward(torch.zeros(1, 1, 32, 32, device="cuda:0"), torch.tensor([0.1]), torch.tensor([0.1]))
     s.close()
+
+
+@pytest.mark.parametrize("layout", ["BCNM", "BNMC"])
+def test_host_train_step_from_8bit_samples(layout):
+    """admmtv_host_train_step_enqueue_n0f8: the batch and the target travel as 8-bit samples (the dataset's format,
+    base_funcs.jl:29-35 converts them on the CPU) and are converted on the device; same result as the float call on value / 255,
+    pipelined over both slots."""
+    M, N, P, B, k, K = 64, 96, 3, 4, 5, 6
+    rng = np.random.Generator(np.random.PCG64(5))
+    _, ht, *_ = _case(M, N, P, B, k, 31)
+    lam = torch.tensor([0.0041]); rho = torch.tensor([0.021])
+    s = host.HostSession(M, N, P, B, k, k, iters=K, training=True)
+    for step in range(3):
+        yu = torch.from_numpy(rng.integers(0, 256, size=(B, P, N, M), dtype=np.uint8))
+        tu = torch.from_numpy(rng.integers(0, 256, size=(B, P, N, M), dtype=np.uint8))
+        yf = (yu.float() / 255.0).pin_memory(); tf = (tu.float() / 255.0).pin_memory()
+        g0, l0 = s.train_step(yf, tf, lam.clone(), rho.clone(), ht.clone())
+        g0, l0 = g0.clone(), float(l0)
+        if layout == "BNMC":
+            yu, tu = yu.permute(0, 2, 3, 1).contiguous(), tu.permute(0, 2, 3, 1).contiguous()
+        sl = step & 1
+        g1, l1 = s.train_step_enqueue_n0f8(sl, yu.pin_memory(), tu.pin_memory(), lam.clone(), rho.clone(), ht.clone(), layout=layout)
+        s.wait(sl)
+        assert float(l1) == l0
+        assert rel_l2(g1[: k * k], g0[: k * k]) < 1e-6 and torch.allclose(g1[k * k:], g0[k * k:], rtol=1e-5, atol=0)
+    s.close()

@@ -31,6 +31,20 @@ for shp in [(70,37,1,2),(16,12,3,2),(5,3,2,1)]:
     x,yy=TL._images(*shp,3); print('gmsd',shp,TL.run_gmsd(lib,x,yy)[0], flush=True)
 for shp in [(45,70,1,2),(24,20,3,2),(11,11,1,1)]:
     x,yy=TL._images(*shp,3); print('ssim',shp,TL.run_ssim(lib,x,yy)[0], TL.run_ssim(lib,x,yy,taps=[0.2]*5)[0], flush=True)
+# round 2c: streaming GMSD strips (ragged rows / columns, planes smaller than a strip), register-blocked SSIM, arbitrary windows, pad_symmetric
+for shp in [(31,65,1,1),(61,129,2,1),(3,2,1,1),(64,64,1,1)]:
+    x,yy=TL._images(*shp,5); print('gmsd strips',shp,TL.run_gmsd(lib,x,yy)[0], flush=True)
+for shp in [(33,33,1,1),(64,43,2,1),(75,97,1,1)]:
+    x,yy=TL._images(*shp,6); print('ssim4',shp,TL.run_ssim(lib,x,yy)[0], TL.run_ssim(lib,x,yy,taps=[0.2]*5)[0], TL.run_ssim(lib,x,yy,taps=[0.25]*4)[0], flush=True)
+for (shp,L1,L2) in [((24,20,1,1),5,5),((45,70,1,1),11,3),((40,36,1,1),11,11),((12,9,1,1),1,4)]:
+    x,yy=TL._images(*shp,7); print('ssim window',shp,L1,L2,TL.run_ssim_window(lib,x,yy,TL._window(L1,L2,L1+L2))[0], flush=True)
+for (M,N,Pn,pads) in [(9,7,3,(5,5,5,5)),(6,11,2,(2,1,0,3)),(4,4,1,(4,4,4,4))]:
+    src=np.asfortranarray(rng_pad:=np.random.default_rng(1).standard_normal((M,N,Pn,1)).astype(np.float32))
+    out=np.asfortranarray(np.zeros((M+pads[0]+pads[1],N+pads[2]+pads[3],Pn,1),np.float32))
+    lib.pad_symmetric(M,N,Pn,pads,0,src.ctypes.data,out.ctypes.data)
+    back=np.asfortranarray(np.zeros((M,N,Pn,1),np.float32))
+    lib.pad_symmetric_adjoint(M,N,Pn,pads,0,out.ctypes.data,back.ctypes.data)
+    print('pad_symmetric',M,N,pads,float(np.abs(back).sum())>0, flush=True)
 rng=np.random.default_rng(0)
 for (M,N,C,B) in [(40,33,3,2),(7,5,5,1)]:
     img=rng.integers(0,256,size=(B,M,N,C),dtype=np.uint8); dst=np.asfortranarray(np.zeros((M,N,C,B),np.float32))
