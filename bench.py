@@ -7,8 +7,8 @@
 Headline ("value"): BASELINE.json's metric -- ADMM megapixel-iterations/s, forward + backward + gradient all-reduce --
 on configs[1]'s batch (64 x 512x512 RGB, motion-blur PSF 15x15) with 10 unrolled iterations per step, inputs resident in
 HBM (admmtv_mse_train_step, include/admmtv_host.h).  "e2e" is the same step through the host-buffer C-ABI session
-(admmtv_host_train_step_enqueue / _wait): batch and target uploaded from pinned host memory and the gradients + loss
-downloaded inside the timed region, every step.  The "others" block carries short runs of every other BASELINE config
+(admmtv_host_train_step_enqueue_n0f8 / _wait): batch and target uploaded from pinned host memory as the 8-bit samples
+they are, the gradients + loss downloaded, inside the timed region, every step ("e2e_f32": the same values as fp32 arrays).  The "others" block carries short runs of every other BASELINE config
 (configs[1] forward-only with 100 iterations, configs[2] strong-scaled over the ranks, configs[3], configs[4] with
 per-image PSFs), each with its own time, roofline fraction and clock record.  Weak scaling: every rank gets its own
 batch of 64 for the headline.
@@ -82,6 +82,7 @@ def config_of(w, name):
     return {"workload": w["desc"], "name": name, "mode": w["mode"], "iters": w["iters"],
             "image": f"{w['M']}x{w['N']}x{w['P']}", "per_gpu_batch": w["B"], "psf": f"{w['k']}x{w['k']} {w['psf']}",
             "lambda": 0.0041, "rho": 0.021, "iso": bool(w.get("iso", False)), "loss": "mse" if w["mode"] == "fwd+bwd" else None,
+            "samples": "8-bit image values k/255 held as fp32" if w["mode"] == "fwd+bwd" else "fp32",
             "l2": "per-iteration state is larger than the 126 MB L2 (no flush needed)"}
 
 
@@ -199,6 +200,11 @@ def make_inputs(w, seed, B=None):
     gp = torch.nn.functional.pad(g.reshape(-1, 1, N, M), (pu, pd, pu, pd), mode="circular")
     y = torch.nn.functional.conv2d(gp, torch.flip(hk, dims=(0, 1)).reshape(1, 1, k, k)).reshape(g.shape)
     y = y + 0.02 * torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32))
+    if w["mode"] == "fwd+bwd":
+        # training batches are decoded 8-bit images (datafeeder.jl:54-68): both arms, the resident step and the host-buffer
+        # step see the same values k / 255, and the host-buffer step can upload them as bytes (e2e below)
+        y = (y.clamp(0, 1) * 255).round() / 255
+        g = (g.clamp(0, 1) * 255).round() / 255
     reps = (B + nb - 1) // nb
     y = y.repeat(reps, 1, 1, 1)[:B].contiguous()
     g = g.repeat(reps, 1, 1, 1)[:B].contiguous()
@@ -444,8 +450,11 @@ class TrainStep:
 
 
 def e2e_train(c, w, B, steps, warmup, ts: TrainStep):
-    """The same step through the host-buffer C-ABI session, two slots pipelined: H2D of batch + target and D2H of
-    gradients + loss inside the timed region, every step."""
+    """The same step through the host-buffer C-ABI session, two slots pipelined, copies inside the timed region every step.
+    Primary: the batch and the target are uploaded as the 8-bit samples they are (admmtv_host_train_step_enqueue_n0f8, one
+    byte per sample, fp32 batch built on the device) and the gradients + loss come back.  "f32": the same values uploaded as
+    fp32 arrays (admmtv_host_train_step_enqueue, what `|> gpu` of train.jl:50 moves): four times the bytes, which saturates
+    the host's memory once eight ranks share it."""
     import torch
     from admm_deconv_b200 import host
 
@@ -456,53 +465,39 @@ def e2e_train(c, w, B, steps, warmup, ts: TrainStep):
     h = ts.h_host.clone().pin_memory()
     grads = [torch.empty(s.ngrad).pin_memory() for _ in range(2)]
     loss = [torch.empty(1).pin_memory() for _ in range(2)]
+    yu = (ts.y_host * 255).round().to(torch.uint8).pin_memory()      # exact: the batch holds k / 255
+    gu = (ts.g_host * 255).round().to(torch.uint8).pin_memory()
+    small = (h.numel() + 2) * 4
 
-    def run(n):
-        for i in range(n):
-            sl = i & 1
-            if i >= 2:
-                s.wait(sl)
-            s.train_step_enqueue(sl, ts.y_host, ts.g_host, lam, rho, h, grads=grads[sl], loss=loss[sl])
-        s.wait(0); s.wait(1)
-
-    run(max(warmup, 3))
-    barrier(c)
-    t0 = time.perf_counter()
-    run(steps)
-    barrier(c)
-    ms = (time.perf_counter() - t0) * 1e3 / steps
-    ms = max_over_ranks(c, [ms])[0]
-    out = {"ms_per_step": ms, "h2d_bytes_per_step": (ts.y_host.numel() + ts.g_host.numel()) * 4 + (h.numel() + 2) * 4,
-           "d2h_bytes_per_step": s.ngrad * 4 + 8, "loss": float(loss[(steps - 1) & 1]), "launches_per_step": s.launches(),
-           "path": "admmtv_host_train_step_enqueue / admmtv_host_wait (include/admmtv_host.h), pinned host buffers, 2 slots",
-           "timer": "host wall clock around the blocking calls (max over ranks)"}
-    # The same step fed with the dataset's own sample format (8-bit images, converted on the device): a quarter of the bytes
-    # cross PCIe, which is what keeps eight ranks on one host from saturating its memory.  Reported beside the float path.
-    try:
-        yu = (ts.y_host.clamp(0, 1) * 255).round().to(torch.uint8).pin_memory()
-        gu = (ts.g_host.clamp(0, 1) * 255).round().to(torch.uint8).pin_memory()
-
-        def run8(n):
+    def timed(enqueue):
+        def run(n):
             for i in range(n):
                 sl = i & 1
                 if i >= 2:
                     s.wait(sl)
-                s.train_step_enqueue_n0f8(sl, yu, gu, lam, rho, h, grads=grads[sl], loss=loss[sl])
+                enqueue(sl)
             s.wait(0); s.wait(1)
-
-        run8(max(warmup, 3))
+        run(max(warmup, 3))
         barrier(c)
         t0 = time.perf_counter()
-        run8(steps)
+        run(steps)
         barrier(c)
-        ms8 = max_over_ranks(c, [(time.perf_counter() - t0) * 1e3 / steps])[0]
-        out["n0f8"] = {"ms_per_step": ms8, "h2d_bytes_per_step": yu.numel() + gu.numel() + (h.numel() + 2) * 4,
-                       "d2h_bytes_per_step": s.ngrad * 4 + 8, "loss": float(loss[(steps - 1) & 1]),
-                       "launches_per_step": s.launches() + 2,
-                       "path": "admmtv_host_train_step_enqueue_n0f8: batch and target as 8-bit samples (value / 255, clamped to [0, 1]) in "
-                               "pinned host memory, fp32 batch built on the device (2 more launches), same kernels afterwards"}
+        return max_over_ranks(c, [(time.perf_counter() - t0) * 1e3 / steps])[0]
+
+    ms8 = timed(lambda sl: s.train_step_enqueue_n0f8(sl, yu, gu, lam, rho, h, grads=grads[sl], loss=loss[sl]))
+    loss8 = float(loss[(steps - 1) & 1])
+    out = {"ms_per_step": ms8, "h2d_bytes_per_step": yu.numel() + gu.numel() + small,
+           "d2h_bytes_per_step": s.ngrad * 4 + 8, "loss": loss8, "launches_per_step": s.launches() + 2,
+           "path": "admmtv_host_train_step_enqueue_n0f8 / admmtv_host_wait (include/admmtv_host.h): batch and target as 8-bit "
+                   "samples in pinned host memory, fp32 batch built on the device (2 more launches), 2 slots",
+           "timer": "host wall clock around the blocking calls (max over ranks)"}
+    try:
+        msf = timed(lambda sl: s.train_step_enqueue(sl, ts.y_host, ts.g_host, lam, rho, h, grads=grads[sl], loss=loss[sl]))
+        out["f32"] = {"ms_per_step": msf, "h2d_bytes_per_step": (ts.y_host.numel() + ts.g_host.numel()) * 4 + small,
+                      "d2h_bytes_per_step": s.ngrad * 4 + 8, "loss": float(loss[(steps - 1) & 1]), "launches_per_step": s.launches(),
+                      "path": "admmtv_host_train_step_enqueue: the same values as fp32 host arrays"}
     except Exception as e:   # the extra measurement must never take the headline down
-        out["n0f8"] = {"error": repr(e)}
+        out["f32"] = {"error": repr(e)}
     s.close()
     return out
 
@@ -666,12 +661,12 @@ def run_native(args, w, name):
             px_all = w["B"] * w["P"] * w["N"] * w["M"] * c.world
             line["roofline"] = extra["roofline"]
             e = dict(e)
-            n8 = e.pop("n0f8", None)
+            f32 = e.pop("f32", None)
             line["e2e"] = {"value": px_all * w["iters"] / (e["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT, **e}
-            if n8 is not None:
-                if "ms_per_step" in n8:
-                    n8 = {"value": px_all * w["iters"] / (n8["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT, **n8}
-                line["e2e_n0f8"] = n8
+            if f32 is not None:
+                if "ms_per_step" in f32:
+                    f32 = {"value": px_all * w["iters"] / (f32["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT, **f32}
+                line["e2e_f32"] = f32
             line["gpu_launches"] = extra["launches_per_step"] * args.steps
             if c.world > 1:
                 line["collective"] = r["collective"]
