@@ -323,6 +323,28 @@ int admmtv_batch_from_n0f8(int M, int N, int C, int B, int device, const uint8_t
   if (stride_c < 0 || stride_i < 0 || stride_j < 0 || stride_b < 0) return ADMMTV_ERR_SHAPE;
   DevGuard guard(device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  {
+    // contiguous layouts take the vectorised kernels (bit-identical results)
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t plane = (size_t)M * N, n = plane * C * B;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    if (aligned && stride_i == 1 && stride_j == M && stride_c == (int64_t)plane && stride_b == (int64_t)(plane * C)) {
+      const size_t n16 = n / 16, nb = (n16 + 255) / 256;
+      ADMMTV_LAUNCH(k_batch_flat_n0f8, dim3((unsigned)(nb < 148 * 32 ? (nb ? nb : 1) : 148 * 32)), dim3(256), 0, st, src, dst, n16, n);
+      cudaError_t e = cudaGetLastError();
+      return e == cudaSuccess ? ADMMTV_OK : (int)e;
+    }
+    if (aligned && stride_c == 1 && stride_i == C && stride_j == (int64_t)C * M && stride_b % 4 == 0 && plane % 4 == 0 &&
+        (C == 1 || C == 3 || C == 4)) {
+      const size_t px4 = plane / 4, tot = px4 * B, nb = (tot + 255) / 256;
+      const dim3 grid((unsigned)(nb < 148 * 32 ? (nb ? nb : 1) : 148 * 32));
+      if (C == 1) ADMMTV_LAUNCH(k_batch_interleaved_n0f8<1>, grid, dim3(256), 0, st, src, dst, px4, plane, (long long)stride_b, B);
+      else if (C == 3) ADMMTV_LAUNCH(k_batch_interleaved_n0f8<3>, grid, dim3(256), 0, st, src, dst, px4, plane, (long long)stride_b, B);
+      else ADMMTV_LAUNCH(k_batch_interleaved_n0f8<4>, grid, dim3(256), 0, st, src, dst, px4, plane, (long long)stride_b, B);
+      cudaError_t e = cudaGetLastError();
+      return e == cudaSuccess ? ADMMTV_OK : (int)e;
+    }
+  }
   BatchArgs a{};
   a.src = src; a.dst = dst; a.M = M; a.N = N; a.C = C; a.B = B;
   a.tiles_i = (M + BA_T - 1) / BA_T; a.tiles_j = (N + BA_T - 1) / BA_T;

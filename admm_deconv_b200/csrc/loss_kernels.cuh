@@ -791,4 +791,44 @@ __global__ void __launch_bounds__(BA_NT) k_batch_from_n0f8(BatchArgs A) {
   }
 }
 
+
+// Fast paths of the same conversion for the two CONTIGUOUS layouts (every access a full, aligned vector; the general kernel
+// above spends its time on per-element index arithmetic: 234 us for 64 x 512^2 x 3 samples against 40 us of DRAM time).
+// (a) planar bytes in the destination's own order (stride_i = 1, stride_j = M, stride_c = M N, stride_b = M N C): a flat
+//     elementwise pass, 16 samples per thread.
+__global__ void __launch_bounds__(256) k_batch_flat_n0f8(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n16, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < n16; e += (size_t)gridDim.x * 256) {
+    const uint4 v = reinterpret_cast<const uint4*>(src)[e];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    float4* o = reinterpret_cast<float4*>(dst) + 4 * e;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      o[q] = make_float4((float)(w[q] & 255u) / 255.f, (float)((w[q] >> 8) & 255u) / 255.f, (float)((w[q] >> 16) & 255u) / 255.f,
+                         (float)(w[q] >> 24) / 255.f);
+  }
+  if (blockIdx.x == 0)   // tail (n not a multiple of 16)
+    for (size_t e = 16 * n16 + threadIdx.x; e < n; e += 256) dst[e] = (float)src[e] / 255.f;
+}
+// (b) channel-interleaved pixels, dim 1 fastest (stride_c = 1, stride_i = C, stride_j = C M: Julia Matrix{RGB{N0f8}}): pixel
+//     p = i + M j of image b sits at byte C p + c.  A thread takes 4 pixels = C aligned 32-bit words and writes one float4 per plane.
+template <int C>
+__global__ void __launch_bounds__(256) k_batch_interleaved_n0f8(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t px4,
+                                                                size_t plane, long long sb, int B) {
+  const size_t total = px4 * (size_t)B;   // px4 = M N / 4 groups of 4 pixels per image
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const size_t b = e / px4, g = e % px4;
+    const unsigned* sp = reinterpret_cast<const unsigned*>(src + b * (size_t)sb) + g * C;
+    unsigned w[C];
+#pragma unroll
+    for (int q = 0; q < C; ++q) w[q] = sp[q];
+    float out[C][4];
+#pragma unroll
+    for (int k = 0; k < 4 * C; ++k)   // byte k of the group = channel k % C of pixel k / C
+      out[k % C][k / C] = (float)((w[k / 4] >> (8 * (k % 4))) & 255u) / 255.f;
+    float* dp = dst + b * (size_t)C * plane + 4 * g;
+#pragma unroll
+    for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(dp + (size_t)c * plane) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+  }
+}
+
 }  // namespace admmtv

@@ -40,6 +40,7 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct uint3 { unsigned x, y, z; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 
 namespace emu {
 struct BlockCtx {

@@ -1,7 +1,8 @@
 """Static SASS instruction-class counts of the hot kernels of libadmmtv.so (cuobjdump -sass), written as CSV.
     python tools/sass_summary.py [lib] > profiles/<round>_sass_summary.csv
 UTMALDG / UTMASTG = TMA tensor tile load / store (cp.async.bulk.tensor), SYNCS = mbarrier operations, UBLKPF = TMA bulk L2
-prefetch, FADD2 / FFMA2 / FMUL2 = packed dual-fp32 arithmetic."""
+prefetch, FADD2 / FFMA2 / FMUL2 = packed dual-fp32 arithmetic, UCGABAR_* = cluster barrier (barrier.cluster.arrive / wait;
+the distributed-shared-memory accesses of k_dim2c are the LD / ST through the mapa'd window, counted under "total")."""
 import collections
 import os
 import re
@@ -11,9 +12,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "admm_deconv_b200", "libadmmtv.so")
 HOT = re.compile(r"k_dim1_fwd(_tma)?<(7|8|9|11), |k_dim1_bwd(_tma)?<(8|9), |k_dim2t?<(9|11), |k_small<7, 7|k_pack_fft1(_tma)?<9, 0|k_dim1_out(_tma)?<9, 1|"
-                 r"k_dim1_bwd_last(_tma)?<9, 0")
+                 r"k_dim1_bwd_last(_tma)?<9, 0|k_dim2c<12, 0|k_gmsd_(fwd|bwd)_s|k_ssim_(fwd|bwd)4<11")
 CLASSES = ["UTMALDG", "UTMASTG", "SYNCS", "UBLKPF", "FADD2", "FFMA2", "FMUL2", "FADD", "FFMA", "FMUL", "LDG", "STG", "LDS", "STS", "RED",
-           "ATOMG", "BAR", "WARPSYNC", "SHFL", "DADD", "LDGSTS"]
+           "ATOMG", "BAR", "WARPSYNC", "SHFL", "DADD", "LDGSTS", "UCGABAR_ARV", "UCGABAR_WAIT", "MUFU"]
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 names = {}
 counts = collections.OrderedDict()
