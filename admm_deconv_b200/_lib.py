@@ -62,6 +62,7 @@ HOST_SYMBOLS = (
     "admmtv_host_pin",
     "admmtv_host_unpin",
     "admmtv_host_forward_enqueue",
+    "admmtv_host_forward_enqueue_n0f8",
     "admmtv_host_train_step_enqueue",
     "admmtv_host_train_step_enqueue_n0f8",
     "admmtv_host_grad_floats",
@@ -154,6 +155,7 @@ class AdmmTvLib:
             L.admmtv_host_unpin.argtypes = [vp]
             L.admmtv_host_forward_enqueue.argtypes = [vp, i] + [vp] * 6
             L.admmtv_host_train_step_enqueue.argtypes = [vp, i] + [vp] * 9 + [C.POINTER(Hooks)]
+            L.admmtv_host_forward_enqueue_n0f8.argtypes = [vp, i, vp] + [C.c_int64] * 4 + [vp] * 5
             L.admmtv_host_train_step_enqueue_n0f8.argtypes = [vp, i, vp, vp] + [C.c_int64] * 4 + [vp] * 6 + [C.POINTER(Hooks)]
             L.admmtv_host_grad_floats.argtypes = [C.POINTER(Desc)]
             L.admmtv_host_wait.argtypes = [vp, i]
@@ -251,6 +253,10 @@ class AdmmTvLib:
     def host_train_step_enqueue(self, sess, slot, y, target, h, lam, rho, bias, grads_out, loss_out, ybar_out=None, hooks=None):
         self._raise(self.lib.admmtv_host_train_step_enqueue(sess, slot, y, target, h, lam, rho, bias, grads_out, loss_out, ybar_out,
                                                             None if hooks is None else C.byref(hooks)))
+
+    def host_forward_enqueue_n0f8(self, sess, slot, y, strides, h, lam, rho, bias, x_out):
+        sc, si, sj, sb = strides
+        self._raise(self.lib.admmtv_host_forward_enqueue_n0f8(sess, slot, y, sc, si, sj, sb, h, lam, rho, bias, x_out))
 
     def host_train_step_enqueue_n0f8(self, sess, slot, y, target, strides, h, lam, rho, bias, grads_out, loss_out, hooks=None):
         sc, si, sj, sb = strides

@@ -257,6 +257,42 @@ int admmtv_host_forward_enqueue(admmtv_host_session* s, int slot, const float* y
   return ADMMTV_OK;
 }
 
+int admmtv_host_forward_enqueue_n0f8(admmtv_host_session* s, int slot, const uint8_t* y, int64_t stride_c, int64_t stride_i,
+                                     int64_t stride_j, int64_t stride_b, float* h, float* lambda, float* rho, const float* bias,
+                                     float* x_out) {
+  if (!s || !y || !lambda || !rho || !x_out) return ADMMTV_ERR_NULL;
+  if (s->nh > 0 && !h) return ADMMTV_ERR_NULL;
+  if (s->d.has_bias && !bias) return ADMMTV_ERR_NULL;
+  if (slot < 0 || slot > 1) return ADMMTV_ERR_ENUM;
+  if (stride_c < 0 || stride_i < 0 || stride_j < 0 || stride_b < 0) return ADMMTV_ERR_SHAPE;
+  DevGuard guard(s->d.device);
+  if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
+  Slot& sl = s->slot[slot];
+  // the slot's output buffer x (written by the forward only after the conversion kernel has run) stages the bytes
+  const int Bin = (int)(s->in_img / ((size_t)s->d.M * s->d.N * s->d.P));
+  const size_t ny = (size_t)((int64_t)(s->d.P - 1) * stride_c + (int64_t)(s->d.M - 1) * stride_i + (int64_t)(s->d.N - 1) * stride_j +
+                             (int64_t)(Bin - 1) * stride_b + 1);
+  if (ny > s->out_img * 4) return ADMMTV_ERR_SHAPE;
+  uint8_t* sy = reinterpret_cast<uint8_t*>(sl.x);
+  HCHECK(cudaMemcpyAsync(sy, y, ny, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
+  HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
+  int rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, Bin, s->d.device, sy, stride_c, stride_i, stride_j, stride_b, sl.y, s->compute);
+  if (rc) return rc;
+  if ((rc = upload_params(s, h, lambda, rho, bias))) return rc;
+  rc = admmtv_forward(&s->d, sl.y, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho, s->d.has_bias ? s->bias : nullptr, sl.x,
+                      s->ws_fwd, nullptr, s->compute);
+  if (rc) return rc;
+  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  HCHECK(cudaEventRecord(sl.compute_done, s->compute));
+  HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
+  HCHECK(cudaMemcpyAsync(x_out, sl.x, s->out_img * 4, cudaMemcpyDeviceToHost, s->copy_out));
+  HCHECK(cudaEventRecord(sl.out_done, s->copy_out));
+  sl.loss_out = nullptr;
+  sl.pending = true;
+  return ADMMTV_OK;
+}
+
 int admmtv_host_train_step_enqueue(admmtv_host_session* s, int slot, const float* y, const float* target, float* h,
                                    float* lambda, float* rho, const float* bias, float* grads_out, float* loss_out,
                                    float* ybar_out, const admmtv_hooks* hooks) {

@@ -77,6 +77,24 @@ class HostSession:
                                          _hptr(bias), _hptr(grads), _hptr(loss), _hptr(ybar), self._hooks)
         return grads, loss
 
+    def _n0f8_strides(self, layout):
+        M, N, P = self.desc.M, self.desc.N, self.desc.P
+        if layout == "BCNM":
+            return (M * N, 1, M, M * N * P)          # channel, dim 1 (M), dim 2 (N), image
+        if layout == "BNMC":
+            return (1, P, P * M, M * N * P)
+        raise ValueError("layout must be 'BCNM' or 'BNMC'")
+
+    def forward_enqueue_n0f8(self, slot, y_u8, lam, rho, h=None, bias=None, out=None, layout="BCNM"):
+        """Forward fed with 8-bit samples (value / 255); ``out`` is the fp32 (B,P,N,M) result (``admmtv_host_forward_enqueue_n0f8``)."""
+        if y_u8.is_cuda or y_u8.dtype != torch.uint8 or not y_u8.is_contiguous():
+            raise TypeError("n0f8 host arguments must be contiguous CPU uint8 tensors")
+        d = self.desc
+        out = torch.empty((d.B, d.P, d.N, d.M), dtype=torch.float32) if out is None else out
+        self.lib.host_forward_enqueue_n0f8(self._sess, slot, y_u8.data_ptr(), self._n0f8_strides(layout), _hptr(h), _hptr(lam),
+                                           _hptr(rho), _hptr(bias), _hptr(out))
+        return out
+
     def train_step_enqueue_n0f8(self, slot, y_u8, target_u8, lam, rho, h=None, bias=None, grads=None, loss=None, layout="BCNM"):
         """The same step fed with 8-bit samples (value / 255), the dataset's own format: 1 byte per sample crosses PCIe and the
         conversion to the fp32 (M,N,P,B) batch runs on the device (``admmtv_host_train_step_enqueue_n0f8``).
@@ -85,13 +103,7 @@ class HostSession:
         for t in (y_u8, target_u8):
             if t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous():
                 raise TypeError("n0f8 host arguments must be contiguous CPU uint8 tensors")
-        M, N, P = self.desc.M, self.desc.N, self.desc.P
-        if layout == "BCNM":
-            strides = (M * N, 1, M, M * N * P)          # channel, dim 1 (M), dim 2 (N), image
-        elif layout == "BNMC":
-            strides = (1, P, P * M, M * N * P)
-        else:
-            raise ValueError("layout must be 'BCNM' or 'BNMC'")
+        strides = self._n0f8_strides(layout)
         grads = torch.empty(self.ngrad, dtype=torch.float32) if grads is None else grads
         loss = torch.empty(1, dtype=torch.float32) if loss is None else loss
         self.lib.host_train_step_enqueue_n0f8(self._sess, slot, y_u8.data_ptr(), target_u8.data_ptr(), strides, _hptr(h), _hptr(lam),

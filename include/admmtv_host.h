@@ -46,6 +46,14 @@ int admmtv_host_unpin(void* host_ptr);
 int admmtv_host_forward_enqueue(admmtv_host_session* s, int slot, const float* y, float* h, float* lambda, float* rho,
                                 const float* bias, float* x_out);
 
+/* The same forward call fed with 8-bit samples (N0f8, value / 255: a decoded image before `img2tensor`, base_funcs.jl:29-35;
+ * admm_deconv_test.jl:60-76 converts on the CPU and uploads fp32): `y` is a HOST byte array with ELEMENT strides
+ * stride_c / stride_i / stride_j / stride_b as in admmtv_batch_from_n0f8; one byte per sample crosses PCIe and the fp32
+ * batch is built on the device.  x_out is fp32 as above.  Bit-identical to the float call on value / 255. */
+int admmtv_host_forward_enqueue_n0f8(admmtv_host_session* s, int slot, const uint8_t* y, int64_t stride_c, int64_t stride_i,
+                                     int64_t stride_j, int64_t stride_b, float* h, float* lambda, float* rho, const float* bias,
+                                     float* x_out);
+
 /* One training step through slot 0 or 1 (train.jl:49-54 with the mean-squared-error loss):
  *   y, target -> device ; x = layer(y) with the per-iteration checkpoint ; loss = mean((x - target)^2),
  *   xbar = 2 (x - target) / numel ; admmtv_backward ; [hooks->allreduce_sum on the packed gradient buffer, once:

@@ -126,3 +126,19 @@ def test_host_train_step_from_8bit_samples(layout):
         assert float(l1) == l0
         assert rel_l2(g1[: k * k], g0[: k * k]) < 1e-6 and torch.allclose(g1[k * k:], g0[k * k:], rtol=1e-5, atol=0)
     s.close()
+
+
+def test_host_forward_from_8bit_samples():
+    """admmtv_host_forward_enqueue_n0f8: a decoded 8-bit image goes up as bytes; same restored image as the float call on value / 255."""
+    M, N, P, B, k = 96, 64, 3, 2, 7
+    rng = np.random.Generator(np.random.PCG64(9))
+    _, ht, *_ = _case(M, N, P, B, k, 41)
+    lam = torch.tensor([0.0041]); rho = torch.tensor([0.021])
+    s = host.HostSession(M, N, P, B, k, k, iters=9)
+    yu = torch.from_numpy(rng.integers(0, 256, size=(B, P, N, M), dtype=np.uint8))
+    x0 = s.forward((yu.float() / 255.0).pin_memory(), lam.clone(), rho.clone(), ht.clone()).clone()
+    for layout, src in (("BCNM", yu), ("BNMC", yu.permute(0, 2, 3, 1).contiguous())):
+        x1 = s.forward_enqueue_n0f8(1, src.pin_memory(), lam.clone(), rho.clone(), ht.clone(), layout=layout)
+        s.wait(1)
+        assert torch.equal(x1, x0), layout
+    s.close()
