@@ -89,11 +89,13 @@ class _Gmsd(torch.autograd.Function):
 
 
 def gmsd(x: torch.Tensor, y: torch.Tensor, t: float = 0.0026, alpha: float = 0.0, reduction=None) -> torch.Tensor:
-    """gmsd.jl:13-27.  ``reduction`` (gmsd.jl:13, default ``Flux.mean``) is applied to the per-image scores inside the
-    kernel; only the mean is implemented (None or ``torch.mean``)."""
-    if reduction is not None and reduction is not torch.mean:
-        raise NotImplementedError("gmsd: only reduction = mean is implemented")
-    return _Gmsd.apply(x, y, t, alpha)
+    """gmsd.jl:13-27.  ``reduction`` (gmsd.jl:13, default ``Flux.mean``) is applied to the B per-image scores; the kernel
+    returns their mean, ``torch.sum`` is that times B (the two reductions ``julia/ADMMTVLosses.jl`` takes as well)."""
+    if reduction is None or reduction is torch.mean:
+        return _Gmsd.apply(x, y, t, alpha)
+    if reduction is torch.sum:
+        return _Gmsd.apply(x, y, t, alpha) * float(x.shape[0])
+    raise NotImplementedError("gmsd: reduction must be torch.mean (default) or torch.sum")
 
 
 gmsd_loss = gmsd   # gmsd.jl:30

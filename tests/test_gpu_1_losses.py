@@ -38,6 +38,9 @@ def test_gmsd_params_and_cotangent():
     vo, go = _oracle(lambda a, b: LO.gmsd(a, b, 0.01, 0.5), x, y)
     assert abs(v - vo) <= 1e-5 * abs(vo)
     assert _rel(g, -2.5 * go) <= 2e-5
+    # reduction = sum over the per-image scores (gmsd.jl:13 takes any reduction; mean and sum are fused)
+    v2, g2 = _gpu(lambda a, b: A.gmsd(a, b, 0.01, 0.5, torch.sum), x, y)
+    assert abs(v2 - 2 * vo) <= 1e-5 * abs(2 * vo) and _rel(g2, 2 * go) <= 2e-5
 
 
 @pytest.mark.parametrize("M,N,C,B", [(24, 20, 3, 2), (45, 70, 1, 2), (256, 256, 3, 2), (100, 333, 3, 1)])
