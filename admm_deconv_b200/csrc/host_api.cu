@@ -31,7 +31,7 @@ struct admmtv_host_session {
   bool own_arena, own_compute;
   cudaStream_t copy_in, compute, copy_out;
   Slot slot[2];
-  float *h, *lambda, *rho, *bias;   // device parameters
+  float *h[2], *lambda[2], *rho[2], *bias[2];   // device parameters, one set per slot (uploaded ahead of the slot's images)
   float *ybar, *packed;             // training
   double* loss_acc;                 // device
   double* loss_host[2];             // pinned
@@ -42,7 +42,7 @@ struct admmtv_host_session {
 namespace {
 
 struct Layout {
-  size_t y[2], t[2], x[2], h, lam, rho, bias, ybar, packed, loss, ws_fwd, ws_bwd, ckpt, total;
+  size_t y[2], t[2], x[2], h[2], lam[2], rho[2], bias[2], ybar, packed, loss, ws_fwd, ws_bwd, ckpt, total;
 };
 
 inline int param_entries(const admmtv_desc* d) { return (d->flags & ADMMTV_FLAG_PER_ITER_PARAMS) ? d->iters : 1; }
@@ -66,10 +66,12 @@ int plan(const admmtv_desc* d, int training, Layout& L, size_t& in_img, size_t& 
     L.t[s] = take(training ? out_img * 4 : 0);
     L.x[s] = take(out_img * 4);
   }
-  L.h = take((size_t)(nh > 0 ? nh : 1) * G * 4);
-  L.lam = take((size_t)G * PS * 4);
-  L.rho = take((size_t)G * PS * 4);
-  L.bias = take((size_t)G * 4);
+  for (int s = 0; s < 2; ++s) {
+    L.h[s] = take((size_t)(nh > 0 ? nh : 1) * G * 4);
+    L.lam[s] = take((size_t)G * PS * 4);
+    L.rho[s] = take((size_t)G * PS * 4);
+    L.bias[s] = take((size_t)G * 4);
+  }
   L.ybar = take(training ? in_img * 4 : 0);
   L.packed = take((size_t)ngrad * 4);
   L.loss = take(16);
@@ -98,22 +100,24 @@ struct DevGuard {
     if (e__ != cudaSuccess) return (int)e__;  \
   } while (0)
 
-// parameters host -> device on the compute stream (tiny), before the kernels that read them
-int upload_params(admmtv_host_session* s, const float* h, const float* lambda, const float* rho, const float* bias) {
-  if (s->nh > 0) HCHECK(cudaMemcpyAsync(s->h, h, (size_t)s->nh * s->G * 4, cudaMemcpyHostToDevice, s->compute));
-  HCHECK(cudaMemcpyAsync(s->lambda, lambda, (size_t)s->G * s->PS * 4, cudaMemcpyHostToDevice, s->compute));
-  HCHECK(cudaMemcpyAsync(s->rho, rho, (size_t)s->G * s->PS * 4, cudaMemcpyHostToDevice, s->compute));
-  if (s->d.has_bias) HCHECK(cudaMemcpyAsync(s->bias, bias, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->compute));
+// Parameters host -> device (tiny).  They travel on the COPY-IN stream in front of the slot's images and into the slot's own
+// parameter set: on the compute stream they would queue on the host-to-device copy engine behind the NEXT step's images,
+// which are issued while this step is still waiting to start.
+int upload_params(admmtv_host_session* s, int slot, const float* h, const float* lambda, const float* rho, const float* bias) {
+  if (s->nh > 0) HCHECK(cudaMemcpyAsync(s->h[slot], h, (size_t)s->nh * s->G * 4, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaMemcpyAsync(s->lambda[slot], lambda, (size_t)s->G * s->PS * 4, cudaMemcpyHostToDevice, s->copy_in));
+  HCHECK(cudaMemcpyAsync(s->rho[slot], rho, (size_t)s->G * s->PS * 4, cudaMemcpyHostToDevice, s->copy_in));
+  if (s->d.has_bias) HCHECK(cudaMemcpyAsync(s->bias[slot], bias, (size_t)s->G * 4, cudaMemcpyHostToDevice, s->copy_in));
   return 0;
 }
 // the persisted clamp (deconv_admm.jl:216-219) back to the caller's arrays.  These few bytes travel on the COMPUTE stream
-// (like the gradients and the loss): the next step's kernels overwrite the same device words, and stream order is the
-// cheapest way to keep them apart; only the image-sized transfers use the copy streams.
-int download_params(admmtv_host_session* s, float* h, float* lambda, float* rho) {
+// (like the gradients and the loss): stream order keeps them behind the kernels that wrote them; only the image-sized
+// transfers use the copy streams.
+int download_params(admmtv_host_session* s, int slot, float* h, float* lambda, float* rho) {
   if (s->d.flags & ADMMTV_FLAG_NO_CLAMP) return 0;
-  if (s->nh > 0) HCHECK(cudaMemcpyAsync(h, s->h, (size_t)s->nh * s->G * 4, cudaMemcpyDeviceToHost, s->compute));
-  HCHECK(cudaMemcpyAsync(lambda, s->lambda, (size_t)s->G * s->PS * 4, cudaMemcpyDeviceToHost, s->compute));
-  HCHECK(cudaMemcpyAsync(rho, s->rho, (size_t)s->G * s->PS * 4, cudaMemcpyDeviceToHost, s->compute));
+  if (s->nh > 0) HCHECK(cudaMemcpyAsync(h, s->h[slot], (size_t)s->nh * s->G * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(lambda, s->lambda[slot], (size_t)s->G * s->PS * 4, cudaMemcpyDeviceToHost, s->compute));
+  HCHECK(cudaMemcpyAsync(rho, s->rho[slot], (size_t)s->G * s->PS * 4, cudaMemcpyDeviceToHost, s->compute));
   return 0;
 }
 
@@ -179,10 +183,12 @@ int admmtv_host_session_create(const admmtv_desc* d, int training, void* device_
     admmtv_host_session_destroy(s);
     return (int)e;
   }
-  s->h = reinterpret_cast<float*>(s->arena + L.h);
-  s->lambda = reinterpret_cast<float*>(s->arena + L.lam);
-  s->rho = reinterpret_cast<float*>(s->arena + L.rho);
-  s->bias = reinterpret_cast<float*>(s->arena + L.bias);
+  for (int i = 0; i < 2; ++i) {
+    s->h[i] = reinterpret_cast<float*>(s->arena + L.h[i]);
+    s->lambda[i] = reinterpret_cast<float*>(s->arena + L.lam[i]);
+    s->rho[i] = reinterpret_cast<float*>(s->arena + L.rho[i]);
+    s->bias[i] = reinterpret_cast<float*>(s->arena + L.bias[i]);
+  }
   s->ybar = reinterpret_cast<float*>(s->arena + L.ybar);
   s->packed = reinterpret_cast<float*>(s->arena + L.packed);
   s->loss_acc = reinterpret_cast<double*>(s->arena + L.loss);
@@ -238,16 +244,16 @@ int admmtv_host_forward_enqueue(admmtv_host_session* s, int slot, const float* y
   DevGuard guard(s->d.device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
   Slot& sl = s->slot[slot];
-  // the slot's previous use was waited for by the caller, so its device buffers are free
+  // the slot's previous use was waited for by the caller, so its device buffers (images and parameter set) are free
+  int rc = upload_params(s, slot, h, lambda, rho, bias);
+  if (rc) return rc;
   HCHECK(cudaMemcpyAsync(sl.y, y, s->in_img * 4, cudaMemcpyHostToDevice, s->copy_in));
   HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
   HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
-  int rc = upload_params(s, h, lambda, rho, bias);
+  rc = admmtv_forward(&s->d, sl.y, s->nh > 0 ? s->h[slot] : nullptr, s->lambda[slot], s->rho[slot],
+                      s->d.has_bias ? s->bias[slot] : nullptr, sl.x, s->ws_fwd, nullptr, s->compute);
   if (rc) return rc;
-  rc = admmtv_forward(&s->d, sl.y, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho, s->d.has_bias ? s->bias : nullptr, sl.x,
-                      s->ws_fwd, nullptr, s->compute);
-  if (rc) return rc;
-  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  if ((rc = download_params(s, slot, h, lambda, rho))) return rc;
   HCHECK(cudaEventRecord(sl.compute_done, s->compute));
   HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
   HCHECK(cudaMemcpyAsync(x_out, sl.x, s->out_img * 4, cudaMemcpyDeviceToHost, s->copy_out));
@@ -274,16 +280,17 @@ int admmtv_host_forward_enqueue_n0f8(admmtv_host_session* s, int slot, const uin
                              (int64_t)(Bin - 1) * stride_b + 1);
   if (ny > s->out_img * 4) return ADMMTV_ERR_SHAPE;
   uint8_t* sy = reinterpret_cast<uint8_t*>(sl.x);
+  int rc = upload_params(s, slot, h, lambda, rho, bias);
+  if (rc) return rc;
   HCHECK(cudaMemcpyAsync(sy, y, ny, cudaMemcpyHostToDevice, s->copy_in));
   HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
   HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
-  int rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, Bin, s->d.device, sy, stride_c, stride_i, stride_j, stride_b, sl.y, s->compute);
+  if ((rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, Bin, s->d.device, sy, stride_c, stride_i, stride_j, stride_b, sl.y, s->compute)))
+    return rc;
+  rc = admmtv_forward(&s->d, sl.y, s->nh > 0 ? s->h[slot] : nullptr, s->lambda[slot], s->rho[slot],
+                      s->d.has_bias ? s->bias[slot] : nullptr, sl.x, s->ws_fwd, nullptr, s->compute);
   if (rc) return rc;
-  if ((rc = upload_params(s, h, lambda, rho, bias))) return rc;
-  rc = admmtv_forward(&s->d, sl.y, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho, s->d.has_bias ? s->bias : nullptr, sl.x,
-                      s->ws_fwd, nullptr, s->compute);
-  if (rc) return rc;
-  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  if ((rc = download_params(s, slot, h, lambda, rho))) return rc;
   HCHECK(cudaEventRecord(sl.compute_done, s->compute));
   HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
   HCHECK(cudaMemcpyAsync(x_out, sl.x, s->out_img * 4, cudaMemcpyDeviceToHost, s->copy_out));
@@ -304,19 +311,19 @@ int admmtv_host_train_step_enqueue(admmtv_host_session* s, int slot, const float
   DevGuard guard(s->d.device);
   if (!guard.ok) return ADMMTV_ERR_NO_DEVICE;
   Slot& sl = s->slot[slot];
+  int rc = upload_params(s, slot, h, lambda, rho, bias);
+  if (rc) return rc;
   HCHECK(cudaMemcpyAsync(sl.y, y, s->in_img * 4, cudaMemcpyHostToDevice, s->copy_in));
   HCHECK(cudaMemcpyAsync(sl.target, target, s->out_img * 4, cudaMemcpyHostToDevice, s->copy_in));
   HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
   HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
-  int rc = upload_params(s, h, lambda, rho, bias);
-  if (rc) return rc;
-  if ((rc = admmtv_mse_train_step(&s->d, sl.y, sl.target, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho,
-                                  s->d.has_bias ? s->bias : nullptr, sl.x, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
+  if ((rc = admmtv_mse_train_step(&s->d, sl.y, sl.target, s->nh > 0 ? s->h[slot] : nullptr, s->lambda[slot], s->rho[slot],
+                                  s->d.has_bias ? s->bias[slot] : nullptr, sl.x, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
                                   s->ckpt, s->ws_bwd, s->compute, hooks)))
     return rc;
   HCHECK(cudaMemcpyAsync(grads_out, s->packed, (size_t)s->ngrad * 4, cudaMemcpyDeviceToHost, s->compute));
   HCHECK(cudaMemcpyAsync(s->loss_host[slot], s->loss_acc, sizeof(double), cudaMemcpyDeviceToHost, s->compute));
-  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  if ((rc = download_params(s, slot, h, lambda, rho))) return rc;
   HCHECK(cudaEventRecord(sl.compute_done, s->compute));
   HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
   if (ybar_out) {
@@ -355,23 +362,24 @@ int admmtv_host_train_step_enqueue_n0f8(admmtv_host_session* s, int slot, const 
   if (al256(ny) + nt > s->out_img * 4) return ADMMTV_ERR_SHAPE;   // padded strides larger than 4 bytes per sample
   uint8_t* sy = reinterpret_cast<uint8_t*>(sl.x);
   uint8_t* st = sy + al256(ny);
+  int rc = upload_params(s, slot, h, lambda, rho, bias);
+  if (rc) return rc;
   HCHECK(cudaMemcpyAsync(sy, y, ny, cudaMemcpyHostToDevice, s->copy_in));
   HCHECK(cudaMemcpyAsync(st, target, nt, cudaMemcpyHostToDevice, s->copy_in));
   HCHECK(cudaEventRecord(sl.in_ready, s->copy_in));
   HCHECK(cudaStreamWaitEvent(s->compute, sl.in_ready, 0));
-  int rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, Bin, s->d.device, sy, stride_c, stride_i, stride_j, stride_b, sl.y, s->compute);
-  if (rc) return rc;
+  if ((rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, Bin, s->d.device, sy, stride_c, stride_i, stride_j, stride_b, sl.y, s->compute)))
+    return rc;
   if ((rc = admmtv_batch_from_n0f8(s->d.M, s->d.N, s->d.P, s->d.B, s->d.device, st, stride_c, stride_i, stride_j, stride_b, sl.target,
                                    s->compute)))
     return rc;
-  if ((rc = upload_params(s, h, lambda, rho, bias))) return rc;
-  if ((rc = admmtv_mse_train_step(&s->d, sl.y, sl.target, s->nh > 0 ? s->h : nullptr, s->lambda, s->rho,
-                                  s->d.has_bias ? s->bias : nullptr, sl.x, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
+  if ((rc = admmtv_mse_train_step(&s->d, sl.y, sl.target, s->nh > 0 ? s->h[slot] : nullptr, s->lambda[slot], s->rho[slot],
+                                  s->d.has_bias ? s->bias[slot] : nullptr, sl.x, s->ybar, s->packed, s->loss_acc, s->ws_fwd,
                                   s->ckpt, s->ws_bwd, s->compute, hooks)))
     return rc;
   HCHECK(cudaMemcpyAsync(grads_out, s->packed, (size_t)s->ngrad * 4, cudaMemcpyDeviceToHost, s->compute));
   HCHECK(cudaMemcpyAsync(s->loss_host[slot], s->loss_acc, sizeof(double), cudaMemcpyDeviceToHost, s->compute));
-  if ((rc = download_params(s, h, lambda, rho))) return rc;
+  if ((rc = download_params(s, slot, h, lambda, rho))) return rc;
   HCHECK(cudaEventRecord(sl.compute_done, s->compute));
   HCHECK(cudaStreamWaitEvent(s->copy_out, sl.compute_done, 0));
   HCHECK(cudaEventRecord(sl.out_done, s->copy_out));
