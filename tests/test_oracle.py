@@ -180,3 +180,25 @@ def test_per_iteration_parameters_teacher_forced_equals_autograd(iso):
     xs = O.tvd_fft_fast(y, lam[:1], rho[:1], h, iso, K)
     xe = O.tvd_fft_fast(y, lam[:1].repeat(K), rho[:1].repeat(K), h, iso, K)
     assert torch.equal(xs, xe)
+
+
+def test_restated_primitives_agree_with_independent_libraries():
+    """The oracle is unpinned upstream (no Julia here), so its building blocks are checked against implementations it does
+    not share code with: NNlib.conv (a TRUE convolution, kernel flipped) vs scipy.signal.convolve2d('valid'), pad_circular vs
+    numpy.pad('wrap'), NNlib.pad_symmetric vs numpy.pad('symmetric'), rfft over dims (1,2) with dim 1 halved vs numpy.fft."""
+    from scipy.signal import convolve2d
+    from oracle import losses_oracle as LO
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((9, 7, 2, 2)); w = rng.standard_normal((4, 3, 1, 2))          # (H,W,C,B), (kh,kw,1,C): groups = C
+    out = O.nnlib_conv(torch.from_numpy(x), torch.from_numpy(w), groups=2).numpy()
+    for c in range(2):
+        for b in range(2):
+            assert np.allclose(out[:, :, c, b], convolve2d(x[:, :, c, b], w[:, :, 0, c], mode="valid"), atol=1e-12)
+    pads = (2, 1, 0, 3)                                                                    # (d1_lo, d1_hi, d2_lo, d2_hi)
+    npad = ((pads[0], pads[1]), (pads[2], pads[3]), (0, 0), (0, 0))
+    assert np.array_equal(O.pad_circular(torch.from_numpy(x), pads).numpy(), np.pad(x, npad, mode="wrap"))
+    assert np.array_equal(LO.pad_symmetric(torch.from_numpy(x), pads).numpy(), np.pad(x, npad, mode="symmetric"))
+    X = O.rfft12(torch.from_numpy(x)).numpy()
+    ref = np.fft.fft(np.fft.rfft(x, axis=0), axis=1)                                        # halve dim 1, full transform along dim 2
+    assert X.shape == (9 // 2 + 1, 7, 2, 2) and np.allclose(X, ref, atol=1e-12)
+    assert np.allclose(O.irfft12(torch.from_numpy(X), 9).numpy(), x, atol=1e-12)
