@@ -61,3 +61,38 @@ def test_gradients_finite_difference():
         fd = (float(fn(x + eps * d, y)) - float(fn(x - eps * d, y))) / (2 * eps)
         an = float((xr.grad * d).sum())
         assert abs(fd - an) <= 1e-6 * max(1.0, abs(an))
+
+
+def test_losses_agree_with_a_scipy_formulation():
+    """Independent of the oracle's NNlib restatement: SSIM through scipy.signal.convolve2d('valid') with the 11 x 11 Gaussian,
+    GMSD through scipy.ndimage.correlate with wrap-around Sobel/8 stencils (written from the formulas, gmsd.jl:5-27 / ssim.jl:112-123)."""
+    import numpy as np
+    from scipy.ndimage import correlate
+    from scipy.signal import convolve2d
+    rng = np.random.default_rng(11)
+    x = rng.random((24, 20, 2, 2)); y = np.clip(x + 0.1 * rng.standard_normal(x.shape), 0, 1)
+    g = np.array(LO.SSIM_KERNEL); K = np.outer(g, g)
+    tot = []
+    for b in range(2):
+        for c in range(2):
+            f = lambda a: convolve2d(a, K, mode="valid")
+            X, Y = x[:, :, c, b], y[:, :, c, b]
+            mx, my = f(X), f(Y)
+            sx, sy, sxy = f(X * X) - mx * mx, f(Y * Y) - my * my, f(X * Y) - mx * my
+            tot.append(((2 * mx * my + 1e-4) * (2 * sxy + 9e-4) / ((mx * mx + my * my + 1e-4) * (sx + sy + 9e-4))).mean())
+    assert abs(float(LO.ssim(torch.from_numpy(x), torch.from_numpy(y))) - np.mean(tot)) < 1e-12
+    # GMSD: true convolution with SOBEL_X = [1 2 1; 0 0 0; -1 -2 -1]/8 (rows = dim 1) == correlation with the flipped stencil
+    kx = np.array([[1, 2, 1], [0, 0, 0], [-1, -2, -1]], float) / 8
+    scores = []
+    for b in range(2):
+        maps = []
+        for img in (x, y):
+            m = []
+            for c in range(2):
+                a = img[:, :, c, b]
+                gx = correlate(a, kx[::-1, ::-1], mode="wrap"); gy = correlate(a, kx.T[::-1, ::-1], mode="wrap")
+                m.append(np.sqrt(gx * gx + gy * gy + 1e-16))
+            maps.append(np.stack(m, -1))
+        gms = (2 * maps[0] * maps[1] + 0.0026) / (maps[0] ** 2 + maps[1] ** 2 + 0.0026)
+        scores.append(np.sqrt(((gms - gms.mean()) ** 2).mean()))
+    assert abs(float(LO.gmsd(torch.from_numpy(x), torch.from_numpy(y))) - np.mean(scores)) < 1e-12
