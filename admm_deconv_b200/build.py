@@ -63,6 +63,15 @@ def build(emulate: bool = False, force: bool = False, jobs: int | None = None, v
         objdir = os.path.join(CSRC, "_obj_" + tag)
         lib = os.path.join(HERE, f"libadmmtv_{tag}.so")
     os.makedirs(objdir, exist_ok=True)
+    # one builder at a time per object directory: concurrent callers (e.g. the ranks of a multi-process test) wait here and
+    # then find everything up to date instead of compiling and linking the same files at once
+    import fcntl
+    with open(os.path.join(objdir, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build_locked(emulate, force, jobs, verbose, sizes, defines, objdir, lib)
+
+
+def _build_locked(emulate, force, jobs, verbose, sizes, defines, objdir, lib) -> str:
     deps = _deps() + ([os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "cuda_emu.cpp")] if emulate else [])
     jobs = jobs or os.cpu_count() or 4
     logs = {}

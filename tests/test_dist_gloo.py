@@ -123,7 +123,8 @@ def _iso_worker(rank, world, port, out, iso_flag):
 
 
 @pytest.mark.parametrize("iso_flag", [16, 32])    # precomputed / inline per-pixel terms
-def test_two_rank_global_isotropic_equals_single_device(iso_flag):
+def test_two_rank_global_isotropic_equals_single_device(iso_flag, emu):
+    # `emu`: the emulation library is built HERE, once, before the two ranks start (they would otherwise race to build it)
     world = 2
     port = _free_port()
     out = mp.Manager().dict()
