@@ -103,8 +103,7 @@ int Dim2Launch<LN>::run(const Geom& g, int variant, const Dim2Args& a_in, cudaSt
       if (cluster_ok && g.M % CC::TR == 0) switch (variant) {
         case D2_C: return launch_k(k_dim2c<LN, 0>, cgrid, CC::NT, CC::SMEM, st, a);
         case D2_KCONJ: return launch_k(k_dim2c<LN, 1>, cgrid, CC::NT, CC::SMEM, st, a);
-        case D2_K: return launch_k(k_dim2c<LN, 2>, cgrid, CC::NT, CC::SMEM, st, a);
-        default: break;
+        default: break;   // D2_K (backward without a PSF gradient) and every saving / accumulating variant: k_dim2
       }
     }
   }

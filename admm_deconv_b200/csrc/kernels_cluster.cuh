@@ -126,7 +126,7 @@ ADMMTV_DI void d2c_inv_rest(float2* tile, const float2* __restrict__ twN, int ti
   }
 }
 
-// MUL as k_dim2: 0 = real table ctab, 1 = complex table ktab, 2 = its conjugate
+// MUL as k_dim2: 0 = real table ctab, 1 = complex table ktab, 2 = its conjugate (the dispatch ships 0 and 1, the variants the GPU suite exercises at N = 4096)
 template <int LN, int MUL>
 __global__ void __cluster_dims__(Dim2cCfg<LN>::CS, 1, 1) __launch_bounds__(Dim2cCfg<LN>::NT, ADMMTV_D2C_MINB) k_dim2c(Dim2Args A) {
   namespace cg = cooperative_groups;
